@@ -1,0 +1,409 @@
+// lap_device.cuh - exact linear assignment for one (rows x cols) problem, solved by one CTA.
+//
+// Replaces utils::linear_assignment + LAPSolver (reference src/utils/matching.cpp:14-60,
+// include/motcpp/association/lap_solver.hpp:36-332).  The reference pads the cost matrix to
+// (n+m)^2 with thresh/2 and runs dense Jonker-Volgenant in fp64; that is equivalent to choosing
+// the partial matching that minimises sum(c_ij - thresh), in which a pair with c_ij > thresh can
+// never appear.  So instead of a dense O((n+m)^3) solve this kernel
+//   1. extracts the candidate pairs c_ij <= thresh (one thread per row, columns staged in smem),
+//   2. labels the connected components of the candidate graph (min-label propagation, smem atomics),
+//   3. gives every component to a warp, which runs a shortest-augmenting-path (Hungarian) solve in
+//      fp64 with one LANE PER COLUMN: duals, distances and predecessors live in registers and the
+//      per-step minimum is a warp-shuffle reduction.  A component with more than 32 columns+rows
+//      falls back to the same algorithm striding over a global-memory scratch area.
+// The result equals the reference's whenever the optimum is unique (always, for continuous costs);
+// ties are broken by lowest column / lowest row, not by JV's scan order (DESIGN.md "Ties").
+#pragma once
+#include "block_utils.cuh"
+
+namespace mot {
+
+constexpr int kLapNone = 0x7fffffff;
+
+struct LapWorkspace {
+    // shared memory
+    int* row_label;            // [n_max]
+    int* col_label;            // [m_max]
+    int* scratch_a;            // [max(e_cap, n_max + 1)] edges, later packed per-label offsets
+    int* scratch_b;            // [n_max] packed per-label fill cursors
+    unsigned short* comp_rows; // [n_max] row ids grouped by component
+    unsigned short* comp_cols; // [m_max]
+    unsigned short* comp_list; // [n_max] component roots
+    short* row2col;            // [n_max] result
+    short* col2row;            // [m_max] result
+    int* ctl;                  // [8] counters: 0 edges, 1 overflow, 2 changed, 3 n_comp, 4 next_comp
+    BlockScratch* bs;
+    int e_cap;
+    // global-memory scratch for components too large for one warp's registers
+    double* g_u;               // [n_max]
+    double* g_v;               // [m_max + n_max]
+    double* g_minv;            // [m_max + n_max]
+    int* g_way;                // [m_max + n_max]
+    int* g_prow;               // [m_max + n_max]
+    unsigned char* g_flags;    // [m_max + 2 * n_max] used[] then in_tree[]
+};
+
+__device__ __forceinline__ double lap_inf() { return 1.0e300; }
+
+// Ascending sort of a short segment held in shared memory, by one warp.
+__device__ __forceinline__ void warp_sort_u16(unsigned short* seg, int n) {
+    const int lane = lane_id();
+    if (n <= 1) return;
+    if (n <= 32) {
+        const int v = lane < n ? (int)seg[lane] : 0x7fffffff;
+        int rank = 0;
+        for (int k = 0; k < n; ++k) {
+            const int o = __shfl_sync(kFullMask, v, k);
+            rank += (o < v) ? 1 : 0;               // ids are distinct
+        }
+        __syncwarp();
+        if (lane < n) seg[rank] = (unsigned short)v;
+        __syncwarp();
+        return;
+    }
+    // odd-even transposition sort for the rare big component
+    for (int pass = 0; pass < n; ++pass) {
+        for (int k = (pass & 1) + 2 * lane; k + 1 < n; k += 64) {
+            const unsigned short a = seg[k], b = seg[k + 1];
+            if (a > b) { seg[k] = b; seg[k + 1] = a; }
+        }
+        __syncwarp();
+    }
+}
+
+// (min value, lowest lane on ties) across the warp
+__device__ __forceinline__ void warp_argmin(double& key, int& arg) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ok = __shfl_xor_sync(kFullMask, key, o);
+        const int oa = __shfl_xor_sync(kFullMask, arg, o);
+        if (ok < key || (ok == key && oa < arg)) { key = ok; arg = oa; }
+    }
+}
+
+// Component with r rows and c columns, r + c <= 32.  Lane l < c owns real column cols[l]; lane
+// c + k owns the private "stay unmatched" column of row k (cost 0, reachable only from row k).
+template <class Cost>
+__device__ __forceinline__ void warp_hungarian_small(const unsigned short* rows, int r, const unsigned short* cols,
+                                                     int c, float thresh, const Cost& cost, short* row2col,
+                                                     short* col2row) {
+    const int lane = lane_id();
+    const bool is_real = lane < c;
+    const bool is_col = lane < c + r;
+    const int dummy_of = lane - c;
+    const int col_id = is_real ? (int)cols[lane] : -1;
+    const int row_id = lane < r ? (int)rows[lane] : -1;
+    const double INF = lap_inf();
+    const double Ld = (double)thresh;
+    double v = 0.0, u = 0.0;
+    int prow = -1;
+    for (int s = 0; s < r; ++s) {
+        double minv = INF;
+        int way = -1;
+        bool used = false;
+        bool in_tree = (lane == s);
+        int i0 = s, j0 = -1;
+        for (;;) {
+            const int i0_id = __shfl_sync(kFullMask, row_id, i0);
+            const double u0 = __shfl_sync(kFullMask, u, i0);
+            double cur = INF;
+            if (is_real) {
+                const float cf = cost.pair(i0_id, col_id);
+                if (cf <= thresh) cur = ((double)cf - Ld) - u0 - v;
+            } else if (is_col && dummy_of == i0) {
+                cur = 0.0 - u0 - v;
+            }
+            if (is_col && !used && cur < minv) { minv = cur; way = j0; }
+            double key = (is_col && !used) ? minv : INF;
+            int arg = lane;
+            warp_argmin(key, arg);
+            const double delta = key;
+            if (is_col) { if (used) v -= delta; else minv -= delta; }
+            if (in_tree) u += delta;
+            j0 = arg;
+            if (lane == j0) used = true;
+            i0 = __shfl_sync(kFullMask, prow, j0);
+            if (i0 < 0) break;
+            if (lane == i0) in_tree = true;
+        }
+        int j = j0;
+        while (j >= 0) {
+            const int jp = __shfl_sync(kFullMask, way, j);
+            const int from = __shfl_sync(kFullMask, prow, jp < 0 ? 0 : jp);
+            if (lane == j) prow = (jp < 0) ? s : from;
+            j = jp;
+        }
+    }
+    const int matched_row = (is_real && prow >= 0) ? prow : 0;
+    const int matched_row_id = __shfl_sync(kFullMask, row_id, matched_row);
+    if (is_real && prow >= 0) {
+        col2row[col_id] = (short)matched_row_id;
+        row2col[matched_row_id] = (short)col_id;
+    }
+}
+
+// Same algorithm for a component of any size; per-column state lives in global scratch at
+// positions [pc, pc + c) for real columns and [m_max + pr, m_max + pr + r) for the private ones.
+template <class Cost>
+__device__ __noinline__ void warp_hungarian_big(const LapWorkspace& ws, int m_max, int n_max,
+                                                const unsigned short* rows, int r, int pr,
+                                                const unsigned short* cols, int c, int pc, float thresh,
+                                                const Cost& cost, short* row2col, short* col2row) {
+    const int lane = lane_id();
+    const double INF = lap_inf();
+    const double Ld = (double)thresh;
+    const int total = c + r;
+    unsigned char* used = ws.g_flags;
+    unsigned char* in_tree = ws.g_flags + m_max + n_max;
+    // position of column slot k (0 <= k < total) in the global arrays
+    auto cpos = [&](int k) { return k < c ? pc + k : m_max + pr + (k - c); };
+    for (int k = lane; k < total; k += 32) { ws.g_v[cpos(k)] = 0.0; ws.g_prow[cpos(k)] = -1; }
+    for (int k = lane; k < r; k += 32) ws.g_u[pr + k] = 0.0;
+    __syncwarp();
+    for (int s = 0; s < r; ++s) {
+        for (int k = lane; k < total; k += 32) { ws.g_minv[cpos(k)] = INF; ws.g_way[cpos(k)] = -1; used[cpos(k)] = 0; }
+        for (int k = lane; k < r; k += 32) in_tree[pr + k] = (k == s) ? 1 : 0;
+        __syncwarp();
+        int i0 = s, j0 = -1;
+        for (;;) {
+            const int i0_id = (int)rows[i0];
+            const double u0 = ws.g_u[pr + i0];
+            double key = INF;
+            int arg = 0x7fffffff;
+            for (int k = lane; k < total; k += 32) {
+                const int p = cpos(k);
+                if (used[p]) continue;
+                double cur = INF;
+                if (k < c) {
+                    const float cf = cost.pair(i0_id, (int)cols[k]);
+                    if (cf <= thresh) cur = ((double)cf - Ld) - u0 - ws.g_v[p];
+                } else if (k - c == i0) {
+                    cur = 0.0 - u0 - ws.g_v[p];
+                }
+                double mv = ws.g_minv[p];
+                if (cur < mv) { mv = cur; ws.g_minv[p] = cur; ws.g_way[p] = j0; }
+                if (mv < key) { key = mv; arg = k; }       // ascending k per lane => lowest k on ties
+            }
+            warp_argmin(key, arg);
+            const double delta = key;
+            for (int k = lane; k < total; k += 32) {
+                const int p = cpos(k);
+                if (used[p]) ws.g_v[p] -= delta; else ws.g_minv[p] -= delta;
+            }
+            for (int k = lane; k < r; k += 32)
+                if (in_tree[pr + k]) ws.g_u[pr + k] += delta;
+            __syncwarp();
+            j0 = arg;
+            if (lane == 0) used[cpos(j0)] = 1;
+            i0 = ws.g_prow[cpos(j0)];
+            __syncwarp();
+            if (i0 < 0) break;
+            if (lane == 0) in_tree[pr + i0] = 1;
+            __syncwarp();
+        }
+        if (lane == 0) {
+            int j = j0;
+            while (j >= 0) {
+                const int jp = ws.g_way[cpos(j)];
+                ws.g_prow[cpos(j)] = (jp < 0) ? s : ws.g_prow[cpos(jp)];
+                j = jp;
+            }
+        }
+        __syncwarp();
+    }
+    for (int k = lane; k < c; k += 32) {
+        const int pw = ws.g_prow[pc + k];
+        if (pw >= 0) {
+            const int rid = (int)rows[pw], cid = (int)cols[k];
+            col2row[cid] = (short)rid;
+            row2col[rid] = (short)cid;
+        }
+    }
+    __syncwarp();
+}
+
+// Cost functor contract:
+//   struct Cost {
+//     struct Row { ... };                                   // whatever a row needs in registers
+//     __device__ Row  row(int i) const;                     // load row i once
+//     __device__ bool reject(const Row&, int j) const;      // cheap test: true => cost(i,j) > thresh for sure
+//     __device__ float cost(const Row&, int j) const;       // exact fp32 cost
+//     __device__ float pair(int i, int j) const;            // == cost(row(i), j)
+//   };
+// On return (all threads) ws.row2col[0..n) / ws.col2row[0..m) hold the assignment (-1 = unmatched).
+template <class Cost>
+__device__ void block_lap(const LapWorkspace& ws, int n, int m, int n_max, int m_max, float thresh, const Cost& cost) {
+    const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) { ws.row2col[i] = -1; ws.row_label[i] = kLapNone; }
+    for (int j = tid; j < m; j += nt) { ws.col2row[j] = -1; ws.col_label[j] = kLapNone; }
+    if (tid < 8) ws.ctl[tid] = 0;
+    __syncthreads();
+    if (n == 0 || m == 0) return;
+
+    // ---- 1. candidate pairs
+    for (int i = tid; i < n; i += nt) {
+        const typename Cost::Row rw = cost.row(i);
+        for (int j = 0; j < m; ++j) {
+            if (cost.reject(rw, j)) continue;
+            const float cf = cost.cost(rw, j);
+            if (cf <= thresh) {
+                const int e = atomicAdd(&ws.ctl[0], 1);
+                if (e < ws.e_cap) ws.scratch_a[e] = (i << 16) | j;
+                else ws.ctl[1] = 1;
+            }
+        }
+    }
+    __syncthreads();
+    const int n_edges = min(ws.ctl[0], ws.e_cap);
+    const bool overflow = ws.ctl[1] != 0;
+
+    // ---- 2. connected components by min-label propagation
+    if (overflow) {
+        // too many candidates for the edge buffer: treat everything as one component (still exact)
+        for (int i = tid; i < n; i += nt) ws.row_label[i] = 0;
+        for (int j = tid; j < m; j += nt) ws.col_label[j] = 0;
+        __syncthreads();
+    } else {
+        for (int e = tid; e < n_edges; e += nt) { const int i = ws.scratch_a[e] >> 16; ws.row_label[i] = i; }
+        __syncthreads();
+        for (;;) {
+            for (int e = tid; e < n_edges; e += nt) {
+                const int pk = ws.scratch_a[e];
+                atomicMin(&ws.col_label[pk & 0xffff], ws.row_label[pk >> 16]);
+            }
+            __syncthreads();
+            if (tid == 0) ws.ctl[2] = 0;
+            __syncthreads();
+            for (int e = tid; e < n_edges; e += nt) {
+                const int pk = ws.scratch_a[e];
+                const int cl = ws.col_label[pk & 0xffff];
+                const int old = atomicMin(&ws.row_label[pk >> 16], cl);
+                if (cl < old) ws.ctl[2] = 1;
+            }
+            __syncthreads();
+            if (ws.ctl[2] == 0) break;
+        }
+    }
+
+    // ---- 3. group rows / columns by component: counts (packed rows | cols << 16) -> offsets -> fill
+    int* off = ws.scratch_a;       // [n + 1] packed exclusive offsets per label
+    int* cur = ws.scratch_b;       // [n] packed fill cursors per label
+    for (int i = tid; i <= n; i += nt) off[i] = 0;
+    for (int i = tid; i < n; i += nt) cur[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) { const int l = ws.row_label[i]; if (l != kLapNone) atomicAdd(&off[l], 1); }
+    for (int j = tid; j < m; j += nt) { const int l = ws.col_label[j]; if (l != kLapNone) atomicAdd(&off[l], 1 << 16); }
+    __syncthreads();
+    for (int i = tid; i < n; i += nt)
+        if ((off[i] & 0xffff) != 0) { const int k = atomicAdd(&ws.ctl[3], 1); ws.comp_list[k] = (unsigned short)i; }
+    block_exclusive_scan(off, n, ws.bs, true);
+    for (int i = tid; i < n; i += nt) {
+        const int l = ws.row_label[i];
+        if (l != kLapNone) { const int k = atomicAdd(&cur[l], 1) & 0xffff; ws.comp_rows[(off[l] & 0xffff) + k] = (unsigned short)i; }
+    }
+    for (int j = tid; j < m; j += nt) {
+        const int l = ws.col_label[j];
+        if (l != kLapNone) { const int k = atomicAdd(&cur[l], 1 << 16) >> 16; ws.comp_cols[(off[l] >> 16) + k] = (unsigned short)j; }
+    }
+    __syncthreads();
+
+    // ---- 4. one warp per component
+    const int n_comp = ws.ctl[3];
+    for (;;) {
+        int k = 0;
+        if (lane == 0) k = atomicAdd(&ws.ctl[4], 1);
+        k = __shfl_sync(kFullMask, k, 0);
+        if (k >= n_comp) break;
+        const int root = (int)ws.comp_list[k];
+        const int o0 = off[root], o1 = off[root + 1];
+        const int pr = o0 & 0xffff, r = (o1 & 0xffff) - pr;
+        const int pc = o0 >> 16, c = (o1 >> 16) - pc;
+        unsigned short* rows = ws.comp_rows + pr;
+        unsigned short* cols = ws.comp_cols + pc;
+        warp_sort_u16(rows, r);
+        warp_sort_u16(cols, c);
+        if (r + c <= 32) warp_hungarian_small(rows, r, cols, c, thresh, cost, ws.row2col, ws.col2row);
+        else warp_hungarian_big(ws, m_max, n_max, rows, r, pr, cols, c, pc, thresh, cost, ws.row2col, ws.col2row);
+    }
+    (void)warp; (void)nwarps;
+    __syncthreads();
+}
+
+}  // namespace mot
+
+namespace mot {
+
+// ---- shared-memory carve-up for LapWorkspace (sizes in bytes, 16-byte aligned pieces)
+MOT_HD inline size_t lap_align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+MOT_HD inline size_t lap_smem_bytes(int n_max, int m_max, int e_cap) {
+    const int a = e_cap > n_max + 1 ? e_cap : n_max + 1;
+    size_t b = 0;
+    b += lap_align16(sizeof(int) * (size_t)n_max);              // row_label
+    b += lap_align16(sizeof(int) * (size_t)m_max);              // col_label
+    b += lap_align16(sizeof(int) * (size_t)a);                  // scratch_a
+    b += lap_align16(sizeof(int) * (size_t)n_max);              // scratch_b
+    b += lap_align16(sizeof(unsigned short) * (size_t)n_max);   // comp_rows
+    b += lap_align16(sizeof(unsigned short) * (size_t)m_max);   // comp_cols
+    b += lap_align16(sizeof(unsigned short) * (size_t)n_max);   // comp_list
+    b += lap_align16(sizeof(short) * (size_t)n_max);            // row2col
+    b += lap_align16(sizeof(short) * (size_t)m_max);            // col2row
+    b += lap_align16(sizeof(int) * 8);                          // ctl
+    b += lap_align16(sizeof(BlockScratch));
+    return b;
+}
+
+__device__ __forceinline__ unsigned char* lap_carve(unsigned char* p, int n_max, int m_max, int e_cap, LapWorkspace& ws) {
+    const int a = e_cap > n_max + 1 ? e_cap : n_max + 1;
+    ws.row_label = (int*)p;            p += lap_align16(sizeof(int) * (size_t)n_max);
+    ws.col_label = (int*)p;            p += lap_align16(sizeof(int) * (size_t)m_max);
+    ws.scratch_a = (int*)p;            p += lap_align16(sizeof(int) * (size_t)a);
+    ws.scratch_b = (int*)p;            p += lap_align16(sizeof(int) * (size_t)n_max);
+    ws.comp_rows = (unsigned short*)p; p += lap_align16(sizeof(unsigned short) * (size_t)n_max);
+    ws.comp_cols = (unsigned short*)p; p += lap_align16(sizeof(unsigned short) * (size_t)m_max);
+    ws.comp_list = (unsigned short*)p; p += lap_align16(sizeof(unsigned short) * (size_t)n_max);
+    ws.row2col = (short*)p;            p += lap_align16(sizeof(short) * (size_t)n_max);
+    ws.col2row = (short*)p;            p += lap_align16(sizeof(short) * (size_t)m_max);
+    ws.ctl = (int*)p;                  p += lap_align16(sizeof(int) * 8);
+    ws.bs = (BlockScratch*)p;          p += lap_align16(sizeof(BlockScratch));
+    ws.e_cap = e_cap;
+    return p;
+}
+
+// global scratch (bytes) for the large-component fallback of one problem
+MOT_HD inline size_t lap_gscratch_bytes(int n_max, int m_max) {
+    const size_t cols = (size_t)n_max + (size_t)m_max;
+    size_t b = 0;
+    b += lap_align16(sizeof(double) * (size_t)n_max);   // u
+    b += lap_align16(sizeof(double) * cols);            // v
+    b += lap_align16(sizeof(double) * cols);            // minv
+    b += lap_align16(sizeof(int) * cols);               // way
+    b += lap_align16(sizeof(int) * cols);               // prow
+    b += lap_align16(cols + (size_t)n_max);             // flags
+    return b;
+}
+
+__device__ __forceinline__ void lap_carve_gscratch(unsigned char* g, int n_max, int m_max, LapWorkspace& ws) {
+    const size_t cols = (size_t)n_max + (size_t)m_max;
+    ws.g_u = (double*)g;        g += lap_align16(sizeof(double) * (size_t)n_max);
+    ws.g_v = (double*)g;        g += lap_align16(sizeof(double) * cols);
+    ws.g_minv = (double*)g;     g += lap_align16(sizeof(double) * cols);
+    ws.g_way = (int*)g;         g += lap_align16(sizeof(int) * cols);
+    ws.g_prow = (int*)g;        g += lap_align16(sizeof(int) * cols);
+    ws.g_flags = (unsigned char*)g;
+}
+
+// Dense-matrix cost: the standalone mot_lap() entry point (row-major fp32, leading dimension ld).
+struct MatrixCost {
+    const float* c;
+    int ld;
+    struct Row { const float* p; };
+    __device__ __forceinline__ Row row(int i) const { return Row{c + (size_t)i * ld}; }
+    __device__ __forceinline__ bool reject(const Row&, int) const { return false; }
+    __device__ __forceinline__ float cost(const Row& r, int j) const { return r.p[j]; }
+    __device__ __forceinline__ float pair(int i, int j) const { return c[(size_t)i * ld + j]; }
+};
+
+}  // namespace mot

@@ -1,0 +1,104 @@
+/*
+ * oracle.h - CPU restatement of motcpp's association hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is linked into, imported by or
+ * called from the product library (motcpp_b200/).  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load liboracle.so, and there
+ * only as the checker / the CPU baseline.
+ *
+ * Every function cites the reference file:line (relative to /root/reference) it follows.
+ * Arithmetic is plain fp32 (fp64 inside the assignment solver), evaluated in the
+ * operation order documented in DESIGN.md "Arithmetic contract", compiled with
+ * -ffp-contract=off so no FMA is ever formed.
+ *
+ * Pinning status (see oracle/README.md):
+ *   - LAP: pinned against the reference's REAL lap_solver.hpp (oracle/_ref/libref_lap.so)
+ *     and against the KATs of reference tests/test_matching.cpp.
+ *   - IoU: pinned against tests/test_iou.cpp KATs.  XYSR KF: tests/test_kalman_filter.cpp KATs.
+ *   - XYAH / XYWH KF covariances, fuse_score, cosine, gating, tracker state machines:
+ *     the reference holds no golden values => "parity unpinned" beyond hand-derived KATs.
+ *
+ * All matrices are ROW-MAJOR float unless stated otherwise.
+ */
+#ifndef MOT_ORACLE_H
+#define MOT_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------- box conversions (include/motcpp/utils/ops.hpp:15-211) ---------- */
+void orc_xyxy2xywh(const float* in, float* out);
+void orc_xywh2xyxy(const float* in, float* out);
+void orc_xywh2tlwh(const float* in, float* out);
+void orc_tlwh2xyah(const float* in, float* out);
+void orc_xyah2xywh(const float* in, float* out);
+void orc_xyxy2xysr(const float* in, float* out);
+void orc_xysr2xyxy(const float* in, float* out);
+
+/* ---------------- Kalman XYAH (src/motion/kalman_filter.cpp, kalman_filters/xyah_kf.cpp) */
+void orc_kf_xyah_initiate(const float* z4, float* mean8, float* cov64);
+void orc_kf_xyah_predict(float* mean8, float* cov64);
+void orc_kf_xyah_project(const float* mean8, const float* cov64, float conf, float* pm4, float* pc16);
+/* returns 0 on the Cholesky path, 1 when the reference would take its pseudo-inverse fallback
+ * (state left untouched by the oracle in that case). */
+int orc_kf_xyah_update(float* mean8, float* cov64, const float* z4, float conf);
+/* metric: 0 = "maha" (reference computes d^T S^-2 d, kalman_filter.cpp:166-172), 1 = "gaussian" */
+void orc_kf_xyah_gating(const float* mean8, const float* cov64, const float* meas, int m,
+                        int only_position, int metric, float* out);
+
+/* ---------------- Kalman XYSR (src/motion/kalman_filters/xysr_kf.cpp:10-112) ----------- */
+/* q_xy_scale / q_s_scale: OC-SORT multiplies Q(4,4),Q(5,5) and Q(6,6) (ocsort.cpp:77-79); SORT passes 1,1 */
+void orc_kf_xysr_init(const float* z4, float* x7, float* P49);
+void orc_kf_xysr_predict(float* x7, float* P49, float q_xy_scale, float q_s_scale);
+int orc_kf_xysr_update(float* x7, float* P49, const float* z4);
+
+/* ---------------- Kalman XYWH (include/motcpp/motion/kalman_filters/xywh_kf.hpp:17-185) -- */
+void orc_kf_xywh_initiate(const float* z4, float* mean8, float* cov64);
+void orc_kf_xywh_predict(float* mean8, float* cov64);
+void orc_kf_xywh_update(float* mean8, float* cov64, const float* z4);
+void orc_kf_xywh_gating(const float* mean8, const float* cov64, const float* meas, int m,
+                        int only_position, float* out);
+
+/* ---------------- cost build (include/motcpp/utils/iou.hpp:63-100, src/utils/matching.cpp) */
+void orc_iou_batch(const float* a, int n, const float* b, int m, float* out);      /* (n,m) */
+void orc_iou_distance(const float* a, int n, const float* b, int m, float* out);   /* 1 - iou */
+void orc_fuse_score(float* cost, int n, int m, const float* det_conf);             /* in place */
+/* metric 0 = cosine, 1 = euclidean (matching.cpp:67-107) */
+void orc_embedding_distance(const float* t, int n, const float* d, int m, int dim, int metric, float* out);
+
+/* ---------------- linear assignment (matching.cpp:14-60, lap_solver.hpp:36-332) --------- */
+/* row2col[n], col2row[m] = -1 when unmatched; returns number of matches */
+int orc_linear_assignment(const float* cost, int n, int m, int ld, float thresh,
+                          int* row2col, int* col2row);
+
+/* ---------------- trackers (state machines) --------------------------------------------- */
+typedef struct OrcByteTrack OrcByteTrack;
+/* arguments follow ByteTrack's ctor (include/motcpp/trackers/bytetrack.hpp:97-110); the
+ * unused BaseTracker knobs (per_class, nr_classes, asso_func, is_obb) are fixed at defaults. */
+OrcByteTrack* orc_bytetrack_create(float det_thresh, int max_age, int max_obs, int min_hits,
+                                   float iou_threshold, float min_conf, float track_thresh,
+                                   float match_thresh, int track_buffer, int frame_rate);
+void orc_bytetrack_destroy(OrcByteTrack*);
+void orc_bytetrack_reset(OrcByteTrack*);
+/* dets: (n,6) row-major [x1,y1,x2,y2,conf,cls]; out: capacity out_cap rows of 8 floats
+ * [x1,y1,x2,y2,id,conf,cls,det_ind]; returns number of rows (or -needed if out_cap too small) */
+int orc_bytetrack_update(OrcByteTrack*, const float* dets, int n, float* out, int out_cap);
+/* introspection for parity tests */
+int orc_bytetrack_counts(const OrcByteTrack*, int* n_active, int* n_lost);
+/* dump list (0 = active, 1 = lost) as rows of [id, state, is_activated, frame_id, start_frame,
+ * tracklet_len, mean0..7, cov0..63] = 78 floats; returns rows written */
+int orc_bytetrack_dump(const OrcByteTrack*, int which, float* out, int cap_rows);
+/* sizes of the three LAP sub-problems of the last update(): [n1,m1,n2,m2,n3,m3,n_dup_a,n_dup_b] */
+void orc_bytetrack_last_sizes(const OrcByteTrack*, int* sizes8);
+
+typedef struct OrcSort OrcSort;
+OrcSort* orc_sort_create(float det_thresh, int max_age, int max_obs, int min_hits, float iou_threshold);
+void orc_sort_destroy(OrcSort*);
+void orc_sort_reset(OrcSort*);
+int orc_sort_update(OrcSort*, const float* dets, int n, float* out, int out_cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

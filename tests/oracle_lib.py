@@ -1,0 +1,284 @@
+"""ctypes bindings for oracle/liboracle.so and oracle/_ref/libref_lap.so.
+
+TEST INFRASTRUCTURE: imported only by tests/, bench.py's cpu_baseline / --impl reference legs
+and __graft_entry__.smoke().  The product package (motcpp_b200/) never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+_LIB = None
+_REF = None
+
+f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+def build_oracle(force: bool = False) -> None:
+    so = os.path.join(ORACLE_DIR, "liboracle.so")
+    if force or not os.path.exists(so):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"], stdout=subprocess.DEVNULL)
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        build_oracle()
+        L = C.CDLL(os.path.join(ORACLE_DIR, "liboracle.so"))
+        L.orc_linear_assignment.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_float, i32p, i32p]
+        L.orc_linear_assignment.restype = C.c_int
+        for name in ("orc_iou_batch", "orc_iou_distance"):
+            getattr(L, name).argtypes = [f32p, C.c_int, f32p, C.c_int, f32p]
+            getattr(L, name).restype = None
+        L.orc_fuse_score.argtypes = [f32p, C.c_int, C.c_int, f32p]
+        L.orc_embedding_distance.argtypes = [f32p, C.c_int, f32p, C.c_int, C.c_int, C.c_int, f32p]
+        for name in ("orc_xyxy2xywh", "orc_xywh2xyxy", "orc_xywh2tlwh", "orc_tlwh2xyah", "orc_xyah2xywh",
+                     "orc_xyxy2xysr", "orc_xysr2xyxy"):
+            getattr(L, name).argtypes = [f32p, f32p]
+        L.orc_kf_xyah_initiate.argtypes = [f32p, f32p, f32p]
+        L.orc_kf_xyah_predict.argtypes = [f32p, f32p]
+        L.orc_kf_xyah_project.argtypes = [f32p, f32p, C.c_float, f32p, f32p]
+        L.orc_kf_xyah_update.argtypes = [f32p, f32p, f32p, C.c_float]
+        L.orc_kf_xyah_update.restype = C.c_int
+        L.orc_kf_xyah_gating.argtypes = [f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, f32p]
+        L.orc_kf_xysr_init.argtypes = [f32p, f32p, f32p]
+        L.orc_kf_xysr_predict.argtypes = [f32p, f32p, C.c_float, C.c_float]
+        L.orc_kf_xysr_update.argtypes = [f32p, f32p, f32p]
+        L.orc_kf_xysr_update.restype = C.c_int
+        L.orc_kf_xywh_initiate.argtypes = [f32p, f32p, f32p]
+        L.orc_kf_xywh_predict.argtypes = [f32p, f32p]
+        L.orc_kf_xywh_update.argtypes = [f32p, f32p, f32p]
+        L.orc_kf_xywh_gating.argtypes = [f32p, f32p, f32p, C.c_int, C.c_int, f32p]
+        L.orc_bytetrack_create.argtypes = [C.c_float, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                           C.c_float, C.c_float, C.c_int, C.c_int]
+        L.orc_bytetrack_create.restype = C.c_void_p
+        L.orc_bytetrack_destroy.argtypes = [C.c_void_p]
+        L.orc_bytetrack_reset.argtypes = [C.c_void_p]
+        L.orc_bytetrack_update.argtypes = [C.c_void_p, f32p, C.c_int, f32p, C.c_int]
+        L.orc_bytetrack_update.restype = C.c_int
+        L.orc_bytetrack_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orc_bytetrack_counts.restype = C.c_int
+        L.orc_bytetrack_dump.argtypes = [C.c_void_p, C.c_int, f32p, C.c_int]
+        L.orc_bytetrack_dump.restype = C.c_int
+        L.orc_bytetrack_last_sizes.argtypes = [C.c_void_p, i32p]
+        L.orc_sort_create.argtypes = [C.c_float, C.c_int, C.c_int, C.c_int, C.c_float]
+        L.orc_sort_create.restype = C.c_void_p
+        L.orc_sort_destroy.argtypes = [C.c_void_p]
+        L.orc_sort_reset.argtypes = [C.c_void_p]
+        L.orc_sort_update.argtypes = [C.c_void_p, f32p, C.c_int, f32p, C.c_int]
+        L.orc_sort_update.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def ref_lap():
+    """The reference's real LAP solver (oracle/_ref/libref_lap.so) or None if it was never built."""
+    global _REF
+    if _REF is None:
+        so = os.path.join(ORACLE_DIR, "_ref", "libref_lap.so")
+        if not os.path.exists(so):
+            return None
+        R = C.CDLL(so)
+        R.ref_linear_assignment.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_float, i32p, i32p]
+        R.ref_linear_assignment.restype = C.c_int
+        _REF = R
+    return _REF
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+# ------------------------------------------------------------------ functional wrappers
+def linear_assignment(cost, thresh, use_ref=False):
+    cost = _f32(cost)
+    n, m = cost.shape
+    r2c = np.full(n, -1, np.int32)
+    c2r = np.full(m, -1, np.int32)
+    if n and m:
+        fn = ref_lap().ref_linear_assignment if use_ref else lib().orc_linear_assignment
+        fn(cost, n, m, m, float(thresh), r2c, c2r)
+    return r2c, c2r
+
+
+def iou_batch(a, b):
+    a, b = _f32(a).reshape(-1, 4), _f32(b).reshape(-1, 4)
+    out = np.zeros((a.shape[0], b.shape[0]), np.float32)
+    if out.size:
+        lib().orc_iou_batch(a, a.shape[0], b, b.shape[0], out)
+    return out
+
+
+def iou_distance(a, b):
+    a, b = _f32(a).reshape(-1, 4), _f32(b).reshape(-1, 4)
+    out = np.zeros((a.shape[0], b.shape[0]), np.float32)
+    if out.size:
+        lib().orc_iou_distance(a, a.shape[0], b, b.shape[0], out)
+    return out
+
+
+def fuse_score(cost, conf):
+    cost = _f32(cost).copy()
+    if cost.size:
+        lib().orc_fuse_score(cost, cost.shape[0], cost.shape[1], _f32(conf))
+    return cost
+
+
+def embedding_distance(t, d, metric="cosine"):
+    t, d = _f32(t), _f32(d)
+    out = np.zeros((t.shape[0], d.shape[0]), np.float32)
+    if out.size:
+        lib().orc_embedding_distance(t, t.shape[0], d, d.shape[0], t.shape[1], 0 if metric == "cosine" else 1, out)
+    return out
+
+
+def convert(name, box):
+    out = np.zeros(4, np.float32)
+    getattr(lib(), "orc_" + name)(_f32(box), out)
+    return out
+
+
+class KFXYAH:
+    @staticmethod
+    def initiate(z):
+        m, c = np.zeros(8, np.float32), np.zeros(64, np.float32)
+        lib().orc_kf_xyah_initiate(_f32(z), m, c)
+        return m, c.reshape(8, 8)
+
+    @staticmethod
+    def predict(mean, cov):
+        m, c = _f32(mean).copy(), _f32(cov).reshape(-1).copy()
+        lib().orc_kf_xyah_predict(m, c)
+        return m, c.reshape(8, 8)
+
+    @staticmethod
+    def update(mean, cov, z, conf=0.0):
+        m, c = _f32(mean).copy(), _f32(cov).reshape(-1).copy()
+        rc = lib().orc_kf_xyah_update(m, c, _f32(z), float(conf))
+        return m, c.reshape(8, 8), rc
+
+    @staticmethod
+    def gating(mean, cov, meas, only_position=False, metric="maha"):
+        meas = _f32(meas).reshape(-1, 4)
+        out = np.zeros(meas.shape[0], np.float32)
+        lib().orc_kf_xyah_gating(_f32(mean), _f32(cov).reshape(-1), meas, meas.shape[0], int(only_position),
+                                 0 if metric == "maha" else 1, out)
+        return out
+
+
+class KFXYSR:
+    @staticmethod
+    def init(z):
+        x, p = np.zeros(7, np.float32), np.zeros(49, np.float32)
+        lib().orc_kf_xysr_init(_f32(z), x, p)
+        return x, p.reshape(7, 7)
+
+    @staticmethod
+    def predict(x, p, q_xy=1.0, q_s=1.0):
+        x, p = _f32(x).copy(), _f32(p).reshape(-1).copy()
+        lib().orc_kf_xysr_predict(x, p, float(q_xy), float(q_s))
+        return x, p.reshape(7, 7)
+
+    @staticmethod
+    def update(x, p, z):
+        x, p = _f32(x).copy(), _f32(p).reshape(-1).copy()
+        rc = lib().orc_kf_xysr_update(x, p, _f32(z))
+        return x, p.reshape(7, 7), rc
+
+
+class KFXYWH:
+    @staticmethod
+    def initiate(z):
+        m, c = np.zeros(8, np.float32), np.zeros(64, np.float32)
+        lib().orc_kf_xywh_initiate(_f32(z), m, c)
+        return m, c.reshape(8, 8)
+
+    @staticmethod
+    def predict(mean, cov):
+        m, c = _f32(mean).copy(), _f32(cov).reshape(-1).copy()
+        lib().orc_kf_xywh_predict(m, c)
+        return m, c.reshape(8, 8)
+
+    @staticmethod
+    def update(mean, cov, z):
+        m, c = _f32(mean).copy(), _f32(cov).reshape(-1).copy()
+        lib().orc_kf_xywh_update(m, c, _f32(z))
+        return m, c.reshape(8, 8)
+
+    @staticmethod
+    def gating(mean, cov, meas, only_position=False):
+        meas = _f32(meas).reshape(-1, 4)
+        out = np.zeros(meas.shape[0], np.float32)
+        lib().orc_kf_xywh_gating(_f32(mean), _f32(cov).reshape(-1), meas, meas.shape[0], int(only_position), out)
+        return out
+
+
+class ByteTrack:
+    """Oracle ByteTrack with the reference's constructor argument order (bytetrack.hpp:97-110)."""
+
+    def __init__(self, det_thresh=0.3, max_age=30, max_obs=50, min_hits=3, iou_threshold=0.3,
+                 min_conf=0.1, track_thresh=0.45, match_thresh=0.8, track_buffer=25, frame_rate=30):
+        self._h = lib().orc_bytetrack_create(det_thresh, max_age, max_obs, min_hits, iou_threshold,
+                                             min_conf, track_thresh, match_thresh, track_buffer, frame_rate)
+        self._cap = 4096
+        self._out = np.zeros((self._cap, 8), np.float32)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_bytetrack_destroy(self._h)
+            self._h = None
+
+    def reset(self):
+        lib().orc_bytetrack_reset(self._h)
+
+    def update(self, dets):
+        dets = _f32(dets).reshape(-1, 6)
+        n = lib().orc_bytetrack_update(self._h, dets, dets.shape[0], self._out, self._cap)
+        if n < 0:
+            self._cap = -n * 2
+            self._out = np.zeros((self._cap, 8), np.float32)
+            raise RuntimeError("oracle output buffer too small; state already advanced")
+        return self._out[:n].copy()
+
+    def counts(self):
+        a, b = C.c_int(), C.c_int()
+        lib().orc_bytetrack_counts(self._h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def dump(self, which):
+        na, nl = self.counts()
+        cap = max(1, na if which == 0 else nl)
+        buf = np.zeros((cap, 78), np.float32)
+        k = lib().orc_bytetrack_dump(self._h, which, buf, cap)
+        return buf[:k]
+
+    def last_sizes(self):
+        s = np.zeros(8, np.int32)
+        lib().orc_bytetrack_last_sizes(self._h, s)
+        return s
+
+
+class Sort:
+    def __init__(self, det_thresh=0.3, max_age=1, max_obs=50, min_hits=3, iou_threshold=0.3):
+        self._h = lib().orc_sort_create(det_thresh, max_age, max_obs, min_hits, iou_threshold)
+        self._out = np.zeros((4096, 8), np.float32)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_sort_destroy(self._h)
+            self._h = None
+
+    def reset(self):
+        lib().orc_sort_reset(self._h)
+
+    def update(self, dets):
+        dets = _f32(dets).reshape(-1, 6)
+        n = lib().orc_sort_update(self._h, dets, dets.shape[0], self._out, self._out.shape[0])
+        assert n >= 0
+        return self._out[:n].copy()
