@@ -1,0 +1,171 @@
+/*
+ * motb200.h - C ABI of the B200-native association engine (libmotb200.so).
+ *
+ * This is the drop-in boundary for motcpp's per-frame hot path.  The reference has no FFI of its
+ * own: its boundary is the C++ class motcpp::BaseTracker and a few free functions.  Each entry
+ * point below names the reference interface it replaces (paths relative to the motcpp tree);
+ * INTEGRATION.md shows the C++ binding a motcpp maintainer would add on top of this header, and
+ * include/motcpp_b200/*.hpp ships that binding (same class names, constructor arguments and
+ * exceptions as the reference).
+ *
+ * Conventions
+ *   - plain C types only; every function returns a mot_status (0 = ok); mot_last_error() gives
+ *     the message of the calling thread's last failure.  No exceptions cross this boundary.
+ *   - matrices are ROW-MAJOR float32 unless stated otherwise (Eigen::MatrixXf is column-major: the
+ *     C++ binding transposes on the way in/out).
+ *   - "device" pointers are CUDA device memory of the engine's GPU; "host" pointers are ordinary
+ *     host memory (pinned memory from mot_host_alloc makes the copies asynchronous).
+ *   - `stream` arguments are a cudaStream_t passed as void* (NULL = the legacy default stream).
+ *   - there is no CPU fallback: every compute entry point fails with MOT_ERR_NO_DEVICE when no
+ *     CUDA device is present.
+ */
+#ifndef MOTB200_H
+#define MOTB200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum mot_status {
+    MOT_OK = 0,
+    MOT_ERR_INVALID_ARGUMENT = 1,  /* -> std::invalid_argument in the C++ binding (src/tracker.cpp:108-125) */
+    MOT_ERR_CUDA = 2,              /* -> std::runtime_error */
+    MOT_ERR_NO_DEVICE = 3,
+    MOT_ERR_CAPACITY = 4,          /* a stream ran out of track slots / output rows / detection slots */
+    MOT_ERR_NUMERIC = 5,           /* a Kalman update hit the reference's pseudo-inverse fallback */
+    MOT_ERR_UNSUPPORTED = 6
+} mot_status;
+
+const char* mot_last_error(void);
+int mot_version(void);                 /* 100 * major + minor */
+int mot_device_count(void);            /* 0 when no CUDA device is usable */
+
+/* ---- memory helpers (so a caller needs no CUDA headers) ------------------------------------ */
+int mot_device_alloc(void** ptr, size_t bytes);
+int mot_device_free(void* ptr);
+int mot_host_alloc(void** ptr, size_t bytes);            /* pinned */
+int mot_host_free(void* ptr);
+int mot_copy_h2d(void* dst_device, const void* src_host, size_t bytes, void* stream);
+int mot_copy_d2h(void* dst_host, const void* src_device, size_t bytes, void* stream);
+int mot_memset_device(void* dst_device, int value, size_t bytes, void* stream);
+int mot_stream_sync(void* stream);
+
+/* ---- tracker engine: BaseTracker::update for S independent camera streams ------------------ */
+/* replaces motcpp::BaseTracker::update / reset (include/motcpp/tracker.hpp:67-74) and the concrete
+ * front-ends' update(): ByteTrack src/trackers/bytetrack.cpp:166, Sort src/trackers/sort.cpp:102,
+ * OCSort src/trackers/ocsort.cpp:285, BotSort src/trackers/botsort.cpp:260. */
+typedef enum mot_tracker_kind {
+    MOT_TRACKER_SORT = 0,
+    MOT_TRACKER_BYTETRACK = 1,
+    MOT_TRACKER_OCSORT = 2,
+    MOT_TRACKER_BOTSORT = 3
+} mot_tracker_kind;
+
+typedef struct mot_engine_config {
+    int kind;               /* mot_tracker_kind */
+    int n_streams;          /* independent trackers living on this GPU */
+    int track_capacity;     /* live + lost tracks per stream (0 = default 1536) */
+    int max_dets;           /* detections per stream per frame (0 = default 512) */
+    int device;             /* CUDA device ordinal */
+    int n_chunks;           /* host-buffer calls are pipelined over this many stream chunks (0 = auto) */
+    /* BaseTracker ctor (include/motcpp/tracker.hpp:47-55) */
+    float det_thresh;
+    int max_age, max_obs, min_hits;
+    float iou_threshold;
+    /* ByteTrack ctor (include/motcpp/trackers/bytetrack.hpp:97-110) */
+    float min_conf, track_thresh, match_thresh;
+    int track_buffer, frame_rate;
+    /* OCSort ctor (include/motcpp/trackers/ocsort.hpp:88-102) */
+    int delta_t;
+    float inertia;
+    int use_byte;
+    float q_xy_scaling, q_s_scaling;
+    /* BotSort ctor (include/motcpp/trackers/botsort.hpp:108-134) */
+    float track_high_thresh, track_low_thresh, new_track_thresh;
+    float proximity_thresh, appearance_thresh;
+    int fuse_first_associate, with_reid, emb_dim;
+} mot_engine_config;
+
+typedef struct mot_engine mot_engine;
+
+/* fills cfg with the reference constructor defaults of `kind` */
+int mot_engine_default_config(int kind, mot_engine_config* cfg);
+int mot_engine_create(const mot_engine_config* cfg, mot_engine** out);
+int mot_engine_destroy(mot_engine* e);
+/* BaseTracker::reset(): clears every stream; ByteTrack/SORT/OC-SORT keep their ID counters
+ * (reference bytetrack.hpp:38-40), BoT-SORT restarts at 0 (botsort.cpp:257). */
+int mot_engine_reset(mot_engine* e);
+
+/* One call = n_frames consecutive update()s for every stream, HOST buffers:
+ *   dets   [n_frames][S][ld_dets][6]  rows [x1,y1,x2,y2,conf,cls]
+ *   n_dets [n_frames][S]
+ *   out    [n_frames][S][ld_out][8]   rows [x1,y1,x2,y2,id,conf,cls,det_ind]
+ *   n_out  [n_frames][S]
+ * Copies in, runs, copies out and returns when the results are in `out` (pipelined over stream
+ * chunks).  n_frames = 1 is the reference's tracker->update(dets, img) for S trackers at once. */
+int mot_engine_update_host(mot_engine* e, int n_frames, const float* dets, const int* n_dets, int ld_dets,
+                           float* out, int* n_out, int ld_out);
+/* Same contract with DEVICE buffers, asynchronous on `stream`; no host synchronisation. */
+int mot_engine_update_device(mot_engine* e, int n_frames, const float* d_dets, const int* d_n_dets, int ld_dets,
+                             float* d_out, int* d_n_out, int ld_out, void* stream);
+/* Per-stream sticky error bits since the last reset (0 = fine): 1 track capacity, 2 too many
+ * detections, 4 output rows truncated, 8 Kalman fallback.  Synchronises.  flags may be NULL; the
+ * return value is MOT_OK or the most severe condition as a mot_status. */
+int mot_engine_check(mot_engine* e, int* flags_per_stream);
+/* Introspection for tests: header ints of one stream [n_active,n_lost,n_free,id_counter,frame,err,
+ * n1,m1,n2,m2,n3,m3,dupA,dupB,..] (16 ints), and a dump of one list (0 active, 1 lost) as rows of
+ * [id,state,is_activated,frame_id,start_frame,tracklet_len,mean 8,cov 64] (78 floats). */
+int mot_engine_stream_header(mot_engine* e, int stream_index, int* hdr16);
+int mot_engine_dump_list(mot_engine* e, int stream_index, int which, float* rows78, int cap_rows, int* n_rows);
+/* launch geometry actually used (for the bench's gpu_launches / roofline bookkeeping) */
+int mot_engine_info(mot_engine* e, int* threads_per_cta, int* smem_bytes, int* ctas, int* state_bytes_per_stream);
+
+/* ---- standalone kernels (DEVICE pointers, asynchronous on `stream`) ------------------------ */
+/* Kalman state records: kind 0 XYAH / 2 XYWH = 72 floats [mean 8 | cov 8x8]; kind 1 XYSR = 56
+ * floats [x 7 | P 7x7].  n tracks, contiguous.
+ *   initiate: KalmanFilterXYAH::initiate src/motion/kalman_filter.cpp:29-42 (+ xyah_kf.cpp:14-29),
+ *             KalmanFilterXYSR ctor state xysr_kf.cpp:49-55, KalmanFilterXYWH::initiate xywh_kf.hpp:41-63
+ *   predict : kalman_filter.cpp:44-58 / xysr_kf.cpp:71-77 / xywh_kf.hpp:70-94
+ *   update  : kalman_filter.cpp:77-112 / xysr_kf.cpp:79-112 / xywh_kf.hpp:103-135
+ *   gating  : kalman_filter.cpp:148-176 (XYAH; "maha" is the reference's d^T S^-2 d) /
+ *             xywh_kf.hpp:140-177 (XYWH) */
+int mot_kf_initiate(int kind, float* recs, const float* z4, long long n, void* stream);
+/* flags: optional n bytes, bit0 = zero the height velocity before predicting (ByteTrack lost tracks);
+ * q_xy_scaling / q_s_scaling only matter for XYSR (OC-SORT: 0.01 / 0.0001, SORT: 1 / 1). */
+int mot_kf_predict(int kind, float* recs, const unsigned char* flags, long long n, float q_xy_scaling,
+                   float q_s_scaling, void* stream);
+/* conf: optional n floats (XYAH NSA scaling); fail: optional n bytes, 1 where the reference would
+ * have taken its pseudo-inverse fallback (that record is left untouched). */
+int mot_kf_update(int kind, float* recs, const float* z4, const float* conf, long long n, unsigned char* fail,
+                  void* stream);
+/* out (n_tracks x n_meas) row-major.  metric 0 = "maha", 1 = "gaussian" (XYAH only). */
+int mot_kf_gating(int kind, const float* recs, int n_tracks, const float* meas4, int n_meas, int only_position,
+                  int metric, float* out, void* stream);
+
+/* N x M cost matrices.  a (n x 4), b (m x 4) xyxy boxes; out row-major with leading dimension ld.
+ *   mode 0 iou_batch (include/motcpp/utils/iou.hpp:63-100), 1 iou_distance (src/utils/matching.cpp:62-65),
+ *   2 iou_distance then fuse_score with conf[m] (matching.cpp:130-143) */
+int mot_cost_iou(const float* a, int n, const float* b, int m, const float* conf, float* out, int ld, int mode,
+                 void* stream);
+/* embedding_distance(metric="cosine") (src/utils/matching.cpp:67-92): max(0, 1 - t.d/(|t||d| + 1e-10)).
+ * t (n x dim), d (m x dim) fp32 row-major; tcgen05 tensor-core contraction with a 3-term bf16
+ * split (fp32-level accuracy), out row-major ld. */
+int mot_cost_cosine(const float* t, int n, const float* d, int m, int dim, float* out, int ld, void* stream);
+
+/* utils::linear_assignment (src/utils/matching.cpp:14-60) + LAPSolver (include/motcpp/association/
+ * lap_solver.hpp:251-332): cost row-major (n x m), pairs with cost > thresh never match.
+ * row2col[n] / col2row[m]: -1 = unmatched.  Batched: problem p reads cost + p*stride_cost and
+ * writes row2col + p*n, col2row + p*m (n_rows/n_cols: optional per-problem sizes <= n, m). */
+int mot_lap_device(const float* cost, int n, int m, int ld, float thresh, int* row2col, int* col2row, void* stream);
+int mot_lap_batch_device(const float* cost, long long stride_cost, int n_problems, const int* n_rows,
+                         const int* n_cols, int n, int m, int ld, float thresh, int* row2col, int* col2row,
+                         void* stream);
+/* convenience: host pointers, synchronous */
+int mot_lap_host(const float* cost, int n, int m, int ld, float thresh, int* row2col, int* col2row);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOTB200_H */

@@ -1,0 +1,429 @@
+"""Host-side mirror of the reference's operator interface for the association hot path, on top of
+the C ABI (include/motb200.h).  Names, argument meaning and error behaviour follow motcpp:
+
+    motcpp::trackers::ByteTrack(det_thresh, max_age, ..., frame_rate).update(dets, img, embs)
+        include/motcpp/trackers/bytetrack.hpp:97-110, src/trackers/bytetrack.cpp:166
+    motcpp::utils::{iou_batch, iou_distance, fuse_score, linear_assignment, embedding_distance}
+        include/motcpp/utils/iou.hpp:63, include/motcpp/utils/matching.hpp:43-55,99-108
+    motcpp::motion::KalmanFilterXYAH / KalmanFilterXYSR, motcpp::KalmanFilterXYWH
+
+Everything computes on the GPU; numpy is only the host container (the reference's Eigen::MatrixXf).
+std::invalid_argument maps to ValueError, std::runtime_error to RuntimeError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import KF_XYAH, KF_XYSR, KF_XYWH, EngineConfig, MotError, check, load
+
+
+def _raise(e: MotError):
+    if e.code == _lib.MOT_ERR_INVALID_ARGUMENT:
+        raise ValueError(str(e)) from None
+    raise e
+
+
+# ------------------------------------------------------------------ device / pinned memory helpers
+class DeviceArray:
+    """A typed device allocation with numpy-flavoured upload/download (no torch needed)."""
+
+    def __init__(self, shape, dtype=np.float32):
+        self.shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        p = C.c_void_p()
+        check(load().mot_device_alloc(C.byref(p), max(self.nbytes, 1)))
+        self.ptr = p.value
+
+    @classmethod
+    def from_host(cls, arr, dtype=None):
+        arr = np.ascontiguousarray(arr, dtype=dtype)
+        d = cls(arr.shape, arr.dtype)
+        d.upload(arr)
+        return d
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr, dtype=self.dtype)
+        assert arr.nbytes == self.nbytes, (arr.shape, self.shape)
+        if self.nbytes:
+            check(load().mot_copy_h2d(self.ptr, arr.ctypes.data, self.nbytes, None))
+            check(load().mot_stream_sync(None))
+
+    def download(self) -> np.ndarray:
+        out = np.empty(self.shape, self.dtype)
+        if self.nbytes:
+            check(load().mot_copy_d2h(out.ctypes.data, self.ptr, self.nbytes, None))
+            check(load().mot_stream_sync(None))
+        return out
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            load().mot_device_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+    """numpy array over page-locked host memory (so engine copies are asynchronous DMA)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape, dtype=np.int64))
+    p = C.c_void_p()
+    check(load().mot_host_alloc(C.byref(p), max(n * dtype.itemsize, 1)))
+    buf = (C.c_char * max(n * dtype.itemsize, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+    return arr
+
+
+# ------------------------------------------------------------------ utils:: free functions
+def iou_batch(bboxes1, bboxes2, _mode=0, _conf=None) -> np.ndarray:
+    """utils::iou_batch (iou.hpp:63-100): (N,4),(M,4) xyxy -> (N,M)."""
+    a = np.ascontiguousarray(bboxes1, np.float32).reshape(-1, 4)
+    b = np.ascontiguousarray(bboxes2, np.float32).reshape(-1, 4)
+    n, m = a.shape[0], b.shape[0]
+    if n == 0 or m == 0:
+        return np.zeros((n, m), np.float32) if _mode == 0 else np.ones((n, m), np.float32)
+    _lib.require_gpu()
+    ld = (m + 3) // 4 * 4
+    da, db, do = DeviceArray.from_host(a), DeviceArray.from_host(b), DeviceArray((n, ld))
+    dc = DeviceArray.from_host(np.ascontiguousarray(_conf, np.float32)) if _conf is not None else None
+    try:
+        check(load().mot_cost_iou(da.ptr, n, db.ptr, m, dc.ptr if dc else None, do.ptr, ld, _mode, None))
+    except MotError as e:
+        _raise(e)
+    return np.ascontiguousarray(do.download()[:, :m])
+
+
+def iou_distance(atracks, btracks) -> np.ndarray:
+    """utils::iou_distance (matching.cpp:62-65): 1 - iou_batch."""
+    return iou_batch(atracks, btracks, _mode=1)
+
+
+def iou_distance_fused(atracks, btracks, det_confs) -> np.ndarray:
+    """fuse_score(iou_distance(a, b), det_confs) in one kernel (matching.cpp:130-143)."""
+    return iou_batch(atracks, btracks, _mode=2, _conf=det_confs)
+
+
+def embedding_distance(track_features, det_features, metric: str = "cosine") -> np.ndarray:
+    """utils::embedding_distance (matching.cpp:67-107), cosine metric on tensor cores."""
+    if metric != "cosine":
+        raise ValueError("Unknown metric: " + metric if metric != "euclidean" else
+                         "euclidean embedding distance is not on the accelerated path")
+    t = np.ascontiguousarray(track_features, np.float32)
+    d = np.ascontiguousarray(det_features, np.float32)
+    n, m = t.shape[0], d.shape[0]
+    if n == 0 or m == 0:
+        return np.zeros((n, m), np.float32)
+    _lib.require_gpu()
+    ld = (m + 3) // 4 * 4
+    dt, dd, do = DeviceArray.from_host(t), DeviceArray.from_host(d), DeviceArray((n, ld))
+    try:
+        check(load().mot_cost_cosine(dt.ptr, n, dd.ptr, m, t.shape[1], do.ptr, ld, None))
+    except MotError as e:
+        _raise(e)
+    return np.ascontiguousarray(do.download()[:, :m])
+
+
+@dataclass
+class LinearAssignmentResult:
+    """utils::LinearAssignmentResult (matching.hpp:32-36)."""
+    matches: List[Tuple[int, int]] = field(default_factory=list)
+    unmatched_a: List[int] = field(default_factory=list)
+    unmatched_b: List[int] = field(default_factory=list)
+
+
+def linear_assignment(cost_matrix, thresh: float) -> LinearAssignmentResult:
+    """utils::linear_assignment (matching.cpp:14-60): matches in ascending row order."""
+    cost = np.ascontiguousarray(cost_matrix, np.float32)
+    if cost.ndim != 2:
+        raise ValueError("cost_matrix must be 2-D")
+    n, m = cost.shape
+    res = LinearAssignmentResult()
+    if n == 0 or m == 0:
+        res.unmatched_a = list(range(n))
+        res.unmatched_b = list(range(m))
+        return res
+    _lib.require_gpu()
+    r2c = np.empty(n, np.int32)
+    c2r = np.empty(m, np.int32)
+    try:
+        check(load().mot_lap_host(cost.ctypes.data, n, m, m, float(thresh), r2c.ctypes.data, c2r.ctypes.data))
+    except MotError as e:
+        _raise(e)
+    res.matches = [(int(i), int(j)) for i, j in enumerate(r2c) if j >= 0]
+    res.unmatched_a = [int(i) for i in np.nonzero(r2c < 0)[0]]
+    res.unmatched_b = [int(j) for j in np.nonzero(c2r < 0)[0]]
+    return res
+
+
+def linear_assignment_arrays(cost_matrix, thresh: float):
+    """Same solve, raw row2col / col2row arrays (-1 = unmatched)."""
+    cost = np.ascontiguousarray(cost_matrix, np.float32)
+    n, m = cost.shape
+    r2c = np.full(n, -1, np.int32)
+    c2r = np.full(m, -1, np.int32)
+    if n and m:
+        _lib.require_gpu()
+        check(load().mot_lap_host(cost.ctypes.data, n, m, m, float(thresh), r2c.ctypes.data, c2r.ctypes.data))
+    return r2c, c2r
+
+
+# ------------------------------------------------------------------ Kalman filters (batched)
+class _BatchedKF:
+    KIND = KF_XYAH
+    NX = 8
+
+    @property
+    def rec(self) -> int:
+        return self.NX + self.NX * self.NX
+
+    def _pack(self, mean, cov) -> np.ndarray:
+        mean = np.ascontiguousarray(mean, np.float32).reshape(-1, self.NX)
+        cov = np.ascontiguousarray(cov, np.float32).reshape(-1, self.NX * self.NX)
+        return np.concatenate([mean, cov], axis=1)
+
+    def _unpack(self, recs, single):
+        mean = recs[:, :self.NX]
+        cov = recs[:, self.NX:].reshape(-1, self.NX, self.NX)
+        return (mean[0], cov[0]) if single else (mean, cov)
+
+    def initiate(self, measurement):
+        z = np.ascontiguousarray(measurement, np.float32)
+        single = z.ndim == 1
+        z = z.reshape(-1, 4)
+        _lib.require_gpu()
+        dz, dr = DeviceArray.from_host(z), DeviceArray((z.shape[0], self.rec))
+        check(load().mot_kf_initiate(self.KIND, dr.ptr, dz.ptr, z.shape[0], None))
+        return self._unpack(dr.download(), single)
+
+    def predict(self, mean, covariance, zero_vh=None, q_xy_scaling=1.0, q_s_scaling=1.0):
+        single = np.ndim(mean) == 1
+        recs = self._pack(mean, covariance)
+        _lib.require_gpu()
+        dr = DeviceArray.from_host(recs)
+        df = DeviceArray.from_host(np.ascontiguousarray(zero_vh, np.uint8)) if zero_vh is not None else None
+        check(load().mot_kf_predict(self.KIND, dr.ptr, df.ptr if df else None, recs.shape[0], float(q_xy_scaling),
+                                    float(q_s_scaling), None))
+        return self._unpack(dr.download(), single)
+
+    def update(self, mean, covariance, measurement, confidence=None, return_fail=False):
+        single = np.ndim(mean) == 1
+        recs = self._pack(mean, covariance)
+        z = np.ascontiguousarray(measurement, np.float32).reshape(-1, 4)
+        n = recs.shape[0]
+        _lib.require_gpu()
+        dr, dz = DeviceArray.from_host(recs), DeviceArray.from_host(z)
+        dc = None
+        if confidence is not None:
+            dc = DeviceArray.from_host(np.broadcast_to(np.asarray(confidence, np.float32), (n,)).copy())
+        dfail = DeviceArray((n,), np.uint8)
+        check(load().mot_kf_update(self.KIND, dr.ptr, dz.ptr, dc.ptr if dc else None, n, dfail.ptr, None))
+        out = self._unpack(dr.download(), single)
+        return (*out, dfail.download()) if return_fail else out
+
+
+class KalmanFilterXYAH(_BatchedKF):
+    """motion::KalmanFilterXYAH (kalman_filter.cpp, xyah_kf.cpp), batched over tracks."""
+    KIND = KF_XYAH
+
+    def gating_distance(self, mean, covariance, measurements, only_position=False, metric="maha"):
+        if metric not in ("maha", "gaussian"):
+            raise ValueError("Invalid metric: " + metric)          # kalman_filter.cpp:174
+        recs = self._pack(mean, covariance)
+        meas = np.ascontiguousarray(measurements, np.float32).reshape(-1, 4)
+        if recs.shape[0] == 0 or meas.shape[0] == 0:
+            return np.zeros((recs.shape[0], meas.shape[0]), np.float32)
+        _lib.require_gpu()
+        dr, dm, do = DeviceArray.from_host(recs), DeviceArray.from_host(meas), DeviceArray((recs.shape[0], meas.shape[0]))
+        check(load().mot_kf_gating(self.KIND, dr.ptr, recs.shape[0], dm.ptr, meas.shape[0], int(only_position),
+                                   0 if metric == "maha" else 1, do.ptr, None))
+        out = do.download()
+        return out[0] if np.ndim(mean) == 1 else out
+
+
+class KalmanFilterXYWH(KalmanFilterXYAH):
+    """motcpp::KalmanFilterXYWH (xywh_kf.hpp), batched over tracks."""
+    KIND = KF_XYWH
+
+    def gating_distance(self, mean, covariance, measurements, only_position=False, metric="maha"):
+        return super().gating_distance(mean, covariance, measurements, only_position, "maha")
+
+
+class KalmanFilterXYSR(_BatchedKF):
+    """motion::KalmanFilterXYSR (xysr_kf.cpp), batched over tracks; state 7, covariance 7x7."""
+    KIND = KF_XYSR
+    NX = 7
+
+
+# ------------------------------------------------------------------ tracker engine
+_ERR_BITS = {1: "track capacity exceeded", 2: "too many detections", 4: "output rows truncated",
+             8: "Kalman update left the Cholesky path"}
+
+
+class Engine:
+    """S independent trackers resident on one GPU (mot_engine_*)."""
+
+    def __init__(self, kind: int = _lib.TRACKER_BYTETRACK, n_streams: int = 1, track_capacity: int = 0,
+                 max_dets: int = 0, device: int = 0, n_chunks: int = 0, **params):
+        _lib.require_gpu()
+        cfg = EngineConfig()
+        check(load().mot_engine_default_config(kind, C.byref(cfg)))
+        cfg.n_streams, cfg.track_capacity, cfg.max_dets = n_streams, track_capacity, max_dets
+        cfg.device, cfg.n_chunks = device, n_chunks
+        valid = {f[0] for f in EngineConfig._fields_}
+        for k, v in params.items():
+            if k not in valid:
+                raise ValueError(f"unknown tracker parameter {k!r}")
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        h = C.c_void_p()
+        try:
+            check(load().mot_engine_create(C.byref(cfg), C.byref(h)))
+        except MotError as e:
+            _raise(e)
+        self._h = h.value
+        self.n_streams = n_streams
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().mot_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        check(load().mot_engine_reset(self._h))
+
+    def update(self, dets: np.ndarray, n_dets: np.ndarray, out: Optional[np.ndarray] = None,
+               n_out: Optional[np.ndarray] = None, ld_out: int = 0):
+        """dets (T,S,ld,6) or (S,ld,6) float32, n_dets (T,S) or (S,) int32 -> out (T,S,ld_out,8), n_out (T,S)."""
+        dets = np.asarray(dets)
+        squeeze = dets.ndim == 3
+        if squeeze:
+            dets = dets[None]
+        if dets.dtype != np.float32 or not dets.flags.c_contiguous:
+            dets = np.ascontiguousarray(dets, np.float32)
+        T, S, ld, six = dets.shape
+        if six != 6:
+            raise ValueError("Detections must have 6 (AABB) or 7 (OBB) columns")     # src/tracker.cpp:110
+        if S != self.n_streams:
+            raise ValueError(f"expected {self.n_streams} streams, got {S}")
+        n_dets = np.ascontiguousarray(n_dets, np.int32).reshape(T, S)
+        if ld_out <= 0:
+            ld_out = self.cfg.track_capacity or 1536
+        if out is None:
+            out = np.empty((T, S, ld_out, 8), np.float32)
+        if n_out is None:
+            n_out = np.empty((T, S), np.int32)
+        try:
+            check(load().mot_engine_update_host(self._h, T, dets.ctypes.data, n_dets.ctypes.data, ld, out.ctypes.data,
+                                                n_out.ctypes.data, out.shape[2]))
+        except MotError as e:
+            _raise(e)
+        return (out[0], n_out[0]) if squeeze else (out, n_out)
+
+    def update_device(self, n_frames, d_dets, d_n_dets, ld_dets, d_out, d_n_out, ld_out, stream=None):
+        """Raw device-pointer path (ints / c_void_p), asynchronous on `stream`."""
+        check(load().mot_engine_update_device(self._h, n_frames, d_dets, d_n_dets, ld_dets, d_out, d_n_out, ld_out,
+                                              stream))
+
+    def check(self) -> np.ndarray:
+        flags = np.zeros(self.n_streams, np.int32)
+        rc = load().mot_engine_check(self._h, flags.ctypes.data)
+        if rc != _lib.MOT_OK:
+            bits = int(np.bitwise_or.reduce(flags))
+            what = ", ".join(v for k, v in _ERR_BITS.items() if bits & k)
+            raise RuntimeError(f"engine error flags 0x{bits:x}: {what}")
+        return flags
+
+    def header(self, stream: int = 0) -> np.ndarray:
+        h = np.zeros(16, np.int32)
+        check(load().mot_engine_stream_header(self._h, stream, h.ctypes.data))
+        return h
+
+    def dump(self, stream: int, which: int) -> np.ndarray:
+        hdr = self.header(stream)
+        n = int(hdr[0] if which == 0 else hdr[1])
+        buf = np.zeros((max(n, 1), 78), np.float32)
+        k = C.c_int()
+        check(load().mot_engine_dump_list(self._h, stream, which, buf.ctypes.data, max(n, 1), C.byref(k)))
+        return buf[:k.value]
+
+    def info(self):
+        a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        check(load().mot_engine_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return {"threads_per_cta": a.value, "smem_bytes": b.value, "ctas": c.value, "state_bytes_per_stream": d.value}
+
+
+class _Image:
+    """What the hot path needs from cv::Mat: empty(), rows, cols (src/tracker.cpp:114,166-171)."""
+
+    def __init__(self, img):
+        if img is None:
+            self.rows = self.cols = 0
+        elif hasattr(img, "shape"):
+            self.rows, self.cols = (int(img.shape[0]), int(img.shape[1])) if len(img.shape) >= 2 else (0, 0)
+        else:
+            self.rows, self.cols = int(img[0]), int(img[1])
+
+    def empty(self) -> bool:
+        return self.rows == 0 or self.cols == 0
+
+
+class ByteTrack:
+    """motcpp::trackers::ByteTrack with the reference's positional constructor
+    (include/motcpp/trackers/bytetrack.hpp:97-110).  One stream; for many streams use Engine."""
+
+    def __init__(self, det_thresh=0.3, max_age=30, max_obs=50, min_hits=3, iou_threshold=0.3, per_class=False,
+                 nr_classes=80, asso_func="iou", is_obb=False, min_conf=0.1, track_thresh=0.45, match_thresh=0.8,
+                 track_buffer=25, frame_rate=30, track_capacity=0, max_dets=0, device=0):
+        if asso_func != "iou":
+            raise ValueError("Invalid association mode: " + str(asso_func) + " (only \"iou\" is accelerated)")
+        if per_class or is_obb:
+            raise ValueError("per_class / OBB tracking are outside the accelerated hot path")
+        self._engine = Engine(_lib.TRACKER_BYTETRACK, 1, track_capacity, max_dets, device, det_thresh=det_thresh,
+                              max_age=max_age, max_obs=max_obs, min_hits=min_hits, iou_threshold=iou_threshold,
+                              min_conf=min_conf, track_thresh=track_thresh, match_thresh=match_thresh,
+                              track_buffer=track_buffer, frame_rate=frame_rate)
+        self._max_dets = max_dets or 512
+        self._cap = track_capacity or 1536
+        self._dets = np.zeros((1, self._max_dets, 6), np.float32)
+        self._out = np.empty((1, 1, self._cap, 8), np.float32)
+        self._n_out = np.empty((1, 1), np.int32)
+
+    def reset(self):
+        self._engine.reset()
+
+    def update(self, dets, img, embs=None) -> np.ndarray:
+        dets = np.asarray(dets, np.float32)
+        if dets.ndim != 2:
+            dets = dets.reshape(0, 6) if dets.size == 0 else dets
+        # BaseTracker::check_inputs (src/tracker.cpp:108-125)
+        if dets.shape[0] > 0 and dets.shape[1] not in (6, 7):
+            raise ValueError("Detections must have 6 (AABB) or 7 (OBB) columns")
+        if _Image(img).empty():
+            raise ValueError("Image cannot be empty")
+        if embs is not None and np.shape(embs)[0] > 0 and np.shape(embs)[0] != dets.shape[0]:
+            raise ValueError("Detections and embeddings must have same number of rows")
+        if dets.shape[0] > 0 and dets.shape[1] == 7:
+            raise ValueError("OBB detections are outside the accelerated hot path")
+        n = dets.shape[0]
+        if n > self._max_dets:
+            raise ValueError(f"{n} detections exceed max_dets={self._max_dets}")
+        self._dets[0, :n] = dets[:, :6] if n else 0
+        self._engine.update(self._dets[None], np.array([[n]], np.int32), self._out, self._n_out)
+        self._engine.check()
+        return self._out[0, 0, :int(self._n_out[0, 0])].copy()

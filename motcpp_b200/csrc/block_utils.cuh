@@ -12,36 +12,44 @@ struct BlockScratch {
     int pad[3];
 };
 
-// Stable compaction of the indices k in [0, n) for which pred(k) is true.  emit(k, pos) is called
-// by the thread that owns k with pos = rank of k among the kept indices (ascending k), offset by
-// `start`.  Returns start + number kept (same value in every thread).
+// Stable compaction of the indices k in [0, n) for which pred(k) is true.  Every thread takes a
+// contiguous run of ceil(n / blockDim) indices (at most 32), so one block-wide scan serves any n
+// up to 32 * blockDim.  emit(k, pos) is called by the thread that owns k, with pos = start + rank
+// of k among the kept indices (ascending k).  Returns start + number kept, in every thread; the
+// emitted data is visible to the whole block on return.  pred must be side-effect free.
 template <class Pred, class Emit>
 __device__ __forceinline__ int block_compact(int n, int start, BlockScratch* bs, Pred pred, Emit emit) {
+    if (n <= 0) return start;
     const int nt = (int)blockDim.x, tid = (int)threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-    __syncthreads();                       // protect bs against a previous use
-    if (tid == 0) bs->base = start;
-    __syncthreads();
-    for (int tile = 0; tile < n; tile += nt) {
-        const int k = tile + tid;
-        const bool keep = (k < n) && pred(k);
-        const unsigned ballot = __ballot_sync(kFullMask, keep);
-        const int within = __popc(ballot & ((1u << lane) - 1u));
-        if (lane == 0) bs->warp_sum[warp] = __popc(ballot);
-        __syncthreads();
-        int before = 0, total = 0;
-        for (int w = 0; w < nwarps; ++w) {
-            const int s = bs->warp_sum[w];
-            if (w < warp) before += s;
-            total += s;
-        }
-        const int base = bs->base;
-        if (keep) emit(k, base + before + within);
-        __syncthreads();
-        if (tid == 0) bs->base = base + total;
-        __syncthreads();
+    const int items = (n + nt - 1) / nt;
+    const int lo = tid * items;
+    unsigned keep = 0;
+    for (int q = 0; q < items; ++q) {
+        const int k = lo + q;
+        if (k < n && pred(k)) keep |= (1u << q);
     }
-    return bs->base;
+    const int cnt = __popc(keep);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFullMask, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();                       // bs may still be read by a previous call
+    if (lane == 31) bs->warp_sum[warp] = incl;
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < nwarps; ++w) {
+        const int s = bs->warp_sum[w];
+        if (w < warp) before += s;
+        total += s;
+    }
+    int pos = start + before + incl - cnt;
+    for (int q = 0; q < items; ++q)
+        if ((keep >> q) & 1u) emit(lo + q, pos++);
+    __syncthreads();
+    return start + total;
 }
 
 // In-place exclusive scan of data[0..n) (shared or global memory); writes the grand total to

@@ -1,0 +1,512 @@
+// cabi.cu - the extern "C" boundary (include/motb200.h) over the sm_100a kernels.
+// Host code only launches kernels and moves bytes; there is no CPU implementation of any
+// operator in this library.
+#include "../../include/motb200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bytetrack_kernel.cuh"
+#include "kernels_cost.cuh"
+#include "kernels_kf.cuh"
+#include "kernels_lap.cuh"
+#include "kernels_cosine.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define MOT_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fail(e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver ? MOT_ERR_NO_DEVICE : MOT_ERR_CUDA, \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+int require_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(MOT_ERR_NO_DEVICE, "no CUDA device available (libmotb200 has no CPU fallback): %s",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    return MOT_OK;
+}
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+constexpr int kMaxChunks = 8;
+
+}  // namespace
+
+struct mot_engine {
+    mot_engine_config cfg;
+    mot::BtLayout layout;
+    mot::BtParams bt;
+    int e_cap = 4096;
+    size_t smem_bytes = 0;
+    unsigned char* d_state = nullptr;
+    int n_chunks = 1;
+    cudaStream_t streams[kMaxChunks] = {};
+    // staging for the host-buffer path (grow-only)
+    float* d_dets = nullptr;  size_t dets_cap = 0;
+    int* d_ndets = nullptr;   size_t ndets_cap = 0;
+    float* d_out = nullptr;   size_t out_cap = 0;
+    int* d_nout = nullptr;    size_t nout_cap = 0;
+};
+
+
+// ---- helpers (C++ linkage)
+static int engine_reset_impl(mot_engine* e, int keep_ids) {
+    mot::bytetrack_reset_kernel<<<std::min(e->cfg.n_streams, 4096), 256, 0, e->streams[0]>>>(
+        e->d_state, e->layout, e->cfg.n_streams, keep_ids);
+    MOT_CUDA(cudaGetLastError());
+    MOT_CUDA(cudaStreamSynchronize(e->streams[0]));
+    return MOT_OK;
+}
+
+static mot::BtArgs make_args(mot_engine* e, int T, const float* dets, const int* nd, int ld_dets, float* out, int* nout,
+                             int ld_out, int s_begin, int s_end) {
+    mot::BtArgs a{};
+    a.state = e->d_state; a.layout = e->layout;
+    a.dets = dets; a.n_dets = nd; a.out = out; a.n_out = nout;
+    a.T = T; a.S = e->cfg.n_streams; a.s_begin = s_begin; a.s_end = s_end;
+    a.ld_dets = ld_dets; a.ld_out = ld_out; a.e_cap = e->e_cap; a.p = e->bt;
+    return a;
+}
+
+template <class T>
+static int grow(T** p, size_t* cap, size_t need) {
+    if (*cap >= need) return MOT_OK;
+    if (*p) MOT_CUDA(cudaFree(*p));
+    *p = nullptr; *cap = 0;
+    MOT_CUDA(cudaMalloc(p, need * sizeof(T)));
+    *cap = need;
+    return MOT_OK;
+}
+
+static int kf_grid(long long n) {
+    const long long groups_per_block = 256 / 8;
+    long long blocks = (n + groups_per_block - 1) / groups_per_block;
+    const long long cap = (long long)sm_count() * 8;
+    return (int)std::max<long long>(1, std::min(blocks, cap));
+}
+
+
+extern "C" {
+
+const char* mot_last_error(void) { return g_err.c_str(); }
+int mot_version(void) { return 100; }
+int mot_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int mot_device_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return fail(MOT_ERR_INVALID_ARGUMENT, "null out pointer");
+    if (int rc = require_device()) return rc;
+    MOT_CUDA(cudaMalloc(ptr, bytes ? bytes : 1));
+    return MOT_OK;
+}
+int mot_device_free(void* ptr) { MOT_CUDA(cudaFree(ptr)); return MOT_OK; }
+int mot_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return fail(MOT_ERR_INVALID_ARGUMENT, "null out pointer");
+    if (int rc = require_device()) return rc;
+    MOT_CUDA(cudaMallocHost(ptr, bytes ? bytes : 1));
+    return MOT_OK;
+}
+int mot_host_free(void* ptr) { MOT_CUDA(cudaFreeHost(ptr)); return MOT_OK; }
+int mot_copy_h2d(void* dst, const void* src, size_t bytes, void* stream) {
+    MOT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return MOT_OK;
+}
+int mot_copy_d2h(void* dst, const void* src, size_t bytes, void* stream) {
+    MOT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return MOT_OK;
+}
+int mot_memset_device(void* dst, int value, size_t bytes, void* stream) {
+    MOT_CUDA(cudaMemsetAsync(dst, value, bytes, (cudaStream_t)stream));
+    return MOT_OK;
+}
+int mot_stream_sync(void* stream) { MOT_CUDA(cudaStreamSynchronize((cudaStream_t)stream)); return MOT_OK; }
+
+// ------------------------------------------------------------------------------ engine
+int mot_engine_default_config(int kind, mot_engine_config* c) {
+    if (!c) return fail(MOT_ERR_INVALID_ARGUMENT, "null config");
+    std::memset(c, 0, sizeof(*c));
+    c->kind = kind;
+    c->n_streams = 1;
+    c->track_capacity = 0; c->max_dets = 0; c->device = 0; c->n_chunks = 0;
+    // BaseTracker defaults (include/motcpp/tracker.hpp:47-55)
+    c->det_thresh = 0.3f; c->max_age = 30; c->max_obs = 50; c->min_hits = 3; c->iou_threshold = 0.3f;
+    // ByteTrack (bytetrack.hpp:97-110)
+    c->min_conf = 0.1f; c->track_thresh = 0.45f; c->match_thresh = 0.8f; c->track_buffer = 25; c->frame_rate = 30;
+    // OCSort (ocsort.hpp:88-102)
+    c->delta_t = 3; c->inertia = 0.2f; c->use_byte = 0; c->q_xy_scaling = 0.01f; c->q_s_scaling = 0.0001f;
+    // BotSort (botsort.hpp:108-134)
+    c->track_high_thresh = 0.5f; c->track_low_thresh = 0.1f; c->new_track_thresh = 0.6f;
+    c->proximity_thresh = 0.5f; c->appearance_thresh = 0.25f; c->fuse_first_associate = 0; c->with_reid = 1;
+    c->emb_dim = 0;
+    switch (kind) {
+        case MOT_TRACKER_SORT: c->max_age = 1; break;             // sort.hpp:70
+        case MOT_TRACKER_BYTETRACK: break;
+        case MOT_TRACKER_OCSORT: c->det_thresh = 0.2f; break;
+        case MOT_TRACKER_BOTSORT: c->track_buffer = 30; break;
+        default: return fail(MOT_ERR_INVALID_ARGUMENT, "unknown tracker kind %d", kind);
+    }
+    return MOT_OK;
+}
+
+int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
+    if (!cfg || !out) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    if (cfg->kind != MOT_TRACKER_BYTETRACK)
+        return fail(MOT_ERR_UNSUPPORTED, "tracker kind %d is not built in this library version (ByteTrack = 1 is)", cfg->kind);
+    if (cfg->n_streams <= 0) return fail(MOT_ERR_INVALID_ARGUMENT, "n_streams must be positive");
+    if (int rc = require_device()) return rc;
+    MOT_CUDA(cudaSetDevice(cfg->device));
+    mot_engine* e = new mot_engine();
+    e->cfg = *cfg;
+    if (e->cfg.track_capacity <= 0) e->cfg.track_capacity = 1536;
+    if (e->cfg.max_dets <= 0) e->cfg.max_dets = 512;
+    if (e->cfg.track_capacity > 16384 || e->cfg.max_dets > 16384) {
+        delete e;
+        return fail(MOT_ERR_INVALID_ARGUMENT, "track_capacity / max_dets above 16384 are not supported");
+    }
+    // BaseTracker ctor fix-up (src/tracker.cpp:37-39)
+    if (e->cfg.max_age >= e->cfg.max_obs) e->cfg.max_obs = e->cfg.max_age + 5;
+    e->layout = mot::BtLayout::make(e->cfg.track_capacity, e->cfg.max_dets);
+    e->bt.min_conf = cfg->min_conf;
+    e->bt.track_thresh = cfg->track_thresh;
+    e->bt.match_thresh = cfg->match_thresh;
+    e->bt.det_thresh = cfg->track_thresh;                                        // bytetrack.cpp:145
+    e->bt.max_time_lost = (int)(cfg->frame_rate / 30.0f * cfg->track_buffer);    // bytetrack.cpp:141-142
+    e->e_cap = 4096;
+    e->smem_bytes = mot::bt_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap);
+    int max_optin = 0;
+    MOT_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
+    if (e->smem_bytes > (size_t)max_optin) {
+        const size_t need = e->smem_bytes;
+        delete e;
+        return fail(MOT_ERR_INVALID_ARGUMENT, "track_capacity/max_dets need %zu B of shared memory per CTA (limit %d)",
+                    need, max_optin);
+    }
+    MOT_CUDA(cudaFuncSetAttribute(mot::bytetrack_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)e->smem_bytes));
+    e->n_chunks = cfg->n_chunks > 0 ? std::min(cfg->n_chunks, kMaxChunks) : (cfg->n_streams >= 64 ? 4 : 1);
+    e->n_chunks = std::min(e->n_chunks, cfg->n_streams);
+    for (int c = 0; c < e->n_chunks; ++c) MOT_CUDA(cudaStreamCreateWithFlags(&e->streams[c], cudaStreamNonBlocking));
+    MOT_CUDA(cudaMalloc(&e->d_state, e->layout.stride * (size_t)cfg->n_streams));
+    MOT_CUDA(cudaMemsetAsync(e->d_state, 0, e->layout.stride * (size_t)cfg->n_streams, e->streams[0]));
+    if (int rc = engine_reset_impl(e, 0)) { mot_engine_destroy(e); return rc; }
+    *out = e;
+    return MOT_OK;
+}
+
+int mot_engine_destroy(mot_engine* e) {
+    if (!e) return MOT_OK;
+    cudaSetDevice(e->cfg.device);
+    for (int c = 0; c < kMaxChunks; ++c)
+        if (e->streams[c]) cudaStreamDestroy(e->streams[c]);
+    cudaFree(e->d_state); cudaFree(e->d_dets); cudaFree(e->d_ndets); cudaFree(e->d_out); cudaFree(e->d_nout);
+    delete e;
+    return MOT_OK;
+}
+
+int mot_engine_reset(mot_engine* e) {
+    if (!e) return fail(MOT_ERR_INVALID_ARGUMENT, "null engine");
+    MOT_CUDA(cudaSetDevice(e->cfg.device));
+    for (int c = 0; c < e->n_chunks; ++c) MOT_CUDA(cudaStreamSynchronize(e->streams[c]));
+    return engine_reset_impl(e, /*keep_ids=*/1);
+}
+
+int mot_engine_update_device(mot_engine* e, int T, const float* d_dets, const int* d_n_dets, int ld_dets,
+                             float* d_out, int* d_n_out, int ld_out, void* stream) {
+    if (!e || !d_dets || !d_n_dets || !d_out || !d_n_out) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
+    if (T <= 0 || ld_dets <= 0 || ld_out <= 0) return fail(MOT_ERR_INVALID_ARGUMENT, "non-positive size");
+    if ((ld_out * 8 * sizeof(float)) % 16 != 0 || (((size_t)d_out) & 15)) return fail(MOT_ERR_INVALID_ARGUMENT, "out must be 16-byte aligned");
+    const int S = e->cfg.n_streams;
+    mot::BtArgs a = make_args(e, T, d_dets, d_n_dets, ld_dets, d_out, d_n_out, ld_out, 0, S);
+    mot::bytetrack_step_kernel<<<S, mot::kBtThreads, e->smem_bytes, (cudaStream_t)stream>>>(a);
+    MOT_CUDA(cudaGetLastError());
+    return MOT_OK;
+}
+
+int mot_engine_update_host(mot_engine* e, int T, const float* dets, const int* n_dets, int ld_dets, float* out,
+                           int* n_out, int ld_out) {
+    if (!e || !dets || !n_dets || !out || !n_out) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
+    if (T <= 0 || ld_dets <= 0 || ld_out <= 0) return fail(MOT_ERR_INVALID_ARGUMENT, "non-positive size");
+    MOT_CUDA(cudaSetDevice(e->cfg.device));
+    const int S = e->cfg.n_streams;
+    const size_t TS = (size_t)T * S;
+    if (int rc = grow(&e->d_dets, &e->dets_cap, TS * ld_dets * 6)) return rc;
+    if (int rc = grow(&e->d_ndets, &e->ndets_cap, TS)) return rc;
+    if (int rc = grow(&e->d_out, &e->out_cap, TS * ld_out * 8)) return rc;
+    if (int rc = grow(&e->d_nout, &e->nout_cap, TS)) return rc;
+    const int C = e->n_chunks;
+    for (int c = 0; c < C; ++c) {
+        const int s0 = (int)((long long)S * c / C), s1 = (int)((long long)S * (c + 1) / C);
+        if (s1 <= s0) continue;
+        cudaStream_t st = e->streams[c];
+        const size_t det_row = (size_t)ld_dets * 6 * sizeof(float), out_row = (size_t)ld_out * 8 * sizeof(float);
+        // [T][S][...] -> a (T x chunk) sub-block is a 2-D copy with pitch S * row
+        MOT_CUDA(cudaMemcpy2DAsync(e->d_dets + (size_t)s0 * ld_dets * 6, S * det_row, dets + (size_t)s0 * ld_dets * 6,
+                                   S * det_row, (s1 - s0) * det_row, T, cudaMemcpyHostToDevice, st));
+        MOT_CUDA(cudaMemcpy2DAsync(e->d_ndets + s0, S * sizeof(int), n_dets + s0, S * sizeof(int),
+                                   (s1 - s0) * sizeof(int), T, cudaMemcpyHostToDevice, st));
+        mot::BtArgs a = make_args(e, T, e->d_dets, e->d_ndets, ld_dets, e->d_out, e->d_nout, ld_out, s0, s1);
+        mot::bytetrack_step_kernel<<<s1 - s0, mot::kBtThreads, e->smem_bytes, st>>>(a);
+        MOT_CUDA(cudaGetLastError());
+        MOT_CUDA(cudaMemcpy2DAsync(out + (size_t)s0 * ld_out * 8, S * out_row, e->d_out + (size_t)s0 * ld_out * 8,
+                                   S * out_row, (s1 - s0) * out_row, T, cudaMemcpyDeviceToHost, st));
+        MOT_CUDA(cudaMemcpy2DAsync(n_out + s0, S * sizeof(int), e->d_nout + s0, S * sizeof(int),
+                                   (s1 - s0) * sizeof(int), T, cudaMemcpyDeviceToHost, st));
+    }
+    for (int c = 0; c < C; ++c) MOT_CUDA(cudaStreamSynchronize(e->streams[c]));
+    return MOT_OK;
+}
+
+int mot_engine_check(mot_engine* e, int* flags) {
+    if (!e) return fail(MOT_ERR_INVALID_ARGUMENT, "null engine");
+    MOT_CUDA(cudaSetDevice(e->cfg.device));
+    MOT_CUDA(cudaDeviceSynchronize());
+    const int S = e->cfg.n_streams;
+    std::vector<int> err(S);
+    MOT_CUDA(cudaMemcpy2D(err.data(), sizeof(int), e->d_state + sizeof(int) * mot::kHdrError, e->layout.stride,
+                          sizeof(int), S, cudaMemcpyDeviceToHost));
+    int all = 0;
+    for (int s = 0; s < S; ++s) { all |= err[s]; if (flags) flags[s] = err[s]; }
+    if (all & (mot::kErrCapacity | mot::kErrTooManyDets | mot::kErrOutput))
+        return fail(MOT_ERR_CAPACITY, "engine capacity exceeded (flags 0x%x: 1 track slots, 2 detections, 4 output rows)", all);
+    if (all & mot::kErrKalman) return fail(MOT_ERR_NUMERIC, "a Kalman update left the Cholesky path");
+    return MOT_OK;
+}
+
+int mot_engine_stream_header(mot_engine* e, int s, int* hdr16) {
+    if (!e || !hdr16 || s < 0 || s >= e->cfg.n_streams) return fail(MOT_ERR_INVALID_ARGUMENT, "bad argument");
+    MOT_CUDA(cudaSetDevice(e->cfg.device));
+    MOT_CUDA(cudaDeviceSynchronize());
+    MOT_CUDA(cudaMemcpy(hdr16, e->d_state + (size_t)s * e->layout.stride, sizeof(int) * mot::kHdrInts, cudaMemcpyDeviceToHost));
+    return MOT_OK;
+}
+
+int mot_engine_dump_list(mot_engine* e, int s, int which, float* rows, int cap_rows, int* n_rows) {
+    if (!e || !rows || !n_rows || s < 0 || s >= e->cfg.n_streams) return fail(MOT_ERR_INVALID_ARGUMENT, "bad argument");
+    MOT_CUDA(cudaSetDevice(e->cfg.device));
+    MOT_CUDA(cudaDeviceSynchronize());
+    std::vector<unsigned char> slab(e->layout.off_gscratch);
+    MOT_CUDA(cudaMemcpy(slab.data(), e->d_state + (size_t)s * e->layout.stride, slab.size(), cudaMemcpyDeviceToHost));
+    const mot::BtLayout& L = e->layout;
+    const int* hdr = (const int*)slab.data();
+    const unsigned short* list = (const unsigned short*)(slab.data() + L.off_lists) + (which == 0 ? 0 : L.cap);
+    const int n = which == 0 ? hdr[mot::kHdrActive] : hdr[mot::kHdrLost];
+    const unsigned char* sflag = slab.data() + L.off_sflag;
+    const int* meta = (const int*)(slab.data() + L.off_meta);
+    const float* recs = (const float*)(slab.data() + L.off_recs);
+    int k = 0;
+    for (; k < n && k < cap_rows; ++k) {
+        const int slot = list[k];
+        float* o = rows + 78 * (size_t)k;
+        o[0] = (float)meta[slot]; o[1] = (float)(sflag[slot] & 0x0f); o[2] = (sflag[slot] & 0x10) ? 1.0f : 0.0f;
+        o[3] = (float)meta[2 * L.cap + slot]; o[4] = (float)meta[3 * L.cap + slot]; o[5] = (float)meta[L.cap + slot];
+        std::memcpy(o + 6, recs + (size_t)slot * mot::kRecFloats, sizeof(float) * mot::kRecFloats);
+    }
+    *n_rows = k;
+    return MOT_OK;
+}
+
+int mot_engine_info(mot_engine* e, int* threads, int* smem, int* ctas, int* state_bytes) {
+    if (!e) return fail(MOT_ERR_INVALID_ARGUMENT, "null engine");
+    if (threads) *threads = mot::kBtThreads;
+    if (smem) *smem = (int)e->smem_bytes;
+    if (ctas) *ctas = e->cfg.n_streams;
+    if (state_bytes) *state_bytes = (int)e->layout.stride;
+    return MOT_OK;
+}
+
+// ------------------------------------------------------------------------------ standalone kernels
+int mot_kf_initiate(int kind, float* recs, const float* z, long long n, void* stream) {
+    if (!recs || !z || n < 0) return fail(MOT_ERR_INVALID_ARGUMENT, "bad argument");
+    if (int rc = require_device()) return rc;
+    if (n == 0) return MOT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (kind) {
+        case mot::kKfXYAH: mot::kf_initiate_kernel<mot::kKfXYAH><<<kf_grid(n), 256, 0, st>>>(recs, z, n); break;
+        case mot::kKfXYSR: mot::kf_initiate_kernel<mot::kKfXYSR><<<kf_grid(n), 256, 0, st>>>(recs, z, n); break;
+        case mot::kKfXYWH: mot::kf_initiate_kernel<mot::kKfXYWH><<<kf_grid(n), 256, 0, st>>>(recs, z, n); break;
+        default: return fail(MOT_ERR_INVALID_ARGUMENT, "unknown Kalman kind %d", kind);
+    }
+    MOT_CUDA(cudaGetLastError());
+    return MOT_OK;
+}
+
+int mot_kf_predict(int kind, float* recs, const unsigned char* flags, long long n, float q_xy, float q_s, void* stream) {
+    if (!recs || n < 0) return fail(MOT_ERR_INVALID_ARGUMENT, "bad argument");
+    if (int rc = require_device()) return rc;
+    if (n == 0) return MOT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const float q44 = 0.01f * q_xy, q66 = 0.0001f * q_s;     // xysr_kf.cpp:58-61 then ocsort.cpp:77-79, in fp32
+    switch (kind) {
+        case mot::kKfXYAH: mot::kf_predict_kernel<mot::kKfXYAH><<<kf_grid(n), 256, 0, st>>>(recs, flags, n, q44, q66); break;
+        case mot::kKfXYSR: mot::kf_predict_kernel<mot::kKfXYSR><<<kf_grid(n), 256, 0, st>>>(recs, flags, n, q44, q66); break;
+        case mot::kKfXYWH: mot::kf_predict_kernel<mot::kKfXYWH><<<kf_grid(n), 256, 0, st>>>(recs, flags, n, q44, q66); break;
+        default: return fail(MOT_ERR_INVALID_ARGUMENT, "unknown Kalman kind %d", kind);
+    }
+    MOT_CUDA(cudaGetLastError());
+    return MOT_OK;
+}
+
+int mot_kf_update(int kind, float* recs, const float* z, const float* conf, long long n, unsigned char* failflags,
+                  void* stream) {
+    if (!recs || !z || n < 0) return fail(MOT_ERR_INVALID_ARGUMENT, "bad argument");
+    if (int rc = require_device()) return rc;
+    if (n == 0) return MOT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (kind) {
+        case mot::kKfXYAH: mot::kf_update_kernel<mot::kKfXYAH><<<kf_grid(n), 256, 0, st>>>(recs, z, conf, n, failflags); break;
+        case mot::kKfXYSR: mot::kf_update_kernel<mot::kKfXYSR><<<kf_grid(n), 256, 0, st>>>(recs, z, conf, n, failflags); break;
+        case mot::kKfXYWH: mot::kf_update_kernel<mot::kKfXYWH><<<kf_grid(n), 256, 0, st>>>(recs, z, conf, n, failflags); break;
+        default: return fail(MOT_ERR_INVALID_ARGUMENT, "unknown Kalman kind %d", kind);
+    }
+    MOT_CUDA(cudaGetLastError());
+    return MOT_OK;
+}
+
+int mot_kf_gating(int kind, const float* recs, int n_tracks, const float* meas, int n_meas, int only_position,
+                  int metric, float* out, void* stream) {
+    if (!recs || !meas || !out || n_tracks < 0 || n_meas < 0) return fail(MOT_ERR_INVALID_ARGUMENT, "bad argument");
+    if (int rc = require_device()) return rc;
+    if (n_tracks == 0 || n_meas == 0) return MOT_OK;
+    if (kind == mot::kKfXYAH && metric != 0 && metric != 1)
+        return fail(MOT_ERR_INVALID_ARGUMENT, "Invalid metric: %d", metric);     // kalman_filter.cpp:174
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)n_tracks * n_meas;
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)sm_count() * 16));
+    if (kind == mot::kKfXYAH)
+        mot::kf_gating_kernel<mot::kKfXYAH><<<blocks, 256, 0, st>>>(recs, n_tracks, meas, n_meas, only_position, metric, out);
+    else if (kind == mot::kKfXYWH)
+        mot::kf_gating_kernel<mot::kKfXYWH><<<blocks, 256, 0, st>>>(recs, n_tracks, meas, n_meas, only_position, metric, out);
+    else
+        return fail(MOT_ERR_INVALID_ARGUMENT, "gating is defined for XYAH (0) and XYWH (2) only");
+    MOT_CUDA(cudaGetLastError());
+    return MOT_OK;
+}
+
+int mot_cost_iou(const float* a, int n, const float* b, int m, const float* conf, float* out, int ld, int mode,
+                 void* stream) {
+    if (n < 0 || m < 0 || ld < m) return fail(MOT_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (n == 0 || m == 0) return MOT_OK;
+    if (!a || !b || !out) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
+    if (mode == mot::kCostIouDistanceFused && !conf) return fail(MOT_ERR_INVALID_ARGUMENT, "fuse_score needs det confidences");
+    if (mode < 0 || mode > 2) return fail(MOT_ERR_INVALID_ARGUMENT, "unknown mode %d", mode);
+    if (int rc = require_device()) return rc;
+    const int col_tiles = (m + mot::kCostTileCols - 1) / mot::kCostTileCols;
+    const int row_groups = (n + mot::kCostTileRows - 1) / mot::kCostTileRows;
+    dim3 grid((unsigned)std::min(row_groups, sm_count() * 8), (unsigned)std::min(col_tiles, 64));
+    mot::iou_cost_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, n, b, m, conf, out, ld, mode);
+    MOT_CUDA(cudaGetLastError());
+    return MOT_OK;
+}
+
+int mot_cost_cosine(const float* t, int n, const float* d, int m, int dim, float* out, int ld, void* stream) {
+    if (n < 0 || m < 0 || dim <= 0 || ld < m) return fail(MOT_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (n == 0 || m == 0) return MOT_OK;
+    if (!t || !d || !out) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
+    if (int rc = require_device()) return rc;
+    std::string err;
+    const int rc = mot::launch_cosine(t, n, d, m, dim, out, ld, (cudaStream_t)stream, err);
+    if (rc != MOT_OK) return fail(rc, "%s", err.c_str());
+    return MOT_OK;
+}
+
+int mot_lap_batch_device(const float* cost, long long stride_cost, int n_problems, const int* n_rows,
+                         const int* n_cols, int n, int m, int ld, float thresh, int* row2col, int* col2row,
+                         void* stream) {
+    if (n < 0 || m < 0 || n_problems < 0 || (m > 0 && ld < m)) return fail(MOT_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (n > 32767 || m > 32767) return fail(MOT_ERR_INVALID_ARGUMENT, "n, m above 32767 are not supported");
+    if (int rc = require_device()) return rc;
+    if (n_problems == 0) return MOT_OK;
+    if (!row2col || !col2row) return fail(MOT_ERR_INVALID_ARGUMENT, "null result pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0 || m == 0) {
+        if (n) MOT_CUDA(cudaMemsetAsync(row2col, 0xff, sizeof(int) * (size_t)n * n_problems, st));
+        if (m) MOT_CUDA(cudaMemsetAsync(col2row, 0xff, sizeof(int) * (size_t)m * n_problems, st));
+        return MOT_OK;
+    }
+    if (!cost) return fail(MOT_ERR_INVALID_ARGUMENT, "null cost pointer");
+    int dev = 0, max_optin = 0;
+    MOT_CUDA(cudaGetDevice(&dev));
+    MOT_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    int e_cap = 8192;
+    size_t smem = mot::lap_smem_bytes(n, m, e_cap);
+    while (smem > (size_t)max_optin && e_cap > 1024) { e_cap /= 2; smem = mot::lap_smem_bytes(n, m, e_cap); }
+    if (smem > (size_t)max_optin)
+        return fail(MOT_ERR_INVALID_ARGUMENT, "problem %d x %d needs %zu B of shared memory (limit %d)", n, m, smem, max_optin);
+    MOT_CUDA(cudaFuncSetAttribute(mot::lap_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unsigned char* gs = nullptr;
+    const size_t gs_bytes = mot::lap_gscratch_bytes(n, m);
+    const int grid = std::min(n_problems, sm_count() * 4);
+    MOT_CUDA(cudaMallocAsync((void**)&gs, gs_bytes * (size_t)n_problems, st));
+    mot::LapBatchArgs a{};
+    a.cost = cost; a.stride_cost = stride_cost; a.n_rows = n_rows; a.n_cols = n_cols;
+    a.n = n; a.m = m; a.ld = ld; a.thresh = thresh; a.row2col = row2col; a.col2row = col2row;
+    a.gscratch = gs; a.n_max = n; a.m_max = m; a.e_cap = e_cap; a.n_problems = n_problems;
+    mot::lap_dense_kernel<<<grid, 256, smem, st>>>(a);
+    MOT_CUDA(cudaGetLastError());
+    MOT_CUDA(cudaFreeAsync(gs, st));
+    return MOT_OK;
+}
+
+int mot_lap_device(const float* cost, int n, int m, int ld, float thresh, int* row2col, int* col2row, void* stream) {
+    return mot_lap_batch_device(cost, 0, 1, nullptr, nullptr, n, m, ld, thresh, row2col, col2row, stream);
+}
+
+int mot_lap_host(const float* cost, int n, int m, int ld, float thresh, int* row2col, int* col2row) {
+    if (n < 0 || m < 0) return fail(MOT_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (int rc = require_device()) return rc;
+    for (int i = 0; i < n; ++i) row2col[i] = -1;
+    for (int j = 0; j < m; ++j) col2row[j] = -1;
+    if (n == 0 || m == 0) return MOT_OK;                      // matching.cpp:20-28
+    float* d_cost = nullptr; int *d_r = nullptr, *d_c = nullptr;
+    MOT_CUDA(cudaMalloc(&d_cost, sizeof(float) * (size_t)n * ld));
+    MOT_CUDA(cudaMalloc(&d_r, sizeof(int) * n));
+    MOT_CUDA(cudaMalloc(&d_c, sizeof(int) * m));
+    MOT_CUDA(cudaMemcpy(d_cost, cost, sizeof(float) * (size_t)n * ld, cudaMemcpyHostToDevice));
+    int rc = mot_lap_device(d_cost, n, m, ld, thresh, d_r, d_c, nullptr);
+    if (rc == MOT_OK) {
+        MOT_CUDA(cudaMemcpy(row2col, d_r, sizeof(int) * n, cudaMemcpyDeviceToHost));
+        MOT_CUDA(cudaMemcpy(col2row, d_c, sizeof(int) * m, cudaMemcpyDeviceToHost));
+    }
+    cudaFree(d_cost); cudaFree(d_r); cudaFree(d_c);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,97 @@
+// cost_device.cuh - box conversions and IoU-family cost functors (exact fp32, reference op order).
+//   conversions  reference include/motcpp/utils/ops.hpp:15-211
+//   iou_batch    reference include/motcpp/utils/iou.hpp:63-100
+//   iou_distance reference src/utils/matching.cpp:62-65
+//   fuse_score   reference src/utils/matching.cpp:130-143
+#pragma once
+#include "simt.cuh"
+
+namespace mot {
+
+// xyxy -> xywh (ops.hpp:15-22)
+__device__ __forceinline__ float4 xyxy2xywh(float4 b) {
+    const float w = xsub(b.z, b.x), h = xsub(b.w, b.y);
+    return make_float4(xadd(b.x, xmul(w, 0.5f)), xadd(b.y, xmul(h, 0.5f)), w, h);
+}
+// xywh -> xyxy (ops.hpp:27-34)
+__device__ __forceinline__ float4 xywh2xyxy(float4 b) {
+    const float hw = xmul(b.z, 0.5f), hh = xmul(b.w, 0.5f);
+    return make_float4(xsub(b.x, hw), xsub(b.y, hh), xadd(b.x, hw), xadd(b.y, hh));
+}
+// xywh -> tlwh -> xyah (ops.hpp:39-44, 78-85), the chain STrack's ctor runs (bytetrack.cpp:26-29)
+__device__ __forceinline__ float4 xywh2xyah_via_tlwh(float4 b) {
+    const float t = xsub(b.x, xmul(b.z, 0.5f)), l = xsub(b.y, xmul(b.w, 0.5f));
+    const float a = (b.w > 0.0f) ? xdiv(b.z, b.w) : 0.0f;
+    return make_float4(xadd(t, xmul(b.z, 0.5f)), xadd(l, xmul(b.w, 0.5f)), a, b.w);
+}
+// xyah -> xywh -> xyxy (ops.hpp:108-112, 27-34): STrack::xyxy() (bytetrack.cpp:118-128)
+__device__ __forceinline__ float4 xyah2xyxy(float x, float y, float a, float h) {
+    return xywh2xyxy(make_float4(x, y, xmul(a, h), h));
+}
+// xyxy -> xysr (ops.hpp:188-197)
+__device__ __forceinline__ float4 xyxy2xysr(float4 b) {
+    const float w = xsub(b.z, b.x), h = xsub(b.w, b.y);
+    return make_float4(xadd(b.x, xmul(w, 0.5f)), xadd(b.y, xmul(h, 0.5f)), xmul(w, h),
+                       (h > 1e-6f) ? xdiv(w, h) : 0.0f);
+}
+// xysr -> xyxy (ops.hpp:202-211)
+__device__ __forceinline__ float4 xysr2xyxy(float x, float y, float s, float r) {
+    const float w = xsqrt(xmul(s, r));
+    const float h = xdiv(s, w);
+    const float hw = xmul(w, 0.5f), hh = xmul(h, 0.5f);
+    return make_float4(xsub(x, hw), xsub(y, hh), xadd(x, hw), xadd(y, hh));
+}
+
+__device__ __forceinline__ float box_area(float4 b) { return xmul(xsub(b.z, b.x), xsub(b.w, b.y)); }
+
+// iou.hpp:81-98 for one pair; area_a precomputed
+__device__ __forceinline__ float iou_pair(float4 a, float area_a, float4 b) {
+    const float area_b = box_area(b);
+    const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+    const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+    const float w = fmaxf(0.0f, xsub(xx2, xx1));
+    const float h = fmaxf(0.0f, xsub(yy2, yy1));
+    const float inter = xmul(w, h);
+    const float uni = xsub(xadd(area_a, area_b), inter);
+    return (uni > 0.0f) ? xdiv(inter, uni) : 0.0f;
+}
+
+// true => the boxes share no interior => IoU is exactly 0
+__device__ __forceinline__ bool boxes_disjoint(float4 a, float4 b) {
+    return !((fminf(a.z, b.z) > fmaxf(a.x, b.x)) && (fminf(a.w, b.w) > fmaxf(a.y, b.y)));
+}
+
+// Cost functor for block_lap(): rows = row_box[i], columns = det_box[col_map[j]];
+// cost = 1 - IoU, optionally fused with the detection score: 1 - (1 - d) * conf.
+// `prune` must only be set when thresh < 1 (a disjoint pair costs exactly 1).
+struct IouCost {
+    static constexpr bool kWarpPerRow = false;
+    const float4* row_box;
+    const float4* det_box;
+    const float* det_conf;
+    const unsigned short* col_map;
+    bool fuse;
+    bool prune;
+    struct Row { float4 b; float area; };
+    __device__ __forceinline__ Row row(int i) const {
+        Row r;
+        r.b = row_box[i];
+        r.area = box_area(r.b);
+        return r;
+    }
+    __device__ __forceinline__ bool reject(const Row& r, int j) const {
+        return prune && boxes_disjoint(r.b, det_box[col_map[j]]);
+    }
+    __device__ __forceinline__ float cost(const Row& r, int j) const {
+        const int d = col_map[j];
+        float dist = xsub(1.0f, iou_pair(r.b, r.area, det_box[d]));
+        if (fuse) {
+            const float sim = xsub(1.0f, dist);
+            dist = xsub(1.0f, xmul(sim, det_conf[d]));
+        }
+        return dist;
+    }
+    __device__ __forceinline__ float pair(int i, int j) const { return cost(row(i), j); }
+};
+
+}  // namespace mot

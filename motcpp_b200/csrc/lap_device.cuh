@@ -242,16 +242,37 @@ __device__ void block_lap(const LapWorkspace& ws, int n, int m, int n_max, int m
     __syncthreads();
     if (n == 0 || m == 0) return;
 
-    // ---- 1. candidate pairs
-    for (int i = tid; i < n; i += nt) {
-        const typename Cost::Row rw = cost.row(i);
-        for (int j = 0; j < m; ++j) {
-            if (cost.reject(rw, j)) continue;
-            const float cf = cost.cost(rw, j);
-            if (cf <= thresh) {
-                const int e = atomicAdd(&ws.ctl[0], 1);
-                if (e < ws.e_cap) ws.scratch_a[e] = (i << 16) | j;
-                else ws.ctl[1] = 1;
+    // ---- 1. candidate pairs.  Costs that live in shared memory / registers are scanned one row per
+    //         thread; a dense matrix in global memory is scanned one row per warp so loads coalesce.
+    if (Cost::kWarpPerRow) {
+        for (int i = warp; i < n; i += nwarps) {
+            const typename Cost::Row rw = cost.row(i);
+            for (int j0 = 0; j0 < m; j0 += 32) {
+                const int j = j0 + lane;
+                const bool cand = (j < m) && (cost.cost(rw, j) <= thresh);
+                const unsigned ballot = __ballot_sync(kFullMask, cand);
+                if (ballot == 0) continue;
+                int e0 = 0;
+                if (lane == 0) e0 = atomicAdd(&ws.ctl[0], __popc(ballot));
+                e0 = __shfl_sync(kFullMask, e0, 0);
+                if (cand) {
+                    const int e = e0 + __popc(ballot & ((1u << lane) - 1u));
+                    if (e < ws.e_cap) ws.scratch_a[e] = (i << 16) | j;
+                    else ws.ctl[1] = 1;
+                }
+            }
+        }
+    } else {
+        for (int i = tid; i < n; i += nt) {
+            const typename Cost::Row rw = cost.row(i);
+            for (int j = 0; j < m; ++j) {
+                if (cost.reject(rw, j)) continue;
+                const float cf = cost.cost(rw, j);
+                if (cf <= thresh) {
+                    const int e = atomicAdd(&ws.ctl[0], 1);
+                    if (e < ws.e_cap) ws.scratch_a[e] = (i << 16) | j;
+                    else ws.ctl[1] = 1;
+                }
             }
         }
     }
@@ -327,7 +348,6 @@ __device__ void block_lap(const LapWorkspace& ws, int n, int m, int n_max, int m
         if (r + c <= 32) warp_hungarian_small(rows, r, cols, c, thresh, cost, ws.row2col, ws.col2row);
         else warp_hungarian_big(ws, m_max, n_max, rows, r, pr, cols, c, pc, thresh, cost, ws.row2col, ws.col2row);
     }
-    (void)warp; (void)nwarps;
     __syncthreads();
 }
 
@@ -397,6 +417,7 @@ __device__ __forceinline__ void lap_carve_gscratch(unsigned char* g, int n_max, 
 
 // Dense-matrix cost: the standalone mot_lap() entry point (row-major fp32, leading dimension ld).
 struct MatrixCost {
+    static constexpr bool kWarpPerRow = true;
     const float* c;
     int ld;
     struct Row { const float* p; };

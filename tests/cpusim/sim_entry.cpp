@@ -25,3 +25,76 @@ int sim_lap(const float* cost, int n, int m, int ld, float thresh, int* row2col,
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ ByteTrack engine under the emulator
+#include "../../motcpp_b200/csrc/bytetrack_kernel.cuh"
+
+namespace {
+struct SimBt {
+    mot::BtLayout L;
+    int S, e_cap;
+    mot::BtParams p;
+    std::vector<unsigned char> state;
+};
+}  // namespace
+
+extern "C" {
+
+void* sim_bt_create(int S, int cap, int d_max, int e_cap, float min_conf, float track_thresh, float match_thresh,
+                    int track_buffer, int frame_rate) {
+    auto* h = new SimBt();
+    h->L = mot::BtLayout::make(cap, d_max);
+    h->S = S; h->e_cap = e_cap;
+    h->p.min_conf = min_conf; h->p.track_thresh = track_thresh; h->p.match_thresh = match_thresh;
+    h->p.det_thresh = track_thresh;
+    h->p.max_time_lost = (int)(frame_rate / 30.0f * track_buffer);
+    h->state.assign(h->L.stride * (size_t)S + 256, 0);
+    unsigned char* st = h->state.data();
+    const mot::BtLayout L = h->L;
+    cpusim::launch(dim3(S), dim3(64), 0, [=] { mot::bytetrack_reset_kernel(st, L, S, 0); });
+    return h;
+}
+void sim_bt_destroy(void* hv) { delete (SimBt*)hv; }
+
+int sim_bt_update(void* hv, const float* dets, const int* n_dets, int T, int ld_dets, float* out, int* n_out,
+                  int ld_out, int threads, int os_threads) {
+    auto* h = (SimBt*)hv;
+    mot::BtArgs a{};
+    a.state = h->state.data(); a.layout = h->L;
+    a.dets = dets; a.n_dets = n_dets; a.out = out; a.n_out = n_out;
+    a.T = T; a.S = h->S; a.ld_dets = ld_dets; a.ld_out = ld_out; a.e_cap = h->e_cap; a.p = h->p; a.s_begin = 0; a.s_end = h->S;
+    const size_t smem = mot::bt_smem_bytes(h->L.cap, h->L.d_max, h->e_cap);
+    cpusim::launch(dim3(h->S), dim3(threads), smem, [=] { mot::bytetrack_step_kernel(a); }, os_threads);
+    return 0;
+}
+
+// header (16 ints) of stream s
+void sim_bt_header(void* hv, int s, int* hdr16) {
+    auto* h = (SimBt*)hv;
+    std::memcpy(hdr16, h->state.data() + (size_t)s * h->L.stride, sizeof(int) * mot::kHdrInts);
+}
+
+// rows of [id, state, activated, frame_id, start_frame, tracklet_len, mean 8, cov 64] for list `which`
+int sim_bt_dump(void* hv, int s, int which, float* outrows, int cap_rows) {
+    auto* h = (SimBt*)hv;
+    unsigned char* base = h->state.data() + (size_t)s * h->L.stride;
+    const int* hdr = (const int*)base;
+    const unsigned short* lists = (const unsigned short*)(base + h->L.off_lists);
+    const unsigned short* list = lists + (which == 0 ? 0 : h->L.cap);
+    const int n = which == 0 ? hdr[mot::kHdrActive] : hdr[mot::kHdrLost];
+    const unsigned char* sflag = base + h->L.off_sflag;
+    const int* meta = (const int*)(base + h->L.off_meta);
+    const float* recs = (const float*)(base + h->L.off_recs);
+    const int cap = h->L.cap;
+    int k = 0;
+    for (; k < n && k < cap_rows; ++k) {
+        const int slot = list[k];
+        float* o = outrows + 78 * k;
+        o[0] = (float)meta[slot]; o[1] = (float)(sflag[slot] & 0x0f); o[2] = (sflag[slot] & 0x10) ? 1.0f : 0.0f;
+        o[3] = (float)meta[2 * cap + slot]; o[4] = (float)meta[3 * cap + slot]; o[5] = (float)meta[cap + slot];
+        std::memcpy(o + 6, recs + (size_t)slot * mot::kRecFloats, sizeof(float) * mot::kRecFloats);
+    }
+    return k;
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+"""ctypes loader for tests/cpusim/libmotb200_cpusim.so: the product's kernel sources compiled
+against the SIMT emulator.  TEST INFRASTRUCTURE (kernel-logic unit tests without a GPU)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SIM_DIR = os.path.join(HERE, "cpusim")
+f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        subprocess.check_call(["make", "-C", SIM_DIR, "-s"], stdout=subprocess.DEVNULL)
+        S = C.CDLL(os.path.join(SIM_DIR, "libmotb200_cpusim.so"))
+        S.sim_lap.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_float, i32p, i32p, C.c_int, C.c_int]
+        S.sim_bt_create.argtypes = [C.c_int] * 4 + [C.c_float] * 3 + [C.c_int] * 2
+        S.sim_bt_create.restype = C.c_void_p
+        S.sim_bt_update.argtypes = [C.c_void_p, f32p, i32p, C.c_int, C.c_int, f32p, i32p, C.c_int, C.c_int, C.c_int]
+        S.sim_bt_header.argtypes = [C.c_void_p, C.c_int, i32p]
+        S.sim_bt_dump.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, C.c_int]
+        S.sim_bt_dump.restype = C.c_int
+        S.sim_bt_destroy.argtypes = [C.c_void_p]
+        _LIB = S
+    return _LIB
+
+
+def sim_lap(cost, thresh, e_cap=4096, threads=128):
+    cost = np.ascontiguousarray(cost, np.float32)
+    n, m = cost.shape
+    r = np.full(max(n, 1), -7, np.int32)
+    q = np.full(max(m, 1), -7, np.int32)
+    lib().sim_lap(cost, n, m, max(m, 1), float(thresh), r, q, e_cap, threads)
+    return r[:n], q[:m]
+
+
+class SimByteTrack:
+    def __init__(self, n_streams=1, cap=256, d_max=64, e_cap=4096, min_conf=0.1, track_thresh=0.45,
+                 match_thresh=0.8, track_buffer=30, frame_rate=30):
+        self.S, self.cap, self.d_max = n_streams, cap, d_max
+        self.h = lib().sim_bt_create(n_streams, cap, d_max, e_cap, min_conf, track_thresh, match_thresh,
+                                     track_buffer, frame_rate)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().sim_bt_destroy(self.h)
+            self.h = None
+
+    def update(self, dets, n_dets, threads=128, os_threads=1):
+        """dets (T,S,ld,6), n_dets (T,S) -> out (T,S,cap,8), n_out (T,S)"""
+        dets = np.ascontiguousarray(dets, np.float32)
+        T, S, ld, _ = dets.shape
+        n_dets = np.ascontiguousarray(n_dets, np.int32).reshape(T, S)
+        out = np.zeros((T, S, self.cap, 8), np.float32)
+        n_out = np.zeros((T, S), np.int32)
+        lib().sim_bt_update(self.h, dets, n_dets, T, ld, out, n_out, self.cap, threads, os_threads)
+        return out, n_out
+
+    def header(self, s=0):
+        h = np.zeros(16, np.int32)
+        lib().sim_bt_header(self.h, s, h)
+        return h
+
+    def dump(self, s, which):
+        buf = np.zeros((max(self.cap, 1), 78), np.float32)
+        k = lib().sim_bt_dump(self.h, s, which, buf, self.cap)
+        return buf[:k]

@@ -1,0 +1,100 @@
+"""Kernel LOGIC under the SIMT emulator (tests/cpusim): the same .cuh sources the product builds
+with nvcc, run fiber-per-thread on the CPU and compared bit-for-bit with the oracle.  Small sizes
+only; the real parity tests are the -m gpu ones."""
+import numpy as np
+import pytest
+
+import sim_lib
+from motcpp_b200 import synth
+
+
+def _rand_cost(rng, kind):
+    if kind == 0:
+        n, m = rng.integers(1, 12, 2)
+        return rng.random((n, m)).astype(np.float32), 0.5
+    if kind == 1:
+        n, m = rng.integers(5, 60, 2)
+        return np.where(rng.random((n, m)) < 0.9, 1.0, rng.random((n, m))).astype(np.float32), 0.8
+    if kind == 2:                       # dense: one big component -> global-scratch solver
+        n, m = rng.integers(20, 50, 2)
+        return rng.random((n, m)).astype(np.float32), 0.7
+    if kind == 3:
+        n, m = rng.integers(30, 200, 2)
+        return np.where(rng.random((n, m)) < 0.985, 1.0, rng.random((n, m))).astype(np.float32), 0.8
+    n, m = rng.integers(1, 40, 2)
+    return -(rng.random((n, m)) * 1.3).astype(np.float32), -0.3
+
+
+def test_block_lap_matches_oracle(oracle):
+    rng = np.random.default_rng(1)
+    for trial in range(150):
+        c, th = _rand_cost(rng, trial % 5)
+        e_cap = 4096 if trial % 7 else 16          # tiny edge buffer -> overflow (single component) path
+        got = sim_lib.sim_lap(c, th, e_cap, [32, 64, 128, 256][trial % 4])
+        ref = oracle.linear_assignment(c, th)
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]), (trial, c.shape)
+
+
+def test_block_lap_empty_sides():
+    r, c = sim_lib.sim_lap(np.zeros((0, 5), np.float32), 0.5)
+    assert r.size == 0 and np.all(c == -1)
+    r, c = sim_lib.sim_lap(np.zeros((4, 0), np.float32), 0.5)
+    assert c.size == 0 and np.all(r == -1)
+
+
+def _run_stream(oracle, dets, counts, cap, d_max, threads, e_cap=4096):
+    T = dets.shape[0]
+    sim = sim_lib.SimByteTrack(1, cap, d_max, e_cap, 0.1, 0.45, 0.8, 30, 30)
+    ref = oracle.ByteTrack(0.3, 30, 50, 3, 0.3, 0.1, 0.45, 0.8, 30, 30)
+    for t in range(T):
+        n = int(counts[t])
+        want = ref.update(dets[t, :n])
+        out, n_out = sim.update(dets[t][None, None], np.array([[n]]), threads)
+        got = out[0, 0, :n_out[0, 0]]
+        assert got.shape == want.shape and np.array_equal(got, want), f"frame {t}"
+        assert sim.header()[5] == 0
+        if t % 10 == 0 or t == T - 1:               # full state, covariances included
+            for which in (0, 1):
+                assert np.array_equal(sim.dump(0, which), ref.dump(which)), f"frame {t} list {which}"
+    return sim.header()
+
+
+@pytest.mark.parametrize("sid,threads", [(0, 128), (1, 64), (2, 256)])
+def test_bytetrack_kernel_stress_streams(oracle, sid, threads):
+    dets, counts = synth.stress_stream(sid, n_frames=120)
+    hdr = _run_stream(oracle, dets, counts, 256, 64, threads)
+    assert hdr[4] == 120
+
+
+def test_bytetrack_kernel_detection_gaps(oracle):
+    dets, counts = synth.stress_stream(7, n_frames=130)
+    counts = counts.copy()
+    counts[40:75] = 0                              # > max_time_lost empty frames: everything expires
+    counts[100] = 0
+    _run_stream(oracle, dets, counts, 256, 64, 128)
+
+
+def test_bytetrack_kernel_edge_overflow_path(oracle):
+    dets, counts = synth.stress_stream(3, n_frames=40)
+    _run_stream(oracle, dets, counts, 256, 64, 128, e_cap=8)    # forces the dense single-component solve
+
+
+def test_bytetrack_kernel_headline_shape(oracle):
+    dets = synth.bytetrack_stream(0, n_frames=12)
+    _run_stream(oracle, dets, np.full(12, 512), 1536, 512, 256)
+
+
+def test_bytetrack_kernel_multi_stream_sequence(oracle):
+    """T frames x S streams in one launch == S oracles stepped frame by frame."""
+    S, T = 3, 25
+    streams = [synth.stress_stream(10 + s, n_frames=T) for s in range(S)]
+    ld = streams[0][0].shape[1]
+    dets = np.stack([st[0] for st in streams], 1)            # (T,S,ld,6)
+    counts = np.stack([st[1] for st in streams], 1)          # (T,S)
+    sim = sim_lib.SimByteTrack(S, 256, ld, 4096)
+    out, n_out = sim.update(dets, counts, 128, os_threads=3)
+    for s in range(S):
+        ref = oracle.ByteTrack(0.3, 30, 50, 3, 0.3, 0.1, 0.45, 0.8, 30, 30)
+        for t in range(T):
+            want = ref.update(dets[t, s, :counts[t, s]])
+            assert np.array_equal(out[t, s, :n_out[t, s]], want), (s, t)
