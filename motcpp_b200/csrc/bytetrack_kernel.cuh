@@ -202,7 +202,7 @@ __device__ __forceinline__ void bt_kalman_pairs(const BtStream& st, const float*
     }
 }
 
-__device__ void bt_frame(const BtArgs& a, const BtStream& st, const BtSmem& sm, const float* dets, int n_det_in,
+__device__ void bt_frame(const BtArgs& a, const BtStream& st, BtSmem& sm, const float* dets, int n_det_in,
                          float* out, int* n_out) {
     const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
     const int cap = a.layout.cap, d_max = a.layout.d_max;
@@ -390,18 +390,35 @@ __device__ void bt_frame(const BtArgs& a, const BtStream& st, const BtSmem& sm, 
         if (fits)
             for (int j = tid; j < nl; j += nt) sm.row_box[na + j] = bt_track_box(st.recs + (size_t)sm.list_b[j] * kRecFloats);
         __syncthreads();
-        for (int i = tid; i < na; i += nt) {
-            const float4 ba = sm.row_box[i];
-            const float area = box_area(ba);
-            for (int j = 0; j < nl; ++j) {
-                const float4 bb = fits ? sm.row_box[na + j] : bt_track_box(st.recs + (size_t)sm.list_b[j] * kRecFloats);
-                if (boxes_disjoint(ba, bb)) continue;                  // distance exactly 1
-                const float pd = xsub(1.0f, iou_pair(ba, area, bb));
-                if (pd < 0.15f) {
-                    const int sa = sm.list_a[i], sb = sm.list_b[j];
-                    const int tp = st.frame_id[sa] - st.start_frame[sa];
-                    const int tq = st.frame_id[sb] - st.start_frame[sb];
-                    if (tp > tq) sm.dup_b[j] = 1; else sm.dup_a[i] = 1;
+        auto mark = [&](int i, int j, float4 ba, float area, float4 bb) {
+            const float pd = xsub(1.0f, iou_pair(ba, area, bb));
+            if (pd < 0.15f) {
+                const int sa = sm.list_a[i], sb = sm.list_b[j];
+                const int tp = st.frame_id[sa] - st.start_frame[sa];
+                const int tq = st.frame_id[sb] - st.start_frame[sb];
+                if (tp > tq) sm.dup_b[j] = 1; else sm.dup_a[i] = 1;
+            }
+        };
+        bool use_grid = false;
+        if (fits && (long long)na * nl >= 8192) {
+            grid_build(sm.lap.grid, nl, sm.bs, [&](int j) { return sm.row_box[na + j]; });
+            use_grid = sm.lap.grid.valid != 0;
+        }
+        if (use_grid) {
+            for (int i = tid; i < na; i += nt) {
+                const float4 ba = sm.row_box[i];
+                const float area = box_area(ba);
+                grid_query(sm.lap.grid, ba, [&](int j) { return sm.row_box[na + j]; },
+                           [&](int j, float4 bb) { mark(i, j, ba, area, bb); });
+            }
+        } else {
+            for (int i = tid; i < na; i += nt) {
+                const float4 ba = sm.row_box[i];
+                const float area = box_area(ba);
+                for (int j = 0; j < nl; ++j) {
+                    const float4 bb = fits ? sm.row_box[na + j] : bt_track_box(st.recs + (size_t)sm.list_b[j] * kRecFloats);
+                    if (boxes_disjoint(ba, bb)) continue;                  // distance exactly 1
+                    mark(i, j, ba, area, bb);
                 }
             }
         }

@@ -66,6 +66,7 @@ __device__ __forceinline__ bool boxes_disjoint(float4 a, float4 b) {
 // `prune` must only be set when thresh < 1 (a disjoint pair costs exactly 1).
 struct IouCost {
     static constexpr bool kWarpPerRow = false;
+    static constexpr bool kGrid = true;      // rows/columns are boxes: block_lap may index the columns spatially
     const float4* row_box;
     const float4* det_box;
     const float* det_conf;
@@ -79,6 +80,7 @@ struct IouCost {
         r.area = box_area(r.b);
         return r;
     }
+    __device__ __forceinline__ float4 col_box(int j) const { return det_box[col_map[j]]; }
     __device__ __forceinline__ bool reject(const Row& r, int j) const {
         return prune && boxes_disjoint(r.b, det_box[col_map[j]]);
     }

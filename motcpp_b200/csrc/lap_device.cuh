@@ -15,10 +15,12 @@
 // ties are broken by lowest column / lowest row, not by JV's scan order (DESIGN.md "Ties").
 #pragma once
 #include "block_utils.cuh"
+#include "grid_device.cuh"
 
 namespace mot {
 
 constexpr int kLapNone = 0x7fffffff;
+constexpr int kLapGridItems = 4096;      // (column, cell) entries the spatial index can hold
 
 struct LapWorkspace {
     // shared memory
@@ -34,6 +36,7 @@ struct LapWorkspace {
     int* ctl;                  // [8] counters: 0 edges, 1 overflow, 2 changed, 3 n_comp, 4 next_comp
     BlockScratch* bs;
     int e_cap;
+    BoxGrid grid;              // spatial index over the columns (box costs only)
     // global-memory scratch for components too large for one warp's registers
     double* g_u;               // [n_max]
     double* g_v;               // [m_max + n_max]
@@ -144,11 +147,15 @@ __device__ __forceinline__ void warp_hungarian_small(const unsigned short* rows,
 
 // Same algorithm for a component of any size; per-column state lives in global scratch at
 // positions [pc, pc + c) for real columns and [m_max + pr, m_max + pr + r) for the private ones.
+struct LapGlobalScratch {      // by-value view of the global-memory scratch (keeps LapWorkspace out of local memory)
+    double* g_u; double* g_v; double* g_minv; int* g_way; int* g_prow; unsigned char* g_flags;
+};
+
 template <class Cost>
-__device__ __noinline__ void warp_hungarian_big(const LapWorkspace& ws, int m_max, int n_max,
+__device__ __noinline__ void warp_hungarian_big(const LapGlobalScratch ws, int m_max, int n_max,
                                                 const unsigned short* rows, int r, int pr,
                                                 const unsigned short* cols, int c, int pc, float thresh,
-                                                const Cost& cost, short* row2col, short* col2row) {
+                                                const Cost cost, short* row2col, short* col2row) {
     const int lane = lane_id();
     const double INF = lap_inf();
     const double Ld = (double)thresh;
@@ -232,7 +239,7 @@ __device__ __noinline__ void warp_hungarian_big(const LapWorkspace& ws, int m_ma
 //   };
 // On return (all threads) ws.row2col[0..n) / ws.col2row[0..m) hold the assignment (-1 = unmatched).
 template <class Cost>
-__device__ void block_lap(const LapWorkspace& ws, int n, int m, int n_max, int m_max, float thresh, const Cost& cost) {
+__device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, float thresh, const Cost& cost) {
     const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     __syncthreads();
@@ -263,15 +270,39 @@ __device__ void block_lap(const LapWorkspace& ws, int n, int m, int n_max, int m
             }
         }
     } else {
-        for (int i = tid; i < n; i += nt) {
-            const typename Cost::Row rw = cost.row(i);
-            for (int j = 0; j < m; ++j) {
-                if (cost.reject(rw, j)) continue;
-                const float cf = cost.cost(rw, j);
-                if (cf <= thresh) {
-                    const int e = atomicAdd(&ws.ctl[0], 1);
-                    if (e < ws.e_cap) ws.scratch_a[e] = (i << 16) | j;
-                    else ws.ctl[1] = 1;
+        bool use_grid = false;
+        if constexpr (Cost::kGrid) {
+            // box costs: index the columns so that only overlapping pairs are evaluated at all
+            if (cost.prune && (long long)n * m >= 8192) {
+                grid_build(ws.grid, m, ws.bs, [&](int j) { return cost.col_box(j); });
+                use_grid = ws.grid.valid != 0;
+            }
+        }
+        if (use_grid) {
+            if constexpr (Cost::kGrid) {
+                for (int i = tid; i < n; i += nt) {
+                    const typename Cost::Row rw = cost.row(i);
+                    grid_query(ws.grid, rw.b, [&](int j) { return cost.col_box(j); }, [&](int j, float4) {
+                        const float cf = cost.cost(rw, j);
+                        if (cf <= thresh) {
+                            const int e = atomicAdd(&ws.ctl[0], 1);
+                            if (e < ws.e_cap) ws.scratch_a[e] = (i << 16) | j;
+                            else ws.ctl[1] = 1;
+                        }
+                    });
+                }
+            }
+        } else {
+            for (int i = tid; i < n; i += nt) {
+                const typename Cost::Row rw = cost.row(i);
+                for (int j = 0; j < m; ++j) {
+                    if (cost.reject(rw, j)) continue;
+                    const float cf = cost.cost(rw, j);
+                    if (cf <= thresh) {
+                        const int e = atomicAdd(&ws.ctl[0], 1);
+                        if (e < ws.e_cap) ws.scratch_a[e] = (i << 16) | j;
+                        else ws.ctl[1] = 1;
+                    }
                 }
             }
         }
@@ -346,7 +377,8 @@ __device__ void block_lap(const LapWorkspace& ws, int n, int m, int n_max, int m
         warp_sort_u16(rows, r);
         warp_sort_u16(cols, c);
         if (r + c <= 32) warp_hungarian_small(rows, r, cols, c, thresh, cost, ws.row2col, ws.col2row);
-        else warp_hungarian_big(ws, m_max, n_max, rows, r, pr, cols, c, pc, thresh, cost, ws.row2col, ws.col2row);
+        else warp_hungarian_big(LapGlobalScratch{ws.g_u, ws.g_v, ws.g_minv, ws.g_way, ws.g_prow, ws.g_flags}, m_max, n_max,
+                                rows, r, pr, cols, c, pc, thresh, cost, ws.row2col, ws.col2row);
     }
     __syncthreads();
 }
@@ -372,6 +404,7 @@ MOT_HD inline size_t lap_smem_bytes(int n_max, int m_max, int e_cap) {
     b += lap_align16(sizeof(short) * (size_t)m_max);            // col2row
     b += lap_align16(sizeof(int) * 8);                          // ctl
     b += lap_align16(sizeof(BlockScratch));
+    b += lap_align16(grid_smem_bytes(kLapGridItems));
     return b;
 }
 
@@ -388,6 +421,7 @@ __device__ __forceinline__ unsigned char* lap_carve(unsigned char* p, int n_max,
     ws.col2row = (short*)p;            p += lap_align16(sizeof(short) * (size_t)m_max);
     ws.ctl = (int*)p;                  p += lap_align16(sizeof(int) * 8);
     ws.bs = (BlockScratch*)p;          p += lap_align16(sizeof(BlockScratch));
+    grid_carve(p, kLapGridItems, ws.grid);  p += lap_align16(grid_smem_bytes(kLapGridItems));
     ws.e_cap = e_cap;
     return p;
 }
@@ -418,6 +452,7 @@ __device__ __forceinline__ void lap_carve_gscratch(unsigned char* g, int n_max, 
 // Dense-matrix cost: the standalone mot_lap() entry point (row-major fp32, leading dimension ld).
 struct MatrixCost {
     static constexpr bool kWarpPerRow = true;
+    static constexpr bool kGrid = false;
     const float* c;
     int ld;
     struct Row { const float* p; };

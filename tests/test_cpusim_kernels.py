@@ -84,6 +84,13 @@ def test_bytetrack_kernel_headline_shape(oracle):
     _run_stream(oracle, dets, np.full(12, 512), 1536, 512, 256)
 
 
+def test_bytetrack_kernel_crowded_grid_overflow(oracle):
+    """512 detections on a 960x540 canvas: the spatial index overflows and the kernel must fall back
+    to visiting all pairs; components get large (exercises the >32-node solver too)."""
+    dets = synth.bytetrack_stream(1, n_frames=6, canvas=(960, 540))
+    _run_stream(oracle, dets, np.full(6, 512), 2048, 512, 256)
+
+
 def test_bytetrack_kernel_multi_stream_sequence(oracle):
     """T frames x S streams in one launch == S oracles stepped frame by frame."""
     S, T = 3, 25

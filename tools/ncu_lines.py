@@ -1,0 +1,87 @@
+#!/usr/bin/env python
+"""Join an ncu report's SASS page with nvdisasm line info and aggregate executed instructions and
+stall samples per CUDA source line (ncu's CLI cannot export the per-line view as CSV).
+
+    python tools/ncu_lines.py gpurun_out/prof.ncu-rep motcpp_b200/libmotb200.so bytetrack_step_kernel [top]
+"""
+import csv
+import io
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+
+def line_map(so, kernel):
+    tmp = tempfile.mkdtemp()
+    subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
+    cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+    txt = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
+    m = {}
+    cur = None
+    inside = False
+    for ln in txt.splitlines():
+        if ln.startswith("//---------------------"):
+            inside = (".text." in ln) and (kernel in ln)
+            continue
+        if not inside:
+            continue
+        f = re.match(r'\s*//## File "(.*)", line (\d+)', ln)
+        if f:
+            cur = (os.path.basename(f.group(1)), int(f.group(2)))
+            continue
+        a = re.match(r"\s*/\*([0-9a-f]+)\*/\s+(\S.*?);", ln)
+        if a and cur:
+            m[int(a.group(1), 16)] = cur
+    return m
+
+
+def main():
+    rep, so, kernel = sys.argv[1:4]
+    top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+    lm = line_map(so, kernel)
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kernel],
+                         capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr = next(r for r in rows if r and r[0] == "Address")
+    ia, ii, isamp = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("# Samples")
+    stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
+    data = [r for r in rows if r and r[0].startswith("0x")]
+    base = min(int(r[ia], 16) for r in data)
+    agg = {}
+    tot_i = tot_s = 0
+    for r in data:
+        off = int(r[ia], 16) - base
+        key = lm.get(off, ("?", 0))
+        inst, samp = int(r[ii] or 0), int(r[isamp] or 0)
+        a = agg.setdefault(key, [0, 0, {}])
+        a[0] += inst
+        a[1] += samp
+        for c in stall_cols:
+            v = int(r[c] or 0)
+            if v:
+                a[2][hdr[c]] = a[2].get(hdr[c], 0) + v
+        tot_i += inst
+        tot_s += samp
+    print(f"total warp instructions {tot_i:,}  samples {tot_s:,}")
+    print("== by instructions executed")
+    for key, (inst, samp, st) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+        print(f"{key[0]}:{key[1]:<5} inst {100*inst/tot_i:5.1f}%  samples {100*samp/max(tot_s,1):5.1f}%")
+    print("== by stall samples")
+    for key, (inst, samp, st) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
+        tops = ", ".join(f"{k[6:]} {v}" for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:3])
+        print(f"{key[0]}:{key[1]:<5} samples {100*samp/max(tot_s,1):5.1f}%  inst {100*inst/tot_i:5.1f}%  [{tops}]")
+    # per-file totals
+    files = {}
+    for key, (inst, samp, st) in agg.items():
+        f = files.setdefault(key[0], [0, 0])
+        f[0] += inst
+        f[1] += samp
+    print("== by file")
+    for f, (inst, samp) in sorted(files.items(), key=lambda kv: -kv[1][0]):
+        print(f"{f:<28} inst {100*inst/tot_i:5.1f}%  samples {100*samp/max(tot_s,1):5.1f}%")
+
+
+if __name__ == "__main__":
+    main()
