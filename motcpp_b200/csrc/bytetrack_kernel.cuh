@@ -42,9 +42,9 @@ struct BtParams {
 struct BtLayout {
     int cap, d_max;
     size_t off_lists, off_sflag, off_meta, off_recs, off_gscratch, stride;
-    MOT_HD static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
-    MOT_HD static BtLayout make(int cap, int d_max) {
-        BtLayout L;
+    MOT_HD static constexpr size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+    MOT_HD static constexpr BtLayout make(int cap, int d_max) {
+        BtLayout L{};
         L.cap = cap; L.d_max = d_max;
         size_t o = al(sizeof(int) * kHdrInts);
         L.off_lists = o;    o = al(o + sizeof(unsigned short) * 3 * (size_t)cap);
@@ -83,7 +83,6 @@ struct BtStream {
 
 struct BtArgs {
     unsigned char* state;     // [S] slabs of layout.stride bytes
-    BtLayout layout;
     const float* dets;        // [T][S][ld_dets][6]
     const int* n_dets;        // [T][S]
     float* out;               // [T][S][ld_out][8]
@@ -114,7 +113,7 @@ struct BtSmem {
     LapWorkspace lap;
 };
 
-MOT_HD inline size_t bt_smem_bytes(int cap, int d_max, int e_cap) {
+MOT_HD constexpr size_t bt_smem_bytes(int cap, int d_max, int e_cap) {
     size_t b = 0;
     b += lap_align16(sizeof(float4) * (size_t)d_max);
     b += lap_align16(sizeof(float) * (size_t)d_max);
@@ -202,10 +201,11 @@ __device__ __forceinline__ void bt_kalman_pairs(const BtStream& st, const float*
     }
 }
 
-__device__ void bt_frame(const BtArgs& a, const BtStream& st, BtSmem& sm, const float* dets, int n_det_in,
-                         float* out, int* n_out) {
+template <int CAP, int DMAX>
+__device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, BtSmem& sm, const float* dets, int n_det_in,
+                                         float* out, int* n_out) {
     const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
-    const int cap = a.layout.cap, d_max = a.layout.d_max;
+    constexpr int cap = CAP, d_max = DMAX;
     const int lap_m_max = d_max;
     __syncthreads();
     const int frame = st.hdr[kHdrFrame] + 1;                  // frame_count_ == frame_id_ (:181-182)
@@ -461,20 +461,29 @@ __device__ void bt_frame(const BtArgs& a, const BtStream& st, BtSmem& sm, const 
 }
 
 // One CTA per stream; each CTA walks its streams' T frames in order (state stays hot in L1/L2).
+// CAP / DMAX / ECAP are compile-time so that every shared-memory and state pointer is "base +
+// constant" (no registers spent on the ~50 pointers of the carve-up).
+template <int CAP, int DMAX, int ECAP>
 __global__ void __launch_bounds__(kBtThreads) bytetrack_step_kernel(BtArgs a) {
     MOT_DYNAMIC_SMEM(smem);
     BtSmem sm;
-    bt_carve(smem, a.layout.cap, a.layout.d_max, a.e_cap, sm);
+    bt_carve(smem, CAP, DMAX, ECAP, sm);
+    constexpr BtLayout L = BtLayout::make(CAP, DMAX);
     for (int s = a.s_begin + (int)blockIdx.x; s < a.s_end; s += (int)gridDim.x) {
-        BtStream st = BtStream::at(a.state + (size_t)s * a.layout.stride, a.layout);
-        lap_carve_gscratch(st.gscratch, a.layout.cap, a.layout.d_max, sm.lap);
+        BtStream st = BtStream::at(a.state + (size_t)s * L.stride, L);
+        lap_carve_gscratch(st.gscratch, CAP, DMAX, sm.lap);
         for (int t = 0; t < a.T; ++t) {
             const size_t fs = (size_t)t * a.S + s;
-            bt_frame(a, st, sm, a.dets + fs * (size_t)a.ld_dets * 6, a.n_dets[fs], a.out + fs * (size_t)a.ld_out * 8,
-                     a.n_out + fs);
+            bt_frame<CAP, DMAX>(a, st, sm, a.dets + fs * (size_t)a.ld_dets * 6, a.n_dets[fs],
+                                a.out + fs * (size_t)a.ld_out * 8, a.n_out + fs);
         }
     }
 }
+
+// The (track capacity, detections per frame, candidate-edge buffer) shapes the library is built for.
+struct BtShape { int cap, d_max, e_cap; };
+constexpr BtShape kBtShapes[] = {{256, 64, 1024}, {1536, 512, 4096}, {2048, 512, 4096}, {3072, 1024, 4096}};
+constexpr int kNumBtShapes = sizeof(kBtShapes) / sizeof(kBtShapes[0]);
 
 // reset / first-time initialisation of the per-stream slabs
 __global__ void bytetrack_reset_kernel(unsigned char* state, BtLayout L, int S, int keep_id_counter) {

@@ -70,6 +70,7 @@ struct mot_engine {
     mot_engine_config cfg;
     mot::BtLayout layout;
     mot::BtParams bt;
+    int shape = 0;             // index into mot::kBtShapes
     int e_cap = 4096;
     size_t smem_bytes = 0;
     unsigned char* d_state = nullptr;
@@ -92,10 +93,39 @@ static int engine_reset_impl(mot_engine* e, int keep_ids) {
     return MOT_OK;
 }
 
+template <int I>
+static cudaError_t bt_set_smem(size_t bytes) {
+    constexpr mot::BtShape sh = mot::kBtShapes[I];
+    return cudaFuncSetAttribute(mot::bytetrack_step_kernel<sh.cap, sh.d_max, sh.e_cap>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+template <int I>
+static void bt_launch_one(int grid, size_t smem, cudaStream_t st, const mot::BtArgs& a) {
+    constexpr mot::BtShape sh = mot::kBtShapes[I];
+    mot::bytetrack_step_kernel<sh.cap, sh.d_max, sh.e_cap><<<grid, mot::kBtThreads, smem, st>>>(a);
+}
+static cudaError_t bt_prepare(int shape, size_t smem) {
+    switch (shape) {
+        case 0: return bt_set_smem<0>(smem);
+        case 1: return bt_set_smem<1>(smem);
+        case 2: return bt_set_smem<2>(smem);
+        default: return bt_set_smem<3>(smem);
+    }
+}
+static void bt_launch(int shape, int grid, size_t smem, cudaStream_t st, const mot::BtArgs& a) {
+    switch (shape) {
+        case 0: bt_launch_one<0>(grid, smem, st, a); break;
+        case 1: bt_launch_one<1>(grid, smem, st, a); break;
+        case 2: bt_launch_one<2>(grid, smem, st, a); break;
+        default: bt_launch_one<3>(grid, smem, st, a); break;
+    }
+}
+static_assert(mot::kNumBtShapes == 4, "update the dispatch switches");
+
 static mot::BtArgs make_args(mot_engine* e, int T, const float* dets, const int* nd, int ld_dets, float* out, int* nout,
                              int ld_out, int s_begin, int s_end) {
     mot::BtArgs a{};
-    a.state = e->d_state; a.layout = e->layout;
+    a.state = e->d_state;
     a.dets = dets; a.n_dets = nd; a.out = out; a.n_out = nout;
     a.T = T; a.S = e->cfg.n_streams; a.s_begin = s_begin; a.s_end = s_end;
     a.ld_dets = ld_dets; a.ld_out = ld_out; a.e_cap = e->e_cap; a.p = e->bt;
@@ -197,10 +227,18 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     e->cfg = *cfg;
     if (e->cfg.track_capacity <= 0) e->cfg.track_capacity = 1536;
     if (e->cfg.max_dets <= 0) e->cfg.max_dets = 512;
-    if (e->cfg.track_capacity > 16384 || e->cfg.max_dets > 16384) {
+    // round the request up to the nearest shape the kernel is instantiated for
+    e->shape = -1;
+    for (int i = 0; i < mot::kNumBtShapes; ++i)
+        if (mot::kBtShapes[i].cap >= e->cfg.track_capacity && mot::kBtShapes[i].d_max >= e->cfg.max_dets) { e->shape = i; break; }
+    if (e->shape < 0) {
+        const int tc = e->cfg.track_capacity, md = e->cfg.max_dets;
         delete e;
-        return fail(MOT_ERR_INVALID_ARGUMENT, "track_capacity / max_dets above 16384 are not supported");
+        return fail(MOT_ERR_INVALID_ARGUMENT, "track_capacity %d / max_dets %d exceed the largest built shape (3072 tracks / 1024 detections)", tc, md);
     }
+    e->cfg.track_capacity = mot::kBtShapes[e->shape].cap;
+    e->cfg.max_dets = mot::kBtShapes[e->shape].d_max;
+    e->e_cap = mot::kBtShapes[e->shape].e_cap;
     // BaseTracker ctor fix-up (src/tracker.cpp:37-39)
     if (e->cfg.max_age >= e->cfg.max_obs) e->cfg.max_obs = e->cfg.max_age + 5;
     e->layout = mot::BtLayout::make(e->cfg.track_capacity, e->cfg.max_dets);
@@ -209,7 +247,6 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     e->bt.match_thresh = cfg->match_thresh;
     e->bt.det_thresh = cfg->track_thresh;                                        // bytetrack.cpp:145
     e->bt.max_time_lost = (int)(cfg->frame_rate / 30.0f * cfg->track_buffer);    // bytetrack.cpp:141-142
-    e->e_cap = 4096;
     e->smem_bytes = mot::bt_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap);
     int max_optin = 0;
     MOT_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
@@ -219,8 +256,7 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
         return fail(MOT_ERR_INVALID_ARGUMENT, "track_capacity/max_dets need %zu B of shared memory per CTA (limit %d)",
                     need, max_optin);
     }
-    MOT_CUDA(cudaFuncSetAttribute(mot::bytetrack_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)e->smem_bytes));
+    MOT_CUDA(bt_prepare(e->shape, e->smem_bytes));
     e->n_chunks = cfg->n_chunks > 0 ? std::min(cfg->n_chunks, kMaxChunks) : (cfg->n_streams >= 64 ? 4 : 1);
     e->n_chunks = std::min(e->n_chunks, cfg->n_streams);
     for (int c = 0; c < e->n_chunks; ++c) MOT_CUDA(cudaStreamCreateWithFlags(&e->streams[c], cudaStreamNonBlocking));
@@ -255,7 +291,7 @@ int mot_engine_update_device(mot_engine* e, int T, const float* d_dets, const in
     if ((ld_out * 8 * sizeof(float)) % 16 != 0 || (((size_t)d_out) & 15)) return fail(MOT_ERR_INVALID_ARGUMENT, "out must be 16-byte aligned");
     const int S = e->cfg.n_streams;
     mot::BtArgs a = make_args(e, T, d_dets, d_n_dets, ld_dets, d_out, d_n_out, ld_out, 0, S);
-    mot::bytetrack_step_kernel<<<S, mot::kBtThreads, e->smem_bytes, (cudaStream_t)stream>>>(a);
+    bt_launch(e->shape, S, e->smem_bytes, (cudaStream_t)stream, a);
     MOT_CUDA(cudaGetLastError());
     return MOT_OK;
 }
@@ -283,7 +319,7 @@ int mot_engine_update_host(mot_engine* e, int T, const float* dets, const int* n
         MOT_CUDA(cudaMemcpy2DAsync(e->d_ndets + s0, S * sizeof(int), n_dets + s0, S * sizeof(int),
                                    (s1 - s0) * sizeof(int), T, cudaMemcpyHostToDevice, st));
         mot::BtArgs a = make_args(e, T, e->d_dets, e->d_ndets, ld_dets, e->d_out, e->d_nout, ld_out, s0, s1);
-        mot::bytetrack_step_kernel<<<s1 - s0, mot::kBtThreads, e->smem_bytes, st>>>(a);
+        bt_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
         MOT_CUDA(cudaGetLastError());
         MOT_CUDA(cudaMemcpy2DAsync(out + (size_t)s0 * ld_out * 8, S * out_row, e->d_out + (size_t)s0 * ld_out * 8,
                                    S * out_row, (s1 - s0) * out_row, T, cudaMemcpyDeviceToHost, st));

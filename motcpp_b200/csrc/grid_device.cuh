@@ -31,7 +31,7 @@ struct BoxGrid {
     }
 };
 
-MOT_HD inline size_t grid_smem_bytes(int cap) {
+MOT_HD constexpr size_t grid_smem_bytes(int cap) {
     return ((sizeof(int) * (kGridCells + 1) + 15) & ~(size_t)15) + sizeof(int) * kGridCells +
            ((sizeof(unsigned short) * (size_t)cap + 15) & ~(size_t)15) + sizeof(float) * 4 * 32;
 }

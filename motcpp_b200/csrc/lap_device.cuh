@@ -33,7 +33,7 @@ struct LapWorkspace {
     unsigned short* comp_list; // [n_max] component roots
     short* row2col;            // [n_max] result
     short* col2row;            // [m_max] result
-    int* ctl;                  // [8] counters: 0 edges, 1 overflow, 2 changed, 3 n_comp, 4 next_comp
+    int* ctl;                  // [8] counters: 0 edges, 1 overflow, 2 changed, 3 n_trivial, 4 next_warp, 5 n_team, 6 n_warp
     BlockScratch* bs;
     int e_cap;
     BoxGrid grid;              // spatial index over the columns (box costs only)
@@ -74,28 +74,33 @@ __device__ __forceinline__ void warp_sort_u16(unsigned short* seg, int n) {
     }
 }
 
-// (min value, lowest lane on ties) across the warp
-__device__ __forceinline__ void warp_argmin(double& key, int& arg) {
+// (min value, lowest lane on ties) across a team of W consecutive lanes
+template <int W>
+__device__ __forceinline__ void team_argmin(unsigned mask, double& key, int& arg) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double ok = __shfl_xor_sync(kFullMask, key, o);
-        const int oa = __shfl_xor_sync(kFullMask, arg, o);
+    for (int o = W / 2; o > 0; o >>= 1) {
+        const double ok = __shfl_xor_sync(mask, key, o, W);
+        const int oa = __shfl_xor_sync(mask, arg, o, W);
         if (ok < key || (ok == key && oa < arg)) { key = ok; arg = oa; }
     }
 }
+__device__ __forceinline__ void warp_argmin(double& key, int& arg) { team_argmin<32>(kFullMask, key, arg); }
 
-// Component with r rows and c columns, r + c <= 32.  Lane l < c owns real column cols[l]; lane
-// c + k owns the private "stay unmatched" column of row k (cost 0, reachable only from row k).
-template <class Cost>
-__device__ __forceinline__ void warp_hungarian_small(const unsigned short* rows, int r, const unsigned short* cols,
-                                                     int c, float thresh, const Cost& cost, short* row2col,
-                                                     short* col2row) {
-    const int lane = lane_id();
-    const bool is_real = lane < c;
-    const bool is_col = lane < c + r;
-    const int dummy_of = lane - c;
-    const int col_id = is_real ? (int)cols[lane] : -1;
-    const int row_id = lane < r ? (int)rows[lane] : -1;
+// Component with r rows and c columns, r + c <= W, solved by a team of W consecutive lanes
+// (`mask` names them, `tl` is the lane's index inside the team).  Team lane l < c owns real column
+// cols[l]; lane c + k owns the private "stay unmatched" column of row k (cost 0, reachable only
+// from row k).  Shortest augmenting paths with duals, all state in registers:
+//   u  (row duals)    in lane k for row k          v    (column duals) per lane
+//   minv / way / used (per search)                 prow (row matched to this column, -1 = free)
+template <int W, class Cost>
+__device__ __forceinline__ void team_hungarian(unsigned mask, int tl, const unsigned short* rows, int r,
+                                               const unsigned short* cols, int c, float thresh, const Cost& cost,
+                                               short* row2col, short* col2row) {
+    const bool is_real = tl < c;
+    const bool is_col = tl < c + r;
+    const int dummy_of = tl - c;
+    const int col_id = is_real ? (int)cols[tl] : -1;
+    const int row_id = tl < r ? (int)rows[tl] : -1;
     const double INF = lap_inf();
     const double Ld = (double)thresh;
     double v = 0.0, u = 0.0;
@@ -104,11 +109,11 @@ __device__ __forceinline__ void warp_hungarian_small(const unsigned short* rows,
         double minv = INF;
         int way = -1;
         bool used = false;
-        bool in_tree = (lane == s);
+        bool in_tree = (tl == s);
         int i0 = s, j0 = -1;
         for (;;) {
-            const int i0_id = __shfl_sync(kFullMask, row_id, i0);
-            const double u0 = __shfl_sync(kFullMask, u, i0);
+            const int i0_id = __shfl_sync(mask, row_id, i0, W);
+            const double u0 = __shfl_sync(mask, u, i0, W);
             double cur = INF;
             if (is_real) {
                 const float cf = cost.pair(i0_id, col_id);
@@ -118,35 +123,43 @@ __device__ __forceinline__ void warp_hungarian_small(const unsigned short* rows,
             }
             if (is_col && !used && cur < minv) { minv = cur; way = j0; }
             double key = (is_col && !used) ? minv : INF;
-            int arg = lane;
-            warp_argmin(key, arg);
+            int arg = tl;
+            team_argmin<W>(mask, key, arg);
             const double delta = key;
             if (is_col) { if (used) v -= delta; else minv -= delta; }
             if (in_tree) u += delta;
             j0 = arg;
-            if (lane == j0) used = true;
-            i0 = __shfl_sync(kFullMask, prow, j0);
+            if (tl == j0) used = true;
+            i0 = __shfl_sync(mask, prow, j0, W);
             if (i0 < 0) break;
-            if (lane == i0) in_tree = true;
+            if (tl == i0) in_tree = true;
         }
         int j = j0;
         while (j >= 0) {
-            const int jp = __shfl_sync(kFullMask, way, j);
-            const int from = __shfl_sync(kFullMask, prow, jp < 0 ? 0 : jp);
-            if (lane == j) prow = (jp < 0) ? s : from;
+            const int jp = __shfl_sync(mask, way, j, W);
+            const int from = __shfl_sync(mask, prow, jp < 0 ? 0 : jp, W);
+            if (tl == j) prow = (jp < 0) ? s : from;
             j = jp;
         }
     }
     const int matched_row = (is_real && prow >= 0) ? prow : 0;
-    const int matched_row_id = __shfl_sync(kFullMask, row_id, matched_row);
+    const int matched_row_id = __shfl_sync(mask, row_id, matched_row, W);
     if (is_real && prow >= 0) {
         col2row[col_id] = (short)matched_row_id;
         row2col[matched_row_id] = (short)col_id;
     }
 }
 
-// Same algorithm for a component of any size; per-column state lives in global scratch at
-// positions [pc, pc + c) for real columns and [m_max + pr, m_max + pr + r) for the private ones.
+// ascending insertion sort of a short segment by ONE thread
+__device__ __forceinline__ void insertion_sort_u16(unsigned short* seg, int n) {
+    for (int a = 1; a < n; ++a) {
+        const unsigned short key = seg[a];
+        int b = a - 1;
+        while (b >= 0 && seg[b] > key) { seg[b + 1] = seg[b]; --b; }
+        seg[b + 1] = key;
+    }
+}
+
 struct LapGlobalScratch {      // by-value view of the global-memory scratch (keeps LapWorkspace out of local memory)
     double* g_u; double* g_v; double* g_minv; int* g_way; int* g_prow; unsigned char* g_flags;
 };
@@ -348,8 +361,6 @@ __device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, 
     for (int i = tid; i < n; i += nt) { const int l = ws.row_label[i]; if (l != kLapNone) atomicAdd(&off[l], 1); }
     for (int j = tid; j < m; j += nt) { const int l = ws.col_label[j]; if (l != kLapNone) atomicAdd(&off[l], 1 << 16); }
     __syncthreads();
-    for (int i = tid; i < n; i += nt)
-        if ((off[i] & 0xffff) != 0) { const int k = atomicAdd(&ws.ctl[3], 1); ws.comp_list[k] = (unsigned short)i; }
     block_exclusive_scan(off, n, ws.bs, true);
     for (int i = tid; i < n; i += nt) {
         const int l = ws.row_label[i];
@@ -361,14 +372,60 @@ __device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, 
     }
     __syncthreads();
 
-    // ---- 4. one warp per component
-    const int n_comp = ws.ctl[3];
+    // ---- 4. solve every component with the cheapest exact method that fits it
+    //   trivial (one row or one column): a thread takes the best candidate directly
+    //   r + c <= 8 : an 8-lane team (four components per warp at a time)
+    //   r + c <= 32: a warp          larger: a warp over global scratch
+    unsigned short* list_triv = ws.comp_list;
+    unsigned short* list_team = (unsigned short*)ws.scratch_b;           // the fill cursors are dead now
+    unsigned short* list_warp = list_team + n;
+    for (int i = tid; i < n; i += nt) {
+        const int o0 = off[i], o1 = off[i + 1];
+        const int r = (o1 & 0xffff) - (o0 & 0xffff), c = (o1 >> 16) - (o0 >> 16);
+        if (r == 0) continue;
+        if (r == 1 || c == 1) list_triv[atomicAdd(&ws.ctl[3], 1)] = (unsigned short)i;
+        else if (r + c <= 8) list_team[atomicAdd(&ws.ctl[5], 1)] = (unsigned short)i;
+        else list_warp[atomicAdd(&ws.ctl[6], 1)] = (unsigned short)i;
+    }
+    __syncthreads();
+    const int n_triv = ws.ctl[3], n_team = ws.ctl[5], n_warp = ws.ctl[6];
+    for (int k = tid; k < n_triv; k += nt) {
+        const int root = (int)list_triv[k];
+        const int o0 = off[root], o1 = off[root + 1];
+        const int pr = o0 & 0xffff, r = (o1 & 0xffff) - pr;
+        const int pc = o0 >> 16, c = (o1 >> 16) - pc;
+        float best = 0.0f;
+        int bi = -1, bj = -1;
+        for (int a = 0; a < r; ++a)
+            for (int b = 0; b < c; ++b) {
+                const int i = (int)ws.comp_rows[pr + a], j = (int)ws.comp_cols[pc + b];
+                const float cf = cost.pair(i, j);
+                if (!(cf <= thresh)) continue;
+                if (bi < 0 || cf < best || (cf == best && (i < bi || (i == bi && j < bj)))) { best = cf; bi = i; bj = j; }
+            }
+        if (bi >= 0) { ws.row2col[bi] = (short)bj; ws.col2row[bj] = (short)bi; }
+    }
+    {
+        const int tl = lane & 7, team = tid >> 3, n_teams = nt >> 3;
+        const unsigned tmask = 0xffu << (lane & 24);
+        for (int k = team; k < n_team; k += n_teams) {
+            const int root = (int)list_team[k];
+            const int o0 = off[root], o1 = off[root + 1];
+            const int pr = o0 & 0xffff, r = (o1 & 0xffff) - pr;
+            const int pc = o0 >> 16, c = (o1 >> 16) - pc;
+            unsigned short* rows = ws.comp_rows + pr;
+            unsigned short* cols = ws.comp_cols + pc;
+            if (tl == 0) { insertion_sort_u16(rows, r); insertion_sort_u16(cols, c); }
+            __syncwarp(tmask);
+            team_hungarian<8>(tmask, tl, rows, r, cols, c, thresh, cost, ws.row2col, ws.col2row);
+        }
+    }
     for (;;) {
         int k = 0;
         if (lane == 0) k = atomicAdd(&ws.ctl[4], 1);
         k = __shfl_sync(kFullMask, k, 0);
-        if (k >= n_comp) break;
-        const int root = (int)ws.comp_list[k];
+        if (k >= n_warp) break;
+        const int root = (int)list_warp[k];
         const int o0 = off[root], o1 = off[root + 1];
         const int pr = o0 & 0xffff, r = (o1 & 0xffff) - pr;
         const int pc = o0 >> 16, c = (o1 >> 16) - pc;
@@ -376,7 +433,7 @@ __device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, 
         unsigned short* cols = ws.comp_cols + pc;
         warp_sort_u16(rows, r);
         warp_sort_u16(cols, c);
-        if (r + c <= 32) warp_hungarian_small(rows, r, cols, c, thresh, cost, ws.row2col, ws.col2row);
+        if (r + c <= 32) team_hungarian<32>(kFullMask, lane, rows, r, cols, c, thresh, cost, ws.row2col, ws.col2row);
         else warp_hungarian_big(LapGlobalScratch{ws.g_u, ws.g_v, ws.g_minv, ws.g_way, ws.g_prow, ws.g_flags}, m_max, n_max,
                                 rows, r, pr, cols, c, pc, thresh, cost, ws.row2col, ws.col2row);
     }
@@ -388,9 +445,9 @@ __device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, 
 namespace mot {
 
 // ---- shared-memory carve-up for LapWorkspace (sizes in bytes, 16-byte aligned pieces)
-MOT_HD inline size_t lap_align16(size_t x) { return (x + 15) & ~(size_t)15; }
+MOT_HD constexpr size_t lap_align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-MOT_HD inline size_t lap_smem_bytes(int n_max, int m_max, int e_cap) {
+MOT_HD constexpr size_t lap_smem_bytes(int n_max, int m_max, int e_cap) {
     const int a = e_cap > n_max + 1 ? e_cap : n_max + 1;
     size_t b = 0;
     b += lap_align16(sizeof(int) * (size_t)n_max);              // row_label
@@ -427,7 +484,7 @@ __device__ __forceinline__ unsigned char* lap_carve(unsigned char* p, int n_max,
 }
 
 // global scratch (bytes) for the large-component fallback of one problem
-MOT_HD inline size_t lap_gscratch_bytes(int n_max, int m_max) {
+MOT_HD constexpr size_t lap_gscratch_bytes(int n_max, int m_max) {
     const size_t cols = (size_t)n_max + (size_t)m_max;
     size_t b = 0;
     b += lap_align16(sizeof(double) * (size_t)n_max);   // u

@@ -32,7 +32,7 @@ int sim_lap(const float* cost, int n, int m, int ld, float thresh, int* row2col,
 namespace {
 struct SimBt {
     mot::BtLayout L;
-    int S, e_cap;
+    int S, e_cap, shape;
     mot::BtParams p;
     std::vector<unsigned char> state;
 };
@@ -43,8 +43,13 @@ extern "C" {
 void* sim_bt_create(int S, int cap, int d_max, int e_cap, float min_conf, float track_thresh, float match_thresh,
                     int track_buffer, int frame_rate) {
     auto* h = new SimBt();
-    h->L = mot::BtLayout::make(cap, d_max);
-    h->S = S; h->e_cap = e_cap;
+    h->shape = -1;
+    for (int i = 0; i < mot::kNumBtShapes; ++i)
+        if (mot::kBtShapes[i].cap >= cap && mot::kBtShapes[i].d_max >= d_max) { h->shape = i; break; }
+    if (h->shape < 0) { delete h; return nullptr; }
+    (void)e_cap;
+    h->L = mot::BtLayout::make(mot::kBtShapes[h->shape].cap, mot::kBtShapes[h->shape].d_max);
+    h->S = S; h->e_cap = mot::kBtShapes[h->shape].e_cap;
     h->p.min_conf = min_conf; h->p.track_thresh = track_thresh; h->p.match_thresh = match_thresh;
     h->p.det_thresh = track_thresh;
     h->p.max_time_lost = (int)(frame_rate / 30.0f * track_buffer);
@@ -60,11 +65,21 @@ int sim_bt_update(void* hv, const float* dets, const int* n_dets, int T, int ld_
                   int ld_out, int threads, int os_threads) {
     auto* h = (SimBt*)hv;
     mot::BtArgs a{};
-    a.state = h->state.data(); a.layout = h->L;
+    a.state = h->state.data();
     a.dets = dets; a.n_dets = n_dets; a.out = out; a.n_out = n_out;
     a.T = T; a.S = h->S; a.ld_dets = ld_dets; a.ld_out = ld_out; a.e_cap = h->e_cap; a.p = h->p; a.s_begin = 0; a.s_end = h->S;
     const size_t smem = mot::bt_smem_bytes(h->L.cap, h->L.d_max, h->e_cap);
-    cpusim::launch(dim3(h->S), dim3(threads), smem, [=] { mot::bytetrack_step_kernel(a); }, os_threads);
+    auto run = [&](auto tag) {
+        constexpr int I = decltype(tag)::value;
+        constexpr mot::BtShape sh = mot::kBtShapes[I];
+        cpusim::launch(dim3(h->S), dim3(threads), smem, [=] { mot::bytetrack_step_kernel<sh.cap, sh.d_max, sh.e_cap>(a); }, os_threads);
+    };
+    switch (h->shape) {
+        case 0: run(std::integral_constant<int, 0>{}); break;
+        case 1: run(std::integral_constant<int, 1>{}); break;
+        case 2: run(std::integral_constant<int, 2>{}); break;
+        default: run(std::integral_constant<int, 3>{}); break;
+    }
     return 0;
 }
 
