@@ -120,7 +120,6 @@ MOT_HD constexpr size_t bt_smem_bytes(int cap, int d_max, int e_cap) {
     b += 4 * lap_align16(sizeof(unsigned short) * (size_t)d_max);
     b += lap_align16(sizeof(float4) * (size_t)cap);
     b += 6 * lap_align16(sizeof(unsigned short) * (size_t)cap);
-    b += 2 * lap_align16((size_t)cap);
     b += lap_align16(sizeof(BlockScratch));
     b += lap_smem_bytes(cap, d_max, e_cap);
     return b;
@@ -140,10 +139,10 @@ __device__ __forceinline__ void bt_carve(unsigned char* p, int cap, int d_max, i
     s.list_a = (unsigned short*)p;     p += lap_align16(sizeof(unsigned short) * (size_t)cap);
     s.list_b = (unsigned short*)p;     p += lap_align16(sizeof(unsigned short) * (size_t)cap);
     s.list_c = (unsigned short*)p;     p += lap_align16(sizeof(unsigned short) * (size_t)cap);
-    s.dup_a = p;                       p += lap_align16((size_t)cap);
-    s.dup_b = p;                       p += lap_align16((size_t)cap);
     s.bs = (BlockScratch*)p;           p += lap_align16(sizeof(BlockScratch));
     lap_carve(p, cap, d_max, e_cap, s.lap);
+    s.dup_a = (unsigned char*)s.lap.row_label;      // the assignment workspace is idle during duplicate removal
+    s.dup_b = s.dup_a + cap;
 }
 
 // IoU box of a track from its CURRENT mean (STrack::xyxy, bytetrack.cpp:118-128)
@@ -399,17 +398,35 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
                 if (tp > tq) sm.dup_b[j] = 1; else sm.dup_a[i] = 1;
             }
         };
-        bool use_grid = false;
         if (fits && (long long)na * nl >= 8192) {
+            // lost boxes in the grid; per chunk of rows: collect overlapping pairs, then judge them densely
             grid_build(sm.lap.grid, nl, sm.bs, [&](int j) { return sm.row_box[na + j]; });
-            use_grid = sm.lap.grid.valid != 0;
-        }
-        if (use_grid) {
-            for (int i = tid; i < na; i += nt) {
-                const float4 ba = sm.row_box[i];
-                const float area = box_area(ba);
-                grid_query(sm.lap.grid, ba, [&](int j) { return sm.row_box[na + j]; },
-                           [&](int j, float4 bb) { mark(i, j, ba, area, bb); });
+            for (int base = 0; base < na; base += nt) {
+                const int i = base + tid;
+                if (tid == 0) sm.lap.ctl[7] = 0;
+                __syncthreads();
+                if (i < na)
+                    grid_query(sm.lap.grid, sm.row_box[i], [&](int j) { return sm.row_box[na + j]; }, [&](int j, float4) {
+                        const int q = atomicAdd(&sm.lap.ctl[7], 1);
+                        if (q < sm.lap.p_cap) sm.lap.pairs[q] = (i << 16) | j;
+                    });
+                __syncthreads();
+                const int n_pairs = sm.lap.ctl[7];
+                if (n_pairs <= sm.lap.p_cap) {
+                    for (int q = tid; q < n_pairs; q += nt) {
+                        const int pk = sm.lap.pairs[q];
+                        const float4 ba = sm.row_box[pk >> 16];
+                        mark(pk >> 16, pk & 0xffff, ba, box_area(ba), sm.row_box[na + (pk & 0xffff)]);
+                    }
+                } else if (i < na) {
+                    const float4 ba = sm.row_box[i];
+                    const float area = box_area(ba);
+                    for (int j = 0; j < nl; ++j) {
+                        const float4 bb = sm.row_box[na + j];
+                        if (!boxes_disjoint(ba, bb)) mark(i, j, ba, area, bb);
+                    }
+                }
+                __syncthreads();
             }
         } else {
             for (int i = tid; i < na; i += nt) {

@@ -1,9 +1,11 @@
-// grid_device.cuh - a uniform 32 x 16 grid over a set of boxes in shared memory, rebuilt per use.
+// grid_device.cuh - a uniform 32 x 16 grid over the TOP-LEFT CORNERS of a set of boxes, rebuilt in
+// shared memory per use.
 // The association costs of the reference (iou_batch, include/motcpp/utils/iou.hpp:63-100) are
 // evaluated for ALL N x M pairs; a pair whose boxes are disjoint has IoU exactly 0, cost exactly 1,
 // and can never be an assignment candidate (thresh < 1) nor a duplicate (distance < 0.15).  The
-// grid only decides which pairs are *looked at*: every pair of overlapping boxes is still visited
-// exactly once (in the cell holding the top-left corner of their intersection), so results are
+// grid only decides which pairs are *looked at*: each column box sits in exactly one cell, a row
+// box scans the cells that can hold the corner of a box overlapping it (its own extent dilated by
+// the largest column box), so every overlapping pair is visited exactly once and the results are
 // identical to the dense evaluation.
 #pragma once
 #include "block_utils.cuh"
@@ -17,11 +19,11 @@ constexpr int kGridCells = kGridX * kGridY;
 struct BoxGrid {
     int* cell;                 // [kGridCells + 1] start offset of every cell in items[] (exclusive scan)
     int* cursor;               // [kGridCells] build-time fill cursors
-    unsigned short* items;     // [cap] column indices grouped by cell
-    float* red;                // [4 * 32] block-reduction scratch
+    unsigned short* items;     // [cap] column indices grouped by cell (one entry per finite box)
+    float* red;                // [6 * 32] block-reduction scratch
     int cap;
-    float x0, y0, sx, sy;
-    int valid;                 // 0: grid unusable for this set (too many entries) -> visit all pairs
+    float x0, y0, sx, sy;      // cell = clamp((corner - origin) * scale)
+    float max_w, max_h;        // largest column box
 
     __device__ __forceinline__ int cx(float x) const {
         return (int)fminf(fmaxf(xmul(xsub(x, x0), sx), 0.0f), (float)(kGridX - 1));
@@ -33,16 +35,15 @@ struct BoxGrid {
 
 MOT_HD constexpr size_t grid_smem_bytes(int cap) {
     return ((sizeof(int) * (kGridCells + 1) + 15) & ~(size_t)15) + sizeof(int) * kGridCells +
-           ((sizeof(unsigned short) * (size_t)cap + 15) & ~(size_t)15) + sizeof(float) * 4 * 32;
+           ((sizeof(unsigned short) * (size_t)cap + 15) & ~(size_t)15) + sizeof(float) * 6 * 32;
 }
 
 __device__ __forceinline__ unsigned char* grid_carve(unsigned char* p, int cap, BoxGrid& g) {
     g.cell = (int*)p;               p += (sizeof(int) * (kGridCells + 1) + 15) & ~(size_t)15;
     g.cursor = (int*)p;             p += sizeof(int) * kGridCells;
     g.items = (unsigned short*)p;   p += (sizeof(unsigned short) * (size_t)cap + 15) & ~(size_t)15;
-    g.red = (float*)p;              p += sizeof(float) * 4 * 32;
+    g.red = (float*)p;              p += sizeof(float) * 6 * 32;
     g.cap = cap;
-    g.valid = 0;
     return p;
 }
 
@@ -51,17 +52,18 @@ __device__ __forceinline__ bool box_finite(float4 b) {
     return s == 0.0f;
 }
 
-// Build the grid over boxes box_of(0..n).  All threads of the block must call.  Non-finite boxes
-// are left out (their IoU is NaN: never a candidate).
+// Build the grid over boxes box_of(0..n), n <= g.cap.  All threads of the block must call.
+// Non-finite boxes are left out (their IoU is NaN: never a candidate).
 template <class BoxOf>
 __device__ __forceinline__ void grid_build(BoxGrid& g, int n, BlockScratch* bs, BoxOf box_of) {
     const int tid = (int)threadIdx.x, nt = (int)blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-    float lo_x = 3.0e38f, lo_y = 3.0e38f, hi_x = -3.0e38f, hi_y = -3.0e38f;
+    float lo_x = 3.0e38f, lo_y = 3.0e38f, hi_x = -3.0e38f, hi_y = -3.0e38f, mw = 0.0f, mh = 0.0f;
     for (int j = tid; j < n; j += nt) {
         const float4 b = box_of(j);
         if (!box_finite(b)) continue;
         lo_x = fminf(lo_x, b.x); lo_y = fminf(lo_y, b.y);
-        hi_x = fmaxf(hi_x, b.z); hi_y = fmaxf(hi_y, b.w);
+        hi_x = fmaxf(hi_x, b.x); hi_y = fmaxf(hi_y, b.y);
+        mw = fmaxf(mw, b.z - b.x); mh = fmaxf(mh, b.w - b.y);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -69,64 +71,57 @@ __device__ __forceinline__ void grid_build(BoxGrid& g, int n, BlockScratch* bs, 
         lo_y = fminf(lo_y, __shfl_xor_sync(kFullMask, lo_y, o));
         hi_x = fmaxf(hi_x, __shfl_xor_sync(kFullMask, hi_x, o));
         hi_y = fmaxf(hi_y, __shfl_xor_sync(kFullMask, hi_y, o));
+        mw = fmaxf(mw, __shfl_xor_sync(kFullMask, mw, o));
+        mh = fmaxf(mh, __shfl_xor_sync(kFullMask, mh, o));
     }
     __syncthreads();
-    if (lane == 0) { g.red[warp] = lo_x; g.red[32 + warp] = lo_y; g.red[64 + warp] = hi_x; g.red[96 + warp] = hi_y; }
+    if (lane == 0) {
+        g.red[warp] = lo_x; g.red[32 + warp] = lo_y; g.red[64 + warp] = hi_x; g.red[96 + warp] = hi_y;
+        g.red[128 + warp] = mw; g.red[160 + warp] = mh;
+    }
     for (int c = tid; c <= kGridCells; c += nt) g.cell[c] = 0;
     for (int c = tid; c < kGridCells; c += nt) g.cursor[c] = 0;
     __syncthreads();
     for (int w = 0; w < nwarps; ++w) {
         lo_x = fminf(lo_x, g.red[w]); lo_y = fminf(lo_y, g.red[32 + w]);
         hi_x = fmaxf(hi_x, g.red[64 + w]); hi_y = fmaxf(hi_y, g.red[96 + w]);
+        mw = fmaxf(mw, g.red[128 + w]); mh = fmaxf(mh, g.red[160 + w]);
     }
     const float ex = hi_x - lo_x, ey = hi_y - lo_y;
     g.x0 = lo_x; g.y0 = lo_y;
     g.sx = (ex > 0.0f) ? (float)kGridX / ex : 0.0f;
     g.sy = (ey > 0.0f) ? (float)kGridY / ey : 0.0f;
     if (!(g.sx == g.sx) || !(g.sy == g.sy)) { g.sx = 0.0f; g.sy = 0.0f; }
-    // counts
+    g.max_w = mw; g.max_h = mh;
+    for (int j = tid; j < n; j += nt) {
+        const float4 b = box_of(j);
+        if (box_finite(b)) atomicAdd(&g.cell[g.cy(b.y) * kGridX + g.cx(b.x)], 1);
+    }
+    block_exclusive_scan(g.cell, kGridCells, bs, true);
     for (int j = tid; j < n; j += nt) {
         const float4 b = box_of(j);
         if (!box_finite(b)) continue;
-        const int cx0 = g.cx(b.x), cx1 = g.cx(b.z), cy0 = g.cy(b.y), cy1 = g.cy(b.w);
-        for (int yy = cy0; yy <= cy1; ++yy)
-            for (int xx = cx0; xx <= cx1; ++xx) atomicAdd(&g.cell[yy * kGridX + xx], 1);
-    }
-    const int total = block_exclusive_scan(g.cell, kGridCells, bs, true);
-    g.valid = (total <= g.cap) ? 1 : 0;
-    if (g.valid) {
-        for (int j = tid; j < n; j += nt) {
-            const float4 b = box_of(j);
-            if (!box_finite(b)) continue;
-            const int cx0 = g.cx(b.x), cx1 = g.cx(b.z), cy0 = g.cy(b.y), cy1 = g.cy(b.w);
-            for (int yy = cy0; yy <= cy1; ++yy)
-                for (int xx = cx0; xx <= cx1; ++xx) {
-                    const int c = yy * kGridX + xx;
-                    g.items[g.cell[c] + atomicAdd(&g.cursor[c], 1)] = (unsigned short)j;
-                }
-        }
+        const int c = g.cy(b.y) * kGridX + g.cx(b.x);
+        g.items[g.cell[c] + atomicAdd(&g.cursor[c], 1)] = (unsigned short)j;
     }
     __syncthreads();
 }
 
-// Visit every column j whose box overlaps row box `a` (interior intersection), exactly once.
-// visit(j, box_j) is called for those pairs only.
+// Visit every column j whose box has a non-empty interior intersection with row box `a`, once.
+// A column box b can only overlap a if  a.x1 - max_w < b.x1 < a.x2  (and likewise in y); the scan
+// range is widened by a relative 1e-6 so fp32 rounding in the widths can never drop a pair.
 template <class BoxOf, class Visit>
 __device__ __forceinline__ void grid_query(const BoxGrid& g, float4 a, BoxOf box_of, Visit visit) {
-    const int cx0 = g.cx(a.x), cx1 = g.cx(a.z), cy0 = g.cy(a.y), cy1 = g.cy(a.w);
-    for (int yy = cy0; yy <= cy1; ++yy)
-        for (int xx = cx0; xx <= cx1; ++xx) {
-            const int c = yy * kGridX + xx;
-            const int e1 = g.cell[c + 1];
-            for (int e = g.cell[c]; e < e1; ++e) {
-                const int j = g.items[e];
-                const float4 b = box_of(j);
-                const float ix = fmaxf(a.x, b.x), iy = fmaxf(a.y, b.y);
-                if (!((fminf(a.z, b.z) > ix) && (fminf(a.w, b.w) > iy))) continue;      // disjoint
-                if (g.cx(ix) != xx || g.cy(iy) != yy) continue;                       // counted in another cell
-                visit(j, b);
-            }
+    const float mx = g.max_w + (fabsf(a.x) + g.max_w) * 1e-6f, my = g.max_h + (fabsf(a.y) + g.max_h) * 1e-6f;
+    const int cx0 = g.cx(a.x - mx), cx1 = g.cx(a.z), cy0 = g.cy(a.y - my), cy1 = g.cy(a.w);
+    for (int yy = cy0; yy <= cy1; ++yy) {
+        const int e1 = g.cell[yy * kGridX + cx1 + 1];
+        for (int e = g.cell[yy * kGridX + cx0]; e < e1; ++e) {
+            const int j = g.items[e];
+            const float4 b = box_of(j);
+            if ((fminf(a.z, b.z) > fmaxf(a.x, b.x)) && (fminf(a.w, b.w) > fmaxf(a.y, b.y))) visit(j, b);
         }
+    }
 }
 
 }  // namespace mot

@@ -20,7 +20,6 @@
 namespace mot {
 
 constexpr int kLapNone = 0x7fffffff;
-constexpr int kLapGridItems = 4096;      // (column, cell) entries the spatial index can hold
 
 struct LapWorkspace {
     // shared memory
@@ -37,6 +36,8 @@ struct LapWorkspace {
     BlockScratch* bs;
     int e_cap;
     BoxGrid grid;              // spatial index over the columns (box costs only)
+    int* pairs;                // overlapping (row, col) pairs of one row chunk; aliases scratch_b..comp_list
+    int p_cap;
     // global-memory scratch for components too large for one warp's registers
     double* g_u;               // [n_max]
     double* g_v;               // [m_max + n_max]
@@ -285,39 +286,54 @@ __device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, 
     } else {
         bool use_grid = false;
         if constexpr (Cost::kGrid) {
-            // box costs: index the columns so that only overlapping pairs are evaluated at all
-            if (cost.prune && (long long)n * m >= 8192) {
+            // box costs: index the columns so that only overlapping pairs are looked at
+            if (cost.prune && (long long)n * m >= 8192 && m <= ws.grid.cap) {
                 grid_build(ws.grid, m, ws.bs, [&](int j) { return cost.col_box(j); });
-                use_grid = ws.grid.valid != 0;
+                use_grid = true;
             }
         }
+        auto push_edge = [&](int i, int j) {
+            const int e = atomicAdd(&ws.ctl[0], 1);
+            if (e < ws.e_cap) ws.scratch_a[e] = (i << 16) | j;
+            else ws.ctl[1] = 1;
+        };
+        auto scan_row = [&](int i) {                       // every column, exact cost on the spot
+            const typename Cost::Row rw = cost.row(i);
+            for (int j = 0; j < m; ++j) {
+                if (cost.reject(rw, j)) continue;
+                if (cost.cost(rw, j) <= thresh) push_edge(i, j);
+            }
+        };
         if (use_grid) {
             if constexpr (Cost::kGrid) {
-                for (int i = tid; i < n; i += nt) {
-                    const typename Cost::Row rw = cost.row(i);
-                    grid_query(ws.grid, rw.b, [&](int j) { return cost.col_box(j); }, [&](int j, float4) {
-                        const float cf = cost.cost(rw, j);
-                        if (cf <= thresh) {
-                            const int e = atomicAdd(&ws.ctl[0], 1);
-                            if (e < ws.e_cap) ws.scratch_a[e] = (i << 16) | j;
-                            else ws.ctl[1] = 1;
+                // one row per thread and chunk: (1) collect the overlapping pairs of the chunk through the
+                // grid, (2) evaluate their exact costs densely, one pair per thread (no divergence)
+                for (int base = 0; base < n; base += nt) {
+                    const int i = base + tid;
+                    if (tid == 0) ws.ctl[7] = 0;
+                    __syncthreads();
+                    if (i < n) {
+                        const typename Cost::Row rw = cost.row(i);
+                        grid_query(ws.grid, rw.b, [&](int j) { return cost.col_box(j); }, [&](int j, float4) {
+                            const int q = atomicAdd(&ws.ctl[7], 1);
+                            if (q < ws.p_cap) ws.pairs[q] = (i << 16) | j;
+                        });
+                    }
+                    __syncthreads();
+                    const int n_pairs = ws.ctl[7];
+                    if (n_pairs <= ws.p_cap) {
+                        for (int q = tid; q < n_pairs; q += nt) {
+                            const int pk = ws.pairs[q];
+                            if (cost.pair(pk >> 16, pk & 0xffff) <= thresh) push_edge(pk >> 16, pk & 0xffff);
                         }
-                    });
+                    } else if (i < n) {
+                        scan_row(i);                           // pair buffer too small for this chunk
+                    }
+                    __syncthreads();
                 }
             }
         } else {
-            for (int i = tid; i < n; i += nt) {
-                const typename Cost::Row rw = cost.row(i);
-                for (int j = 0; j < m; ++j) {
-                    if (cost.reject(rw, j)) continue;
-                    const float cf = cost.cost(rw, j);
-                    if (cf <= thresh) {
-                        const int e = atomicAdd(&ws.ctl[0], 1);
-                        if (e < ws.e_cap) ws.scratch_a[e] = (i << 16) | j;
-                        else ws.ctl[1] = 1;
-                    }
-                }
-            }
+            for (int i = tid; i < n; i += nt) scan_row(i);
         }
     }
     __syncthreads();
@@ -461,7 +477,7 @@ MOT_HD constexpr size_t lap_smem_bytes(int n_max, int m_max, int e_cap) {
     b += lap_align16(sizeof(short) * (size_t)m_max);            // col2row
     b += lap_align16(sizeof(int) * 8);                          // ctl
     b += lap_align16(sizeof(BlockScratch));
-    b += lap_align16(grid_smem_bytes(kLapGridItems));
+    b += lap_align16(grid_smem_bytes(n_max > m_max ? n_max : m_max));
     return b;
 }
 
@@ -478,8 +494,10 @@ __device__ __forceinline__ unsigned char* lap_carve(unsigned char* p, int n_max,
     ws.col2row = (short*)p;            p += lap_align16(sizeof(short) * (size_t)m_max);
     ws.ctl = (int*)p;                  p += lap_align16(sizeof(int) * 8);
     ws.bs = (BlockScratch*)p;          p += lap_align16(sizeof(BlockScratch));
-    grid_carve(p, kLapGridItems, ws.grid);  p += lap_align16(grid_smem_bytes(kLapGridItems));
+    grid_carve(p, n_max > m_max ? n_max : m_max, ws.grid);  p += lap_align16(grid_smem_bytes(n_max > m_max ? n_max : m_max));
     ws.e_cap = e_cap;
+    ws.pairs = ws.scratch_b;
+    ws.p_cap = (int)(((unsigned char*)ws.row2col - (unsigned char*)ws.scratch_b) / sizeof(int));
     return p;
 }
 

@@ -349,9 +349,13 @@ def test_bytetrack_reset_keeps_id_counter(oracle):
 
 
 def test_bytetrack_capacity_flag_is_loud():
-    dets = synth.bytetrack_stream(0, n_frames=3)
-    eng = api.Engine(_lib.TRACKER_BYTETRACK, 1, 64, 512, **BT_ARGS)      # 64 slots for 448 new tracks
-    eng.update(dets[0][None], np.array([512], np.int32), ld_out=64)
+    # 64 fresh high-confidence boxes per frame at new places: 256 slots are gone after 4 frames
+    rng = np.random.default_rng(0)
+    eng = api.Engine(_lib.TRACKER_BYTETRACK, 1, 256, 64, **BT_ARGS)
+    for t in range(6):
+        c = rng.uniform(0, 4000, (64, 2)) + 10000 * t
+        dets = np.concatenate([c, c + [50, 110], np.full((64, 1), 0.9), np.zeros((64, 1))], 1).astype(np.float32)
+        eng.update(dets[None], np.array([64], np.int32), ld_out=256)
     with pytest.raises(RuntimeError, match="capacity"):
         eng.check()
     eng.close()

@@ -17,9 +17,10 @@ def line_map(so, kernel):
     tmp = tempfile.mkdtemp()
     subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
     cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-    txt = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
+    txt = subprocess.run(["nvdisasm", "-gi", "-c", cubin], capture_output=True, text=True).stdout
     m = {}
-    cur = None
+    chain = []
+    fresh = True
     inside = False
     for ln in txt.splitlines():
         if ln.startswith("//---------------------"):
@@ -27,21 +28,43 @@ def line_map(so, kernel):
             continue
         if not inside:
             continue
-        f = re.match(r'\s*//## File "(.*)", line (\d+)', ln)
+        f = re.match(r'\s*//## File "(.*?)", line (\d+)', ln)
         if f:
-            cur = (os.path.basename(f.group(1)), int(f.group(2)))
+            if fresh:
+                chain = []
+                fresh = False
+            chain.append((os.path.basename(f.group(1)), int(f.group(2))))
             continue
         a = re.match(r"\s*/\*([0-9a-f]+)\*/\s+(\S.*?);", ln)
-        if a and cur:
-            m[int(a.group(1), 16)] = cur
+        if a and chain:
+            m[int(a.group(1), 16)] = tuple(chain)      # innermost first ... outermost (kernel body) last
+            fresh = True
     return m
+
+
+def user_leaf(chain):
+    for fr in chain:
+        if not fr[0].endswith(".hpp") and not fr[0].endswith(".h"):
+            return fr
+    return chain[0]
+
+
+def phase(chain, phase_file):
+    """the frame of `phase_file` closest to the kernel body (i.e. the call site inside the frame function)"""
+    cands = [fr for fr in chain if fr[0] == phase_file]
+    if len(cands) >= 2:
+        return cands[-2]
+    return cands[-1] if cands else chain[-1]
+
+
+PHASE_FILE = os.environ.get("NCU_PHASE_FILE", "bytetrack_kernel.cuh")
 
 
 def main():
     rep, so, kernel = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-    lm = line_map(so, kernel)
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kernel],
+    lm = line_map(so, kernel)        # `kernel` is matched against the MANGLED name in the cubin
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr = next(r for r in rows if r and r[0] == "Address")
@@ -50,14 +73,20 @@ def main():
     data = [r for r in rows if r and r[0].startswith("0x")]
     base = min(int(r[ia], 16) for r in data)
     agg = {}
+    phases = {}
     tot_i = tot_s = 0
     for r in data:
         off = int(r[ia], 16) - base
-        key = lm.get(off, ("?", 0))
+        ch = lm.get(off, (("?", 0),))
+        key = user_leaf(ch)
+        ph = phase(ch, PHASE_FILE)
+        pa = phases.setdefault(ph, [0, 0])
         inst, samp = int(r[ii] or 0), int(r[isamp] or 0)
         a = agg.setdefault(key, [0, 0, {}])
         a[0] += inst
         a[1] += samp
+        pa[0] += inst
+        pa[1] += samp
         for c in stall_cols:
             v = int(r[c] or 0)
             if v:
@@ -72,6 +101,9 @@ def main():
     for key, (inst, samp, st) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
         tops = ", ".join(f"{k[6:]} {v}" for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:3])
         print(f"{key[0]}:{key[1]:<5} samples {100*samp/max(tot_s,1):5.1f}%  inst {100*inst/tot_i:5.1f}%  [{tops}]")
+    print("== by call site in " + PHASE_FILE + " (inlined callees included)")
+    for key, (inst, samp) in sorted(phases.items(), key=lambda kv: -kv[1][0])[:top]:
+        print(f"{key[0]}:{key[1]:<5} inst {100*inst/tot_i:5.1f}%  samples {100*samp/max(tot_s,1):5.1f}%")
     # per-file totals
     files = {}
     for key, (inst, samp, st) in agg.items():
