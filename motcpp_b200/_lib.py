@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmotb200.so")
+LIB_PATH = os.environ.get("MOT_LIB") or os.path.join(HERE, "libmotb200.so")
 
 MOT_OK = 0
 MOT_ERR_INVALID_ARGUMENT = 1

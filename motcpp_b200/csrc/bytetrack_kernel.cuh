@@ -21,7 +21,15 @@
 
 namespace mot {
 
-constexpr int kBtThreads = 256;
+// 512 threads x 2 CTAs per SM (64 registers/thread, 32 resident warps) measured fastest on B200:
+// 256x1 0.86 M frames/s, 256x2 1.23 M, 384x2 1.43 M, 512x2 1.52 M (profiles/README.md).
+#ifndef MOT_BT_THREADS
+#define MOT_BT_THREADS 512
+#endif
+#ifndef MOT_BT_MINBLOCKS
+#define MOT_BT_MINBLOCKS 2
+#endif
+constexpr int kBtThreads = MOT_BT_THREADS;
 
 enum : int { kStNew = 0, kStTracked = 1, kStLost = 2, kStRemoved = 3 };
 constexpr unsigned char kFlagActivated = 0x10;
@@ -481,7 +489,7 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
 // CAP / DMAX / ECAP are compile-time so that every shared-memory and state pointer is "base +
 // constant" (no registers spent on the ~50 pointers of the carve-up).
 template <int CAP, int DMAX, int ECAP>
-__global__ void __launch_bounds__(kBtThreads) bytetrack_step_kernel(BtArgs a) {
+__global__ void __launch_bounds__(kBtThreads, MOT_BT_MINBLOCKS) bytetrack_step_kernel(BtArgs a) {
     MOT_DYNAMIC_SMEM(smem);
     BtSmem sm;
     bt_carve(smem, CAP, DMAX, ECAP, sm);

@@ -257,7 +257,7 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
                     need, max_optin);
     }
     MOT_CUDA(bt_prepare(e->shape, e->smem_bytes));
-    e->n_chunks = cfg->n_chunks > 0 ? std::min(cfg->n_chunks, kMaxChunks) : (cfg->n_streams >= 64 ? 4 : 1);
+    e->n_chunks = cfg->n_chunks > 0 ? std::min(cfg->n_chunks, kMaxChunks) : (cfg->n_streams >= 128 ? 8 : (cfg->n_streams >= 32 ? 4 : 1));
     e->n_chunks = std::min(e->n_chunks, cfg->n_streams);
     for (int c = 0; c < e->n_chunks; ++c) MOT_CUDA(cudaStreamCreateWithFlags(&e->streams[c], cudaStreamNonBlocking));
     MOT_CUDA(cudaMalloc(&e->d_state, e->layout.stride * (size_t)cfg->n_streams));

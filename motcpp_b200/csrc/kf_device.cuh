@@ -83,22 +83,32 @@ struct Chol4 {
     float l00, l10, l11, l20, l21, l22, l30, l31, l32, l33;
 };
 
+// a / l for l > 0.  The structure of the tracking filters makes most numerators here EXACT zeros
+// (x, y, a, h evolve independently, so S and the gain are block-sparse), and a zero dividend sends
+// the hardware's IEEE division down its slow path.  0 / l is the signed zero itself, so it is
+// returned directly and the divider only ever sees a benign dividend: same bits, no slow path.
+__device__ __forceinline__ float xdiv_pos(float a, float l) {
+    const bool z = (a == 0.0f);
+    const float q = xdiv(z ? 1.0f : a, l);
+    return z ? a : q;
+}
+
 __device__ __forceinline__ bool chol4(const float (&S)[4][4], Chol4& L) {
     float x = S[0][0];
     bool ok = x > 0.0f;
     L.l00 = xsqrt(x);
-    L.l10 = xdiv(S[1][0], L.l00);
-    L.l20 = xdiv(S[2][0], L.l00);
-    L.l30 = xdiv(S[3][0], L.l00);
+    L.l10 = xdiv_pos(S[1][0], L.l00);
+    L.l20 = xdiv_pos(S[2][0], L.l00);
+    L.l30 = xdiv_pos(S[3][0], L.l00);
     x = xsub(S[1][1], xmul(L.l10, L.l10));
     ok = ok && (x > 0.0f);
     L.l11 = xsqrt(x);
-    L.l21 = xdiv(xsub(S[2][1], xmul(L.l20, L.l10)), L.l11);
-    L.l31 = xdiv(xsub(S[3][1], xmul(L.l30, L.l10)), L.l11);
+    L.l21 = xdiv_pos(xsub(S[2][1], xmul(L.l20, L.l10)), L.l11);
+    L.l31 = xdiv_pos(xsub(S[3][1], xmul(L.l30, L.l10)), L.l11);
     x = xsub(S[2][2], xadd(xmul(L.l20, L.l20), xmul(L.l21, L.l21)));
     ok = ok && (x > 0.0f);
     L.l22 = xsqrt(x);
-    L.l32 = xdiv(xsub(S[3][2], xadd(xmul(L.l30, L.l20), xmul(L.l31, L.l21))), L.l22);
+    L.l32 = xdiv_pos(xsub(S[3][2], xadd(xmul(L.l30, L.l20), xmul(L.l31, L.l21))), L.l22);
     x = xsub(S[3][3], xadd(xadd(xmul(L.l30, L.l30), xmul(L.l31, L.l31)), xmul(L.l32, L.l32)));
     ok = ok && (x > 0.0f);
     L.l33 = xsqrt(x);
@@ -107,14 +117,14 @@ __device__ __forceinline__ bool chol4(const float (&S)[4][4], Chol4& L) {
 
 // Solve (L L^T) x = b in place (smallmat.hpp cholesky_solve).
 __device__ __forceinline__ void chol4_solve(const Chol4& L, float (&b)[4]) {
-    b[0] = xdiv(b[0], L.l00);
-    b[1] = xdiv(xsub(b[1], xmul(L.l10, b[0])), L.l11);
-    b[2] = xdiv(xsub(b[2], xadd(xmul(L.l20, b[0]), xmul(L.l21, b[1]))), L.l22);
-    b[3] = xdiv(xsub(b[3], xadd(xadd(xmul(L.l30, b[0]), xmul(L.l31, b[1])), xmul(L.l32, b[2]))), L.l33);
-    b[3] = xdiv(b[3], L.l33);
-    b[2] = xdiv(xsub(b[2], xmul(L.l32, b[3])), L.l22);
-    b[1] = xdiv(xsub(b[1], xadd(xmul(L.l21, b[2]), xmul(L.l31, b[3]))), L.l11);
-    b[0] = xdiv(xsub(b[0], xadd(xadd(xmul(L.l10, b[1]), xmul(L.l20, b[2])), xmul(L.l30, b[3]))), L.l00);
+    b[0] = xdiv_pos(b[0], L.l00);
+    b[1] = xdiv_pos(xsub(b[1], xmul(L.l10, b[0])), L.l11);
+    b[2] = xdiv_pos(xsub(b[2], xadd(xmul(L.l20, b[0]), xmul(L.l21, b[1]))), L.l22);
+    b[3] = xdiv_pos(xsub(b[3], xadd(xadd(xmul(L.l30, b[0]), xmul(L.l31, b[1])), xmul(L.l32, b[2]))), L.l33);
+    b[3] = xdiv_pos(b[3], L.l33);
+    b[2] = xdiv_pos(xsub(b[2], xmul(L.l32, b[3])), L.l22);
+    b[1] = xdiv_pos(xsub(b[1], xadd(xmul(L.l21, b[2]), xmul(L.l31, b[3]))), L.l11);
+    b[0] = xdiv_pos(xsub(b[0], xadd(xadd(xmul(L.l10, b[1]), xmul(L.l20, b[2])), xmul(L.l30, b[3]))), L.l00);
 }
 
 // Gather S = P[0:4,0:4] (all 16 entries) into every lane of the group.

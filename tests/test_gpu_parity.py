@@ -349,12 +349,18 @@ def test_bytetrack_reset_keeps_id_counter(oracle):
 
 
 def test_bytetrack_capacity_flag_is_loud():
-    # 64 fresh high-confidence boxes per frame at new places: 256 slots are gone after 4 frames
+    # every frame: 32 fresh boxes + last frame's 32 again (which confirms them).  With no low-score
+    # detections confirmed tracks are never marked lost (bytetrack.cpp:387), so they pile up: the 256
+    # slots of the smallest shape are gone after ~8 frames and the engine must say so.
     rng = np.random.default_rng(0)
     eng = api.Engine(_lib.TRACKER_BYTETRACK, 1, 256, 64, **BT_ARGS)
-    for t in range(6):
-        c = rng.uniform(0, 4000, (64, 2)) + 10000 * t
-        dets = np.concatenate([c, c + [50, 110], np.full((64, 1), 0.9), np.zeros((64, 1))], 1).astype(np.float32)
+
+    def boxes(t):
+        c = np.random.default_rng(100 + t).uniform(0, 4000, (32, 2)) + 10000 * t
+        return np.concatenate([c, c + [50, 110], np.full((32, 1), 0.9), np.zeros((32, 1))], 1).astype(np.float32)
+
+    for t in range(12):
+        dets = np.concatenate([boxes(t), boxes(t - 1)], 0)
         eng.update(dets[None], np.array([64], np.int32), ld_out=256)
     with pytest.raises(RuntimeError, match="capacity"):
         eng.check()
