@@ -1,0 +1,26 @@
+// The reference's examples/simple_tracking.cpp loop, on the B200 engine: construct a tracker with
+// the reference's positional arguments, call update(dets, img) per frame.
+//   g++ -std=c++17 -Iinclude examples/simple_tracking.cpp -Lmotcpp_b200 -lmotb200 -Wl,-rpath,$PWD/motcpp_b200
+#include <cstdio>
+#include <motcpp_b200/trackers.hpp>
+
+int main() {
+    try {
+        motcpp_b200::ByteTrack tracker(0.3f, 30, 50, 3, 0.3f, false, 80, "iou", false, 0.1f, 0.45f, 0.8f, 30, 30);
+        cv::Mat img(480, 640);
+        Eigen::MatrixXf dets(2, 6);
+        const float rows[2][6] = {{100, 100, 200, 200, 0.9f, 0}, {300, 300, 400, 420, 0.8f, 0}};
+        for (int frame = 0; frame < 3; ++frame) {
+            for (int i = 0; i < 2; ++i)
+                for (int c = 0; c < 6; ++c) dets(i, c) = rows[i][c] + (c < 4 ? 2.0f * frame : 0.0f);
+            const Eigen::MatrixXf tracks = tracker.update(dets, img);
+            for (long i = 0; i < tracks.rows(); ++i)
+                std::printf("frame %d id %d box %.1f %.1f %.1f %.1f conf %.2f\n", frame, (int)tracks(i, 4), tracks(i, 0),
+                            tracks(i, 1), tracks(i, 2), tracks(i, 3), tracks(i, 5));
+        }
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "error: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

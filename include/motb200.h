@@ -5,7 +5,7 @@
  * own: its boundary is the C++ class motcpp::BaseTracker and a few free functions.  Each entry
  * point below names the reference interface it replaces (paths relative to the motcpp tree);
  * INTEGRATION.md shows the C++ binding a motcpp maintainer would add on top of this header, and
- * include/motcpp_b200/*.hpp ships that binding (same class names, constructor arguments and
+ * the headers under include/motcpp_b200/ ship that binding (same class names, constructor arguments and
  * exceptions as the reference).
  *
  * Conventions
