@@ -1,11 +1,321 @@
-// kernels_cosine.cuh - embedding cosine-distance cost matrix (tcgen05 tensor-core contraction).
-// Placeholder until the tcgen05 kernel lands: fails loudly instead of computing anything.
+// kernels_cosine.cuh - embedding cosine-distance cost matrix on the 5th-generation tensor cores.
+//
+// Replaces utils::embedding_distance(metric = "cosine") (reference src/utils/matching.cpp:67-92,
+// template include/motcpp/utils/matching.hpp:187-221):
+//     cost(i,j) = max(0, 1 - t_i . d_j / (|t_i| |d_j| + 1e-10))
+// the one dense contraction of the hot path (BoT-SORT first association, botsort.cpp:449).
+//
+// fp32-level accuracy from bf16 tensor cores: every fp32 value is split into three bf16 terms
+// x = h + m + l (8 + 8 + 8 mantissa bits) and the dot product keeps the six significant partial
+// products  h.h' + h.m' + m.h' + h.l' + l.h' + m.m'  (what is dropped is below 2^-24 relative).
+// The split kernel lays them out side by side along K:
+//     A' = [ h | h | m | h | l | m ]   (n x 6 Dp, bf16)        B' = [ h'| m'| h'| l'| h'| m' ]
+// so the whole thing is ONE bf16 GEMM  C = A' B'^T  with K' = 6 Dp, accumulated in fp32 in TMEM.
+//
+// GEMM kernel (one 128 x 64 output tile per CTA, 192 threads):
+//   warp 4  TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B) into a 6-stage smem ring
+//   warp 5  TMEM allocation + MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M128 N64 K16,
+//           tcgen05.commit onto the ring's "empty" barriers and onto the accumulator barrier
+//   warps 0-3 epilogue: tcgen05.ld (32 lanes x 32 columns) -> norm division, 1 - x, max(0, .) -> float4 stores
+// SASS evidence to look for: UTCHMMA (tcgen05.mma), UTMALDG (TMA), LDTM (tcgen05.ld).
 #pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
 #include <string>
+
 #include "simt.cuh"
+
 namespace mot {
-inline int launch_cosine(const float*, int, const float*, int, int, float*, int, cudaStream_t, std::string& err) {
-    err = "mot_cost_cosine: tcgen05 kernel not built into this library yet";
-    return 6;   // MOT_ERR_UNSUPPORTED
+namespace cosine {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockN = 64;
+constexpr int kBlockK = 64;                   // bf16 elements = 128 bytes = one SWIZZLE_128B row
+constexpr int kStages = 6;
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 192;
+constexpr int kABytes = kBlockM * kBlockK * 2;     // 16 KB
+constexpr int kBBytes = kBlockN * kBlockK * 2;     //  8 KB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kTmemCols = 64;
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256 /*barriers*/;
+
+// ---------------------------------------------------------------- split + norm pre-pass
+// One warp per row.  out row = 6 segments of Dp bf16 (Dp = dim rounded up to 64, zero padded).
+// order: for A (is_b = 0) [h h m h l m], for B (is_b = 1) [h m h l h m]
+__global__ void __launch_bounds__(256) cosine_split_kernel(const float* __restrict__ x, int rows, int dim, int dp,
+                                                           __nv_bfloat16* __restrict__ out, float* __restrict__ norm,
+                                                           int is_b) {
+    const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = (int)(threadIdx.x & 31);
+    const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+    for (int r = warp; r < rows; r += nwarps) {
+        const float* src = x + (size_t)r * dim;
+        __nv_bfloat16* dst = out + (size_t)r * 6 * dp;
+        float acc = 0.0f;
+        for (int k = lane; k < dp; k += 32) {
+            const float v = (k < dim) ? src[k] : 0.0f;
+            acc = __fadd_rn(acc, __fmul_rn(v, v));
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            const float r1 = __fsub_rn(v, __bfloat162float(h));
+            const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+            const float r2 = __fsub_rn(r1, __bfloat162float(m));
+            const __nv_bfloat16 l = __float2bfloat16_rn(r2);
+            if (!is_b) {
+                dst[k] = h; dst[dp + k] = h; dst[2 * dp + k] = m; dst[3 * dp + k] = h; dst[4 * dp + k] = l; dst[5 * dp + k] = m;
+            } else {
+                dst[k] = h; dst[dp + k] = m; dst[2 * dp + k] = h; dst[3 * dp + k] = l; dst[4 * dp + k] = h; dst[5 * dp + k] = m;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+        if (lane == 0) norm[r] = __fsqrt_rn(acc);
+    }
 }
+
+// ---------------------------------------------------------------- PTX helpers (sm_100a)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand tile in smem, rows of 128 bytes, SWIZZLE_128B (8-row atoms of 1024 bytes):
+//   start address >> 4 | LBO (unused for swizzled K-major) | SBO = 1024 B >> 4 | version 1 | layout SWIZZLE_128B (2)
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)0 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+__device__ __forceinline__ uint32_t umma_idesc() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBlockN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------- GEMM + cosine epilogue
+// grid = (ceil(n / 128), ceil(m / 64)); tensor maps: A' (n x kp) box {64, 128}, B' (m x kp) box {64, 64}
+__global__ void __launch_bounds__(kThreads, 1)
+cosine_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int n, int m,
+                   int kp, const float* __restrict__ norm_t, const float* __restrict__ norm_d, float* __restrict__ out,
+                   int ld) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B: 1024-B aligned
+    unsigned char* tiles = smem;
+    uint64_t* full = (uint64_t*)(smem + (size_t)kStages * kStageBytes);
+    uint64_t* empty = full + kStages;
+    uint64_t* acc_ready = empty + kStages;
+    uint32_t* tmem_slot = (uint32_t*)(acc_ready + 1);
+
+    const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
+    const int m0 = (int)blockIdx.x * kBlockM;      // rows of the output (tracks)
+    const int n0 = (int)blockIdx.y * kBlockN;      // columns of the output (detections)
+    const int k_blocks = kp / kBlockK;
+
+    if (threadIdx.x == 4 * 32) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc_ready, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {                                            // ---- TMA producer
+            for (int kb = 0; kb < k_blocks; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
+                mbar_wait(&empty[s], ph ^ 1u);
+                mbar_expect_tx(&full[s], kStageBytes);
+                unsigned char* a_dst = tiles + (size_t)s * kStageBytes;
+                tma_load_2d(a_dst, &map_a, kb * kBlockK, m0, &full[s]);
+                tma_load_2d(a_dst + kABytes, &map_b, kb * kBlockK, n0, &full[s]);
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {                                            // ---- MMA issuer
+            const uint32_t idesc = umma_idesc();
+            for (int kb = 0; kb < k_blocks; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
+                mbar_wait(&full[s], ph);
+                tcgen05_fence_after();
+                const uint32_t a_addr = smem_u32(tiles + (size_t)s * kStageBytes);
+                const uint64_t adesc = umma_smem_desc(a_addr), bdesc = umma_smem_desc(a_addr + kABytes);
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k)          // advance 16 elements = 32 bytes inside the swizzle atom
+                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                umma_commit(&empty[s]);                             // smem slot reusable when these MMAs retire
+            }
+            umma_commit(acc_ready);                                 // accumulator complete
+        }
+    } else {                                                        // ---- epilogue: warps 0..3 own TMEM lanes 32w..32w+31
+        mbar_wait(acc_ready, 0);
+        tcgen05_fence_after();
+        const int row = m0 + warp * 32 + lane;
+        const float tn = (row < n) ? norm_t[row] : 1.0f;
+        const bool vec_ok = ((ld & 3) == 0) && ((((uintptr_t)out) & 15) == 0);
+#pragma unroll
+        for (int c0 = 0; c0 < kBlockN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+            if (row < n) {
+                float* orow = out + (size_t)row * ld + n0 + c0;
+#pragma unroll
+                for (int q = 0; q < 32; q += 4) {
+                    float v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int col = n0 + c0 + q + e;
+                        const float dn = (col < m) ? __ldg(&norm_d[col]) : 1.0f;
+                        const float sim = __fdiv_rn(__uint_as_float(r[q + e]), __fadd_rn(__fmul_rn(tn, dn), 1e-10f));
+                        v[e] = fmaxf(0.0f, __fsub_rn(1.0f, sim));
+                    }
+                    const int col = n0 + c0 + q;
+                    if (vec_ok && col + 3 < m) {
+                        *reinterpret_cast<float4*>(orow + q) = make_float4(v[0], v[1], v[2], v[3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (col + e < m) orow[q + e] = v[e];
+                    }
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+inline bool make_map(CUtensorMap* map, const void* base, int rows, int kp, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)kp, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)kp * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace cosine
+
+// returns a mot_status value; err receives the message on failure
+inline int launch_cosine(const float* t, int n, const float* d, int m, int dim, float* out, int ld, cudaStream_t st,
+                         std::string& err) {
+    using namespace cosine;
+    const int dp = (dim + kBlockK - 1) / kBlockK * kBlockK;
+    const int kp = 6 * dp;
+    __nv_bfloat16 *a = nullptr, *b = nullptr;
+    float *tn = nullptr, *dn = nullptr;
+    auto fail = [&](const char* what, cudaError_t e) {
+        err = std::string("mot_cost_cosine: ") + what + ": " + cudaGetErrorString(e);
+        return 2;   // MOT_ERR_CUDA
+    };
+    cudaError_t e;
+    if ((e = cudaMallocAsync((void**)&a, (size_t)n * kp * 2, st)) != cudaSuccess) return fail("alloc A'", e);
+    if ((e = cudaMallocAsync((void**)&b, (size_t)m * kp * 2, st)) != cudaSuccess) return fail("alloc B'", e);
+    if ((e = cudaMallocAsync((void**)&tn, sizeof(float) * n, st)) != cudaSuccess) return fail("alloc norms", e);
+    if ((e = cudaMallocAsync((void**)&dn, sizeof(float) * m, st)) != cudaSuccess) return fail("alloc norms", e);
+    cosine_split_kernel<<<(n + 7) / 8, 256, 0, st>>>(t, n, dim, dp, a, tn, 0);
+    cosine_split_kernel<<<(m + 7) / 8, 256, 0, st>>>(d, m, dim, dp, b, dn, 1);
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail("split launch", e);
+    CUtensorMap map_a, map_b;
+    if (!make_map(&map_a, a, n, kp, kBlockM) || !make_map(&map_b, b, m, kp, kBlockN)) {
+        err = "mot_cost_cosine: cuTensorMapEncodeTiled failed";
+        return 2;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        if ((e = cudaFuncSetAttribute(cosine_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes)) !=
+            cudaSuccess)
+            return fail("smem attribute", e);
+        attr_set = true;
+    }
+    dim3 grid((unsigned)((n + kBlockM - 1) / kBlockM), (unsigned)((m + kBlockN - 1) / kBlockN));
+    cosine_gemm_kernel<<<grid, kThreads, kSmemBytes, st>>>(map_a, map_b, n, m, kp, tn, dn, out, ld);
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail("gemm launch", e);
+    cudaFreeAsync(a, st); cudaFreeAsync(b, st); cudaFreeAsync(tn, st); cudaFreeAsync(dn, st);
+    return 0;
+}
+
 }  // namespace mot

@@ -420,3 +420,34 @@ def test_bytetrack_full_size_properties():
     hdr = a.header(0)
     assert hdr[3] >= seen_max[0] and hdr[4] == T
     a.close(); b.close()
+
+
+# ------------------------------------------------------------------ cosine embedding cost (tcgen05)
+COSINE_ATOL = 2e-5     # 3-term bf16 split + fp32 tensor-core accumulation vs the oracle's sequential fp32 sum
+
+
+@pytest.mark.parametrize("n,m,dim", [(1, 1, 8), (7, 5, 33), (128, 64, 64), (130, 70, 128), (300, 517, 512), (1024, 1024, 512)])
+def test_cosine_cost_matches_oracle(oracle, n, m, dim):
+    rng = np.random.default_rng(n + 3 * m + dim)
+    t = rng.normal(0, 1, (n, dim)).astype(np.float32)
+    d = rng.normal(0, 1, (m, dim)).astype(np.float32)
+    if n > 4:                                   # some near-duplicates (cost ~ 0) and an exact copy (cost clamps at 0)
+        d[0] = t[1] + 0.05 * rng.normal(0, 1, dim).astype(np.float32)
+        d[m - 1] = 3.0 * t[2]
+    got = api.embedding_distance(t, d)
+    want = oracle.embedding_distance(t, d)
+    assert got.shape == want.shape
+    assert np.all(got >= 0.0)
+    np.testing.assert_allclose(got, want, atol=COSINE_ATOL, rtol=0)
+    if n > 4:
+        assert got[2, m - 1] <= COSINE_ATOL
+
+
+def test_cosine_botsort_embeddings(oracle):
+    """C3-style inputs: unit-norm identity embeddings, detections = identity + noise."""
+    dets, embs = synth.embeddings_stream(0, n_frames=2, n_obj=256, dim=512)
+    got = api.embedding_distance(embs[0], embs[1])
+    want = oracle.embedding_distance(embs[0], embs[1])
+    np.testing.assert_allclose(got, want, atol=COSINE_ATOL, rtol=0)
+    # the matching a downstream LAP would make is unchanged by the tolerance
+    assert np.array_equal(np.argmin(got, 1), np.argmin(want, 1))
