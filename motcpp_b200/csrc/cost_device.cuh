@@ -53,7 +53,12 @@ __device__ __forceinline__ float iou_pair(float4 a, float area_a, float4 b) {
     const float h = fmaxf(0.0f, xsub(yy2, yy1));
     const float inter = xmul(w, h);
     const float uni = xsub(xadd(area_a, area_b), inter);
-    return (uni > 0.0f) ? xdiv(inter, uni) : 0.0f;
+    // 0 / uni is exactly +0; answering it directly keeps zero dividends (disjoint boxes, the vast
+    // majority of an N x M matrix) off the IEEE divider's slow path.  Same bits as the division.
+    if (!(uni > 0.0f)) return 0.0f;
+    const bool z = (inter == 0.0f);
+    const float q = xdiv(z ? 1.0f : inter, uni);
+    return z ? 0.0f : q;
 }
 
 // true => the boxes share no interior => IoU is exactly 0

@@ -24,7 +24,13 @@ def main():
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     kn = hdr.index("Kernel Name")
-    for r in rows[2:]:
+    body = rows[2:]
+    if "--last" in sys.argv:                      # keep the last capture of every kernel name
+        last = {}
+        for r in body:
+            last[r[kn]] = r
+        body = list(last.values())
+    for r in body:
         print("kernel:", r[kn])
         for h, u, v in zip(hdr, units, r):
             if h in WANT:
