@@ -427,3 +427,33 @@ class ByteTrack:
         self._engine.update(self._dets[None], np.array([[n]], np.int32), self._out, self._n_out)
         self._engine.check()
         return self._out[0, 0, :int(self._n_out[0, 0])].copy()
+
+
+class Sort:
+    """motcpp::trackers::Sort with the reference's positional constructor
+    (include/motcpp/trackers/sort.hpp:69-77).  Like the reference it performs no input validation
+    (Sort::update never calls check_inputs, src/trackers/sort.cpp:102-108) and ignores the image."""
+
+    def __init__(self, det_thresh=0.3, max_age=1, max_obs=50, min_hits=3, iou_threshold=0.3, per_class=False,
+                 nr_classes=80, asso_func="iou", is_obb=False, track_capacity=256, max_dets=64, device=0):
+        if asso_func != "iou" or per_class or is_obb:
+            raise ValueError("only asso_func=\"iou\", per_class=False, is_obb=False are on the accelerated path")
+        self._engine = Engine(_lib.TRACKER_SORT, 1, track_capacity, max_dets, device, det_thresh=det_thresh,
+                              max_age=max_age, max_obs=max_obs, min_hits=min_hits, iou_threshold=iou_threshold)
+        self._max_dets = max(max_dets, 1)
+        self._dets = np.zeros((1, 1, self._max_dets, 6), np.float32)
+        self._out = np.empty((1, 1, max(track_capacity, 256), 8), np.float32)
+        self._n_out = np.empty((1, 1), np.int32)
+
+    def reset(self):
+        self._engine.reset()
+
+    def update(self, dets, img=None, embs=None) -> np.ndarray:
+        dets = np.asarray(dets, np.float32).reshape(-1, 6) if np.size(dets) else np.zeros((0, 6), np.float32)
+        n = dets.shape[0]
+        if n > self._max_dets:
+            raise ValueError(f"{n} detections exceed max_dets={self._max_dets}")
+        self._dets[0, 0, :n] = dets
+        self._engine.update(self._dets, np.array([[n]], np.int32), self._out, self._n_out)
+        self._engine.check()
+        return self._out[0, 0, :int(self._n_out[0, 0])].copy()

@@ -17,6 +17,7 @@
 #include "kernels_kf.cuh"
 #include "kernels_lap.cuh"
 #include "kernels_cosine.cuh"
+#include "sort_kernel.cuh"
 
 namespace {
 
@@ -68,8 +69,12 @@ constexpr int kMaxChunks = 8;
 
 struct mot_engine {
     mot_engine_config cfg;
-    mot::BtLayout layout;
+    mot::BtLayout layout;          // ByteTrack slab layout (kind == BYTETRACK)
+    mot::SortLayout sort_layout;   // SORT slab layout (kind == SORT)
+    size_t stride = 0;             // bytes per stream slab (whichever layout is live)
+    int threads = 0;
     mot::BtParams bt;
+    mot::SortParams sortp;
     int shape = 0;             // index into mot::kBtShapes
     int e_cap = 4096;
     size_t smem_bytes = 0;
@@ -86,8 +91,11 @@ struct mot_engine {
 
 // ---- helpers (C++ linkage)
 static int engine_reset_impl(mot_engine* e, int keep_ids) {
-    mot::bytetrack_reset_kernel<<<std::min(e->cfg.n_streams, 4096), 256, 0, e->streams[0]>>>(
-        e->d_state, e->layout, e->cfg.n_streams, keep_ids);
+    const int grid = std::min(e->cfg.n_streams, 4096);
+    if (e->cfg.kind == MOT_TRACKER_SORT)
+        mot::sort_reset_kernel<<<grid, 256, 0, e->streams[0]>>>(e->d_state, e->sort_layout, e->cfg.n_streams, keep_ids);
+    else
+        mot::bytetrack_reset_kernel<<<grid, 256, 0, e->streams[0]>>>(e->d_state, e->layout, e->cfg.n_streams, keep_ids);
     MOT_CUDA(cudaGetLastError());
     MOT_CUDA(cudaStreamSynchronize(e->streams[0]));
     return MOT_OK;
@@ -122,6 +130,38 @@ static void bt_launch(int shape, int grid, size_t smem, cudaStream_t st, const m
 }
 static_assert(mot::kNumBtShapes == 4, "update the dispatch switches");
 
+template <int I>
+static cudaError_t sort_set_smem(size_t bytes) {
+    constexpr mot::BtShape sh = mot::kBtShapes[I];
+    return cudaFuncSetAttribute(mot::sort_step_kernel<sh.cap, sh.d_max, sh.e_cap>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+template <int I>
+static void sort_launch_one(int grid, size_t smem, cudaStream_t st, const mot::SortArgs& a) {
+    constexpr mot::BtShape sh = mot::kBtShapes[I];
+    mot::sort_step_kernel<sh.cap, sh.d_max, sh.e_cap><<<grid, mot::kSortThreads, smem, st>>>(a);
+}
+static cudaError_t sort_prepare(int shape, size_t smem) {
+    switch (shape) {
+        case 0: return sort_set_smem<0>(smem);
+        case 1: return sort_set_smem<1>(smem);
+        case 2: return sort_set_smem<2>(smem);
+        default: return sort_set_smem<3>(smem);
+    }
+}
+static void sort_launch(int shape, int grid, size_t smem, cudaStream_t st, const mot::SortArgs& a) {
+    switch (shape) {
+        case 0: sort_launch_one<0>(grid, smem, st, a); break;
+        case 1: sort_launch_one<1>(grid, smem, st, a); break;
+        case 2: sort_launch_one<2>(grid, smem, st, a); break;
+        default: sort_launch_one<3>(grid, smem, st, a); break;
+    }
+}
+
+// one launch covering streams [s0, s1) for T frames, whatever the tracker kind
+static void engine_launch(mot_engine* e, int T, const float* dets, const int* nd, int ld_dets, float* out, int* nout,
+                          int ld_out, int s0, int s1, cudaStream_t st);
+
 static mot::BtArgs make_args(mot_engine* e, int T, const float* dets, const int* nd, int ld_dets, float* out, int* nout,
                              int ld_out, int s_begin, int s_end) {
     mot::BtArgs a{};
@@ -130,6 +170,20 @@ static mot::BtArgs make_args(mot_engine* e, int T, const float* dets, const int*
     a.T = T; a.S = e->cfg.n_streams; a.s_begin = s_begin; a.s_end = s_end;
     a.ld_dets = ld_dets; a.ld_out = ld_out; a.e_cap = e->e_cap; a.p = e->bt;
     return a;
+}
+
+static void engine_launch(mot_engine* e, int T, const float* dets, const int* nd, int ld_dets, float* out, int* nout,
+                          int ld_out, int s0, int s1, cudaStream_t st) {
+    if (e->cfg.kind == MOT_TRACKER_SORT) {
+        mot::SortArgs a{};
+        a.state = e->d_state; a.dets = dets; a.n_dets = nd; a.out = out; a.n_out = nout;
+        a.T = T; a.S = e->cfg.n_streams; a.ld_dets = ld_dets; a.ld_out = ld_out; a.s_begin = s0; a.s_end = s1;
+        a.p = e->sortp;
+        sort_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
+    } else {
+        mot::BtArgs a = make_args(e, T, dets, nd, ld_dets, out, nout, ld_out, s0, s1);
+        bt_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
+    }
 }
 
 template <class T>
@@ -218,8 +272,8 @@ int mot_engine_default_config(int kind, mot_engine_config* c) {
 int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     if (!cfg || !out) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
     *out = nullptr;
-    if (cfg->kind != MOT_TRACKER_BYTETRACK)
-        return fail(MOT_ERR_UNSUPPORTED, "tracker kind %d is not built in this library version (ByteTrack = 1 is)", cfg->kind);
+    if (cfg->kind != MOT_TRACKER_BYTETRACK && cfg->kind != MOT_TRACKER_SORT)
+        return fail(MOT_ERR_UNSUPPORTED, "tracker kind %d is not built in this library version (SORT = 0 and ByteTrack = 1 are)", cfg->kind);
     if (cfg->n_streams <= 0) return fail(MOT_ERR_INVALID_ARGUMENT, "n_streams must be positive");
     if (int rc = require_device()) return rc;
     MOT_CUDA(cudaSetDevice(cfg->device));
@@ -242,12 +296,21 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     // BaseTracker ctor fix-up (src/tracker.cpp:37-39)
     if (e->cfg.max_age >= e->cfg.max_obs) e->cfg.max_obs = e->cfg.max_age + 5;
     e->layout = mot::BtLayout::make(e->cfg.track_capacity, e->cfg.max_dets);
+    e->sort_layout = mot::SortLayout::make(e->cfg.track_capacity, e->cfg.max_dets);
     e->bt.min_conf = cfg->min_conf;
     e->bt.track_thresh = cfg->track_thresh;
     e->bt.match_thresh = cfg->match_thresh;
     e->bt.det_thresh = cfg->track_thresh;                                        // bytetrack.cpp:145
     e->bt.max_time_lost = (int)(cfg->frame_rate / 30.0f * cfg->track_buffer);    // bytetrack.cpp:141-142
-    e->smem_bytes = mot::bt_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap);
+    e->sortp.det_thresh = cfg->det_thresh;
+    e->sortp.iou_threshold = cfg->iou_threshold;
+    e->sortp.max_age = cfg->max_age;
+    e->sortp.min_hits = cfg->min_hits;
+    const bool is_sort = cfg->kind == MOT_TRACKER_SORT;
+    e->stride = is_sort ? e->sort_layout.stride : e->layout.stride;
+    e->threads = is_sort ? mot::kSortThreads : mot::kBtThreads;
+    e->smem_bytes = is_sort ? mot::sort_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap)
+                            : mot::bt_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap);
     int max_optin = 0;
     MOT_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
     if (e->smem_bytes > (size_t)max_optin) {
@@ -256,12 +319,12 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
         return fail(MOT_ERR_INVALID_ARGUMENT, "track_capacity/max_dets need %zu B of shared memory per CTA (limit %d)",
                     need, max_optin);
     }
-    MOT_CUDA(bt_prepare(e->shape, e->smem_bytes));
+    MOT_CUDA(is_sort ? sort_prepare(e->shape, e->smem_bytes) : bt_prepare(e->shape, e->smem_bytes));
     e->n_chunks = cfg->n_chunks > 0 ? std::min(cfg->n_chunks, kMaxChunks) : (cfg->n_streams >= 128 ? 8 : (cfg->n_streams >= 32 ? 4 : 1));
     e->n_chunks = std::min(e->n_chunks, cfg->n_streams);
     for (int c = 0; c < e->n_chunks; ++c) MOT_CUDA(cudaStreamCreateWithFlags(&e->streams[c], cudaStreamNonBlocking));
-    MOT_CUDA(cudaMalloc(&e->d_state, e->layout.stride * (size_t)cfg->n_streams));
-    MOT_CUDA(cudaMemsetAsync(e->d_state, 0, e->layout.stride * (size_t)cfg->n_streams, e->streams[0]));
+    MOT_CUDA(cudaMalloc(&e->d_state, e->stride * (size_t)cfg->n_streams));
+    MOT_CUDA(cudaMemsetAsync(e->d_state, 0, e->stride * (size_t)cfg->n_streams, e->streams[0]));
     if (int rc = engine_reset_impl(e, 0)) { mot_engine_destroy(e); return rc; }
     *out = e;
     return MOT_OK;
@@ -290,8 +353,7 @@ int mot_engine_update_device(mot_engine* e, int T, const float* d_dets, const in
     if (T <= 0 || ld_dets <= 0 || ld_out <= 0) return fail(MOT_ERR_INVALID_ARGUMENT, "non-positive size");
     if ((ld_out * 8 * sizeof(float)) % 16 != 0 || (((size_t)d_out) & 15)) return fail(MOT_ERR_INVALID_ARGUMENT, "out must be 16-byte aligned");
     const int S = e->cfg.n_streams;
-    mot::BtArgs a = make_args(e, T, d_dets, d_n_dets, ld_dets, d_out, d_n_out, ld_out, 0, S);
-    bt_launch(e->shape, S, e->smem_bytes, (cudaStream_t)stream, a);
+    engine_launch(e, T, d_dets, d_n_dets, ld_dets, d_out, d_n_out, ld_out, 0, S, (cudaStream_t)stream);
     MOT_CUDA(cudaGetLastError());
     return MOT_OK;
 }
@@ -318,8 +380,7 @@ int mot_engine_update_host(mot_engine* e, int T, const float* dets, const int* n
                                    S * det_row, (s1 - s0) * det_row, T, cudaMemcpyHostToDevice, st));
         MOT_CUDA(cudaMemcpy2DAsync(e->d_ndets + s0, S * sizeof(int), n_dets + s0, S * sizeof(int),
                                    (s1 - s0) * sizeof(int), T, cudaMemcpyHostToDevice, st));
-        mot::BtArgs a = make_args(e, T, e->d_dets, e->d_ndets, ld_dets, e->d_out, e->d_nout, ld_out, s0, s1);
-        bt_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
+        engine_launch(e, T, e->d_dets, e->d_ndets, ld_dets, e->d_out, e->d_nout, ld_out, s0, s1, st);
         MOT_CUDA(cudaGetLastError());
         MOT_CUDA(cudaMemcpy2DAsync(out + (size_t)s0 * ld_out * 8, S * out_row, e->d_out + (size_t)s0 * ld_out * 8,
                                    S * out_row, (s1 - s0) * out_row, T, cudaMemcpyDeviceToHost, st));
@@ -336,7 +397,7 @@ int mot_engine_check(mot_engine* e, int* flags) {
     MOT_CUDA(cudaDeviceSynchronize());
     const int S = e->cfg.n_streams;
     std::vector<int> err(S);
-    MOT_CUDA(cudaMemcpy2D(err.data(), sizeof(int), e->d_state + sizeof(int) * mot::kHdrError, e->layout.stride,
+    MOT_CUDA(cudaMemcpy2D(err.data(), sizeof(int), e->d_state + sizeof(int) * mot::kHdrError, e->stride,
                           sizeof(int), S, cudaMemcpyDeviceToHost));
     int all = 0;
     for (int s = 0; s < S; ++s) { all |= err[s]; if (flags) flags[s] = err[s]; }
@@ -350,12 +411,13 @@ int mot_engine_stream_header(mot_engine* e, int s, int* hdr16) {
     if (!e || !hdr16 || s < 0 || s >= e->cfg.n_streams) return fail(MOT_ERR_INVALID_ARGUMENT, "bad argument");
     MOT_CUDA(cudaSetDevice(e->cfg.device));
     MOT_CUDA(cudaDeviceSynchronize());
-    MOT_CUDA(cudaMemcpy(hdr16, e->d_state + (size_t)s * e->layout.stride, sizeof(int) * mot::kHdrInts, cudaMemcpyDeviceToHost));
+    MOT_CUDA(cudaMemcpy(hdr16, e->d_state + (size_t)s * e->stride, sizeof(int) * mot::kHdrInts, cudaMemcpyDeviceToHost));
     return MOT_OK;
 }
 
 int mot_engine_dump_list(mot_engine* e, int s, int which, float* rows, int cap_rows, int* n_rows) {
     if (!e || !rows || !n_rows || s < 0 || s >= e->cfg.n_streams) return fail(MOT_ERR_INVALID_ARGUMENT, "bad argument");
+    if (e->cfg.kind != MOT_TRACKER_BYTETRACK) return fail(MOT_ERR_UNSUPPORTED, "list dumps exist for ByteTrack engines only");
     MOT_CUDA(cudaSetDevice(e->cfg.device));
     MOT_CUDA(cudaDeviceSynchronize());
     std::vector<unsigned char> slab(e->layout.off_gscratch);
@@ -381,10 +443,10 @@ int mot_engine_dump_list(mot_engine* e, int s, int which, float* rows, int cap_r
 
 int mot_engine_info(mot_engine* e, int* threads, int* smem, int* ctas, int* state_bytes) {
     if (!e) return fail(MOT_ERR_INVALID_ARGUMENT, "null engine");
-    if (threads) *threads = mot::kBtThreads;
+    if (threads) *threads = e->threads;
     if (smem) *smem = (int)e->smem_bytes;
     if (ctas) *ctas = e->cfg.n_streams;
-    if (state_bytes) *state_bytes = (int)e->layout.stride;
+    if (state_bytes) *state_bytes = (int)e->stride;
     return MOT_OK;
 }
 

@@ -113,3 +113,47 @@ int sim_bt_dump(void* hv, int s, int which, float* outrows, int cap_rows) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ SORT engine under the emulator
+#include "../../motcpp_b200/csrc/sort_kernel.cuh"
+
+namespace {
+struct SimSort {
+    mot::SortLayout L;
+    int S;
+    mot::SortParams p;
+    std::vector<unsigned char> state;
+};
+}  // namespace
+
+extern "C" {
+
+void* sim_sort_create(int S, float det_thresh, int max_age, int min_hits, float iou_threshold) {
+    auto* h = new SimSort();
+    h->L = mot::SortLayout::make(256, 64);
+    h->S = S;
+    h->p.det_thresh = det_thresh; h->p.max_age = max_age; h->p.min_hits = min_hits; h->p.iou_threshold = iou_threshold;
+    h->state.assign(h->L.stride * (size_t)S + 256, 0);
+    unsigned char* st = h->state.data();
+    const mot::SortLayout L = h->L;
+    cpusim::launch(dim3(S), dim3(64), 0, [=] { mot::sort_reset_kernel(st, L, S, 0); });
+    return h;
+}
+void sim_sort_destroy(void* hv) { delete (SimSort*)hv; }
+
+int sim_sort_update(void* hv, const float* dets, const int* n_dets, int T, int ld_dets, float* out, int* n_out,
+                    int ld_out, int threads) {
+    auto* h = (SimSort*)hv;
+    mot::SortArgs a{};
+    a.state = h->state.data(); a.dets = dets; a.n_dets = n_dets; a.out = out; a.n_out = n_out;
+    a.T = T; a.S = h->S; a.ld_dets = ld_dets; a.ld_out = ld_out; a.s_begin = 0; a.s_end = h->S; a.p = h->p;
+    const size_t smem = mot::sort_smem_bytes(256, 64, 1024);
+    cpusim::launch(dim3(h->S), dim3(threads), smem, [=] { mot::sort_step_kernel<256, 64, 1024>(a); });
+    return 0;
+}
+void sim_sort_header(void* hv, int s, int* hdr16) {
+    auto* h = (SimSort*)hv;
+    std::memcpy(hdr16, h->state.data() + (size_t)s * h->L.stride, sizeof(int) * 16);
+}
+
+}  // extern "C"

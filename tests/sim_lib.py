@@ -26,6 +26,11 @@ def lib():
         S.sim_bt_dump.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, C.c_int]
         S.sim_bt_dump.restype = C.c_int
         S.sim_bt_destroy.argtypes = [C.c_void_p]
+        S.sim_sort_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_float]
+        S.sim_sort_create.restype = C.c_void_p
+        S.sim_sort_update.argtypes = [C.c_void_p, f32p, i32p, C.c_int, C.c_int, f32p, i32p, C.c_int, C.c_int]
+        S.sim_sort_header.argtypes = [C.c_void_p, C.c_int, i32p]
+        S.sim_sort_destroy.argtypes = [C.c_void_p]
         _LIB = S
     return _LIB
 
@@ -70,3 +75,28 @@ class SimByteTrack:
         buf = np.zeros((max(self.cap, 1), 78), np.float32)
         k = lib().sim_bt_dump(self.h, s, which, buf, self.cap)
         return buf[:k]
+
+
+class SimSort:
+    def __init__(self, n_streams=1, det_thresh=0.3, max_age=1, min_hits=3, iou_threshold=0.3):
+        self.S, self.cap = n_streams, 256
+        self.h = lib().sim_sort_create(n_streams, det_thresh, max_age, min_hits, iou_threshold)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().sim_sort_destroy(self.h)
+            self.h = None
+
+    def update(self, dets, n_dets, threads=128):
+        dets = np.ascontiguousarray(dets, np.float32)
+        T, S, ld, _ = dets.shape
+        n_dets = np.ascontiguousarray(n_dets, np.int32).reshape(T, S)
+        out = np.zeros((T, S, self.cap, 8), np.float32)
+        n_out = np.zeros((T, S), np.int32)
+        lib().sim_sort_update(self.h, dets, n_dets, T, ld, out, n_out, self.cap, threads)
+        return out, n_out
+
+    def header(self, s=0):
+        h = np.zeros(16, np.int32)
+        lib().sim_sort_header(self.h, s, h)
+        return h

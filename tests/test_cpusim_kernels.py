@@ -105,3 +105,40 @@ def test_bytetrack_kernel_multi_stream_sequence(oracle):
         for t in range(T):
             want = ref.update(dets[t, s, :counts[t, s]])
             assert np.array_equal(out[t, s, :n_out[t, s]], want), (s, t)
+
+
+# ------------------------------------------------------------------ SORT kernel
+@pytest.mark.parametrize("sid,args,threads", [(0, (0.3, 1, 3, 0.3), 128), (1, (0.3, 3, 1, 0.3), 64), (2, (0.5, 30, 3, 0.2), 256)])
+def test_sort_kernel_stress_streams(oracle, sid, args, threads):
+    dets, counts = synth.stress_stream(20 + sid, n_frames=150)
+    det_thresh, max_age, min_hits, iou_thr = args
+    sim = sim_lib.SimSort(1, det_thresh, max_age, min_hits, iou_thr)
+    ref = oracle.Sort(det_thresh, max_age, 50, min_hits, iou_thr)
+    seen = 0
+    for t in range(dets.shape[0]):
+        n = int(counts[t])
+        want = ref.update(dets[t, :n])
+        out, n_out = sim.update(dets[t][None, None], np.array([[n]]), threads)
+        got = out[0, 0, :n_out[0, 0]]
+        assert got.shape == want.shape and np.array_equal(got, want), f"frame {t}"
+        assert sim.header()[5] == 0
+        seen += len(want)
+    assert seen > 100
+
+
+def test_sort_kernel_reference_kats():
+    # reference tests/test_sort.cpp:50-68 and :70-85
+    det = np.zeros((1, 1, 64, 6), np.float32)
+    det[0, 0, 0] = [100, 100, 200, 200, 0.9, 0]
+    one, zero = np.array([[1]]), np.array([[0]])
+    s = sim_lib.SimSort(1, 0.3, 3, 1, 0.3)
+    s.update(det, one)
+    s.update(det, one)
+    det[0, 0, 0, :4] = [110, 110, 210, 210]
+    out, n = s.update(det, one)
+    assert n[0, 0] == 1 and int(out[0, 0, 0, 4]) == 1
+    s = sim_lib.SimSort(1, 0.3, 2, 1, 0.3)
+    s.update(det, one)
+    s.update(det, zero)
+    out, n = s.update(det, zero)
+    assert n[0, 0] == 0

@@ -451,3 +451,67 @@ def test_cosine_botsort_embeddings(oracle):
     np.testing.assert_allclose(got, want, atol=COSINE_ATOL, rtol=0)
     # the matching a downstream LAP would make is unchanged by the tolerance
     assert np.array_equal(np.argmin(got, 1), np.argmin(want, 1))
+
+
+# ------------------------------------------------------------------ SORT engine
+@pytest.mark.parametrize("sid,args", [(0, (0.3, 1, 3, 0.3)), (1, (0.3, 3, 1, 0.3)), (2, (0.5, 30, 3, 0.2))])
+def test_sort_stress_streams(oracle, sid, args):
+    dets, counts = synth.stress_stream(20 + sid, n_frames=250)
+    det_thresh, max_age, min_hits, iou_thr = args
+    eng = api.Engine(_lib.TRACKER_SORT, 1, 256, dets.shape[1], det_thresh=det_thresh, max_age=max_age,
+                     min_hits=min_hits, iou_threshold=iou_thr)
+    ref = oracle.Sort(det_thresh, max_age, 50, min_hits, iou_thr)
+    out, n_out = eng.update(dets[:, None], counts[:, None], ld_out=256)        # all frames in one launch
+    eng.check()
+    for t in range(dets.shape[0]):
+        want = ref.update(dets[t, :counts[t]])
+        got = out[t, 0, :n_out[t, 0]]
+        assert got.shape == want.shape and np.array_equal(got, want), f"frame {t}"
+    eng.close()
+
+
+def test_sort_reference_kats():
+    # reference tests/test_sort.cpp:50-68, :70-85, :126-148
+    det = np.array([[100, 100, 200, 200, 0.9, 0]], np.float32)
+    s = api.Sort(0.3, 3, 50, 1)
+    s.update(det); s.update(det)
+    out = s.update(np.array([[110, 110, 210, 210, 0.9, 0]], np.float32))
+    assert out.shape == (1, 8) and int(out[0, 4]) == 1 and out[0, 2] > out[0, 0] and out[0, 3] > out[0, 1]
+    s = api.Sort(0.3, 2, 50, 1)
+    s.update(det); s.update(np.zeros((0, 6), np.float32))
+    assert s.update(np.zeros((0, 6), np.float32)).shape[0] == 0
+    s = api.Sort(0.3, 3, 50, 1)
+    s.update(det); s.update(np.zeros((0, 6), np.float32))
+    out = s.update(det)
+    assert out.shape[0] == 1 and int(out[0, 4]) == 1
+
+
+@pytest.mark.parametrize("seq", ["MOT17_02_FRCNN", "MOT17_04_FRCNN"])
+def test_mot17_mini_sort_and_bytetrack(oracle, seq):
+    """BASELINE configs[0]: SORT on assets/MOT17-mini (committed fixture), every frame in order, plus
+    ByteTrack on the same detections; the whole sequence runs as one launch and must equal the oracle."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "mot17_mini_dets.npz"))
+    frames, dets = z[seq + "_frames"], z[seq + "_dets"]
+    f0, f1 = int(frames.min()), int(frames.max())
+    T = f1 - f0 + 1
+    batch = np.zeros((T, 1, 64, 6), np.float32)
+    counts = np.zeros((T, 1), np.int32)
+    for t in range(T):
+        d = dets[frames == f0 + t]
+        batch[t, 0, :len(d)] = d
+        counts[t, 0] = len(d)
+    for kind, ref, kw in ((_lib.TRACKER_SORT, oracle.Sort(0.3, 1, 50, 3, 0.3),
+                           dict(det_thresh=0.3, max_age=1, max_obs=50, min_hits=3, iou_threshold=0.3)),
+                          (_lib.TRACKER_BYTETRACK, _oracle_bt(oracle), BT_ARGS)):
+        eng = api.Engine(kind, 1, 256, 64, **kw)
+        out, n_out = eng.update(batch, counts, ld_out=256)
+        eng.check()
+        total = 0
+        for t in range(T):
+            want = ref.update(batch[t, 0, :counts[t, 0]])
+            got = out[t, 0, :n_out[t, 0]]
+            assert got.shape == want.shape and np.array_equal(got, want), f"{seq} kind {kind} frame {f0 + t}"
+            total += len(want)
+        assert total == int(z[f"{seq}_{'sort' if kind == _lib.TRACKER_SORT else 'bytetrack'}_digest"][1])
+        eng.close()

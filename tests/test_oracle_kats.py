@@ -217,3 +217,26 @@ def test_bytetrack_kats(oracle):
     # a detection AT track_thresh belongs to neither set (strict comparisons, bytetrack.cpp:190-193)
     bt = oracle.ByteTrack(track_thresh=0.5)
     assert bt.update(np.array([[0, 0, 10, 20, 0.5, 0]], np.float32)).shape[0] == 0
+
+
+# ---------------------------------------------------------------- golden fixture (BASELINE configs[0])
+def test_mot17_mini_fixture_digests(oracle):
+    """tests/golden/mot17_mini_dets.npz: the reference's MOT17-mini detections + digests of the oracle's
+    SORT / ByteTrack outputs recorded when the fixture was made (make_mot17_mini_fixture.py)."""
+    import hashlib
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "mot17_mini_dets.npz"))
+    for seq in ("MOT17_02_FRCNN", "MOT17_04_FRCNN"):
+        frames, dets = z[seq + "_frames"], z[seq + "_dets"]
+        for name, trk in (("sort", oracle.Sort(0.3, 1, 50, 3, 0.3)),
+                          ("bytetrack", oracle.ByteTrack(0.3, 30, 50, 3, 0.3, 0.1, 0.45, 0.8, 30, 30))):
+            h = hashlib.sha256()
+            rows = 0
+            for f in range(int(frames.min()), int(frames.max()) + 1):
+                out = trk.update(dets[frames == f])
+                h.update(np.int32(f).tobytes())
+                h.update(out.tobytes())
+                rows += len(out)
+            want_digest, want_rows = z[f"{seq}_{name}_digest"]
+            assert rows == int(want_rows)
+            assert h.hexdigest() == str(want_digest), f"{seq} {name}: oracle output changed"
