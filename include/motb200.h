@@ -149,6 +149,13 @@ int mot_kf_gating(int kind, const float* recs, int n_tracks, const float* meas4,
  *   2 iou_distance then fuse_score with conf[m] (matching.cpp:130-143) */
 int mot_cost_iou(const float* a, int n, const float* b, int m, const float* conf, float* out, int ld, int mode,
                  void* stream);
+/* OC-SORT association cost (ocsort_assoc::associate, src/trackers/ocsort.cpp:617-700): rows = detections
+ * dets5 (n_dets x 5) [x1,y1,x2,y2,score], columns = tracks: predicted boxes trks4 (n_trks x 4), velocities
+ * vel2 (n_trks x 2) as (dy, dx), k_previous_obs rows prev5 (n_trks x 5) [x1,y1,x2,y2,conf] (conf < 0: none).
+ * out_cost = -(iou + valid * angle * inertia * score) and out_iou (nullable) = iou_batch(dets, trks), both
+ * (n_dets x n_trks) row-major with leading dimension ld.  acosf is the correctly rounded one. */
+int mot_cost_ocm(const float* dets5, int n_dets, const float* trks4, const float* vel2, const float* prev5, int n_trks,
+                 float inertia, float* out_cost, float* out_iou, int ld, void* stream);
 /* embedding_distance(metric="cosine") (src/utils/matching.cpp:67-92): max(0, 1 - t.d/(|t||d| + 1e-10)).
  * t (n x dim), d (m x dim) fp32 row-major; tcgen05 tensor-core contraction with a 3-term bf16
  * split (fp32-level accuracy), out row-major ld. */

@@ -71,6 +71,7 @@ SYMBOLS = {
     "mot_kf_update": (_I, [_I, _VP, _VP, _VP, _LL, _VP, _VP]),
     "mot_kf_gating": (_I, [_I, _VP, _I, _VP, _I, _I, _I, _VP, _VP]),
     "mot_cost_iou": (_I, [_VP, _I, _VP, _I, _VP, _VP, _I, _I, _VP]),
+    "mot_cost_ocm": (_I, [_VP, _I, _VP, _VP, _VP, _I, _F, _VP, _VP, _I, _VP]),
     "mot_cost_cosine": (_I, [_VP, _I, _VP, _I, _I, _VP, _I, _VP]),
     "mot_lap_device": (_I, [_VP, _I, _I, _I, _F, _VP, _VP, _VP]),
     "mot_lap_batch_device": (_I, [_VP, _LL, _I, _VP, _VP, _I, _I, _I, _F, _VP, _VP, _VP]),

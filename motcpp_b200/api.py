@@ -113,6 +113,30 @@ def iou_distance_fused(atracks, btracks, det_confs) -> np.ndarray:
     return iou_batch(atracks, btracks, _mode=2, _conf=det_confs)
 
 
+def ocm_cost(detections, trackers, velocities, previous_obs, vdc_weight: float):
+    """OC-SORT association cost (ocsort_assoc::associate, ocsort.cpp:617-700): detections (N,5) [xyxy,score],
+    trackers (M,4) predicted boxes, velocities (M,2) (dy,dx), previous_obs (M,5) -> (cost, iou), both (N,M),
+    cost = -(iou + valid * angle * vdc_weight * score)."""
+    d = np.ascontiguousarray(detections, np.float32).reshape(-1, 5)
+    t = np.ascontiguousarray(trackers, np.float32).reshape(-1, 4)
+    v = np.ascontiguousarray(velocities, np.float32).reshape(-1, 2)
+    p = np.ascontiguousarray(previous_obs, np.float32).reshape(-1, 5)
+    n, m = d.shape[0], t.shape[0]
+    if v.shape[0] != m or p.shape[0] != m:
+        raise ValueError("velocities / previous_obs must have one row per tracker")
+    if n == 0 or m == 0:
+        return np.zeros((n, m), np.float32), np.zeros((n, m), np.float32)
+    _lib.require_gpu()
+    ld = (m + 3) // 4 * 4
+    dd, dt, dv, dp = (DeviceArray.from_host(x) for x in (d, t, v, p))
+    dc, di = DeviceArray((n, ld)), DeviceArray((n, ld))
+    try:
+        check(load().mot_cost_ocm(dd.ptr, n, dt.ptr, dv.ptr, dp.ptr, m, float(vdc_weight), dc.ptr, di.ptr, ld, None))
+    except MotError as e:
+        _raise(e)
+    return np.ascontiguousarray(dc.download()[:, :m]), np.ascontiguousarray(di.download()[:, :m])
+
+
 def embedding_distance(track_features, det_features, metric: str = "cosine") -> np.ndarray:
     """utils::embedding_distance (matching.cpp:67-107), cosine metric on tensor cores."""
     if metric != "cosine":
@@ -354,9 +378,13 @@ class Engine:
         check(load().mot_engine_stream_header(self._h, stream, h.ctypes.data))
         return h
 
-    def dump(self, stream: int, which: int) -> np.ndarray:
+    def dump(self, stream: int, which: int = 0) -> np.ndarray:
+        """ByteTrack: rows of 78 floats for list `which` (0 active, 1 lost).  OC-SORT: rows of
+        [id, age, hits, hit_streak, time_since_update, conf, cls, det_ind, last_obs 5, velocity 2, x 7, P 49, pad]."""
         hdr = self.header(stream)
         n = int(hdr[0] if which == 0 else hdr[1])
+        if self.cfg.kind == _lib.TRACKER_OCSORT and which != 0:
+            n = 0
         buf = np.zeros((max(n, 1), 78), np.float32)
         k = C.c_int()
         check(load().mot_engine_dump_list(self._h, stream, which, buf.ctypes.data, max(n, 1), C.byref(k)))
@@ -454,6 +482,52 @@ class Sort:
         if n > self._max_dets:
             raise ValueError(f"{n} detections exceed max_dets={self._max_dets}")
         self._dets[0, 0, :n] = dets
+        self._engine.update(self._dets, np.array([[n]], np.int32), self._out, self._n_out)
+        self._engine.check()
+        return self._out[0, 0, :int(self._n_out[0, 0])].copy()
+
+
+class OCSort:
+    """motcpp::trackers::OCSort with the reference's positional constructor
+    (include/motcpp/trackers/ocsort.hpp:88-102).  One stream; for many streams use Engine."""
+
+    def __init__(self, det_thresh=0.2, max_age=30, max_obs=50, min_hits=3, iou_threshold=0.3, per_class=False,
+                 nr_classes=80, asso_func="iou", is_obb=False, min_conf=0.1, delta_t=3, inertia=0.2, use_byte=False,
+                 Q_xy_scaling=0.01, Q_s_scaling=0.0001, track_capacity=1536, max_dets=512, device=0):
+        if asso_func != "iou":
+            raise ValueError("Invalid association mode: " + str(asso_func) + " (only \"iou\" is accelerated)")
+        if per_class or is_obb:
+            raise ValueError("per_class / OBB tracking are outside the accelerated hot path")
+        self._engine = Engine(_lib.TRACKER_OCSORT, 1, track_capacity, max_dets, device, det_thresh=det_thresh,
+                              max_age=max_age, max_obs=max_obs, min_hits=min_hits, iou_threshold=iou_threshold,
+                              min_conf=min_conf, delta_t=delta_t, inertia=inertia, use_byte=int(bool(use_byte)),
+                              q_xy_scaling=Q_xy_scaling, q_s_scaling=Q_s_scaling)
+        self._max_dets = self._engine.cfg.max_dets
+        self._cap = self._engine.cfg.track_capacity
+        self._dets = np.zeros((1, 1, self._max_dets, 6), np.float32)
+        self._out = np.empty((1, 1, self._cap, 8), np.float32)
+        self._n_out = np.empty((1, 1), np.int32)
+
+    def reset(self):
+        self._engine.reset()
+
+    def update(self, dets, img, embs=None) -> np.ndarray:
+        dets = np.asarray(dets, np.float32)
+        if dets.ndim != 2:
+            dets = dets.reshape(0, 6) if dets.size == 0 else dets
+        # BaseTracker::check_inputs (src/tracker.cpp:108-125)
+        if dets.shape[0] > 0 and dets.shape[1] not in (6, 7):
+            raise ValueError("Detections must have 6 (AABB) or 7 (OBB) columns")
+        if _Image(img).empty():
+            raise ValueError("Image cannot be empty")
+        if embs is not None and np.shape(embs)[0] > 0 and np.shape(embs)[0] != dets.shape[0]:
+            raise ValueError("Detections and embeddings must have same number of rows")
+        if dets.shape[0] > 0 and dets.shape[1] == 7:
+            raise ValueError("OBB detections are outside the accelerated hot path")
+        n = dets.shape[0]
+        if n > self._max_dets:
+            raise ValueError(f"{n} detections exceed max_dets={self._max_dets}")
+        self._dets[0, 0, :n] = dets[:, :6] if n else 0
         self._engine.update(self._dets, np.array([[n]], np.int32), self._out, self._n_out)
         self._engine.check()
         return self._out[0, 0, :int(self._n_out[0, 0])].copy()

@@ -18,6 +18,7 @@
 #include "kernels_lap.cuh"
 #include "kernels_cosine.cuh"
 #include "sort_kernel.cuh"
+#include "ocsort_kernel.cuh"
 
 namespace {
 
@@ -71,6 +72,8 @@ struct mot_engine {
     mot_engine_config cfg;
     mot::BtLayout layout;          // ByteTrack slab layout (kind == BYTETRACK)
     mot::SortLayout sort_layout;   // SORT slab layout (kind == SORT)
+    mot::OcLayout oc_layout;       // OC-SORT slab layout (kind == OCSORT)
+    mot::OcParams ocp;
     size_t stride = 0;             // bytes per stream slab (whichever layout is live)
     int threads = 0;
     mot::BtParams bt;
@@ -94,6 +97,8 @@ static int engine_reset_impl(mot_engine* e, int keep_ids) {
     const int grid = std::min(e->cfg.n_streams, 4096);
     if (e->cfg.kind == MOT_TRACKER_SORT)
         mot::sort_reset_kernel<<<grid, 256, 0, e->streams[0]>>>(e->d_state, e->sort_layout, e->cfg.n_streams, keep_ids);
+    else if (e->cfg.kind == MOT_TRACKER_OCSORT)
+        mot::ocsort_reset_kernel<<<grid, 256, 0, e->streams[0]>>>(e->d_state, e->oc_layout, e->cfg.n_streams, keep_ids);
     else
         mot::bytetrack_reset_kernel<<<grid, 256, 0, e->streams[0]>>>(e->d_state, e->layout, e->cfg.n_streams, keep_ids);
     MOT_CUDA(cudaGetLastError());
@@ -158,6 +163,33 @@ static void sort_launch(int shape, int grid, size_t smem, cudaStream_t st, const
     }
 }
 
+template <int I>
+static cudaError_t oc_set_smem(size_t bytes) {
+    constexpr mot::OcShape sh = mot::kOcShapes[I];
+    return cudaFuncSetAttribute(mot::ocsort_step_kernel<sh.cap, sh.d_max, sh.e_cap>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+template <int I>
+static void oc_launch_one(int grid, size_t smem, cudaStream_t st, const mot::OcArgs& a) {
+    constexpr mot::OcShape sh = mot::kOcShapes[I];
+    mot::ocsort_step_kernel<sh.cap, sh.d_max, sh.e_cap><<<grid, mot::kOcThreads, smem, st>>>(a);
+}
+static cudaError_t oc_prepare(int shape, size_t smem) {
+    switch (shape) {
+        case 0: return oc_set_smem<0>(smem);
+        case 1: return oc_set_smem<1>(smem);
+        default: return oc_set_smem<2>(smem);
+    }
+}
+static void oc_launch(int shape, int grid, size_t smem, cudaStream_t st, const mot::OcArgs& a) {
+    switch (shape) {
+        case 0: oc_launch_one<0>(grid, smem, st, a); break;
+        case 1: oc_launch_one<1>(grid, smem, st, a); break;
+        default: oc_launch_one<2>(grid, smem, st, a); break;
+    }
+}
+static_assert(mot::kNumOcShapes == 3, "update the OC-SORT dispatch switches");
+
 // one launch covering streams [s0, s1) for T frames, whatever the tracker kind
 static void engine_launch(mot_engine* e, int T, const float* dets, const int* nd, int ld_dets, float* out, int* nout,
                           int ld_out, int s0, int s1, cudaStream_t st);
@@ -180,6 +212,12 @@ static void engine_launch(mot_engine* e, int T, const float* dets, const int* nd
         a.T = T; a.S = e->cfg.n_streams; a.ld_dets = ld_dets; a.ld_out = ld_out; a.s_begin = s0; a.s_end = s1;
         a.p = e->sortp;
         sort_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
+    } else if (e->cfg.kind == MOT_TRACKER_OCSORT) {
+        mot::OcArgs a{};
+        a.state = e->d_state; a.dets = dets; a.n_dets = nd; a.out = out; a.n_out = nout;
+        a.T = T; a.S = e->cfg.n_streams; a.ld_dets = ld_dets; a.ld_out = ld_out; a.s_begin = s0; a.s_end = s1;
+        a.p = e->ocp;
+        oc_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
     } else {
         mot::BtArgs a = make_args(e, T, dets, nd, ld_dets, out, nout, ld_out, s0, s1);
         bt_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
@@ -272,31 +310,41 @@ int mot_engine_default_config(int kind, mot_engine_config* c) {
 int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     if (!cfg || !out) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
     *out = nullptr;
-    if (cfg->kind != MOT_TRACKER_BYTETRACK && cfg->kind != MOT_TRACKER_SORT)
-        return fail(MOT_ERR_UNSUPPORTED, "tracker kind %d is not built in this library version (SORT = 0 and ByteTrack = 1 are)", cfg->kind);
+    if (cfg->kind != MOT_TRACKER_BYTETRACK && cfg->kind != MOT_TRACKER_SORT && cfg->kind != MOT_TRACKER_OCSORT)
+        return fail(MOT_ERR_UNSUPPORTED, "tracker kind %d is not built in this library version (SORT = 0, ByteTrack = 1 and OC-SORT = 2 are)", cfg->kind);
     if (cfg->n_streams <= 0) return fail(MOT_ERR_INVALID_ARGUMENT, "n_streams must be positive");
+    if (cfg->kind == MOT_TRACKER_OCSORT && (cfg->delta_t < 1 || cfg->delta_t > mot::kOcRing))
+        return fail(MOT_ERR_UNSUPPORTED, "delta_t %d is outside 1..%d (observation ring size)", cfg->delta_t, mot::kOcRing);
     if (int rc = require_device()) return rc;
     MOT_CUDA(cudaSetDevice(cfg->device));
     mot_engine* e = new mot_engine();
     e->cfg = *cfg;
+    const bool is_sort = cfg->kind == MOT_TRACKER_SORT, is_oc = cfg->kind == MOT_TRACKER_OCSORT;
     if (e->cfg.track_capacity <= 0) e->cfg.track_capacity = 1536;
     if (e->cfg.max_dets <= 0) e->cfg.max_dets = 512;
     // round the request up to the nearest shape the kernel is instantiated for
     e->shape = -1;
-    for (int i = 0; i < mot::kNumBtShapes; ++i)
-        if (mot::kBtShapes[i].cap >= e->cfg.track_capacity && mot::kBtShapes[i].d_max >= e->cfg.max_dets) { e->shape = i; break; }
+    if (is_oc) {
+        for (int i = 0; i < mot::kNumOcShapes; ++i)
+            if (mot::kOcShapes[i].cap >= e->cfg.track_capacity && mot::kOcShapes[i].d_max >= e->cfg.max_dets) { e->shape = i; break; }
+    } else {
+        for (int i = 0; i < mot::kNumBtShapes; ++i)
+            if (mot::kBtShapes[i].cap >= e->cfg.track_capacity && mot::kBtShapes[i].d_max >= e->cfg.max_dets) { e->shape = i; break; }
+    }
     if (e->shape < 0) {
         const int tc = e->cfg.track_capacity, md = e->cfg.max_dets;
         delete e;
-        return fail(MOT_ERR_INVALID_ARGUMENT, "track_capacity %d / max_dets %d exceed the largest built shape (3072 tracks / 1024 detections)", tc, md);
+        return fail(MOT_ERR_INVALID_ARGUMENT, "track_capacity %d / max_dets %d exceed the largest built shape (%s)", tc, md,
+                    is_oc ? "3072 tracks / 2048 detections" : "3072 tracks / 1024 detections");
     }
-    e->cfg.track_capacity = mot::kBtShapes[e->shape].cap;
-    e->cfg.max_dets = mot::kBtShapes[e->shape].d_max;
-    e->e_cap = mot::kBtShapes[e->shape].e_cap;
+    e->cfg.track_capacity = is_oc ? mot::kOcShapes[e->shape].cap : mot::kBtShapes[e->shape].cap;
+    e->cfg.max_dets = is_oc ? mot::kOcShapes[e->shape].d_max : mot::kBtShapes[e->shape].d_max;
+    e->e_cap = is_oc ? mot::kOcShapes[e->shape].e_cap : mot::kBtShapes[e->shape].e_cap;
     // BaseTracker ctor fix-up (src/tracker.cpp:37-39)
     if (e->cfg.max_age >= e->cfg.max_obs) e->cfg.max_obs = e->cfg.max_age + 5;
     e->layout = mot::BtLayout::make(e->cfg.track_capacity, e->cfg.max_dets);
     e->sort_layout = mot::SortLayout::make(e->cfg.track_capacity, e->cfg.max_dets);
+    e->oc_layout = mot::OcLayout::make(e->cfg.track_capacity, e->cfg.max_dets);
     e->bt.min_conf = cfg->min_conf;
     e->bt.track_thresh = cfg->track_thresh;
     e->bt.match_thresh = cfg->match_thresh;
@@ -306,10 +354,20 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     e->sortp.iou_threshold = cfg->iou_threshold;
     e->sortp.max_age = cfg->max_age;
     e->sortp.min_hits = cfg->min_hits;
-    const bool is_sort = cfg->kind == MOT_TRACKER_SORT;
-    e->stride = is_sort ? e->sort_layout.stride : e->layout.stride;
-    e->threads = is_sort ? mot::kSortThreads : mot::kBtThreads;
+    e->ocp.det_thresh = cfg->det_thresh;
+    e->ocp.iou_threshold = cfg->iou_threshold;                                   // asso_threshold_ (ocsort.cpp:195)
+    e->ocp.min_conf = cfg->min_conf;
+    e->ocp.inertia = cfg->inertia;
+    e->ocp.q44 = 0.01f * cfg->q_xy_scaling;                                      // xysr_kf.cpp:58-61 then ocsort.cpp:77-79, in fp32
+    e->ocp.q66 = 0.0001f * cfg->q_s_scaling;
+    e->ocp.max_age = cfg->max_age;
+    e->ocp.min_hits = cfg->min_hits;
+    e->ocp.delta_t = cfg->delta_t;
+    e->ocp.use_byte = cfg->use_byte;
+    e->stride = is_sort ? e->sort_layout.stride : (is_oc ? e->oc_layout.stride : e->layout.stride);
+    e->threads = is_sort ? mot::kSortThreads : (is_oc ? mot::kOcThreads : mot::kBtThreads);
     e->smem_bytes = is_sort ? mot::sort_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap)
+                  : is_oc   ? mot::oc_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap)
                             : mot::bt_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap);
     int max_optin = 0;
     MOT_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
@@ -319,7 +377,8 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
         return fail(MOT_ERR_INVALID_ARGUMENT, "track_capacity/max_dets need %zu B of shared memory per CTA (limit %d)",
                     need, max_optin);
     }
-    MOT_CUDA(is_sort ? sort_prepare(e->shape, e->smem_bytes) : bt_prepare(e->shape, e->smem_bytes));
+    MOT_CUDA(is_sort ? sort_prepare(e->shape, e->smem_bytes)
+                     : (is_oc ? oc_prepare(e->shape, e->smem_bytes) : bt_prepare(e->shape, e->smem_bytes)));
     e->n_chunks = cfg->n_chunks > 0 ? std::min(cfg->n_chunks, kMaxChunks) : (cfg->n_streams >= 128 ? 8 : (cfg->n_streams >= 32 ? 4 : 1));
     e->n_chunks = std::min(e->n_chunks, cfg->n_streams);
     for (int c = 0; c < e->n_chunks; ++c) MOT_CUDA(cudaStreamCreateWithFlags(&e->streams[c], cudaStreamNonBlocking));
@@ -417,9 +476,35 @@ int mot_engine_stream_header(mot_engine* e, int s, int* hdr16) {
 
 int mot_engine_dump_list(mot_engine* e, int s, int which, float* rows, int cap_rows, int* n_rows) {
     if (!e || !rows || !n_rows || s < 0 || s >= e->cfg.n_streams) return fail(MOT_ERR_INVALID_ARGUMENT, "bad argument");
-    if (e->cfg.kind != MOT_TRACKER_BYTETRACK) return fail(MOT_ERR_UNSUPPORTED, "list dumps exist for ByteTrack engines only");
+    if (e->cfg.kind != MOT_TRACKER_BYTETRACK && e->cfg.kind != MOT_TRACKER_OCSORT)
+        return fail(MOT_ERR_UNSUPPORTED, "list dumps exist for ByteTrack and OC-SORT engines only");
     MOT_CUDA(cudaSetDevice(e->cfg.device));
     MOT_CUDA(cudaDeviceSynchronize());
+    if (e->cfg.kind == MOT_TRACKER_OCSORT) {
+        // rows of [id, age, hits, hit_streak, time_since_update, conf, cls, det_ind, last_obs 5, velocity 2, x 7, P 49, pad 7]
+        const mot::OcLayout& L = e->oc_layout;
+        std::vector<unsigned char> slab(L.off_ocm);
+        MOT_CUDA(cudaMemcpy(slab.data(), e->d_state + (size_t)s * L.stride, slab.size(), cudaMemcpyDeviceToHost));
+        const int* hdr = (const int*)slab.data();
+        const unsigned short* list = (const unsigned short*)(slab.data() + L.off_lists);
+        const int* m = (const int*)(slab.data() + L.off_meta);
+        const float* obs = (const float*)(slab.data() + L.off_obs);
+        const float* recs = (const float*)(slab.data() + L.off_recs);
+        const int n = which == 0 ? hdr[mot::kOHdrTracks] : 0, cap = L.cap;
+        int k = 0;
+        for (; k < n && k < cap_rows; ++k) {
+            const int slot = list[k];
+            float* o = rows + 78 * (size_t)k;
+            std::memset(o, 0, 78 * sizeof(float));
+            o[0] = (float)m[slot]; o[1] = (float)m[cap + slot]; o[2] = (float)m[2 * cap + slot]; o[3] = (float)m[3 * cap + slot];
+            o[4] = (float)m[4 * cap + slot]; o[5] = ((const float*)m)[7 * cap + slot]; o[6] = (float)m[5 * cap + slot];
+            o[7] = (float)m[6 * cap + slot];
+            std::memcpy(o + 8, obs + (size_t)slot * mot::kOcObsFloats, 7 * sizeof(float));
+            std::memcpy(o + 15, recs + (size_t)slot * mot::kOcRecFloats, 56 * sizeof(float));
+        }
+        *n_rows = k;
+        return MOT_OK;
+    }
     std::vector<unsigned char> slab(e->layout.off_gscratch);
     MOT_CUDA(cudaMemcpy(slab.data(), e->d_state + (size_t)s * e->layout.stride, slab.size(), cudaMemcpyDeviceToHost));
     const mot::BtLayout& L = e->layout;
@@ -530,6 +615,21 @@ int mot_cost_iou(const float* a, int n, const float* b, int m, const float* conf
     const int row_groups = (n + mot::kCostTileRows - 1) / mot::kCostTileRows;
     dim3 grid((unsigned)std::min(row_groups, sm_count() * 8), (unsigned)std::min(col_tiles, 64));
     mot::iou_cost_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, n, b, m, conf, out, ld, mode);
+    MOT_CUDA(cudaGetLastError());
+    return MOT_OK;
+}
+
+int mot_cost_ocm(const float* dets5, int n_dets, const float* trks4, const float* vel2, const float* prev5, int n_trks,
+                 float inertia, float* out_cost, float* out_iou, int ld, void* stream) {
+    if (n_dets < 0 || n_trks < 0 || ld < n_trks) return fail(MOT_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (n_dets == 0 || n_trks == 0) return MOT_OK;
+    if (!dets5 || !trks4 || !vel2 || !prev5 || !out_cost) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
+    if (int rc = require_device()) return rc;
+    const int col_tiles = (n_trks + mot::kCostTileCols - 1) / mot::kCostTileCols;
+    const int row_groups = (n_dets + mot::kCostTileRows - 1) / mot::kCostTileRows;
+    dim3 grid((unsigned)std::min(row_groups, sm_count() * 8), (unsigned)std::min(col_tiles, 64));
+    mot::ocm_cost_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dets5, n_dets, trks4, vel2, prev5, n_trks, inertia,
+                                                                 out_cost, out_iou, ld);
     MOT_CUDA(cudaGetLastError());
     return MOT_OK;
 }

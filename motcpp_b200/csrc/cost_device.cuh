@@ -66,6 +66,10 @@ __device__ __forceinline__ bool boxes_disjoint(float4 a, float4 b) {
     return !((fminf(a.z, b.z) > fmaxf(a.x, b.x)) && (fminf(a.w, b.w) > fmaxf(a.y, b.y)));
 }
 
+// Tie-break infinitesimal of the OC-SORT assignments (see OcmCost::pair_bias): prefers the higher column, then
+// couples rows and columns so that two rows on two bit-identical columns also have a single optimum.
+__device__ __forceinline__ double twin_bias(int i, int j) { return -(double)(64 * j + ((i * j) & 63)) * 0x1p-50; }
+
 // Cost functor for block_lap(): rows = row_box[i], columns = det_box[col_map[j]];
 // cost = 1 - IoU, optionally fused with the detection score: 1 - (1 - d) * conf.
 // `prune` must only be set when thresh < 1 (a disjoint pair costs exactly 1).
@@ -99,6 +103,8 @@ struct IouCost {
         return dist;
     }
     __device__ __forceinline__ float pair(int i, int j) const { return cost(row(i), j); }
+    __device__ __forceinline__ bool is_candidate(const Row& r, int, int j, float thresh) const { return cost(r, j) <= thresh; }
+    __device__ __forceinline__ double pair_bias(int, int) const { return 0.0; }
 };
 
 }  // namespace mot

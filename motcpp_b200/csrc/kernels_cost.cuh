@@ -7,6 +7,7 @@
 // output (4 B per pair) is the only HBM stream that matters.
 #pragma once
 #include "cost_device.cuh"
+#include "ocm_device.cuh"
 
 namespace mot {
 
@@ -60,6 +61,72 @@ __global__ void __launch_bounds__(256) iou_cost_kernel(const float* __restrict__
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
                         if (q + e < cn) orow[q + e] = v[e];
+                }
+            }
+        }
+    }
+}
+
+// OC-SORT association cost -(iou + angle cost * score) for every (detection, track) pair
+// (ocsort_assoc::associate, ocsort.cpp:617-700).  Rows = detections [x1,y1,x2,y2,score], columns = tracks:
+// predicted box trks4, velocity vel2 = (dy, dx), k_previous_obs prev5 = [x1,y1,x2,y2,conf] (conf < 0 = none).
+// out_cost / out_iou (nullable) are (n_dets x n_trks) row-major with leading dimension ld.  One thread per
+// (detection, 4 tracks); the track tile sits in shared memory.  Issue-bound (one fp64 acos per pair), the 4 B
+// per pair written is the only HBM stream.
+__global__ void __launch_bounds__(256) ocm_cost_kernel(const float* __restrict__ dets5, int n_dets,
+                                                       const float* __restrict__ trks4, const float* __restrict__ vel2,
+                                                       const float* __restrict__ prev5, int n_trks, float inertia,
+                                                       float* __restrict__ out_cost, float* __restrict__ out_iou, int ld) {
+    __shared__ float4 s_box[kCostTileCols];
+    __shared__ float4 s_ocm[kCostTileCols];
+    __shared__ float s_valid[kCostTileCols];
+    const int tid = (int)threadIdx.x;
+    const int tx = tid & 31, ty = tid >> 5;
+    const int col_tiles = (n_trks + kCostTileCols - 1) / kCostTileCols;
+    const int row_groups = (n_dets + kCostTileRows - 1) / kCostTileRows;
+    const bool vec_ok = ((ld & 3) == 0) && ((((size_t)out_cost) & 15) == 0) && ((((size_t)out_iou) & 15) == 0);
+    for (int ct = (int)blockIdx.y; ct < col_tiles; ct += (int)gridDim.y) {
+        const int c0 = ct * kCostTileCols;
+        const int cn = min(kCostTileCols, n_trks - c0);
+        __syncthreads();
+        for (int k = tid; k < cn; k += 256) {
+            const float* p = prev5 + (size_t)(c0 + k) * 5;
+            s_box[k] = *reinterpret_cast<const float4*>(trks4 + (size_t)(c0 + k) * 4);
+            s_ocm[k] = make_float4(xdiv(xadd(p[0], p[2]), 2.0f), xdiv(xadd(p[1], p[3]), 2.0f), vel2[(size_t)(c0 + k) * 2],
+                                   vel2[(size_t)(c0 + k) * 2 + 1]);
+            s_valid[k] = (p[4] >= 0.0f) ? 1.0f : 0.0f;
+        }
+        __syncthreads();
+        for (int rg = (int)blockIdx.x; rg < row_groups; rg += (int)gridDim.x) {
+            const int i = rg * kCostTileRows + ty;
+            if (i >= n_dets) continue;
+            const float* d = dets5 + (size_t)i * 5;
+            const float4 rb = make_float4(d[0], d[1], d[2], d[3]);
+            const float score = d[4];
+            const float area = box_area(rb);
+            const float cx = xdiv(xadd(rb.x, rb.z), 2.0f), cy = xdiv(xadd(rb.y, rb.w), 2.0f);
+            float* crow = out_cost + (size_t)i * ld + c0;
+            float* irow = out_iou ? out_iou + (size_t)i * ld + c0 : nullptr;
+            for (int q = tx * 4; q < cn; q += 128) {
+                float vc[4], vi[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = q + e;
+                    vc[e] = 0.0f; vi[e] = 0.0f;
+                    if (j < cn) {
+                        const float iou = iou_pair(rb, area, s_box[j]);
+                        const float ac = xmul(ocm_angle_cost(cx, cy, s_ocm[j], s_valid[j], inertia), score);
+                        vi[e] = iou;
+                        vc[e] = -xadd(iou, ac);
+                    }
+                }
+                if (vec_ok && q + 3 < cn) {
+                    *reinterpret_cast<float4*>(crow + q) = make_float4(vc[0], vc[1], vc[2], vc[3]);
+                    if (irow) *reinterpret_cast<float4*>(irow + q) = make_float4(vi[0], vi[1], vi[2], vi[3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (q + e < cn) { crow[q + e] = vc[e]; if (irow) irow[q + e] = vi[e]; }
                 }
             }
         }

@@ -118,7 +118,7 @@ __device__ __forceinline__ void team_hungarian(unsigned mask, int tl, const unsi
             double cur = INF;
             if (is_real) {
                 const float cf = cost.pair(i0_id, col_id);
-                if (cf <= thresh) cur = ((double)cf - Ld) - u0 - v;
+                if (cf <= thresh) cur = (((double)cf - Ld) + cost.pair_bias(i0_id, col_id)) - u0 - v;
             } else if (is_col && dummy_of == i0) {
                 cur = 0.0 - u0 - v;
             }
@@ -197,7 +197,7 @@ __device__ __noinline__ void warp_hungarian_big(const LapGlobalScratch ws, int m
                 double cur = INF;
                 if (k < c) {
                     const float cf = cost.pair(i0_id, (int)cols[k]);
-                    if (cf <= thresh) cur = ((double)cf - Ld) - u0 - ws.g_v[p];
+                    if (cf <= thresh) cur = (((double)cf - Ld) + cost.pair_bias(i0_id, (int)cols[k])) - u0 - ws.g_v[p];
                 } else if (k - c == i0) {
                     cur = 0.0 - u0 - ws.g_v[p];
                 }
@@ -250,6 +250,10 @@ __device__ __noinline__ void warp_hungarian_big(const LapGlobalScratch ws, int m
 //     __device__ bool reject(const Row&, int j) const;      // cheap test: true => cost(i,j) > thresh for sure
 //     __device__ float cost(const Row&, int j) const;       // exact fp32 cost
 //     __device__ float pair(int i, int j) const;            // == cost(row(i), j)
+//     __device__ double pair_bias(int i, int j) const;      // 0.0, or an infinitesimal (a multiple of 2^-50 below
+//                          2^-32) added to cost(i,j) in fp64: decides between exactly tied optima only
+//     __device__ bool is_candidate(const Row&, int i, int j, float thresh) const;   // cost(row, j) <= thresh; called
+//                          exactly ONCE per examined pair (step 1 only), so a functor may tally side statistics there
 //   };
 // On return (all threads) ws.row2col[0..n) / ws.col2row[0..m) hold the assignment (-1 = unmatched).
 template <class Cost>
@@ -270,7 +274,7 @@ __device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, 
             const typename Cost::Row rw = cost.row(i);
             for (int j0 = 0; j0 < m; j0 += 32) {
                 const int j = j0 + lane;
-                const bool cand = (j < m) && (cost.cost(rw, j) <= thresh);
+                const bool cand = (j < m) && cost.is_candidate(rw, i, j, thresh);
                 const unsigned ballot = __ballot_sync(kFullMask, cand);
                 if (ballot == 0) continue;
                 int e0 = 0;
@@ -301,7 +305,7 @@ __device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, 
             const typename Cost::Row rw = cost.row(i);
             for (int j = 0; j < m; ++j) {
                 if (cost.reject(rw, j)) continue;
-                if (cost.cost(rw, j) <= thresh) push_edge(i, j);
+                if (cost.is_candidate(rw, i, j, thresh)) push_edge(i, j);
             }
         };
         if (use_grid) {
@@ -324,7 +328,8 @@ __device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, 
                     if (n_pairs <= ws.p_cap) {
                         for (int q = tid; q < n_pairs; q += nt) {
                             const int pk = ws.pairs[q];
-                            if (cost.pair(pk >> 16, pk & 0xffff) <= thresh) push_edge(pk >> 16, pk & 0xffff);
+                            const int pi = pk >> 16, pj = pk & 0xffff;
+                            if (cost.is_candidate(cost.row(pi), pi, pj, thresh)) push_edge(pi, pj);
                         }
                     } else if (i < n) {
                         scan_row(i);                           // pair buffer too small for this chunk
@@ -410,13 +415,14 @@ __device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, 
         const int o0 = off[root], o1 = off[root + 1];
         const int pr = o0 & 0xffff, r = (o1 & 0xffff) - pr;
         const int pc = o0 >> 16, c = (o1 >> 16) - pc;
-        float best = 0.0f;
+        double best = 0.0;
         int bi = -1, bj = -1;
         for (int a = 0; a < r; ++a)
             for (int b = 0; b < c; ++b) {
                 const int i = (int)ws.comp_rows[pr + a], j = (int)ws.comp_cols[pc + b];
-                const float cf = cost.pair(i, j);
-                if (!(cf <= thresh)) continue;
+                const float cf0 = cost.pair(i, j);
+                if (!(cf0 <= thresh)) continue;
+                const double cf = (double)cf0 + cost.pair_bias(i, j);
                 if (bi < 0 || cf < best || (cf == best && (i < bi || (i == bi && j < bj)))) { best = cf; bi = i; bj = j; }
             }
         if (bi >= 0) { ws.row2col[bi] = (short)bj; ws.col2row[bj] = (short)bi; }
@@ -535,6 +541,8 @@ struct MatrixCost {
     __device__ __forceinline__ bool reject(const Row&, int) const { return false; }
     __device__ __forceinline__ float cost(const Row& r, int j) const { return r.p[j]; }
     __device__ __forceinline__ float pair(int i, int j) const { return c[(size_t)i * ld + j]; }
+    __device__ __forceinline__ bool is_candidate(const Row& r, int, int j, float thresh) const { return r.p[j] <= thresh; }
+    __device__ __forceinline__ double pair_bias(int, int) const { return 0.0; }
 };
 
 }  // namespace mot

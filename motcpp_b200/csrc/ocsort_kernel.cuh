@@ -1,0 +1,628 @@
+// ocsort_kernel.cuh - OC-SORT's whole per-frame update() as one kernel, one CTA per camera stream.
+// Replaces reference src/trackers/ocsort.cpp:285-606 (OCSort::update), :610-737 (associate) and
+// :53-156 (KalmanBoxTracker):
+//   confidence split (:311-320)                                         -> phase A
+//   predict every track in place, drop NaN boxes (:337-365)             -> phase B
+//   no tracks: spawn from every high detection, empty output (:367-384) -> early exit
+//   velocities and k_previous_obs of every track (:394-410)             -> phase C
+//   first association: OCM cost, trivial 1:1 shortcut or assignment, IoU filter (:413-420, :610-737) -> phase D
+//   update matched tracks (:423-430)                                    -> phase E
+//   BYTE pass on low-confidence detections (:433-479, use_byte)         -> phase F
+//   re-match leftovers against LAST OBSERVATIONS (:482-545)             -> phase G
+//   update(None) (:548-550), new tracks (:553-561)                      -> phases H, I
+//   output in reverse track order, age-out (:564-592)                   -> phase J
+// Reference quirks kept on purpose (parity trap 8): an assignment pair rejected by the
+// IoU filter is pushed to BOTH unmatched lists and then added again by the final sweep, so those
+// lists can hold an index twice; the re-match then sees duplicated rows / columns, a track can be
+// updated twice in one frame and a detection can spawn two tracks.  The lists here keep the
+// duplicates, in the reference's order.
+// State: [x 7 | P 7x7] fp32 padded to 64 floats, per-track observation ring (the reference's unbounded
+// age -> bbox map is only ever queried for the last delta_t ages, else for its newest entry, which is
+// last_observation), IDs from a per-stream counter.
+#pragma once
+#include "block_utils.cuh"
+#include "cost_device.cuh"
+#include "kf_device.cuh"
+#include "lap_device.cuh"
+#include "ocm_device.cuh"
+
+namespace mot {
+
+#ifndef MOT_OC_THREADS
+#define MOT_OC_THREADS 512
+#endif
+constexpr int kOcThreads = MOT_OC_THREADS;
+constexpr int kOcRecFloats = 64;       // 56 used
+constexpr int kOcRing = 8;             // observation ring entries per track: delta_t <= kOcRing
+constexpr int kOcObsFloats = 8;        // last_observation[5], velocity (dy, dx), pad
+
+enum : int {
+    kOHdrTracks = 0, kOHdrFree = 2, kOHdrIdCounter = 3, kOHdrFrame = 4, kOHdrError = 5,
+    kOHdrNHigh = 6, kOHdrNTrk = 7, kOHdrUsedLap = 8, kOHdrMatched = 9, kOHdrLeftDets = 10, kOHdrLeftTrks = 11,
+    kOHdrRematched = 12, kOHdrSpawned = 13
+};
+
+struct OcParams {
+    float det_thresh, iou_threshold, min_conf, inertia;
+    float q44, q66;                    // fl(0.01f * Q_xy_scaling), fl(0.0001f * Q_s_scaling)
+    int max_age, min_hits, delta_t, use_byte;
+};
+
+struct OcLayout {
+    int cap, d_max;
+    size_t off_lists, off_meta, off_obs, off_ring_box, off_ring_conf, off_ring_age, off_recs, off_ocm, off_valid,
+        off_gscratch, stride;
+    MOT_HD static constexpr size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+    MOT_HD static constexpr OcLayout make(int cap, int d_max) {
+        OcLayout L{};
+        L.cap = cap; L.d_max = d_max;
+        size_t o = al(sizeof(int) * 16);
+        L.off_lists = o;     o = al(o + sizeof(unsigned short) * 2 * (size_t)cap);
+        L.off_meta = o;      o = al(o + sizeof(int) * 8 * (size_t)cap);
+        L.off_obs = o;       o = al(o + sizeof(float) * kOcObsFloats * (size_t)cap);
+        L.off_ring_box = o;  o = al(o + sizeof(float4) * kOcRing * (size_t)cap);
+        L.off_ring_conf = o; o = al(o + sizeof(float) * kOcRing * (size_t)cap);
+        L.off_ring_age = o;  o = al(o + sizeof(int) * kOcRing * (size_t)cap);
+        L.off_recs = o;      o = al(o + sizeof(float) * kOcRecFloats * (size_t)cap);
+        L.off_ocm = o;       o = al(o + sizeof(float4) * (size_t)cap);
+        L.off_valid = o;     o = al(o + (size_t)cap);
+        L.off_gscratch = o;  o = al(o + lap_gscratch_bytes(d_max, cap));
+        L.stride = o;
+        return L;
+    }
+};
+
+struct OcStream {
+    int* hdr;
+    unsigned short *list, *freel;
+    int *id, *age, *hits, *streak, *tsu, *cls, *det_ind;
+    float* conf;
+    float* obs;                // [cap][8]
+    float4* ring_box;          // [cap][kOcRing]
+    float* ring_conf;
+    int* ring_age;
+    float* recs;
+    float4* ocm;               // per-frame scratch, indexed by track POSITION
+    unsigned char* valid;
+    unsigned char* gscratch;
+    __device__ __forceinline__ static OcStream at(unsigned char* base, const OcLayout& L) {
+        OcStream s;
+        s.hdr = (int*)base;
+        s.list = (unsigned short*)(base + L.off_lists);
+        s.freel = s.list + L.cap;
+        int* m = (int*)(base + L.off_meta);
+        s.id = m; s.age = m + L.cap; s.hits = m + 2 * L.cap; s.streak = m + 3 * L.cap; s.tsu = m + 4 * L.cap;
+        s.cls = m + 5 * L.cap; s.det_ind = m + 6 * L.cap; s.conf = (float*)(m + 7 * L.cap);
+        s.obs = (float*)(base + L.off_obs);
+        s.ring_box = (float4*)(base + L.off_ring_box);
+        s.ring_conf = (float*)(base + L.off_ring_conf);
+        s.ring_age = (int*)(base + L.off_ring_age);
+        s.recs = (float*)(base + L.off_recs);
+        s.ocm = (float4*)(base + L.off_ocm);
+        s.valid = base + L.off_valid;
+        s.gscratch = base + L.off_gscratch;
+        return s;
+    }
+};
+
+struct OcArgs {
+    unsigned char* state;
+    const float* dets;        // [T][S][ld_dets][6]
+    const int* n_dets;        // [T][S]
+    float* out;               // [T][S][ld_out][8]
+    int* n_out;               // [T][S]
+    int T, S, ld_dets, ld_out;
+    int s_begin, s_end;
+    OcParams p;
+};
+
+struct OcSmem {
+    float4* det_box;            // [d_max] raw xyxy
+    float* det_conf;            // [d_max]
+    unsigned short* high;       // [d_max] conf > det_thresh
+    unsigned short* second;     // [d_max] min_conf < conf < det_thresh (use_byte)
+    unsigned short* ud;         // [d_max] unmatched detections (detection indices, duplicates kept)
+    unsigned short* ud2;        // [d_max]
+    unsigned short* pair_det;   // [d_max] detection of every update pair
+    unsigned char* det_flag;    // [d_max] per detection / per row: 0 none, 1 kept match, 2 filtered; later "gone"
+    float4* trk_box;            // [cap] predicted boxes, later last observations
+    unsigned short* list_a;     // [cap] live track slots in order
+    unsigned short* ut;         // [cap] unmatched tracks (track POSITIONS, duplicates kept)
+    unsigned short* ut2;        // [cap]
+    unsigned short* pair_trk;   // [cap] track position of every update pair
+    unsigned char* trk_flag;    // [cap]
+    unsigned* row_bits;         // [d_max / 32]
+    unsigned* col_bits;         // [cap / 32]
+    int* flags;                 // [4]
+    BlockScratch* bs;
+    LapWorkspace lap;
+};
+
+MOT_HD constexpr size_t oc_smem_bytes(int cap, int d_max, int e_cap) {
+    size_t b = 0;
+    b += lap_align16(sizeof(float4) * (size_t)d_max);
+    b += lap_align16(sizeof(float) * (size_t)d_max);
+    b += 5 * lap_align16(sizeof(unsigned short) * (size_t)d_max);
+    b += lap_align16((size_t)d_max);
+    b += lap_align16(sizeof(float4) * (size_t)cap);
+    b += 4 * lap_align16(sizeof(unsigned short) * (size_t)cap);
+    b += lap_align16((size_t)cap);
+    b += lap_align16(sizeof(unsigned) * (size_t)((d_max + 31) / 32));
+    b += lap_align16(sizeof(unsigned) * (size_t)((cap + 31) / 32));
+    b += lap_align16(sizeof(int) * 4);
+    b += lap_align16(sizeof(BlockScratch));
+    b += lap_smem_bytes(d_max, cap, e_cap);
+    return b;
+}
+
+__device__ __forceinline__ void oc_carve(unsigned char* p, int cap, int d_max, int e_cap, OcSmem& s) {
+    s.det_box = (float4*)p;             p += lap_align16(sizeof(float4) * (size_t)d_max);
+    s.det_conf = (float*)p;             p += lap_align16(sizeof(float) * (size_t)d_max);
+    s.high = (unsigned short*)p;        p += lap_align16(sizeof(unsigned short) * (size_t)d_max);
+    s.second = (unsigned short*)p;      p += lap_align16(sizeof(unsigned short) * (size_t)d_max);
+    s.ud = (unsigned short*)p;          p += lap_align16(sizeof(unsigned short) * (size_t)d_max);
+    s.ud2 = (unsigned short*)p;         p += lap_align16(sizeof(unsigned short) * (size_t)d_max);
+    s.pair_det = (unsigned short*)p;    p += lap_align16(sizeof(unsigned short) * (size_t)d_max);
+    s.det_flag = p;                     p += lap_align16((size_t)d_max);
+    s.trk_box = (float4*)p;             p += lap_align16(sizeof(float4) * (size_t)cap);
+    s.list_a = (unsigned short*)p;      p += lap_align16(sizeof(unsigned short) * (size_t)cap);
+    s.ut = (unsigned short*)p;          p += lap_align16(sizeof(unsigned short) * (size_t)cap);
+    s.ut2 = (unsigned short*)p;         p += lap_align16(sizeof(unsigned short) * (size_t)cap);
+    s.pair_trk = (unsigned short*)p;    p += lap_align16(sizeof(unsigned short) * (size_t)cap);
+    s.trk_flag = p;                     p += lap_align16((size_t)cap);
+    s.row_bits = (unsigned*)p;          p += lap_align16(sizeof(unsigned) * (size_t)((d_max + 31) / 32));
+    s.col_bits = (unsigned*)p;          p += lap_align16(sizeof(unsigned) * (size_t)((cap + 31) / 32));
+    s.flags = (int*)p;                  p += lap_align16(sizeof(int) * 4);
+    s.bs = (BlockScratch*)p;            p += lap_align16(sizeof(BlockScratch));
+    lap_carve(p, d_max, cap, e_cap, s.lap);
+}
+
+// KalmanBoxTracker::get_state / predict's return value (free convert_x_to_bbox, ocsort.cpp:172-181)
+__device__ __forceinline__ float4 oc_track_box(const float* rec) { return xysr2xyxy(rec[0], rec[1], rec[2], rec[3]); }
+
+// k_previous_obs (ocsort.cpp:24-51) for a track that has at least one observation: the oldest entry among
+// ages age-k .. age-1, else the newest observation overall (= last_observation).  Returns box, conf in `c`.
+__device__ __forceinline__ float4 oc_k_previous_obs(const OcStream& st, int slot, int age, int k, float& c) {
+    for (int dt = k; dt >= 1; --dt) {
+        const int a = age - dt;
+        if (a < 1) continue;                                    // no observation is ever stored under age <= 0
+        const int e = slot * kOcRing + (a & (kOcRing - 1));
+        if (st.ring_age[e] == a) { c = st.ring_conf[e]; return st.ring_box[e]; }
+    }
+    const float* o = st.obs + (size_t)slot * kOcObsFloats;
+    c = o[4];
+    return make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// KalmanBoxTracker::update with a real box (ocsort.cpp:89-127) for n_pairs (track position, detection)
+// pairs over DISTINCT tracks, one 8-lane group per pair.
+template <class TrkOf, class DetOf>
+__device__ __forceinline__ void oc_update_pairs(const OcStream& st, const OcSmem& sm, const float* dets, int n_pairs,
+                                                int delta_t, TrkOf trk_of, DetOf det_of) {
+    const int lane = lane_id(), g = lane & 7, base = lane & ~7;
+    const int groups = (int)(blockDim.x >> 3), gid = (int)(threadIdx.x >> 3);
+    const int rounds = (n_pairs + groups - 1) / groups;
+    for (int it = 0; it < rounds; ++it) {
+        const int q = it * groups + gid;
+        const bool live = q < n_pairs;
+        const int slot = live ? (int)sm.list_a[trk_of(q)] : 0;
+        const int det = live ? det_of(q) : 0;
+        float* rec = st.recs + (size_t)slot * kOcRecFloats;
+        KfRow7 s;
+        kf7_load_row(rec, live ? g : 7, s);
+        if (!live) { s.m = 1.0f; for (int j = 0; j < 7; ++j) s.p[j] = (j == g) ? 1.0f : 0.0f; }
+        float z[4] = {0.0f, 0.0f, 1.0f, 1.0f};
+        const float4 box = live ? sm.det_box[det] : make_float4(0.0f, 0.0f, 1.0f, 1.0f);
+        if (live) {
+            const float4 zz = xyxy2xysr(box);
+            z[0] = zz.x; z[1] = zz.y; z[2] = zz.z; z[3] = zz.w;
+        }
+        if (live && g == 0) {
+            float* o = st.obs + (size_t)slot * kOcObsFloats;
+            const float conf = sm.det_conf[det];
+            const int age = st.age[slot];
+            const float4 last = make_float4(o[0], o[1], o[2], o[3]);
+            if (box_sum4(last) >= 0.0f) {                                        // :97-108
+                float pc;
+                const float4 prev = oc_k_previous_obs(st, slot, age, delta_t, pc);
+                const float2 v = (box_sum4(prev) >= 0.0f) ? speed_direction(prev, box) : speed_direction(last, box);
+                o[5] = v.x; o[6] = v.y;
+            }
+            o[0] = box.x; o[1] = box.y; o[2] = box.z; o[3] = box.w; o[4] = conf;   // :111-115
+            const int e = slot * kOcRing + (age & (kOcRing - 1));
+            st.ring_box[e] = box; st.ring_conf[e] = conf; st.ring_age[e] = age;
+            st.det_ind[slot] = det;
+            st.conf[slot] = conf;
+            st.cls[slot] = (int)dets[(size_t)det * 6 + 5];
+            st.tsu[slot] = 0;
+            st.hits[slot] += 1;
+            st.streak[slot] += 1;
+        }
+        const bool ok = kf_xysr_update(s, g, base, z);
+        if (live) {
+            if (ok) kf7_store_row(rec, g, s);
+            else if (g == 0) atomicOr(&st.hdr[kOHdrError], 8);
+        }
+    }
+}
+
+// Updates for the matches of a BYTE / re-match assignment, whose column list may name a track twice: the
+// reference applies them in ascending row order, so a track's second update must see its first.
+//   row r matched iff lap.row2col[r] >= 0; det_of_row(r), trk_of_col(c) translate list positions.
+template <class DetOfRow, class TrkOfCol>
+__device__ __forceinline__ int oc_apply_matches(const OcStream& st, OcSmem& sm, const float* dets, int n_rows, int delta_t,
+                                                DetOfRow det_of_row, TrkOfCol trk_of_col) {
+    const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
+    int* first_row = sm.lap.col_label;                 // dead between block_lap calls; one int per track position
+    for (int r = tid; r < n_rows; r += nt) {
+        const int c = sm.lap.row2col[r];
+        if (c >= 0) first_row[trk_of_col(c)] = 0x7fffffff;
+    }
+    __syncthreads();
+    for (int r = tid; r < n_rows; r += nt) {
+        const int c = sm.lap.row2col[r];
+        if (c >= 0) atomicMin(&first_row[trk_of_col(c)], r);
+    }
+    __syncthreads();
+    int total = 0;
+    for (int round = 0; round < 2; ++round) {
+        const int n_pairs = block_compact(n_rows, 0, sm.bs,
+                                          [&](int r) {
+                                              const int c = sm.lap.row2col[r];
+                                              if (c < 0) return false;
+                                              return (first_row[trk_of_col(c)] == r) == (round == 0);
+                                          },
+                                          [&](int r, int pos) {
+                                              sm.pair_det[pos] = (unsigned short)det_of_row(r);
+                                              sm.pair_trk[pos] = (unsigned short)trk_of_col(sm.lap.row2col[r]);
+                                          });
+        if (n_pairs == 0) continue;
+        total += n_pairs;
+        oc_update_pairs(st, sm, dets, n_pairs, delta_t, [&](int q) { return (int)sm.pair_trk[q]; },
+                        [&](int q) { return (int)sm.pair_det[q]; });
+        __syncthreads();
+    }
+    return total;
+}
+
+// KalmanBoxTracker ctor (ocsort.cpp:53-87) for `n_new` detections det_of(k), appended to list_a at n_trk + k
+template <class DetOf>
+__device__ __forceinline__ void oc_spawn(const OcStream& st, OcSmem& sm, const float* dets, int n_new, int n_trk, int n_free,
+                                         int id_base, DetOf det_of) {
+    const int lane = lane_id(), g = lane & 7;
+    const int groups = (int)(blockDim.x >> 3), gid = (int)(threadIdx.x >> 3);
+    for (int k = gid; k < n_new; k += groups) {
+        const int det = det_of(k);
+        const int slot = st.freel[n_free - 1 - k];
+        const float4 q = xyxy2xysr(sm.det_box[det]);
+        const float z[4] = {q.x, q.y, q.z, q.w};
+        KfRow7 s;
+        kf_xysr_init(s, g, z);
+        kf7_store_row(st.recs + (size_t)slot * kOcRecFloats, g, s);
+        st.ring_age[slot * kOcRing + g] = -1;
+        if (g == 0) {
+            st.id[slot] = id_base + 1 + k;
+            st.age[slot] = 0; st.hits[slot] = 0; st.streak[slot] = 0; st.tsu[slot] = 0;
+            st.conf[slot] = sm.det_conf[det];
+            st.cls[slot] = (int)dets[(size_t)det * 6 + 5];
+            st.det_ind[slot] = det;
+            float* o = st.obs + (size_t)slot * kOcObsFloats;
+            o[0] = -1.0f; o[1] = -1.0f; o[2] = -1.0f; o[3] = -1.0f; o[4] = -1.0f; o[5] = 0.0f; o[6] = 0.0f; o[7] = 0.0f;
+            sm.list_a[n_trk + k] = (unsigned short)slot;
+        }
+    }
+}
+
+template <int CAP, int DMAX>
+__device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, OcSmem& sm, const float* dets, int n_det_in,
+                                         float* out, int* n_out) {
+    const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
+    const int lane = tid & 31, g = lane & 7, base = lane & ~7;
+    const int groups = nt >> 3, gid = tid >> 3;
+    __syncthreads();
+    const int frame = st.hdr[kOHdrFrame] + 1;                    // frame_count_ (:293)
+    const int n_trk0 = st.hdr[kOHdrTracks];
+    int n_free = st.hdr[kOHdrFree];
+    const int id_base = st.hdr[kOHdrIdCounter];
+    const float thr = a.p.iou_threshold;
+    const int delta_t = a.p.delta_t;
+    int n_det = n_det_in;
+    if (n_det > DMAX) { n_det = DMAX; if (tid == 0) atomicOr(&st.hdr[kOHdrError], 2); }
+
+    // ---- A. detections and the confidence split (:311-320)
+    float max_abs_score = 0.0f;
+    for (int j = tid; j < n_det; j += nt) {
+        const float* r = dets + (size_t)j * 6;
+        sm.det_box[j] = make_float4(r[0], r[1], r[2], r[3]);
+        sm.det_conf[j] = r[4];
+        max_abs_score = fmaxf(max_abs_score, fabsf(r[4]));
+    }
+    if (tid < 4) sm.flags[tid] = 0;
+    __syncthreads();
+    const float dth = a.p.det_thresh, lo = a.p.min_conf;
+    const int n_high = block_compact(n_det, 0, sm.bs, [&](int j) { return sm.det_conf[j] > dth; },
+                                     [&](int j, int pos) { sm.high[pos] = (unsigned short)j; });
+    int n_second = 0;
+    if (a.p.use_byte)
+        n_second = block_compact(n_det, 0, sm.bs, [&](int j) { const float c = sm.det_conf[j]; return c > lo && c < dth; },
+                                 [&](int j, int pos) { sm.second[pos] = (unsigned short)j; });
+    // a disjoint pair has iou 0: it can be an assignment candidate only if the angle cost alone reaches the
+    // threshold (|angle cost| <= inertia * score / 2) and it never satisfies iou > thr when thr >= 0
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) max_abs_score = fmaxf(max_abs_score, __shfl_xor_sync(kFullMask, max_abs_score, o));
+        if (lane == 0) atomicMax(&sm.flags[3], __float_as_int(max_abs_score));   // non-negative floats order as ints
+    }
+    __syncthreads();
+    const float score_bound = __int_as_float(sm.flags[3]);
+    const bool prune_first = thr >= 0.0f && (0.5f * fabsf(a.p.inertia) * score_bound * 1.0001f + 1e-7f) < thr;
+    const bool prune_rest = thr > 0.0f;
+    __syncthreads();
+    if (tid == 0) sm.flags[3] = 0;
+
+    // ---- B. predict every track in place (KalmanBoxTracker::predict :134-151); a NaN box removes the track
+    {
+        const int rounds = (n_trk0 + groups - 1) / groups;
+        for (int it = 0; it < rounds; ++it) {
+            const int k = it * groups + gid;
+            const bool live = k < n_trk0;
+            const int slot = live ? (int)st.list[k] : 0;
+            float* rec = st.recs + (size_t)slot * kOcRecFloats;
+            KfRow7 s;
+            kf7_load_row(rec, live ? g : 7, s);
+            const float x6 = __shfl_sync(kFullMask, s.m, base + 6), x2 = __shfl_sync(kFullMask, s.m, base + 2);
+            if (g == 6 && xadd(x6, x2) <= 0.0f) s.m = 0.0f;                  // :135-137
+            kf_xysr_predict(s, g, base, a.p.q44, a.p.q66);
+            const float x0 = __shfl_sync(kFullMask, s.m, base + 0), x1 = __shfl_sync(kFullMask, s.m, base + 1);
+            const float xs = __shfl_sync(kFullMask, s.m, base + 2), xr = __shfl_sync(kFullMask, s.m, base + 3);
+            if (live) {
+                kf7_store_row(rec, g, s);
+                if (g == 0) {
+                    st.age[slot] += 1;
+                    if (st.tsu[slot] > 0) st.streak[slot] = 0;
+                    st.tsu[slot] += 1;
+                    const float4 b = xysr2xyxy(x0, x1, xs, xr);
+                    sm.trk_flag[k] = (b.x != b.x || b.y != b.y || b.z != b.z || b.w != b.w) ? 1 : 0;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int n_trk = block_compact(n_trk0, 0, sm.bs, [&](int k) { return sm.trk_flag[k] == 0; },
+                                    [&](int k, int pos) { sm.list_a[pos] = st.list[k]; });
+    n_free = block_compact(n_trk0, n_free, sm.bs, [&](int k) { return sm.trk_flag[k] != 0; },
+                           [&](int k, int pos) { st.freel[pos] = st.list[k]; });
+
+    if (n_trk == 0) {
+        // ---- no tracks: every high detection starts one, nothing is emitted (:367-384)
+        int n_new = n_high;
+        if (n_new > n_free) { n_new = n_free; if (tid == 0) atomicOr(&st.hdr[kOHdrError], 1); }
+        oc_spawn(st, sm, dets, n_new, 0, n_free, id_base, [&](int k) { return (int)sm.high[k]; });
+        __syncthreads();
+        for (int k = tid; k < n_new; k += nt) st.list[k] = sm.list_a[k];
+        if (tid == 0) {
+            *n_out = 0;
+            st.hdr[kOHdrTracks] = n_new;
+            st.hdr[kOHdrFree] = n_free - n_new;
+            st.hdr[kOHdrIdCounter] = id_base + n_new;
+            st.hdr[kOHdrFrame] = frame;
+            st.hdr[kOHdrNHigh] = n_high; st.hdr[kOHdrNTrk] = 0; st.hdr[kOHdrUsedLap] = 0; st.hdr[kOHdrMatched] = 0;
+            st.hdr[kOHdrLeftDets] = 0; st.hdr[kOHdrLeftTrks] = 0; st.hdr[kOHdrRematched] = 0; st.hdr[kOHdrSpawned] = 0;
+        }
+        __syncthreads();
+        return;
+    }
+
+    // ---- C. predicted boxes, velocities and k_previous_obs of every track (:394-410)
+    for (int k = tid; k < n_trk; k += nt) {
+        const int slot = sm.list_a[k];
+        sm.trk_box[k] = oc_track_box(st.recs + (size_t)slot * kOcRecFloats);
+        const float* o = st.obs + (size_t)slot * kOcObsFloats;
+        float4 prev = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
+        float pc = -1.0f;
+        if (st.hits[slot] > 0) prev = oc_k_previous_obs(st, slot, st.age[slot], delta_t, pc);
+        st.ocm[k] = make_float4(xdiv(xadd(prev.x, prev.z), 2.0f), xdiv(xadd(prev.y, prev.w), 2.0f), o[5], o[6]);
+        st.valid[k] = (pc >= 0.0f) ? 1 : 0;
+        sm.trk_flag[k] = 0;
+    }
+    for (int i = tid; i < n_high; i += nt) sm.det_flag[i] = 0;
+    for (int w = tid; w < (DMAX + 31) / 32; w += nt) sm.row_bits[w] = 0;
+    for (int w = tid; w < (CAP + 31) / 32; w += nt) sm.col_bits[w] = 0;
+    __syncthreads();
+
+    // ---- D. first association (:413-420, associate :610-737); rows = high detections, columns = tracks
+    OcmCost ocm{sm.det_box, sm.det_conf, sm.high, sm.trk_box, st.ocm, st.valid, a.p.inertia, thr, prune_first,
+                sm.row_bits, sm.col_bits, sm.pair_det /* row_hit */, sm.flags};
+    block_lap(sm.lap, n_high, n_trk, DMAX, CAP, -thr, ocm);
+    const bool trivial = sm.flags[0] != 0 && sm.flags[1] == 0;   // max row sum == 1 && max column sum == 1 (:676-680)
+    __syncthreads();
+    if (trivial) {
+        // every pair with iou > thr is a match, nothing else is (:681-689)
+        for (int j = tid; j < n_trk; j += nt) sm.lap.col2row[j] = -1;
+        __syncthreads();
+        for (int i = tid; i < n_high; i += nt) {
+            const bool hit = (sm.row_bits[i >> 5] >> (i & 31)) & 1u;
+            const int j = hit ? (int)sm.pair_det[i] : -1;
+            sm.lap.row2col[i] = (short)j;
+            if (hit) { sm.lap.col2row[j] = (short)i; sm.det_flag[i] = 1; sm.trk_flag[j] = 1; }
+        }
+    } else {
+        // assignment pairs below the IoU threshold go to both unmatched lists (:702-712)
+        for (int i = tid; i < n_high; i += nt) {
+            const int j = sm.lap.row2col[i];
+            if (j < 0) continue;
+            const OcmCost::Row rw = ocm.row(i);
+            const unsigned char f = (ocm.iou(rw, j) >= thr) ? 1 : 2;
+            sm.det_flag[i] = f; sm.trk_flag[j] = f;
+        }
+    }
+    __syncthreads();
+    // unmatched lists in the reference's order: filtered pairs (ascending detection), then the sweep (:715-735)
+    int n_ud = block_compact(n_high, 0, sm.bs, [&](int i) { return sm.det_flag[i] == 2; },
+                             [&](int i, int pos) {
+                                 if (pos < DMAX) sm.ud[pos] = sm.high[i];
+                                 if (pos < CAP) sm.ut[pos] = (unsigned short)sm.lap.row2col[i];
+                             });
+    int n_ut = n_ud;
+    n_ud = block_compact(n_high, n_ud, sm.bs, [&](int i) { return sm.det_flag[i] != 1; },
+                         [&](int i, int pos) { if (pos < DMAX) sm.ud[pos] = sm.high[i]; });
+    n_ut = block_compact(n_trk, n_ut, sm.bs, [&](int j) { return sm.trk_flag[j] != 1; },
+                         [&](int j, int pos) { if (pos < CAP) sm.ut[pos] = (unsigned short)j; });
+    if (n_ud > DMAX || n_ut > CAP) {
+        if (tid == 0) atomicOr(&st.hdr[kOHdrError], 1);
+        n_ud = min(n_ud, DMAX); n_ut = min(n_ut, CAP);
+    }
+    const int n_match = block_compact(n_high, 0, sm.bs, [&](int i) { return sm.det_flag[i] == 1; },
+                                      [&](int i, int pos) {
+                                          sm.pair_det[pos] = sm.high[i];
+                                          sm.pair_trk[pos] = (unsigned short)sm.lap.row2col[i];
+                                      });
+
+    // ---- E. update the matched tracks (:423-430)
+    oc_update_pairs(st, sm, dets, n_match, delta_t, [&](int q) { return (int)sm.pair_trk[q]; },
+                    [&](int q) { return (int)sm.pair_det[q]; });
+    __syncthreads();
+    // detection / track flags now mean "taken out of the unmatched lists"
+    for (int j = tid; j < n_det; j += nt) sm.det_flag[j] = 0;
+    for (int k = tid; k < n_trk; k += nt) sm.trk_flag[k] = 0;
+    __syncthreads();
+
+    // ---- F. BYTE pass: low-confidence detections x unmatched tracks, predicted boxes (:433-479)
+    if (a.p.use_byte && n_second > 0 && n_ut > 0) {
+        if (tid == 0) sm.flags[0] = 0;
+        __syncthreads();
+        NegIouCost cost{sm.det_box, sm.second, sm.trk_box, sm.ut, thr, prune_rest, sm.flags};
+        block_lap(sm.lap, n_second, n_ut, DMAX, CAP, -thr, cost);
+        if (sm.flags[0] != 0) {                                   // max_iou > threshold (:445-446)
+            for (int r = tid; r < n_second; r += nt) {
+                const int c = sm.lap.row2col[r];
+                if (c >= 0) sm.trk_flag[sm.ut[c]] = 1;
+            }
+            oc_apply_matches(st, sm, dets, n_second, delta_t, [&](int r) { return (int)sm.second[r]; },
+                             [&](int c) { return (int)sm.ut[c]; });
+            const int n_keep = block_compact(n_ut, 0, sm.bs, [&](int p) { return sm.trk_flag[sm.ut[p]] == 0; },
+                                             [&](int p, int pos) { sm.ut2[pos] = sm.ut[p]; });
+            for (int p = tid; p < n_keep; p += nt) sm.ut[p] = sm.ut2[p];
+            n_ut = n_keep;
+        }
+        __syncthreads();
+    }
+
+    // ---- G. re-match the leftovers on the tracks' last observations (:482-545)
+    int n_rematch = 0, n_left_d = 0, n_left_t = 0;
+    if (n_ud > 0 && n_ut > 0) {
+        n_left_d = n_ud; n_left_t = n_ut;
+        for (int p = tid; p < n_ut; p += nt) {
+            const int k = sm.ut[p];
+            const float* o = st.obs + (size_t)sm.list_a[k] * kOcObsFloats;
+            sm.trk_box[k] = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        if (tid == 0) sm.flags[0] = 0;
+        __syncthreads();
+        NegIouCost cost{sm.det_box, sm.ud, sm.trk_box, sm.ut, thr, prune_rest, sm.flags};
+        block_lap(sm.lap, n_ud, n_ut, DMAX, CAP, -thr, cost);
+        if (sm.flags[0] != 0) {                                   // max_iou > threshold (:507-509)
+            for (int r = tid; r < n_ud; r += nt) {
+                const int c = sm.lap.row2col[r];
+                if (c >= 0) { sm.trk_flag[sm.ut[c]] = 1; sm.det_flag[sm.ud[r]] = 1; }
+            }
+            n_rematch = oc_apply_matches(st, sm, dets, n_ud, delta_t, [&](int r) { return (int)sm.ud[r]; },
+                                         [&](int c) { return (int)sm.ut[c]; });
+            const int kt = block_compact(n_ut, 0, sm.bs, [&](int p) { return sm.trk_flag[sm.ut[p]] == 0; },
+                                         [&](int p, int pos) { sm.ut2[pos] = sm.ut[p]; });
+            const int kd = block_compact(n_ud, 0, sm.bs, [&](int p) { return sm.det_flag[sm.ud[p]] == 0; },
+                                         [&](int p, int pos) { sm.ud2[pos] = sm.ud[p]; });
+            for (int p = tid; p < kt; p += nt) sm.ut[p] = sm.ut2[p];
+            for (int p = tid; p < kd; p += nt) sm.ud[p] = sm.ud2[p];
+            n_ut = kt; n_ud = kd;
+        }
+        __syncthreads();
+    }
+
+    // ---- H. update(None) for the tracks still unmatched: only det_ind changes (:548-550, :90, :128-131)
+    for (int p = tid; p < n_ut; p += nt) st.det_ind[sm.list_a[sm.ut[p]]] = 0;
+
+    // ---- I. new tracks for the detections still unmatched, list order, duplicates included (:553-561)
+    int n_new = n_ud;
+    if (n_new > n_free || n_trk + n_new > CAP) {
+        n_new = min(n_free, CAP - n_trk);
+        if (tid == 0) atomicOr(&st.hdr[kOHdrError], 1);
+    }
+    oc_spawn(st, sm, dets, n_new, n_trk, n_free, id_base, [&](int k) { return (int)sm.ud[k]; });
+    __syncthreads();
+    const int n_all = n_trk + n_new;
+    n_free -= n_new;
+
+    // ---- J. output in REVERSE track order, then age-out (:564-592)
+    const int min_hits = a.p.min_hits, max_age = a.p.max_age;
+    const int n_rows = block_compact(n_all, 0, sm.bs,
+                                     [&](int q) {
+                                         const int slot = sm.list_a[n_all - 1 - q];
+                                         return st.tsu[slot] < 1 && (st.streak[slot] >= min_hits || frame <= min_hits);
+                                     },
+                                     [&](int q, int pos) {
+                                         if (pos >= a.ld_out) return;
+                                         const int slot = sm.list_a[n_all - 1 - q];
+                                         const float* o = st.obs + (size_t)slot * kOcObsFloats;
+                                         float4 b = make_float4(o[0], o[1], o[2], o[3]);
+                                         if (box_sum4(b) < 0.0f) b = oc_track_box(st.recs + (size_t)slot * kOcRecFloats);
+                                         float* w = out + (size_t)pos * 8;
+                                         *reinterpret_cast<float4*>(w) = b;
+                                         *reinterpret_cast<float4*>(w + 4) = make_float4((float)(st.id[slot] + 1), st.conf[slot],
+                                                                                         (float)st.cls[slot], (float)st.det_ind[slot]);
+                                     });
+    const int n_keep = block_compact(n_all, 0, sm.bs, [&](int k) { return st.tsu[sm.list_a[k]] <= max_age; },
+                                     [&](int k, int pos) { st.list[pos] = sm.list_a[k]; });
+    n_free = block_compact(n_all, n_free, sm.bs, [&](int k) { return st.tsu[sm.list_a[k]] > max_age; },
+                           [&](int k, int pos) { st.freel[pos] = sm.list_a[k]; });
+    if (tid == 0) {
+        if (n_rows > a.ld_out) atomicOr(&st.hdr[kOHdrError], 4);
+        *n_out = n_rows < a.ld_out ? n_rows : a.ld_out;
+        st.hdr[kOHdrTracks] = n_keep;
+        st.hdr[kOHdrFree] = n_free;
+        st.hdr[kOHdrIdCounter] = id_base + n_new;
+        st.hdr[kOHdrFrame] = frame;
+        st.hdr[kOHdrNHigh] = n_high; st.hdr[kOHdrNTrk] = n_trk; st.hdr[kOHdrUsedLap] = (!trivial && n_high > 0) ? 1 : 0;
+        st.hdr[kOHdrMatched] = n_match; st.hdr[kOHdrLeftDets] = n_left_d; st.hdr[kOHdrLeftTrks] = n_left_t;
+        st.hdr[kOHdrRematched] = n_rematch; st.hdr[kOHdrSpawned] = n_new;
+    }
+    __syncthreads();
+}
+
+template <int CAP, int DMAX, int ECAP>
+__global__ void __launch_bounds__(kOcThreads) ocsort_step_kernel(OcArgs a) {
+    MOT_DYNAMIC_SMEM(smem);
+    OcSmem sm;
+    oc_carve(smem, CAP, DMAX, ECAP, sm);
+    constexpr OcLayout L = OcLayout::make(CAP, DMAX);
+    for (int s = a.s_begin + (int)blockIdx.x; s < a.s_end; s += (int)gridDim.x) {
+        OcStream st = OcStream::at(a.state + (size_t)s * L.stride, L);
+        lap_carve_gscratch(st.gscratch, DMAX, CAP, sm.lap);
+        for (int t = 0; t < a.T; ++t) {
+            const size_t fs = (size_t)t * a.S + s;
+            oc_frame<CAP, DMAX>(a, st, sm, a.dets + fs * (size_t)a.ld_dets * 6, a.n_dets[fs],
+                                a.out + fs * (size_t)a.ld_out * 8, a.n_out + fs);
+        }
+    }
+}
+
+__global__ void ocsort_reset_kernel(unsigned char* state, OcLayout L, int S, int keep_id_counter) {
+    for (int s = (int)blockIdx.x; s < S; s += (int)gridDim.x) {
+        OcStream st = OcStream::at(state + (size_t)s * L.stride, L);
+        for (int k = (int)threadIdx.x; k < L.cap; k += (int)blockDim.x) st.freel[k] = (unsigned short)(L.cap - 1 - k);
+        if (threadIdx.x == 0) {
+            const int idc = keep_id_counter ? st.hdr[kOHdrIdCounter] : 0;
+            for (int k = 0; k < 16; ++k) st.hdr[k] = 0;
+            st.hdr[kOHdrFree] = L.cap;
+            st.hdr[kOHdrIdCounter] = idc;
+        }
+        __syncthreads();
+    }
+}
+
+// The (track capacity, detections per frame, candidate-edge buffer) shapes the OC-SORT kernel is built for
+struct OcShape { int cap, d_max, e_cap; };
+constexpr OcShape kOcShapes[] = {{256, 64, 1024}, {1536, 512, 4096}, {3072, 2048, 4096}};
+constexpr int kNumOcShapes = sizeof(kOcShapes) / sizeof(kOcShapes[0]);
+
+}  // namespace mot

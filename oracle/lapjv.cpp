@@ -173,8 +173,9 @@ private:
 
 }  // namespace
 
-extern "C" int orc_linear_assignment(const float* cost, int n, int m, int ld, float thresh,
-                                     int* row2col, int* col2row) {
+namespace {
+// biased: adds the tie-break infinitesimal -(64 j + (i j mod 64)) 2^-50 to every real entry (see orc_linear_assignment_biased)
+int solve_extended(const float* cost, int n, int m, int ld, float thresh, bool biased, int* row2col, int* col2row) {
     for (int i = 0; i < n; ++i) row2col[i] = -1;
     for (int j = 0; j < m; ++j) col2row[j] = -1;
     if (n == 0 || m == 0) return 0;                                   // matching.cpp:20-28
@@ -184,7 +185,10 @@ extern "C" int orc_linear_assignment(const float* cost, int n, int m, int ld, fl
     for (int i = 0; i < N; ++i)
         for (int j = 0; j < N; ++j) {
             double val;
-            if (i < n && j < m) val = (double)cost[(size_t)i * ld + j];   // matching.cpp:31 cast
+            if (i < n && j < m) {
+                val = (double)cost[(size_t)i * ld + j];                   // matching.cpp:31 cast
+                if (biased) val += -(double)(64 * j + ((i * j) & 63)) * 0x1p-50;
+            }
             else if (i >= n && j >= m) val = 0.0;
             else val = half;
             ext[(size_t)i * N + j] = val;
@@ -202,4 +206,22 @@ extern "C" int orc_linear_assignment(const float* cost, int n, int m, int ld, fl
         col2row[j] = (i >= n) ? -1 : i;
     }
     return matches;
+}
+}  // namespace
+
+extern "C" int orc_linear_assignment(const float* cost, int n, int m, int ld, float thresh,
+                                     int* row2col, int* col2row) {
+    return solve_extended(cost, n, m, ld, thresh, false, row2col, col2row);
+}
+
+// NOT the reference's behaviour: the same problem with an infinitesimal added to every real entry in fp64,
+//   cost(i,j) - (64 j + (i j mod 64)) 2^-50,
+// far below the 2^-26 granularity of sums of fp32 costs of magnitude >= 0.25, so it only decides between
+// otherwise exactly tied optima: it prefers the HIGHER column, and makes "two rows on two identical columns"
+// unique as well.  This is the tie-break the CUDA OC-SORT kernel applies to the reference's bit-identical
+// "twin" tracks (DESIGN.md "Ties"); tests use it to separate kernel-logic parity from LAPJV's scan-order
+// tie-breaking.
+extern "C" int orc_linear_assignment_biased(const float* cost, int n, int m, int ld, float thresh,
+                                            int* row2col, int* col2row) {
+    return solve_extended(cost, n, m, ld, thresh, true, row2col, col2row);
 }

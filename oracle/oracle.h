@@ -72,6 +72,10 @@ void orc_embedding_distance(const float* t, int n, const float* d, int m, int di
 int orc_linear_assignment(const float* cost, int n, int m, int ld, float thresh,
                           int* row2col, int* col2row);
 
+/* NOT reference behaviour: same problem with cost(i,j) - (64 j + (i j mod 64)) 2^-50 in fp64, i.e. exact ties
+ * resolved towards the higher column - the CUDA OC-SORT kernel's rule for bit-identical twin tracks. */
+int orc_linear_assignment_biased(const float* cost, int n, int m, int ld, float thresh, int* row2col, int* col2row);
+
 /* ---------------- trackers (state machines) --------------------------------------------- */
 typedef struct OrcByteTrack OrcByteTrack;
 /* arguments follow ByteTrack's ctor (include/motcpp/trackers/bytetrack.hpp:97-110); the
@@ -97,6 +101,34 @@ OrcSort* orc_sort_create(float det_thresh, int max_age, int max_obs, int min_hit
 void orc_sort_destroy(OrcSort*);
 void orc_sort_reset(OrcSort*);
 int orc_sort_update(OrcSort*, const float* dets, int n, float* out, int out_cap);
+
+/* ---------------- OC-SORT (src/trackers/ocsort.cpp) -------------------------------------- */
+/* correctly rounded fp32 arc cosine (fixed fp64 operation sequence, see oracle/ocsort.cpp) */
+float orc_acosf(float x);
+/* ocsort_assoc::associate cost (ocsort.cpp:610-700): dets5 (n_dets x 5) [xyxy,score], trks4 (n_trks x 4),
+ * vel2 (n_trks x 2) (dy,dx), prev5 (n_trks x 5) k_previous_obs rows; out_cost = -(iou + angle cost),
+ * out_iou (nullable) = iou_batch(dets, trks); both (n_dets x n_trks) row-major */
+void orc_ocm_cost(const float* dets5, int n_dets, const float* trks4, const float* vel2, const float* prev5,
+                  int n_trks, float inertia, float* out_cost, float* out_iou);
+typedef struct OrcOcSort OrcOcSort;
+/* arguments follow OCSort's ctor (include/motcpp/trackers/ocsort.hpp:88-102) */
+OrcOcSort* orc_ocsort_create(float det_thresh, int max_age, int max_obs, int min_hits, float iou_threshold,
+                             float min_conf, int delta_t, float inertia, int use_byte, float q_xy_scaling,
+                             float q_s_scaling);
+void orc_ocsort_destroy(OrcOcSort*);
+void orc_ocsort_reset(OrcOcSort*);
+int orc_ocsort_update(OrcOcSort*, const float* dets, int n, float* out, int out_cap);
+int orc_ocsort_count(const OrcOcSort*);
+/* tests: keep / fetch the first-association cost matrix (n_high x n_trk) of the last update() */
+void orc_ocsort_capture(OrcOcSort*, int on);
+/* 0 (default) = the reference's LAPJV tie-breaking; 1 = orc_linear_assignment_biased in the first association */
+void orc_ocsort_set_tie_mode(OrcOcSort*, int mode);
+int orc_ocsort_last_cost(const OrcOcSort*, float* out, int cap);
+/* [n_high, n_trk, used_lap, n_first_matches, n_left_dets, n_left_trks, n_rematched, n_spawned] of the last update() */
+void orc_ocsort_last_sizes(const OrcOcSort*, int* sizes8);
+/* rows of [id, age, hits, hit_streak, time_since_update, conf, cls, det_ind, last_obs 5, velocity 2,
+ * k_previous_obs(delta_t) 5, x 7, P 49] = 76 floats */
+int orc_ocsort_dump(const OrcOcSort*, float* out, int cap_rows);
 
 #ifdef __cplusplus
 }

@@ -157,3 +157,76 @@ void sim_sort_header(void* hv, int s, int* hdr16) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ OC-SORT engine under the emulator
+#include "../../motcpp_b200/csrc/ocsort_kernel.cuh"
+
+namespace {
+struct SimOc {
+    mot::OcLayout L;
+    int S;
+    mot::OcParams p;
+    std::vector<unsigned char> state;
+};
+}  // namespace
+
+extern "C" {
+
+float sim_acosf(float x) { return mot::acosf_cr(x); }
+
+void* sim_oc_create(int S, float det_thresh, int max_age, int min_hits, float iou_threshold, float min_conf, int delta_t,
+                    float inertia, int use_byte, float q_xy, float q_s) {
+    auto* h = new SimOc();
+    h->L = mot::OcLayout::make(256, 64);
+    h->S = S;
+    h->p.det_thresh = det_thresh; h->p.max_age = max_age; h->p.min_hits = min_hits; h->p.iou_threshold = iou_threshold;
+    h->p.min_conf = min_conf; h->p.delta_t = delta_t; h->p.inertia = inertia; h->p.use_byte = use_byte;
+    h->p.q44 = 0.01f * q_xy; h->p.q66 = 0.0001f * q_s;
+    h->state.assign(h->L.stride * (size_t)S + 256, 0);
+    unsigned char* st = h->state.data();
+    const mot::OcLayout L = h->L;
+    cpusim::launch(dim3(S), dim3(64), 0, [=] { mot::ocsort_reset_kernel(st, L, S, 0); });
+    return h;
+}
+void sim_oc_destroy(void* hv) { delete (SimOc*)hv; }
+
+int sim_oc_update(void* hv, const float* dets, const int* n_dets, int T, int ld_dets, float* out, int* n_out, int ld_out,
+                  int threads) {
+    auto* h = (SimOc*)hv;
+    mot::OcArgs a{};
+    a.state = h->state.data(); a.dets = dets; a.n_dets = n_dets; a.out = out; a.n_out = n_out;
+    a.T = T; a.S = h->S; a.ld_dets = ld_dets; a.ld_out = ld_out; a.s_begin = 0; a.s_end = h->S; a.p = h->p;
+    const size_t smem = mot::oc_smem_bytes(256, 64, 1024);
+    cpusim::launch(dim3(h->S), dim3(threads), smem, [=] { mot::ocsort_step_kernel<256, 64, 1024>(a); });
+    return 0;
+}
+void sim_oc_header(void* hv, int s, int* hdr16) {
+    auto* h = (SimOc*)hv;
+    std::memcpy(hdr16, h->state.data() + (size_t)s * h->L.stride, sizeof(int) * 16);
+}
+
+// rows of [id, age, hits, hit_streak, time_since_update, conf, cls, det_ind, last_obs 5, velocity 2, x 7, P 49] = 71 floats
+int sim_oc_dump(void* hv, int s, float* rows, int cap_rows) {
+    auto* h = (SimOc*)hv;
+    unsigned char* base = h->state.data() + (size_t)s * h->L.stride;
+    const mot::OcLayout& L = h->L;
+    const int* hdr = (const int*)base;
+    const unsigned short* list = (const unsigned short*)(base + L.off_lists);
+    const int* m = (const int*)(base + L.off_meta);
+    const float* obs = (const float*)(base + L.off_obs);
+    const float* recs = (const float*)(base + L.off_recs);
+    const int n = hdr[mot::kOHdrTracks], cap = L.cap;
+    int k = 0;
+    for (; k < n && k < cap_rows; ++k) {
+        const int slot = list[k];
+        float* o = rows + 71 * k;
+        o[0] = (float)m[slot]; o[1] = (float)m[cap + slot]; o[2] = (float)m[2 * cap + slot]; o[3] = (float)m[3 * cap + slot];
+        o[4] = (float)m[4 * cap + slot]; o[5] = ((const float*)m)[7 * cap + slot]; o[6] = (float)m[5 * cap + slot];
+        o[7] = (float)m[6 * cap + slot];
+        std::memcpy(o + 8, obs + (size_t)slot * mot::kOcObsFloats, 7 * sizeof(float));
+        std::memcpy(o + 15, recs + (size_t)slot * mot::kOcRecFloats, 56 * sizeof(float));
+    }
+    return k;
+}
+
+}  // extern "C"

@@ -73,6 +73,27 @@ def lib() -> C.CDLL:
         L.orc_sort_reset.argtypes = [C.c_void_p]
         L.orc_sort_update.argtypes = [C.c_void_p, f32p, C.c_int, f32p, C.c_int]
         L.orc_sort_update.restype = C.c_int
+        L.orc_acosf.argtypes = [C.c_float]
+        L.orc_acosf.restype = C.c_float
+        L.orc_ocm_cost.argtypes = [f32p, C.c_int, f32p, f32p, f32p, C.c_int, C.c_float, f32p, f32p]
+        L.orc_ocsort_create.argtypes = [C.c_float, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
+                                        C.c_float, C.c_int, C.c_float, C.c_float]
+        L.orc_ocsort_create.restype = C.c_void_p
+        L.orc_ocsort_destroy.argtypes = [C.c_void_p]
+        L.orc_ocsort_reset.argtypes = [C.c_void_p]
+        L.orc_ocsort_update.argtypes = [C.c_void_p, f32p, C.c_int, f32p, C.c_int]
+        L.orc_ocsort_update.restype = C.c_int
+        L.orc_ocsort_count.argtypes = [C.c_void_p]
+        L.orc_ocsort_count.restype = C.c_int
+        L.orc_ocsort_set_tie_mode.argtypes = [C.c_void_p, C.c_int]
+        L.orc_linear_assignment_biased.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_float, i32p, i32p]
+        L.orc_linear_assignment_biased.restype = C.c_int
+        L.orc_ocsort_capture.argtypes = [C.c_void_p, C.c_int]
+        L.orc_ocsort_last_cost.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_ocsort_last_cost.restype = C.c_int
+        L.orc_ocsort_last_sizes.argtypes = [C.c_void_p, i32p]
+        L.orc_ocsort_dump.argtypes = [C.c_void_p, f32p, C.c_int]
+        L.orc_ocsort_dump.restype = C.c_int
         _LIB = L
     return _LIB
 
@@ -282,3 +303,60 @@ class Sort:
         n = lib().orc_sort_update(self._h, dets, dets.shape[0], self._out, self._out.shape[0])
         assert n >= 0
         return self._out[:n].copy()
+
+
+def ocm_cost(dets5, trks4, vel2, prev5, inertia):
+    """(cost, iou), both (n_dets, n_trks): ocsort_assoc::associate's -(iou + angle cost) and iou_batch(dets, trks)."""
+    dets5, trks4 = _f32(dets5).reshape(-1, 5), _f32(trks4).reshape(-1, 4)
+    vel2, prev5 = _f32(vel2).reshape(-1, 2), _f32(prev5).reshape(-1, 5)
+    cost = np.zeros((dets5.shape[0], trks4.shape[0]), np.float32)
+    iou = np.zeros_like(cost)
+    if cost.size:
+        lib().orc_ocm_cost(dets5, dets5.shape[0], trks4, vel2, prev5, trks4.shape[0], float(inertia), cost, iou)
+    return cost, iou
+
+
+class OCSort:
+    """Oracle OC-SORT with the reference's constructor argument order (ocsort.hpp:88-102)."""
+
+    def __init__(self, det_thresh=0.2, max_age=30, max_obs=50, min_hits=3, iou_threshold=0.3, min_conf=0.1,
+                 delta_t=3, inertia=0.2, use_byte=False, q_xy_scaling=0.01, q_s_scaling=0.0001, tie_mode=0):
+        self._h = lib().orc_ocsort_create(det_thresh, max_age, max_obs, min_hits, iou_threshold, min_conf, delta_t,
+                                          inertia, int(use_byte), q_xy_scaling, q_s_scaling)
+        lib().orc_ocsort_set_tie_mode(self._h, int(tie_mode))
+        self._out = np.zeros((8192, 8), np.float32)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_ocsort_destroy(self._h)
+            self._h = None
+
+    def reset(self):
+        lib().orc_ocsort_reset(self._h)
+
+    def update(self, dets):
+        dets = _f32(dets).reshape(-1, 6)
+        n = lib().orc_ocsort_update(self._h, dets, dets.shape[0], self._out, self._out.shape[0])
+        assert n >= 0
+        return self._out[:n].copy()
+
+    def dump(self):
+        cap = max(1, lib().orc_ocsort_count(self._h))
+        buf = np.zeros((cap, 76), np.float32)
+        k = lib().orc_ocsort_dump(self._h, buf, cap)
+        return buf[:k]
+
+    def last_sizes(self):
+        s = np.zeros(8, np.int32)
+        lib().orc_ocsort_last_sizes(self._h, s)
+        return s
+
+    def capture(self, on=True):
+        lib().orc_ocsort_capture(self._h, int(on))
+
+    def last_cost(self):
+        n = lib().orc_ocsort_last_cost(self._h, None, 0)
+        sz = self.last_sizes()
+        buf = np.zeros(max(n, 1), np.float32)
+        lib().orc_ocsort_last_cost(self._h, buf.ctypes.data_as(C.c_void_p), n)
+        return buf[:n].reshape(int(sz[0]), int(sz[1])) if n else np.zeros((0, 0), np.float32)

@@ -31,6 +31,16 @@ def lib():
         S.sim_sort_update.argtypes = [C.c_void_p, f32p, i32p, C.c_int, C.c_int, f32p, i32p, C.c_int, C.c_int]
         S.sim_sort_header.argtypes = [C.c_void_p, C.c_int, i32p]
         S.sim_sort_destroy.argtypes = [C.c_void_p]
+        S.sim_acosf.argtypes = [C.c_float]
+        S.sim_acosf.restype = C.c_float
+        S.sim_oc_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float,
+                                    C.c_int, C.c_float, C.c_float]
+        S.sim_oc_create.restype = C.c_void_p
+        S.sim_oc_update.argtypes = [C.c_void_p, f32p, i32p, C.c_int, C.c_int, f32p, i32p, C.c_int, C.c_int]
+        S.sim_oc_header.argtypes = [C.c_void_p, C.c_int, i32p]
+        S.sim_oc_dump.argtypes = [C.c_void_p, C.c_int, f32p, C.c_int]
+        S.sim_oc_dump.restype = C.c_int
+        S.sim_oc_destroy.argtypes = [C.c_void_p]
         _LIB = S
     return _LIB
 
@@ -100,3 +110,35 @@ class SimSort:
         h = np.zeros(16, np.int32)
         lib().sim_sort_header(self.h, s, h)
         return h
+
+
+class SimOCSort:
+    def __init__(self, n_streams=1, det_thresh=0.2, max_age=30, min_hits=3, iou_threshold=0.3, min_conf=0.1, delta_t=3,
+                 inertia=0.2, use_byte=False, q_xy_scaling=0.01, q_s_scaling=0.0001):
+        self.S, self.cap = n_streams, 256
+        self.h = lib().sim_oc_create(n_streams, det_thresh, max_age, min_hits, iou_threshold, min_conf, delta_t, inertia,
+                                     int(use_byte), q_xy_scaling, q_s_scaling)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().sim_oc_destroy(self.h)
+            self.h = None
+
+    def update(self, dets, n_dets, threads=128):
+        dets = np.ascontiguousarray(dets, np.float32)
+        T, S, ld, _ = dets.shape
+        n_dets = np.ascontiguousarray(n_dets, np.int32).reshape(T, S)
+        out = np.zeros((T, S, self.cap, 8), np.float32)
+        n_out = np.zeros((T, S), np.int32)
+        lib().sim_oc_update(self.h, dets, n_dets, T, ld, out, n_out, self.cap, threads)
+        return out, n_out
+
+    def header(self, s=0):
+        h = np.zeros(16, np.int32)
+        lib().sim_oc_header(self.h, s, h)
+        return h
+
+    def dump(self, s=0):
+        buf = np.zeros((self.cap, 71), np.float32)
+        k = lib().sim_oc_dump(self.h, s, buf, self.cap)
+        return buf[:k]
