@@ -110,6 +110,13 @@ int mot_engine_update_host(mot_engine* e, int n_frames, const float* dets, const
 /* Same contract with DEVICE buffers, asynchronous on `stream`; no host synchronisation. */
 int mot_engine_update_device(mot_engine* e, int n_frames, const float* d_dets, const int* d_n_dets, int ld_dets,
                              float* d_out, int* d_n_out, int ld_out, void* stream);
+/* BoT-SORT engines (created with emb_dim = D > 0): the same calls with the detections' ReID embeddings,
+ * embs [n_frames][S][ld_dets][D] fp32 (row j of a frame belongs to detection j; NULL = no embeddings).  Replaces the
+ * `embs` argument of BaseTracker::update (include/motcpp/tracker.hpp:67-69, src/trackers/botsort.cpp:260-283). */
+int mot_engine_update_host_embs(mot_engine* e, int n_frames, const float* dets, const int* n_dets, int ld_dets,
+                                const float* embs, float* out, int* n_out, int ld_out);
+int mot_engine_update_device_embs(mot_engine* e, int n_frames, const float* d_dets, const int* d_n_dets, int ld_dets,
+                                  const float* d_embs, float* d_out, int* d_n_out, int ld_out, void* stream);
 /* Per-stream sticky error bits since the last reset (0 = fine): 1 track capacity, 2 too many
  * detections, 4 output rows truncated, 8 Kalman fallback.  Synchronises.  flags may be NULL; the
  * return value is MOT_OK or the most severe condition as a mot_status. */
@@ -118,6 +125,10 @@ int mot_engine_check(mot_engine* e, int* flags_per_stream);
  * n1,m1,n2,m2,n3,m3,dupA,dupB,..] (16 ints), and a dump of one list (0 active, 1 lost) as rows of
  * [id,state,is_activated,frame_id,start_frame,tracklet_len,mean 8,cov 64] (78 floats). */
 int mot_engine_stream_header(mot_engine* e, int stream_index, int* hdr16);
+/* BoT-SORT engines: list `which` (0 active, 1 lost) as rows of [id,state,is_activated,frame_id,start_frame,
+ * tracklet_len,conf,cls,det_ind,has_feat,mean 8,cov 64] (82 floats); feats (nullable) receives the tracks'
+ * smoothed features, emb_dim floats per row. */
+int mot_engine_dump_bot(mot_engine* e, int stream_index, int which, float* rows82, float* feats, int cap_rows, int* n_rows);
 int mot_engine_dump_list(mot_engine* e, int stream_index, int which, float* rows78, int cap_rows, int* n_rows);
 /* launch geometry actually used (for the bench's gpu_launches / roofline bookkeeping) */
 int mot_engine_info(mot_engine* e, int* threads_per_cta, int* smem_bytes, int* ctas, int* state_bytes_per_stream);

@@ -62,6 +62,9 @@ SYMBOLS = {
     "mot_engine_reset": (_I, [_VP]),
     "mot_engine_update_host": (_I, [_VP, _I, _VP, _VP, _I, _VP, _VP, _I]),
     "mot_engine_update_device": (_I, [_VP, _I, _VP, _VP, _I, _VP, _VP, _I, _VP]),
+    "mot_engine_update_host_embs": (_I, [_VP, _I, _VP, _VP, _I, _VP, _VP, _VP, _I]),
+    "mot_engine_update_device_embs": (_I, [_VP, _I, _VP, _VP, _I, _VP, _VP, _VP, _I, _VP]),
+    "mot_engine_dump_bot": (_I, [_VP, _I, _I, _VP, _VP, _I, C.POINTER(_I)]),
     "mot_engine_check": (_I, [_VP, _VP]),
     "mot_engine_stream_header": (_I, [_VP, _I, _VP]),
     "mot_engine_dump_list": (_I, [_VP, _I, _I, _VP, _I, C.POINTER(_I)]),

@@ -332,12 +332,15 @@ class Engine:
         check(load().mot_engine_reset(self._h))
 
     def update(self, dets: np.ndarray, n_dets: np.ndarray, out: Optional[np.ndarray] = None,
-               n_out: Optional[np.ndarray] = None, ld_out: int = 0):
-        """dets (T,S,ld,6) or (S,ld,6) float32, n_dets (T,S) or (S,) int32 -> out (T,S,ld_out,8), n_out (T,S)."""
+               n_out: Optional[np.ndarray] = None, ld_out: int = 0, embs: Optional[np.ndarray] = None):
+        """dets (T,S,ld,6) or (S,ld,6) float32, n_dets (T,S) or (S,) int32 -> out (T,S,ld_out,8), n_out (T,S).
+        BoT-SORT engines also take embs (T,S,ld,emb_dim): the ReID feature of every detection row."""
         dets = np.asarray(dets)
         squeeze = dets.ndim == 3
         if squeeze:
             dets = dets[None]
+            if embs is not None:
+                embs = np.asarray(embs)[None]
         if dets.dtype != np.float32 or not dets.flags.c_contiguous:
             dets = np.ascontiguousarray(dets, np.float32)
         T, S, ld, six = dets.shape
@@ -352,9 +355,15 @@ class Engine:
             out = np.empty((T, S, ld_out, 8), np.float32)
         if n_out is None:
             n_out = np.empty((T, S), np.int32)
+        ep = None
+        if embs is not None:
+            embs = np.ascontiguousarray(embs, np.float32)
+            if embs.shape[:3] != (T, S, ld) or embs.shape[3] != self.cfg.emb_dim:
+                raise ValueError("Detections and embeddings must have same number of rows")   # src/tracker.cpp:118-121
+            ep = embs.ctypes.data
         try:
-            check(load().mot_engine_update_host(self._h, T, dets.ctypes.data, n_dets.ctypes.data, ld, out.ctypes.data,
-                                                n_out.ctypes.data, out.shape[2]))
+            check(load().mot_engine_update_host_embs(self._h, T, dets.ctypes.data, n_dets.ctypes.data, ld, ep,
+                                                     out.ctypes.data, n_out.ctypes.data, out.shape[2]))
         except MotError as e:
             _raise(e)
         return (out[0], n_out[0]) if squeeze else (out, n_out)
@@ -389,6 +398,19 @@ class Engine:
         k = C.c_int()
         check(load().mot_engine_dump_list(self._h, stream, which, buf.ctypes.data, max(n, 1), C.byref(k)))
         return buf[:k.value]
+
+    def dump_bot(self, stream: int, which: int, with_feats: bool = False):
+        """BoT-SORT engines: rows of [id, state, is_activated, frame_id, start_frame, tracklet_len, conf, cls, det_ind,
+        has_feat, mean 8, cov 64] for list `which` (0 active, 1 lost) and optionally the smoothed features."""
+        hdr = self.header(stream)
+        n = max(int(hdr[0] if which == 0 else hdr[1]), 1)
+        buf = np.zeros((n, 82), np.float32)
+        dim = int(self.cfg.emb_dim)
+        feats = np.zeros((n, max(dim, 1)), np.float32)
+        k = C.c_int()
+        check(load().mot_engine_dump_bot(self._h, stream, which, buf.ctypes.data,
+                                         feats.ctypes.data if (with_feats and dim) else None, n, C.byref(k)))
+        return (buf[:k.value], feats[:k.value]) if with_feats else buf[:k.value]
 
     def info(self):
         a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
@@ -529,5 +551,69 @@ class OCSort:
             raise ValueError(f"{n} detections exceed max_dets={self._max_dets}")
         self._dets[0, 0, :n] = dets[:, :6] if n else 0
         self._engine.update(self._dets, np.array([[n]], np.int32), self._out, self._n_out)
+        self._engine.check()
+        return self._out[0, 0, :int(self._n_out[0, 0])].copy()
+
+
+class BotSort:
+    """motcpp::trackers::BotSort with the reference's positional constructor
+    (include/motcpp/trackers/botsort.hpp:108-134).  Camera-motion compensation and the ReID network are image
+    processing outside the accelerated path: cmc_method must be "none" and embeddings are passed to update()
+    (the reference's `embs` argument).  One stream; for many streams use Engine."""
+
+    def __init__(self, reid_weights="", use_half=False, use_gpu=False, det_thresh=0.3, max_age=30, max_obs=50,
+                 min_hits=3, iou_threshold=0.3, per_class=False, nr_classes=80, asso_func="iou", is_obb=False,
+                 track_high_thresh=0.5, track_low_thresh=0.1, new_track_thresh=0.6, track_buffer=30, match_thresh=0.8,
+                 proximity_thresh=0.5, appearance_thresh=0.25, cmc_method="none", frame_rate=30,
+                 fuse_first_associate=False, with_reid=True, emb_dim=0, track_capacity=1536, max_dets=512, device=0):
+        if cmc_method not in ("none", "", None):
+            raise ValueError("camera-motion compensation (cmc_method=%r) is outside the accelerated hot path" % cmc_method)
+        if reid_weights:
+            raise ValueError("ReID inference is outside the accelerated hot path: pass embeddings to update()")
+        if asso_func != "iou" or per_class or is_obb:
+            raise ValueError("only asso_func=\"iou\", per_class=False, is_obb=False are on the accelerated path")
+        self._engine = Engine(_lib.TRACKER_BOTSORT, 1, track_capacity, max_dets, device, det_thresh=det_thresh,
+                              max_age=max_age, max_obs=max_obs, min_hits=min_hits, iou_threshold=iou_threshold,
+                              track_high_thresh=track_high_thresh, track_low_thresh=track_low_thresh,
+                              new_track_thresh=new_track_thresh, track_buffer=track_buffer, match_thresh=match_thresh,
+                              proximity_thresh=proximity_thresh, appearance_thresh=appearance_thresh,
+                              frame_rate=frame_rate, fuse_first_associate=int(bool(fuse_first_associate)),
+                              with_reid=int(bool(with_reid)), emb_dim=emb_dim)
+        self._dim = emb_dim
+        self._max_dets = self._engine.cfg.max_dets
+        self._cap = self._engine.cfg.track_capacity
+        self._dets = np.zeros((1, 1, self._max_dets, 6), np.float32)
+        self._embs = np.zeros((1, 1, self._max_dets, emb_dim), np.float32) if emb_dim else None
+        self._out = np.empty((1, 1, self._cap, 8), np.float32)
+        self._n_out = np.empty((1, 1), np.int32)
+
+    def reset(self):
+        self._engine.reset()
+
+    def update(self, dets, img, embs=None) -> np.ndarray:
+        dets = np.asarray(dets, np.float32)
+        if dets.ndim != 2:
+            dets = dets.reshape(0, 6) if dets.size == 0 else dets
+        # BaseTracker::check_inputs(dets, img) (src/tracker.cpp:108-125; BotSort passes no embs to it)
+        if dets.shape[0] > 0 and dets.shape[1] not in (6, 7):
+            raise ValueError("Detections must have 6 (AABB) or 7 (OBB) columns")
+        if _Image(img).empty():
+            raise ValueError("Image cannot be empty")
+        if dets.shape[0] > 0 and dets.shape[1] == 7:
+            raise ValueError("OBB detections are outside the accelerated hot path")
+        n = dets.shape[0]
+        if n == 0:
+            return np.zeros((0, 8), np.float32)                 # botsort.cpp:267-269
+        if n > self._max_dets:
+            raise ValueError(f"{n} detections exceed max_dets={self._max_dets}")
+        self._dets[0, 0, :n] = dets[:, :6]
+        e = None
+        if embs is not None and np.size(embs) and self._dim:
+            embs = np.asarray(embs, np.float32)
+            if embs.shape != (n, self._dim):
+                raise ValueError("Detections and embeddings must have same number of rows")
+            self._embs[0, 0, :n] = embs
+            e = self._embs
+        self._engine.update(self._dets, np.array([[n]], np.int32), self._out, self._n_out, embs=e)
         self._engine.check()
         return self._out[0, 0, :int(self._n_out[0, 0])].copy()

@@ -19,6 +19,7 @@
 #include "kernels_cosine.cuh"
 #include "sort_kernel.cuh"
 #include "ocsort_kernel.cuh"
+#include "botsort_kernel.cuh"
 
 namespace {
 
@@ -74,6 +75,9 @@ struct mot_engine {
     mot::SortLayout sort_layout;   // SORT slab layout (kind == SORT)
     mot::OcLayout oc_layout;       // OC-SORT slab layout (kind == OCSORT)
     mot::OcParams ocp;
+    mot::BotLayout bot_layout;     // BoT-SORT slab layout (kind == BOTSORT; feature dimension is a run-time size)
+    mot::BotParams botp;
+    float* d_embs = nullptr;  size_t embs_cap = 0;
     size_t stride = 0;             // bytes per stream slab (whichever layout is live)
     int threads = 0;
     mot::BtParams bt;
@@ -99,6 +103,8 @@ static int engine_reset_impl(mot_engine* e, int keep_ids) {
         mot::sort_reset_kernel<<<grid, 256, 0, e->streams[0]>>>(e->d_state, e->sort_layout, e->cfg.n_streams, keep_ids);
     else if (e->cfg.kind == MOT_TRACKER_OCSORT)
         mot::ocsort_reset_kernel<<<grid, 256, 0, e->streams[0]>>>(e->d_state, e->oc_layout, e->cfg.n_streams, keep_ids);
+    else if (e->cfg.kind == MOT_TRACKER_BOTSORT)
+        mot::botsort_reset_kernel<<<grid, 256, 0, e->streams[0]>>>(e->d_state, e->bot_layout, e->cfg.n_streams);
     else
         mot::bytetrack_reset_kernel<<<grid, 256, 0, e->streams[0]>>>(e->d_state, e->layout, e->cfg.n_streams, keep_ids);
     MOT_CUDA(cudaGetLastError());
@@ -190,9 +196,36 @@ static void oc_launch(int shape, int grid, size_t smem, cudaStream_t st, const m
 }
 static_assert(mot::kNumOcShapes == 3, "update the OC-SORT dispatch switches");
 
+template <int I>
+static cudaError_t bot_set_smem(size_t bytes) {
+    constexpr mot::BtShape sh = mot::kBotShapes[I];
+    return cudaFuncSetAttribute(mot::botsort_step_kernel<sh.cap, sh.d_max, sh.e_cap>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+template <int I>
+static void bot_launch_one(int grid, size_t smem, cudaStream_t st, const mot::BotArgs& a) {
+    constexpr mot::BtShape sh = mot::kBotShapes[I];
+    mot::botsort_step_kernel<sh.cap, sh.d_max, sh.e_cap><<<grid, mot::kBotThreads, smem, st>>>(a);
+}
+static cudaError_t bot_prepare(int shape, size_t smem) {
+    switch (shape) {
+        case 0: return bot_set_smem<0>(smem);
+        case 1: return bot_set_smem<1>(smem);
+        default: return bot_set_smem<2>(smem);
+    }
+}
+static void bot_launch(int shape, int grid, size_t smem, cudaStream_t st, const mot::BotArgs& a) {
+    switch (shape) {
+        case 0: bot_launch_one<0>(grid, smem, st, a); break;
+        case 1: bot_launch_one<1>(grid, smem, st, a); break;
+        default: bot_launch_one<2>(grid, smem, st, a); break;
+    }
+}
+static_assert(mot::kNumBotShapes == 3, "update the BoT-SORT dispatch switches");
+
 // one launch covering streams [s0, s1) for T frames, whatever the tracker kind
-static void engine_launch(mot_engine* e, int T, const float* dets, const int* nd, int ld_dets, float* out, int* nout,
-                          int ld_out, int s0, int s1, cudaStream_t st);
+static void engine_launch(mot_engine* e, int T, const float* dets, const int* nd, int ld_dets, const float* embs,
+                          float* out, int* nout, int ld_out, int s0, int s1, cudaStream_t st);
 
 static mot::BtArgs make_args(mot_engine* e, int T, const float* dets, const int* nd, int ld_dets, float* out, int* nout,
                              int ld_out, int s_begin, int s_end) {
@@ -204,9 +237,15 @@ static mot::BtArgs make_args(mot_engine* e, int T, const float* dets, const int*
     return a;
 }
 
-static void engine_launch(mot_engine* e, int T, const float* dets, const int* nd, int ld_dets, float* out, int* nout,
-                          int ld_out, int s0, int s1, cudaStream_t st) {
-    if (e->cfg.kind == MOT_TRACKER_SORT) {
+static void engine_launch(mot_engine* e, int T, const float* dets, const int* nd, int ld_dets, const float* embs,
+                          float* out, int* nout, int ld_out, int s0, int s1, cudaStream_t st) {
+    if (e->cfg.kind == MOT_TRACKER_BOTSORT) {
+        mot::BotArgs a{};
+        a.state = e->d_state; a.L = e->bot_layout; a.dets = dets; a.n_dets = nd; a.embs = embs; a.out = out; a.n_out = nout;
+        a.T = T; a.S = e->cfg.n_streams; a.ld_dets = ld_dets; a.ld_out = ld_out; a.s_begin = s0; a.s_end = s1;
+        a.p = e->botp;
+        bot_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
+    } else if (e->cfg.kind == MOT_TRACKER_SORT) {
         mot::SortArgs a{};
         a.state = e->d_state; a.dets = dets; a.n_dets = nd; a.out = out; a.n_out = nout;
         a.T = T; a.S = e->cfg.n_streams; a.ld_dets = ld_dets; a.ld_out = ld_out; a.s_begin = s0; a.s_end = s1;
@@ -310,8 +349,10 @@ int mot_engine_default_config(int kind, mot_engine_config* c) {
 int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     if (!cfg || !out) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
     *out = nullptr;
-    if (cfg->kind != MOT_TRACKER_BYTETRACK && cfg->kind != MOT_TRACKER_SORT && cfg->kind != MOT_TRACKER_OCSORT)
-        return fail(MOT_ERR_UNSUPPORTED, "tracker kind %d is not built in this library version (SORT = 0, ByteTrack = 1 and OC-SORT = 2 are)", cfg->kind);
+    if (cfg->kind < MOT_TRACKER_SORT || cfg->kind > MOT_TRACKER_BOTSORT)
+        return fail(MOT_ERR_INVALID_ARGUMENT, "unknown tracker kind %d", cfg->kind);
+    if (cfg->kind == MOT_TRACKER_BOTSORT && (cfg->emb_dim < 0 || (cfg->emb_dim & 3)))
+        return fail(MOT_ERR_INVALID_ARGUMENT, "emb_dim %d must be a non-negative multiple of 4", cfg->emb_dim);
     if (cfg->n_streams <= 0) return fail(MOT_ERR_INVALID_ARGUMENT, "n_streams must be positive");
     if (cfg->kind == MOT_TRACKER_OCSORT && (cfg->delta_t < 1 || cfg->delta_t > mot::kOcRing))
         return fail(MOT_ERR_UNSUPPORTED, "delta_t %d is outside 1..%d (observation ring size)", cfg->delta_t, mot::kOcRing);
@@ -320,6 +361,7 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     mot_engine* e = new mot_engine();
     e->cfg = *cfg;
     const bool is_sort = cfg->kind == MOT_TRACKER_SORT, is_oc = cfg->kind == MOT_TRACKER_OCSORT;
+    const bool is_bot = cfg->kind == MOT_TRACKER_BOTSORT;
     if (e->cfg.track_capacity <= 0) e->cfg.track_capacity = 1536;
     if (e->cfg.max_dets <= 0) e->cfg.max_dets = 512;
     // round the request up to the nearest shape the kernel is instantiated for
@@ -327,6 +369,9 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     if (is_oc) {
         for (int i = 0; i < mot::kNumOcShapes; ++i)
             if (mot::kOcShapes[i].cap >= e->cfg.track_capacity && mot::kOcShapes[i].d_max >= e->cfg.max_dets) { e->shape = i; break; }
+    } else if (is_bot) {
+        for (int i = 0; i < mot::kNumBotShapes; ++i)
+            if (mot::kBotShapes[i].cap >= e->cfg.track_capacity && mot::kBotShapes[i].d_max >= e->cfg.max_dets) { e->shape = i; break; }
     } else {
         for (int i = 0; i < mot::kNumBtShapes; ++i)
             if (mot::kBtShapes[i].cap >= e->cfg.track_capacity && mot::kBtShapes[i].d_max >= e->cfg.max_dets) { e->shape = i; break; }
@@ -335,11 +380,11 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
         const int tc = e->cfg.track_capacity, md = e->cfg.max_dets;
         delete e;
         return fail(MOT_ERR_INVALID_ARGUMENT, "track_capacity %d / max_dets %d exceed the largest built shape (%s)", tc, md,
-                    is_oc ? "3072 tracks / 2048 detections" : "3072 tracks / 1024 detections");
+                    is_oc ? "3072 tracks / 2048 detections" : (is_bot ? "2048 tracks / 1024 detections" : "3072 tracks / 1024 detections"));
     }
-    e->cfg.track_capacity = is_oc ? mot::kOcShapes[e->shape].cap : mot::kBtShapes[e->shape].cap;
-    e->cfg.max_dets = is_oc ? mot::kOcShapes[e->shape].d_max : mot::kBtShapes[e->shape].d_max;
-    e->e_cap = is_oc ? mot::kOcShapes[e->shape].e_cap : mot::kBtShapes[e->shape].e_cap;
+    e->cfg.track_capacity = is_oc ? mot::kOcShapes[e->shape].cap : (is_bot ? mot::kBotShapes[e->shape].cap : mot::kBtShapes[e->shape].cap);
+    e->cfg.max_dets = is_oc ? mot::kOcShapes[e->shape].d_max : (is_bot ? mot::kBotShapes[e->shape].d_max : mot::kBtShapes[e->shape].d_max);
+    e->e_cap = is_oc ? mot::kOcShapes[e->shape].e_cap : (is_bot ? mot::kBotShapes[e->shape].e_cap : mot::kBtShapes[e->shape].e_cap);
     // BaseTracker ctor fix-up (src/tracker.cpp:37-39)
     if (e->cfg.max_age >= e->cfg.max_obs) e->cfg.max_obs = e->cfg.max_age + 5;
     e->layout = mot::BtLayout::make(e->cfg.track_capacity, e->cfg.max_dets);
@@ -364,10 +409,22 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     e->ocp.min_hits = cfg->min_hits;
     e->ocp.delta_t = cfg->delta_t;
     e->ocp.use_byte = cfg->use_byte;
-    e->stride = is_sort ? e->sort_layout.stride : (is_oc ? e->oc_layout.stride : e->layout.stride);
-    e->threads = is_sort ? mot::kSortThreads : (is_oc ? mot::kOcThreads : mot::kBtThreads);
+    e->bot_layout = mot::BotLayout::make(e->cfg.track_capacity, e->cfg.max_dets, cfg->emb_dim);
+    e->botp.track_high_thresh = cfg->track_high_thresh;
+    e->botp.track_low_thresh = cfg->track_low_thresh;
+    e->botp.new_track_thresh = cfg->new_track_thresh;
+    e->botp.match_thresh = cfg->match_thresh;
+    e->botp.proximity_thresh = cfg->proximity_thresh;
+    e->botp.appearance_thresh = cfg->appearance_thresh;
+    e->botp.max_time_lost = (int)(cfg->frame_rate / 30.0f * cfg->track_buffer);  // botsort.cpp:235-236
+    e->botp.fuse_first = cfg->fuse_first_associate;
+    e->botp.with_reid = cfg->with_reid;
+    e->botp.dim = cfg->emb_dim;
+    e->stride = is_sort ? e->sort_layout.stride : (is_oc ? e->oc_layout.stride : (is_bot ? e->bot_layout.stride : e->layout.stride));
+    e->threads = is_sort ? mot::kSortThreads : (is_oc ? mot::kOcThreads : (is_bot ? mot::kBotThreads : mot::kBtThreads));
     e->smem_bytes = is_sort ? mot::sort_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap)
                   : is_oc   ? mot::oc_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap)
+                  : is_bot  ? mot::bot_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap)
                             : mot::bt_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap);
     int max_optin = 0;
     MOT_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
@@ -378,7 +435,8 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
                     need, max_optin);
     }
     MOT_CUDA(is_sort ? sort_prepare(e->shape, e->smem_bytes)
-                     : (is_oc ? oc_prepare(e->shape, e->smem_bytes) : bt_prepare(e->shape, e->smem_bytes)));
+                     : (is_oc ? oc_prepare(e->shape, e->smem_bytes)
+                              : (is_bot ? bot_prepare(e->shape, e->smem_bytes) : bt_prepare(e->shape, e->smem_bytes))));
     e->n_chunks = cfg->n_chunks > 0 ? std::min(cfg->n_chunks, kMaxChunks) : (cfg->n_streams >= 128 ? 8 : (cfg->n_streams >= 32 ? 4 : 1));
     e->n_chunks = std::min(e->n_chunks, cfg->n_streams);
     for (int c = 0; c < e->n_chunks; ++c) MOT_CUDA(cudaStreamCreateWithFlags(&e->streams[c], cudaStreamNonBlocking));
@@ -394,7 +452,7 @@ int mot_engine_destroy(mot_engine* e) {
     cudaSetDevice(e->cfg.device);
     for (int c = 0; c < kMaxChunks; ++c)
         if (e->streams[c]) cudaStreamDestroy(e->streams[c]);
-    cudaFree(e->d_state); cudaFree(e->d_dets); cudaFree(e->d_ndets); cudaFree(e->d_out); cudaFree(e->d_nout);
+    cudaFree(e->d_state); cudaFree(e->d_embs); cudaFree(e->d_dets); cudaFree(e->d_ndets); cudaFree(e->d_out); cudaFree(e->d_nout);
     delete e;
     return MOT_OK;
 }
@@ -403,43 +461,59 @@ int mot_engine_reset(mot_engine* e) {
     if (!e) return fail(MOT_ERR_INVALID_ARGUMENT, "null engine");
     MOT_CUDA(cudaSetDevice(e->cfg.device));
     for (int c = 0; c < e->n_chunks; ++c) MOT_CUDA(cudaStreamSynchronize(e->streams[c]));
-    return engine_reset_impl(e, /*keep_ids=*/1);
+    return engine_reset_impl(e, /*keep_ids=*/1);     // BoT-SORT ignores the flag: its ids restart (botsort.cpp:257)
 }
 
-int mot_engine_update_device(mot_engine* e, int T, const float* d_dets, const int* d_n_dets, int ld_dets,
-                             float* d_out, int* d_n_out, int ld_out, void* stream) {
+int mot_engine_update_device_embs(mot_engine* e, int T, const float* d_dets, const int* d_n_dets, int ld_dets,
+                                  const float* d_embs, float* d_out, int* d_n_out, int ld_out, void* stream) {
     if (!e || !d_dets || !d_n_dets || !d_out || !d_n_out) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
     if (T <= 0 || ld_dets <= 0 || ld_out <= 0) return fail(MOT_ERR_INVALID_ARGUMENT, "non-positive size");
     if ((ld_out * 8 * sizeof(float)) % 16 != 0 || (((size_t)d_out) & 15)) return fail(MOT_ERR_INVALID_ARGUMENT, "out must be 16-byte aligned");
+    if (d_embs && (e->cfg.kind != MOT_TRACKER_BOTSORT || e->cfg.emb_dim <= 0))
+        return fail(MOT_ERR_INVALID_ARGUMENT, "embeddings need a BoT-SORT engine created with emb_dim > 0");
+    if (d_embs && (((size_t)d_embs) & 15)) return fail(MOT_ERR_INVALID_ARGUMENT, "embs must be 16-byte aligned");
     const int S = e->cfg.n_streams;
-    engine_launch(e, T, d_dets, d_n_dets, ld_dets, d_out, d_n_out, ld_out, 0, S, (cudaStream_t)stream);
+    engine_launch(e, T, d_dets, d_n_dets, ld_dets, d_embs, d_out, d_n_out, ld_out, 0, S, (cudaStream_t)stream);
     MOT_CUDA(cudaGetLastError());
     return MOT_OK;
 }
 
-int mot_engine_update_host(mot_engine* e, int T, const float* dets, const int* n_dets, int ld_dets, float* out,
-                           int* n_out, int ld_out) {
+int mot_engine_update_device(mot_engine* e, int T, const float* d_dets, const int* d_n_dets, int ld_dets,
+                             float* d_out, int* d_n_out, int ld_out, void* stream) {
+    return mot_engine_update_device_embs(e, T, d_dets, d_n_dets, ld_dets, nullptr, d_out, d_n_out, ld_out, stream);
+}
+
+int mot_engine_update_host_embs(mot_engine* e, int T, const float* dets, const int* n_dets, int ld_dets, const float* embs,
+                                float* out, int* n_out, int ld_out) {
     if (!e || !dets || !n_dets || !out || !n_out) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
     if (T <= 0 || ld_dets <= 0 || ld_out <= 0) return fail(MOT_ERR_INVALID_ARGUMENT, "non-positive size");
+    if (embs && (e->cfg.kind != MOT_TRACKER_BOTSORT || e->cfg.emb_dim <= 0))
+        return fail(MOT_ERR_INVALID_ARGUMENT, "embeddings need a BoT-SORT engine created with emb_dim > 0");
     MOT_CUDA(cudaSetDevice(e->cfg.device));
     const int S = e->cfg.n_streams;
     const size_t TS = (size_t)T * S;
+    const size_t dim = embs ? (size_t)e->cfg.emb_dim : 0;
     if (int rc = grow(&e->d_dets, &e->dets_cap, TS * ld_dets * 6)) return rc;
     if (int rc = grow(&e->d_ndets, &e->ndets_cap, TS)) return rc;
     if (int rc = grow(&e->d_out, &e->out_cap, TS * ld_out * 8)) return rc;
     if (int rc = grow(&e->d_nout, &e->nout_cap, TS)) return rc;
+    if (embs) if (int rc = grow(&e->d_embs, &e->embs_cap, TS * ld_dets * dim)) return rc;
     const int C = e->n_chunks;
     for (int c = 0; c < C; ++c) {
         const int s0 = (int)((long long)S * c / C), s1 = (int)((long long)S * (c + 1) / C);
         if (s1 <= s0) continue;
         cudaStream_t st = e->streams[c];
         const size_t det_row = (size_t)ld_dets * 6 * sizeof(float), out_row = (size_t)ld_out * 8 * sizeof(float);
+        const size_t emb_row = (size_t)ld_dets * dim * sizeof(float);
         // [T][S][...] -> a (T x chunk) sub-block is a 2-D copy with pitch S * row
         MOT_CUDA(cudaMemcpy2DAsync(e->d_dets + (size_t)s0 * ld_dets * 6, S * det_row, dets + (size_t)s0 * ld_dets * 6,
                                    S * det_row, (s1 - s0) * det_row, T, cudaMemcpyHostToDevice, st));
         MOT_CUDA(cudaMemcpy2DAsync(e->d_ndets + s0, S * sizeof(int), n_dets + s0, S * sizeof(int),
                                    (s1 - s0) * sizeof(int), T, cudaMemcpyHostToDevice, st));
-        engine_launch(e, T, e->d_dets, e->d_ndets, ld_dets, e->d_out, e->d_nout, ld_out, s0, s1, st);
+        if (embs)
+            MOT_CUDA(cudaMemcpy2DAsync(e->d_embs + (size_t)s0 * ld_dets * dim, S * emb_row, embs + (size_t)s0 * ld_dets * dim,
+                                       S * emb_row, (s1 - s0) * emb_row, T, cudaMemcpyHostToDevice, st));
+        engine_launch(e, T, e->d_dets, e->d_ndets, ld_dets, embs ? e->d_embs : nullptr, e->d_out, e->d_nout, ld_out, s0, s1, st);
         MOT_CUDA(cudaGetLastError());
         MOT_CUDA(cudaMemcpy2DAsync(out + (size_t)s0 * ld_out * 8, S * out_row, e->d_out + (size_t)s0 * ld_out * 8,
                                    S * out_row, (s1 - s0) * out_row, T, cudaMemcpyDeviceToHost, st));
@@ -447,6 +521,46 @@ int mot_engine_update_host(mot_engine* e, int T, const float* dets, const int* n
                                    (s1 - s0) * sizeof(int), T, cudaMemcpyDeviceToHost, st));
     }
     for (int c = 0; c < C; ++c) MOT_CUDA(cudaStreamSynchronize(e->streams[c]));
+    return MOT_OK;
+}
+
+int mot_engine_update_host(mot_engine* e, int T, const float* dets, const int* n_dets, int ld_dets, float* out,
+                           int* n_out, int ld_out) {
+    return mot_engine_update_host_embs(e, T, dets, n_dets, ld_dets, nullptr, out, n_out, ld_out);
+}
+
+// BoT-SORT engines: list `which` (0 active, 1 lost) as rows of [id, state, is_activated, frame_id, start_frame,
+// tracklet_len, conf, cls, det_ind, has_feat, mean 8, cov 64] (82 floats) and, when feats != NULL, the smooth features
+int mot_engine_dump_bot(mot_engine* e, int s, int which, float* rows82, float* feats, int cap_rows, int* n_rows) {
+    if (!e || !rows82 || !n_rows || s < 0 || s >= e->cfg.n_streams) return fail(MOT_ERR_INVALID_ARGUMENT, "bad argument");
+    if (e->cfg.kind != MOT_TRACKER_BOTSORT) return fail(MOT_ERR_UNSUPPORTED, "not a BoT-SORT engine");
+    MOT_CUDA(cudaSetDevice(e->cfg.device));
+    MOT_CUDA(cudaDeviceSynchronize());
+    const mot::BotLayout& L = e->bot_layout;
+    std::vector<unsigned char> slab(L.off_tnorm);
+    const unsigned char* dbase = e->d_state + (size_t)s * L.stride;
+    MOT_CUDA(cudaMemcpy(slab.data(), dbase, slab.size(), cudaMemcpyDeviceToHost));
+    const int* hdr = (const int*)slab.data();
+    const unsigned short* list = (const unsigned short*)(slab.data() + L.off_lists) + (which == 0 ? 0 : L.cap);
+    const int n = which == 0 ? hdr[mot::kHdrActive] : hdr[mot::kHdrLost];
+    const unsigned char* sflag = slab.data() + L.off_sflag;
+    const int* m = (const int*)(slab.data() + L.off_meta);
+    const float* recs = (const float*)(slab.data() + L.off_recs);
+    const int cap = L.cap;
+    int k = 0;
+    for (; k < n && k < cap_rows; ++k) {
+        const int slot = list[k];
+        float* o = rows82 + 82 * (size_t)k;
+        o[0] = (float)m[slot]; o[1] = (float)(sflag[slot] & 0x0f); o[2] = (sflag[slot] & 0x10) ? 1.0f : 0.0f;
+        o[3] = (float)m[2 * cap + slot]; o[4] = (float)m[3 * cap + slot]; o[5] = (float)m[cap + slot];
+        o[6] = ((const float*)m)[6 * cap + slot]; o[7] = (float)m[4 * cap + slot]; o[8] = (float)m[5 * cap + slot];
+        o[9] = (sflag[slot] & 0x20) ? 1.0f : 0.0f;
+        std::memcpy(o + 10, recs + (size_t)slot * mot::kRecFloats, sizeof(float) * mot::kRecFloats);
+        if (feats && L.dim > 0)
+            MOT_CUDA(cudaMemcpy(feats + (size_t)L.dim * k, dbase + L.off_feats + sizeof(float) * (size_t)slot * L.dim,
+                                sizeof(float) * L.dim, cudaMemcpyDeviceToHost));
+    }
+    *n_rows = k;
     return MOT_OK;
 }
 

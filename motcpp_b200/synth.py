@@ -171,3 +171,58 @@ def ocsort_stream(stream_id: int = 0, n_frames: int = 250, n_obj: int = 2048, ca
         out[t, :, 4] = rng.uniform(0.25, 0.99, n_obj)
         out[t, :, 5] = 0.0
     return out
+
+
+def stress_stream_reid(stream_id: int = 0, n_frames: int = 200, n_obj: int = 40, dim: int = 32, canvas=(960, 540),
+                       noise: float = 0.5, config: int = 8):
+    """Parity-stress generator with ReID embeddings for BoT-SORT (not timed): the stress_stream scenario
+    (misses, confidence drops, births/deaths, crossings, clutter) plus one feature vector per detection:
+    normalise(identity_k + noise * N(0, I)) for true objects (deliberately NOT unit length: a random scale is
+    applied so the tracker's own normalisation is exercised), random vectors for clutter.
+    Returns dets (T, max_dets, 6), counts (T,), embs (T, max_dets, dim)."""
+    rng = _rng(config, stream_id)
+    W, H = canvas
+    w = rng.uniform(30, 90, n_obj)
+    h = 2.2 * w
+    cx = rng.uniform(0, W, n_obj)
+    cy = rng.uniform(0, H, n_obj)
+    vx = rng.normal(0, 4, n_obj)
+    vy = rng.normal(0, 2, n_obj)
+    ident = rng.normal(0, 1, (n_obj, dim))
+    ident /= np.linalg.norm(ident, axis=1, keepdims=True)
+    alive = rng.random(n_obj) < 0.7
+    max_dets = n_obj + 16
+    out = np.zeros((n_frames, max_dets, 6), np.float32)
+    embs = np.zeros((n_frames, max_dets, dim), np.float32)
+    counts = np.zeros(n_frames, np.int32)
+    for t in range(n_frames):
+        cx += vx
+        cy += vy
+        flip = (cx < 0) | (cx > W)
+        vx[flip] = -vx[flip]
+        flip = (cy < 0) | (cy > H)
+        vy[flip] = -vy[flip]
+        alive ^= rng.random(n_obj) < 0.01
+        rows, feats = [], []
+        for k in np.nonzero(alive)[0]:
+            if rng.random() < 0.10:
+                continue
+            conf = rng.uniform(0.55, 0.99)
+            if rng.random() < 0.08:
+                conf = rng.uniform(0.12, 0.5)
+            b = _boxes(cx[k], cy[k], w[k], h[k]) + rng.normal(0, 1.5, 4)
+            rows.append([*b, conf, 0.0])
+            e = ident[k] + noise * rng.normal(0, 1, dim) / np.sqrt(dim)
+            feats.append(e / np.linalg.norm(e) * rng.uniform(0.5, 2.0))
+        for _ in range(int(rng.integers(0, 6))):
+            cw = rng.uniform(30, 90)
+            b = _boxes(rng.uniform(0, W), rng.uniform(0, H), cw, 2.2 * cw)
+            rows.append([*b, rng.uniform(0.05, 0.99), 0.0])
+            feats.append(rng.normal(0, 1, dim))
+        rows = np.asarray(rows, np.float32).reshape(-1, 6)
+        feats = np.asarray(feats, np.float32).reshape(-1, dim)
+        perm = rng.permutation(len(rows))[:max_dets]
+        out[t, :len(perm)] = rows[perm]
+        embs[t, :len(perm)] = feats[perm]
+        counts[t] = len(perm)
+    return out, counts, embs

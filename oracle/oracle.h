@@ -130,6 +130,24 @@ void orc_ocsort_last_sizes(const OrcOcSort*, int* sizes8);
  * k_previous_obs(delta_t) 5, x 7, P 49] = 76 floats */
 int orc_ocsort_dump(const OrcOcSort*, float* out, int cap_rows);
 
+/* ---------------- BoT-SORT (src/trackers/botsort.cpp; cmc_method = "none", embeddings passed in) ------ */
+typedef struct OrcBotSort OrcBotSort;
+/* BotSort-specific ctor arguments (include/motcpp/trackers/botsort.hpp:108-134); BaseTracker knobs are unused by
+ * BotSort::update */
+OrcBotSort* orc_botsort_create(float track_high_thresh, float track_low_thresh, float new_track_thresh, int track_buffer,
+                               float match_thresh, float proximity_thresh, float appearance_thresh, int frame_rate,
+                               int fuse_first_associate, int with_reid);
+void orc_botsort_destroy(OrcBotSort*);
+void orc_botsort_reset(OrcBotSort*);
+/* dets (n,6); embs (n,dim) row-major or NULL; returns rows written (or -needed) */
+int orc_botsort_update(OrcBotSort*, const float* dets, int n, const float* embs, int dim, float* out, int out_cap);
+int orc_botsort_counts(const OrcBotSort*, int* n_active, int* n_lost);          /* returns frame_count */
+/* [n1, m1, n2, m2, n3, m3, n_new, n_lost_after] of the last update() */
+void orc_botsort_last_sizes(const OrcBotSort*, int* sizes8);
+/* list `which` (0 active, 1 lost): rows of [id, state, is_activated, frame_id, start_frame, tracklet_len, conf, cls,
+ * det_ind, has_feat, mean 8, cov 64] = 82 floats; feats (nullable): smooth_feat rows of dim floats */
+int orc_botsort_dump(const OrcBotSort*, int which, float* out, float* feats, int dim, int cap_rows);
+
 #ifdef __cplusplus
 }
 #endif

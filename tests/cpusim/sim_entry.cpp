@@ -230,3 +230,79 @@ int sim_oc_dump(void* hv, int s, float* rows, int cap_rows) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ BoT-SORT engine under the emulator
+#include "../../motcpp_b200/csrc/botsort_kernel.cuh"
+
+namespace {
+struct SimBot {
+    mot::BotLayout L;
+    int S;
+    mot::BotParams p;
+    std::vector<unsigned char> state;
+};
+}  // namespace
+
+extern "C" {
+
+void* sim_bot_create(int S, int dim, float high, float low, float new_thresh, int track_buffer, float match_thresh,
+                     float prox, float app, int frame_rate, int fuse_first, int with_reid) {
+    auto* h = new SimBot();
+    h->L = mot::BotLayout::make(256, 64, dim);
+    h->S = S;
+    h->p.track_high_thresh = high; h->p.track_low_thresh = low; h->p.new_track_thresh = new_thresh;
+    h->p.match_thresh = match_thresh; h->p.proximity_thresh = prox; h->p.appearance_thresh = app;
+    h->p.max_time_lost = (int)(frame_rate / 30.0f * track_buffer);
+    h->p.fuse_first = fuse_first; h->p.with_reid = with_reid; h->p.dim = dim;
+    h->state.assign(h->L.stride * (size_t)S + 256, 0);
+    unsigned char* st = h->state.data();
+    const mot::BotLayout L = h->L;
+    cpusim::launch(dim3(S), dim3(64), 0, [=] { mot::botsort_reset_kernel(st, L, S); });
+    return h;
+}
+void sim_bot_destroy(void* hv) { delete (SimBot*)hv; }
+
+int sim_bot_update(void* hv, const float* dets, const int* n_dets, const float* embs, int T, int ld_dets, float* out,
+                   int* n_out, int ld_out, int threads) {
+    auto* h = (SimBot*)hv;
+    mot::BotArgs a{};
+    a.state = h->state.data(); a.L = h->L; a.dets = dets; a.n_dets = n_dets; a.embs = embs; a.out = out; a.n_out = n_out;
+    a.T = T; a.S = h->S; a.ld_dets = ld_dets; a.ld_out = ld_out; a.s_begin = 0; a.s_end = h->S; a.p = h->p;
+    const size_t smem = mot::bot_smem_bytes(256, 64, 1024);
+    cpusim::launch(dim3(h->S), dim3(threads), smem, [=] { mot::botsort_step_kernel<256, 64, 1024>(a); });
+    return 0;
+}
+void sim_bot_header(void* hv, int s, int* hdr16) {
+    auto* h = (SimBot*)hv;
+    std::memcpy(hdr16, h->state.data() + (size_t)s * h->L.stride, sizeof(int) * 16);
+}
+
+// list `which` (0 active, 1 lost): rows of [id, state, is_activated, frame_id, start_frame, tracklet_len, conf, cls,
+// det_ind, has_feat, mean 8, cov 64] = 82 floats; feats (nullable): smooth_feat rows of dim floats
+int sim_bot_dump(void* hv, int s, int which, float* rows, float* feats, int cap_rows) {
+    auto* h = (SimBot*)hv;
+    unsigned char* base = h->state.data() + (size_t)s * h->L.stride;
+    const mot::BotLayout& L = h->L;
+    const int* hdr = (const int*)base;
+    const unsigned short* list = (const unsigned short*)(base + L.off_lists) + (which == 0 ? 0 : L.cap);
+    const int n = which == 0 ? hdr[mot::kHdrActive] : hdr[mot::kHdrLost];
+    const unsigned char* sflag = base + L.off_sflag;
+    const int* m = (const int*)(base + L.off_meta);
+    const float* recs = (const float*)(base + L.off_recs);
+    const float* ft = (const float*)(base + L.off_feats);
+    const int cap = L.cap;
+    int k = 0;
+    for (; k < n && k < cap_rows; ++k) {
+        const int slot = list[k];
+        float* o = rows + 82 * k;
+        o[0] = (float)m[slot]; o[1] = (float)(sflag[slot] & 0x0f); o[2] = (sflag[slot] & 0x10) ? 1.0f : 0.0f;
+        o[3] = (float)m[2 * cap + slot]; o[4] = (float)m[3 * cap + slot]; o[5] = (float)m[cap + slot];
+        o[6] = ((const float*)m)[6 * cap + slot]; o[7] = (float)m[4 * cap + slot]; o[8] = (float)m[5 * cap + slot];
+        o[9] = (sflag[slot] & 0x20) ? 1.0f : 0.0f;
+        std::memcpy(o + 10, recs + (size_t)slot * mot::kRecFloats, sizeof(float) * mot::kRecFloats);
+        if (feats && L.dim > 0) std::memcpy(feats + (size_t)L.dim * k, ft + (size_t)slot * L.dim, sizeof(float) * L.dim);
+    }
+    return k;
+}
+
+}  // extern "C"

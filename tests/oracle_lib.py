@@ -94,6 +94,18 @@ def lib() -> C.CDLL:
         L.orc_ocsort_last_sizes.argtypes = [C.c_void_p, i32p]
         L.orc_ocsort_dump.argtypes = [C.c_void_p, f32p, C.c_int]
         L.orc_ocsort_dump.restype = C.c_int
+        L.orc_botsort_create.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_float,
+                                         C.c_int, C.c_int, C.c_int]
+        L.orc_botsort_create.restype = C.c_void_p
+        L.orc_botsort_destroy.argtypes = [C.c_void_p]
+        L.orc_botsort_reset.argtypes = [C.c_void_p]
+        L.orc_botsort_update.argtypes = [C.c_void_p, f32p, C.c_int, C.c_void_p, C.c_int, f32p, C.c_int]
+        L.orc_botsort_update.restype = C.c_int
+        L.orc_botsort_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orc_botsort_counts.restype = C.c_int
+        L.orc_botsort_last_sizes.argtypes = [C.c_void_p, i32p]
+        L.orc_botsort_dump.argtypes = [C.c_void_p, C.c_int, f32p, C.c_void_p, C.c_int, C.c_int]
+        L.orc_botsort_dump.restype = C.c_int
         _LIB = L
     return _LIB
 
@@ -360,3 +372,53 @@ class OCSort:
         buf = np.zeros(max(n, 1), np.float32)
         lib().orc_ocsort_last_cost(self._h, buf.ctypes.data_as(C.c_void_p), n)
         return buf[:n].reshape(int(sz[0]), int(sz[1])) if n else np.zeros((0, 0), np.float32)
+
+
+class BotSort:
+    """Oracle BoT-SORT; BotSort-specific constructor arguments in the reference's order (botsort.hpp:121-133),
+    cmc_method fixed to "none", embeddings passed to update()."""
+
+    def __init__(self, track_high_thresh=0.5, track_low_thresh=0.1, new_track_thresh=0.6, track_buffer=30,
+                 match_thresh=0.8, proximity_thresh=0.5, appearance_thresh=0.25, frame_rate=30,
+                 fuse_first_associate=False, with_reid=True):
+        self._h = lib().orc_botsort_create(track_high_thresh, track_low_thresh, new_track_thresh, track_buffer,
+                                           match_thresh, proximity_thresh, appearance_thresh, frame_rate,
+                                           int(fuse_first_associate), int(with_reid))
+        self._out = np.zeros((8192, 8), np.float32)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_botsort_destroy(self._h)
+            self._h = None
+
+    def reset(self):
+        lib().orc_botsort_reset(self._h)
+
+    def update(self, dets, embs=None):
+        dets = _f32(dets).reshape(-1, 6)
+        if embs is not None and np.size(embs):
+            embs = _f32(embs).reshape(dets.shape[0], -1)
+            ep, dim = embs.ctypes.data_as(C.c_void_p), embs.shape[1]
+        else:
+            ep, dim = None, 0
+        n = lib().orc_botsort_update(self._h, dets, dets.shape[0], ep, dim, self._out, self._out.shape[0])
+        assert n >= 0
+        return self._out[:n].copy()
+
+    def counts(self):
+        a, b = C.c_int(), C.c_int()
+        lib().orc_botsort_counts(self._h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def dump(self, which, dim=0):
+        na, nl = self.counts()
+        cap = max(1, na if which == 0 else nl)
+        buf = np.zeros((cap, 82), np.float32)
+        feats = np.zeros((cap, max(dim, 1)), np.float32)
+        k = lib().orc_botsort_dump(self._h, which, buf, feats.ctypes.data_as(C.c_void_p) if dim else None, dim, cap)
+        return (buf[:k], feats[:k]) if dim else buf[:k]
+
+    def last_sizes(self):
+        s = np.zeros(8, np.int32)
+        lib().orc_botsort_last_sizes(self._h, s)
+        return s

@@ -41,6 +41,14 @@ def lib():
         S.sim_oc_dump.argtypes = [C.c_void_p, C.c_int, f32p, C.c_int]
         S.sim_oc_dump.restype = C.c_int
         S.sim_oc_destroy.argtypes = [C.c_void_p]
+        S.sim_bot_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float,
+                                     C.c_float, C.c_int, C.c_int, C.c_int]
+        S.sim_bot_create.restype = C.c_void_p
+        S.sim_bot_update.argtypes = [C.c_void_p, f32p, i32p, C.c_void_p, C.c_int, C.c_int, f32p, i32p, C.c_int, C.c_int]
+        S.sim_bot_header.argtypes = [C.c_void_p, C.c_int, i32p]
+        S.sim_bot_dump.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, C.c_void_p, C.c_int]
+        S.sim_bot_dump.restype = C.c_int
+        S.sim_bot_destroy.argtypes = [C.c_void_p]
         _LIB = S
     return _LIB
 
@@ -142,3 +150,44 @@ class SimOCSort:
         buf = np.zeros((self.cap, 71), np.float32)
         k = lib().sim_oc_dump(self.h, s, buf, self.cap)
         return buf[:k]
+
+
+class SimBotSort:
+    def __init__(self, n_streams=1, dim=0, track_high_thresh=0.5, track_low_thresh=0.1, new_track_thresh=0.6,
+                 track_buffer=30, match_thresh=0.8, proximity_thresh=0.5, appearance_thresh=0.25, frame_rate=30,
+                 fuse_first_associate=False, with_reid=True):
+        self.S, self.cap, self.dim = n_streams, 256, dim
+        self.h = lib().sim_bot_create(n_streams, dim, track_high_thresh, track_low_thresh, new_track_thresh, track_buffer,
+                                      match_thresh, proximity_thresh, appearance_thresh, frame_rate,
+                                      int(fuse_first_associate), int(with_reid))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().sim_bot_destroy(self.h)
+            self.h = None
+
+    def update(self, dets, n_dets, embs=None, threads=128):
+        """dets (T,S,ld,6), n_dets (T,S), embs (T,S,ld,dim) or None"""
+        dets = np.ascontiguousarray(dets, np.float32)
+        T, S, ld, _ = dets.shape
+        n_dets = np.ascontiguousarray(n_dets, np.int32).reshape(T, S)
+        ep = None
+        if embs is not None and self.dim > 0:
+            embs = np.ascontiguousarray(embs, np.float32)
+            assert embs.shape == (T, S, ld, self.dim)
+            ep = embs.ctypes.data_as(C.c_void_p)
+        out = np.zeros((T, S, self.cap, 8), np.float32)
+        n_out = np.zeros((T, S), np.int32)
+        lib().sim_bot_update(self.h, dets, n_dets, ep, T, ld, out, n_out, self.cap, threads)
+        return out, n_out
+
+    def header(self, s=0):
+        h = np.zeros(16, np.int32)
+        lib().sim_bot_header(self.h, s, h)
+        return h
+
+    def dump(self, s, which):
+        buf = np.zeros((self.cap, 82), np.float32)
+        feats = np.zeros((self.cap, max(self.dim, 1)), np.float32)
+        k = lib().sim_bot_dump(self.h, s, which, buf, feats.ctypes.data_as(C.c_void_p) if self.dim else None, self.cap)
+        return buf[:k], feats[:k]
