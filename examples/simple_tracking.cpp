@@ -7,12 +7,22 @@
 int main() {
     try {
         motcpp_b200::ByteTrack tracker(0.3f, 30, 50, 3, 0.3f, false, 80, "iou", false, 0.1f, 0.45f, 0.8f, 30, 30);
+        // the other front-ends, with the argument lists tools/motcpp_eval.cpp passes them
+        motcpp_b200::Sort sort(0.3f, 1, 50, 3, 0.3f);
+        motcpp_b200::OCSort ocsort(0.2f, 30, 50, 3, 0.3f, false, 80, "iou", false, 0.1f, 3, 0.2f, false, 0.01f, 0.0001f);
+        motcpp_b200::BotSort botsort("", false, false, 0.3f, 30, 50, 3, 0.3f, false, 80, "iou", false, 0.6f, 0.1f, 0.7f, 30,
+                                     0.8f, 0.5f, 0.25f, "none", 30, false, true, /*emb_dim=*/4);
         cv::Mat img(480, 640);
         Eigen::MatrixXf dets(2, 6);
         const float rows[2][6] = {{100, 100, 200, 200, 0.9f, 0}, {300, 300, 400, 420, 0.8f, 0}};
         for (int frame = 0; frame < 3; ++frame) {
             for (int i = 0; i < 2; ++i)
                 for (int c = 0; c < 6; ++c) dets(i, c) = rows[i][c] + (c < 4 ? 2.0f * frame : 0.0f);
+            Eigen::MatrixXf embs(2, 4);
+            for (int i = 0; i < 2; ++i)
+                for (int c = 0; c < 4; ++c) embs(i, c) = (c == i) ? 1.0f : 0.1f;
+            std::printf("frame %d rows: sort %ld ocsort %ld botsort %ld\n", frame, (long)sort.update(dets, img).rows(),
+                        (long)ocsort.update(dets, img).rows(), (long)botsort.update(dets, img, embs).rows());
             const Eigen::MatrixXf tracks = tracker.update(dets, img);
             for (long i = 0; i < tracks.rows(); ++i)
                 std::printf("frame %d id %d box %.1f %.1f %.1f %.1f conf %.2f\n", frame, (int)tracks(i, 4), tracks(i, 0),

@@ -1,7 +1,8 @@
 // trackers.hpp - C++17 binding of the C ABI (include/motb200.h) with motcpp's own class surface:
-//   motcpp_b200::ByteTrack(det_thresh, max_age, ..., frame_rate).update(dets, img[, embs]) / reset()
-// Constructor arguments, defaults, return layout and exceptions follow
-// include/motcpp/trackers/bytetrack.hpp:97-110, include/motcpp/tracker.hpp:47-74 and
+//   motcpp_b200::{Sort, ByteTrack, OCSort, BotSort}(<the reference's positional ctor arguments>)
+//       .update(dets, img[, embs]) / .reset()
+// Constructor arguments, defaults, return layout and exceptions follow include/motcpp/trackers/sort.hpp:69-77,
+// bytetrack.hpp:97-110, ocsort.hpp:88-102, botsort.hpp:108-134, include/motcpp/tracker.hpp:47-74 and
 // src/tracker.cpp:108-125.  Header-only; link with -lmotb200.
 #pragma once
 #include <stdexcept>
@@ -30,13 +31,20 @@ public:
     // dets (N,6) [x1,y1,x2,y2,conf,cls] -> (M,8) [x1,y1,x2,y2,id,conf,cls,det_ind]
     virtual Eigen::MatrixXf update(const Eigen::MatrixXf& dets, const cv::Mat& img,
                                    const Eigen::MatrixXf& embs = Eigen::MatrixXf()) {
-        check_inputs(dets, img, embs);
+        if (validate_) check_inputs(dets, img, embs);
         const int n = static_cast<int>(dets.rows());
         if (n > max_dets_) throw std::invalid_argument("more detections than max_dets");
         for (int i = 0; i < n; ++i)                       // Eigen is column-major, the ABI row-major
             for (int c = 0; c < 6; ++c) dets_rm_[static_cast<size_t>(i) * 6 + c] = dets(i, c);
+        const float* embs_ptr = nullptr;
+        if (emb_dim_ > 0 && embs.rows() == dets.rows() && embs.cols() == emb_dim_ && n > 0) {
+            for (int i = 0; i < n; ++i)
+                for (int c = 0; c < emb_dim_; ++c) embs_rm_[static_cast<size_t>(i) * emb_dim_ + c] = embs(i, c);
+            embs_ptr = embs_rm_.data();
+        }
         int n_out = 0;
-        throw_on(mot_engine_update_host(engine_, 1, dets_rm_.data(), &n, max_dets_, out_rm_.data(), &n_out, cap_));
+        throw_on(mot_engine_update_host_embs(engine_, 1, dets_rm_.data(), &n, max_dets_, embs_ptr, out_rm_.data(), &n_out,
+                                             cap_));
         throw_on(mot_engine_check(engine_, nullptr));
         Eigen::MatrixXf out(n_out, 8);
         for (int i = 0; i < n_out; ++i)
@@ -63,12 +71,19 @@ protected:
         mot_engine_info(engine_, &threads, &smem, &ctas, &bytes);
         max_dets_ = cfg.max_dets > 0 ? cfg.max_dets : 512;
         cap_ = cfg.track_capacity > 0 ? cfg.track_capacity : 1536;
+        emb_dim_ = cfg.kind == MOT_TRACKER_BOTSORT ? cfg.emb_dim : 0;
         dets_rm_.resize(static_cast<size_t>(max_dets_) * 6);
         out_rm_.resize(static_cast<size_t>(cap_) * 8);
+        embs_rm_.resize(static_cast<size_t>(max_dets_) * static_cast<size_t>(emb_dim_));
+    }
+    static void only_iou_aabb(const std::string& asso_func, bool per_class, bool is_obb) {
+        if (asso_func != "iou") throw std::invalid_argument("Invalid association mode: " + asso_func);   // iou.hpp:407
+        if (per_class || is_obb) throw std::invalid_argument("per_class / OBB are outside the accelerated hot path");
     }
     mot_engine* engine_ = nullptr;
-    int max_dets_ = 512, cap_ = 1536;
-    std::vector<float> dets_rm_, out_rm_;
+    int max_dets_ = 512, cap_ = 1536, emb_dim_ = 0;
+    bool validate_ = true;
+    std::vector<float> dets_rm_, out_rm_, embs_rm_;
 };
 
 class ByteTrack : public BaseTracker {
@@ -87,14 +102,118 @@ private:
                                   bool per_class, int /*nr_classes*/, const std::string& asso_func, bool is_obb,
                                   float min_conf, float track_thresh, float match_thresh, int track_buffer,
                                   int frame_rate, int track_capacity, int max_dets, int device) {
-        if (asso_func != "iou") throw std::invalid_argument("Invalid association mode: " + asso_func);   // iou.hpp:407
-        if (per_class || is_obb) throw std::invalid_argument("per_class / OBB are outside the accelerated hot path");
+        only_iou_aabb(asso_func, per_class, is_obb);
         mot_engine_config c;
         throw_on(mot_engine_default_config(MOT_TRACKER_BYTETRACK, &c));
         c.n_streams = 1; c.track_capacity = track_capacity; c.max_dets = max_dets; c.device = device;
         c.det_thresh = det_thresh; c.max_age = max_age; c.max_obs = max_obs; c.min_hits = min_hits;
         c.iou_threshold = iou_threshold; c.min_conf = min_conf; c.track_thresh = track_thresh;
         c.match_thresh = match_thresh; c.track_buffer = track_buffer; c.frame_rate = frame_rate;
+        return c;
+    }
+};
+
+// motcpp::trackers::Sort (include/motcpp/trackers/sort.hpp:69-77).  Like the reference it never validates its
+// input (Sort::update does not call check_inputs, src/trackers/sort.cpp:102-108).
+class Sort : public BaseTracker {
+public:
+    Sort(float det_thresh = 0.3f, int max_age = 1, int max_obs = 50, int min_hits = 3, float iou_threshold = 0.3f,
+         bool per_class = false, int nr_classes = 80, const std::string& asso_func = "iou", bool is_obb = false,
+         int track_capacity = 256, int max_dets = 64, int device = 0)
+        : BaseTracker(make(det_thresh, max_age, max_obs, min_hits, iou_threshold, per_class, nr_classes, asso_func, is_obb,
+                           track_capacity, max_dets, device)) { validate_ = false; }
+
+private:
+    static mot_engine_config make(float det_thresh, int max_age, int max_obs, int min_hits, float iou_threshold,
+                                  bool per_class, int /*nr_classes*/, const std::string& asso_func, bool is_obb,
+                                  int track_capacity, int max_dets, int device) {
+        only_iou_aabb(asso_func, per_class, is_obb);
+        mot_engine_config c;
+        throw_on(mot_engine_default_config(MOT_TRACKER_SORT, &c));
+        c.n_streams = 1; c.track_capacity = track_capacity; c.max_dets = max_dets; c.device = device;
+        c.det_thresh = det_thresh; c.max_age = max_age; c.max_obs = max_obs; c.min_hits = min_hits;
+        c.iou_threshold = iou_threshold;
+        return c;
+    }
+};
+
+// motcpp::trackers::OCSort (include/motcpp/trackers/ocsort.hpp:88-102)
+class OCSort : public BaseTracker {
+public:
+    OCSort(float det_thresh = 0.2f, int max_age = 30, int max_obs = 50, int min_hits = 3, float iou_threshold = 0.3f,
+           bool per_class = false, int nr_classes = 80, const std::string& asso_func = "iou", bool is_obb = false,
+           float min_conf = 0.1f, int delta_t = 3, float inertia = 0.2f, bool use_byte = false,
+           float Q_xy_scaling = 0.01f, float Q_s_scaling = 0.0001f, int track_capacity = 0, int max_dets = 0,
+           int device = 0)
+        : BaseTracker(make(det_thresh, max_age, max_obs, min_hits, iou_threshold, per_class, nr_classes, asso_func, is_obb,
+                           min_conf, delta_t, inertia, use_byte, Q_xy_scaling, Q_s_scaling, track_capacity, max_dets,
+                           device)) {}
+
+private:
+    static mot_engine_config make(float det_thresh, int max_age, int max_obs, int min_hits, float iou_threshold,
+                                  bool per_class, int /*nr_classes*/, const std::string& asso_func, bool is_obb,
+                                  float min_conf, int delta_t, float inertia, bool use_byte, float q_xy, float q_s,
+                                  int track_capacity, int max_dets, int device) {
+        only_iou_aabb(asso_func, per_class, is_obb);
+        mot_engine_config c;
+        throw_on(mot_engine_default_config(MOT_TRACKER_OCSORT, &c));
+        c.n_streams = 1; c.track_capacity = track_capacity; c.max_dets = max_dets; c.device = device;
+        c.det_thresh = det_thresh; c.max_age = max_age; c.max_obs = max_obs; c.min_hits = min_hits;
+        c.iou_threshold = iou_threshold; c.min_conf = min_conf; c.delta_t = delta_t; c.inertia = inertia;
+        c.use_byte = use_byte ? 1 : 0; c.q_xy_scaling = q_xy; c.q_s_scaling = q_s;
+        return c;
+    }
+};
+
+// motcpp::trackers::BotSort (include/motcpp/trackers/botsort.hpp:108-134).  Camera-motion compensation and ReID
+// inference are image processing outside the association hot path: cmc_method must be "none", reid_weights empty,
+// and the embeddings are passed to update() - the reference's own `embs` argument (botsort.cpp:276-283).
+class BotSort : public BaseTracker {
+public:
+    BotSort(const std::string& reid_weights = "", bool use_half = false, bool use_gpu = false, float det_thresh = 0.3f,
+            int max_age = 30, int max_obs = 50, int min_hits = 3, float iou_threshold = 0.3f, bool per_class = false,
+            int nr_classes = 80, const std::string& asso_func = "iou", bool is_obb = false,
+            float track_high_thresh = 0.5f, float track_low_thresh = 0.1f, float new_track_thresh = 0.6f,
+            int track_buffer = 30, float match_thresh = 0.8f, float proximity_thresh = 0.5f,
+            float appearance_thresh = 0.25f, const std::string& cmc_method = "none", int frame_rate = 30,
+            bool fuse_first_associate = false, bool with_reid = true, int emb_dim = 0, int track_capacity = 0,
+            int max_dets = 0, int device = 0)
+        : BaseTracker(make(reid_weights, use_half, use_gpu, det_thresh, max_age, max_obs, min_hits, iou_threshold, per_class,
+                           asso_func, is_obb, track_high_thresh, track_low_thresh, new_track_thresh, track_buffer,
+                           match_thresh, proximity_thresh, appearance_thresh, cmc_method, frame_rate, fuse_first_associate,
+                           with_reid, emb_dim, track_capacity, max_dets, device)) {}
+
+    // BotSort::update validates (dets, img) only and returns at once on an empty frame (botsort.cpp:265-269)
+    Eigen::MatrixXf update(const Eigen::MatrixXf& dets, const cv::Mat& img,
+                           const Eigen::MatrixXf& embs = Eigen::MatrixXf()) override {
+        check_inputs(dets, img, Eigen::MatrixXf());
+        if (dets.rows() == 0) return Eigen::MatrixXf(0, 8);
+        if (embs.rows() > 0 && (embs.rows() != dets.rows() || embs.cols() != emb_dim_))
+            throw std::invalid_argument("Detections and embeddings must have same number of rows");
+        validate_ = false;
+        return BaseTracker::update(dets, img, embs);
+    }
+
+private:
+    static mot_engine_config make(const std::string& reid_weights, bool, bool, float det_thresh, int max_age, int max_obs,
+                                  int min_hits, float iou_threshold, bool per_class, const std::string& asso_func,
+                                  bool is_obb, float high, float low, float new_thresh, int track_buffer,
+                                  float match_thresh, float prox, float app, const std::string& cmc_method,
+                                  int frame_rate, bool fuse_first, bool with_reid, int emb_dim, int track_capacity,
+                                  int max_dets, int device) {
+        only_iou_aabb(asso_func, per_class, is_obb);
+        if (!(cmc_method.empty() || cmc_method == "none"))
+            throw std::invalid_argument("camera-motion compensation is outside the accelerated hot path (cmc_method must be \"none\")");
+        if (!reid_weights.empty())
+            throw std::invalid_argument("ReID inference is outside the accelerated hot path: pass embeddings to update()");
+        mot_engine_config c;
+        throw_on(mot_engine_default_config(MOT_TRACKER_BOTSORT, &c));
+        c.n_streams = 1; c.track_capacity = track_capacity; c.max_dets = max_dets; c.device = device;
+        c.det_thresh = det_thresh; c.max_age = max_age; c.max_obs = max_obs; c.min_hits = min_hits;
+        c.iou_threshold = iou_threshold; c.track_high_thresh = high; c.track_low_thresh = low;
+        c.new_track_thresh = new_thresh; c.track_buffer = track_buffer; c.match_thresh = match_thresh;
+        c.proximity_thresh = prox; c.appearance_thresh = app; c.frame_rate = frame_rate;
+        c.fuse_first_associate = fuse_first ? 1 : 0; c.with_reid = with_reid ? 1 : 0; c.emb_dim = emb_dim;
         return c;
     }
 };

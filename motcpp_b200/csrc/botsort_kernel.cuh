@@ -31,11 +31,13 @@
 namespace mot {
 
 #ifndef MOT_BOT_THREADS
-#define MOT_BOT_THREADS 512
+#define MOT_BOT_THREADS 1024
 #endif
+// 1024 threads x 1 CTA per SM (64 registers): the feature passes are DRAM-latency bound and want every resident warp;
+// measured on the 1024 x 1024 x 512 case: 512 threads 679 us / frame, 1024 threads 577 us / frame.
 constexpr int kBotThreads = MOT_BOT_THREADS;
 constexpr unsigned char kFlagHasFeat = 0x20;
-constexpr int kBotCacheSlots = 2048;         // (pair -> embedding term) cache entries in shared memory
+constexpr int kBotTableSlots = 4096;         // (pair -> embedding term) hash table entries in shared memory
 
 enum : int { kBHdrNew = 12, kBHdrLostAfter = 13 };
 
@@ -126,7 +128,7 @@ struct BotSmem {
     unsigned short* list_a;     // [cap]
     unsigned short* list_b;     // [cap]
     unsigned short* list_c;     // [cap]
-    unsigned long long* cache;  // [kBotCacheSlots] packed (row << 16 | col) : float bits
+    unsigned long long* cache;  // [kBotTableSlots] open-addressing table: tag (row << 16 | det, top bit set) : float bits
     BlockScratch* bs;
     LapWorkspace lap;
 };
@@ -138,7 +140,7 @@ MOT_HD constexpr size_t bot_smem_bytes(int cap, int d_max, int e_cap) {
     b += 4 * lap_align16(sizeof(unsigned short) * (size_t)d_max);
     b += lap_align16(sizeof(float4) * (size_t)cap);
     b += 6 * lap_align16(sizeof(unsigned short) * (size_t)cap);
-    b += lap_align16(sizeof(unsigned long long) * kBotCacheSlots);
+    b += lap_align16(sizeof(unsigned long long) * kBotTableSlots);
     b += lap_align16(sizeof(BlockScratch));
     b += lap_smem_bytes(cap, d_max, e_cap);
     return b;
@@ -158,27 +160,60 @@ __device__ __forceinline__ void bot_carve(unsigned char* p, int cap, int d_max, 
     s.list_a = (unsigned short*)p;     p += lap_align16(sizeof(unsigned short) * (size_t)cap);
     s.list_b = (unsigned short*)p;     p += lap_align16(sizeof(unsigned short) * (size_t)cap);
     s.list_c = (unsigned short*)p;     p += lap_align16(sizeof(unsigned short) * (size_t)cap);
-    s.cache = (unsigned long long*)p;  p += lap_align16(sizeof(unsigned long long) * kBotCacheSlots);
+    s.cache = (unsigned long long*)p;  p += lap_align16(sizeof(unsigned long long) * kBotTableSlots);
     s.bs = (BlockScratch*)p;           p += lap_align16(sizeof(BlockScratch));
     lap_carve(p, cap, d_max, e_cap, s.lap);
 }
 
-// sequential fp32 dot product / norm (oracle/botsort.cpp seq_dot): acc = x0 y0; acc += xk yk, ascending k
-__device__ __forceinline__ float seq_dot(const float* __restrict__ x, const float* __restrict__ y, int n) {
-    if (n <= 0) return 0.0f;
-    const float4* xv = reinterpret_cast<const float4*>(x);
-    const float4* yv = reinterpret_cast<const float4*>(y);
-    float4 a = xv[0], b = yv[0];
-    float acc = xmul(a.x, b.x);
-    acc = xadd(acc, xmul(a.y, b.y)); acc = xadd(acc, xmul(a.z, b.z)); acc = xadd(acc, xmul(a.w, b.w));
-    for (int k = 1; k < (n >> 2); ++k) {
-        a = xv[k]; b = yv[k];
-        acc = xadd(acc, xmul(a.x, b.x)); acc = xadd(acc, xmul(a.y, b.y));
-        acc = xadd(acc, xmul(a.z, b.z)); acc = xadd(acc, xmul(a.w, b.w));
-    }
+// ---- feature arithmetic.  Summation order ("lanes32", shared with oracle/botsort.cpp lanes_dot): the products of
+// float4 number q go, in order x y z w, into partial sum q % 32 (each partial starts at +0 and takes its float4s in
+// ascending q); the 32 partials are then combined by the butterfly p[l] += p[l ^ o], o = 16, 8, 4, 2, 1.  A warp
+// evaluates it with coalesced float4 loads and five shuffles; one thread can evaluate the same order on its own.
+__device__ __forceinline__ float lanes32_reduce(float p) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) p = xadd(p, __shfl_xor_sync(kFullMask, p, o));
+    return p;
+}
+__device__ __forceinline__ float dot4(float acc, float4 a, float4 b) {
+    acc = xadd(acc, xmul(a.x, b.x)); acc = xadd(acc, xmul(a.y, b.y));
+    acc = xadd(acc, xmul(a.z, b.z)); acc = xadd(acc, xmul(a.w, b.w));
     return acc;
 }
-__device__ __forceinline__ float seq_norm(const float* __restrict__ x, int n) { return xsqrt(seq_dot(x, x, n)); }
+// all 32 lanes: prefetch the `dim` floats at v (the next work item of this warp) into L2
+__device__ __forceinline__ void warp_prefetch_vec(const float* v, int dim) {
+    for (int b = lane_id() * 128; b < dim * 4; b += 32 * 128) prefetch_l2(reinterpret_cast<const char*>(v) + b);
+}
+// all 32 lanes of a warp; dim % 4 == 0, both pointers 16-byte aligned
+__device__ __forceinline__ float warp_dot(const float* __restrict__ x, const float* __restrict__ y, int dim) {
+    const float4* xv = reinterpret_cast<const float4*>(x);
+    const float4* yv = reinterpret_cast<const float4*>(y);
+    const int nq = dim >> 2;
+    float acc = 0.0f;
+#pragma unroll 4
+    for (int q = lane_id(); q < nq; q += 32) acc = dot4(acc, xv[q], yv[q]);
+    return lanes32_reduce(acc);
+}
+// the same value computed by ONE thread (assignment-solver fallback when a pair is not in the table)
+__device__ __noinline__ float thread_dot_lanes32(const float* __restrict__ x, const float* __restrict__ y, int dim) {
+    const float4* xv = reinterpret_cast<const float4*>(x);
+    const float4* yv = reinterpret_cast<const float4*>(y);
+    const int nq = dim >> 2;
+    float part[32];
+#pragma unroll
+    for (int l = 0; l < 32; ++l) part[l] = 0.0f;
+    for (int q0 = 0; q0 < nq; q0 += 32) {
+#pragma unroll
+        for (int l = 0; l < 32; ++l)
+            if (q0 + l < nq) part[l] = dot4(part[l], xv[q0 + l], yv[q0 + l]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int l = 0; l < 32; ++l)
+            if (l < o) part[l] = xadd(part[l], part[l + o]);
+    }
+    return part[0];
+}
 
 // track box from its CURRENT mean (BotSTrack::xyxy, botsort.cpp:171-181)
 __device__ __forceinline__ float4 bot_track_box(const float* rec) {
@@ -198,6 +233,7 @@ struct BotCost {
     const float* tnorm;               // [cap]
     const float* dfeat;               // [d_max][dim] normalised detection features
     const float* dnorm;               // [d_max]
+    const unsigned char* sflag;       // [cap]
     unsigned long long* cache;
     int dim;
     float prox, app;
@@ -213,23 +249,38 @@ struct BotCost {
     __device__ __forceinline__ float4 col_box(int j) const { return det_box[col_map[j]]; }
     __device__ __forceinline__ bool reject(const Row& r, int j) const { return prune && boxes_disjoint(r.b, det_box[col_map[j]]); }
     // embedding_distance(...)/2 with the appearance threshold applied (matching.cpp:83-90, botsort.cpp:450-457)
-    __device__ __forceinline__ float emb_term(int i, int d) const {
-        const unsigned key = ((unsigned)i << 16) | (unsigned)d;
-        const unsigned h = (key * 2654435761u) >> 21;                       // 11 bits: kBotCacheSlots
-        const unsigned long long hit = cache[h];
-        if ((unsigned)(hit >> 32) == (key ^ 0x80000000u)) return __uint_as_float((unsigned)hit);
-        float sim;
-        if (dim > 0) {
-            const int slot = row_slot[i];
-            const float dot = seq_dot(feats + (size_t)slot * dim, dfeat + (size_t)d * dim, dim);
-            sim = xdiv(dot, xadd(xmul(tnorm[slot], dnorm[d]), 1e-10f));
-        } else {
-            sim = xdiv(0.0f, 1e-10f);                                        // empty feature vectors
-        }
+    __device__ __forceinline__ float emb_from_dot(float dot, float tn, float dn) const {
+        const float sim = xdiv(dot, xadd(xmul(tn, dn), 1e-10f));
         float e = xdiv(fmaxf(0.0f, xsub(1.0f, sim)), 2.0f);
         if (e > app) e = 1.0f;
-        cache[h] = ((unsigned long long)(key ^ 0x80000000u) << 32) | (unsigned long long)__float_as_uint(e);
         return e;
+    }
+    __device__ __forceinline__ static unsigned table_tag(int i, int d) { return 0x80000000u | ((unsigned)i << 16) | (unsigned)d; }
+    __device__ __forceinline__ static unsigned table_home(unsigned tag) { return (tag * 2654435761u) >> 20; }      // 12 bits
+    __device__ __forceinline__ void table_insert(int i, int d, float e) const {
+        const unsigned tag = table_tag(i, d);
+        const unsigned long long entry = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(e);
+        unsigned h = table_home(tag);
+        for (int probe = 0; probe < 64; ++probe) {
+            const unsigned long long old = atomicCAS(&cache[h], 0ull, entry);
+            if (old == 0ull || (unsigned)(old >> 32) == tag) return;
+            h = (h + 1) & (kBotTableSlots - 1);
+        }
+    }
+    __device__ __forceinline__ float emb_term(int i, int d) const {
+        const unsigned tag = table_tag(i, d);
+        unsigned h = table_home(tag);
+        for (int probe = 0; probe < 64; ++probe) {
+            const unsigned long long hit = cache[h];
+            if ((unsigned)(hit >> 32) == tag) return __uint_as_float((unsigned)hit);
+            if (hit == 0ull) break;
+            h = (h + 1) & (kBotTableSlots - 1);
+        }
+        // not tabulated (pre-pass buffer overflow, or proximity_thresh >= 1): one thread evaluates the same sums
+        const int slot = row_slot[i];
+        const bool hf = dim > 0 && (sflag[slot] & kFlagHasFeat) != 0;
+        const float dot = hf ? thread_dot_lanes32(feats + (size_t)slot * dim, dfeat + (size_t)d * dim, dim) : 0.0f;
+        return emb_from_dot(dot, hf ? tnorm[slot] : 0.0f, dim > 0 ? dnorm[d] : 0.0f);
     }
     __device__ __forceinline__ float cost(const Row& r, int j) const {
         const int d = col_map[j];
@@ -290,30 +341,118 @@ __device__ __forceinline__ void bot_update_pairs(const BotArgs& a, const BotStre
     const int dim = a.p.dim;
     if (!with_feat || dim <= 0 || embs == nullptr || n_pairs == 0) return;
     __syncthreads();
-    // smooth = alpha * smooth + (1 - alpha) * feat (raw detection feature), element-wise over all pairs
+    // update_features (:158-169), one warp per track: smooth = alpha * smooth + (1 - alpha) * feat (the RAW detection
+    // feature), its norm, the division, and the norm of the result (what embedding_distance recomputes next frame)
     const float alpha = 0.9f, beta = xsub(1.0f, alpha);
-    const int total = n_pairs * dim;
-    for (int e = tid; e < total; e += nt) {
-        const int k = e / dim, c = e - k * dim;
+    const int nq = dim >> 2, warp = tid >> 5, nwarps = nt >> 5;
+    for (int k = warp; k < n_pairs; k += nwarps) {
         const int slot = slot_of(k), det = det_of(k);
-        float* f = st.feats + (size_t)slot * dim + c;
-        const float raw = embs[(size_t)det * dim + c];
-        *f = (st.sflag[slot] & kFlagHasFeat) ? xadd(xmul(alpha, *f), xmul(beta, raw)) : raw;
+        if (k + nwarps < n_pairs) {
+            warp_prefetch_vec(st.feats + (size_t)slot_of(k + nwarps) * dim, dim);
+            warp_prefetch_vec(embs + (size_t)det_of(k + nwarps) * dim, dim);
+        }
+        float4* fv = reinterpret_cast<float4*>(st.feats + (size_t)slot * dim);
+        const float4* rv = reinterpret_cast<const float4*>(embs + (size_t)det * dim);
+        const bool has = (st.sflag[slot] & kFlagHasFeat) != 0;
+        float acc = 0.0f, acc2 = 0.0f;
+        if (nq <= 128) {
+            // up to 512 floats: the whole vector stays in registers (4 float4 per lane), one read and one write
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int q = lane + 32 * j;
+                v[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (q < nq) {
+                    v[j] = rv[q];
+                    if (has) {
+                        const float4 o = fv[q];
+                        v[j] = make_float4(xadd(xmul(alpha, o.x), xmul(beta, v[j].x)), xadd(xmul(alpha, o.y), xmul(beta, v[j].y)),
+                                           xadd(xmul(alpha, o.z), xmul(beta, v[j].z)), xadd(xmul(alpha, o.w), xmul(beta, v[j].w)));
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (lane + 32 * j < nq) acc = dot4(acc, v[j], v[j]);
+            const float nrm = xsqrt(lanes32_reduce(acc));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int q = lane + 32 * j;
+                if (q < nq) {
+                    if (nrm > 0.0f) v[j] = make_float4(xdiv(v[j].x, nrm), xdiv(v[j].y, nrm), xdiv(v[j].z, nrm), xdiv(v[j].w, nrm));
+                    fv[q] = v[j];
+                    acc2 = dot4(acc2, v[j], v[j]);
+                }
+            }
+        } else {
+#pragma unroll 4
+            for (int q = lane; q < nq; q += 32) {
+                float4 v = rv[q];
+                if (has) {
+                    const float4 o = fv[q];
+                    v = make_float4(xadd(xmul(alpha, o.x), xmul(beta, v.x)), xadd(xmul(alpha, o.y), xmul(beta, v.y)),
+                                    xadd(xmul(alpha, o.z), xmul(beta, v.z)), xadd(xmul(alpha, o.w), xmul(beta, v.w)));
+                }
+                fv[q] = v;
+                acc = dot4(acc, v, v);
+            }
+            const float nrm = xsqrt(lanes32_reduce(acc));
+#pragma unroll 4
+            for (int q = lane; q < nq; q += 32) {           // every lane re-reads exactly the float4s it wrote
+                float4 v = fv[q];
+                if (nrm > 0.0f) { v = make_float4(xdiv(v.x, nrm), xdiv(v.y, nrm), xdiv(v.z, nrm), xdiv(v.w, nrm)); fv[q] = v; }
+                acc2 = dot4(acc2, v, v);
+            }
+        }
+        const float tn = xsqrt(lanes32_reduce(acc2));
+        if (lane == 0) { st.tnorm[slot] = tn; st.sflag[slot] |= kFlagHasFeat; }
     }
     __syncthreads();
-    for (int k = tid; k < n_pairs; k += nt) {
-        const int slot = slot_of(k);
-        st.tnorm[slot] = seq_norm(st.feats + (size_t)slot * dim, dim);
-        st.sflag[slot] |= kFlagHasFeat;
+}
+
+// Tabulates the embedding term of every (row, column) pair whose IoU distance passes the proximity gate, one warp per
+// pair (coalesced feature reads), before the assignment consults them through BotCost::emb_term.
+template <class Cost>
+__device__ __forceinline__ void bot_emb_prepass(const BotStream& st, BotSmem& sm, const Cost& cost, int n, int m) {
+    const int tid = (int)threadIdx.x, nt = (int)blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    for (int h = tid; h < kBotTableSlots; h += nt) sm.cache[h] = 0ull;
+    if (n == 0 || m == 0 || !cost.reid || cost.dim <= 0 || !cost.prune || m > sm.lap.grid.cap) { __syncthreads(); return; }
+    grid_build(sm.lap.grid, m, sm.bs, [&](int j) { return cost.col_box(j); });
+    int inserted = 0;
+    for (int base = 0; base < n; base += nt) {
+        const int i = base + tid;
+        if (tid == 0) sm.lap.ctl[7] = 0;
+        __syncthreads();
+        if (i < n) {
+            const typename Cost::Row rw = cost.row(i);
+            grid_query(sm.lap.grid, rw.b, [&](int j) { return cost.col_box(j); }, [&](int j, float4 b) {
+                const float dist = xsub(1.0f, iou_pair(rw.b, rw.area, b));
+                if (!(dist > cost.prox)) {
+                    const int q = atomicAdd(&sm.lap.ctl[7], 1);
+                    if (q < sm.lap.p_cap) sm.lap.pairs[q] = (i << 16) | j;
+                }
+            });
+        }
+        __syncthreads();
+        const int n_pairs = min(sm.lap.ctl[7], sm.lap.p_cap);
+        if (inserted + n_pairs <= (kBotTableSlots * 3) / 4) {
+            for (int q = warp; q < n_pairs; q += nwarps) {
+                const int pk = sm.lap.pairs[q];
+                const int pi = pk >> 16, d = cost.col_map[pk & 0xffff];
+                const int slot = cost.row_slot[pi];
+                if (q + nwarps < n_pairs) {
+                    const int nk = sm.lap.pairs[q + nwarps];
+                    warp_prefetch_vec(st.feats + (size_t)cost.row_slot[nk >> 16] * cost.dim, cost.dim);
+                    warp_prefetch_vec(st.dfeat + (size_t)cost.col_map[nk & 0xffff] * cost.dim, cost.dim);
+                }
+                const bool hf = (st.sflag[slot] & kFlagHasFeat) != 0;
+                const float dot = hf ? warp_dot(st.feats + (size_t)slot * cost.dim, st.dfeat + (size_t)d * cost.dim, cost.dim) : 0.0f;
+                if (lane == 0) cost.table_insert(pi, d, cost.emb_from_dot(dot, hf ? st.tnorm[slot] : 0.0f, cost.dnorm[d]));
+            }
+            inserted += n_pairs;
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    for (int e = tid; e < total; e += nt) {
-        const int k = e / dim, c = e - k * dim;
-        const int slot = slot_of(k);
-        const float nrm = st.tnorm[slot];
-        if (nrm > 0.0f) { float* f = st.feats + (size_t)slot * dim + c; *f = xdiv(*f, nrm); }
-    }
-    __syncthreads();
 }
 
 template <int CAP, int DMAX>
@@ -342,7 +481,6 @@ __device__ __forceinline__ void bot_frame(const BotArgs& a, const BotStream& st,
         sm.det_box[j] = xywh2xyxy(xyxy2xywh(make_float4(r[0], r[1], r[2], r[3])));
         sm.det_conf[j] = r[4];
     }
-    for (int h = tid; h < kBotCacheSlots; h += nt) sm.cache[h] = 0ull;
     __syncthreads();
     const float t_hi = a.p.track_high_thresh, t_lo = a.p.track_low_thresh;
     const int n_first = block_compact(n_det, 0, sm.bs, [&](int j) { return sm.det_conf[j] > t_hi; },
@@ -352,18 +490,50 @@ __device__ __forceinline__ void bot_frame(const BotArgs& a, const BotStream& st,
                                        [&](int j, int pos) { sm.second[pos] = (unsigned short)j; });
     const bool have_feat = reid && dim > 0 && embs != nullptr;
     if (have_feat) {
-        // BotSTrack(det, feat): smooth_feat = feat / |feat| (:39-46); its norm is what embedding_distance recomputes
-        for (int k = tid; k < n_first; k += nt) { const int d = sm.first[k]; st.dnorm[d] = seq_norm(embs + (size_t)d * dim, dim); }
-        __syncthreads();
-        const int total = n_first * dim;
-        for (int e = tid; e < total; e += nt) {
-            const int k = e / dim, c = e - k * dim;
+        // BotSTrack(det, feat): smooth_feat = feat / |feat| (:39-46), and the norm of THAT vector, which
+        // embedding_distance recomputes for every pair (matching.cpp:86-87); one warp per detection
+        const int nq = dim >> 2, warp = tid >> 5, nwarps = nt >> 5;
+        for (int k = warp; k < n_first; k += nwarps) {
             const int d = sm.first[k];
-            const float raw = embs[(size_t)d * dim + c], nrm = st.dnorm[d];
-            st.dfeat[(size_t)d * dim + c] = (nrm > 0.0f) ? xdiv(raw, nrm) : raw;
+            const float* raw = embs + (size_t)d * dim;
+            if (k + nwarps < n_first) warp_prefetch_vec(embs + (size_t)sm.first[k + nwarps] * dim, dim);
+            const float4* rv = reinterpret_cast<const float4*>(raw);
+            float4* ov = reinterpret_cast<float4*>(st.dfeat + (size_t)d * dim);
+            float acc = 0.0f;
+            if (nq <= 128) {
+                float4 v[4];
+                float a0 = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int q = lane + 32 * j;
+                    v[j] = (q < nq) ? rv[q] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (lane + 32 * j < nq) a0 = dot4(a0, v[j], v[j]);
+                const float nrm = xsqrt(lanes32_reduce(a0));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int q = lane + 32 * j;
+                    if (q < nq) {
+                        if (nrm > 0.0f) v[j] = make_float4(xdiv(v[j].x, nrm), xdiv(v[j].y, nrm), xdiv(v[j].z, nrm), xdiv(v[j].w, nrm));
+                        ov[q] = v[j];
+                        acc = dot4(acc, v[j], v[j]);
+                    }
+                }
+            } else {
+                const float nrm = xsqrt(warp_dot(raw, raw, dim));
+#pragma unroll 4
+                for (int q = lane; q < nq; q += 32) {
+                    float4 v = rv[q];
+                    if (nrm > 0.0f) v = make_float4(xdiv(v.x, nrm), xdiv(v.y, nrm), xdiv(v.z, nrm), xdiv(v.w, nrm));
+                    ov[q] = v;
+                    acc = dot4(acc, v, v);
+                }
+            }
+            const float n2 = xsqrt(lanes32_reduce(acc));
+            if (lane == 0) st.dnorm[DMAX + d] = n2;
         }
-        __syncthreads();
-        for (int k = tid; k < n_first; k += nt) { const int d = sm.first[k]; st.dnorm[DMAX + d] = seq_norm(st.dfeat + (size_t)d * dim, dim); }
     }
 
     // ---- B. pool = tracked (activated) ++ lost ; unconfirmed kept aside (:293-309)
@@ -396,21 +566,16 @@ __device__ __forceinline__ void bot_frame(const BotArgs& a, const BotStream& st,
     for (int r = tid; r < n1; r += nt) {
         const int slot = sm.pool[r];
         sm.row_box[r] = bot_track_box(st.recs + (size_t)slot * kRecFloats);
-        if (have_feat) st.tnorm[slot] = (st.sflag[slot] & kFlagHasFeat) ? seq_norm(st.feats + (size_t)slot * dim, dim) : 0.0f;
     }
-    if (have_feat)
-        for (int i = tid; i < n_unc; i += nt) {
-            const int slot = sm.unconf[i];
-            st.tnorm[slot] = (st.sflag[slot] & kFlagHasFeat) ? seq_norm(st.feats + (size_t)slot * dim, dim) : 0.0f;
-        }
-    __syncthreads();
+    __syncthreads();       // (a track's |smooth_feat| is kept in tnorm[] from the moment the feature was last written)
 
     // ---- D. first association (:402-495)
     const int fdim = have_feat ? dim : 0;
     {
         BotCost cost{sm.row_box, sm.pool, sm.det_box, sm.det_conf, sm.first, st.feats, st.tnorm, st.dfeat, st.dnorm + DMAX,
-                     sm.cache, fdim, a.p.proximity_thresh, a.p.appearance_thresh, a.p.fuse_first != 0, reid,
+                     st.sflag, sm.cache, fdim, a.p.proximity_thresh, a.p.appearance_thresh, a.p.fuse_first != 0, reid,
                      a.p.match_thresh < 1.0f && (!reid || a.p.proximity_thresh < 1.0f)};
+        bot_emb_prepass(st, sm, cost, n1, n_first);
         block_lap(sm.lap, n1, n_first, CAP, DMAX, a.p.match_thresh, cost);
     }
     const int n_m1 = block_compact(n1, 0, sm.bs, [&](int r) { return sm.lap.row2col[r] >= 0; },
@@ -464,10 +629,11 @@ __device__ __forceinline__ void bot_frame(const BotArgs& a, const BotStream& st,
     const unsigned short* final_list = sm.udet;
     if (n_unc > 0 && n_udet > 0) {
         for (int i = tid; i < n_unc; i += nt) sm.row_box[i] = bot_track_box(st.recs + (size_t)sm.unconf[i] * kRecFloats);
-        for (int h = tid; h < kBotCacheSlots; h += nt) sm.cache[h] = 0ull;
         __syncthreads();
         BotCost cost{sm.row_box, sm.unconf, sm.det_box, sm.det_conf, sm.udet, st.feats, st.tnorm, st.dfeat, st.dnorm + DMAX,
-                     sm.cache, fdim, a.p.proximity_thresh, a.p.appearance_thresh, true, reid, !reid || a.p.proximity_thresh < 1.0f};
+                     st.sflag, sm.cache, fdim, a.p.proximity_thresh, a.p.appearance_thresh, true, reid,
+                     !reid || a.p.proximity_thresh < 1.0f};
+        bot_emb_prepass(st, sm, cost, n_unc, n_udet);
         block_lap(sm.lap, n_unc, n_udet, CAP, DMAX, 0.7f, cost);
         const int n_m3 = block_compact(n_unc, 0, sm.bs, [&](int i) { return sm.lap.row2col[i] >= 0; },
                                        [&](int i, int pos) { sm.sel[pos] = (unsigned short)i; });
@@ -510,10 +676,13 @@ __device__ __forceinline__ void bot_frame(const BotArgs& a, const BotStream& st,
         }
     }
     if (have_feat) {
-        const int total = n_new * dim;
-        for (int e = tid; e < total; e += nt) {
-            const int k = e / dim, c = e - k * dim;
-            st.feats[(size_t)st.freel[n_free - 1 - k] * dim + c] = st.dfeat[(size_t)sm.sel[k] * dim + c];
+        const int nq = dim >> 2, warp = tid >> 5, nwarps = nt >> 5;
+        for (int k = warp; k < n_new; k += nwarps) {       // smooth_feat of a new track = the detection's normalised feature
+            const int det = sm.sel[k], slot = st.freel[n_free - 1 - k];
+            const float4* src = reinterpret_cast<const float4*>(st.dfeat + (size_t)det * dim);
+            float4* dst = reinterpret_cast<float4*>(st.feats + (size_t)slot * dim);
+            for (int q = lane; q < nq; q += 32) dst[q] = src[q];
+            if (lane == 0) st.tnorm[slot] = st.dnorm[DMAX + det];
         }
     }
     __syncthreads();

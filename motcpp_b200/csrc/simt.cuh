@@ -22,6 +22,15 @@ namespace mot {
 
 constexpr unsigned kFullMask = 0xffffffffu;
 
+// Hint: start moving the 128-byte line at p towards L2 (hides DRAM latency of the NEXT work item).
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#if !defined(MOT_CPUSIM)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 __device__ __forceinline__ int lane_id() { return (int)(threadIdx.x & 31u); }
 __device__ __forceinline__ int warp_id() { return (int)(threadIdx.x >> 5); }
 

@@ -11,8 +11,8 @@
 //     out of the new lost list, and nothing ever copies it to active_tracks_: it vanishes (:712-744);
 //   - unmatched tracked tracks become Lost only when the second association actually runs (:525-559);
 //   - remove_duplicate_stracks exists (:810) but is never called.
-// Vector sums (.dot(), .norm()) are sequential here; Eigen's order is unspecified, so feature values agree
-// with the stock build to fp32 round-off, not bit for bit.
+// Vector sums (.dot(), .norm()) use the fixed "lanes32" order below; Eigen's order is unspecified, so feature
+// values agree with the stock build to fp32 round-off, not bit for bit.
 // ID counter is per tracker instance and restarts at 0 on reset (botsort.cpp:249,257).
 #include "oracle.h"
 
@@ -25,11 +25,21 @@ namespace {
 
 enum State { New = 0, Tracked = 1, Lost = 2, Removed = 3 };
 
+// Summation order of every feature dot product / norm ("lanes32", shared with the CUDA kernel so that a warp can
+// evaluate it with coalesced loads): the products of elements 4q..4q+3 go, in that order, into partial sum q % 32
+// (each partial starts at +0 and takes its quadruples in ascending q); the 32 partials are then combined by the
+// butterfly p[l] += p[l ^ o], o = 16, 8, 4, 2, 1.  Eigen's own .dot()/.norm() order is vectorised and
+// unspecified, so any fixed order agrees with the stock build to fp32 round-off only.
 float seq_dot(const float* x, const float* y, int n) {
-    if (n == 0) return 0.0f;
-    float acc = x[0] * y[0];
-    for (int k = 1; k < n; ++k) acc = acc + x[k] * y[k];
-    return acc;
+    float part[32];
+    for (int l = 0; l < 32; ++l) part[l] = 0.0f;
+    for (int k = 0; k < n; ++k) {
+        const int l = (k >> 2) & 31;
+        part[l] = part[l] + x[k] * y[k];
+    }
+    for (int o = 16; o > 0; o >>= 1)
+        for (int l = 0; l < o; ++l) part[l] = part[l] + part[l + o];
+    return part[0];
 }
 float seq_norm(const float* x, int n) { return std::sqrt(seq_dot(x, x, n)); }
 

@@ -84,3 +84,32 @@ def test_host_side_argument_checks():
     assert api.iou_batch(np.zeros((0, 4)), np.zeros((2, 4))).shape == (0, 2)
     with pytest.raises(ValueError):
         api.embedding_distance(np.zeros((1, 4)), np.zeros((1, 4)), metric="manhattan")
+
+
+def _build_cpp_example(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "simple_tracking")
+    lib_dir = os.path.join(ROOT, "motcpp_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "simple_tracking.cpp"), "-L" + lib_dir, "-lmotb200",
+                           "-Wl,-rpath," + lib_dir, "-o", exe])
+    return exe
+
+
+def test_cpp_binding_compiles_and_fails_loudly_without_gpu(lib, tmp_path):
+    """include/motcpp_b200/trackers.hpp (Sort / ByteTrack / OCSort / BotSort with the reference's positional
+    constructors) builds with plain g++ against the C ABI."""
+    import subprocess
+    exe = _build_cpp_example(tmp_path)
+    if lib.mot_device_count() > 0:
+        pytest.skip("a GPU is present")
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 1 and "no CPU fallback" in p.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_binding_runs_on_gpu(lib, tmp_path):
+    import subprocess
+    p = subprocess.run([_build_cpp_example(tmp_path)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert "frame 2 rows: sort 2 ocsort 2 botsort 2" in p.stdout and "frame 2 id 1" in p.stdout

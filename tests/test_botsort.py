@@ -101,6 +101,9 @@ def test_botsort_kernel_logic_under_emulator(oracle):
     _sim_vs_oracle(oracle, 7, 60, 32, {**CLI, "track_high_thresh": 0.5, "new_track_thresh": 0.6, "track_buffer": 10,
                                       "appearance_thresh": 0.6, "with_reid": False})
     _sim_vs_oracle(oracle, 8, 50, 64, CLI, n_obj=48, canvas=(480, 270))
+    # proximity_thresh = 1: no pair is gated out, nothing can be pruned or tabulated -> dense scan, per-thread dot fallback
+    _sim_vs_oracle(oracle, 9, 30, 32, {**CLI, "proximity_thresh": 1.0})
+    _sim_vs_oracle(oracle, 10, 12, 516, CLI)         # more than 512 floats: the streaming (not register-resident) feature passes
 
 
 # ------------------------------------------------------------------ GPU parity through the C ABI

@@ -128,6 +128,99 @@ def main():
         emit("lap_256x512_dense_adversarial", ms, us_per_solve=1e3 * ms[0],
              matches_oracle=bool(np.array_equal(r2c[0].cpu().numpy(), refd[0])), bound="latency")
 
+    # ---------------- OC-SORT association cost (ocm): 4 B written per pair, one fp64 acos per pair
+    for (N, M) in ((2048, 2048), (8192, 8192)):
+        if not want("ocm") or (args.quick and N > 2048):
+            continue
+        c = torch.rand((N + M, 2), device=dev) * 8000
+        w = torch.rand((N + M, 2), device=dev) * 100 + 40
+        boxes = torch.cat([c, c + w], 1).contiguous()
+        dets5 = torch.cat([boxes[:N], torch.rand((N, 1), device=dev)], 1).contiguous()
+        trks = boxes[N:].contiguous()
+        vel = torch.nn.functional.normalize(torch.randn((M, 2), device=dev), dim=1).contiguous()
+        prev = torch.cat([trks + torch.randn((M, 4), device=dev) * 3, torch.rand((M, 1), device=dev)], 1).contiguous()
+        out = torch.empty((N, M), device=dev)
+        ms = timeit(lambda: api.check(lib.mot_cost_ocm(dets5.data_ptr(), N, trks.data_ptr(), vel.data_ptr(), prev.data_ptr(), M,
+                                                       0.2, out.data_ptr(), None, M, st)))
+        by = 4 * N * M + 20 * N + 44 * M
+        emit(f"ocm_cost_{N}x{M}", ms, algorithmic_bytes=by, achieved_gbs=by / ms[0] / 1e6, peak_gbs=HBM,
+             frac=by / ms[0] / 1e6 / HBM, bound="hbm nominally; issue-bound (fp64 acos per pair)", pairs_per_us=N * M / ms[0] / 1e3)
+
+    # ---------------- whole-tracker engines other than the headline ByteTrack one (device-resident, frames/s)
+    def engine_bench(name, kind, S, cap, d_max, dets_np, embs_np, warm_frames, T, iters, params, state_bytes_per_track, dim=0):
+        n_frames = dets_np.shape[0]
+        assert n_frames >= warm_frames + T * iters
+        D = dets_np.shape[-2]
+        src = torch.from_numpy(dets_np).to(dev)                       # (F, D, 6) or (F, nsrc, D, 6)
+        if src.ndim == 3:
+            src = src[:, None]
+        idx = torch.arange(S, device=dev) % src.shape[1]
+        dets = src[:, idx].contiguous()                               # (F, S, D, 6)
+        counts = torch.full((n_frames, S), D, dtype=torch.int32, device=dev)
+        embs = None
+        if embs_np is not None:
+            e = torch.from_numpy(embs_np).to(dev)
+            if e.ndim == 3:
+                e = e[:, None]
+            embs = e[:, idx].contiguous()                             # (F, S, D, dim)
+        eng = api.Engine(kind, S, cap, d_max, emb_dim=dim, **params)
+        out = torch.empty((T, S, cap, 8), device=dev)
+        n_out = torch.empty((T, S), dtype=torch.int32, device=dev)
+
+        def run(f0, nf):
+            ep = embs[f0:f0 + nf].data_ptr() if embs is not None else None
+            api.check(lib.mot_engine_update_device_embs(eng._h, nf, dets[f0:f0 + nf].data_ptr(), counts[f0:f0 + nf].data_ptr(), D,
+                                                        ep, out.data_ptr(), n_out.data_ptr(), cap, st))
+        f = 0
+        while f < warm_frames:
+            nf = min(T, warm_frames - f)
+            run(f, nf)
+            f += nf
+        torch.cuda.synchronize()
+        times = []
+        for it in range(iters):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            run(f, T)
+            b.record()
+            torch.cuda.synchronize()
+            times.append(a.elapsed_time(b))
+            f += T
+        eng.check()
+        hdr = eng.header(0)
+        ms = float(np.median(times))
+        rows = float(n_out.float().mean().item())
+        n_trk = int(hdr[0]) + (int(hdr[1]) if kind != _lib.TRACKER_OCSORT else 0)
+        by_frame = 2 * n_trk * state_bytes_per_track + D * 24 + rows * 32 + D * dim * 4
+        emit(name, (ms, float(np.min(times))), streams=S, frames_per_launch=T, frames_per_s=S * T / ms * 1e3,
+             us_per_frame_per_cta=ms * 1e3 / T / max(1, (S + 147) // 148), mean_output_rows=rows, tracks=n_trk, header=hdr[:14].tolist(),
+             algorithmic_bytes_per_frame=by_frame, achieved_gbs=by_frame * S * T / ms / 1e6, peak_gbs=HBM,
+             frac=by_frame * S * T / ms / 1e6 / HBM, info=eng.info())
+        eng.close()
+
+    if want("engine_ocsort"):
+        OC = dict(det_thresh=0.2, max_age=30, max_obs=50, min_hits=3, iou_threshold=0.3, min_conf=0.1, delta_t=3,
+                  inertia=0.2, use_byte=0, q_xy_scaling=0.01, q_s_scaling=0.0001)
+        T, iters, warm = (5, 3, 10) if args.quick else (10, 5, 20)
+        d = np.stack([synth.ocsort_stream(s, n_frames=warm + T * iters) for s in range(2 if args.quick else 4)], 1)
+        engine_bench("engine_ocsort_c4_2048x2048", _lib.TRACKER_OCSORT, 148, 3072, 2048, d, None, warm, T, iters, OC,
+                     state_bytes_per_track=224 + 32 + 32)
+    if want("engine_botsort"):
+        BOT = dict(track_high_thresh=0.6, track_low_thresh=0.1, new_track_thresh=0.7, track_buffer=30, match_thresh=0.8,
+                   proximity_thresh=0.5, appearance_thresh=0.25, frame_rate=30, fuse_first_associate=0, with_reid=1)
+        T, iters, warm = (4, 3, 4) if args.quick else (6, 4, 6)
+        pairs = [synth.embeddings_stream(s, n_frames=warm + T * iters) for s in range(2)]
+        d = np.stack([p[0] for p in pairs], 1)
+        e = np.stack([p[1] for p in pairs], 1)
+        engine_bench("engine_botsort_c3_1024x1024x512", _lib.TRACKER_BOTSORT, 148, 2048, 1024, d, e, warm, T, iters, BOT,
+                     state_bytes_per_track=288 + 2048, dim=512)
+    if want("engine_sort"):
+        SORT = dict(det_thresh=0.3, max_age=1, max_obs=50, min_hits=3, iou_threshold=0.3)
+        T, iters, warm = 50, 5, 50
+        d = np.stack([synth.bytetrack_stream(s, n_frames=warm + T * iters, n_clutter=32, n_low=32, config=1) for s in range(4)], 1)
+        engine_bench("engine_sort_256x320", _lib.TRACKER_SORT, 296, 1536, 512, d, None, warm, T, iters, SORT,
+                     state_bytes_per_track=224)
+
     # ---------------- cosine embedding cost on tensor cores
     for (N, M, D) in ((1024, 1024, 512), (4096, 4096, 512)):
         if not want("cos") or (args.quick and N > 1024):
