@@ -115,6 +115,28 @@ __device__ __forceinline__ bool chol4(const float (&S)[4][4], Chol4& L) {
     return ok;
 }
 
+// The tracking filters keep x, y, a|s|w, h|r statistically independent (F and H never mix them), so the innovation
+// covariance S is DIAGONAL for every state these trackers can reach: all off-diagonal entries are exact zeros.
+// Then the factor is diag(sqrt(S_ii)) and each solve is two divisions - the very operations the general code
+// performs on those entries (its other terms multiply or subtract exact zeros), so the values are identical.
+// The test is made warp-uniform by the callers; a non-diagonal S takes the general path.
+__device__ __forceinline__ bool sym4_is_diagonal(const float (&S)[4][4]) {
+    return S[1][0] == 0.0f && S[2][0] == 0.0f && S[2][1] == 0.0f && S[3][0] == 0.0f && S[3][1] == 0.0f && S[3][2] == 0.0f &&
+           S[0][1] == 0.0f && S[0][2] == 0.0f && S[1][2] == 0.0f && S[0][3] == 0.0f && S[1][3] == 0.0f && S[2][3] == 0.0f;
+}
+__device__ __forceinline__ bool chol4_diag(const float (&S)[4][4], Chol4& L) {
+    const bool ok = S[0][0] > 0.0f && S[1][1] > 0.0f && S[2][2] > 0.0f && S[3][3] > 0.0f;
+    L.l00 = xsqrt(S[0][0]); L.l11 = xsqrt(S[1][1]); L.l22 = xsqrt(S[2][2]); L.l33 = xsqrt(S[3][3]);
+    L.l10 = 0.0f; L.l20 = 0.0f; L.l21 = 0.0f; L.l30 = 0.0f; L.l31 = 0.0f; L.l32 = 0.0f;
+    return ok;
+}
+__device__ __forceinline__ void chol4_solve_diag(const Chol4& L, float (&b)[4]) {
+    b[0] = xdiv_pos(xdiv_pos(b[0], L.l00), L.l00);
+    b[1] = xdiv_pos(xdiv_pos(b[1], L.l11), L.l11);
+    b[2] = xdiv_pos(xdiv_pos(b[2], L.l22), L.l22);
+    b[3] = xdiv_pos(xdiv_pos(b[3], L.l33), L.l33);
+}
+
 // Solve (L L^T) x = b in place (smallmat.hpp cholesky_solve).
 __device__ __forceinline__ void chol4_solve(const Chol4& L, float (&b)[4]) {
     b[0] = xdiv_pos(b[0], L.l00);
@@ -185,9 +207,15 @@ __device__ __forceinline__ bool kf_xyah_update(KfRow& s, int g, int base, const 
 #pragma unroll
     for (int a = 0; a < 4; ++a) innov[a] = xsub(z[a], __shfl_sync(kFullMask, s.m, base + a));
     Chol4 L;
-    const bool ok = chol4(S, L);
     float k[4] = {s.p[0], s.p[1], s.p[2], s.p[3]};       // row g of P H^T
-    chol4_solve(L, k);
+    bool ok;
+    if (__all_sync(kFullMask, sym4_is_diagonal(S))) {
+        ok = chol4_diag(S, L);
+        chol4_solve_diag(L, k);
+    } else {
+        ok = chol4(S, L);
+        chol4_solve(L, k);
+    }
     if (!ok) return false;                               // uniform across the group
     kf_apply_gain8(s, base, k, S, innov);
     return true;
@@ -282,15 +310,26 @@ __device__ __forceinline__ bool kf_xysr_update(KfRow7& s, int g, int base, const
 #pragma unroll
     for (int a = 0; a < 4; ++a) y[a] = xsub(z[a], __shfl_sync(kFullMask, s.m, base + a));
     Chol4 L;
-    const bool ok = chol4(S, L);
+    bool ok;
     float sinv[4][4];                                    // chol.solve(Identity), column by column
+    if (__all_sync(kFullMask, sym4_is_diagonal(S))) {
+        ok = chol4_diag(S, L);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        float b[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        b[c] = 1.0f;
-        chol4_solve(L, b);
+        for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int a = 0; a < 4; ++a) sinv[a][c] = b[a];
+            for (int c = 0; c < 4; ++c) sinv[a][c] = 0.0f;
+        sinv[0][0] = xdiv(xdiv(1.0f, L.l00), L.l00); sinv[1][1] = xdiv(xdiv(1.0f, L.l11), L.l11);
+        sinv[2][2] = xdiv(xdiv(1.0f, L.l22), L.l22); sinv[3][3] = xdiv(xdiv(1.0f, L.l33), L.l33);
+    } else {
+        ok = chol4(S, L);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float b[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            b[c] = 1.0f;
+            chol4_solve(L, b);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) sinv[a][c] = b[a];
+        }
     }
     if (!ok) return false;
     float k[4];                                          // K(g,:) = (P H^T)(g,:) * Sinv

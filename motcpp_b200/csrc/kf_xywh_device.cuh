@@ -75,7 +75,15 @@ __device__ __forceinline__ bool kf_xywh_update(KfRow& s, int g, int base, const 
 #pragma unroll
     for (int a = 0; a < 4; ++a) innov[a] = xsub(z[a], __shfl_sync(kFullMask, s.m, base + a));
     float inv[4][4];
-    inverse4_lu(S, inv);
+    if (__all_sync(kFullMask, sym4_is_diagonal(S))) {
+        // LU with partial pivoting of a diagonal matrix: no row swaps, zero multipliers, inverse = diag(1 / S_ii)
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) inv[a][c] = (a == c) ? xdiv(1.0f, S[a][a]) : 0.0f;
+    } else {
+        inverse4_lu(S, inv);
+    }
     float k[4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
