@@ -88,6 +88,7 @@ struct mot_engine {
     unsigned char* d_state = nullptr;
     int n_chunks = 1;
     cudaStream_t streams[kMaxChunks] = {};
+    cudaEvent_t ev_in[kMaxChunks] = {}, ev_run[kMaxChunks] = {};   // frame-chunk pipeline of the host-buffer path
     // staging for the host-buffer path (grow-only)
     float* d_dets = nullptr;  size_t dets_cap = 0;
     int* d_ndets = nullptr;   size_t ndets_cap = 0;
@@ -439,7 +440,11 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
                               : (is_bot ? bot_prepare(e->shape, e->smem_bytes) : bt_prepare(e->shape, e->smem_bytes))));
     e->n_chunks = cfg->n_chunks > 0 ? std::min(cfg->n_chunks, kMaxChunks) : (cfg->n_streams >= 128 ? 8 : (cfg->n_streams >= 32 ? 4 : 1));
     e->n_chunks = std::min(e->n_chunks, cfg->n_streams);
-    for (int c = 0; c < e->n_chunks; ++c) MOT_CUDA(cudaStreamCreateWithFlags(&e->streams[c], cudaStreamNonBlocking));
+    for (int c = 0; c < kMaxChunks; ++c) {
+        MOT_CUDA(cudaStreamCreateWithFlags(&e->streams[c], cudaStreamNonBlocking));
+        MOT_CUDA(cudaEventCreateWithFlags(&e->ev_in[c], cudaEventDisableTiming));
+        MOT_CUDA(cudaEventCreateWithFlags(&e->ev_run[c], cudaEventDisableTiming));
+    }
     MOT_CUDA(cudaMalloc(&e->d_state, e->stride * (size_t)cfg->n_streams));
     MOT_CUDA(cudaMemsetAsync(e->d_state, 0, e->stride * (size_t)cfg->n_streams, e->streams[0]));
     if (int rc = engine_reset_impl(e, 0)) { mot_engine_destroy(e); return rc; }
@@ -450,8 +455,11 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
 int mot_engine_destroy(mot_engine* e) {
     if (!e) return MOT_OK;
     cudaSetDevice(e->cfg.device);
-    for (int c = 0; c < kMaxChunks; ++c)
+    for (int c = 0; c < kMaxChunks; ++c) {
         if (e->streams[c]) cudaStreamDestroy(e->streams[c]);
+        if (e->ev_in[c]) cudaEventDestroy(e->ev_in[c]);
+        if (e->ev_run[c]) cudaEventDestroy(e->ev_run[c]);
+    }
     cudaFree(e->d_state); cudaFree(e->d_embs); cudaFree(e->d_dets); cudaFree(e->d_ndets); cudaFree(e->d_out); cudaFree(e->d_nout);
     delete e;
     return MOT_OK;
@@ -460,7 +468,7 @@ int mot_engine_destroy(mot_engine* e) {
 int mot_engine_reset(mot_engine* e) {
     if (!e) return fail(MOT_ERR_INVALID_ARGUMENT, "null engine");
     MOT_CUDA(cudaSetDevice(e->cfg.device));
-    for (int c = 0; c < e->n_chunks; ++c) MOT_CUDA(cudaStreamSynchronize(e->streams[c]));
+    for (int c = 0; c < kMaxChunks; ++c) MOT_CUDA(cudaStreamSynchronize(e->streams[c]));
     return engine_reset_impl(e, /*keep_ids=*/1);     // BoT-SORT ignores the flag: its ids restart (botsort.cpp:257)
 }
 
@@ -498,6 +506,33 @@ int mot_engine_update_host_embs(mot_engine* e, int T, const float* dets, const i
     if (int rc = grow(&e->d_out, &e->out_cap, TS * ld_out * 8)) return rc;
     if (int rc = grow(&e->d_nout, &e->nout_cap, TS)) return rc;
     if (embs) if (int rc = grow(&e->d_embs, &e->embs_cap, TS * ld_dets * dim)) return rc;
+    if (T >= 4) {
+        // Many frames per call: pipeline over FRAME chunks.  A stream's frames are sequential on its CTA, so a launch
+        // lasts T x (time per frame) whatever the number of streams; cutting T lets the copies of chunk c+1 / c-1
+        // overlap the kernel of chunk c (streams[0] computes, streams[1] copies in, streams[2] copies out).
+        const int C = std::min(kMaxChunks, T / 2);
+        cudaStream_t s_run = e->streams[0], s_in = e->streams[1], s_out = e->streams[2];
+        const size_t det_fr = (size_t)S * ld_dets * 6, out_fr = (size_t)S * ld_out * 8, emb_fr = (size_t)S * ld_dets * dim;
+        for (int c = 0; c < C; ++c) {
+            const int t0 = (int)((long long)T * c / C), t1 = (int)((long long)T * (c + 1) / C), nt = t1 - t0;
+            MOT_CUDA(cudaMemcpyAsync(e->d_dets + t0 * det_fr, dets + t0 * det_fr, nt * det_fr * sizeof(float), cudaMemcpyHostToDevice, s_in));
+            MOT_CUDA(cudaMemcpyAsync(e->d_ndets + (size_t)t0 * S, n_dets + (size_t)t0 * S, (size_t)nt * S * sizeof(int), cudaMemcpyHostToDevice, s_in));
+            if (embs)
+                MOT_CUDA(cudaMemcpyAsync(e->d_embs + t0 * emb_fr, embs + t0 * emb_fr, nt * emb_fr * sizeof(float), cudaMemcpyHostToDevice, s_in));
+            MOT_CUDA(cudaEventRecord(e->ev_in[c], s_in));
+            MOT_CUDA(cudaStreamWaitEvent(s_run, e->ev_in[c], 0));
+            engine_launch(e, nt, e->d_dets + t0 * det_fr, e->d_ndets + (size_t)t0 * S, ld_dets, embs ? e->d_embs + t0 * emb_fr : nullptr,
+                          e->d_out + t0 * out_fr, e->d_nout + (size_t)t0 * S, ld_out, 0, S, s_run);
+            MOT_CUDA(cudaGetLastError());
+            MOT_CUDA(cudaEventRecord(e->ev_run[c], s_run));
+            MOT_CUDA(cudaStreamWaitEvent(s_out, e->ev_run[c], 0));
+            MOT_CUDA(cudaMemcpyAsync(out + t0 * out_fr, e->d_out + t0 * out_fr, nt * out_fr * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+            MOT_CUDA(cudaMemcpyAsync(n_out + (size_t)t0 * S, e->d_nout + (size_t)t0 * S, (size_t)nt * S * sizeof(int), cudaMemcpyDeviceToHost, s_out));
+        }
+        MOT_CUDA(cudaStreamSynchronize(s_out));
+        return MOT_OK;
+    }
+    // Few frames per call: pipeline over STREAM chunks instead (each chunk on its own CUDA stream)
     const int C = e->n_chunks;
     for (int c = 0; c < C; ++c) {
         const int s0 = (int)((long long)S * c / C), s1 = (int)((long long)S * (c + 1) / C);
