@@ -39,12 +39,10 @@ __device__ __forceinline__ int block_compact(int n, int start, BlockScratch* bs,
     __syncthreads();                       // bs may still be read by a previous call
     if (lane == 31) bs->warp_sum[warp] = incl;
     __syncthreads();
-    int before = 0, total = 0;
-    for (int w = 0; w < nwarps; ++w) {
-        const int s = bs->warp_sum[w];
-        if (w < warp) before += s;
-        total += s;
-    }
+    // every warp sums the per-warp counts itself: lane w holds warp w's count, two redux.sync do the rest
+    const int ws = (lane < nwarps) ? bs->warp_sum[lane] : 0;
+    const int total = __reduce_add_sync(kFullMask, ws);
+    const int before = __reduce_add_sync(kFullMask, (lane < warp) ? ws : 0);
     int pos = start + before + incl - cnt;
     for (int q = 0; q < items; ++q)
         if ((keep >> q) & 1u) emit(lo + q, pos++);
@@ -71,12 +69,9 @@ __device__ __forceinline__ int block_exclusive_scan(int* data, int n, BlockScrat
         }
         if (lane == 31) bs->warp_sum[warp] = incl;
         __syncthreads();
-        int before = 0, total = 0;
-        for (int w = 0; w < nwarps; ++w) {
-            const int s = bs->warp_sum[w];
-            if (w < warp) before += s;
-            total += s;
-        }
+        const int ws = (lane < nwarps) ? bs->warp_sum[lane] : 0;
+        const int total = __reduce_add_sync(kFullMask, ws);
+        const int before = __reduce_add_sync(kFullMask, (lane < warp) ? ws : 0);
         const int base = bs->base;
         if (k < n) data[k] = base + before + incl - v;
         __syncthreads();

@@ -341,6 +341,10 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
     return r;
 }
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+static inline int __reduce_add_sync(unsigned mask, int v) {          // full-warp masks only (what the kernels use)
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    return v;
+}
 static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == mask; }
 static inline unsigned __activemask() { return 0xffffffffu; }
 
