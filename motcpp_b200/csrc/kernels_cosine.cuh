@@ -12,9 +12,10 @@
 //     A' = [ h | h | m | h | l | m ]   (n x 6 Dp, bf16)        B' = [ h'| m'| h'| l'| h'| m' ]
 // so the whole thing is ONE bf16 GEMM  C = A' B'^T  with K' = 6 Dp, accumulated in fp32 in TMEM.
 //
-// GEMM kernel (one 128 x 64 output tile per CTA, 192 threads):
+// GEMM kernel (one 128 x 128 output tile per CTA, 192 threads; with N = 64 the MMA was starved by shared-memory
+// operand reads - 6 KB per K16 step for 131 k MACs - N = 128 balances the two):
 //   warp 4  TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B) into a 6-stage smem ring
-//   warp 5  TMEM allocation + MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M128 N64 K16,
+//   warp 5  TMEM allocation + MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M128 N128 K16,
 //           tcgen05.commit onto the ring's "empty" barriers and onto the accumulator barrier
 //   warps 0-3 epilogue: tcgen05.ld (32 lanes x 32 columns) -> norm division, 1 - x, max(0, .) -> float4 stores
 // SASS evidence to look for: UTCHMMA (tcgen05.mma), UTMALDG (TMA), LDTM (tcgen05.ld).
@@ -31,47 +32,68 @@ namespace mot {
 namespace cosine {
 
 constexpr int kBlockM = 128;
-constexpr int kBlockN = 64;
 constexpr int kBlockK = 64;                   // bf16 elements = 128 bytes = one SWIZZLE_128B row
 constexpr int kStages = 6;
 constexpr int kUmmaK = 16;
 constexpr int kThreads = 192;
 constexpr int kABytes = kBlockM * kBlockK * 2;     // 16 KB
-constexpr int kBBytes = kBlockN * kBlockK * 2;     //  8 KB
-constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kTmemCols = 64;
-constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256 /*barriers*/;
+// BLOCK_N = 64 or 128 (template parameter): one SM ingests its operands from L2 at ~64 B/cycle, so a CTA is bound by
+// (128 + N) x 128 B per 64-deep k-block rather than by the MMA; 128 x 128 tiles minimise total L2 traffic (large
+// problems), 128 x 64 tiles put twice as many SMs to work when there are fewer 128 x 128 tiles than SMs.
+__host__ __device__ constexpr int b_bytes(int block_n) { return block_n * kBlockK * 2; }
+__host__ __device__ constexpr int stage_bytes(int block_n) { return kABytes + b_bytes(block_n); }
+constexpr size_t smem_bytes(int block_n) {
+    return 1024 /*align slack*/ + (size_t)kStages * stage_bytes(block_n) + 256 /*barriers*/ + sizeof(float) * block_n;
+}
 
 // ---------------------------------------------------------------- split + norm pre-pass
-// One warp per row.  out row = 6 segments of Dp bf16 (Dp = dim rounded up to 64, zero padded).
-// order: for A (is_b = 0) [h h m h l m], for B (is_b = 1) [h m h l h m]
-__global__ void __launch_bounds__(256) cosine_split_kernel(const float* __restrict__ x, int rows, int dim, int dp,
-                                                           __nv_bfloat16* __restrict__ out, float* __restrict__ norm,
-                                                           int is_b) {
+// One launch for both operands, one warp per row, four consecutive floats per lane (float4 in, 8-byte bf16x4 out).
+// out row = 6 segments of Dp bf16 (Dp = dim rounded up to 64, zero padded).
+// order: A' rows [h h m h l m], B' rows [h m h l h m]
+struct __align__(8) bf16x4 { __nv_bfloat16 a, b, c, d; };
+
+__global__ void __launch_bounds__(256) cosine_split_kernel(const float* __restrict__ xa, int rows_a,
+                                                           const float* __restrict__ xb, int rows_b, int dim, int dp,
+                                                           __nv_bfloat16* __restrict__ out_a, __nv_bfloat16* __restrict__ out_b,
+                                                           float* __restrict__ norm_a, float* __restrict__ norm_b) {
     const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = (int)(threadIdx.x & 31);
     const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
-    for (int r = warp; r < rows; r += nwarps) {
-        const float* src = x + (size_t)r * dim;
-        __nv_bfloat16* dst = out + (size_t)r * 6 * dp;
+    const bool vec = ((dim & 3) == 0) && ((((uintptr_t)xa) & 15) == 0) && ((((uintptr_t)xb) & 15) == 0);
+    for (int r = warp; r < rows_a + rows_b; r += nwarps) {
+        const bool is_b = r >= rows_a;
+        const int rr = is_b ? r - rows_a : r;
+        const float* src = (is_b ? xb : xa) + (size_t)rr * dim;
+        __nv_bfloat16* dst = (is_b ? out_b : out_a) + (size_t)rr * 6 * dp;
         float acc = 0.0f;
-        for (int k = lane; k < dp; k += 32) {
-            const float v = (k < dim) ? src[k] : 0.0f;
-            acc = __fadd_rn(acc, __fmul_rn(v, v));
-            const __nv_bfloat16 h = __float2bfloat16_rn(v);
-            const float r1 = __fsub_rn(v, __bfloat162float(h));
-            const __nv_bfloat16 m = __float2bfloat16_rn(r1);
-            const float r2 = __fsub_rn(r1, __bfloat162float(m));
-            const __nv_bfloat16 l = __float2bfloat16_rn(r2);
-            if (!is_b) {
-                dst[k] = h; dst[dp + k] = h; dst[2 * dp + k] = m; dst[3 * dp + k] = h; dst[4 * dp + k] = l; dst[5 * dp + k] = m;
+        for (int k = lane * 4; k < dp; k += 128) {
+            float v[4];
+            if (vec && k + 3 < dim) {
+                const float4 q = *reinterpret_cast<const float4*>(src + k);
+                v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
             } else {
-                dst[k] = h; dst[dp + k] = m; dst[2 * dp + k] = h; dst[3 * dp + k] = l; dst[4 * dp + k] = h; dst[5 * dp + k] = m;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = (k + e < dim) ? src[k + e] : 0.0f;
             }
+            __nv_bfloat16 h[4], m[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                acc = __fadd_rn(acc, __fmul_rn(v[e], v[e]));
+                h[e] = __float2bfloat16_rn(v[e]);
+                const float r1 = __fsub_rn(v[e], __bfloat162float(h[e]));
+                m[e] = __float2bfloat16_rn(r1);
+                const float r2 = __fsub_rn(r1, __bfloat162float(m[e]));
+                l[e] = __float2bfloat16_rn(r2);
+            }
+            const bf16x4 H{h[0], h[1], h[2], h[3]}, M{m[0], m[1], m[2], m[3]}, L{l[0], l[1], l[2], l[3]};
+            bf16x4* o = reinterpret_cast<bf16x4*>(dst + k);
+            const int seg = dp / 4;                     // bf16x4 units per segment
+            if (!is_b) { o[0] = H; o[seg] = H; o[2 * seg] = M; o[3 * seg] = H; o[4 * seg] = L; o[5 * seg] = M; }
+            else       { o[0] = H; o[seg] = M; o[2 * seg] = H; o[3 * seg] = L; o[4 * seg] = H; o[5 * seg] = M; }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
-        if (lane == 0) norm[r] = __fsqrt_rn(acc);
+        if (lane == 0) (is_b ? norm_b : norm_a)[rr] = __fsqrt_rn(acc);
     }
 }
 
@@ -115,8 +137,8 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
     return d;
 }
 // kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
-__device__ __forceinline__ uint32_t umma_idesc() {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBlockN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+__device__ __forceinline__ uint32_t umma_idesc(int block_n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(block_n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -143,7 +165,8 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
 }
 
 // ---------------------------------------------------------------- GEMM + cosine epilogue
-// grid = (ceil(n / 128), ceil(m / 64)); tensor maps: A' (n x kp) box {64, 128}, B' (m x kp) box {64, 64}
+// grid = (ceil(n / 128), ceil(m / 128)); tensor maps: A' (n x kp) box {64, 128}, B' (m x kp) box {64, 128}
+template <int kBlockN>
 __global__ void __launch_bounds__(kThreads, 1)
 cosine_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int n, int m,
                    int kp, const float* __restrict__ norm_t, const float* __restrict__ norm_d, float* __restrict__ out,
@@ -151,10 +174,12 @@ cosine_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B: 1024-B aligned
     unsigned char* tiles = smem;
+    constexpr int kBBytes = b_bytes(kBlockN), kStageBytes = stage_bytes(kBlockN), kTmemCols = kBlockN;
     uint64_t* full = (uint64_t*)(smem + (size_t)kStages * kStageBytes);
     uint64_t* empty = full + kStages;
     uint64_t* acc_ready = empty + kStages;
     uint32_t* tmem_slot = (uint32_t*)(acc_ready + 1);
+    float* s_dn = (float*)(smem + (size_t)kStages * kStageBytes + 256);      // |d_j| of this tile's columns
 
     const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
     const int m0 = (int)blockIdx.x * kBlockM;      // rows of the output (tracks)
@@ -191,7 +216,7 @@ cosine_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
     } else if (warp == 5) {
         if (lane == 0) {                                            // ---- MMA issuer
-            const uint32_t idesc = umma_idesc();
+            const uint32_t idesc = umma_idesc(kBlockN);
             for (int kb = 0; kb < k_blocks; ++kb) {
                 const int s = kb % kStages;
                 const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
@@ -207,10 +232,14 @@ cosine_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             umma_commit(acc_ready);                                 // accumulator complete
         }
     } else {                                                        // ---- epilogue: warps 0..3 own TMEM lanes 32w..32w+31
-        mbar_wait(acc_ready, 0);
-        tcgen05_fence_after();
+        // stage the column norms while the main loop runs; the four epilogue warps meet on named barrier 1
+        for (int c = (int)threadIdx.x; c < kBlockN; c += 128) s_dn[c] = (n0 + c < m) ? norm_d[n0 + c] : 1.0f;
         const int row = m0 + warp * 32 + lane;
         const float tn = (row < n) ? norm_t[row] : 1.0f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        mbar_wait(acc_ready, 0);
+        tcgen05_fence_after();
+        {
         const bool vec_ok = ((ld & 3) == 0) && ((((uintptr_t)out) & 15) == 0);
 #pragma unroll
         for (int c0 = 0; c0 < kBlockN; c0 += 32) {
@@ -223,9 +252,9 @@ cosine_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     float v[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const int col = n0 + c0 + q + e;
-                        const float dn = (col < m) ? __ldg(&norm_d[col]) : 1.0f;
-                        const float sim = __fdiv_rn(__uint_as_float(r[q + e]), __fadd_rn(__fmul_rn(tn, dn), 1e-10f));
+                        // the accumulator already carries ~1e-7 relative error from the bf16 split: a fast division
+                        // (2 ulp) costs nothing in accuracy and keeps the epilogue off the IEEE-division slow path
+                        const float sim = __fdividef(__uint_as_float(r[q + e]), __fadd_rn(__fmul_rn(tn, s_dn[c0 + q + e]), 1e-10f));
                         v[e] = fmaxf(0.0f, __fsub_rn(1.0f, sim));
                     }
                     const int col = n0 + c0 + q;
@@ -238,6 +267,7 @@ cosine_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     }
                 }
             }
+        }
         }
     }
     tcgen05_fence_before();
@@ -285,36 +315,56 @@ inline int launch_cosine(const float* t, int n, const float* d, int m, int dim, 
     using namespace cosine;
     const int dp = (dim + kBlockK - 1) / kBlockK * kBlockK;
     const int kp = 6 * dp;
-    __nv_bfloat16 *a = nullptr, *b = nullptr;
-    float *tn = nullptr, *dn = nullptr;
     auto fail = [&](const char* what, cudaError_t e) {
         err = std::string("mot_cost_cosine: ") + what + ": " + cudaGetErrorString(e);
         return 2;   // MOT_ERR_CUDA
     };
     cudaError_t e;
-    if ((e = cudaMallocAsync((void**)&a, (size_t)n * kp * 2, st)) != cudaSuccess) return fail("alloc A'", e);
-    if ((e = cudaMallocAsync((void**)&b, (size_t)m * kp * 2, st)) != cudaSuccess) return fail("alloc B'", e);
-    if ((e = cudaMallocAsync((void**)&tn, sizeof(float) * n, st)) != cudaSuccess) return fail("alloc norms", e);
-    if ((e = cudaMallocAsync((void**)&dn, sizeof(float) * m, st)) != cudaSuccess) return fail("alloc norms", e);
-    cosine_split_kernel<<<(n + 7) / 8, 256, 0, st>>>(t, n, dim, dp, a, tn, 0);
-    cosine_split_kernel<<<(m + 7) / 8, 256, 0, st>>>(d, m, dim, dp, b, dn, 1);
+    // grow-only per-device workspace for the split operands and the norms; calls on one device are stream-ordered
+    // by the caller (like every other entry point, mot_cost_cosine is not re-entrant on the same buffers)
+    struct Workspace { unsigned char* p = nullptr; size_t cap = 0; };
+    static Workspace ws[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    Workspace& w = ws[dev & 63];
+    const size_t a_bytes = (((size_t)n * kp * 2) + 1023) & ~(size_t)1023, b_bytes = (((size_t)m * kp * 2) + 1023) & ~(size_t)1023;
+    const size_t need = a_bytes + b_bytes + sizeof(float) * ((size_t)n + m) + 1024;
+    if (w.cap < need) {
+        if (w.p) { cudaDeviceSynchronize(); cudaFree(w.p); w.p = nullptr; w.cap = 0; }
+        if ((e = cudaMalloc((void**)&w.p, need)) != cudaSuccess) return fail("workspace", e);
+        w.cap = need;
+    }
+    __nv_bfloat16* a = (__nv_bfloat16*)w.p;
+    __nv_bfloat16* b = (__nv_bfloat16*)(w.p + a_bytes);
+    float* tn = (float*)(w.p + a_bytes + b_bytes);
+    float* dn = tn + n;
+    cosine_split_kernel<<<(n + m + 7) / 8, 256, 0, st>>>(t, n, d, m, dim, dp, a, b, tn, dn);
     if ((e = cudaGetLastError()) != cudaSuccess) return fail("split launch", e);
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    const bool wide = (long long)((n + 127) / 128) * ((m + 127) / 128) >= n_sm;      // enough 128 x 128 tiles for every SM
     CUtensorMap map_a, map_b;
-    if (!make_map(&map_a, a, n, kp, kBlockM) || !make_map(&map_b, b, m, kp, kBlockN)) {
+    if (!make_map(&map_a, a, n, kp, kBlockM) || !make_map(&map_b, b, m, kp, wide ? 128 : 64)) {
         err = "mot_cost_cosine: cuTensorMapEncodeTiled failed";
         return 2;
     }
-    static bool attr_set = false;
+    static bool attr_done[64] = {};
+    bool& attr_set = attr_done[dev & 63];
     if (!attr_set) {
-        if ((e = cudaFuncSetAttribute(cosine_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes)) !=
-            cudaSuccess)
+        if ((e = cudaFuncSetAttribute(cosine_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(64))) != cudaSuccess ||
+            (e = cudaFuncSetAttribute(cosine_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(128))) != cudaSuccess)
             return fail("smem attribute", e);
         attr_set = true;
     }
-    dim3 grid((unsigned)((n + kBlockM - 1) / kBlockM), (unsigned)((m + kBlockN - 1) / kBlockN));
-    cosine_gemm_kernel<<<grid, kThreads, kSmemBytes, st>>>(map_a, map_b, n, m, kp, tn, dn, out, ld);
+    const int tiles_m = (n + kBlockM - 1) / kBlockM;
+    if (wide) {
+        dim3 grid((unsigned)tiles_m, (unsigned)((m + 127) / 128));
+        cosine_gemm_kernel<128><<<grid, kThreads, smem_bytes(128), st>>>(map_a, map_b, n, m, kp, tn, dn, out, ld);
+    } else {
+        dim3 grid((unsigned)tiles_m, (unsigned)((m + 63) / 64));
+        cosine_gemm_kernel<64><<<grid, kThreads, smem_bytes(64), st>>>(map_a, map_b, n, m, kp, tn, dn, out, ld);
+    }
     if ((e = cudaGetLastError()) != cudaSuccess) return fail("gemm launch", e);
-    cudaFreeAsync(a, st); cudaFreeAsync(b, st); cudaFreeAsync(tn, st); cudaFreeAsync(dn, st);
     return 0;
 }
 
