@@ -35,6 +35,10 @@ sys.path.insert(0, ROOT)
 METRIC = "tracker.update() frames/sec at 256 tracks x 512 dets (ByteTrack)"
 UNIT = "frames/s"
 ALGO_BYTES_PER_UPDATE = 167_936          # state in+out 147,456 + dets 12,288 + output 8,192
+# dram__bytes_read.sum + dram__bytes_write.sum of one bytetrack_step_kernel launch (ncu --set full, 148 streams x 20
+# frames, steady state) / 2960 frames: profiles/r1_bytetrack_step_ncu_full.txt.  Below the algorithmic figure because
+# most of a stream's 0.56 MB of state stays in the 126 MB L2 from one frame to the next.
+NCU_DRAM_BYTES_PER_UPDATE = 50_800          # (80.92 + 69.44) MB / 2960 frames
 BT_ARGS = dict(det_thresh=0.3, max_age=30, max_obs=50, min_hits=3, iou_threshold=0.3, min_conf=0.1,
                track_thresh=0.45, match_thresh=0.8, track_buffer=30, frame_rate=30)     # tools/motcpp_eval.cpp:133-148
 N_DETS = 512
@@ -130,6 +134,23 @@ class ClockSampler:
         self.index, self.rows, self._stop, self._th = index, [], threading.Event(), None
 
     def _loop(self):
+        # NVML (a query costs ~0.1 ms) so that a timed region of tens of milliseconds still gets many samples;
+        # nvidia-smi (one process per query, ~50 ms) is the fallback
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+            while not self._stop.is_set():
+                sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+                r = int(get_reasons(h))
+                self.rows.append([str(sm), str(mx), "0"] + ["Active" if r & b else "Not Active" for _, b in bits])
+                self._stop.wait(0.005)
+            return
+        except Exception:
+            pass
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -276,7 +297,9 @@ def main():
     avg_launch_s = float(np.mean(launch_ms)) * 1e-3
     achieved = ALGO_BYTES_PER_UPDATE * S * F / avg_launch_s / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                "traffic": None, "kernel": "bytetrack_step_kernel",
+                "traffic": NCU_DRAM_BYTES_PER_UPDATE * S * F, "kernel": "bytetrack_step_kernel",
+                "traffic_source": "ncu --set full dram__bytes_read+write per update() (profiles/r1_bytetrack_step_ncu_full.txt) "
+                                  "x updates per launch",
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_UPDATE * S * F,
                 "avg_launch_ms": float(np.mean(launch_ms)),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
