@@ -204,6 +204,9 @@ def _engine_vs_oracle(oracle, streams, args, cap, d_max, T_chunk=None, check_sta
 @pytest.mark.gpu
 def test_gpu_ocsort_engine_matches_oracle_stress(oracle, gpu):
     streams = [synth.stress_stream(200 + s, n_frames=160) for s in range(4)]
+    for d, c in streams:
+        c[20::23] = 0                                   # empty frames; stream 0 also loses every detection for a while
+    streams[0][1][60:95] = 0                            # longer than max_age: every track ages out, ids keep counting
     _engine_vs_oracle(oracle, streams, OC_ARGS, 256, 64, T_chunk=40)
     streams = [synth.stress_stream(300 + s, n_frames=100) for s in range(3)]
     _engine_vs_oracle(oracle, streams, {**OC_ARGS, "use_byte": True}, 256, 64, T_chunk=1)
@@ -231,3 +234,17 @@ def test_gpu_ocsort_c4_full_size(oracle, gpu):
     d = synth.ocsort_stream(0, n_frames=8)
     streams = [(d, np.full(d.shape[0], d.shape[1], np.int32))]
     _engine_vs_oracle(oracle, streams, OC_ARGS, 3072, 2048)
+
+
+@pytest.mark.gpu
+def test_gpu_ocsort_capacity_and_argument_errors(oracle, gpu):
+    d = synth.bytetrack_stream(1, n_frames=12, n_clutter=192, n_low=0, config=4)     # 448 fresh detections per frame
+    eng = api.Engine(_lib.TRACKER_OCSORT, 1, 256, 512, **OC_ARGS)                    # rounded up to 1536 tracks
+    eng.update(d[:, None], np.full((12, 1), d.shape[1], np.int32), ld_out=64)        # far more rows than ld_out
+    with pytest.raises(RuntimeError, match="output rows truncated"):
+        eng.check()
+    eng.close()
+    with pytest.raises(_lib.MotError):
+        api.Engine(_lib.TRACKER_OCSORT, 1, 256, 64, **{**OC_ARGS, "delta_t": 9})     # observation ring holds 8 ages
+    with pytest.raises(ValueError):
+        api.Engine(_lib.TRACKER_OCSORT, 1, 4096, 4096, **OC_ARGS)                    # beyond the largest built shape

@@ -221,6 +221,32 @@ def main():
         engine_bench("engine_sort_256x320", _lib.TRACKER_SORT, 296, 1536, 512, d, None, warm, T, iters, SORT,
                      state_bytes_per_track=224)
 
+    # ---------------- drop-in latency: ONE stream, ONE frame per call through the host-buffer C ABI (the reference's
+    #                  tracker.update(dets, img) usage pattern), pinned buffers, synchronous
+    if want("latency"):
+        import time
+        BT = dict(det_thresh=0.3, max_age=30, max_obs=50, min_hits=3, iou_threshold=0.3, min_conf=0.1, track_thresh=0.45,
+                  match_thresh=0.8, track_buffer=30, frame_rate=30)
+        d = synth.bytetrack_stream(0, n_frames=400)
+        eng = api.Engine(_lib.TRACKER_BYTETRACK, 1, 1536, 512, **BT)
+        h_d = api.pinned_empty((1, 1, 512, 6), np.float32)
+        h_n = api.pinned_empty((1, 1), np.int32)
+        h_o = api.pinned_empty((1, 1, 1536, 8), np.float32)
+        h_c = api.pinned_empty((1, 1), np.int32)
+        h_n[...] = 512
+        lat = []
+        for t in range(400):
+            h_d[0, 0] = d[t]
+            t0 = time.perf_counter()
+            api.check(lib.mot_engine_update_host(eng._h, 1, h_d.ctypes.data, h_n.ctypes.data, 512, h_o.ctypes.data, h_c.ctypes.data, 1536))
+            lat.append(time.perf_counter() - t0)
+        eng.check()
+        lat = np.array(lat[150:]) * 1e3
+        emit("latency_bytetrack_c2_one_stream_one_frame", (float(np.median(lat)), float(lat.min())), p99_ms=float(np.percentile(lat, 99)),
+             calls_per_s=1e3 / float(np.median(lat)), rows=int(h_c[0, 0]),
+             note="mot_engine_update_host(T=1, S=1): H2D 12 KB + kernel + D2H 48 KB + sync per call; the CPU oracle takes ~20 ms per such frame")
+        eng.close()
+
     # ---------------- cosine embedding cost on tensor cores
     for (N, M, D) in ((1024, 1024, 512), (4096, 4096, 512)):
         if not want("cos") or (args.quick and N > 1024):
