@@ -65,7 +65,7 @@ int sm_count() {
     return n;
 }
 
-constexpr int kMaxChunks = 8;
+constexpr int kMaxChunks = 16;
 
 }  // namespace
 

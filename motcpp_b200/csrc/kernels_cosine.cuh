@@ -12,7 +12,7 @@
 //     A' = [ h | h | m | h | l | m ]   (n x 6 Dp, bf16)        B' = [ h'| m'| h'| l'| h'| m' ]
 // so the whole thing is ONE bf16 GEMM  C = A' B'^T  with K' = 6 Dp, accumulated in fp32 in TMEM.
 //
-// GEMM kernel (one 128 x 128 output tile per CTA, 192 threads; with N = 64 the MMA was starved by shared-memory
+// GEMM kernel (persistent CTAs over 128 x 128 (or 128 x 64) output tiles, two TMEM accumulator stages, 192 threads; with N = 64 the MMA was starved by shared-memory
 // operand reads - 6 KB per K16 step for 131 k MACs - N = 128 balances the two):
 //   warp 4  TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B) into a 6-stage smem ring
 //   warp 5  TMEM allocation + MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M128 N128 K16,
@@ -24,6 +24,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <string>
 
 #include "simt.cuh"
@@ -43,7 +44,7 @@ constexpr int kABytes = kBlockM * kBlockK * 2;     // 16 KB
 __host__ __device__ constexpr int b_bytes(int block_n) { return block_n * kBlockK * 2; }
 __host__ __device__ constexpr int stage_bytes(int block_n) { return kABytes + b_bytes(block_n); }
 constexpr size_t smem_bytes(int block_n) {
-    return 1024 /*align slack*/ + (size_t)kStages * stage_bytes(block_n) + 256 /*barriers*/ + sizeof(float) * block_n;
+    return 1024 /*align slack*/ + (size_t)kStages * stage_bytes(block_n) + 256 /*barriers*/ + sizeof(float) * 2 * block_n;
 }
 
 // ---------------------------------------------------------------- split + norm pre-pass
@@ -166,31 +167,38 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
 
 // ---------------------------------------------------------------- GEMM + cosine epilogue
 // grid = (ceil(n / 128), ceil(m / 128)); tensor maps: A' (n x kp) box {64, 128}, B' (m x kp) box {64, 128}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent CTAs: tile t = blockIdx.x, blockIdx.x + gridDim.x, ... (m-tile fastest, so concurrently running CTAs
+// share B' panels in L2).  Two TMEM accumulator stages: the MMA warp fills stage (i & 1) of tile i while the four
+// epilogue warps drain stage ((i - 1) & 1) of the previous tile.
 template <int kBlockN>
 __global__ void __launch_bounds__(kThreads, 1)
 cosine_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int n, int m,
                    int kp, const float* __restrict__ norm_t, const float* __restrict__ norm_d, float* __restrict__ out,
-                   int ld) {
+                   int ld, int tiles_m, int tiles_total) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B: 1024-B aligned
     unsigned char* tiles = smem;
-    constexpr int kBBytes = b_bytes(kBlockN), kStageBytes = stage_bytes(kBlockN), kTmemCols = kBlockN;
+    constexpr int kBBytes = b_bytes(kBlockN), kStageBytes = stage_bytes(kBlockN), kTmemCols = 2 * kBlockN;
+    (void)kBBytes;
     uint64_t* full = (uint64_t*)(smem + (size_t)kStages * kStageBytes);
     uint64_t* empty = full + kStages;
-    uint64_t* acc_ready = empty + kStages;
-    uint32_t* tmem_slot = (uint32_t*)(acc_ready + 1);
-    float* s_dn = (float*)(smem + (size_t)kStages * kStageBytes + 256);      // |d_j| of this tile's columns
+    uint64_t* acc_full = empty + kStages;            // [2]
+    uint64_t* acc_empty = acc_full + 2;              // [2]
+    uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+    float* s_dn = (float*)(smem + (size_t)kStages * kStageBytes + 256);      // [2][kBlockN] |d_j| of a tile's columns
 
     const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
-    const int m0 = (int)blockIdx.x * kBlockM;      // rows of the output (tracks)
-    const int n0 = (int)blockIdx.y * kBlockN;      // columns of the output (detections)
     const int k_blocks = kp / kBlockK;
 
     if (threadIdx.x == 4 * 32) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(acc_ready, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 5) {
@@ -204,70 +212,90 @@ cosine_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
     if (warp == 4) {
         if (lane == 0) {                                            // ---- TMA producer
-            for (int kb = 0; kb < k_blocks; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
-                mbar_wait(&empty[s], ph ^ 1u);
-                mbar_expect_tx(&full[s], kStageBytes);
-                unsigned char* a_dst = tiles + (size_t)s * kStageBytes;
-                tma_load_2d(a_dst, &map_a, kb * kBlockK, m0, &full[s]);
-                tma_load_2d(a_dst + kABytes, &map_b, kb * kBlockK, n0, &full[s]);
+            int it = 0;
+            for (int t = (int)blockIdx.x; t < tiles_total; t += (int)gridDim.x) {
+                const int m0 = (t % tiles_m) * kBlockM, n0 = (t / tiles_m) * kBlockN;
+                for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+                    const int s = it % kStages;
+                    const uint32_t ph = (uint32_t)(it / kStages) & 1u;
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    mbar_expect_tx(&full[s], kStageBytes);
+                    unsigned char* a_dst = tiles + (size_t)s * kStageBytes;
+                    tma_load_2d(a_dst, &map_a, kb * kBlockK, m0, &full[s]);
+                    tma_load_2d(a_dst + kABytes, &map_b, kb * kBlockK, n0, &full[s]);
+                }
             }
         }
     } else if (warp == 5) {
         if (lane == 0) {                                            // ---- MMA issuer
             const uint32_t idesc = umma_idesc(kBlockN);
-            for (int kb = 0; kb < k_blocks; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
-                mbar_wait(&full[s], ph);
+            int it = 0, ti = 0;
+            for (int t = (int)blockIdx.x; t < tiles_total; t += (int)gridDim.x, ++ti) {
+                const int as = ti & 1;
+                mbar_wait(&acc_empty[as], ((uint32_t)(ti >> 1) & 1u) ^ 1u);        // epilogue drained this stage
                 tcgen05_fence_after();
-                const uint32_t a_addr = smem_u32(tiles + (size_t)s * kStageBytes);
-                const uint64_t adesc = umma_smem_desc(a_addr), bdesc = umma_smem_desc(a_addr + kABytes);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(as * kBlockN);
+                for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+                    const int s = it % kStages;
+                    const uint32_t ph = (uint32_t)(it / kStages) & 1u;
+                    mbar_wait(&full[s], ph);
+                    tcgen05_fence_after();
+                    const uint32_t a_addr = smem_u32(tiles + (size_t)s * kStageBytes);
+                    const uint64_t adesc = umma_smem_desc(a_addr), bdesc = umma_smem_desc(a_addr + kABytes);
 #pragma unroll
-                for (int k = 0; k < kBlockK / kUmmaK; ++k)          // advance 16 elements = 32 bytes inside the swizzle atom
-                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-                umma_commit(&empty[s]);                             // smem slot reusable when these MMAs retire
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k)      // advance 16 elements = 32 bytes inside the swizzle atom
+                        umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    umma_commit(&empty[s]);                         // smem slot reusable when these MMAs retire
+                }
+                umma_commit(&acc_full[as]);                         // accumulator of this tile complete
             }
-            umma_commit(acc_ready);                                 // accumulator complete
         }
     } else {                                                        // ---- epilogue: warps 0..3 own TMEM lanes 32w..32w+31
-        // stage the column norms while the main loop runs; the four epilogue warps meet on named barrier 1
-        for (int c = (int)threadIdx.x; c < kBlockN; c += 128) s_dn[c] = (n0 + c < m) ? norm_d[n0 + c] : 1.0f;
-        const int row = m0 + warp * 32 + lane;
-        const float tn = (row < n) ? norm_t[row] : 1.0f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        mbar_wait(acc_ready, 0);
-        tcgen05_fence_after();
-        {
         const bool vec_ok = ((ld & 3) == 0) && ((((uintptr_t)out) & 15) == 0);
+        int ti = 0;
+        for (int t = (int)blockIdx.x; t < tiles_total; t += (int)gridDim.x, ++ti) {
+            const int as = ti & 1;
+            const int m0 = (t % tiles_m) * kBlockM, n0 = (t / tiles_m) * kBlockN;
+            float* dn = s_dn + as * kBlockN;
+            // stage the column norms while the main loop runs; the four epilogue warps meet on named barrier 1
+            for (int c = (int)threadIdx.x; c < kBlockN; c += 128) dn[c] = (n0 + c < m) ? norm_d[n0 + c] : 1.0f;
+            const int row = m0 + warp * 32 + lane;
+            const float tn = (row < n) ? norm_t[row] : 1.0f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(&acc_full[as], (uint32_t)(ti >> 1) & 1u);
+            tcgen05_fence_after();
 #pragma unroll
-        for (int c0 = 0; c0 < kBlockN; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
-            if (row < n) {
-                float* orow = out + (size_t)row * ld + n0 + c0;
+            for (int c0 = 0; c0 < kBlockN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * kBlockN + c0), r);
+                if (c0 + 32 >= kBlockN) {                           // last read of this stage: hand it back to the MMA warp
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[as]);
+                }
+                if (row < n) {
+                    float* orow = out + (size_t)row * ld + n0 + c0;
 #pragma unroll
-                for (int q = 0; q < 32; q += 4) {
-                    float v[4];
+                    for (int q = 0; q < 32; q += 4) {
+                        float v[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        // the accumulator already carries ~1e-7 relative error from the bf16 split: a fast division
-                        // (2 ulp) costs nothing in accuracy and keeps the epilogue off the IEEE-division slow path
-                        const float sim = __fdividef(__uint_as_float(r[q + e]), __fadd_rn(__fmul_rn(tn, s_dn[c0 + q + e]), 1e-10f));
-                        v[e] = fmaxf(0.0f, __fsub_rn(1.0f, sim));
-                    }
-                    const int col = n0 + c0 + q;
-                    if (vec_ok && col + 3 < m) {
-                        *reinterpret_cast<float4*>(orow + q) = make_float4(v[0], v[1], v[2], v[3]);
-                    } else {
+                        for (int e = 0; e < 4; ++e) {
+                            // the accumulator already carries ~1e-7 relative error from the bf16 split: a fast division
+                            // (2 ulp) costs nothing in accuracy and keeps the epilogue off the IEEE-division slow path
+                            const float sim = __fdividef(__uint_as_float(r[q + e]), __fadd_rn(__fmul_rn(tn, dn[c0 + q + e]), 1e-10f));
+                            v[e] = fmaxf(0.0f, __fsub_rn(1.0f, sim));
+                        }
+                        const int col = n0 + c0 + q;
+                        if (vec_ok && col + 3 < m) {
+                            *reinterpret_cast<float4*>(orow + q) = make_float4(v[0], v[1], v[2], v[3]);
+                        } else {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (col + e < m) orow[q + e] = v[e];
+                            for (int e = 0; e < 4; ++e)
+                                if (col + e < m) orow[q + e] = v[e];
+                        }
                     }
                 }
             }
-        }
         }
     }
     tcgen05_fence_before();
@@ -358,11 +386,13 @@ inline int launch_cosine(const float* t, int n, const float* d, int m, int dim, 
     }
     const int tiles_m = (n + kBlockM - 1) / kBlockM;
     if (wide) {
-        dim3 grid((unsigned)tiles_m, (unsigned)((m + 127) / 128));
-        cosine_gemm_kernel<128><<<grid, kThreads, smem_bytes(128), st>>>(map_a, map_b, n, m, kp, tn, dn, out, ld);
+        const int total = tiles_m * ((m + 127) / 128);
+        cosine_gemm_kernel<128><<<std::min(total, n_sm), kThreads, smem_bytes(128), st>>>(map_a, map_b, n, m, kp, tn, dn, out, ld,
+                                                                                        tiles_m, total);
     } else {
-        dim3 grid((unsigned)tiles_m, (unsigned)((m + 63) / 64));
-        cosine_gemm_kernel<64><<<grid, kThreads, smem_bytes(64), st>>>(map_a, map_b, n, m, kp, tn, dn, out, ld);
+        const int total = tiles_m * ((m + 63) / 64);
+        cosine_gemm_kernel<64><<<std::min(total, n_sm), kThreads, smem_bytes(64), st>>>(map_a, map_b, n, m, kp, tn, dn, out, ld,
+                                                                                      tiles_m, total);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return fail("gemm launch", e);
     return 0;
