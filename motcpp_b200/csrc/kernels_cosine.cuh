@@ -34,17 +34,17 @@ namespace cosine {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                   // bf16 elements = 128 bytes = one SWIZZLE_128B row
-constexpr int kStages = 6;
 constexpr int kUmmaK = 16;
 constexpr int kThreads = 192;
 constexpr int kABytes = kBlockM * kBlockK * 2;     // 16 KB
-// BLOCK_N = 64 or 128 (template parameter): one SM ingests its operands from L2 at ~64 B/cycle, so a CTA is bound by
-// (128 + N) x 128 B per 64-deep k-block rather than by the MMA; 128 x 128 tiles minimise total L2 traffic (large
-// problems), 128 x 64 tiles put twice as many SMs to work when there are fewer 128 x 128 tiles than SMs.
+// BLOCK_N = 64, 128 or 256 (template parameter): one SM ingests its operands from L2 at ~64 B/cycle, so a CTA is bound by
+// (128 + N) x 128 B per 64-deep k-block rather than by the MMA (N x 2 cycles per k-block): the wider the tile, the
+// closer to the tensor peak (N = 128: 50 %, N = 256: 67 %); narrower tiles put more SMs to work on small problems.
+__host__ __device__ constexpr int n_stages(int block_n) { return block_n >= 256 ? 4 : 6; }      // 4 x 48 KB or 6 x 32 / 24 KB
 __host__ __device__ constexpr int b_bytes(int block_n) { return block_n * kBlockK * 2; }
 __host__ __device__ constexpr int stage_bytes(int block_n) { return kABytes + b_bytes(block_n); }
 constexpr size_t smem_bytes(int block_n) {
-    return 1024 /*align slack*/ + (size_t)kStages * stage_bytes(block_n) + 256 /*barriers*/ + sizeof(float) * 2 * block_n;
+    return 1024 /*align slack*/ + (size_t)n_stages(block_n) * stage_bytes(block_n) + 256 /*barriers*/ + sizeof(float) * 2 * block_n;
 }
 
 // ---------------------------------------------------------------- split + norm pre-pass
@@ -183,6 +183,7 @@ cosine_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B: 1024-B aligned
     unsigned char* tiles = smem;
     constexpr int kBBytes = b_bytes(kBlockN), kStageBytes = stage_bytes(kBlockN), kTmemCols = 2 * kBlockN;
+    constexpr int kStages = n_stages(kBlockN);
     (void)kBBytes;
     uint64_t* full = (uint64_t*)(smem + (size_t)kStages * kStageBytes);
     uint64_t* empty = full + kStages;
@@ -370,9 +371,11 @@ inline int launch_cosine(const float* t, int n, const float* d, int m, int dim, 
     if ((e = cudaGetLastError()) != cudaSuccess) return fail("split launch", e);
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    const bool wide = (long long)((n + 127) / 128) * ((m + 127) / 128) >= n_sm;      // enough 128 x 128 tiles for every SM
+    // widest tile that still gives every SM at least two tiles
+    const long long tm = (n + 127) / 128;
+    const int block_n = (tm * ((m + 255) / 256) >= 2LL * n_sm) ? 256 : ((tm * ((m + 127) / 128) >= n_sm) ? 128 : 64);
     CUtensorMap map_a, map_b;
-    if (!make_map(&map_a, a, n, kp, kBlockM) || !make_map(&map_b, b, m, kp, wide ? 128 : 64)) {
+    if (!make_map(&map_a, a, n, kp, kBlockM) || !make_map(&map_b, b, m, kp, block_n)) {
         err = "mot_cost_cosine: cuTensorMapEncodeTiled failed";
         return 2;
     }
@@ -380,12 +383,17 @@ inline int launch_cosine(const float* t, int n, const float* d, int m, int dim, 
     bool& attr_set = attr_done[dev & 63];
     if (!attr_set) {
         if ((e = cudaFuncSetAttribute(cosine_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(64))) != cudaSuccess ||
-            (e = cudaFuncSetAttribute(cosine_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(128))) != cudaSuccess)
+            (e = cudaFuncSetAttribute(cosine_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(128))) != cudaSuccess ||
+            (e = cudaFuncSetAttribute(cosine_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(256))) != cudaSuccess)
             return fail("smem attribute", e);
         attr_set = true;
     }
     const int tiles_m = (n + kBlockM - 1) / kBlockM;
-    if (wide) {
+    if (block_n == 256) {
+        const int total = tiles_m * ((m + 255) / 256);
+        cosine_gemm_kernel<256><<<std::min(total, n_sm), kThreads, smem_bytes(256), st>>>(map_a, map_b, n, m, kp, tn, dn, out, ld,
+                                                                                        tiles_m, total);
+    } else if (block_n == 128) {
         const int total = tiles_m * ((m + 127) / 128);
         cosine_gemm_kernel<128><<<std::min(total, n_sm), kThreads, smem_bytes(128), st>>>(map_a, map_b, n, m, kp, tn, dn, out, ld,
                                                                                         tiles_m, total);

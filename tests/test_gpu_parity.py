@@ -443,6 +443,20 @@ def test_cosine_cost_matches_oracle(oracle, n, m, dim):
         assert got[2, m - 1] <= COSINE_ATOL
 
 
+@pytest.mark.parametrize("n,m,dim", [(2048, 2100, 64), (4096, 4800, 32), (5000, 9500, 16)])
+def test_cosine_cost_large_tiles(n, m, dim):
+    """Sizes that select the 128 x 128 and 128 x 256 persistent-tile variants (several tiles per CTA, both TMEM
+    accumulator stages in use, ragged right / bottom edges).  Checked against a float64 numpy evaluation of the
+    same formula (the C oracle is the same arithmetic in fp32; it would take minutes at these sizes)."""
+    rng = np.random.default_rng(n + m + dim)
+    t = rng.normal(0, 1, (n, dim)).astype(np.float32)
+    d = rng.normal(0, 1, (m, dim)).astype(np.float32)
+    got = api.embedding_distance(t, d)
+    t64, d64 = t.astype(np.float64), d.astype(np.float64)
+    sim = (t64 @ d64.T) / (np.linalg.norm(t64, axis=1)[:, None] * np.linalg.norm(d64, axis=1)[None] + 1e-10)
+    np.testing.assert_allclose(got, np.maximum(0.0, 1.0 - sim), atol=COSINE_ATOL, rtol=0)
+
+
 def test_cosine_botsort_embeddings(oracle):
     """C3-style inputs: unit-norm identity embeddings, detections = identity + noise."""
     dets, embs = synth.embeddings_stream(0, n_frames=2, n_obj=256, dim=512)
