@@ -78,6 +78,7 @@ SYMBOLS = {
     "mot_cost_cosine": (_I, [_VP, _I, _VP, _I, _I, _VP, _I, _VP]),
     "mot_lap_device": (_I, [_VP, _I, _I, _I, _F, _VP, _VP, _VP]),
     "mot_lap_batch_device": (_I, [_VP, _LL, _I, _VP, _VP, _I, _I, _I, _F, _VP, _VP, _VP]),
+    "mot_lap_jv_batch_device": (_I, [_VP, _LL, _I, _I, _I, _I, _F, _VP, _VP, _VP]),
     "mot_lap_host": (_I, [_VP, _I, _I, _I, _F, _VP, _VP]),
 }
 

@@ -201,6 +201,27 @@ def linear_assignment_arrays(cost_matrix, thresh: float):
     return r2c, c2r
 
 
+def linear_assignment_reference_order(cost_matrices, thresh: float):
+    """The reference's dense LAPJV itself on the GPU (mot_lap_jv_batch_device): cost (P, n, m) or (n, m) with
+    n + m <= 384 -> (row2col, col2row), ties resolved exactly as utils::linear_assignment resolves them."""
+    cost = np.ascontiguousarray(cost_matrices, np.float32)
+    single = cost.ndim == 2
+    if single:
+        cost = cost[None]
+    P, n, m = cost.shape
+    r2c = np.full((P, n), -1, np.int32)
+    c2r = np.full((P, m), -1, np.int32)
+    if P and n and m:
+        _lib.require_gpu()
+        dc, dr, dq = DeviceArray.from_host(cost), DeviceArray((P, n), np.int32), DeviceArray((P, m), np.int32)
+        try:
+            check(load().mot_lap_jv_batch_device(dc.ptr, n * m, P, n, m, m, float(thresh), dr.ptr, dq.ptr, None))
+        except MotError as e:
+            _raise(e)
+        r2c, c2r = dr.download(), dq.download()
+    return (r2c[0], c2r[0]) if single else (r2c, c2r)
+
+
 # ------------------------------------------------------------------ Kalman filters (batched)
 class _BatchedKF:
     KIND = KF_XYAH

@@ -832,6 +832,20 @@ int mot_lap_batch_device(const float* cost, long long stride_cost, int n_problem
     return MOT_OK;
 }
 
+int mot_lap_jv_batch_device(const float* cost, long long stride_cost, int n_problems, int n, int m, int ld, float thresh,
+                            int* row2col, int* col2row, void* stream) {
+    if (n <= 0 || m <= 0 || n_problems < 0 || ld < m) return fail(MOT_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (n + m > mot::kLapJvMax)
+        return fail(MOT_ERR_UNSUPPORTED, "the reference-order LAPJV is built for rows + columns <= %d (got %d)", mot::kLapJvMax, n + m);
+    if (int rc = require_device()) return rc;
+    if (n_problems == 0) return MOT_OK;
+    if (!cost || !row2col || !col2row) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
+    mot::lap_jv_kernel<<<std::min(n_problems, sm_count() * 16), 32, 0, (cudaStream_t)stream>>>(cost, stride_cost, n_problems, n, m, ld,
+                                                                                             thresh, row2col, col2row);
+    MOT_CUDA(cudaGetLastError());
+    return MOT_OK;
+}
+
 int mot_lap_device(const float* cost, int n, int m, int ld, float thresh, int* row2col, int* col2row, void* stream) {
     return mot_lap_batch_device(cost, 0, 1, nullptr, nullptr, n, m, ld, thresh, row2col, col2row, stream);
 }

@@ -2,6 +2,7 @@
 // One CTA per problem; see lap_device.cuh for the algorithm and the reference lines it replaces.
 #pragma once
 #include "lap_device.cuh"
+#include "jv_device.cuh"
 
 namespace mot {
 
@@ -34,6 +35,22 @@ __global__ void __launch_bounds__(256) lap_dense_kernel(LapBatchArgs a) {
         for (int i = (int)threadIdx.x; i < n; i += (int)blockDim.x) r2c[i] = (int)ws.row2col[i];
         for (int j = (int)threadIdx.x; j < m; j += (int)blockDim.x) c2r[j] = (int)ws.col2row[j];
         __syncthreads();
+    }
+}
+
+// The reference's dense LAPJV itself (jv_device.cuh), one warp per problem, rows + columns <= kLapJvMax: reproduces
+// utils::linear_assignment INCLUDING its scan-order tie-breaking (what the sparse solver above does not promise).
+constexpr int kLapJvMax = 384;
+
+__global__ void __launch_bounds__(32) lap_jv_kernel(const float* __restrict__ cost, long long stride_cost, int n_problems, int n, int m,
+                                                    int ld, float thresh, int* __restrict__ row2col, int* __restrict__ col2row) {
+    __shared__ __align__(16) unsigned char work[jv_work_bytes(kLapJvMax + 1)];
+    const JvWork w = jv_carve(work, kLapJvMax + 1);
+    for (int p = (int)blockIdx.x; p < n_problems; p += (int)gridDim.x) {
+        warp_dense_lapjv(JvCost{cost + (size_t)p * stride_cost, n, m, ld, (double)thresh / 2.0}, n + m, w);
+        for (int i = (int)threadIdx.x; i < n; i += 32) { const int j = w.x[i]; row2col[(size_t)p * n + i] = j < m ? j : -1; }
+        for (int j = (int)threadIdx.x; j < m; j += 32) { const int i = w.y[j]; col2row[(size_t)p * m + j] = i < n ? i : -1; }
+        __syncwarp();
     }
 }
 

@@ -97,7 +97,7 @@ struct OcmCost {
     const unsigned short* row_map;
     const float4* trk_box;            // predicted boxes (shared memory)
     const float4* ocm;                // {cx, cy, vy, vx} of k_previous_obs / velocity per track
-    const unsigned char* valid;       // previous_obs(4) >= 0
+    const unsigned char* valid;       // bit 0: previous_obs(4) >= 0, bit 1: the track has a live twin
     float inertia, iou_thr;
     bool prune;                       // a disjoint pair can neither be a candidate nor count as iou > thr
     unsigned* row_bits;               // [ceil(n/32)] rows that have one pair with iou > thr
@@ -119,7 +119,7 @@ struct OcmCost {
     __device__ __forceinline__ bool reject(const Row& r, int j) const { return prune && boxes_disjoint(r.b, trk_box[j]); }
     __device__ __forceinline__ float iou(const Row& r, int j) const { return iou_pair(r.b, r.area, trk_box[j]); }
     __device__ __forceinline__ float cost_from_iou(const Row& r, int j, float v) const {
-        const float va = valid[j] ? 1.0f : 0.0f;
+        const float va = (valid[j] & 1) ? 1.0f : 0.0f;
         if (va == 0.0f) return -v;                     // 0 * angle * inertia * score adds exactly +-0
         const float ac = xmul(ocm_angle_cost(r.cx, r.cy, ocm[j], va, inertia), r.score);
         return -xadd(v, ac);

@@ -25,6 +25,7 @@
 #include "kf_device.cuh"
 #include "lap_device.cuh"
 #include "ocm_device.cuh"
+#include "jv_device.cuh"
 
 namespace mot {
 
@@ -35,11 +36,20 @@ constexpr int kOcThreads = MOT_OC_THREADS;
 constexpr int kOcRecFloats = 64;       // 56 used
 constexpr int kOcRing = 8;             // observation ring entries per track: delta_t <= kOcRing
 constexpr int kOcObsFloats = 8;        // last_observation[5], velocity (dy, dx), pad
+// Exact reference tie-breaking: when a "twin" track (see the file header) is an assignment candidate and the problem is
+// small enough (rows + columns <= kJvMax), the frame's assignment is redone by the reference's own dense LAPJV
+// (jv_device.cuh) on the full cost matrix; larger problems keep the sparse solver's "higher column" rule.
+#ifndef MOT_OC_JVMAX
+#define MOT_OC_JVMAX 384
+#endif
+constexpr int kJvMax = MOT_OC_JVMAX;
+constexpr int kJvDenseMax = (kJvMax / 2) * (kJvMax / 2) + 16;  // n * m <= (n + m)^2 / 4
+constexpr unsigned short kNoTwin = 0xffff;
 
 enum : int {
     kOHdrTracks = 0, kOHdrFree = 2, kOHdrIdCounter = 3, kOHdrFrame = 4, kOHdrError = 5,
     kOHdrNHigh = 6, kOHdrNTrk = 7, kOHdrUsedLap = 8, kOHdrMatched = 9, kOHdrLeftDets = 10, kOHdrLeftTrks = 11,
-    kOHdrRematched = 12, kOHdrSpawned = 13
+    kOHdrRematched = 12, kOHdrSpawned = 13, kOHdrExactSolves = 14      // cumulative count of dense-LAPJV re-solves
 };
 
 struct OcParams {
@@ -51,7 +61,7 @@ struct OcParams {
 struct OcLayout {
     int cap, d_max;
     size_t off_lists, off_meta, off_obs, off_ring_box, off_ring_conf, off_ring_age, off_recs, off_ocm, off_valid,
-        off_gscratch, stride;
+        off_twin, off_jv, off_gscratch, stride;
     MOT_HD static constexpr size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
     MOT_HD static constexpr OcLayout make(int cap, int d_max) {
         OcLayout L{};
@@ -66,6 +76,8 @@ struct OcLayout {
         L.off_recs = o;      o = al(o + sizeof(float) * kOcRecFloats * (size_t)cap);
         L.off_ocm = o;       o = al(o + sizeof(float4) * (size_t)cap);
         L.off_valid = o;     o = al(o + (size_t)cap);
+        L.off_twin = o;      o = al(o + sizeof(unsigned short) * (size_t)cap);
+        L.off_jv = o;        o = al(o + sizeof(float) * kJvDenseMax);
         L.off_gscratch = o;  o = al(o + lap_gscratch_bytes(d_max, cap));
         L.stride = o;
         return L;
@@ -84,6 +96,8 @@ struct OcStream {
     float* recs;
     float4* ocm;               // per-frame scratch, indexed by track POSITION
     unsigned char* valid;
+    unsigned short* twin;      // [cap] slot of the bit-identical twin spawned from the same detection, kNoTwin = none
+    float* jv_dense;           // [kJvDenseMax] dense cost matrix of the exact-tie path
     unsigned char* gscratch;
     __device__ __forceinline__ static OcStream at(unsigned char* base, const OcLayout& L) {
         OcStream s;
@@ -100,6 +114,8 @@ struct OcStream {
         s.recs = (float*)(base + L.off_recs);
         s.ocm = (float4*)(base + L.off_ocm);
         s.valid = base + L.off_valid;
+        s.twin = (unsigned short*)(base + L.off_twin);
+        s.jv_dense = (float*)(base + L.off_jv);
         s.gscratch = base + L.off_gscratch;
         return s;
     }
@@ -134,6 +150,7 @@ struct OcSmem {
     unsigned* row_bits;         // [d_max / 32]
     unsigned* col_bits;         // [cap / 32]
     int* flags;                 // [4]
+    unsigned char* jv;          // working arrays of the dense LAPJV (aliases lap.scratch_a when that is big enough)
     BlockScratch* bs;
     LapWorkspace lap;
 };
@@ -152,6 +169,7 @@ MOT_HD constexpr size_t oc_smem_bytes(int cap, int d_max, int e_cap) {
     b += lap_align16(sizeof(int) * 4);
     b += lap_align16(sizeof(BlockScratch));
     b += lap_smem_bytes(d_max, cap, e_cap);
+    if (sizeof(int) * (size_t)e_cap < jv_work_bytes(kJvMax + 1)) b += lap_align16(jv_work_bytes(kJvMax + 1));
     return b;
 }
 
@@ -174,7 +192,9 @@ __device__ __forceinline__ void oc_carve(unsigned char* p, int cap, int d_max, i
     s.col_bits = (unsigned*)p;          p += lap_align16(sizeof(unsigned) * (size_t)((cap + 31) / 32));
     s.flags = (int*)p;                  p += lap_align16(sizeof(int) * 4);
     s.bs = (BlockScratch*)p;            p += lap_align16(sizeof(BlockScratch));
-    lap_carve(p, d_max, cap, e_cap, s.lap);
+    p = lap_carve(p, d_max, cap, e_cap, s.lap);
+    // the candidate-edge buffer is dead once block_lap has returned, which is exactly when the dense LAPJV runs
+    s.jv = (sizeof(int) * (size_t)e_cap >= jv_work_bytes(kJvMax + 1)) ? (unsigned char*)s.lap.scratch_a : p;
 }
 
 // KalmanBoxTracker::get_state / predict's return value (free convert_x_to_bbox, ocsort.cpp:172-181)
@@ -231,6 +251,8 @@ __device__ __forceinline__ void oc_update_pairs(const OcStream& st, const OcSmem
             o[0] = box.x; o[1] = box.y; o[2] = box.z; o[3] = box.w; o[4] = conf;   // :111-115
             const int e = slot * kOcRing + (age & (kOcRing - 1));
             st.ring_box[e] = box; st.ring_conf[e] = conf; st.ring_age[e] = age;
+            const unsigned short tw = st.twin[slot];          // an updated track stops being anybody's twin
+            if (tw != kNoTwin) { st.twin[tw] = kNoTwin; st.twin[slot] = kNoTwin; }
             st.det_ind[slot] = det;
             st.conf[slot] = conf;
             st.cls[slot] = (int)dets[(size_t)det * 6 + 5];
@@ -313,6 +335,22 @@ __device__ __forceinline__ void oc_spawn(const OcStream& st, OcSmem& sm, const f
     }
 }
 
+// The reference's dense LAPJV (jv_device.cuh) on the full n x m cost matrix pair(i, j); overwrites lap.row2col / col2row.
+// Requires n + m <= kJvMax.  All threads of the block must call.
+template <class Pair>
+__device__ __forceinline__ void oc_exact_assignment(const OcStream& st, OcSmem& sm, int n, int m, float thresh, Pair pair) {
+    const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
+    for (int e = tid; e < n * m; e += nt) st.jv_dense[e] = pair(e / m, e - (e / m) * m);
+    __syncthreads();
+    const JvWork w = jv_carve(sm.jv, kJvMax + 1);
+    if (tid == 0) st.hdr[kOHdrExactSolves] += 1;
+    if (tid < 32) warp_dense_lapjv(JvCost{st.jv_dense, n, m, m, (double)thresh / 2.0}, n + m, w);
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) { const int j = w.x[i]; sm.lap.row2col[i] = (short)(j < m ? j : -1); }     // lap_solver.hpp:326-331
+    for (int j = tid; j < m; j += nt) { const int i = w.y[j]; sm.lap.col2row[j] = (short)(i < n ? i : -1); }
+    __syncthreads();
+}
+
 template <int CAP, int DMAX>
 __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, OcSmem& sm, const float* dets, int n_det_in,
                                          float* out, int* n_out) {
@@ -391,7 +429,12 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
     const int n_trk = block_compact(n_trk0, 0, sm.bs, [&](int k) { return sm.trk_flag[k] == 0; },
                                     [&](int k, int pos) { sm.list_a[pos] = st.list[k]; });
     n_free = block_compact(n_trk0, n_free, sm.bs, [&](int k) { return sm.trk_flag[k] != 0; },
-                           [&](int k, int pos) { st.freel[pos] = st.list[k]; });
+                           [&](int k, int pos) {
+                               const int slot = st.list[k];
+                               const unsigned short tw = st.twin[slot];
+                               if (tw != kNoTwin) { st.twin[tw] = kNoTwin; st.twin[slot] = kNoTwin; }
+                               st.freel[pos] = (unsigned short)slot;
+                           });
 
     if (n_trk == 0) {
         // ---- no tracks: every high detection starts one, nothing is emitted (:367-384)
@@ -399,7 +442,7 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
         if (n_new > n_free) { n_new = n_free; if (tid == 0) atomicOr(&st.hdr[kOHdrError], 1); }
         oc_spawn(st, sm, dets, n_new, 0, n_free, id_base, [&](int k) { return (int)sm.high[k]; });
         __syncthreads();
-        for (int k = tid; k < n_new; k += nt) st.list[k] = sm.list_a[k];
+        for (int k = tid; k < n_new; k += nt) { st.list[k] = sm.list_a[k]; st.twin[sm.list_a[k]] = kNoTwin; }
         if (tid == 0) {
             *n_out = 0;
             st.hdr[kOHdrTracks] = n_new;
@@ -422,7 +465,7 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
         float pc = -1.0f;
         if (st.hits[slot] > 0) prev = oc_k_previous_obs(st, slot, st.age[slot], delta_t, pc);
         st.ocm[k] = make_float4(xdiv(xadd(prev.x, prev.z), 2.0f), xdiv(xadd(prev.y, prev.w), 2.0f), o[5], o[6]);
-        st.valid[k] = (pc >= 0.0f) ? 1 : 0;
+        st.valid[k] = (unsigned char)(((pc >= 0.0f) ? 1 : 0) | ((st.twin[slot] != kNoTwin) ? 2 : 0));
         sm.trk_flag[k] = 0;
     }
     for (int i = tid; i < n_high; i += nt) sm.det_flag[i] = 0;
@@ -435,7 +478,19 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
                 sm.row_bits, sm.col_bits, sm.pair_det /* row_hit */, sm.flags};
     block_lap(sm.lap, n_high, n_trk, DMAX, CAP, -thr, ocm);
     const bool trivial = sm.flags[0] != 0 && sm.flags[1] == 0;   // max row sum == 1 && max column sum == 1 (:676-680)
+    // the optimum can only be non-unique if it uses a track that still has a bit-identical twin (the twin is then an
+    // equally good column); bit 1 of valid[] marks such tracks
+    if (!trivial && n_high + n_trk <= kJvMax)
+        for (int j = tid; j < n_trk; j += nt)
+            if (sm.lap.col2row[j] >= 0 && (st.valid[j] & 2)) sm.flags[2] = 1;
     __syncthreads();
+    const bool exact1 = sm.flags[2] != 0;
+    __syncthreads();
+    if (exact1) {
+        // a twin track is a candidate: the optimum may be non-unique, so redo the assignment with the reference's own
+        // dense LAPJV over the full (n_high x n_trk) cost matrix (associate :690-700 -> linear_assignment)
+        oc_exact_assignment(st, sm, n_high, n_trk, -thr, [&](int i, int j) { return ocm.pair(i, j); });
+    }
     if (trivial) {
         // every pair with iou > thr is a match, nothing else is (:681-689)
         for (int j = tid; j < n_trk; j += nt) sm.lap.col2row[j] = -1;
@@ -491,8 +546,18 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
     if (a.p.use_byte && n_second > 0 && n_ut > 0) {
         if (tid == 0) sm.flags[0] = 0;
         __syncthreads();
+        if (tid == 0) sm.flags[2] = 0;
+        __syncthreads();
         NegIouCost cost{sm.det_box, sm.second, sm.trk_box, sm.ut, thr, prune_rest, sm.flags};
         block_lap(sm.lap, n_second, n_ut, DMAX, CAP, -thr, cost);
+        if (sm.flags[0] != 0 && n_second + n_ut <= kJvMax)
+            for (int p = tid; p < n_ut; p += nt)
+                if (sm.lap.col2row[p] >= 0 && (st.valid[sm.ut[p]] & 2)) sm.flags[2] = 1;
+        __syncthreads();
+        if (sm.flags[2] != 0) {
+            __syncthreads();
+            oc_exact_assignment(st, sm, n_second, n_ut, -thr, [&](int i, int j) { return cost.pair(i, j); });
+        }
         if (sm.flags[0] != 0) {                                   // max_iou > threshold (:445-446)
             for (int r = tid; r < n_second; r += nt) {
                 const int c = sm.lap.row2col[r];
@@ -550,6 +615,20 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
     }
     oc_spawn(st, sm, dets, n_new, n_trk, n_free, id_base, [&](int k) { return (int)sm.ud[k]; });
     __syncthreads();
+    {
+        // a detection that sits twice in the list has just spawned two bit-identical tracks: link them as twins
+        int* first_pos = sm.lap.row_label;          // [DMAX] ints, idle outside block_lap
+        int* last_pos = sm.lap.scratch_b;           // [DMAX] ints
+        for (int k = tid; k < n_new; k += nt) { first_pos[sm.ud[k]] = 0x7fffffff; last_pos[sm.ud[k]] = -1; }
+        __syncthreads();
+        for (int k = tid; k < n_new; k += nt) { atomicMin(&first_pos[sm.ud[k]], k); atomicMax(&last_pos[sm.ud[k]], k); }
+        __syncthreads();
+        for (int k = tid; k < n_new; k += nt) {
+            const int d = sm.ud[k], f = first_pos[d], l = last_pos[d];
+            st.twin[sm.list_a[n_trk + k]] = (f != l) ? sm.list_a[n_trk + (k == f ? l : f)] : kNoTwin;
+        }
+        __syncthreads();
+    }
     const int n_all = n_trk + n_new;
     n_free -= n_new;
 
@@ -574,7 +653,12 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
     const int n_keep = block_compact(n_all, 0, sm.bs, [&](int k) { return st.tsu[sm.list_a[k]] <= max_age; },
                                      [&](int k, int pos) { st.list[pos] = sm.list_a[k]; });
     n_free = block_compact(n_all, n_free, sm.bs, [&](int k) { return st.tsu[sm.list_a[k]] > max_age; },
-                           [&](int k, int pos) { st.freel[pos] = sm.list_a[k]; });
+                           [&](int k, int pos) {
+                               const int slot = sm.list_a[k];
+                               const unsigned short tw = st.twin[slot];
+                               if (tw != kNoTwin) { st.twin[tw] = kNoTwin; st.twin[slot] = kNoTwin; }
+                               st.freel[pos] = (unsigned short)slot;
+                           });
     if (tid == 0) {
         if (n_rows > a.ld_out) atomicOr(&st.hdr[kOHdrError], 4);
         *n_out = n_rows < a.ld_out ? n_rows : a.ld_out;

@@ -217,7 +217,7 @@ Assoc associate(const std::vector<float>& dets5, int n_dets, const std::vector<f
         } else {                                                               // :690-712
             *used_lap = 1;
             std::vector<int> r2c(n_dets), c2r(n_trks);
-            if (tie_mode == 0)
+            if (tie_mode == 0 || (tie_mode == 2 && n_dets + n_trks <= 384))
                 orc_linear_assignment(cost.data(), n_dets, n_trks, n_trks, -iou_threshold, r2c.data(), c2r.data());
             else   // exact ties (bit-identical twin tracks) resolved towards the higher column, as the CUDA kernel does
                 orc_linear_assignment_biased(cost.data(), n_dets, n_trks, n_trks, -iou_threshold, r2c.data(), c2r.data());
@@ -249,7 +249,8 @@ struct OrcOcSort {
     int frame_count = 0;
     int id_counter = 0;
     int last_sizes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int tie_mode = 0;                           // 0 = the reference's LAPJV scan order, 1 = prefer the higher column
+    int tie_mode = 0;                           // 0 = the reference's LAPJV scan order, 1 = prefer the higher column,
+                                                // 2 = the CUDA kernel's policy: 0 while rows + columns <= 384, else 1
     bool capture = false;                       // tests: keep the first-association cost matrix of the last update()
     std::vector<float> last_cost;
     std::vector<KalmanBoxTracker> tracks;
@@ -339,7 +340,8 @@ int orc_ocsort_update(OrcOcSort* s, const float* dets, int n, float* out, int ou
             std::vector<float> cost(iou.size());
             for (size_t k = 0; k < iou.size(); ++k) cost[k] = -iou[k];
             std::vector<int> r2c(n_second), c2r(nu);
-            if (s->tie_mode == 0) orc_linear_assignment(cost.data(), n_second, nu, nu, -s->iou_threshold, r2c.data(), c2r.data());
+            if (s->tie_mode == 0 || (s->tie_mode == 2 && n_second + nu <= 384))
+                orc_linear_assignment(cost.data(), n_second, nu, nu, -s->iou_threshold, r2c.data(), c2r.data());
             else orc_linear_assignment_biased(cost.data(), n_second, nu, nu, -s->iou_threshold, r2c.data(), c2r.data());
             std::vector<int> gone;
             for (int j = 0; j < n_second; ++j) {
@@ -372,7 +374,8 @@ int orc_ocsort_update(OrcOcSort* s, const float* dets, int n, float* out, int ou
             std::vector<float> cost(iou.size());
             for (size_t k = 0; k < iou.size(); ++k) cost[k] = -iou[k];
             std::vector<int> r2c(nd), c2r(nu);
-            if (s->tie_mode == 0) orc_linear_assignment(cost.data(), nd, nu, nu, -s->iou_threshold, r2c.data(), c2r.data());
+            if (s->tie_mode == 0 || (s->tie_mode == 2 && nd + nu <= 384))
+                orc_linear_assignment(cost.data(), nd, nu, nu, -s->iou_threshold, r2c.data(), c2r.data());
             else orc_linear_assignment_biased(cost.data(), nd, nu, nu, -s->iou_threshold, r2c.data(), c2r.data());
             std::vector<int> gone_d, gone_t;
             for (int k = 0; k < nd; ++k) {

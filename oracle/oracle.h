@@ -121,7 +121,8 @@ int orc_ocsort_update(OrcOcSort*, const float* dets, int n, float* out, int out_
 int orc_ocsort_count(const OrcOcSort*);
 /* tests: keep / fetch the first-association cost matrix (n_high x n_trk) of the last update() */
 void orc_ocsort_capture(OrcOcSort*, int on);
-/* 0 (default) = the reference's LAPJV tie-breaking; 1 = orc_linear_assignment_biased in the first association */
+/* 0 (default) = the reference's LAPJV tie-breaking; 1 = orc_linear_assignment_biased; 2 = the CUDA kernel's policy:
+ * the reference's LAPJV while rows + columns <= 384 (kJvMax in csrc/ocsort_kernel.cuh), the biased solver above that */
 void orc_ocsort_set_tie_mode(OrcOcSort*, int mode);
 int orc_ocsort_last_cost(const OrcOcSort*, float* out, int cap);
 /* [n_high, n_trk, used_lap, n_first_matches, n_left_dets, n_left_trks, n_rematched, n_spawned] of the last update() */

@@ -2,10 +2,13 @@
 sm_100a kernels through the C ABI (GPU) - reference src/trackers/ocsort.cpp.
 
 Ties.  The reference spawns bit-identical "twin" tracks (parity trap 8), so exactly tied
-assignment optima are systematic in OC-SORT.  The oracle has two modes: tie_mode=0 resolves them with
-the reference's LAPJV scan order (pinned to the real lap_solver.hpp), tie_mode=1 with the
-"prefer the higher column" infinitesimal the CUDA kernel uses.  Kernel parity is asserted bit for bit
-against tie_mode=1; test_tie_modes_differ_only_on_twin_ties measures how the two modes relate.
+assignment optima are systematic in OC-SORT.  Oracle modes: tie_mode=0 resolves them with the reference's LAPJV
+scan order (pinned to the real lap_solver.hpp); tie_mode=1 with the "prefer the higher column" infinitesimal of
+the sparse CUDA solver; tie_mode=2 is the CUDA kernel's policy - whenever a twin is an assignment candidate and
+rows + columns <= 384 the kernel re-solves the frame with the reference's own dense LAPJV (csrc/jv_device.cuh), so
+it equals tie_mode=0 there, and falls back to the tie_mode=1 rule for larger problems.  Kernel parity is asserted
+bit for bit against tie_mode=2 (== the reference for every problem of the small shape, where rows + columns <= 320);
+test_tie_modes_differ_only_on_twin_ties measures how modes 0 and 1 relate.
 """
 import ctypes as C
 
@@ -96,7 +99,7 @@ def test_ocsort_duplicate_spawn_trap(oracle):
 # ------------------------------------------------------------------ kernel logic under the emulator (CPU)
 def _sim_vs_oracle(oracle, seed, T, args, n_obj=40, canvas=(960, 540), threads=128):
     d, c = synth.stress_stream(seed, n_frames=T, n_obj=n_obj, canvas=canvas)
-    ref = oracle.OCSort(**args, tie_mode=1)
+    ref = oracle.OCSort(**args, tie_mode=2)
     sim = sim_lib.SimOCSort(1, args["det_thresh"], args["max_age"], args["min_hits"], args["iou_threshold"],
                             args["min_conf"], args["delta_t"], args["inertia"], args["use_byte"], args["q_xy_scaling"],
                             args["q_s_scaling"])
@@ -118,7 +121,7 @@ def _sim_vs_oracle(oracle, seed, T, args, n_obj=40, canvas=(960, 540), threads=1
 
 
 def test_ocsort_kernel_logic_under_emulator(oracle):
-    st = _sim_vs_oracle(oracle, 0, 110, OC_ARGS)
+    st = _sim_vs_oracle(oracle, 0, 110, OC_ARGS)          # frame 105 of this stream has a twin tie the two rules disagree on
     assert st[2] > 50 and st[6] > 0 and st[7] > 20          # assignments, re-matches and spawns all happened
     _sim_vs_oracle(oracle, 7, 70, {**OC_ARGS, "use_byte": True}, threads=64)
     _sim_vs_oracle(oracle, 8, 60, {**OC_ARGS, "use_byte": True, "inertia": 0.9})        # dense (unpruned) path
@@ -184,7 +187,7 @@ def _engine_vs_oracle(oracle, streams, args, cap, d_max, T_chunk=None, check_sta
     dets = np.stack([s[0] for s in streams], 1)
     counts = np.stack([s[1] for s in streams], 1).astype(np.int32)
     eng = api.Engine(_lib.TRACKER_OCSORT, S, cap, d_max, **args)
-    refs = [oracle.OCSort(**args, tie_mode=1) for _ in range(S)]
+    refs = [oracle.OCSort(**args, tie_mode=2) for _ in range(S)]
     T_chunk = T_chunk or T
     for t0 in range(0, T, T_chunk):
         t1 = min(T, t0 + T_chunk)
@@ -218,7 +221,7 @@ def test_gpu_ocsort_c2_shape_and_api_mirror(oracle, gpu):
     d = synth.bytetrack_stream(3, n_frames=45, n_clutter=24, n_low=40, config=4)   # 320 detections / frame
     streams = [(d, np.full(d.shape[0], d.shape[1], np.int32))]
     _engine_vs_oracle(oracle, streams, OC_ARGS, 1536, 512, T_chunk=15)
-    trk, ref = api.OCSort(), oracle.OCSort(tie_mode=1)
+    trk, ref = api.OCSort(), oracle.OCSort(tie_mode=2)
     dd, cc = synth.stress_stream(77, n_frames=50)
     for t in range(50):
         assert np.array_equal(trk.update(dd[t, :cc[t]], (540, 960)), ref.update(dd[t, :cc[t]]))
@@ -248,3 +251,14 @@ def test_gpu_ocsort_capacity_and_argument_errors(oracle, gpu):
         api.Engine(_lib.TRACKER_OCSORT, 1, 256, 64, **{**OC_ARGS, "delta_t": 9})     # observation ring holds 8 ages
     with pytest.raises(ValueError):
         api.Engine(_lib.TRACKER_OCSORT, 1, 4096, 4096, **OC_ARGS)                    # beyond the largest built shape
+
+
+def test_small_shape_kernel_equals_reference_tie_breaking(oracle):
+    """rows + columns <= 320 for the 256-track / 64-detection shape, so the kernel's policy IS the reference's LAPJV:
+    tie_mode 2 and tie_mode 0 are the same tracker there, frame after frame, on streams full of twin ties."""
+    for seed in (0, 3):
+        d, c = synth.stress_stream(seed, n_frames=150, n_obj=40)
+        a, b = oracle.OCSort(**OC_ARGS, tie_mode=0), oracle.OCSort(**OC_ARGS, tie_mode=2)
+        for t in range(150):
+            assert np.array_equal(a.update(d[t, :c[t]]), b.update(d[t, :c[t]]))
+        assert np.array_equal(a.dump(), b.dump())
