@@ -172,6 +172,28 @@ int mot_cost_ocm(const float* dets5, int n_dets, const float* trks4, const float
  * split (fp32-level accuracy), out row-major ld. */
 int mot_cost_cosine(const float* t, int n, const float* d, int m, int dim, float* out, int ld, void* stream);
 
+/* ---- StrongSORT cost builders (reference src/trackers/strongsort.cpp) ------------------------------- */
+/* NearestNeighborDistanceMetric::distance, metric "cosine" (strongsort.cpp:240-334): samples (n_samples x dim) = every
+ * target's gallery rows, seg[n_samples] = the target (output row) each sample belongs to, feats (m x dim) the raw
+ * detection features.  out (n_targets x m, ld) = min over a target's samples of 1 - (s/|s|).(f/|f|); a target without
+ * samples gets 1e5 (:271).  tcgen05 contraction (3-term bf16 split, fp32 accumulate) with the per-target minimum folded
+ * into the GEMM epilogue. */
+int mot_cost_nn_cosine(const float* samples, const int* seg, int n_samples, int n_targets, const float* feats, int m,
+                       int dim, float* out, int ld, void* stream);
+/* linear_assignment::gate_cost_matrix (strongsort.cpp:451-492) IN PLACE on cost (n_tracks x n_meas, ld): entries whose
+ * gating distance (KalmanFilterXYAH::gating_distance "maha", kalman_filter.cpp:148-176) exceeds 9.4877 become gated_cost
+ * (INFTY_COST = 1e5 in the reference), then cost = mc_lambda * cost + (1 - mc_lambda) * gating distance.
+ * recs = XYAH records (72 floats per track), meas4 = (n_meas x 4) xyah rows (Detection::to_xyah). */
+int mot_cost_gate(float* cost, int ld, const float* recs, int n_tracks, const float* meas4, int n_meas, float mc_lambda,
+                  float gated_cost, int only_position, void* stream);
+/* iou_matching::iou_cost (strongsort.cpp:502-585): 1 - IoU of tlwh boxes (union > 1e-6 guard); tsu (nullable) = the
+ * tracks' time_since_update, rows with tsu > 1 are 1e5.  out (n x m, ld). */
+int mot_cost_iou_tlwh(const float* trk_tlwh, const int* tsu, int n, const float* det_tlwh, int m, float* out, int ld,
+                      void* stream);
+/* KalmanFilterXYSR::apply_affine_correction (src/motion/kalman_filters/xysr_kf.cpp:114-141) on n XYSR records in place:
+ * the camera-motion warp of DeepOC-SORT.  m2x2 (row-major) and t2 are HOST pointers. */
+int mot_kf_xysr_affine(float* recs, long long n, const float* m2x2, const float* t2, void* stream);
+
 /* utils::linear_assignment (src/utils/matching.cpp:14-60) + LAPSolver (include/motcpp/association/
  * lap_solver.hpp:251-332): cost row-major (n x m), pairs with cost > thresh never match.
  * row2col[n] / col2row[m]: -1 = unmatched.  Batched: problem p reads cost + p*stride_cost and

@@ -157,6 +157,74 @@ def embedding_distance(track_features, det_features, metric: str = "cosine") -> 
     return np.ascontiguousarray(do.download()[:, :m])
 
 
+# ------------------------------------------------------------------ StrongSORT cost builders (strongsort.cpp)
+INFTY_COST = 1e5          # linear_assignment::INFTY_COST (include/motcpp/trackers/strongsort.hpp)
+
+
+def nn_cosine_distance(samples, targets_of_samples, n_targets: int, features) -> np.ndarray:
+    """NearestNeighborDistanceMetric::distance, metric "cosine" (strongsort.cpp:240-334): samples (S,D) are the gallery
+    rows of all targets, targets_of_samples[s] the output row of sample s, features (M,D) the raw detection features
+    -> (n_targets, M) = min over a target's samples of 1 - cos; targets without samples get 1e5.  Tensor cores."""
+    smp = np.ascontiguousarray(samples, np.float32)
+    seg = np.ascontiguousarray(targets_of_samples, np.int32).reshape(-1)
+    f = np.ascontiguousarray(features, np.float32)
+    if smp.ndim != 2 or f.ndim != 2 or (smp.shape[0] and smp.shape[1] != f.shape[1]) or seg.shape[0] != smp.shape[0]:
+        raise ValueError("samples (S,D), targets_of_samples (S,), features (M,D) expected")
+    if seg.size and (seg.min() < 0 or seg.max() >= n_targets):
+        raise ValueError("targets_of_samples out of range")
+    m = f.shape[0]
+    if n_targets == 0 or m == 0:
+        return np.zeros((n_targets, m), np.float32)
+    _lib.require_gpu()
+    ld = (m + 3) // 4 * 4
+    ds, dg, df, do = DeviceArray.from_host(smp), DeviceArray.from_host(seg), DeviceArray.from_host(f), DeviceArray((n_targets, ld))
+    try:
+        check(load().mot_cost_nn_cosine(ds.ptr, dg.ptr, smp.shape[0], n_targets, df.ptr, m, f.shape[1], do.ptr, ld, None))
+    except MotError as e:
+        _raise(e)
+    return np.ascontiguousarray(do.download()[:, :m])
+
+
+def gate_cost_matrix(cost_matrix, means, covariances, measurements_xyah, mc_lambda: float, gated_cost: float = INFTY_COST,
+                     only_position: bool = False) -> np.ndarray:
+    """linear_assignment::gate_cost_matrix (strongsort.cpp:451-492): cost (N,M), the N tracks' XYAH means (N,8) and
+    covariances (N,8,8), the M detections as xyah rows -> gated + motion-blended cost (N,M)."""
+    c = np.ascontiguousarray(cost_matrix, np.float32)
+    mu = np.ascontiguousarray(means, np.float32).reshape(-1, 8)
+    cv = np.ascontiguousarray(covariances, np.float32).reshape(-1, 64)
+    z = np.ascontiguousarray(measurements_xyah, np.float32).reshape(-1, 4)
+    n, m = mu.shape[0], z.shape[0]
+    if c.shape != (n, m) or cv.shape[0] != n:
+        raise ValueError("cost_matrix must be (tracks x measurements)")
+    if n == 0 or m == 0:
+        return c.copy()
+    _lib.require_gpu()
+    dc, dr, dz = DeviceArray.from_host(c), DeviceArray.from_host(np.concatenate([mu, cv], axis=1)), DeviceArray.from_host(z)
+    try:
+        check(load().mot_cost_gate(dc.ptr, m, dr.ptr, n, dz.ptr, m, float(mc_lambda), float(gated_cost), int(only_position), None))
+    except MotError as e:
+        _raise(e)
+    return dc.download()
+
+
+def iou_cost_tlwh(track_tlwh, det_tlwh, time_since_update=None) -> np.ndarray:
+    """iou_matching::iou_cost (strongsort.cpp:502-585): 1 - IoU of tlwh boxes; rows with time_since_update > 1 = 1e5."""
+    a = np.ascontiguousarray(track_tlwh, np.float32).reshape(-1, 4)
+    b = np.ascontiguousarray(det_tlwh, np.float32).reshape(-1, 4)
+    n, m = a.shape[0], b.shape[0]
+    if n == 0 or m == 0:
+        return np.zeros((n, m), np.float32)
+    _lib.require_gpu()
+    ld = (m + 3) // 4 * 4
+    da, db, do = DeviceArray.from_host(a), DeviceArray.from_host(b), DeviceArray((n, ld))
+    dt = DeviceArray.from_host(np.ascontiguousarray(time_since_update, np.int32)) if time_since_update is not None else None
+    try:
+        check(load().mot_cost_iou_tlwh(da.ptr, dt.ptr if dt else None, n, db.ptr, m, do.ptr, ld, None))
+    except MotError as e:
+        _raise(e)
+    return np.ascontiguousarray(do.download()[:, :m])
+
+
 @dataclass
 class LinearAssignmentResult:
     """utils::LinearAssignmentResult (matching.hpp:32-36)."""
@@ -307,6 +375,17 @@ class KalmanFilterXYSR(_BatchedKF):
     """motion::KalmanFilterXYSR (xysr_kf.cpp), batched over tracks; state 7, covariance 7x7."""
     KIND = KF_XYSR
     NX = 7
+
+    def apply_affine_correction(self, mean, covariance, m, t):
+        """KalmanFilterXYSR::apply_affine_correction (xysr_kf.cpp:114-141) for a batch of states: m (2,2), t (2,)."""
+        single = np.ndim(mean) == 1
+        recs = self._pack(mean, covariance)
+        m2 = np.ascontiguousarray(m, np.float32).reshape(4)
+        t2 = np.ascontiguousarray(t, np.float32).reshape(2)
+        _lib.require_gpu()
+        dr = DeviceArray.from_host(recs)
+        check(load().mot_kf_xysr_affine(dr.ptr, recs.shape[0], m2.ctypes.data, t2.ctypes.data, None))
+        return self._unpack(dr.download(), single)
 
 
 # ------------------------------------------------------------------ tracker engine

@@ -794,6 +794,57 @@ int mot_cost_cosine(const float* t, int n, const float* d, int m, int dim, float
     return MOT_OK;
 }
 
+int mot_cost_nn_cosine(const float* samples, const int* seg, int n_samples, int n_targets, const float* feats, int m,
+                       int dim, float* out, int ld, void* stream) {
+    if (n_samples < 0 || n_targets < 0 || m < 0 || dim <= 0 || ld < m) return fail(MOT_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (n_targets == 0 || m == 0) return MOT_OK;
+    if ((n_samples > 0 && (!samples || !seg)) || !feats || !out) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
+    if (int rc = require_device()) return rc;
+    std::string err;
+    const int rc = mot::launch_nn_cosine(samples, seg, n_samples, n_targets, feats, m, dim, out, ld, (cudaStream_t)stream, err);
+    if (rc != MOT_OK) return fail(rc, "%s", err.c_str());
+    return MOT_OK;
+}
+
+int mot_cost_gate(float* cost, int ld, const float* recs, int n_tracks, const float* meas4, int n_meas, float mc_lambda,
+                  float gated_cost, int only_position, void* stream) {
+    if (n_tracks < 0 || n_meas < 0 || ld < n_meas) return fail(MOT_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (n_tracks == 0 || n_meas == 0) return MOT_OK;
+    if (!cost || !recs || !meas4) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
+    if (int rc = require_device()) return rc;
+    const int blocks = std::max(1, std::min((n_tracks + 7) / 8, sm_count() * 8));
+    mot::gate_cost_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(cost, ld, recs, n_tracks, meas4, n_meas, mc_lambda,
+                                                                    gated_cost, only_position);
+    MOT_CUDA(cudaGetLastError());
+    return MOT_OK;
+}
+
+int mot_cost_iou_tlwh(const float* trk_tlwh, const int* tsu, int n, const float* det_tlwh, int m, float* out, int ld,
+                      void* stream) {
+    if (n < 0 || m < 0 || ld < m) return fail(MOT_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (n == 0 || m == 0) return MOT_OK;
+    if (!trk_tlwh || !det_tlwh || !out) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
+    if (int rc = require_device()) return rc;
+    const int col_tiles = (m + mot::kCostTileCols - 1) / mot::kCostTileCols;
+    const int row_groups = (n + mot::kCostTileRows - 1) / mot::kCostTileRows;
+    dim3 grid((unsigned)std::min(row_groups, sm_count() * 8), (unsigned)std::min(col_tiles, 64));
+    mot::iou_tlwh_cost_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(trk_tlwh, tsu, n, det_tlwh, m, out, ld);
+    MOT_CUDA(cudaGetLastError());
+    return MOT_OK;
+}
+
+int mot_kf_xysr_affine(float* recs, long long n, const float* m2x2, const float* t2, void* stream) {
+    if (n < 0) return fail(MOT_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (n == 0) return MOT_OK;
+    if (!recs || !m2x2 || !t2) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
+    if (int rc = require_device()) return rc;
+    const mot::Affine6 a{m2x2[0], m2x2[1], m2x2[2], m2x2[3], t2[0], t2[1]};      // HOST pointers: six scalars
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)sm_count() * 8));
+    mot::kf_xysr_affine_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(recs, n, a);
+    MOT_CUDA(cudaGetLastError());
+    return MOT_OK;
+}
+
 int mot_lap_batch_device(const float* cost, long long stride_cost, int n_problems, const int* n_rows,
                          const int* n_cols, int n, int m, int ld, float thresh, int* row2col, int* col2row,
                          void* stream) {

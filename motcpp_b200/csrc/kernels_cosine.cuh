@@ -178,7 +178,7 @@ template <int kBlockN>
 __global__ void __launch_bounds__(kThreads, 1)
 cosine_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int n, int m,
                    int kp, const float* __restrict__ norm_t, const float* __restrict__ norm_d, float* __restrict__ out,
-                   int ld, int tiles_m, int tiles_total) {
+                   int ld, int tiles_m, int tiles_total, const int* __restrict__ row_seg) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B: 1024-B aligned
     unsigned char* tiles = smem;
@@ -274,7 +274,36 @@ cosine_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[as]);
                 }
-                if (row < n) {
+                if (row_seg != nullptr) {
+                    // nearest-neighbour mode (NearestNeighborDistanceMetric::distance, strongsort.cpp:240-334): rows are
+                    // gallery samples, out[row_seg[row]][col] = min over the rows of a target of 1 - cos, kept as
+                    // order-preserving int keys.  A 32-row slab that lies inside one target (the common case: galleries
+                    // hold up to `budget` = 100 rows) is reduced with redux.sync first: 32 atomics per 32 x 32 block.
+                    const bool valid = row < n;
+                    const int seg = valid ? row_seg[row] : -1;
+                    const unsigned vm = __ballot_sync(0xffffffffu, valid);
+                    if (vm != 0u) {
+                        const int seg0 = __shfl_sync(0xffffffffu, seg, __ffs(vm) - 1);
+                        const bool uniform = __all_sync(0xffffffffu, !valid || seg == seg0) && seg0 >= 0;
+                        const float tnn = (tn > 1e-10f) ? tn : 1.0f;            // rows with |x| <= 1e-10 stay unnormalised (:318-329)
+                        int* okeys = reinterpret_cast<int*>(out);
+                        int mine = 0x7fffffff;
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) {
+                            const float dnv = dn[c0 + q];
+                            const float v = __fsub_rn(1.0f, __fdividef(__uint_as_float(r[q]), __fmul_rn(tnn, (dnv > 1e-10f) ? dnv : 1.0f)));
+                            const int bits = __float_as_int(v);
+                            const int key = valid ? ((bits >= 0) ? bits : (bits ^ 0x7fffffff)) : 0x7fffffff;
+                            if (uniform) {
+                                const int red = __reduce_min_sync(0xffffffffu, key);
+                                if (lane == q) mine = red;
+                            } else if (valid && seg >= 0 && n0 + c0 + q < m) {
+                                atomicMin(okeys + (size_t)seg * ld + n0 + c0 + q, key);
+                            }
+                        }
+                        if (uniform && n0 + c0 + lane < m) atomicMin(okeys + (size_t)seg0 * ld + n0 + c0 + lane, mine);
+                    }
+                } else if (row < n) {
                     float* orow = out + (size_t)row * ld + n0 + c0;
 #pragma unroll
                     for (int q = 0; q < 32; q += 4) {
@@ -340,7 +369,7 @@ inline bool make_map(CUtensorMap* map, const void* base, int rows, int kp, int b
 
 // returns a mot_status value; err receives the message on failure
 inline int launch_cosine(const float* t, int n, const float* d, int m, int dim, float* out, int ld, cudaStream_t st,
-                         std::string& err) {
+                         std::string& err, const int* row_seg = nullptr) {
     using namespace cosine;
     const int dp = (dim + kBlockK - 1) / kBlockK * kBlockK;
     const int kp = 6 * dp;
@@ -392,17 +421,52 @@ inline int launch_cosine(const float* t, int n, const float* d, int m, int dim, 
     if (block_n == 256) {
         const int total = tiles_m * ((m + 255) / 256);
         cosine_gemm_kernel<256><<<std::min(total, n_sm), kThreads, smem_bytes(256), st>>>(map_a, map_b, n, m, kp, tn, dn, out, ld,
-                                                                                        tiles_m, total);
+                                                                                        tiles_m, total, row_seg);
     } else if (block_n == 128) {
         const int total = tiles_m * ((m + 127) / 128);
         cosine_gemm_kernel<128><<<std::min(total, n_sm), kThreads, smem_bytes(128), st>>>(map_a, map_b, n, m, kp, tn, dn, out, ld,
-                                                                                        tiles_m, total);
+                                                                                        tiles_m, total, row_seg);
     } else {
         const int total = tiles_m * ((m + 63) / 64);
         cosine_gemm_kernel<64><<<std::min(total, n_sm), kThreads, smem_bytes(64), st>>>(map_a, map_b, n, m, kp, tn, dn, out, ld,
-                                                                                      tiles_m, total);
+                                                                                      tiles_m, total, row_seg);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return fail("gemm launch", e);
+    return 0;
+}
+
+// ---------------------------------------------------------------- nearest-neighbour cosine (StrongSORT gallery)
+namespace cosine {
+__global__ void __launch_bounds__(256) nn_fill_kernel(int* __restrict__ keys, int n_targets, int m, int ld) {
+    const long long total = (long long)n_targets * m;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x)
+        keys[(size_t)(k / m) * ld + (k % m)] = 0x7fffffff;
+}
+// key -> float; a target that received no sample keeps the fill value and becomes 1e5 (strongsort.cpp:271)
+__global__ void __launch_bounds__(256) nn_decode_kernel(float* __restrict__ out, int n_targets, int m, int ld) {
+    const long long total = (long long)n_targets * m;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+        float* p = out + (size_t)(k / m) * ld + (k % m);
+        const int key = __float_as_int(*p);
+        *p = (key == 0x7fffffff) ? 1e5f : __int_as_float((key >= 0) ? key : (key ^ 0x7fffffff));
+    }
+}
+}  // namespace cosine
+
+// NearestNeighborDistanceMetric::distance with the cosine metric: samples (n_samples x dim) x feats (m x dim) on the
+// tensor cores, the per-target minimum folded into the GEMM epilogue.  out (n_targets x m, ld).
+inline int launch_nn_cosine(const float* samples, const int* seg, int n_samples, int n_targets, const float* feats, int m,
+                            int dim, float* out, int ld, cudaStream_t st, std::string& err) {
+    const long long total = (long long)n_targets * m;
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, 148 * 8));
+    cosine::nn_fill_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<int*>(out), n_targets, m, ld);
+    if (n_samples > 0) {
+        const int rc = launch_cosine(samples, n_samples, feats, m, dim, out, ld, st, err, seg);
+        if (rc != 0) return rc;
+    }
+    cosine::nn_decode_kernel<<<blocks, 256, 0, st>>>(out, n_targets, m, ld);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("mot_cost_nn_cosine: ") + cudaGetErrorString(e); return 2; }
     return 0;
 }
 

@@ -8,6 +8,7 @@
 #pragma once
 #include "cost_device.cuh"
 #include "ocm_device.cuh"
+#include "gate_device.cuh"
 
 namespace mot {
 
@@ -127,6 +128,70 @@ __global__ void __launch_bounds__(256) ocm_cost_kernel(const float* __restrict__
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
                         if (q + e < cn) { crow[q + e] = vc[e]; if (irow) irow[q + e] = vi[e]; }
+                }
+            }
+        }
+    }
+}
+
+// linear_assignment::gate_cost_matrix (reference src/trackers/strongsort.cpp:451-492) IN PLACE on cost (n_tracks x n_meas,
+// leading dimension ld): Mahalanobis gate (entries with gating distance > 9.4877 become gated_cost) followed by the
+// motion blend mc_lambda * cost + (1 - mc_lambda) * gating distance.  recs = XYAH records (72 floats per track),
+// meas4 = (n_meas x 4) xyah rows.  One warp per track row: lane 0's projection + Cholesky factor is broadcast, the 32
+// lanes then sweep the row with coalesced read-modify-writes.  8 B per pair of HBM traffic, ~45 exact-fp32 operations
+// (7 IEEE divisions) per pair: issue-bound, like iou_cost_kernel.
+__global__ void __launch_bounds__(256) gate_cost_kernel(float* __restrict__ cost, int ld, const float* __restrict__ recs,
+                                                        int n_tracks, const float* __restrict__ meas4, int n_meas,
+                                                        float mc_lambda, float gated_cost, int only_position) {
+    const int warps_per_cta = (int)blockDim.x >> 5;
+    const int lane = lane_id();
+    for (int i = (int)blockIdx.x * warps_per_cta + warp_id(); i < n_tracks; i += (int)gridDim.x * warps_per_cta) {
+        const GateRow g = gate_prepare(recs + (size_t)i * kRecFloats);     // same values in every lane (loads broadcast)
+        float* row = cost + (size_t)i * ld;
+        for (int j = lane; j < n_meas; j += 32) {
+            const float4 z = *reinterpret_cast<const float4*>(meas4 + (size_t)j * 4);
+            row[j] = gate_blend(row[j], gate_distance(g, z, only_position != 0), mc_lambda, gated_cost);
+        }
+    }
+}
+
+// iou_matching::iou_cost (reference src/trackers/strongsort.cpp:502-585): 1 - IoU of tlwh boxes with the reference's
+// `union > 1e-6` guard; rows whose time_since_update > 1 are INFTY_COST (:567-570).  Same tiling as iou_cost_kernel.
+__global__ void __launch_bounds__(256) iou_tlwh_cost_kernel(const float* __restrict__ trk, const int* __restrict__ tsu, int n,
+                                                            const float* __restrict__ det, int m, float* __restrict__ out,
+                                                            int ld) {
+    __shared__ float4 s_box[kCostTileCols];
+    const int tid = (int)threadIdx.x;
+    const int tx = tid & 31, ty = tid >> 5;
+    const int col_tiles = (m + kCostTileCols - 1) / kCostTileCols;
+    const int row_groups = (n + kCostTileRows - 1) / kCostTileRows;
+    const bool vec_ok = ((ld & 3) == 0) && ((((size_t)out) & 15) == 0);
+    for (int ct = (int)blockIdx.y; ct < col_tiles; ct += (int)gridDim.y) {
+        const int c0 = ct * kCostTileCols;
+        const int cn = min(kCostTileCols, m - c0);
+        __syncthreads();
+        for (int k = tid; k < cn; k += 256) s_box[k] = *reinterpret_cast<const float4*>(det + (size_t)(c0 + k) * 4);
+        __syncthreads();
+        for (int rg = (int)blockIdx.x; rg < row_groups; rg += (int)gridDim.x) {
+            const int i = rg * kCostTileRows + ty;
+            if (i >= n) continue;
+            const float4 rb = *reinterpret_cast<const float4*>(trk + (size_t)i * 4);
+            const bool stale = tsu != nullptr && tsu[i] > 1;
+            float* orow = out + (size_t)i * ld + c0;
+            for (int q = tx * 4; q < cn; q += 128) {
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = q + e;
+                    v[e] = 0.0f;
+                    if (j < cn) v[e] = stale ? kInftyCost : xsub(1.0f, iou_tlwh_pair(rb, s_box[j]));
+                }
+                if (vec_ok && q + 3 < cn) {
+                    *reinterpret_cast<float4*>(orow + q) = make_float4(v[0], v[1], v[2], v[3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (q + e < cn) orow[q + e] = v[e];
                 }
             }
         }

@@ -177,4 +177,34 @@ __global__ void __launch_bounds__(256) kf_gating_kernel(const float* __restrict_
     }
 }
 
+// KalmanFilterXYSR::apply_affine_correction (reference src/motion/kalman_filters/xysr_kf.cpp:114-141): the camera-motion
+// warp x[0:2] = m x[0:2] + t, x[4:6] = m x[4:6], P blocks (0,0), (4,4), (0,4) -> m B m^T, (4,0) = (0,4)^T, for n XYSR
+// records [x 7 | P 7x7] in place.  One thread per track (20 of the record's 56 floats change).  aff6 = [m00 m01 m10 m11 t0 t1].
+struct Affine6 { float m00, m01, m10, m11, t0, t1; };
+__global__ void __launch_bounds__(256) kf_xysr_affine_kernel(float* __restrict__ recs, long long n, Affine6 a) {
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        float* x = recs + k * kRecFloatsXYSR;
+        float* P = x + 7;
+        const float c0 = xadd(xmul(a.m00, x[0]), xmul(a.m01, x[1])), c1 = xadd(xmul(a.m10, x[0]), xmul(a.m11, x[1]));
+        const float v0 = xadd(xmul(a.m00, x[4]), xmul(a.m01, x[5])), v1 = xadd(xmul(a.m10, x[4]), xmul(a.m11, x[5]));
+        x[0] = xadd(c0, a.t0); x[1] = xadd(c1, a.t1);
+        x[4] = v0; x[5] = v1;
+        auto block = [&](int r0, int q0, float (&o)[4]) {
+            const float b00 = P[r0 * 7 + q0], b01 = P[r0 * 7 + q0 + 1], b10 = P[(r0 + 1) * 7 + q0], b11 = P[(r0 + 1) * 7 + q0 + 1];
+            const float a00 = xadd(xmul(a.m00, b00), xmul(a.m01, b10)), a01 = xadd(xmul(a.m00, b01), xmul(a.m01, b11));
+            const float a10 = xadd(xmul(a.m10, b00), xmul(a.m11, b10)), a11 = xadd(xmul(a.m10, b01), xmul(a.m11, b11));
+            o[0] = xadd(xmul(a00, a.m00), xmul(a01, a.m01)); o[1] = xadd(xmul(a00, a.m10), xmul(a01, a.m11));
+            o[2] = xadd(xmul(a10, a.m00), xmul(a11, a.m01)); o[3] = xadd(xmul(a10, a.m10), xmul(a11, a.m11));
+        };
+        float pp[4], vv[4], pv[4];
+        block(0, 0, pp);
+        block(4, 4, vv);
+        block(0, 4, pv);
+        P[0] = pp[0]; P[1] = pp[1]; P[7] = pp[2]; P[8] = pp[3];
+        P[32] = vv[0]; P[33] = vv[1]; P[39] = vv[2]; P[40] = vv[3];
+        P[4] = pv[0]; P[5] = pv[1]; P[11] = pv[2]; P[12] = pv[3];
+        P[28] = pv[0]; P[35] = pv[1]; P[29] = pv[2]; P[36] = pv[3];
+    }
+}
+
 }  // namespace mot

@@ -76,6 +76,21 @@ int orc_linear_assignment(const float* cost, int n, int m, int ld, float thresh,
  * resolved towards the higher column - the CUDA OC-SORT kernel's rule for bit-identical twin tracks. */
 int orc_linear_assignment_biased(const float* cost, int n, int m, int ld, float thresh, int* row2col, int* col2row);
 
+/* ---------------- StrongSORT cost builders (src/trackers/strongsort.cpp) + XYSR affine correction ------------ */
+/* NearestNeighborDistanceMetric::distance, "cosine" (:240-334): samples (n_samples x dim) with seg[s] = target row,
+ * feats (m x dim) raw; out (n_targets x m) = min over the target's samples of 1 - cos; no samples -> 1e5 */
+void orc_nn_cosine_distance(const float* samples, const int* seg, int n_samples, int n_targets, const float* feats,
+                            int m, int dim, float* out);
+/* linear_assignment::gate_cost_matrix (:451-492), in place; recs = XYAH records of 72 floats, meas (n_meas x 4) xyah */
+void orc_gate_cost_matrix(float* cost, int ld, const float* recs, int n_tracks, const float* meas, int n_meas,
+                          float mc_lambda, float gated_cost, int only_position);
+/* iou_matching::iou_cost (:502-585): tlwh boxes, tsu nullable (rows with tsu > 1 -> 1e5); out (n x m) */
+void orc_iou_cost_tlwh(const float* trk, const int* tsu, int n, const float* det, int m, float* out);
+/* min_cost_matching's clamp (:372-377): entries > max_distance -> max_distance + 1e-5 */
+void orc_clamp_cost(float* cost, int n, int m, int ld, float max_distance);
+/* KalmanFilterXYSR::apply_affine_correction (src/motion/kalman_filters/xysr_kf.cpp:114-141); m2 row-major 2x2 */
+void orc_kf_xysr_affine(float* x7, float* P49, const float* m2, const float* t2);
+
 /* ---------------- trackers (state machines) --------------------------------------------- */
 typedef struct OrcByteTrack OrcByteTrack;
 /* arguments follow ByteTrack's ctor (include/motcpp/trackers/bytetrack.hpp:97-110); the

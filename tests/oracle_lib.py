@@ -76,6 +76,11 @@ def lib() -> C.CDLL:
         L.orc_acosf.argtypes = [C.c_float]
         L.orc_acosf.restype = C.c_float
         L.orc_ocm_cost.argtypes = [f32p, C.c_int, f32p, f32p, f32p, C.c_int, C.c_float, f32p, f32p]
+        L.orc_nn_cosine_distance.argtypes = [f32p, i32p, C.c_int, C.c_int, f32p, C.c_int, C.c_int, f32p]
+        L.orc_gate_cost_matrix.argtypes = [f32p, C.c_int, f32p, C.c_int, f32p, C.c_int, C.c_float, C.c_float, C.c_int]
+        L.orc_iou_cost_tlwh.argtypes = [f32p, C.c_void_p, C.c_int, f32p, C.c_int, f32p]
+        L.orc_clamp_cost.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_float]
+        L.orc_kf_xysr_affine.argtypes = [f32p, f32p, f32p, f32p]
         L.orc_ocsort_create.argtypes = [C.c_float, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
                                         C.c_float, C.c_int, C.c_float, C.c_float]
         L.orc_ocsort_create.restype = C.c_void_p
@@ -315,6 +320,45 @@ class Sort:
         n = lib().orc_sort_update(self._h, dets, dets.shape[0], self._out, self._out.shape[0])
         assert n >= 0
         return self._out[:n].copy()
+
+
+def nn_cosine_distance(samples, seg, n_targets, feats):
+    """NearestNeighborDistanceMetric::distance "cosine" (strongsort.cpp:240-334) -> (n_targets, m)."""
+    samples, feats = _f32(samples), _f32(feats)
+    seg = np.ascontiguousarray(seg, np.int32)
+    out = np.zeros((n_targets, feats.shape[0]), np.float32)
+    if out.size:
+        lib().orc_nn_cosine_distance(samples.reshape(-1), seg, samples.shape[0], n_targets, feats.reshape(-1),
+                                     feats.shape[0], feats.shape[1], out)
+    return out
+
+
+def gate_cost_matrix(cost, means, covs, meas, mc_lambda, gated_cost=1e5, only_position=False):
+    """linear_assignment::gate_cost_matrix (strongsort.cpp:451-492); returns the gated copy."""
+    out = _f32(cost).copy()
+    n, m = out.shape
+    recs = np.ascontiguousarray(np.concatenate([_f32(means).reshape(n, 8), _f32(covs).reshape(n, 64)], axis=1))
+    if out.size:
+        lib().orc_gate_cost_matrix(out, m, recs.reshape(-1), n, _f32(meas).reshape(-1), m, float(mc_lambda),
+                                   float(gated_cost), int(only_position))
+    return out
+
+
+def iou_cost_tlwh(trk, det, tsu=None):
+    """iou_matching::iou_cost (strongsort.cpp:502-585)."""
+    trk, det = _f32(trk).reshape(-1, 4), _f32(det).reshape(-1, 4)
+    out = np.zeros((trk.shape[0], det.shape[0]), np.float32)
+    t = np.ascontiguousarray(tsu, np.int32) if tsu is not None else None
+    if out.size:
+        lib().orc_iou_cost_tlwh(trk, t.ctypes.data if t is not None else None, trk.shape[0], det, det.shape[0], out)
+    return out
+
+
+def kf_xysr_affine(x7, P, m2, t2):
+    """KalmanFilterXYSR::apply_affine_correction (xysr_kf.cpp:114-141) -> (x, P)."""
+    x, p = _f32(x7).copy(), _f32(P).reshape(-1).copy()
+    lib().orc_kf_xysr_affine(x, p, _f32(m2).reshape(-1), _f32(t2))
+    return x, p.reshape(7, 7)
 
 
 def ocm_cost(dets5, trks4, vel2, prev5, inertia):
