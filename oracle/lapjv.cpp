@@ -175,7 +175,7 @@ private:
 
 namespace {
 // biased: adds the tie-break infinitesimal -(64 j + (i j mod 64)) 2^-50 to every real entry (see orc_linear_assignment_biased)
-int solve_extended(const float* cost, int n, int m, int ld, float thresh, bool biased, int* row2col, int* col2row) {
+int solve_extended(const float* cost, int n, int m, int ld, float thresh, bool biased, int* row2col, int* col2row, int dup_first = 0) {
     for (int i = 0; i < n; ++i) row2col[i] = -1;
     for (int j = 0; j < m; ++j) col2row[j] = -1;
     if (n == 0 || m == 0) return 0;                                   // matching.cpp:20-28
@@ -188,6 +188,7 @@ int solve_extended(const float* cost, int n, int m, int ld, float thresh, bool b
             if (i < n && j < m) {
                 val = (double)cost[(size_t)i * ld + j];                   // matching.cpp:31 cast
                 if (biased) val += -(double)(64 * j + ((i * j) & 63)) * 0x1p-50;
+                if (dup_first > 0 && i >= dup_first) val += (double)(j + 1) * 0x1p-50;
             }
             else if (i >= n && j >= m) val = 0.0;
             else val = half;
@@ -224,4 +225,13 @@ extern "C" int orc_linear_assignment(const float* cost, int n, int m, int ld, fl
 extern "C" int orc_linear_assignment_biased(const float* cost, int n, int m, int ld, float thresh,
                                             int* row2col, int* col2row) {
     return solve_extended(cost, n, m, ld, thresh, true, row2col, col2row);
+}
+
+// NOT the reference's behaviour: rows i >= n_first (the second copies of StrongSORT's duplicated track rows, see
+// oracle/strongsort.cpp "q1") get + (j + 1) 2^-50 added in fp64.  Between exactly tied optima this gives a lone
+// candidate detection to the FIRST copy and, of two candidates, the lower-indexed one to the second copy - the CUDA
+// StrongSORT kernel's rule for problems too large for its on-device LAPJV.
+extern "C" int orc_linear_assignment_rowdup(const float* cost, int n, int m, int ld, float thresh, int n_first,
+                                            int* row2col, int* col2row) {
+    return solve_extended(cost, n, m, ld, thresh, false, row2col, col2row, n_first);
 }

@@ -91,6 +91,27 @@ void orc_clamp_cost(float* cost, int n, int m, int ld, float max_distance);
 /* KalmanFilterXYSR::apply_affine_correction (src/motion/kalman_filters/xysr_kf.cpp:114-141); m2 row-major 2x2 */
 void orc_kf_xysr_affine(float* x7, float* P49, const float* m2, const float* t2);
 
+/* NOT reference behaviour: + (j + 1) 2^-50 on rows i >= n_first (StrongSORT's duplicated track rows), see lapjv.cpp */
+int orc_linear_assignment_rowdup(const float* cost, int n, int m, int ld, float thresh, int n_first, int* row2col, int* col2row);
+
+/* ---------------- StrongSORT (src/trackers/strongsort.cpp; ECC warp = identity, embeddings passed in) -------- */
+typedef struct OrcStrongSort OrcStrongSort;
+/* the StrongSORT ctor arguments that reach the association (include/motcpp/trackers/strongsort.hpp:287-305) */
+OrcStrongSort* orc_strongsort_create(int max_age, float min_conf, float max_cos_dist, float max_iou_dist, int n_init,
+                                     int nn_budget, float mc_lambda, float ema_alpha);
+void orc_strongsort_destroy(OrcStrongSort*);
+void orc_strongsort_reset(OrcStrongSort*);
+/* dets (n x 6), embs (n x dim) or NULL; out rows [x1,y1,x2,y2,id,conf,cls,det_ind] */
+int orc_strongsort_update(OrcStrongSort*, const float* dets, int n, const float* embs, int dim, float* out, int out_cap);
+/* duplicated-row ties of the IoU stage: 0 = the reference's LAPJV, 1 = orc_linear_assignment_rowdup,
+ * 2 = the CUDA kernel's policy (LAPJV while rows + columns <= 384, rowdup above) */
+void orc_strongsort_set_tie_mode(OrcStrongSort*, int mode);
+/* [rows_a, cols_a, rows_b, cols_b, n_matches_a, n_matches_b, dup_first, n_spawned] of the last update() */
+void orc_strongsort_last_sizes(const OrcStrongSort*, int* out8);
+int orc_strongsort_count(const OrcStrongSort*);
+/* rows of [id,state,hits,age,tsu,conf,cls,det_ind,has_feat,n_samples,mean 8,cov 64] (82 floats) in track-list order */
+int orc_strongsort_dump(const OrcStrongSort*, float* rows82, float* feats, int dim, int cap_rows);
+
 /* ---------------- trackers (state machines) --------------------------------------------- */
 typedef struct OrcByteTrack OrcByteTrack;
 /* arguments follow ByteTrack's ctor (include/motcpp/trackers/bytetrack.hpp:97-110); the

@@ -76,6 +76,15 @@ def lib() -> C.CDLL:
         L.orc_acosf.argtypes = [C.c_float]
         L.orc_acosf.restype = C.c_float
         L.orc_ocm_cost.argtypes = [f32p, C.c_int, f32p, f32p, f32p, C.c_int, C.c_float, f32p, f32p]
+        L.orc_strongsort_create.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_float, C.c_float]
+        L.orc_strongsort_create.restype = C.c_void_p
+        L.orc_strongsort_destroy.argtypes = [C.c_void_p]
+        L.orc_strongsort_reset.argtypes = [C.c_void_p]
+        L.orc_strongsort_update.argtypes = [C.c_void_p, f32p, C.c_int, C.c_void_p, C.c_int, f32p, C.c_int]
+        L.orc_strongsort_set_tie_mode.argtypes = [C.c_void_p, C.c_int]
+        L.orc_strongsort_last_sizes.argtypes = [C.c_void_p, i32p]
+        L.orc_strongsort_count.argtypes = [C.c_void_p]
+        L.orc_strongsort_dump.argtypes = [C.c_void_p, f32p, C.c_void_p, C.c_int, C.c_int]
         L.orc_nn_cosine_distance.argtypes = [f32p, i32p, C.c_int, C.c_int, f32p, C.c_int, C.c_int, f32p]
         L.orc_gate_cost_matrix.argtypes = [f32p, C.c_int, f32p, C.c_int, f32p, C.c_int, C.c_float, C.c_float, C.c_int]
         L.orc_iou_cost_tlwh.argtypes = [f32p, C.c_void_p, C.c_int, f32p, C.c_int, f32p]
@@ -465,4 +474,50 @@ class BotSort:
     def last_sizes(self):
         s = np.zeros(8, np.int32)
         lib().orc_botsort_last_sizes(self._h, s)
+        return s
+
+
+class StrongSort:
+    """Oracle StrongSORT: the constructor arguments that reach the association, reference names and defaults
+    (include/motcpp/trackers/strongsort.hpp:287-305); ECC warp = identity, embeddings passed to update()."""
+
+    def __init__(self, max_age=30, min_conf=0.1, max_cos_dist=0.2, max_iou_dist=0.7, n_init=3, nn_budget=100,
+                 mc_lambda=0.98, ema_alpha=0.9, tie_mode=0):
+        self._h = lib().orc_strongsort_create(max_age, min_conf, max_cos_dist, max_iou_dist, n_init, nn_budget,
+                                              mc_lambda, ema_alpha)
+        lib().orc_strongsort_set_tie_mode(self._h, tie_mode)
+        self._out = np.zeros((8192, 8), np.float32)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_strongsort_destroy(self._h)
+            self._h = None
+
+    def reset(self):
+        lib().orc_strongsort_reset(self._h)
+
+    def update(self, dets, embs=None):
+        dets = _f32(dets).reshape(-1, 6)
+        if embs is not None and np.size(embs):
+            embs = _f32(embs).reshape(dets.shape[0], -1)
+            ep, dim = embs.ctypes.data_as(C.c_void_p), embs.shape[1]
+        else:
+            ep, dim = None, 0
+        n = lib().orc_strongsort_update(self._h, dets, dets.shape[0], ep, dim, self._out, self._out.shape[0])
+        assert n >= 0
+        return self._out[:n].copy()
+
+    def count(self):
+        return lib().orc_strongsort_count(self._h)
+
+    def dump(self, dim=0):
+        cap = max(1, self.count())
+        buf = np.zeros((cap, 82), np.float32)
+        feats = np.zeros((cap, max(dim, 1)), np.float32)
+        k = lib().orc_strongsort_dump(self._h, buf, feats.ctypes.data_as(C.c_void_p) if dim else None, dim, cap)
+        return (buf[:k], feats[:k]) if dim else buf[:k]
+
+    def last_sizes(self):
+        s = np.zeros(8, np.int32)
+        lib().orc_strongsort_last_sizes(self._h, s)
         return s

@@ -261,6 +261,43 @@ def main():
              frac_executed=6 * useful / ms[0] / 1e9 / TENSOR, bound="tensor",
              note="time includes the fp32->3xbf16 split pre-pass and stream-ordered allocation")
 
+    # ---------------- StrongSORT cost builders
+    for (NT, BUD, M, D) in ((256, 100, 512, 512), (1024, 100, 1024, 512)):
+        if not want("nn_cos") or (args.quick and NT > 256):
+            continue
+        S = NT * BUD
+        smp = torch.randn((S, D), device=dev)
+        seg = torch.arange(NT, device=dev, dtype=torch.int32).repeat_interleave(BUD).contiguous()
+        f = torch.randn((M, D), device=dev)
+        out = torch.empty((NT, M), device=dev)
+        ms = timeit(lambda: api.check(lib.mot_cost_nn_cosine(smp.data_ptr(), seg.data_ptr(), S, NT, f.data_ptr(), M, D,
+                                                             out.data_ptr(), M, st)))
+        useful = 2.0 * S * M * D
+        emit(f"nn_cosine_{NT}x{BUD}x{M}x{D}", ms, useful_flop=useful, executed_bf16_flop=6 * useful,
+             useful_tflops=useful / ms[0] / 1e9, executed_tflops=6 * useful / ms[0] / 1e9, peak_tflops=TENSOR,
+             frac_executed=6 * useful / ms[0] / 1e9 / TENSOR, bound="tensor",
+             note="gallery of NT targets x BUD samples against M detections: split pre-pass + tcgen05 GEMM with the "
+                  "per-target min in the epilogue + key decode; the gallery is re-split on every call")
+    if want("gate"):
+        NT, M = (2048, 2048) if args.quick else (8192, 8192)
+        z = torch.empty((NT, 4), device=dev)
+        z[:, 0].uniform_(0, 1920); z[:, 1].uniform_(0, 1080); z[:, 2].fill_(0.45); z[:, 3].uniform_(40, 260)
+        recs = torch.empty((NT, 72), device=dev)
+        api.check(lib.mot_kf_initiate(0, recs.data_ptr(), z.data_ptr(), NT, st))
+        api.check(lib.mot_kf_predict(0, recs.data_ptr(), None, NT, 1.0, 1.0, st))
+        meas = torch.empty((M, 4), device=dev)
+        meas[:, 0].uniform_(0, 1920); meas[:, 1].uniform_(0, 1080); meas[:, 2].fill_(0.45); meas[:, 3].uniform_(40, 260)
+        cost = torch.rand((NT, M), device=dev)
+        ms = timeit(lambda: api.check(lib.mot_cost_gate(cost.data_ptr(), M, recs.data_ptr(), NT, meas.data_ptr(), M, 0.98, 1e5, 0, st)))
+        byts = 8.0 * NT * M
+        emit(f"gate_cost_{NT}x{M}", ms, bytes=byts, gbs=byts / ms[0] / 1e6, peak_gbs=HBM, frac=byts / ms[0] / 1e6 / HBM, bound="hbm",
+             pairs_per_us=NT * M / ms[0] / 1e3, note="in place: 4 B read + 4 B written per pair; 7 IEEE divisions per pair")
+        tl = torch.empty((NT, 4), device=dev); tl.uniform_(0, 1000); dl = torch.empty((M, 4), device=dev); dl.uniform_(0, 1000)
+        out = torch.empty((NT, M), device=dev)
+        ms = timeit(lambda: api.check(lib.mot_cost_iou_tlwh(tl.data_ptr(), None, NT, dl.data_ptr(), M, out.data_ptr(), M, st)))
+        byts = 4.0 * NT * M
+        emit(f"iou_tlwh_cost_{NT}x{M}", ms, bytes=byts, gbs=byts / ms[0] / 1e6, peak_gbs=HBM, frac=byts / ms[0] / 1e6 / HBM, bound="hbm")
+
 
 if __name__ == "__main__":
     main()
