@@ -60,7 +60,8 @@ typedef enum mot_tracker_kind {
     MOT_TRACKER_SORT = 0,
     MOT_TRACKER_BYTETRACK = 1,
     MOT_TRACKER_OCSORT = 2,
-    MOT_TRACKER_BOTSORT = 3
+    MOT_TRACKER_BOTSORT = 3,
+    MOT_TRACKER_STRONGSORT = 4
 } mot_tracker_kind;
 
 typedef struct mot_engine_config {
@@ -86,6 +87,11 @@ typedef struct mot_engine_config {
     float track_high_thresh, track_low_thresh, new_track_thresh;
     float proximity_thresh, appearance_thresh;
     int fuse_first_associate, with_reid, emb_dim;
+    /* StrongSORT ctor (include/motcpp/trackers/strongsort.hpp:287-305); min_conf, max_age and emb_dim above are shared.
+     * nn_budget >= 1 is the gallery ring size per track. */
+    float max_cos_dist, max_iou_dist;
+    int n_init, nn_budget;
+    float mc_lambda, ema_alpha;
 } mot_engine_config;
 
 typedef struct mot_engine mot_engine;
@@ -118,7 +124,7 @@ int mot_engine_update_host_embs(mot_engine* e, int n_frames, const float* dets, 
 int mot_engine_update_device_embs(mot_engine* e, int n_frames, const float* d_dets, const int* d_n_dets, int ld_dets,
                                   const float* d_embs, float* d_out, int* d_n_out, int ld_out, void* stream);
 /* Per-stream sticky error bits since the last reset (0 = fine): 1 track capacity, 2 too many
- * detections, 4 output rows truncated, 8 Kalman fallback.  Synchronises.  flags may be NULL; the
+ * detections, 4 output rows truncated, 8 Kalman fallback, 16 StrongSORT candidate table full.  Synchronises.  flags may be NULL; the
  * return value is MOT_OK or the most severe condition as a mot_status. */
 int mot_engine_check(mot_engine* e, int* flags_per_stream);
 /* Introspection for tests: header ints of one stream [n_active,n_lost,n_free,id_counter,frame,err,
@@ -130,6 +136,9 @@ int mot_engine_stream_header(mot_engine* e, int stream_index, int* hdr16);
  * smoothed features, emb_dim floats per row. */
 int mot_engine_dump_bot(mot_engine* e, int stream_index, int which, float* rows82, float* feats, int cap_rows, int* n_rows);
 int mot_engine_dump_list(mot_engine* e, int stream_index, int which, float* rows78, int cap_rows, int* n_rows);
+/* StrongSORT engines: the track list (reference order) as rows of [id,state,hits,0,time_since_update,conf,cls,det_ind,
+ * has_feat,n_gallery_samples,mean 8,cov 64] (82 floats); feats (nullable) receives the smoothed features. */
+int mot_engine_dump_strong(mot_engine* e, int stream_index, float* rows82, float* feats, int cap_rows, int* n_rows);
 /* launch geometry actually used (for the bench's gpu_launches / roofline bookkeeping) */
 int mot_engine_info(mot_engine* e, int* threads_per_cta, int* smem_bytes, int* ctas, int* state_bytes_per_stream);
 

@@ -71,7 +71,7 @@ protected:
         mot_engine_info(engine_, &threads, &smem, &ctas, &bytes);
         max_dets_ = cfg.max_dets > 0 ? cfg.max_dets : 512;
         cap_ = cfg.track_capacity > 0 ? cfg.track_capacity : 1536;
-        emb_dim_ = cfg.kind == MOT_TRACKER_BOTSORT ? cfg.emb_dim : 0;
+        emb_dim_ = (cfg.kind == MOT_TRACKER_BOTSORT || cfg.kind == MOT_TRACKER_STRONGSORT) ? cfg.emb_dim : 0;
         dets_rm_.resize(static_cast<size_t>(max_dets_) * 6);
         out_rm_.resize(static_cast<size_t>(cap_) * 8);
         embs_rm_.resize(static_cast<size_t>(max_dets_) * static_cast<size_t>(emb_dim_));
@@ -214,6 +214,48 @@ private:
         c.new_track_thresh = new_thresh; c.track_buffer = track_buffer; c.match_thresh = match_thresh;
         c.proximity_thresh = prox; c.appearance_thresh = app; c.frame_rate = frame_rate;
         c.fuse_first_associate = fuse_first ? 1 : 0; c.with_reid = with_reid ? 1 : 0; c.emb_dim = emb_dim;
+        return c;
+    }
+};
+
+// motcpp::trackers::StrongSORT (include/motcpp/trackers/strongsort.hpp:287-305).  ReID inference and ECC camera-motion
+// estimation are image processing outside the association hot path: reid_weights must be empty, the embeddings are passed
+// to update() (the reference's own `embs` argument, strongsort.cpp:880-906) and the camera warp is the identity (what
+// motion::ECC::apply yields on a static / featureless image).  nn_budget is the per-track gallery ring size (>= 1).
+class StrongSORT : public BaseTracker {
+public:
+    StrongSORT(const std::string& reid_weights = "", bool use_half = false, bool use_gpu = false, float det_thresh = 0.3f,
+               int max_age = 30, int max_obs = 50, int min_hits = 3, float iou_threshold = 0.3f, bool per_class = false,
+               int nr_classes = 80, const std::string& asso_func = "iou", bool is_obb = false, float min_conf = 0.1f,
+               float max_cos_dist = 0.2f, float max_iou_dist = 0.7f, int n_init = 3, int nn_budget = 100,
+               float mc_lambda = 0.98f, float ema_alpha = 0.9f, int emb_dim = 0, int track_capacity = 0, int max_dets = 0,
+               int device = 0)
+        : BaseTracker(make(reid_weights, use_half, use_gpu, det_thresh, max_age, max_obs, min_hits, iou_threshold, per_class,
+                           nr_classes, asso_func, is_obb, min_conf, max_cos_dist, max_iou_dist, n_init, nn_budget, mc_lambda,
+                           ema_alpha, emb_dim, track_capacity, max_dets, device)) {}
+
+    // an empty frame still advances the tracker: predict + every track missed (strongsort.cpp:833-837)
+    Eigen::MatrixXf update(const Eigen::MatrixXf& dets, const cv::Mat& img,
+                           const Eigen::MatrixXf& embs = Eigen::MatrixXf()) override {
+        check_inputs(dets, img, embs);
+        validate_ = false;
+        return BaseTracker::update(dets, img, embs);
+    }
+
+private:
+    static mot_engine_config make(const std::string& reid_weights, bool, bool, float det_thresh, int max_age, int max_obs,
+                                  int min_hits, float iou_threshold, bool per_class, int, const std::string&, bool is_obb,
+                                  float min_conf, float max_cos_dist, float max_iou_dist, int n_init, int nn_budget,
+                                  float mc_lambda, float ema_alpha, int emb_dim, int track_capacity, int max_dets, int device) {
+        if (per_class || is_obb) throw std::invalid_argument("per_class / OBB are outside the accelerated hot path");
+        if (!reid_weights.empty())
+            throw std::invalid_argument("ReID inference is outside the accelerated hot path: pass embeddings to update()");
+        mot_engine_config c;
+        throw_on(mot_engine_default_config(MOT_TRACKER_STRONGSORT, &c));
+        c.n_streams = 1; c.track_capacity = track_capacity; c.max_dets = max_dets; c.device = device;
+        c.det_thresh = det_thresh; c.max_age = max_age; c.max_obs = max_obs; c.min_hits = min_hits;
+        c.iou_threshold = iou_threshold; c.min_conf = min_conf; c.max_cos_dist = max_cos_dist; c.max_iou_dist = max_iou_dist;
+        c.n_init = n_init; c.nn_budget = nn_budget; c.mc_lambda = mc_lambda; c.ema_alpha = ema_alpha; c.emb_dim = emb_dim;
         return c;
     }
 };

@@ -16,7 +16,7 @@ MOT_ERR_CAPACITY = 4
 MOT_ERR_NUMERIC = 5
 MOT_ERR_UNSUPPORTED = 6
 
-TRACKER_SORT, TRACKER_BYTETRACK, TRACKER_OCSORT, TRACKER_BOTSORT = 0, 1, 2, 3
+TRACKER_SORT, TRACKER_BYTETRACK, TRACKER_OCSORT, TRACKER_BOTSORT, TRACKER_STRONGSORT = 0, 1, 2, 3, 4
 KF_XYAH, KF_XYSR, KF_XYWH = 0, 1, 2
 
 
@@ -39,6 +39,8 @@ class EngineConfig(C.Structure):
         ("track_high_thresh", C.c_float), ("track_low_thresh", C.c_float), ("new_track_thresh", C.c_float),
         ("proximity_thresh", C.c_float), ("appearance_thresh", C.c_float),
         ("fuse_first_associate", C.c_int), ("with_reid", C.c_int), ("emb_dim", C.c_int),
+        ("max_cos_dist", C.c_float), ("max_iou_dist", C.c_float), ("n_init", C.c_int), ("nn_budget", C.c_int),
+        ("mc_lambda", C.c_float), ("ema_alpha", C.c_float),
     ]
 
 
@@ -65,6 +67,7 @@ SYMBOLS = {
     "mot_engine_update_host_embs": (_I, [_VP, _I, _VP, _VP, _I, _VP, _VP, _VP, _I]),
     "mot_engine_update_device_embs": (_I, [_VP, _I, _VP, _VP, _I, _VP, _VP, _VP, _I, _VP]),
     "mot_engine_dump_bot": (_I, [_VP, _I, _I, _VP, _VP, _I, C.POINTER(_I)]),
+    "mot_engine_dump_strong": (_I, [_VP, _I, _VP, _VP, _I, C.POINTER(_I)]),
     "mot_engine_check": (_I, [_VP, _VP]),
     "mot_engine_stream_header": (_I, [_VP, _I, _VP]),
     "mot_engine_dump_list": (_I, [_VP, _I, _I, _VP, _I, C.POINTER(_I)]),

@@ -390,7 +390,7 @@ class KalmanFilterXYSR(_BatchedKF):
 
 # ------------------------------------------------------------------ tracker engine
 _ERR_BITS = {1: "track capacity exceeded", 2: "too many detections", 4: "output rows truncated",
-             8: "Kalman update left the Cholesky path"}
+             8: "Kalman update left the Cholesky path", 16: "StrongSORT candidate table full"}
 
 
 class Engine:
@@ -510,6 +510,18 @@ class Engine:
         k = C.c_int()
         check(load().mot_engine_dump_bot(self._h, stream, which, buf.ctypes.data,
                                          feats.ctypes.data if (with_feats and dim) else None, n, C.byref(k)))
+        return (buf[:k.value], feats[:k.value]) if with_feats else buf[:k.value]
+
+    def dump_strong(self, stream: int, with_feats: bool = False):
+        """StrongSORT engines: the track list (reference vector order) as rows of [id, state, hits, 0, time_since_update,
+        conf, cls, det_ind, has_feat, n_gallery_samples, mean 8, cov 64] and optionally the smoothed features."""
+        n = max(int(self.header(stream)[0]), 1)
+        buf = np.zeros((n, 82), np.float32)
+        dim = int(self.cfg.emb_dim)
+        feats = np.zeros((n, max(dim, 1)), np.float32)
+        k = C.c_int()
+        check(load().mot_engine_dump_strong(self._h, stream, buf.ctypes.data,
+                                            feats.ctypes.data if (with_feats and dim) else None, n, C.byref(k)))
         return (buf[:k.value], feats[:k.value]) if with_feats else buf[:k.value]
 
     def info(self):
@@ -714,6 +726,66 @@ class BotSort:
                 raise ValueError("Detections and embeddings must have same number of rows")
             self._embs[0, 0, :n] = embs
             e = self._embs
+        self._engine.update(self._dets, np.array([[n]], np.int32), self._out, self._n_out, embs=e)
+        self._engine.check()
+        return self._out[0, 0, :int(self._n_out[0, 0])].copy()
+
+
+class StrongSort:
+    """motcpp::trackers::StrongSORT with the reference's positional constructor
+    (include/motcpp/trackers/strongsort.hpp:287-305).  The ReID network and ECC camera-motion estimation are image
+    processing outside the accelerated path: embeddings are passed to update() (the reference's `embs` argument) and the
+    camera warp is the identity (what motion::ECC yields on a static / featureless image).  One stream; for many
+    streams use Engine(TRACKER_STRONGSORT, ...)."""
+
+    def __init__(self, reid_weights="", use_half=False, use_gpu=False, det_thresh=0.3, max_age=30, max_obs=50,
+                 min_hits=3, iou_threshold=0.3, per_class=False, nr_classes=80, asso_func="iou", is_obb=False,
+                 min_conf=0.1, max_cos_dist=0.2, max_iou_dist=0.7, n_init=3, nn_budget=100, mc_lambda=0.98,
+                 ema_alpha=0.9, emb_dim=0, track_capacity=1536, max_dets=512, device=0):
+        if reid_weights:
+            raise ValueError("ReID inference is outside the accelerated hot path: pass embeddings to update()")
+        if per_class or is_obb:
+            raise ValueError("only per_class=False, is_obb=False are on the accelerated path")
+        self._engine = Engine(_lib.TRACKER_STRONGSORT, 1, track_capacity, max_dets, device, det_thresh=det_thresh,
+                              max_age=max_age, max_obs=max_obs, min_hits=min_hits, iou_threshold=iou_threshold,
+                              min_conf=min_conf, max_cos_dist=max_cos_dist, max_iou_dist=max_iou_dist, n_init=n_init,
+                              nn_budget=nn_budget, mc_lambda=mc_lambda, ema_alpha=ema_alpha, emb_dim=emb_dim)
+        self._dim = emb_dim
+        self._max_dets = self._engine.cfg.max_dets
+        self._cap = self._engine.cfg.track_capacity
+        self._dets = np.zeros((1, 1, self._max_dets, 6), np.float32)
+        self._embs = np.zeros((1, 1, self._max_dets, emb_dim), np.float32) if emb_dim else None
+        self._out = np.empty((1, 1, self._cap, 8), np.float32)
+        self._n_out = np.empty((1, 1), np.int32)
+
+    def reset(self):
+        self._engine.reset()
+
+    def update(self, dets, img, embs=None) -> np.ndarray:
+        dets = np.asarray(dets, np.float32)
+        if dets.ndim != 2:
+            dets = dets.reshape(0, 6) if dets.size == 0 else dets
+        # BaseTracker::check_inputs(dets, img, embs) (src/tracker.cpp:108-125)
+        if dets.shape[0] > 0 and dets.shape[1] not in (6, 7):
+            raise ValueError("Detections must have 6 (AABB) or 7 (OBB) columns")
+        if _Image(img).empty():
+            raise ValueError("Image cannot be empty")
+        if dets.shape[0] > 0 and dets.shape[1] == 7:
+            raise ValueError("OBB detections are outside the accelerated hot path")
+        n = dets.shape[0]
+        if embs is not None and np.size(embs) and np.shape(embs)[0] != n:
+            raise ValueError("Detections and embeddings must have same number of rows")
+        if n > self._max_dets:
+            raise ValueError(f"{n} detections exceed max_dets={self._max_dets}")
+        self._dets[0, 0, :n] = dets[:, :6] if n else 0
+        e = None
+        if n and embs is not None and np.size(embs) and self._dim:
+            embs = np.asarray(embs, np.float32)
+            if embs.shape != (n, self._dim):
+                raise ValueError(f"embeddings must be (n, {self._dim})")
+            self._embs[0, 0, :n] = embs
+            e = self._embs
+        # an empty frame still advances the tracker: predict + every track missed (strongsort.cpp:833-837)
         self._engine.update(self._dets, np.array([[n]], np.int32), self._out, self._n_out, embs=e)
         self._engine.check()
         return self._out[0, 0, :int(self._n_out[0, 0])].copy()

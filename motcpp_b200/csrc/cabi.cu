@@ -20,6 +20,7 @@
 #include "sort_kernel.cuh"
 #include "ocsort_kernel.cuh"
 #include "botsort_kernel.cuh"
+#include "strongsort_kernel.cuh"
 
 namespace {
 
@@ -77,6 +78,8 @@ struct mot_engine {
     mot::OcParams ocp;
     mot::BotLayout bot_layout;     // BoT-SORT slab layout (kind == BOTSORT; feature dimension is a run-time size)
     mot::BotParams botp;
+    mot::SsLayout ss_layout;       // StrongSORT slab layout (kind == STRONGSORT; dim and gallery budget are run-time sizes)
+    mot::SsParams ssp;
     float* d_embs = nullptr;  size_t embs_cap = 0;
     size_t stride = 0;             // bytes per stream slab (whichever layout is live)
     int threads = 0;
@@ -106,6 +109,8 @@ static int engine_reset_impl(mot_engine* e, int keep_ids) {
         mot::ocsort_reset_kernel<<<grid, 256, 0, e->streams[0]>>>(e->d_state, e->oc_layout, e->cfg.n_streams, keep_ids);
     else if (e->cfg.kind == MOT_TRACKER_BOTSORT)
         mot::botsort_reset_kernel<<<grid, 256, 0, e->streams[0]>>>(e->d_state, e->bot_layout, e->cfg.n_streams);
+    else if (e->cfg.kind == MOT_TRACKER_STRONGSORT)
+        mot::strongsort_reset_kernel<<<grid, 256, 0, e->streams[0]>>>(e->d_state, e->ss_layout, e->cfg.n_streams);
     else
         mot::bytetrack_reset_kernel<<<grid, 256, 0, e->streams[0]>>>(e->d_state, e->layout, e->cfg.n_streams, keep_ids);
     MOT_CUDA(cudaGetLastError());
@@ -224,6 +229,23 @@ static void bot_launch(int shape, int grid, size_t smem, cudaStream_t st, const 
 }
 static_assert(mot::kNumBotShapes == 3, "update the BoT-SORT dispatch switches");
 
+template <int I>
+static cudaError_t ss_set_smem(size_t bytes) {
+    constexpr mot::BtShape sh = mot::kSsShapes[I];
+    return cudaFuncSetAttribute(mot::strongsort_step_kernel<sh.cap, sh.d_max, sh.e_cap>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+template <int I>
+static void ss_launch_one(int grid, size_t smem, cudaStream_t st, const mot::SsArgs& a) {
+    constexpr mot::BtShape sh = mot::kSsShapes[I];
+    mot::strongsort_step_kernel<sh.cap, sh.d_max, sh.e_cap><<<grid, mot::kSsThreads, smem, st>>>(a);
+}
+static cudaError_t ss_prepare(int shape, size_t smem) { return shape == 0 ? ss_set_smem<0>(smem) : ss_set_smem<1>(smem); }
+static void ss_launch(int shape, int grid, size_t smem, cudaStream_t st, const mot::SsArgs& a) {
+    if (shape == 0) ss_launch_one<0>(grid, smem, st, a); else ss_launch_one<1>(grid, smem, st, a);
+}
+static_assert(mot::kNumSsShapes == 2, "update the StrongSORT dispatch switches");
+
 // one launch covering streams [s0, s1) for T frames, whatever the tracker kind
 static void engine_launch(mot_engine* e, int T, const float* dets, const int* nd, int ld_dets, const float* embs,
                           float* out, int* nout, int ld_out, int s0, int s1, cudaStream_t st);
@@ -240,7 +262,13 @@ static mot::BtArgs make_args(mot_engine* e, int T, const float* dets, const int*
 
 static void engine_launch(mot_engine* e, int T, const float* dets, const int* nd, int ld_dets, const float* embs,
                           float* out, int* nout, int ld_out, int s0, int s1, cudaStream_t st) {
-    if (e->cfg.kind == MOT_TRACKER_BOTSORT) {
+    if (e->cfg.kind == MOT_TRACKER_STRONGSORT) {
+        mot::SsArgs a{};
+        a.state = e->d_state; a.L = e->ss_layout; a.dets = dets; a.n_dets = nd; a.embs = embs; a.out = out; a.n_out = nout;
+        a.T = T; a.S = e->cfg.n_streams; a.ld_dets = ld_dets; a.ld_out = ld_out; a.s_begin = s0; a.s_end = s1;
+        a.p = e->ssp;
+        ss_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
+    } else if (e->cfg.kind == MOT_TRACKER_BOTSORT) {
         mot::BotArgs a{};
         a.state = e->d_state; a.L = e->bot_layout; a.dets = dets; a.n_dets = nd; a.embs = embs; a.out = out; a.n_out = nout;
         a.T = T; a.S = e->cfg.n_streams; a.ld_dets = ld_dets; a.ld_out = ld_out; a.s_begin = s0; a.s_end = s1;
@@ -337,11 +365,14 @@ int mot_engine_default_config(int kind, mot_engine_config* c) {
     c->track_high_thresh = 0.5f; c->track_low_thresh = 0.1f; c->new_track_thresh = 0.6f;
     c->proximity_thresh = 0.5f; c->appearance_thresh = 0.25f; c->fuse_first_associate = 0; c->with_reid = 1;
     c->emb_dim = 0;
+    // StrongSORT (strongsort.hpp:287-305)
+    c->max_cos_dist = 0.2f; c->max_iou_dist = 0.7f; c->n_init = 3; c->nn_budget = 100; c->mc_lambda = 0.98f; c->ema_alpha = 0.9f;
     switch (kind) {
         case MOT_TRACKER_SORT: c->max_age = 1; break;             // sort.hpp:70
         case MOT_TRACKER_BYTETRACK: break;
         case MOT_TRACKER_OCSORT: c->det_thresh = 0.2f; break;
         case MOT_TRACKER_BOTSORT: c->track_buffer = 30; break;
+        case MOT_TRACKER_STRONGSORT: break;
         default: return fail(MOT_ERR_INVALID_ARGUMENT, "unknown tracker kind %d", kind);
     }
     return MOT_OK;
@@ -350,9 +381,11 @@ int mot_engine_default_config(int kind, mot_engine_config* c) {
 int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     if (!cfg || !out) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
     *out = nullptr;
-    if (cfg->kind < MOT_TRACKER_SORT || cfg->kind > MOT_TRACKER_BOTSORT)
+    if (cfg->kind < MOT_TRACKER_SORT || cfg->kind > MOT_TRACKER_STRONGSORT)
         return fail(MOT_ERR_INVALID_ARGUMENT, "unknown tracker kind %d", cfg->kind);
-    if (cfg->kind == MOT_TRACKER_BOTSORT && (cfg->emb_dim < 0 || (cfg->emb_dim & 3)))
+    if (cfg->kind == MOT_TRACKER_STRONGSORT && (cfg->nn_budget < 1 || cfg->nn_budget > 4096))
+        return fail(MOT_ERR_UNSUPPORTED, "nn_budget %d is outside 1..4096 (gallery ring size; the reference's unlimited budget is not supported)", cfg->nn_budget);
+    if ((cfg->kind == MOT_TRACKER_BOTSORT || cfg->kind == MOT_TRACKER_STRONGSORT) && (cfg->emb_dim < 0 || (cfg->emb_dim & 3)))
         return fail(MOT_ERR_INVALID_ARGUMENT, "emb_dim %d must be a non-negative multiple of 4", cfg->emb_dim);
     if (cfg->n_streams <= 0) return fail(MOT_ERR_INVALID_ARGUMENT, "n_streams must be positive");
     if (cfg->kind == MOT_TRACKER_OCSORT && (cfg->delta_t < 1 || cfg->delta_t > mot::kOcRing))
@@ -362,7 +395,7 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     mot_engine* e = new mot_engine();
     e->cfg = *cfg;
     const bool is_sort = cfg->kind == MOT_TRACKER_SORT, is_oc = cfg->kind == MOT_TRACKER_OCSORT;
-    const bool is_bot = cfg->kind == MOT_TRACKER_BOTSORT;
+    const bool is_bot = cfg->kind == MOT_TRACKER_BOTSORT, is_ss = cfg->kind == MOT_TRACKER_STRONGSORT;
     if (e->cfg.track_capacity <= 0) e->cfg.track_capacity = 1536;
     if (e->cfg.max_dets <= 0) e->cfg.max_dets = 512;
     // round the request up to the nearest shape the kernel is instantiated for
@@ -370,6 +403,9 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     if (is_oc) {
         for (int i = 0; i < mot::kNumOcShapes; ++i)
             if (mot::kOcShapes[i].cap >= e->cfg.track_capacity && mot::kOcShapes[i].d_max >= e->cfg.max_dets) { e->shape = i; break; }
+    } else if (is_ss) {
+        for (int i = 0; i < mot::kNumSsShapes; ++i)
+            if (mot::kSsShapes[i].cap >= e->cfg.track_capacity && mot::kSsShapes[i].d_max >= e->cfg.max_dets) { e->shape = i; break; }
     } else if (is_bot) {
         for (int i = 0; i < mot::kNumBotShapes; ++i)
             if (mot::kBotShapes[i].cap >= e->cfg.track_capacity && mot::kBotShapes[i].d_max >= e->cfg.max_dets) { e->shape = i; break; }
@@ -381,11 +417,15 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
         const int tc = e->cfg.track_capacity, md = e->cfg.max_dets;
         delete e;
         return fail(MOT_ERR_INVALID_ARGUMENT, "track_capacity %d / max_dets %d exceed the largest built shape (%s)", tc, md,
-                    is_oc ? "3072 tracks / 2048 detections" : (is_bot ? "2048 tracks / 1024 detections" : "3072 tracks / 1024 detections"));
+                    is_oc ? "3072 tracks / 2048 detections" : (is_bot ? "2048 tracks / 1024 detections" : (is_ss ? "1536 tracks / 512 detections" : "3072 tracks / 1024 detections")));
     }
+    if (is_ss) {
+        e->cfg.track_capacity = mot::kSsShapes[e->shape].cap; e->cfg.max_dets = mot::kSsShapes[e->shape].d_max; e->e_cap = mot::kSsShapes[e->shape].e_cap;
+    } else {
     e->cfg.track_capacity = is_oc ? mot::kOcShapes[e->shape].cap : (is_bot ? mot::kBotShapes[e->shape].cap : mot::kBtShapes[e->shape].cap);
     e->cfg.max_dets = is_oc ? mot::kOcShapes[e->shape].d_max : (is_bot ? mot::kBotShapes[e->shape].d_max : mot::kBtShapes[e->shape].d_max);
     e->e_cap = is_oc ? mot::kOcShapes[e->shape].e_cap : (is_bot ? mot::kBotShapes[e->shape].e_cap : mot::kBtShapes[e->shape].e_cap);
+    }
     // BaseTracker ctor fix-up (src/tracker.cpp:37-39)
     if (e->cfg.max_age >= e->cfg.max_obs) e->cfg.max_obs = e->cfg.max_age + 5;
     e->layout = mot::BtLayout::make(e->cfg.track_capacity, e->cfg.max_dets);
@@ -421,9 +461,13 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     e->botp.fuse_first = cfg->fuse_first_associate;
     e->botp.with_reid = cfg->with_reid;
     e->botp.dim = cfg->emb_dim;
-    e->stride = is_sort ? e->sort_layout.stride : (is_oc ? e->oc_layout.stride : (is_bot ? e->bot_layout.stride : e->layout.stride));
-    e->threads = is_sort ? mot::kSortThreads : (is_oc ? mot::kOcThreads : (is_bot ? mot::kBotThreads : mot::kBtThreads));
-    e->smem_bytes = is_sort ? mot::sort_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap)
+    e->ss_layout = mot::SsLayout::make(e->cfg.track_capacity, e->cfg.max_dets, cfg->emb_dim, std::max(1, cfg->nn_budget));
+    e->ssp.min_conf = cfg->min_conf; e->ssp.max_cos_dist = cfg->max_cos_dist; e->ssp.max_iou_dist = cfg->max_iou_dist;
+    e->ssp.mc_lambda = cfg->mc_lambda; e->ssp.ema_alpha = cfg->ema_alpha; e->ssp.max_age = cfg->max_age;
+    e->ssp.n_init = cfg->n_init; e->ssp.budget = std::max(1, cfg->nn_budget); e->ssp.dim = cfg->emb_dim;
+    e->stride = is_ss ? e->ss_layout.stride : is_sort ? e->sort_layout.stride : (is_oc ? e->oc_layout.stride : (is_bot ? e->bot_layout.stride : e->layout.stride));
+    e->threads = is_ss ? mot::kSsThreads : is_sort ? mot::kSortThreads : (is_oc ? mot::kOcThreads : (is_bot ? mot::kBotThreads : mot::kBtThreads));
+    e->smem_bytes = is_ss ? mot::ss_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap) : is_sort ? mot::sort_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap)
                   : is_oc   ? mot::oc_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap)
                   : is_bot  ? mot::bot_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap)
                             : mot::bt_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap);
@@ -435,7 +479,7 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
         return fail(MOT_ERR_INVALID_ARGUMENT, "track_capacity/max_dets need %zu B of shared memory per CTA (limit %d)",
                     need, max_optin);
     }
-    MOT_CUDA(is_sort ? sort_prepare(e->shape, e->smem_bytes)
+    MOT_CUDA(is_ss ? ss_prepare(e->shape, e->smem_bytes) : is_sort ? sort_prepare(e->shape, e->smem_bytes)
                      : (is_oc ? oc_prepare(e->shape, e->smem_bytes)
                               : (is_bot ? bot_prepare(e->shape, e->smem_bytes) : bt_prepare(e->shape, e->smem_bytes))));
     e->n_chunks = cfg->n_chunks > 0 ? std::min(cfg->n_chunks, kMaxChunks) : (cfg->n_streams >= 128 ? 8 : (cfg->n_streams >= 32 ? 4 : 1));
@@ -477,8 +521,8 @@ int mot_engine_update_device_embs(mot_engine* e, int T, const float* d_dets, con
     if (!e || !d_dets || !d_n_dets || !d_out || !d_n_out) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
     if (T <= 0 || ld_dets <= 0 || ld_out <= 0) return fail(MOT_ERR_INVALID_ARGUMENT, "non-positive size");
     if ((ld_out * 8 * sizeof(float)) % 16 != 0 || (((size_t)d_out) & 15)) return fail(MOT_ERR_INVALID_ARGUMENT, "out must be 16-byte aligned");
-    if (d_embs && (e->cfg.kind != MOT_TRACKER_BOTSORT || e->cfg.emb_dim <= 0))
-        return fail(MOT_ERR_INVALID_ARGUMENT, "embeddings need a BoT-SORT engine created with emb_dim > 0");
+    if (d_embs && ((e->cfg.kind != MOT_TRACKER_BOTSORT && e->cfg.kind != MOT_TRACKER_STRONGSORT) || e->cfg.emb_dim <= 0))
+        return fail(MOT_ERR_INVALID_ARGUMENT, "embeddings need a BoT-SORT / StrongSORT engine created with emb_dim > 0");
     if (d_embs && (((size_t)d_embs) & 15)) return fail(MOT_ERR_INVALID_ARGUMENT, "embs must be 16-byte aligned");
     const int S = e->cfg.n_streams;
     engine_launch(e, T, d_dets, d_n_dets, ld_dets, d_embs, d_out, d_n_out, ld_out, 0, S, (cudaStream_t)stream);
@@ -495,8 +539,8 @@ int mot_engine_update_host_embs(mot_engine* e, int T, const float* dets, const i
                                 float* out, int* n_out, int ld_out) {
     if (!e || !dets || !n_dets || !out || !n_out) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
     if (T <= 0 || ld_dets <= 0 || ld_out <= 0) return fail(MOT_ERR_INVALID_ARGUMENT, "non-positive size");
-    if (embs && (e->cfg.kind != MOT_TRACKER_BOTSORT || e->cfg.emb_dim <= 0))
-        return fail(MOT_ERR_INVALID_ARGUMENT, "embeddings need a BoT-SORT engine created with emb_dim > 0");
+    if (embs && ((e->cfg.kind != MOT_TRACKER_BOTSORT && e->cfg.kind != MOT_TRACKER_STRONGSORT) || e->cfg.emb_dim <= 0))
+        return fail(MOT_ERR_INVALID_ARGUMENT, "embeddings need a BoT-SORT / StrongSORT engine created with emb_dim > 0");
     MOT_CUDA(cudaSetDevice(e->cfg.device));
     const int S = e->cfg.n_streams;
     const size_t TS = (size_t)T * S;
@@ -564,6 +608,41 @@ int mot_engine_update_host(mot_engine* e, int T, const float* dets, const int* n
     return mot_engine_update_host_embs(e, T, dets, n_dets, ld_dets, nullptr, out, n_out, ld_out);
 }
 
+// StrongSORT engines: the track list as rows of [id, state, hits, 0, tsu, conf, cls, det_ind, has_feat, n_samples, mean 8, cov 64]
+int mot_engine_dump_strong(mot_engine* e, int s, float* rows82, float* feats, int cap_rows, int* n_rows) {
+    if (!e || !rows82 || !n_rows || s < 0 || s >= e->cfg.n_streams) return fail(MOT_ERR_INVALID_ARGUMENT, "bad argument");
+    if (e->cfg.kind != MOT_TRACKER_STRONGSORT) return fail(MOT_ERR_UNSUPPORTED, "not a StrongSORT engine");
+    MOT_CUDA(cudaSetDevice(e->cfg.device));
+    MOT_CUDA(cudaDeviceSynchronize());
+    const mot::SsLayout& L = e->ss_layout;
+    std::vector<unsigned char> slab(L.off_gal);
+    const unsigned char* dbase = e->d_state + (size_t)s * L.stride;
+    MOT_CUDA(cudaMemcpy(slab.data(), dbase, slab.size(), cudaMemcpyDeviceToHost));
+    const unsigned char* base = slab.data();
+    const int* hdr = (const int*)base;
+    const unsigned short* list = (const unsigned short*)(base + L.off_lists);
+    const unsigned char* state = base + L.off_state;
+    const int* m = (const int*)(base + L.off_meta);
+    const float* recs = (const float*)(base + L.off_recs);
+    const float* ft = (const float*)(base + L.off_feat);
+    const int cap = L.cap, n = hdr[mot::kHdrActive];
+    int k = 0;
+    for (; k < n && k < cap_rows; ++k) {
+        const int slot = list[k];
+        float* o = rows82 + 82 * (size_t)k;
+        o[0] = (float)m[slot]; o[1] = (float)(state[slot] & 0x0f); o[2] = (float)m[cap + slot]; o[3] = 0.0f;
+        o[4] = (float)m[2 * cap + slot]; o[5] = ((const float*)m)[7 * cap + slot]; o[6] = (float)m[3 * cap + slot];
+        o[7] = (float)m[4 * cap + slot]; o[8] = (state[slot] & mot::kSsHasFeat) ? 1.0f : 0.0f; o[9] = (float)m[5 * cap + slot];
+        std::memcpy(o + 10, recs + (size_t)slot * mot::kRecFloats, sizeof(float) * mot::kRecFloats);
+        if (feats && L.dim > 0) {
+            if (state[slot] & mot::kSsHasFeat) std::memcpy(feats + (size_t)L.dim * k, ft + (size_t)slot * L.dim, sizeof(float) * L.dim);
+            else std::memset(feats + (size_t)L.dim * k, 0, sizeof(float) * L.dim);
+        }
+    }
+    *n_rows = k;
+    return MOT_OK;
+}
+
 // BoT-SORT engines: list `which` (0 active, 1 lost) as rows of [id, state, is_activated, frame_id, start_frame,
 // tracklet_len, conf, cls, det_ind, has_feat, mean 8, cov 64] (82 floats) and, when feats != NULL, the smooth features
 int mot_engine_dump_bot(mot_engine* e, int s, int which, float* rows82, float* feats, int cap_rows, int* n_rows) {
@@ -611,6 +690,7 @@ int mot_engine_check(mot_engine* e, int* flags) {
     for (int s = 0; s < S; ++s) { all |= err[s]; if (flags) flags[s] = err[s]; }
     if (all & (mot::kErrCapacity | mot::kErrTooManyDets | mot::kErrOutput))
         return fail(MOT_ERR_CAPACITY, "engine capacity exceeded (flags 0x%x: 1 track slots, 2 detections, 4 output rows)", all);
+    if (all & mot::kErrTable) return fail(MOT_ERR_CAPACITY, "StrongSORT appearance candidate table full (flag 16)");
     if (all & mot::kErrKalman) return fail(MOT_ERR_NUMERIC, "a Kalman update left the Cholesky path");
     return MOT_OK;
 }

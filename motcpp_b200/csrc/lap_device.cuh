@@ -256,91 +256,23 @@ __device__ __noinline__ void warp_hungarian_big(const LapGlobalScratch ws, int m
 //                          exactly ONCE per examined pair (step 1 only), so a functor may tally side statistics there
 //   };
 // On return (all threads) ws.row2col[0..n) / ws.col2row[0..m) hold the assignment (-1 = unmatched).
-template <class Cost>
-__device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, float thresh, const Cost& cost) {
+// Result / label initialisation shared by block_lap and block_lap_solve's external callers.  All threads must call.
+__device__ __forceinline__ void block_lap_begin(LapWorkspace& ws, int n, int m) {
     const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     __syncthreads();
     for (int i = tid; i < n; i += nt) { ws.row2col[i] = -1; ws.row_label[i] = kLapNone; }
     for (int j = tid; j < m; j += nt) { ws.col2row[j] = -1; ws.col_label[j] = kLapNone; }
     if (tid < 8) ws.ctl[tid] = 0;
     __syncthreads();
-    if (n == 0 || m == 0) return;
+}
 
-    // ---- 1. candidate pairs.  Costs that live in shared memory / registers are scanned one row per
-    //         thread; a dense matrix in global memory is scanned one row per warp so loads coalesce.
-    if (Cost::kWarpPerRow) {
-        for (int i = warp; i < n; i += nwarps) {
-            const typename Cost::Row rw = cost.row(i);
-            for (int j0 = 0; j0 < m; j0 += 32) {
-                const int j = j0 + lane;
-                const bool cand = (j < m) && cost.is_candidate(rw, i, j, thresh);
-                const unsigned ballot = __ballot_sync(kFullMask, cand);
-                if (ballot == 0) continue;
-                int e0 = 0;
-                if (lane == 0) e0 = atomicAdd(&ws.ctl[0], __popc(ballot));
-                e0 = __shfl_sync(kFullMask, e0, 0);
-                if (cand) {
-                    const int e = e0 + __popc(ballot & ((1u << lane) - 1u));
-                    if (e < ws.e_cap) ws.scratch_a[e] = (i << 16) | j;
-                    else ws.ctl[1] = 1;
-                }
-            }
-        }
-    } else {
-        bool use_grid = false;
-        if constexpr (Cost::kGrid) {
-            // box costs: index the columns so that only overlapping pairs are looked at
-            if (cost.prune && (long long)n * m >= 8192 && m <= ws.grid.cap) {
-                grid_build(ws.grid, m, ws.bs, [&](int j) { return cost.col_box(j); });
-                use_grid = true;
-            }
-        }
-        auto push_edge = [&](int i, int j) {
-            const int e = atomicAdd(&ws.ctl[0], 1);
-            if (e < ws.e_cap) ws.scratch_a[e] = (i << 16) | j;
-            else ws.ctl[1] = 1;
-        };
-        auto scan_row = [&](int i) {                       // every column, exact cost on the spot
-            const typename Cost::Row rw = cost.row(i);
-            for (int j = 0; j < m; ++j) {
-                if (cost.reject(rw, j)) continue;
-                if (cost.is_candidate(rw, i, j, thresh)) push_edge(i, j);
-            }
-        };
-        if (use_grid) {
-            if constexpr (Cost::kGrid) {
-                // one row per thread and chunk: (1) collect the overlapping pairs of the chunk through the
-                // grid, (2) evaluate their exact costs densely, one pair per thread (no divergence)
-                for (int base = 0; base < n; base += nt) {
-                    const int i = base + tid;
-                    if (tid == 0) ws.ctl[7] = 0;
-                    __syncthreads();
-                    if (i < n) {
-                        const typename Cost::Row rw = cost.row(i);
-                        grid_query(ws.grid, rw.b, [&](int j) { return cost.col_box(j); }, [&](int j, float4) {
-                            const int q = atomicAdd(&ws.ctl[7], 1);
-                            if (q < ws.p_cap) ws.pairs[q] = (i << 16) | j;
-                        });
-                    }
-                    __syncthreads();
-                    const int n_pairs = ws.ctl[7];
-                    if (n_pairs <= ws.p_cap) {
-                        for (int q = tid; q < n_pairs; q += nt) {
-                            const int pk = ws.pairs[q];
-                            const int pi = pk >> 16, pj = pk & 0xffff;
-                            if (cost.is_candidate(cost.row(pi), pi, pj, thresh)) push_edge(pi, pj);
-                        }
-                    } else if (i < n) {
-                        scan_row(i);                           // pair buffer too small for this chunk
-                    }
-                    __syncthreads();
-                }
-            }
-        } else {
-            for (int i = tid; i < n; i += nt) scan_row(i);
-        }
-    }
+// Steps 2-4 of block_lap: expects the candidate edges (row << 16 | col) in ws.scratch_a[0 .. ws.ctl[0]) (ws.ctl[1] != 0 =
+// buffer overflow) and the labels / results initialised by block_lap_begin.  A caller that finds its candidates by other
+// means (the StrongSORT appearance stage) calls block_lap_begin, pushes edges, then this.  All threads must call.
+template <class Cost>
+__device__ void block_lap_solve(LapWorkspace& ws, int n, int m, int n_max, int m_max, float thresh, const Cost& cost) {
+    const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
+    const int lane = tid & 31;
     __syncthreads();
     const int n_edges = min(ws.ctl[0], ws.e_cap);
     const bool overflow = ws.ctl[1] != 0;
@@ -460,6 +392,94 @@ __device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, 
                                 rows, r, pr, cols, c, pc, thresh, cost, ws.row2col, ws.col2row);
     }
     __syncthreads();
+}
+
+template <class Cost>
+__device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, float thresh, const Cost& cost) {
+    const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) { ws.row2col[i] = -1; ws.row_label[i] = kLapNone; }
+    for (int j = tid; j < m; j += nt) { ws.col2row[j] = -1; ws.col_label[j] = kLapNone; }
+    if (tid < 8) ws.ctl[tid] = 0;
+    __syncthreads();
+    if (n == 0 || m == 0) return;
+
+    // ---- 1. candidate pairs.  Costs that live in shared memory / registers are scanned one row per
+    //         thread; a dense matrix in global memory is scanned one row per warp so loads coalesce.
+    if (Cost::kWarpPerRow) {
+        for (int i = warp; i < n; i += nwarps) {
+            const typename Cost::Row rw = cost.row(i);
+            for (int j0 = 0; j0 < m; j0 += 32) {
+                const int j = j0 + lane;
+                const bool cand = (j < m) && cost.is_candidate(rw, i, j, thresh);
+                const unsigned ballot = __ballot_sync(kFullMask, cand);
+                if (ballot == 0) continue;
+                int e0 = 0;
+                if (lane == 0) e0 = atomicAdd(&ws.ctl[0], __popc(ballot));
+                e0 = __shfl_sync(kFullMask, e0, 0);
+                if (cand) {
+                    const int e = e0 + __popc(ballot & ((1u << lane) - 1u));
+                    if (e < ws.e_cap) ws.scratch_a[e] = (i << 16) | j;
+                    else ws.ctl[1] = 1;
+                }
+            }
+        }
+    } else {
+        bool use_grid = false;
+        if constexpr (Cost::kGrid) {
+            // box costs: index the columns so that only overlapping pairs are looked at
+            if (cost.prune && (long long)n * m >= 8192 && m <= ws.grid.cap) {
+                grid_build(ws.grid, m, ws.bs, [&](int j) { return cost.col_box(j); });
+                use_grid = true;
+            }
+        }
+        auto push_edge = [&](int i, int j) {
+            const int e = atomicAdd(&ws.ctl[0], 1);
+            if (e < ws.e_cap) ws.scratch_a[e] = (i << 16) | j;
+            else ws.ctl[1] = 1;
+        };
+        auto scan_row = [&](int i) {                       // every column, exact cost on the spot
+            const typename Cost::Row rw = cost.row(i);
+            for (int j = 0; j < m; ++j) {
+                if (cost.reject(rw, j)) continue;
+                if (cost.is_candidate(rw, i, j, thresh)) push_edge(i, j);
+            }
+        };
+        if (use_grid) {
+            if constexpr (Cost::kGrid) {
+                // one row per thread and chunk: (1) collect the overlapping pairs of the chunk through the
+                // grid, (2) evaluate their exact costs densely, one pair per thread (no divergence)
+                for (int base = 0; base < n; base += nt) {
+                    const int i = base + tid;
+                    if (tid == 0) ws.ctl[7] = 0;
+                    __syncthreads();
+                    if (i < n) {
+                        const typename Cost::Row rw = cost.row(i);
+                        grid_query(ws.grid, rw.b, [&](int j) { return cost.col_box(j); }, [&](int j, float4) {
+                            const int q = atomicAdd(&ws.ctl[7], 1);
+                            if (q < ws.p_cap) ws.pairs[q] = (i << 16) | j;
+                        });
+                    }
+                    __syncthreads();
+                    const int n_pairs = ws.ctl[7];
+                    if (n_pairs <= ws.p_cap) {
+                        for (int q = tid; q < n_pairs; q += nt) {
+                            const int pk = ws.pairs[q];
+                            const int pi = pk >> 16, pj = pk & 0xffff;
+                            if (cost.is_candidate(cost.row(pi), pi, pj, thresh)) push_edge(pi, pj);
+                        }
+                    } else if (i < n) {
+                        scan_row(i);                           // pair buffer too small for this chunk
+                    }
+                    __syncthreads();
+                }
+            }
+        } else {
+            for (int i = tid; i < n; i += nt) scan_row(i);
+        }
+    }
+    block_lap_solve(ws, n, m, n_max, m_max, thresh, cost);
 }
 
 }  // namespace mot

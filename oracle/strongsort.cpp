@@ -23,6 +23,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <set>
@@ -167,6 +169,7 @@ struct OrcStrongSort {
         for (int r = 0; r < n; ++r) {
             const int c = r2c[r];
             if (c >= 0 && cost[(size_t)r * m + c] <= max_distance) {          // :389-399
+                if (getenv("ORC_SS_DEBUG")) fprintf(stderr, "ORC match row=%d trk=%d det=%d cost=%g thr=%g\n", r, track_idx[r], det_idx[c], cost[(size_t)r * m + c], max_distance);
                 matches.push_back({track_idx[r], det_idx[c]});
                 mr[r] = 1; mc[c] = 1;
             }

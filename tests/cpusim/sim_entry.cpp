@@ -233,6 +233,7 @@ int sim_oc_dump(void* hv, int s, float* rows, int cap_rows) {
 
 // ------------------------------------------------------------------ BoT-SORT engine under the emulator
 #include "../../motcpp_b200/csrc/botsort_kernel.cuh"
+#include "../../motcpp_b200/csrc/strongsort_kernel.cuh"
 
 namespace {
 struct SimBot {
@@ -301,6 +302,77 @@ int sim_bot_dump(void* hv, int s, int which, float* rows, float* feats, int cap_
         o[9] = (sflag[slot] & 0x20) ? 1.0f : 0.0f;
         std::memcpy(o + 10, recs + (size_t)slot * mot::kRecFloats, sizeof(float) * mot::kRecFloats);
         if (feats && L.dim > 0) std::memcpy(feats + (size_t)L.dim * k, ft + (size_t)slot * L.dim, sizeof(float) * L.dim);
+    }
+    return k;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ StrongSORT engine on the emulator
+namespace {
+struct SimSs {
+    mot::SsLayout L;
+    mot::SsParams p;
+    int S;
+    std::vector<unsigned char> state;
+};
+}  // namespace
+
+extern "C" {
+
+void* sim_ss_create(int S, int dim, int max_age, float min_conf, float max_cos, float max_iou, int n_init, int budget,
+                    float mc_lambda, float ema_alpha) {
+    auto* h = new SimSs();
+    h->L = mot::SsLayout::make(256, 64, dim, budget);
+    h->S = S;
+    h->p.min_conf = min_conf; h->p.max_cos_dist = max_cos; h->p.max_iou_dist = max_iou; h->p.mc_lambda = mc_lambda;
+    h->p.ema_alpha = ema_alpha; h->p.max_age = max_age; h->p.n_init = n_init; h->p.budget = budget; h->p.dim = dim;
+    h->state.assign(h->L.stride * (size_t)S + 256, 0);
+    unsigned char* st = h->state.data();
+    const mot::SsLayout L = h->L;
+    cpusim::launch(dim3(S), dim3(64), 0, [=] { mot::strongsort_reset_kernel(st, L, S); });
+    return h;
+}
+void sim_ss_destroy(void* hv) { delete (SimSs*)hv; }
+
+int sim_ss_update(void* hv, const float* dets, const int* n_dets, const float* embs, int T, int ld_dets, float* out,
+                  int* n_out, int ld_out, int threads) {
+    auto* h = (SimSs*)hv;
+    mot::SsArgs a{};
+    a.state = h->state.data(); a.L = h->L; a.dets = dets; a.n_dets = n_dets; a.embs = embs; a.out = out; a.n_out = n_out;
+    a.T = T; a.S = h->S; a.ld_dets = ld_dets; a.ld_out = ld_out; a.s_begin = 0; a.s_end = h->S; a.p = h->p;
+    const size_t smem = mot::ss_smem_bytes(256, 64, 1024);
+    cpusim::launch(dim3(h->S), dim3(threads), smem, [=] { mot::strongsort_step_kernel<256, 64, 1024>(a); });
+    return 0;
+}
+void sim_ss_header(void* hv, int s, int* hdr16) {
+    auto* h = (SimSs*)hv;
+    std::memcpy(hdr16, h->state.data() + (size_t)s * h->L.stride, sizeof(int) * 16);
+}
+// rows of [id, state, hits, 0, tsu, conf, cls, det_ind, has_feat, n_samples, mean 8, cov 64]; feats nullable
+int sim_ss_dump(void* hv, int s, float* rows, float* feats, int cap_rows) {
+    auto* h = (SimSs*)hv;
+    unsigned char* base = h->state.data() + (size_t)s * h->L.stride;
+    const mot::SsLayout& L = h->L;
+    const int* hdr = (const int*)base;
+    const unsigned short* list = (const unsigned short*)(base + L.off_lists);
+    const unsigned char* state = base + L.off_state;
+    const int* m = (const int*)(base + L.off_meta);
+    const float* recs = (const float*)(base + L.off_recs);
+    const float* ft = (const float*)(base + L.off_feat);
+    const int cap = L.cap, n = hdr[mot::kHdrActive];
+    int k = 0;
+    for (; k < n && k < cap_rows; ++k) {
+        const int slot = list[k];
+        float* o = rows + 82 * k;
+        o[0] = (float)m[slot]; o[1] = (float)(state[slot] & 0x0f); o[2] = (float)m[cap + slot]; o[3] = 0.0f;
+        o[4] = (float)m[2 * cap + slot]; o[5] = ((const float*)m)[7 * cap + slot]; o[6] = (float)m[3 * cap + slot];
+        o[7] = (float)m[4 * cap + slot]; o[8] = (state[slot] & mot::kSsHasFeat) ? 1.0f : 0.0f; o[9] = (float)m[5 * cap + slot];
+        std::memcpy(o + 10, recs + (size_t)slot * mot::kRecFloats, sizeof(float) * mot::kRecFloats);
+        if (feats && L.dim > 0) {
+            if (state[slot] & mot::kSsHasFeat) std::memcpy(feats + (size_t)L.dim * k, ft + (size_t)slot * L.dim, sizeof(float) * L.dim);
+            else std::memset(feats + (size_t)L.dim * k, 0, sizeof(float) * L.dim);
+        }
     }
     return k;
 }

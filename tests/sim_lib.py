@@ -49,6 +49,13 @@ def lib():
         S.sim_bot_dump.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, C.c_void_p, C.c_int]
         S.sim_bot_dump.restype = C.c_int
         S.sim_bot_destroy.argtypes = [C.c_void_p]
+        S.sim_ss_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_float, C.c_float]
+        S.sim_ss_create.restype = C.c_void_p
+        S.sim_ss_update.argtypes = [C.c_void_p, f32p, i32p, C.c_void_p, C.c_int, C.c_int, f32p, i32p, C.c_int, C.c_int]
+        S.sim_ss_header.argtypes = [C.c_void_p, C.c_int, i32p]
+        S.sim_ss_dump.argtypes = [C.c_void_p, C.c_int, f32p, C.c_void_p, C.c_int]
+        S.sim_ss_dump.restype = C.c_int
+        S.sim_ss_destroy.argtypes = [C.c_void_p]
         _LIB = S
     return _LIB
 
@@ -190,4 +197,43 @@ class SimBotSort:
         buf = np.zeros((self.cap, 82), np.float32)
         feats = np.zeros((self.cap, max(self.dim, 1)), np.float32)
         k = lib().sim_bot_dump(self.h, s, which, buf, feats.ctypes.data_as(C.c_void_p) if self.dim else None, self.cap)
+        return buf[:k], feats[:k]
+
+
+class SimStrongSort:
+    def __init__(self, n_streams=1, dim=0, max_age=30, min_conf=0.1, max_cos_dist=0.2, max_iou_dist=0.7, n_init=3,
+                 nn_budget=100, mc_lambda=0.98, ema_alpha=0.9):
+        self.S, self.cap, self.dim = n_streams, 256, dim
+        self.h = lib().sim_ss_create(n_streams, dim, max_age, min_conf, max_cos_dist, max_iou_dist, n_init, nn_budget,
+                                     mc_lambda, ema_alpha)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().sim_ss_destroy(self.h)
+            self.h = None
+
+    def update(self, dets, n_dets, embs=None, threads=128):
+        """dets (T,S,ld,6), n_dets (T,S), embs (T,S,ld,dim) or None"""
+        dets = np.ascontiguousarray(dets, np.float32)
+        T, S, ld, _ = dets.shape
+        n_dets = np.ascontiguousarray(n_dets, np.int32).reshape(T, S)
+        ep = None
+        if embs is not None and self.dim > 0:
+            embs = np.ascontiguousarray(embs, np.float32)
+            assert embs.shape == (T, S, ld, self.dim)
+            ep = embs.ctypes.data_as(C.c_void_p)
+        out = np.zeros((T, S, self.cap, 8), np.float32)
+        n_out = np.zeros((T, S), np.int32)
+        lib().sim_ss_update(self.h, dets, n_dets, ep, T, ld, out, n_out, self.cap, threads)
+        return out, n_out
+
+    def header(self, s=0):
+        h = np.zeros(16, np.int32)
+        lib().sim_ss_header(self.h, s, h)
+        return h
+
+    def dump(self, s=0):
+        buf = np.zeros((self.cap, 82), np.float32)
+        feats = np.zeros((self.cap, max(self.dim, 1)), np.float32)
+        k = lib().sim_ss_dump(self.h, s, buf, feats.ctypes.data_as(C.c_void_p) if self.dim else None, self.cap)
         return buf[:k], feats[:k]
