@@ -387,11 +387,15 @@ __device__ __forceinline__ void ss_frame(const SsArgs& a, const SsStream& st, Ss
                         const int d = j0 + l;
                         const float gdl = __shfl_sync(kFullMask, gd, l);
                         const float* f = st.dfeat + (size_t)d * dim;
-                        float best = 0.0f;
-                        for (int s = 0; s < ns; ++s) {
-                            const float c = xsub(1.0f, warp_dot(ring + (size_t)s * dim, f, dim));          // :333
-                            best = (s == 0 || c < best) ? c : best;                                        // minCoeff (:295)
+                        // one gallery sample per LANE (32 independent row streams in flight instead of one dependent
+                        // warp-wide dot product after another); each lane evaluates the oracle's "lanes32" sum on its own
+                        float best = 3.0e38f;
+                        for (int s = lane; s < ns; s += 32) {
+                            const float c = xsub(1.0f, thread_dot_lanes32(ring + (size_t)s * dim, f, dim));   // :333
+                            best = (c < best) ? c : best;                                                  // minCoeff (:295)
                         }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) { const float t = __shfl_xor_sync(kFullMask, best, o); best = (t < best) ? t : best; }
                         const float blended = gate_blend(best, gdl, lam, kInftyCost);                     // :484-487
 #if defined(MOT_CPUSIM) && defined(SS_DEBUG)
                         if (lane == 0) printf("A r=%d slot=%d d=%d ns=%d best=%g gd=%g blended=%g\n", r, slot, d, ns, best, gdl, blended);

@@ -226,3 +226,50 @@ def stress_stream_reid(stream_id: int = 0, n_frames: int = 200, n_obj: int = 40,
         embs[t, :len(perm)] = feats[perm]
         counts[t] = len(perm)
     return out, counts, embs
+
+
+def strongsort_stream(stream_id: int, n_frames: int, n_obj: int = 192, n_clutter: int = 64, dim: int = 128,
+                      canvas=(3840, 2160), noise: float = 0.3, config: int = 6):
+    """StrongSORT workload: n_obj moving objects, each seen TWICE per frame - a confident box and an
+    overlapping low-confidence near-duplicate - plus n_clutter random boxes; 2 n_obj + n_clutter detections per frame.
+    The duplicate matters: with no confirmed track the reference feeds every tentative track to the IoU stage twice and
+    deletes it unless both copies find a detection (oracle/strongsort.cpp q1), so a scene with one clean box per object
+    never confirms anything.  Embeddings: unit identity vectors + noise of total norm `noise`, rescaled by U(0.5, 2) so the
+    tracker's own normalisation is exercised; clutter gets random vectors.  Returns dets (T, D, 6), embs (T, D, dim)."""
+    rng = _rng(config, stream_id)
+    W, H = canvas
+    w = rng.uniform(40, 120, n_obj)
+    h = 2.2 * w
+    cx = rng.uniform(0, W, n_obj)
+    cy = rng.uniform(0, H, n_obj)
+    vx = rng.normal(0, 3, n_obj)
+    vy = rng.normal(0, 3, n_obj)
+    ident = rng.normal(0, 1, (n_obj, dim))
+    ident /= np.linalg.norm(ident, axis=1, keepdims=True)
+    D = 2 * n_obj + n_clutter
+    dets = np.zeros((n_frames, D, 6), np.float32)
+    embs = np.empty((n_frames, D, dim), np.float32)
+    sigma = noise / np.sqrt(dim)
+    for t in range(n_frames):
+        cx += vx
+        cy += vy
+        flip = (cx < 0) | (cx > W)
+        vx[flip] = -vx[flip]
+        flip = (cy < 0) | (cy > H)
+        vy[flip] = -vy[flip]
+        b = np.empty((D, 4))
+        b[:n_obj] = _boxes(cx, cy, w, h) + rng.normal(0, 2, (n_obj, 4))
+        b[n_obj:2 * n_obj] = _boxes(cx, cy, w, h) + rng.normal(0, 4, (n_obj, 4))
+        cw = rng.uniform(40, 120, n_clutter)
+        b[2 * n_obj:] = _boxes(rng.uniform(0, W, n_clutter), rng.uniform(0, H, n_clutter), cw, 2.2 * cw)
+        e = np.empty((D, dim))
+        e[:n_obj] = ident + sigma * rng.normal(0, 1, (n_obj, dim))
+        e[n_obj:2 * n_obj] = ident + sigma * rng.normal(0, 1, (n_obj, dim))
+        e[2 * n_obj:] = rng.normal(0, 1, (n_clutter, dim))
+        e *= rng.uniform(0.5, 2.0, (D, 1))
+        conf = np.concatenate([rng.uniform(0.6, 0.99, n_obj), rng.uniform(0.15, 0.45, n_obj), rng.uniform(0.3, 0.9, n_clutter)])
+        perm = rng.permutation(D)
+        dets[t, :, :4] = b[perm]
+        dets[t, :, 4] = conf[perm]
+        embs[t] = e[perm]
+    return dets, embs

@@ -214,6 +214,16 @@ def main():
         e = np.stack([p[1] for p in pairs], 1)
         engine_bench("engine_botsort_c3_1024x1024x512", _lib.TRACKER_BOTSORT, 148, 2048, 1024, d, e, warm, T, iters, BOT,
                      state_bytes_per_track=288 + 2048, dim=512)
+    if want("engine_strongsort"):
+        SS = dict(max_age=30, min_conf=0.1, max_cos_dist=0.2, max_iou_dist=0.7, n_init=3, nn_budget=100, mc_lambda=0.98, ema_alpha=0.9)
+        T, iters, warm = (4, 3, 110) if args.quick else (10, 4, 120)
+        pairs = [synth.strongsort_stream(s, n_frames=warm + T * iters) for s in range(2)]
+        d = np.stack([p[0] for p in pairs], 1)
+        e = np.stack([p[1] for p in pairs], 1)
+        # per frame: Kalman state of every track twice, its smoothed + re-normalised feature, one gallery row written, the gallery
+        # of every confirmed track read once (budget x dim floats), detections + their embeddings
+        engine_bench("engine_strongsort_192obj_448dets_128d_budget100", _lib.TRACKER_STRONGSORT, 148, 1536, 512, d, e, warm, T, iters, SS,
+                     state_bytes_per_track=288 + 128 * 4 * 2 + 100 * 128 * 4 // 2, dim=128)
     if want("engine_sort"):
         SORT = dict(det_thresh=0.3, max_age=1, max_obs=50, min_hits=3, iou_threshold=0.3)
         T, iters, warm = 50, 5, 50
