@@ -56,7 +56,7 @@ struct SsParams {
 
 struct SsLayout {
     int cap, d_max, dim, budget;
-    size_t off_lists, off_state, off_meta, off_recs, off_feat, off_gal, off_ring, off_dfeat, off_dnorm, off_jv, off_gscratch, stride;
+    size_t off_lists, off_state, off_meta, off_recs, off_feat, off_gal, off_ring, off_dfeat, off_dnorm, off_grad, off_jv, off_gscratch, stride;
     static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
     static SsLayout make(int cap, int d_max, int dim, int budget) {
         SsLayout L{};
@@ -71,6 +71,7 @@ struct SsLayout {
         L.off_ring = o;     o = al(o + sizeof(float) * (size_t)dim * (size_t)budget * (size_t)cap);
         L.off_dfeat = o;    o = al(o + sizeof(float) * (size_t)dim * (size_t)d_max);
         L.off_dnorm = o;    o = al(o + sizeof(float) * (size_t)d_max);
+        L.off_grad = o;     o = al(o + sizeof(float) * (size_t)cap);
         L.off_jv = o;       o = al(o + sizeof(float) * kSsJvDense);
         L.off_gscratch = o; o = al(o + lap_gscratch_bytes(cap, d_max));
         L.stride = o;
@@ -90,6 +91,7 @@ struct SsStream {
     float* ring;                       // [cap][budget][dim] gallery: the last `budget` per-frame copies of gal
     float* dfeat;                      // [d_max][dim] this frame's detection features, normalised (filtered index)
     float* dnorm;                      // [d_max] |raw feature|
+    float* grad;                       // [cap] gallery radius: max over the ring of |sample - gal| (slightly inflated)
     float* jv_dense;                   // [kSsJvDense] dense (clamped) IoU cost matrix of the exact-tie path
     unsigned char* gscratch;
     __device__ __forceinline__ static SsStream at(unsigned char* base, const SsLayout& L) {
@@ -107,6 +109,7 @@ struct SsStream {
         s.ring = (float*)(base + L.off_ring);
         s.dfeat = (float*)(base + L.off_dfeat);
         s.dnorm = (float*)(base + L.off_dnorm);
+        s.grad = (float*)(base + L.off_grad);
         s.jv_dense = (float*)(base + L.off_jv);
         s.gscratch = base + L.off_gscratch;
         return s;
@@ -296,6 +299,7 @@ __device__ __forceinline__ void ss_frame(const SsArgs& a, const SsStream& st, Ss
     const int n_trk = st.hdr[kHdrActive];
     int n_free = st.hdr[kHdrFree];
     const int id_base = st.hdr[kHdrIdCounter];
+    const int frame_no = st.hdr[kHdrFrame];
     int n_in = n_det_in < 0 ? 0 : n_det_in;
     if (n_in > DMAX) { n_in = DMAX; if (tid == 0) atomicOr(&st.hdr[kHdrError], (int)kErrTooManyDets); }
 
@@ -374,6 +378,14 @@ __device__ __forceinline__ void ss_frame(const SsArgs& a, const SsStream& st, Ss
                 if (ns == 0) continue;                                           // no samples: the row is 1e5 (:271)
                 const GateRow gr = gate_prepare(st.recs + (size_t)slot * kRecFloats);
                 const float* ring = st.ring + (size_t)slot * budget * dim;
+                // Every gallery row lies within grad[slot] of the track's current re-normalised feature gal[slot], so
+                // min_s (1 - a_s . b) >= (1 - gal . b) - grad |b|: ONE dot product proves most gate-passing pairs to be
+                // non-candidates (different identities sit near cosine distance 1) and the ring is only walked for the rest.
+                // The bound is evaluated with slack far above fp32 round-off, so it never changes a result.
+                const float* center = st.gal + (size_t)slot * dim;
+                const float rad = xadd(xmul(st.grad[slot], 1.001f), 1e-6f);
+                const float slack = xadd(1e-4f, xmul(1e-6f, (float)dim));
+                const bool can_prune = lam > 1e-3f && ns > 2;
                 for (int j0 = 0; j0 < n_d; j0 += 32) {
                     const int j = j0 + lane;
                     float gd = 0.0f;
@@ -387,6 +399,11 @@ __device__ __forceinline__ void ss_frame(const SsArgs& a, const SsStream& st, Ss
                         const int d = j0 + l;
                         const float gdl = __shfl_sync(kFullMask, gd, l);
                         const float* f = st.dfeat + (size_t)d * dim;
+                        if (can_prune) {
+                            const float lower = xsub(xsub(xsub(1.0f, warp_dot(center, f, dim)), rad), slack);       // <= min_s c_s
+                            const float tau = xadd(xdiv(xsub(thr, xmul(xsub(1.0f, lam), gdl)), lam), slack);      // candidates have c <= tau
+                            if (lower > tau) continue;
+                        }
                         // one gallery sample per LANE (32 independent row streams in flight instead of one dependent
                         // warp-wide dot product after another); each lane evaluates the oracle's "lanes32" sum on its own
                         float best = 3.0e38f;
@@ -649,10 +666,36 @@ __device__ __forceinline__ void ss_frame(const SsArgs& a, const SsStream& st, Ss
             const float4* src = reinterpret_cast<const float4*>(st.gal + (size_t)slot * dim);
             float4* dst = reinterpret_cast<float4*>(st.ring + ((size_t)slot * budget + pos) * dim);
             for (int q = lane; q < (dim >> 2); q += 32) dst[q] = src[q];
-            __syncwarp();                                                         // every lane has read ring_pos
+            const int ns_old = st.ring_n[slot];
+            __syncwarp();                                                         // every lane has read ring_pos / ring_n
+            const int ns_new = (ns_old < budget) ? ns_old + 1 : budget;
             if (lane == 0) {
                 st.ring_pos[slot] = (pos + 1 == budget) ? 0 : pos + 1;
-                if (st.ring_n[slot] < budget) st.ring_n[slot] += 1;
+                st.ring_n[slot] = ns_new;
+            }
+            // Gallery radius for next frame's pruning bound, max_s |ring[s] - gal|.  Exact every fourth frame (one ring row per
+            // lane: the whole ring is read); in between the triangle inequality carries it: the centre moved by
+            // |gal - previous gal| (the previous gal is the ring row appended last frame), so every old row is at most that much
+            // farther away, and the new row is at distance 0.
+            const auto dist2 = [&](const float4* rv) {
+                float d2 = 0.0f;
+                for (int q = 0; q < (dim >> 2); ++q) {
+                    const float4 x = rv[q], c = src[q];
+                    const float ex = x.x - c.x, ey = x.y - c.y, ez = x.z - c.z, ew = x.w - c.w;
+                    d2 += ex * ex + ey * ey + ez * ez + ew * ew;
+                }
+                return d2;
+            };
+            if (ns_new <= 2 || ((frame_no + slot) & 3) == 0) {
+                float worst = 0.0f;
+                for (int sidx = lane; sidx < ns_new; sidx += 32)
+                    worst = fmaxf(worst, dist2(reinterpret_cast<const float4*>(st.ring + ((size_t)slot * budget + sidx) * dim)));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) worst = fmaxf(worst, __shfl_xor_sync(kFullMask, worst, o));
+                if (lane == 0) st.grad[slot] = sqrtf(worst);
+            } else if (lane == 0) {
+                const int prev = (pos == 0) ? budget - 1 : pos - 1;
+                st.grad[slot] = st.grad[slot] + sqrtf(dist2(reinterpret_cast<const float4*>(st.ring + ((size_t)slot * budget + prev) * dim))) * 1.0001f + 1e-6f;
             }
         }
 

@@ -193,7 +193,7 @@ def main():
         n_trk = int(hdr[0]) + (int(hdr[1]) if kind != _lib.TRACKER_OCSORT else 0)
         by_frame = 2 * n_trk * state_bytes_per_track + D * 24 + rows * 32 + D * dim * 4
         emit(name, (ms, float(np.min(times))), streams=S, frames_per_launch=T, frames_per_s=S * T / ms * 1e3,
-             us_per_frame_per_cta=ms * 1e3 / T / max(1, (S + 147) // 148), mean_output_rows=rows, tracks=n_trk, header=hdr[:14].tolist(),
+             us_per_frame_per_cta=ms * 1e3 / T / max(1, (S + 147) // 148), mean_output_rows=rows, tracks=n_trk, header=hdr[:16].tolist(),
              algorithmic_bytes_per_frame=by_frame, achieved_gbs=by_frame * S * T / ms / 1e6, peak_gbs=HBM,
              frac=by_frame * S * T / ms / 1e6 / HBM, info=eng.info())
         eng.close()
