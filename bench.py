@@ -132,41 +132,57 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.rows, self._stop, self._th = index, [], threading.Event(), None
+        self._nvml = None
+
+    # NVML (a query costs ~0.1 ms) so that a timed region of tens of milliseconds still gets many samples; nvidia-smi
+    # (one process per query, ~50 ms) is the fallback.  NVML is initialised in __enter__, BEFORE the timed region, and one
+    # sample is taken synchronously at both ends, so even a very short region is covered.
+    def _nvml_sample(self):
+        N, h, mx, get_reasons = self._nvml
+        bits = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+        sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+        r = int(get_reasons(h))
+        self.rows.append([str(sm), str(mx), "0"] + ["Active" if r & b else "Not Active" for _, b in bits])
+
+    def _smi_sample(self):
+        try:
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                  "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+            if out:
+                self.rows.append([x.strip() for x in out.split(",")])
+        except Exception:
+            pass
+
+    def _sample(self):
+        if self._nvml is not None:
+            try:
+                self._nvml_sample()
+                return
+            except Exception:
+                self._nvml = None
+        self._smi_sample()
 
     def _loop(self):
-        # NVML (a query costs ~0.1 ms) so that a timed region of tens of milliseconds still gets many samples;
-        # nvidia-smi (one process per query, ~50 ms) is the fallback
+        while not self._stop.is_set():
+            self._sample()
+            self._stop.wait(0.002 if self._nvml is not None else 0.2)
+
+    def __enter__(self):
         try:
             import pynvml as N
             N.nvmlInit()
             h = N.nvmlDeviceGetHandleByIndex(self.index)
             mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
             get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
-            bits = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
-            while not self._stop.is_set():
-                sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
-                r = int(get_reasons(h))
-                self.rows.append([str(sm), str(mx), "0"] + ["Active" if r & b else "Not Active" for _, b in bits])
-                self._stop.wait(0.005)
-            return
+            self._nvml = (N, h, mx, get_reasons)
         except Exception:
-            pass
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
-
-    def __enter__(self):
+            self._nvml = None
         self._th = threading.Thread(target=self._loop, daemon=True)
         self._th.start()
         return self
 
     def __exit__(self, *a):
+        self._sample()                      # still under load: the caller synchronises after leaving the block
         self._stop.set()
         self._th.join(timeout=6)
 

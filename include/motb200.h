@@ -199,6 +199,11 @@ int mot_cost_gate(float* cost, int ld, const float* recs, int n_tracks, const fl
  * tracks' time_since_update, rows with tsu > 1 are 1e5.  out (n x m, ld). */
 int mot_cost_iou_tlwh(const float* trk_tlwh, const int* tsu, int n, const float* det_tlwh, int m, float* out, int ld,
                       void* stream);
+/* deepocsort_assoc::compute_aw_max_metric (src/trackers/deepocsort.cpp:294-345), DeepOC-SORT's adaptive embedding weights
+ * (SURVEY 8f-2): out = w * emb_cost with w = w_association_emb * row_weight(i) * col_weight(j), weight = 1 - max(second / max
+ * - bottom, 0) / (1 - bottom) over the row's / column's two largest entries (0 when the largest is 0).  emb_cost, out (n x m). */
+int mot_cost_aw_max_metric(const float* emb_cost, int n, int m, int ld, float w_association_emb, float bottom, float* out,
+                           int ld_out, void* stream);
 /* KalmanFilterXYSR::apply_affine_correction (src/motion/kalman_filters/xysr_kf.cpp:114-141) on n XYSR records in place:
  * the camera-motion warp of DeepOC-SORT.  m2x2 (row-major) and t2 are HOST pointers. */
 int mot_kf_xysr_affine(float* recs, long long n, const float* m2x2, const float* t2, void* stream);

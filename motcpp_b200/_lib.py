@@ -83,6 +83,7 @@ SYMBOLS = {
     "mot_cost_gate": (_I, [_VP, _I, _VP, _I, _VP, _I, _F, _F, _I, _VP]),
     "mot_cost_iou_tlwh": (_I, [_VP, _VP, _I, _VP, _I, _VP, _I, _VP]),
     "mot_kf_xysr_affine": (_I, [_VP, _LL, _VP, _VP, _VP]),
+    "mot_cost_aw_max_metric": (_I, [_VP, _I, _I, _I, _F, _F, _VP, _I, _VP]),
     "mot_lap_device": (_I, [_VP, _I, _I, _I, _F, _VP, _VP, _VP]),
     "mot_lap_batch_device": (_I, [_VP, _LL, _I, _VP, _VP, _I, _I, _I, _F, _VP, _VP, _VP]),
     "mot_lap_jv_batch_device": (_I, [_VP, _LL, _I, _I, _I, _I, _F, _VP, _VP, _VP]),

@@ -225,6 +225,24 @@ def iou_cost_tlwh(track_tlwh, det_tlwh, time_since_update=None) -> np.ndarray:
     return np.ascontiguousarray(do.download()[:, :m])
 
 
+def aw_max_metric(emb_cost, w_association_emb: float = 0.5, bottom: float = 0.5) -> np.ndarray:
+    """deepocsort_assoc::compute_aw_max_metric (deepocsort.cpp:294-345): DeepOC-SORT's adaptive embedding weights."""
+    e = np.ascontiguousarray(emb_cost, np.float32)
+    if e.ndim != 2:
+        raise ValueError("emb_cost must be 2-D")
+    n, m = e.shape
+    if n == 0 or m == 0:
+        return e.copy()
+    _lib.require_gpu()
+    de, do = DeviceArray.from_host(e), DeviceArray((n, m))
+    try:
+        check(load().mot_cost_aw_max_metric(de.ptr, n, m, m, float(w_association_emb), float(bottom), do.ptr, m, None))
+        check(load().mot_stream_sync(None))
+    except MotError as ex:
+        _raise(ex)
+    return do.download()
+
+
 @dataclass
 class LinearAssignmentResult:
     """utils::LinearAssignmentResult (matching.hpp:32-36)."""

@@ -913,6 +913,29 @@ int mot_cost_iou_tlwh(const float* trk_tlwh, const int* tsu, int n, const float*
     return MOT_OK;
 }
 
+int mot_cost_aw_max_metric(const float* emb_cost, int n, int m, int ld, float w_association_emb, float bottom, float* out,
+                           int ld_out, void* stream) {
+    if (n < 0 || m < 0 || ld < m || ld_out < m) return fail(MOT_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (n == 0 || m == 0) return MOT_OK;
+    if (!emb_cost || !out) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
+    if (int rc = require_device()) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* ws = nullptr;                                                 // row / column weights + zero flags
+    const size_t fl = sizeof(float) * ((size_t)n + m);
+    MOT_CUDA(cudaMallocAsync((void**)&ws, fl + (size_t)n + m + 16, st));
+    float* row_w = (float*)ws; float* col_w = row_w + n;
+    unsigned char* row_z = ws + fl; unsigned char* col_z = row_z + n;
+    const int cap = sm_count() * 8;
+    mot::aw_row_top2_kernel<<<std::max(1, std::min((n + 7) / 8, cap)), 256, 0, st>>>(emb_cost, n, m, ld, bottom, row_w, row_z);
+    mot::aw_col_top2_kernel<<<std::max(1, std::min((m + 31) / 32, cap)), 256, 0, st>>>(emb_cost, n, m, ld, bottom, col_w, col_z);
+    const long long total = (long long)n * m;
+    mot::aw_apply_kernel<<<(int)std::max<long long>(1, std::min<long long>((total + 255) / 256, cap)), 256, 0, st>>>(
+        emb_cost, n, m, ld, w_association_emb, row_w, row_z, col_w, col_z, out, ld_out);
+    MOT_CUDA(cudaGetLastError());
+    MOT_CUDA(cudaFreeAsync(ws, st));
+    return MOT_OK;
+}
+
 int mot_kf_xysr_affine(float* recs, long long n, const float* m2x2, const float* t2, void* stream) {
     if (n < 0) return fail(MOT_ERR_INVALID_ARGUMENT, "bad sizes");
     if (n == 0) return MOT_OK;

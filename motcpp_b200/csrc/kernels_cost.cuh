@@ -198,4 +198,70 @@ __global__ void __launch_bounds__(256) iou_tlwh_cost_kernel(const float* __restr
     }
 }
 
+// ---- deepocsort_assoc::compute_aw_max_metric (reference src/trackers/deepocsort.cpp:294-345): the embedding cost is
+// re-weighted by how distinctive the best entry of its row and of its column is: weight = 1 - max(second / max - bottom, 0)
+// / (1 - bottom), zero when the maximum is zero.  Three streaming passes over the (n x m) matrix: row top-2 (one warp
+// per row, coalesced), column top-2 (32 columns per CTA, 8 row phases merged through shared memory), element-wise product.
+struct Top2 { float mx, se; };
+__device__ __forceinline__ void top2_push(Top2& t, float v) { if (v > t.mx) { t.se = t.mx; t.mx = v; } else if (v > t.se) t.se = v; }
+__device__ __forceinline__ void top2_merge(Top2& a, const Top2& b) { top2_push(a, b.mx); top2_push(a, b.se); }
+// weight as the reference writes it; encodes "row / column is all-zero-max" as a NaN-free flag value < 0 is impossible, so
+// the zero case is carried separately: returns the weight, *zero = max == 0
+__device__ __forceinline__ float aw_weight(const Top2& t, float bottom, bool* zero) {
+    *zero = (t.mx == 0.0f);
+    return xsub(1.0f, xdiv(fmaxf(xsub(xdiv(t.se, t.mx), bottom), 0.0f), xsub(1.0f, bottom)));
+}
+
+__global__ void __launch_bounds__(256) aw_row_top2_kernel(const float* __restrict__ emb, int n, int m, int ld, float bottom,
+                                                          float* __restrict__ row_w, unsigned char* __restrict__ row_zero) {
+    const int lane = lane_id(), wpc = (int)blockDim.x >> 5;
+    for (int i = (int)blockIdx.x * wpc + warp_id(); i < n; i += (int)gridDim.x * wpc) {
+        Top2 t{-INFINITY, -INFINITY};
+        const float* row = emb + (size_t)i * ld;
+        for (int j = lane; j < m; j += 32) top2_push(t, row[j]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            Top2 b{__shfl_xor_sync(kFullMask, t.mx, o), __shfl_xor_sync(kFullMask, t.se, o)};
+            top2_merge(t, b);
+        }
+        if (lane == 0) { bool z; row_w[i] = aw_weight(t, bottom, &z); row_zero[i] = z ? 1 : 0; }
+    }
+}
+
+__global__ void __launch_bounds__(256) aw_col_top2_kernel(const float* __restrict__ emb, int n, int m, int ld, float bottom,
+                                                          float* __restrict__ col_w, unsigned char* __restrict__ col_zero) {
+    __shared__ Top2 part[8][32];
+    const int tx = (int)threadIdx.x & 31, ty = (int)threadIdx.x >> 5;
+    for (int c0 = (int)blockIdx.x * 32; c0 < m; c0 += (int)gridDim.x * 32) {
+        const int j = c0 + tx;
+        Top2 t{-INFINITY, -INFINITY};
+        if (j < m)
+            for (int i = ty; i < n; i += 8) top2_push(t, emb[(size_t)i * ld + j]);
+        part[ty][tx] = t;
+        __syncthreads();
+        if (ty == 0 && j < m) {
+            for (int k = 1; k < 8; ++k) top2_merge(t, part[k][tx]);
+            bool z;
+            col_w[j] = aw_weight(t, bottom, &z);
+            col_zero[j] = z ? 1 : 0;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) aw_apply_kernel(const float* __restrict__ emb, int n, int m, int ld, float w_assoc,
+                                                       const float* __restrict__ row_w, const unsigned char* __restrict__ row_zero,
+                                                       const float* __restrict__ col_w, const unsigned char* __restrict__ col_zero,
+                                                       float* __restrict__ out, int ld_out) {
+    const long long total = (long long)n * m;
+    const bool rows_on = m >= 2, cols_on = n >= 2;                             // fewer than two entries: no weighting (:311, :333)
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(k / m), j = (int)(k - (long long)i * m);
+        float w = w_assoc;
+        if (rows_on) w = row_zero[i] ? 0.0f : xmul(w, row_w[i]);
+        if (cols_on) w = col_zero[j] ? 0.0f : xmul(w, col_w[j]);
+        out[(size_t)i * ld_out + j] = xmul(w, emb[(size_t)i * ld + j]);
+    }
+}
+
 }  // namespace mot

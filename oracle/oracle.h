@@ -91,6 +91,8 @@ void orc_clamp_cost(float* cost, int n, int m, int ld, float max_distance);
 /* KalmanFilterXYSR::apply_affine_correction (src/motion/kalman_filters/xysr_kf.cpp:114-141); m2 row-major 2x2 */
 void orc_kf_xysr_affine(float* x7, float* P49, const float* m2, const float* t2);
 
+/* deepocsort_assoc::compute_aw_max_metric (src/trackers/deepocsort.cpp:294-345) */
+void orc_aw_max_metric(const float* emb, int n, int m, int ld, float w_assoc, float bottom, float* out, int ld_out);
 /* NOT reference behaviour: + (j + 1) 2^-50 on rows i >= n_first (StrongSORT's duplicated track rows), see lapjv.cpp */
 int orc_linear_assignment_rowdup(const float* cost, int n, int m, int ld, float thresh, int n_first, int* row2col, int* col2row);
 

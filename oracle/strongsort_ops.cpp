@@ -5,6 +5,7 @@
 //   iou_matching::iou / iou_cost                                                   src/trackers/strongsort.cpp:502-585
 //   linear_assignment::min_cost_matching (threshold clamp)                         src/trackers/strongsort.cpp:372-377
 //   KalmanFilterXYSR::apply_affine_correction                                      src/motion/kalman_filters/xysr_kf.cpp:114-141
+//   deepocsort_assoc::compute_aw_max_metric (DeepOC-SORT adaptive embedding weights) src/trackers/deepocsort.cpp:294-345
 // Pinning: the reference holds no golden values for any of these ("parity unpinned" beyond hand-derived KATs in
 // tests/test_oracle_kats.py).  Eigen's GEMM / .norm() summation order is unspecified; sums here are sequential.
 #include "oracle.h"
@@ -121,6 +122,39 @@ void orc_kf_xysr_affine(float* x7, float* P49, const float* m2, const float* t2)
     P49[4 * 7 + 4] = vv[0]; P49[4 * 7 + 5] = vv[1]; P49[5 * 7 + 4] = vv[2]; P49[5 * 7 + 5] = vv[3];
     P49[4] = pv[0]; P49[5] = pv[1]; P49[7 + 4] = pv[2]; P49[7 + 5] = pv[3];
     P49[4 * 7 + 0] = pv[0]; P49[5 * 7 + 0] = pv[1]; P49[4 * 7 + 1] = pv[2]; P49[5 * 7 + 1] = pv[3];   // transpose (:140)
+}
+
+// deepocsort_assoc::compute_aw_max_metric (src/trackers/deepocsort.cpp:294-345): adaptive weighting of the embedding
+// cost by how distinctive each row's / column's best match is.  emb (n x m, ld) -> out (n x m, ld_out).
+void orc_aw_max_metric(const float* emb, int n, int m, int ld, float w_assoc, float bottom, float* out, int ld_out) {
+    std::vector<float> w((size_t)n * m, w_assoc);
+    auto weight = [&](float mx, float second) { return 1.0f - std::max((second / mx) - bottom, 0.0f) / (1.0f - bottom); };
+    if (m >= 2)
+        for (int i = 0; i < n; ++i) {
+            float mx = -INFINITY, se = -INFINITY;                             // two largest values of the row (:303-313)
+            for (int j = 0; j < m; ++j) {
+                const float v = emb[(size_t)i * ld + j];
+                if (v > mx) { se = mx; mx = v; } else if (v > se) se = v;
+            }
+            for (int j = 0; j < m; ++j) {
+                if (mx == 0.0f) w[(size_t)i * m + j] = 0.0f;                   // setZero (:315-316)
+                else w[(size_t)i * m + j] = w[(size_t)i * m + j] * weight(mx, se);
+            }
+        }
+    if (n >= 2)
+        for (int j = 0; j < m; ++j) {
+            float mx = -INFINITY, se = -INFINITY;
+            for (int i = 0; i < n; ++i) {
+                const float v = emb[(size_t)i * ld + j];
+                if (v > mx) { se = mx; mx = v; } else if (v > se) se = v;
+            }
+            for (int i = 0; i < n; ++i) {
+                if (mx == 0.0f) w[(size_t)i * m + j] = 0.0f;
+                else w[(size_t)i * m + j] = w[(size_t)i * m + j] * weight(mx, se);
+            }
+        }
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < m; ++j) out[(size_t)i * ld_out + j] = w[(size_t)i * m + j] * emb[(size_t)i * ld + j];   // cwiseProduct (:344)
 }
 
 }  // extern "C"

@@ -90,6 +90,7 @@ def lib() -> C.CDLL:
         L.orc_iou_cost_tlwh.argtypes = [f32p, C.c_void_p, C.c_int, f32p, C.c_int, f32p]
         L.orc_clamp_cost.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_float]
         L.orc_kf_xysr_affine.argtypes = [f32p, f32p, f32p, f32p]
+        L.orc_aw_max_metric.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, f32p, C.c_int]
         L.orc_ocsort_create.argtypes = [C.c_float, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
                                         C.c_float, C.c_int, C.c_float, C.c_float]
         L.orc_ocsort_create.restype = C.c_void_p
@@ -360,6 +361,15 @@ def iou_cost_tlwh(trk, det, tsu=None):
     t = np.ascontiguousarray(tsu, np.int32) if tsu is not None else None
     if out.size:
         lib().orc_iou_cost_tlwh(trk, t.ctypes.data if t is not None else None, trk.shape[0], det, det.shape[0], out)
+    return out
+
+
+def aw_max_metric(emb, w_assoc=0.5, bottom=0.5):
+    """deepocsort_assoc::compute_aw_max_metric (deepocsort.cpp:294-345)."""
+    emb = _f32(emb)
+    out = np.zeros_like(emb)
+    if emb.size:
+        lib().orc_aw_max_metric(emb, emb.shape[0], emb.shape[1], emb.shape[1], float(w_assoc), float(bottom), out, emb.shape[1])
     return out
 
 

@@ -80,6 +80,24 @@ def test_oracle_xysr_affine_vs_numpy(oracle):
     assert np.array_equal(ix, x) and np.array_equal(iP[0:2, 0:2], P[0:2, 0:2])
 
 
+def test_oracle_aw_max_metric_kats(oracle):
+    # deepocsort.cpp:294-345 by hand: a distinctive row keeps its weight, an ambiguous one loses it
+    e = np.array([[0.9, 0.1, 0.0], [0.8, 0.8, 0.2]], np.float32)
+    out = oracle.aw_max_metric(e, 0.5, 0.5)
+    f = np.float32
+    def wt(mx, se):
+        return f(1) - max(f(f(se) / f(mx)) - f(0.5), f(0)) / f(0.5)
+    rw = [wt(0.9, 0.1), wt(0.8, 0.8)]                       # 1.0 and 0.0
+    cw = [wt(0.9, 0.8), wt(0.8, 0.1), wt(0.2, 0.0)]
+    assert rw[0] == 1.0 and rw[1] == 0.0
+    want = np.array([[f(f(f(0.5) * rw[i]) * cw[j]) * e[i, j] for j in range(3)] for i in range(2)], np.float32)
+    assert np.array_equal(out, want)
+    z = oracle.aw_max_metric(np.array([[0.0, -1.0], [0.5, 0.25]], np.float32))
+    assert np.all(z[0] == 0.0)                             # row maximum 0: weights zeroed (:315-316)
+    one = oracle.aw_max_metric(np.array([[0.3, 0.7]], np.float32), 0.5, 0.5)          # a single row: columns are not weighted
+    assert np.array_equal(one, np.array([[f(0.5) * wt(0.7, 0.3) * f(0.3), f(0.5) * wt(0.7, 0.3) * f(0.7)]], np.float32))
+
+
 # ------------------------------------------------------------------ GPU parity (through the C ABI)
 @pytest.fixture()
 def _gpu():
@@ -170,3 +188,17 @@ def test_xysr_affine_bit_exact(oracle, _gpu):
     for k in range(n):
         wx, wP = oracle.kf_xysr_affine(xs[k], Ps[k], m, t)
         assert np.array_equal(gx[k], wx) and np.array_equal(gP[k], wP), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,m", [(1, 1), (1, 9), (7, 1), (33, 70), (512, 300), (2048, 2048)])
+def test_aw_max_metric_bit_exact(oracle, _gpu, n, m):
+    rng = np.random.default_rng(n * 31 + m)
+    e = rng.random((n, m)).astype(np.float32)
+    if n > 4 and m > 4:
+        e[1] = 0.0                      # an all-zero row and column: weights zeroed
+        e[:, 2] = 0.0
+        e[3, 4] = e[3].max()            # a duplicated maximum: second == max
+        e[0, 0] = -0.5
+    for w, bottom in ((0.5, 0.5), (0.75, 0.2)):
+        assert np.array_equal(api.aw_max_metric(e, w, bottom), oracle.aw_max_metric(e, w, bottom)), (n, m, w)
