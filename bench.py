@@ -209,6 +209,16 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        # rank 0 prints ONE JSON line on stdout: keep NCCL's own banner / debug output off it
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # pin this rank to the CPUs next to its GPU so that the pinned host buffers of the e2e path are first touched on
+        # the GPU's own NUMA node (8 ranks copying 29 KB per frame each otherwise all cross one socket link)
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            N.nvmlDeviceSetCpuAffinity(N.nvmlDeviceGetHandleByIndex(local))
+        except Exception:
+            pass
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     build.build()
     _lib.require_gpu()

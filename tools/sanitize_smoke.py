@@ -35,4 +35,15 @@ api.iou_distance(A, A[:17])
 api.linear_assignment(rng.random((30, 40)).astype(np.float32), 0.5)
 api.ocm_cost(np.concatenate([A, rng.random((40, 1)).astype(np.float32)], 1), A[:9], rng.normal(size=(9, 2)).astype(np.float32),
              np.concatenate([A[:9], np.ones((9, 1), np.float32)], 1), 0.2)
+trk = api.StrongSort(emb_dim=32, track_capacity=256, max_dets=64, nn_budget=4, max_cos_dist=0.4)
+for t in range(T):
+    trk.update(d[t, :c[t]], (540, 960), e[t, :c[t]])
+smp, seg = rng.normal(size=(150, 64)).astype(np.float32), np.repeat(np.arange(15), 10).astype(np.int32)
+api.nn_cosine_distance(smp, seg, 15, rng.normal(size=(70, 64)).astype(np.float32))
+mu = np.tile(np.array([100, 100, 0.5, 80, 0, 0, 0, 0], np.float32), (9, 1)); cv = np.tile(np.eye(8, dtype=np.float32) * 10, (9, 1, 1))
+api.gate_cost_matrix(rng.random((9, 40)).astype(np.float32), mu, cv, np.tile(np.array([101, 99, 0.5, 81], np.float32), (40, 1)), 0.98)
+api.iou_cost_tlwh(A[:9], A, np.ones(9, np.int32))
+api.aw_max_metric(rng.random((33, 70)).astype(np.float32))
+api.KalmanFilterXYSR().apply_affine_correction(rng.normal(size=(5, 7)).astype(np.float32), np.tile(np.eye(7, dtype=np.float32), (5, 1, 1)),
+                                               np.eye(2, dtype=np.float32), np.zeros(2, np.float32))
 print("sanitize_smoke done")
