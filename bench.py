@@ -201,6 +201,11 @@ def main():
     if args.impl == "reference":
         reference_arm(args)
         return
+    # stdout carries exactly ONE JSON line: everything else this process (or NCCL / a library inside it) writes to
+    # file descriptor 1 is sent to stderr; the line itself goes to the saved descriptor at the very end
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from motcpp_b200 import _lib, api, build, synth
@@ -332,7 +337,7 @@ def main():
                 "note": "update() is assignment-latency bound, not bandwidth bound: the reference-equivalent "
                         "work per frame is ~750k IoU tests + ~250 small exact assignment solves"}
     cpu_baseline = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:                     # reported on rank 0 at N = 1 only
         cores = os.cpu_count() or 1
         fps, dt = cpu_oracle_fps(cores, warm=150, timed=60)
         cpu_baseline = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
@@ -355,7 +360,7 @@ def main():
         "kernel": {"name": "bytetrack_step_kernel", "threads_per_cta": info["threads_per_cta"],
                    "smem_bytes": info["smem_bytes"], "ctas": info["ctas"], "launch_ms": launch_ms},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
