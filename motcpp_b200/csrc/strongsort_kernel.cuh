@@ -37,6 +37,7 @@ namespace mot {
 #define MOT_SS_THREADS 512
 #endif
 constexpr int kSsThreads = MOT_SS_THREADS;
+constexpr int kSsWarpList = 96;             // per-warp buffer of gate-passing detections (flushed when fewer than 32 slots remain)
 constexpr int kSsTableSlots = 4096;          // (row, det) -> blended appearance cost of the candidate pairs
 enum : int { kSsTentative = 1, kSsConfirmed = 2, kSsDeleted = 3 };       // strongsort.hpp TrackState
 constexpr unsigned char kSsHasFeat = 0x10;
@@ -147,6 +148,9 @@ struct SsSmem {
     unsigned short* upd;        // [cap] positions to update
     unsigned short* list_new;   // [cap]
     unsigned long long* cache;  // [kSsTableSlots]
+    unsigned short* wlist;      // [warps][kSsWarpList]
+    float* wgd;                 // [warps][kSsWarpList]
+    int* ectl;                  // [4] appearance-stage row counter
     BlockScratch* bs;
     LapWorkspace lap;
 };
@@ -162,6 +166,7 @@ MOT_HD constexpr size_t ss_smem_bytes(int cap, int d_max, int e_cap) {
     b += 2 * lap_align16(sizeof(int) * (size_t)cap);
     b += 2 * lap_align16(sizeof(unsigned short) * (size_t)cap);
     b += lap_align16(sizeof(unsigned long long) * kSsTableSlots);
+    b += lap_align16(sizeof(unsigned short) * (kSsThreads / 32) * kSsWarpList) + lap_align16(sizeof(float) * (kSsThreads / 32) * kSsWarpList) + 16;
     b += lap_align16(sizeof(BlockScratch));
     b += lap_smem_bytes(cap, d_max, e_cap);
     return b;
@@ -185,6 +190,9 @@ __device__ __forceinline__ void ss_carve(unsigned char* p, int cap, int d_max, i
     s.upd = (unsigned short*)p;        p += lap_align16(sizeof(unsigned short) * (size_t)cap);
     s.list_new = (unsigned short*)p;   p += lap_align16(sizeof(unsigned short) * (size_t)cap);
     s.cache = (unsigned long long*)p;  p += lap_align16(sizeof(unsigned long long) * kSsTableSlots);
+    s.wlist = (unsigned short*)p;      p += lap_align16(sizeof(unsigned short) * (kSsThreads / 32) * kSsWarpList);
+    s.wgd = (float*)p;                 p += lap_align16(sizeof(float) * (kSsThreads / 32) * kSsWarpList);
+    s.ectl = (int*)p;                  p += 16;
     s.bs = (BlockScratch*)p;           p += lap_align16(sizeof(BlockScratch));
     lap_carve(p, cap, d_max, e_cap, s.lap);
 }
@@ -366,13 +374,21 @@ __device__ __forceinline__ void ss_frame(const SsArgs& a, const SsStream& st, Ss
     const bool stage_a = n_d > 0 && n_c > 0;
     if (stage_a) {
         for (int h = tid; h < kSsTableSlots; h += nt) sm.cache[h] = 0ull;
+        if (tid == 0) sm.ectl[0] = 0;
         block_lap_begin(sm.lap, n_c, n_d);
         const SsAppCost app{sm.cache};
         if (have_feat) {
             // one warp per confirmed track: gate every detection (lanes), then the whole warp evaluates the nearest-
             // neighbour cosine of each gate-passing detection against the track's gallery ring
             const float thr = a.p.max_cos_dist, lam = a.p.mc_lambda;
-            for (int r = warp; r < n_c; r += nwarps) {
+            // rows are handed out dynamically (a row's cost depends on how many detections pass its gate)
+            unsigned short* wl = sm.wlist + warp * kSsWarpList;               // this warp's gate-passing detections ...
+            float* wg = sm.wgd + warp * kSsWarpList;                          // ... and their gating distances
+            for (;;) {
+                int r = 0;
+                if (lane == 0) r = atomicAdd(&sm.ectl[0], 1);
+                r = __shfl_sync(kFullMask, r, 0);
+                if (r >= n_c) break;
                 const int slot = st.list[sm.rows_a[r]];
                 const int ns = st.ring_n[slot];
                 if (ns == 0) continue;                                           // no samples: the row is 1e5 (:271)
@@ -386,48 +402,61 @@ __device__ __forceinline__ void ss_frame(const SsArgs& a, const SsStream& st, Ss
                 const float rad = xadd(xmul(st.grad[slot], 1.001f), 1e-6f);
                 const float slack = xadd(1e-4f, xmul(1e-6f, (float)dim));
                 const bool can_prune = lam > 1e-3f && ns > 2;
+                int nl = 0;                                                      // warp-uniform fill of wl / wg
+                // the collected pairs: (1) the pruning bound, one pair per LANE (32 independent dot products in flight);
+                // (2) the survivors' exact nearest-neighbour cosine, one gallery row per lane
+                auto flush = [&]() {
+                    __syncwarp();
+                    for (int b0 = 0; b0 < nl; b0 += 32) {
+                        const int k = b0 + lane;
+                        bool keep = k < nl;
+                        if (keep && can_prune) {
+                            const float lower = xsub(xsub(xsub(1.0f, thread_dot_lanes32(center, st.dfeat + (size_t)wl[k] * dim, dim)), rad), slack);   // <= min_s c_s
+                            const float tau = xadd(xdiv(xsub(thr, xmul(xsub(1.0f, lam), wg[k])), lam), slack);  // candidates have c <= tau
+                            keep = !(lower > tau);
+                        }
+                        unsigned todo = __ballot_sync(kFullMask, keep);
+                        while (todo) {
+                            const int l = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            const int d = wl[b0 + l];
+                            const float gdl = wg[b0 + l];
+                            const float* f = st.dfeat + (size_t)d * dim;
+                            float best = 3.0e38f;
+                            for (int sidx = lane; sidx < ns; sidx += 32) {
+                                const float c = xsub(1.0f, thread_dot_lanes32(ring + (size_t)sidx * dim, f, dim));   // :333
+                                best = (c < best) ? c : best;                                              // minCoeff (:295)
+                            }
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) { const float t = __shfl_xor_sync(kFullMask, best, o); best = (t < best) ? t : best; }
+                            const float blended = gate_blend(best, gdl, lam, kInftyCost);                 // :484-487
+                            if (lane == 0 && blended <= thr) {
+                                if (app.insert(r, d, blended)) {
+                                    const int e = atomicAdd(&sm.lap.ctl[0], 1);
+                                    if (e < sm.lap.e_cap) sm.lap.scratch_a[e] = (r << 16) | d;
+                                    else sm.lap.ctl[1] = 1;
+                                } else {
+                                    atomicOr(&st.hdr[kHdrError], (int)kErrTable);
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    nl = 0;
+                };
                 for (int j0 = 0; j0 < n_d; j0 += 32) {
                     const int j = j0 + lane;
                     float gd = 0.0f;
                     bool pass = false;
                     if (j < n_d) { gd = gate_distance(gr, sm.det_z[j], false); pass = !(gd > kGatingThreshold); }
-                    unsigned todo = __ballot_sync(kFullMask, pass);
-                    if (lane == 0 && todo) atomicAdd(&sm.lap.ctl[7], __popc(todo));
-                    while (todo) {
-                        const int l = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        const int d = j0 + l;
-                        const float gdl = __shfl_sync(kFullMask, gd, l);
-                        const float* f = st.dfeat + (size_t)d * dim;
-                        if (can_prune) {
-                            const float lower = xsub(xsub(xsub(1.0f, warp_dot(center, f, dim)), rad), slack);       // <= min_s c_s
-                            const float tau = xadd(xdiv(xsub(thr, xmul(xsub(1.0f, lam), gdl)), lam), slack);      // candidates have c <= tau
-                            if (lower > tau) continue;
-                        }
-                        // one gallery sample per LANE (32 independent row streams in flight instead of one dependent
-                        // warp-wide dot product after another); each lane evaluates the oracle's "lanes32" sum on its own
-                        float best = 3.0e38f;
-                        for (int s = lane; s < ns; s += 32) {
-                            const float c = xsub(1.0f, thread_dot_lanes32(ring + (size_t)s * dim, f, dim));   // :333
-                            best = (c < best) ? c : best;                                                  // minCoeff (:295)
-                        }
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) { const float t = __shfl_xor_sync(kFullMask, best, o); best = (t < best) ? t : best; }
-                        const float blended = gate_blend(best, gdl, lam, kInftyCost);                     // :484-487
-#if defined(MOT_CPUSIM) && defined(SS_DEBUG)
-                        if (lane == 0) printf("A r=%d slot=%d d=%d ns=%d best=%g gd=%g blended=%g\n", r, slot, d, ns, best, gdl, blended);
-#endif
-                        if (lane == 0 && blended <= thr) {
-                            if (app.insert(r, d, blended)) {
-                                const int e = atomicAdd(&sm.lap.ctl[0], 1);
-                                if (e < sm.lap.e_cap) sm.lap.scratch_a[e] = (r << 16) | d;
-                                else sm.lap.ctl[1] = 1;
-                            } else {
-                                atomicOr(&st.hdr[kHdrError], (int)kErrTable);
-                            }
-                        }
-                    }
+                    const unsigned m = __ballot_sync(kFullMask, pass);
+                    if (m == 0u) continue;
+                    if (pass) { const int pos = nl + __popc(m & ((1u << lane) - 1u)); wl[pos] = (unsigned short)j; wg[pos] = gd; }
+                    nl += __popc(m);
+                    if (lane == 0) atomicAdd(&sm.lap.ctl[7], __popc(m));
+                    if (nl > kSsWarpList - 32) flush();
                 }
+                flush();
             }
         }
         __syncthreads();
