@@ -312,7 +312,7 @@ def main():
         e2e = {"value": world * S * F * K / float(dtt.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(S * F * (N_DETS * 6 * 4 + 4)),
                "d2h_bytes_per_step": int(S * F * (LD_OUT * 8 * 4 + 4)),
-               "api": "mot_engine_update_host (pinned host buffers; copy-in / kernel / copy-out pipelined over %d frame chunks)" % min(16, F // 2),
+               "api": "mot_engine_update_host (pinned host buffers; copy-in / kernel / copy-out pipelined over %d frame chunks)" % min(32, F // 2),
                "checksum_rows": int(h_no.sum())}
 
     if rank != 0:

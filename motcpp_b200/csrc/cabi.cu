@@ -66,7 +66,7 @@ int sm_count() {
     return n;
 }
 
-constexpr int kMaxChunks = 16;
+constexpr int kMaxChunks = 32;
 
 }  // namespace
 
