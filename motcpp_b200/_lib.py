@@ -77,6 +77,7 @@ SYMBOLS = {
     "mot_kf_update": (_I, [_I, _VP, _VP, _VP, _LL, _VP, _VP]),
     "mot_kf_gating": (_I, [_I, _VP, _I, _VP, _I, _I, _I, _VP, _VP]),
     "mot_cost_iou": (_I, [_VP, _I, _VP, _I, _VP, _VP, _I, _I, _VP]),
+    "mot_cost_iou_variant": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _VP, _I, _VP]),
     "mot_cost_ocm": (_I, [_VP, _I, _VP, _VP, _VP, _I, _F, _VP, _VP, _I, _VP]),
     "mot_cost_cosine": (_I, [_VP, _I, _VP, _I, _I, _VP, _I, _VP]),
     "mot_cost_nn_cosine": (_I, [_VP, _VP, _I, _I, _VP, _I, _I, _VP, _I, _VP]),

@@ -113,6 +113,32 @@ def iou_distance_fused(atracks, btracks, det_confs) -> np.ndarray:
     return iou_batch(atracks, btracks, _mode=2, _conf=det_confs)
 
 
+_ASSO_KINDS = {"hmiou": 3, "giou": 4, "diou": 5, "centroid": 6}
+
+
+def asso_batch(asso_func: str, bboxes1, bboxes2, frame_width: int = 0, frame_height: int = 0) -> np.ndarray:
+    """AssociationFunction (iou.hpp:371-411) for "iou", "hmiou", "giou", "diou", "centroid": (N,4),(M,4) xyxy -> (N,M),
+    evaluated pair-wise (the reference's hmiou / giou / diou expressions only line up for M == 1)."""
+    if asso_func == "iou":
+        return iou_batch(bboxes1, bboxes2)
+    if asso_func not in _ASSO_KINDS:
+        raise ValueError("Invalid association mode: " + asso_func)                 # iou.hpp:407
+    a = np.ascontiguousarray(bboxes1, np.float32).reshape(-1, 4)
+    b = np.ascontiguousarray(bboxes2, np.float32).reshape(-1, 4)
+    n, m = a.shape[0], b.shape[0]
+    if n == 0 or m == 0:
+        return np.zeros((n, m), np.float32)
+    _lib.require_gpu()
+    ld = (m + 3) // 4 * 4
+    da, db, do = DeviceArray.from_host(a), DeviceArray.from_host(b), DeviceArray((n, ld))
+    try:
+        check(load().mot_cost_iou_variant(da.ptr, n, db.ptr, m, _ASSO_KINDS[asso_func], int(frame_width), int(frame_height),
+                                          do.ptr, ld, None))
+    except MotError as e:
+        _raise(e)
+    return np.ascontiguousarray(do.download()[:, :m])
+
+
 def ocm_cost(detections, trackers, velocities, previous_obs, vdc_weight: float):
     """OC-SORT association cost (ocsort_assoc::associate, ocsort.cpp:617-700): detections (N,5) [xyxy,score],
     trackers (M,4) predicted boxes, velocities (M,2) (dy,dx), previous_obs (M,5) -> (cost, iou), both (N,M),

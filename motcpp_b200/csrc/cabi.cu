@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -844,6 +845,23 @@ int mot_cost_iou(const float* a, int n, const float* b, int m, const float* conf
     const int row_groups = (n + mot::kCostTileRows - 1) / mot::kCostTileRows;
     dim3 grid((unsigned)std::min(row_groups, sm_count() * 8), (unsigned)std::min(col_tiles, 64));
     mot::iou_cost_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, n, b, m, conf, out, ld, mode);
+    MOT_CUDA(cudaGetLastError());
+    return MOT_OK;
+}
+
+int mot_cost_iou_variant(const float* a, int n, const float* b, int m, int kind, int frame_w, int frame_h, float* out, int ld,
+                         void* stream) {
+    if (n < 0 || m < 0 || ld < m) return fail(MOT_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (kind < mot::kVarHmIou || kind > mot::kVarCentroid)
+        return fail(MOT_ERR_INVALID_ARGUMENT, "Invalid association mode: %d (3 hmiou, 4 giou, 5 diou, 6 centroid)", kind);   // iou.hpp:407
+    if (n == 0 || m == 0) return MOT_OK;
+    if (!a || !b || !out) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
+    if (int rc = require_device()) return rc;
+    const float norm = static_cast<float>(std::sqrt((double)(frame_w * frame_w + frame_h * frame_h)));     // iou.hpp:325
+    const int col_tiles = (m + mot::kCostTileCols - 1) / mot::kCostTileCols;
+    const int row_groups = (n + mot::kCostTileRows - 1) / mot::kCostTileRows;
+    dim3 grid((unsigned)std::min(row_groups, sm_count() * 8), (unsigned)std::min(col_tiles, 64));
+    mot::iou_variant_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, n, b, m, kind, norm, out, ld);
     MOT_CUDA(cudaGetLastError());
     return MOT_OK;
 }

@@ -107,4 +107,34 @@ struct IouCost {
     __device__ __forceinline__ double pair_bias(int, int) const { return 0.0; }
 };
 
+// hmiou / giou / diou / centroid for ONE pair (include/motcpp/utils/iou.hpp:119-330, pair-wise: see kernels_cost.cuh)
+enum : int { kVarHmIou = 3, kVarGIoU = 4, kVarDIoU = 5, kVarCentroid = 6 };
+__device__ __forceinline__ float iou_variant_pair(int kind, float4 p, float area_p, float4 q, float norm) {
+    if (kind == kVarCentroid) {
+        const float dx = xsub(xdiv(xadd(p.x, p.z), 2.0f), xdiv(xadd(q.x, q.z), 2.0f));
+        const float dy = xsub(xdiv(xadd(p.y, p.w), 2.0f), xdiv(xadd(q.y, q.w), 2.0f));
+        return xsub(1.0f, xdiv(xsqrt(xadd(xmul(dx, dx), xmul(dy, dy))), norm));
+    }
+    const float iou = iou_pair(p, area_p, q);
+    if (kind == kVarHmIou) {
+        const float ih = fmaxf(xsub(fminf(p.w, q.w), fmaxf(p.y, q.y)), 0.0f);
+        const float uh = fmaxf(xsub(fmaxf(p.w, q.w), fminf(p.y, q.y)), 1e-10f);
+        return xmul(iou, xdiv(ih, uh));
+    }
+    const float ox = xsub(fmaxf(p.z, q.z), fminf(p.x, q.x)), oy = xsub(fmaxf(p.w, q.w), fminf(p.y, q.y));
+    if (kind == kVarGIoU) {
+        const float enc = xmul(ox, oy);
+        const float a12 = xadd(area_p, box_area(q));
+        const float inter = xdiv(xmul(iou, a12), xadd(iou, 1e-10f));
+        const float uni = xsub(a12, inter);
+        const float g = xsub(iou, xdiv(xsub(enc, uni), xadd(enc, 1e-10f)));
+        return xdiv(xadd(g, 1.0f), 2.0f);
+    }
+    const float dx = xsub(xdiv(xadd(p.x, p.z), 2.0f), xdiv(xadd(q.x, q.z), 2.0f));
+    const float dy = xsub(xdiv(xadd(p.y, p.w), 2.0f), xdiv(xadd(q.y, q.w), 2.0f));
+    const float inner = xadd(xmul(dx, dx), xmul(dy, dy));
+    const float outer = xadd(xmul(ox, ox), xmul(oy, oy));
+    return xdiv(xadd(xsub(iou, xdiv(inner, xadd(outer, 1e-10f))), 1.0f), 2.0f);
+}
+
 }  // namespace mot

@@ -264,4 +264,43 @@ __global__ void __launch_bounds__(256) aw_apply_kernel(const float* __restrict__
     }
 }
 
+// hmiou_batch / giou_batch / diou_batch / centroid_batch (reference include/motcpp/utils/iou.hpp:119-330),
+// evaluated pair-wise - the reference's own expressions only line up when the second set has one row (trap 11), which is
+// the domain on which parity is defined.  Same tiling as iou_cost_kernel.
+__global__ void __launch_bounds__(256) iou_variant_kernel(const float* __restrict__ a, int n, const float* __restrict__ b, int m,
+                                                          int kind, float norm, float* __restrict__ out, int ld) {
+    __shared__ float4 s_box[kCostTileCols];
+    const int tid = (int)threadIdx.x;
+    const int tx = tid & 31, ty = tid >> 5;
+    const int col_tiles = (m + kCostTileCols - 1) / kCostTileCols;
+    const int row_groups = (n + kCostTileRows - 1) / kCostTileRows;
+    const bool vec_ok = ((ld & 3) == 0) && ((((size_t)out) & 15) == 0);
+    for (int ct = (int)blockIdx.y; ct < col_tiles; ct += (int)gridDim.y) {
+        const int c0 = ct * kCostTileCols;
+        const int cn = min(kCostTileCols, m - c0);
+        __syncthreads();
+        for (int k = tid; k < cn; k += 256) s_box[k] = *reinterpret_cast<const float4*>(b + (size_t)(c0 + k) * 4);
+        __syncthreads();
+        for (int rg = (int)blockIdx.x; rg < row_groups; rg += (int)gridDim.x) {
+            const int i = rg * kCostTileRows + ty;
+            if (i >= n) continue;
+            const float4 ra = *reinterpret_cast<const float4*>(a + (size_t)i * 4);
+            const float area = box_area(ra);
+            float* orow = out + (size_t)i * ld + c0;
+            for (int q = tx * 4; q < cn; q += 128) {
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = (q + e < cn) ? iou_variant_pair(kind, ra, area, s_box[q + e], norm) : 0.0f;
+                if (vec_ok && q + 3 < cn) {
+                    *reinterpret_cast<float4*>(orow + q) = make_float4(v[0], v[1], v[2], v[3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (q + e < cn) orow[q + e] = v[e];
+                }
+            }
+        }
+    }
+}
+
 }  // namespace mot

@@ -105,4 +105,52 @@ void orc_embedding_distance(const float* t, int n, const float* d, int m, int di
     }
 }
 
+// hmiou_batch / giou_batch / diou_batch / centroid_batch (include/motcpp/utils/iou.hpp:119-146, :151-187, :258-293,
+// :298-330), evaluated PAIR-WISE: element (i, j) from box a[i] and box b[j].  That is what the reference's expressions
+// mean and what they compute whenever b has ONE row (its `replicate(N, 1)` of a column of b only lines up for M == 1;
+// SURVEY 8 trap 11), which is also all its tests exercise (tests/test_iou.cpp:74-115).  kind: 3 hmiou, 4 giou, 5 diou,
+// 6 centroid (frame_w / frame_h only matter there).  ciou needs atan and is not restated.
+void orc_iou_variant(const float* a, int n, const float* b, int m, int kind, int frame_w, int frame_h, float* out) {
+    const float norm = static_cast<float>(std::sqrt(frame_w * frame_w + frame_h * frame_h));            // :325
+    for (int i = 0; i < n; ++i) {
+        const float* p = a + 4 * i;
+        for (int j = 0; j < m; ++j) {
+            const float* q = b + 4 * j;
+            float iou1;
+            orc_iou_batch(p, 1, q, 1, &iou1);
+            float r = 0.0f;
+            if (kind == 3) {                                                                            // :128-145
+                const float ih = std::max(std::min(p[3], q[3]) - std::max(p[1], q[1]), 0.0f);
+                const float uh = std::max(std::max(p[3], q[3]) - std::min(p[1], q[1]), 1e-10f);
+                r = iou1 * (ih / uh);
+            } else if (kind == 4) {                                                                     // :162-186
+                const float wc = std::max(p[2], q[2]) - std::min(p[0], q[0]);
+                const float hc = std::max(p[3], q[3]) - std::min(p[1], q[1]);
+                const float enc = wc * hc;
+                const float a1 = (p[2] - p[0]) * (p[3] - p[1]), a2 = (q[2] - q[0]) * (q[3] - q[1]);
+                const float inter = iou1 * (a1 + a2) / (iou1 + 1e-10f);
+                const float uni = a1 + a2 - inter;
+                const float g = iou1 - (enc - uni) / (enc + 1e-10f);
+                r = (g + 1.0f) / 2.0f;
+            } else if (kind == 5) {                                                                     // :269-292
+                const float cx1 = (p[0] + p[2]) / 2.0f, cy1 = (p[1] + p[3]) / 2.0f;
+                const float cx2 = (q[0] + q[2]) / 2.0f, cy2 = (q[1] + q[3]) / 2.0f;
+                const float dx = cx1 - cx2, dy = cy1 - cy2;
+                const float inner = dx * dx + dy * dy;
+                const float ox = std::max(p[2], q[2]) - std::min(p[0], q[0]);
+                const float oy = std::max(p[3], q[3]) - std::min(p[1], q[1]);
+                const float outer = ox * ox + oy * oy;
+                const float d = iou1 - inner / (outer + 1e-10f);
+                r = (d + 1.0f) / 2.0f;
+            } else {                                                                                    // :308-329
+                const float dx = (p[0] + p[2]) / 2.0f - (q[0] + q[2]) / 2.0f;
+                const float dy = (p[1] + p[3]) / 2.0f - (q[1] + q[3]) / 2.0f;
+                const float dist = std::sqrt(dx * dx + dy * dy);
+                r = 1.0f - dist / norm;
+            }
+            out[(size_t)i * m + j] = r;
+        }
+    }
+}
+
 }  // extern "C"

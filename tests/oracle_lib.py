@@ -90,6 +90,7 @@ def lib() -> C.CDLL:
         L.orc_iou_cost_tlwh.argtypes = [f32p, C.c_void_p, C.c_int, f32p, C.c_int, f32p]
         L.orc_clamp_cost.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_float]
         L.orc_kf_xysr_affine.argtypes = [f32p, f32p, f32p, f32p]
+        L.orc_iou_variant.argtypes = [f32p, C.c_int, f32p, C.c_int, C.c_int, C.c_int, C.c_int, f32p]
         L.orc_aw_max_metric.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, f32p, C.c_int]
         L.orc_ocsort_create.argtypes = [C.c_float, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
                                         C.c_float, C.c_int, C.c_float, C.c_float]
@@ -361,6 +362,15 @@ def iou_cost_tlwh(trk, det, tsu=None):
     t = np.ascontiguousarray(tsu, np.int32) if tsu is not None else None
     if out.size:
         lib().orc_iou_cost_tlwh(trk, t.ctypes.data if t is not None else None, trk.shape[0], det, det.shape[0], out)
+    return out
+
+
+def iou_variant(kind, a, b, frame_w=0, frame_h=0):
+    """pair-wise hmiou (3) / giou (4) / diou (5) / centroid (6), include/motcpp/utils/iou.hpp:119-330."""
+    a, b = _f32(a).reshape(-1, 4), _f32(b).reshape(-1, 4)
+    out = np.zeros((a.shape[0], b.shape[0]), np.float32)
+    if out.size:
+        lib().orc_iou_variant(a, a.shape[0], b, b.shape[0], int(kind), int(frame_w), int(frame_h), out)
     return out
 
 

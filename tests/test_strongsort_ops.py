@@ -98,6 +98,26 @@ def test_oracle_aw_max_metric_kats(oracle):
     assert np.array_equal(one, np.array([[f(0.5) * wt(0.7, 0.3) * f(0.3), f(0.5) * wt(0.7, 0.3) * f(0.7)]], np.float32))
 
 
+def test_oracle_iou_variant_kats(oracle):
+    # reference tests/test_iou.cpp:74-115 (box1 = [0,0,100,100], box2 = [50,50,150,150], box3 = [200,200,300,300]) + by hand
+    b1, b2, b3 = [[0, 0, 100, 100]], [[50, 50, 150, 150]], [[200, 200, 300, 300]]
+    f = np.float32
+    iou = f(2500) / f(17500)
+    g = oracle.iou_variant(4, b1, b2)[0, 0]
+    inter = iou * f(20000) / (iou + f(1e-10))
+    want_g = (iou - (f(22500) - (f(20000) - inter)) / (f(22500) + f(1e-10)) + f(1)) / f(2)
+    assert 0.0 <= g <= 1.0 and g == want_g                                        # enclosing box 150 x 150
+    d = oracle.iou_variant(5, b1, b2)[0, 0]
+    assert 0.0 <= d <= 1.0 and d == (iou - f(5000) / (f(45000) + f(1e-10)) + f(1)) / f(2)   # centres 50 apart per axis
+    c = oracle.iou_variant(6, b1, b3, 640, 480)[0, 0]
+    assert 0.0 < c < 1.0 and c == f(1) - f(np.sqrt(f(80000))) / f(800.0)           # sqrt(640^2 + 480^2) = 800
+    h = oracle.iou_variant(3, b1, b2)[0, 0]
+    assert h == iou * (f(50) / f(150))
+    # identical boxes: diou is 1; giou is 0.5, because the reference recovers the intersection as iou (a1 + a2) / (iou + 1e-10)
+    # (iou.hpp:181) - twice the true value at iou = 1 - and its union collapses to 0
+    assert oracle.iou_variant(5, b1, b1)[0, 0] == 1.0 and oracle.iou_variant(4, b1, b1)[0, 0] == 0.5
+
+
 # ------------------------------------------------------------------ GPU parity (through the C ABI)
 @pytest.fixture()
 def _gpu():
@@ -202,3 +222,20 @@ def test_aw_max_metric_bit_exact(oracle, _gpu, n, m):
         e[0, 0] = -0.5
     for w, bottom in ((0.5, 0.5), (0.75, 0.2)):
         assert np.array_equal(api.aw_max_metric(e, w, bottom), oracle.aw_max_metric(e, w, bottom)), (n, m, w)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,m", [(1, 1), (40, 1), (7, 5), (300, 517)])
+def test_iou_variants_bit_exact(oracle, _gpu, n, m):
+    rng = np.random.default_rng(n * 13 + m)
+    def boxes(k):
+        xy = rng.uniform(0, 600, (k, 2)); wh = rng.uniform(5, 200, (k, 2))
+        return np.concatenate([xy, xy + wh], 1).astype(np.float32)
+    a, b = boxes(n), boxes(m)
+    b[0] = a[0]
+    for name, kind in (("hmiou", 3), ("giou", 4), ("diou", 5), ("centroid", 6)):
+        got = api.asso_batch(name, a, b, 1920, 1080)
+        assert np.array_equal(got, oracle.iou_variant(kind, a, b, 1920, 1080)), (name, n, m)
+    assert np.array_equal(api.asso_batch("iou", a, b), oracle.iou_batch(a, b))
+    with pytest.raises(ValueError):
+        api.asso_batch("ciou", a, b)
