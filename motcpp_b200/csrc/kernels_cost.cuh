@@ -218,7 +218,15 @@ __global__ void __launch_bounds__(256) aw_row_top2_kernel(const float* __restric
     for (int i = (int)blockIdx.x * wpc + warp_id(); i < n; i += (int)gridDim.x * wpc) {
         Top2 t{-INFINITY, -INFINITY};
         const float* row = emb + (size_t)i * ld;
-        for (int j = lane; j < m; j += 32) top2_push(t, row[j]);
+        if ((ld & 3) == 0 && ((((size_t)emb) & 15) == 0)) {                       // 16 B per lane and iteration, four iterations in flight
+            const float4* r4 = reinterpret_cast<const float4*>(row);
+            const int m4 = m >> 2;
+#pragma unroll 4
+            for (int q = lane; q < m4; q += 32) { const float4 v = r4[q]; top2_push(t, v.x); top2_push(t, v.y); top2_push(t, v.z); top2_push(t, v.w); }
+            for (int j = (m4 << 2) + lane; j < m; j += 32) top2_push(t, row[j]);
+        } else {
+            for (int j = lane; j < m; j += 32) top2_push(t, row[j]);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             Top2 b{__shfl_xor_sync(kFullMask, t.mx, o), __shfl_xor_sync(kFullMask, t.se, o)};
@@ -235,8 +243,17 @@ __global__ void __launch_bounds__(256) aw_col_top2_kernel(const float* __restric
     for (int c0 = (int)blockIdx.x * 32; c0 < m; c0 += (int)gridDim.x * 32) {
         const int j = c0 + tx;
         Top2 t{-INFINITY, -INFINITY};
-        if (j < m)
-            for (int i = ty; i < n; i += 8) top2_push(t, emb[(size_t)i * ld + j]);
+        if (j < m) {
+            int i = ty;
+            for (; i + 56 < n; i += 64) {                                          // eight independent row loads in flight
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = emb[(size_t)(i + 8 * u) * ld + j];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) top2_push(t, v[u]);
+            }
+            for (; i < n; i += 8) top2_push(t, emb[(size_t)i * ld + j]);
+        }
         part[ty][tx] = t;
         __syncthreads();
         if (ty == 0 && j < m) {

@@ -308,6 +308,25 @@ def main():
         byts = 4.0 * NT * M
         emit(f"iou_tlwh_cost_{NT}x{M}", ms, bytes=byts, gbs=byts / ms[0] / 1e6, peak_gbs=HBM, frac=byts / ms[0] / 1e6 / HBM, bound="hbm")
 
+    # ---------------- DeepOC-SORT adaptive weights (8f-2) and the IoU variants (8f-4)
+    if want("aw_max"):
+        N = 2048 if args.quick else 8192
+        e = torch.rand((N, N), device=dev)
+        out = torch.empty((N, N), device=dev)
+        ms = timeit(lambda: api.check(lib.mot_cost_aw_max_metric(e.data_ptr(), N, N, N, 0.5, 0.5, out.data_ptr(), N, st)))
+        byts = 4.0 * N * N * 2          # algorithmic: the matrix read once and written once (the kernels read it three times)
+        emit(f"aw_max_metric_{N}x{N}", ms, bytes=byts, gbs=byts / ms[0] / 1e6, peak_gbs=HBM, frac=byts / ms[0] / 1e6 / HBM, bound="hbm",
+             note="row top-2, column top-2, apply: three streaming passes + stream-ordered workspace allocation")
+    if want("iou_variant"):
+        N = 2048 if args.quick else 8192
+        xy = torch.rand((N, 2), device=dev) * 1500
+        a = torch.cat([xy, xy + 20 + torch.rand((N, 2), device=dev) * 200], 1).contiguous()
+        out = torch.empty((N, N), device=dev)
+        for kind, name in ((3, "hmiou"), (4, "giou"), (5, "diou"), (6, "centroid")):
+            ms = timeit(lambda: api.check(lib.mot_cost_iou_variant(a.data_ptr(), N, a.data_ptr(), N, kind, 1920, 1080, out.data_ptr(), N, st)))
+            byts = 4.0 * N * N
+            emit(f"{name}_cost_{N}x{N}", ms, bytes=byts, gbs=byts / ms[0] / 1e6, peak_gbs=HBM, frac=byts / ms[0] / 1e6 / HBM, bound="hbm")
+
 
 if __name__ == "__main__":
     main()

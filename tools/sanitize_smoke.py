@@ -46,4 +46,6 @@ api.iou_cost_tlwh(A[:9], A, np.ones(9, np.int32))
 api.aw_max_metric(rng.random((33, 70)).astype(np.float32))
 api.KalmanFilterXYSR().apply_affine_correction(rng.normal(size=(5, 7)).astype(np.float32), np.tile(np.eye(7, dtype=np.float32), (5, 1, 1)),
                                                np.eye(2, dtype=np.float32), np.zeros(2, np.float32))
+for _name in ("hmiou", "giou", "diou", "centroid"):
+    api.asso_batch(_name, A, A[:17], 640, 480)
 print("sanitize_smoke done")
