@@ -314,8 +314,9 @@ def linear_assignment_arrays(cost_matrix, thresh: float):
 
 
 def linear_assignment_reference_order(cost_matrices, thresh: float):
-    """The reference's dense LAPJV itself on the GPU (mot_lap_jv_batch_device): cost (P, n, m) or (n, m) with
-    n + m <= 384 -> (row2col, col2row), ties resolved exactly as utils::linear_assignment resolves them."""
+    """The reference's dense LAPJV itself on the GPU (mot_lap_jv_batch_device): cost (P, n, m) or (n, m) ->
+    (row2col, col2row), ties resolved exactly as utils::linear_assignment resolves them (one warp per problem while
+    n + m <= 384, one CTA per problem above that)."""
     cost = np.ascontiguousarray(cost_matrices, np.float32)
     single = cost.ndim == 2
     if single:

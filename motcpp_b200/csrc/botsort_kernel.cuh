@@ -21,6 +21,7 @@
 // fp32 sums: bit-identical costs.  The dense N x M x D contraction the reference computes is available as the
 // tcgen05 kernel behind mot_cost_cosine (kernels_cosine.cuh).
 #pragma once
+#include "shapes.cuh"
 #include "block_utils.cuh"
 #include "cost_device.cuh"
 #include "kf_device.cuh"
@@ -194,7 +195,7 @@ __device__ __forceinline__ float warp_dot(const float* __restrict__ x, const flo
     return lanes32_reduce(acc);
 }
 // the same value computed by ONE thread (assignment-solver fallback when a pair is not in the table)
-__device__ __noinline__ float thread_dot_lanes32(const float* __restrict__ x, const float* __restrict__ y, int dim) {
+static __device__ __noinline__ float thread_dot_lanes32(const float* __restrict__ x, const float* __restrict__ y, int dim) {
     const float4* xv = reinterpret_cast<const float4*>(x);
     const float4* yv = reinterpret_cast<const float4*>(y);
     const int nq = dim >> 2;
@@ -760,7 +761,7 @@ __global__ void __launch_bounds__(kBotThreads) botsort_step_kernel(BotArgs a) {
 }
 
 // BotSort ctor / reset(): everything cleared, ids restart at 0 (botsort.cpp:249,257)
-__global__ void botsort_reset_kernel(unsigned char* state, BotLayout L, int S) {
+static __global__ void botsort_reset_kernel(unsigned char* state, BotLayout L, int S) {
     for (int s = (int)blockIdx.x; s < S; s += (int)gridDim.x) {
         BotStream st = BotStream::at(state + (size_t)s * L.stride, L);
         for (int k = (int)threadIdx.x; k < L.cap; k += (int)blockDim.x) {

@@ -14,6 +14,7 @@
 // All reference quirks listed in SURVEY.md section 8 "parity traps" are kept (predictions are
 // written back only for matched tracks, etc.).  IDs come from a per-stream counter.
 #pragma once
+#include "shapes.cuh"
 #include "block_utils.cuh"
 #include "cost_device.cuh"
 #include "kf_device.cuh"
@@ -505,13 +506,9 @@ __global__ void __launch_bounds__(kBtThreads, MOT_BT_MINBLOCKS) bytetrack_step_k
     }
 }
 
-// The (track capacity, detections per frame, candidate-edge buffer) shapes the library is built for.
-struct BtShape { int cap, d_max, e_cap; };
-constexpr BtShape kBtShapes[] = {{256, 64, 1024}, {1536, 512, 4096}, {2048, 512, 4096}, {3072, 1024, 4096}};
-constexpr int kNumBtShapes = sizeof(kBtShapes) / sizeof(kBtShapes[0]);
 
 // reset / first-time initialisation of the per-stream slabs
-__global__ void bytetrack_reset_kernel(unsigned char* state, BtLayout L, int S, int keep_id_counter) {
+static __global__ void bytetrack_reset_kernel(unsigned char* state, BtLayout L, int S, int keep_id_counter) {
     for (int s = (int)blockIdx.x; s < S; s += (int)gridDim.x) {
         BtStream st = BtStream::at(state + (size_t)s * L.stride, L);
         for (int k = (int)threadIdx.x; k < L.cap; k += (int)blockDim.x) {

@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 
+#include "engine_launch.h"
 #include "bytetrack_kernel.cuh"
 #include "kernels_cost.cuh"
 #include "kernels_kf.cuh"
@@ -119,134 +120,6 @@ static int engine_reset_impl(mot_engine* e, int keep_ids) {
     return MOT_OK;
 }
 
-template <int I>
-static cudaError_t bt_set_smem(size_t bytes) {
-    constexpr mot::BtShape sh = mot::kBtShapes[I];
-    return cudaFuncSetAttribute(mot::bytetrack_step_kernel<sh.cap, sh.d_max, sh.e_cap>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-}
-template <int I>
-static void bt_launch_one(int grid, size_t smem, cudaStream_t st, const mot::BtArgs& a) {
-    constexpr mot::BtShape sh = mot::kBtShapes[I];
-    mot::bytetrack_step_kernel<sh.cap, sh.d_max, sh.e_cap><<<grid, mot::kBtThreads, smem, st>>>(a);
-}
-static cudaError_t bt_prepare(int shape, size_t smem) {
-    switch (shape) {
-        case 0: return bt_set_smem<0>(smem);
-        case 1: return bt_set_smem<1>(smem);
-        case 2: return bt_set_smem<2>(smem);
-        default: return bt_set_smem<3>(smem);
-    }
-}
-static void bt_launch(int shape, int grid, size_t smem, cudaStream_t st, const mot::BtArgs& a) {
-    switch (shape) {
-        case 0: bt_launch_one<0>(grid, smem, st, a); break;
-        case 1: bt_launch_one<1>(grid, smem, st, a); break;
-        case 2: bt_launch_one<2>(grid, smem, st, a); break;
-        default: bt_launch_one<3>(grid, smem, st, a); break;
-    }
-}
-static_assert(mot::kNumBtShapes == 4, "update the dispatch switches");
-
-template <int I>
-static cudaError_t sort_set_smem(size_t bytes) {
-    constexpr mot::BtShape sh = mot::kBtShapes[I];
-    return cudaFuncSetAttribute(mot::sort_step_kernel<sh.cap, sh.d_max, sh.e_cap>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-}
-template <int I>
-static void sort_launch_one(int grid, size_t smem, cudaStream_t st, const mot::SortArgs& a) {
-    constexpr mot::BtShape sh = mot::kBtShapes[I];
-    mot::sort_step_kernel<sh.cap, sh.d_max, sh.e_cap><<<grid, mot::kSortThreads, smem, st>>>(a);
-}
-static cudaError_t sort_prepare(int shape, size_t smem) {
-    switch (shape) {
-        case 0: return sort_set_smem<0>(smem);
-        case 1: return sort_set_smem<1>(smem);
-        case 2: return sort_set_smem<2>(smem);
-        default: return sort_set_smem<3>(smem);
-    }
-}
-static void sort_launch(int shape, int grid, size_t smem, cudaStream_t st, const mot::SortArgs& a) {
-    switch (shape) {
-        case 0: sort_launch_one<0>(grid, smem, st, a); break;
-        case 1: sort_launch_one<1>(grid, smem, st, a); break;
-        case 2: sort_launch_one<2>(grid, smem, st, a); break;
-        default: sort_launch_one<3>(grid, smem, st, a); break;
-    }
-}
-
-template <int I>
-static cudaError_t oc_set_smem(size_t bytes) {
-    constexpr mot::OcShape sh = mot::kOcShapes[I];
-    return cudaFuncSetAttribute(mot::ocsort_step_kernel<sh.cap, sh.d_max, sh.e_cap>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-}
-template <int I>
-static void oc_launch_one(int grid, size_t smem, cudaStream_t st, const mot::OcArgs& a) {
-    constexpr mot::OcShape sh = mot::kOcShapes[I];
-    mot::ocsort_step_kernel<sh.cap, sh.d_max, sh.e_cap><<<grid, mot::kOcThreads, smem, st>>>(a);
-}
-static cudaError_t oc_prepare(int shape, size_t smem) {
-    switch (shape) {
-        case 0: return oc_set_smem<0>(smem);
-        case 1: return oc_set_smem<1>(smem);
-        default: return oc_set_smem<2>(smem);
-    }
-}
-static void oc_launch(int shape, int grid, size_t smem, cudaStream_t st, const mot::OcArgs& a) {
-    switch (shape) {
-        case 0: oc_launch_one<0>(grid, smem, st, a); break;
-        case 1: oc_launch_one<1>(grid, smem, st, a); break;
-        default: oc_launch_one<2>(grid, smem, st, a); break;
-    }
-}
-static_assert(mot::kNumOcShapes == 3, "update the OC-SORT dispatch switches");
-
-template <int I>
-static cudaError_t bot_set_smem(size_t bytes) {
-    constexpr mot::BtShape sh = mot::kBotShapes[I];
-    return cudaFuncSetAttribute(mot::botsort_step_kernel<sh.cap, sh.d_max, sh.e_cap>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-}
-template <int I>
-static void bot_launch_one(int grid, size_t smem, cudaStream_t st, const mot::BotArgs& a) {
-    constexpr mot::BtShape sh = mot::kBotShapes[I];
-    mot::botsort_step_kernel<sh.cap, sh.d_max, sh.e_cap><<<grid, mot::kBotThreads, smem, st>>>(a);
-}
-static cudaError_t bot_prepare(int shape, size_t smem) {
-    switch (shape) {
-        case 0: return bot_set_smem<0>(smem);
-        case 1: return bot_set_smem<1>(smem);
-        default: return bot_set_smem<2>(smem);
-    }
-}
-static void bot_launch(int shape, int grid, size_t smem, cudaStream_t st, const mot::BotArgs& a) {
-    switch (shape) {
-        case 0: bot_launch_one<0>(grid, smem, st, a); break;
-        case 1: bot_launch_one<1>(grid, smem, st, a); break;
-        default: bot_launch_one<2>(grid, smem, st, a); break;
-    }
-}
-static_assert(mot::kNumBotShapes == 3, "update the BoT-SORT dispatch switches");
-
-template <int I>
-static cudaError_t ss_set_smem(size_t bytes) {
-    constexpr mot::BtShape sh = mot::kSsShapes[I];
-    return cudaFuncSetAttribute(mot::strongsort_step_kernel<sh.cap, sh.d_max, sh.e_cap>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-}
-template <int I>
-static void ss_launch_one(int grid, size_t smem, cudaStream_t st, const mot::SsArgs& a) {
-    constexpr mot::BtShape sh = mot::kSsShapes[I];
-    mot::strongsort_step_kernel<sh.cap, sh.d_max, sh.e_cap><<<grid, mot::kSsThreads, smem, st>>>(a);
-}
-static cudaError_t ss_prepare(int shape, size_t smem) { return shape == 0 ? ss_set_smem<0>(smem) : ss_set_smem<1>(smem); }
-static void ss_launch(int shape, int grid, size_t smem, cudaStream_t st, const mot::SsArgs& a) {
-    if (shape == 0) ss_launch_one<0>(grid, smem, st, a); else ss_launch_one<1>(grid, smem, st, a);
-}
-static_assert(mot::kNumSsShapes == 2, "update the StrongSORT dispatch switches");
-
 // one launch covering streams [s0, s1) for T frames, whatever the tracker kind
 static void engine_launch(mot_engine* e, int T, const float* dets, const int* nd, int ld_dets, const float* embs,
                           float* out, int* nout, int ld_out, int s0, int s1, cudaStream_t st);
@@ -268,28 +141,28 @@ static void engine_launch(mot_engine* e, int T, const float* dets, const int* nd
         a.state = e->d_state; a.L = e->ss_layout; a.dets = dets; a.n_dets = nd; a.embs = embs; a.out = out; a.n_out = nout;
         a.T = T; a.S = e->cfg.n_streams; a.ld_dets = ld_dets; a.ld_out = ld_out; a.s_begin = s0; a.s_end = s1;
         a.p = e->ssp;
-        ss_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
+        mot::ss_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
     } else if (e->cfg.kind == MOT_TRACKER_BOTSORT) {
         mot::BotArgs a{};
         a.state = e->d_state; a.L = e->bot_layout; a.dets = dets; a.n_dets = nd; a.embs = embs; a.out = out; a.n_out = nout;
         a.T = T; a.S = e->cfg.n_streams; a.ld_dets = ld_dets; a.ld_out = ld_out; a.s_begin = s0; a.s_end = s1;
         a.p = e->botp;
-        bot_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
+        mot::bot_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
     } else if (e->cfg.kind == MOT_TRACKER_SORT) {
         mot::SortArgs a{};
         a.state = e->d_state; a.dets = dets; a.n_dets = nd; a.out = out; a.n_out = nout;
         a.T = T; a.S = e->cfg.n_streams; a.ld_dets = ld_dets; a.ld_out = ld_out; a.s_begin = s0; a.s_end = s1;
         a.p = e->sortp;
-        sort_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
+        mot::sort_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
     } else if (e->cfg.kind == MOT_TRACKER_OCSORT) {
         mot::OcArgs a{};
         a.state = e->d_state; a.dets = dets; a.n_dets = nd; a.out = out; a.n_out = nout;
         a.T = T; a.S = e->cfg.n_streams; a.ld_dets = ld_dets; a.ld_out = ld_out; a.s_begin = s0; a.s_end = s1;
         a.p = e->ocp;
-        oc_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
+        mot::oc_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
     } else {
         mot::BtArgs a = make_args(e, T, dets, nd, ld_dets, out, nout, ld_out, s0, s1);
-        bt_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
+        mot::bt_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
     }
 }
 
@@ -480,9 +353,9 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
         return fail(MOT_ERR_INVALID_ARGUMENT, "track_capacity/max_dets need %zu B of shared memory per CTA (limit %d)",
                     need, max_optin);
     }
-    MOT_CUDA(is_ss ? ss_prepare(e->shape, e->smem_bytes) : is_sort ? sort_prepare(e->shape, e->smem_bytes)
-                     : (is_oc ? oc_prepare(e->shape, e->smem_bytes)
-                              : (is_bot ? bot_prepare(e->shape, e->smem_bytes) : bt_prepare(e->shape, e->smem_bytes))));
+    MOT_CUDA(is_ss ? mot::ss_prepare(e->shape, e->smem_bytes) : is_sort ? mot::sort_prepare(e->shape, e->smem_bytes)
+                     : (is_oc ? mot::oc_prepare(e->shape, e->smem_bytes)
+                              : (is_bot ? mot::bot_prepare(e->shape, e->smem_bytes) : mot::bt_prepare(e->shape, e->smem_bytes))));
     e->n_chunks = cfg->n_chunks > 0 ? std::min(cfg->n_chunks, kMaxChunks) : (cfg->n_streams >= 128 ? 8 : (cfg->n_streams >= 32 ? 4 : 1));
     e->n_chunks = std::min(e->n_chunks, cfg->n_streams);
     for (int c = 0; c < kMaxChunks; ++c) {
@@ -1007,14 +880,32 @@ int mot_lap_batch_device(const float* cost, long long stride_cost, int n_problem
 int mot_lap_jv_batch_device(const float* cost, long long stride_cost, int n_problems, int n, int m, int ld, float thresh,
                             int* row2col, int* col2row, void* stream) {
     if (n <= 0 || m <= 0 || n_problems < 0 || ld < m) return fail(MOT_ERR_INVALID_ARGUMENT, "bad sizes");
-    if (n + m > mot::kLapJvMax)
-        return fail(MOT_ERR_UNSUPPORTED, "the reference-order LAPJV is built for rows + columns <= %d (got %d)", mot::kLapJvMax, n + m);
+    if (n + m > 32000) return fail(MOT_ERR_INVALID_ARGUMENT, "rows + columns above 32000 are not supported");
     if (int rc = require_device()) return rc;
     if (n_problems == 0) return MOT_OK;
     if (!cost || !row2col || !col2row) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
-    mot::lap_jv_kernel<<<std::min(n_problems, sm_count() * 16), 32, 0, (cudaStream_t)stream>>>(cost, stride_cost, n_problems, n, m, ld,
-                                                                                             thresh, row2col, col2row);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n + m <= mot::kLapJvMax) {          // one warp per problem, all state in shared memory
+        mot::lap_jv_kernel<<<std::min(n_problems, sm_count() * 16), 32, 0, st>>>(cost, stride_cost, n_problems, n, m, ld, thresh,
+                                                                                 row2col, col2row);
+        MOT_CUDA(cudaGetLastError());
+        return MOT_OK;
+    }
+    // any size: one CTA per problem, work arrays in stream-ordered global scratch
+    const size_t smem = mot::jv_block_sbytes(n + m);
+    int dev = 0, max_optin = 0;
+    MOT_CUDA(cudaGetDevice(&dev));
+    MOT_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (smem > (size_t)max_optin)
+        return fail(MOT_ERR_INVALID_ARGUMENT, "problem %d x %d needs %zu B of shared memory (limit %d)", n, m, smem, max_optin);
+    MOT_CUDA(cudaFuncSetAttribute(mot::lap_jv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = std::min(n_problems, sm_count() * 2);
+    unsigned char* gs = nullptr;
+    MOT_CUDA(cudaMallocAsync((void**)&gs, mot::jv_block_gbytes(n + m) * (size_t)grid, st));
+    mot::lap_jv_block_kernel<<<grid, mot::kLapJvBlockThreads, smem, st>>>(cost, stride_cost, n_problems, n, m, ld, thresh, row2col,
+                                                                          col2row, gs);
     MOT_CUDA(cudaGetLastError());
+    MOT_CUDA(cudaFreeAsync(gs, st));
     return MOT_OK;
 }
 

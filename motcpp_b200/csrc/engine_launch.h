@@ -1,0 +1,20 @@
+// engine_launch.h - host-side launchers of the five fused frame-step kernels.  Each family is instantiated in its own
+// translation unit (engine_<name>.cu) so that the library builds in parallel; cabi.cu only sees these declarations.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+
+namespace mot {
+struct BtArgs; struct SortArgs; struct OcArgs; struct BotArgs; struct SsArgs;
+// *_prepare: opt the kernel of `shape` into `smem` bytes of dynamic shared memory; *_launch: one CTA per stream
+cudaError_t bt_prepare(int shape, size_t smem);
+void bt_launch(int shape, int grid, size_t smem, cudaStream_t st, const BtArgs& a);
+cudaError_t sort_prepare(int shape, size_t smem);
+void sort_launch(int shape, int grid, size_t smem, cudaStream_t st, const SortArgs& a);
+cudaError_t oc_prepare(int shape, size_t smem);
+void oc_launch(int shape, int grid, size_t smem, cudaStream_t st, const OcArgs& a);
+cudaError_t bot_prepare(int shape, size_t smem);
+void bot_launch(int shape, int grid, size_t smem, cudaStream_t st, const BotArgs& a);
+cudaError_t ss_prepare(int shape, size_t smem);
+void ss_launch(int shape, int grid, size_t smem, cudaStream_t st, const SsArgs& a);
+}  // namespace mot

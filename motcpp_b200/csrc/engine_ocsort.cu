@@ -1,0 +1,34 @@
+// engine_ocsort.cu - instantiates the fused ocsort frame-step kernels (one per compiled shape) and their launchers.
+#include "engine_launch.h"
+#include "ocsort_kernel.cuh"
+
+namespace mot {
+
+template <int I>
+static cudaError_t oc_set_smem(size_t bytes) {
+    constexpr OcShape sh = kOcShapes[I];
+    return cudaFuncSetAttribute(ocsort_step_kernel<sh.cap, sh.d_max, sh.e_cap>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+template <int I>
+static void oc_launch_one(int grid, size_t smem, cudaStream_t st, const OcArgs& a) {
+    constexpr OcShape sh = kOcShapes[I];
+    ocsort_step_kernel<sh.cap, sh.d_max, sh.e_cap><<<grid, kOcThreads, smem, st>>>(a);
+}
+cudaError_t oc_prepare(int shape, size_t smem) {
+    switch (shape) {
+        case 0: return oc_set_smem<0>(smem);
+        case 1: return oc_set_smem<1>(smem);
+        default: return oc_set_smem<2>(smem);
+    }
+}
+void oc_launch(int shape, int grid, size_t smem, cudaStream_t st, const OcArgs& a) {
+    switch (shape) {
+        case 0: oc_launch_one<0>(grid, smem, st, a); break;
+        case 1: oc_launch_one<1>(grid, smem, st, a); break;
+        default: oc_launch_one<2>(grid, smem, st, a); break;
+    }
+}
+static_assert(kNumOcShapes == 3, "update the OC-SORT dispatch switches");
+
+}  // namespace mot

@@ -63,7 +63,7 @@ __device__ __forceinline__ void warp_lexmin(double& val, int& idx) {
 }
 
 // lap_solver.hpp:157-211 (find_path_dense + the augmentation), lane 0 only
-__device__ __noinline__ void jv_augment_from(const JvCost& c, int N, const JvWork& w, int start) {
+static __device__ __noinline__ void jv_augment_from(const JvCost& c, int N, const JvWork& w, int start) {
     for (int j = 0; j < N; ++j) { w.order[j] = j; w.pred[j] = start; w.dist[j] = c.at(start, j) - w.v[j]; }
     int lo = 0, hi = 0, settled = 0, sink = -1;
     while (sink < 0) {
@@ -124,7 +124,7 @@ __device__ __noinline__ void jv_augment_from(const JvCost& c, int N, const JvWor
 }
 
 // All 32 lanes of one warp.  On return x[0..N) / y[0..N) hold the square assignment (visible to the warp).
-__device__ __noinline__ void warp_dense_lapjv(const JvCost c, int N, const JvWork w) {
+static __device__ __noinline__ void warp_dense_lapjv(const JvCost c, int N, const JvWork w) {
     const int lane = lane_id();
     // ---- column reduction (lap_solver.hpp:36-52): per column the minimum over rows, lowest row on ties
     for (int j = lane; j < N; j += 32) {

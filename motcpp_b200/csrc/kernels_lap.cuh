@@ -3,6 +3,7 @@
 #pragma once
 #include "lap_device.cuh"
 #include "jv_device.cuh"
+#include "jv_block_device.cuh"
 
 namespace mot {
 
@@ -51,6 +52,26 @@ __global__ void __launch_bounds__(32) lap_jv_kernel(const float* __restrict__ co
         for (int i = (int)threadIdx.x; i < n; i += 32) { const int j = w.x[i]; row2col[(size_t)p * n + i] = j < m ? j : -1; }
         for (int j = (int)threadIdx.x; j < m; j += 32) { const int i = w.y[j]; col2row[(size_t)p * m + j] = i < n ? i : -1; }
         __syncwarp();
+    }
+}
+
+
+// The same algorithm for ANY size, one CTA per problem (jv_block_device.cuh): work arrays in global scratch
+// (problem slot = blockIdx.x), the scan-order permutation in dynamic shared memory.
+constexpr int kLapJvBlockThreads = 512;
+__global__ void __launch_bounds__(kLapJvBlockThreads) lap_jv_block_kernel(const float* __restrict__ cost, long long stride_cost,
+                                                                          int n_problems, int n, int m, int ld, float thresh,
+                                                                          int* __restrict__ row2col, int* __restrict__ col2row,
+                                                                          unsigned char* __restrict__ gscratch) {
+    MOT_DYNAMIC_SMEM(smem);
+    __shared__ BlockScratch bs;
+    const int N = n + m;
+    const JvBlockWork w = jv_block_carve(gscratch + (size_t)blockIdx.x * jv_block_gbytes(N), smem, N);
+    for (int p = (int)blockIdx.x; p < n_problems; p += (int)gridDim.x) {
+        block_dense_lapjv(JvCost{cost + (size_t)p * stride_cost, n, m, ld, (double)thresh / 2.0}, N, w, &bs);
+        for (int i = (int)threadIdx.x; i < n; i += (int)blockDim.x) { const int j = w.x[i]; row2col[(size_t)p * n + i] = j < m ? j : -1; }
+        for (int j = (int)threadIdx.x; j < m; j += (int)blockDim.x) { const int i = w.y[j]; col2row[(size_t)p * m + j] = i < n ? i : -1; }
+        __syncthreads();
     }
 }
 

@@ -507,6 +507,14 @@ MOT_HD constexpr size_t lap_smem_bytes(int n_max, int m_max, int e_cap) {
     return b;
 }
 
+// bytes of [row_label, row2col): dead between two block_lap calls, reused by the CTA-wide dense LAPJV (jv_block_device.cuh)
+MOT_HD constexpr size_t lap_idle_bytes(int n_max, int m_max, int e_cap) {
+    const int a = e_cap > n_max + 1 ? e_cap : n_max + 1;
+    return lap_align16(sizeof(int) * (size_t)n_max) + lap_align16(sizeof(int) * (size_t)m_max) + lap_align16(sizeof(int) * (size_t)a) +
+           lap_align16(sizeof(int) * (size_t)n_max) + lap_align16(sizeof(unsigned short) * (size_t)n_max) +
+           lap_align16(sizeof(unsigned short) * (size_t)m_max) + lap_align16(sizeof(unsigned short) * (size_t)n_max);
+}
+
 __device__ __forceinline__ unsigned char* lap_carve(unsigned char* p, int n_max, int m_max, int e_cap, LapWorkspace& ws) {
     const int a = e_cap > n_max + 1 ? e_cap : n_max + 1;
     ws.row_label = (int*)p;            p += lap_align16(sizeof(int) * (size_t)n_max);

@@ -20,12 +20,14 @@
 // age -> bbox map is only ever queried for the last delta_t ages, else for its newest entry, which is
 // last_observation), IDs from a per-stream counter.
 #pragma once
+#include "shapes.cuh"
 #include "block_utils.cuh"
 #include "cost_device.cuh"
 #include "kf_device.cuh"
 #include "lap_device.cuh"
 #include "ocm_device.cuh"
 #include "jv_device.cuh"
+#include "jv_block_device.cuh"
 
 namespace mot {
 
@@ -36,14 +38,14 @@ constexpr int kOcThreads = MOT_OC_THREADS;
 constexpr int kOcRecFloats = 64;       // 56 used
 constexpr int kOcRing = 8;             // observation ring entries per track: delta_t <= kOcRing
 constexpr int kOcObsFloats = 8;        // last_observation[5], velocity (dy, dx), pad
-// Exact reference tie-breaking: when a "twin" track (see the file header) is an assignment candidate and the problem is
-// small enough (rows + columns <= kJvMax), the frame's assignment is redone by the reference's own dense LAPJV
-// (jv_device.cuh) on the full cost matrix; larger problems keep the sparse solver's "higher column" rule.
+// Exact reference tie-breaking: when a "twin" track (see the file header) is an assignment candidate, the frame's
+// assignment is redone by the reference's own dense LAPJV on the full cost matrix - by one warp out of shared memory
+// while rows + columns <= kJvMax (jv_device.cuh), by the whole CTA over per-stream global scratch above that
+// (jv_block_device.cuh).  Either way the result IS the reference's, at any problem size.
 #ifndef MOT_OC_JVMAX
 #define MOT_OC_JVMAX 384
 #endif
 constexpr int kJvMax = MOT_OC_JVMAX;
-constexpr int kJvDenseMax = (kJvMax / 2) * (kJvMax / 2) + 16;  // n * m <= (n + m)^2 / 4
 constexpr unsigned short kNoTwin = 0xffff;
 
 enum : int {
@@ -61,7 +63,7 @@ struct OcParams {
 struct OcLayout {
     int cap, d_max;
     size_t off_lists, off_meta, off_obs, off_ring_box, off_ring_conf, off_ring_age, off_recs, off_ocm, off_valid,
-        off_twin, off_jv, off_gscratch, stride;
+        off_twin, off_jv, off_jvw, off_gscratch, stride;
     MOT_HD static constexpr size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
     MOT_HD static constexpr OcLayout make(int cap, int d_max) {
         OcLayout L{};
@@ -77,7 +79,8 @@ struct OcLayout {
         L.off_ocm = o;       o = al(o + sizeof(float4) * (size_t)cap);
         L.off_valid = o;     o = al(o + (size_t)cap);
         L.off_twin = o;      o = al(o + sizeof(unsigned short) * (size_t)cap);
-        L.off_jv = o;        o = al(o + sizeof(float) * kJvDenseMax);
+        L.off_jv = o;        o = al(o + sizeof(float) * (size_t)d_max * (size_t)cap);          // dense cost matrix of the exact-tie path
+        L.off_jvw = o;       o = al(o + jv_block_gbytes(d_max + cap));                        // its LAPJV work arrays
         L.off_gscratch = o;  o = al(o + lap_gscratch_bytes(d_max, cap));
         L.stride = o;
         return L;
@@ -97,7 +100,8 @@ struct OcStream {
     float4* ocm;               // per-frame scratch, indexed by track POSITION
     unsigned char* valid;
     unsigned short* twin;      // [cap] slot of the bit-identical twin spawned from the same detection, kNoTwin = none
-    float* jv_dense;           // [kJvDenseMax] dense cost matrix of the exact-tie path
+    float* jv_dense;           // [d_max * cap] dense cost matrix of the exact-tie path
+    unsigned char* jv_work;    // jv_block_gbytes(d_max + cap): work arrays of the CTA-wide LAPJV
     unsigned char* gscratch;
     __device__ __forceinline__ static OcStream at(unsigned char* base, const OcLayout& L) {
         OcStream s;
@@ -116,6 +120,7 @@ struct OcStream {
         s.valid = base + L.off_valid;
         s.twin = (unsigned short*)(base + L.off_twin);
         s.jv_dense = (float*)(base + L.off_jv);
+        s.jv_work = base + L.off_jvw;
         s.gscratch = base + L.off_gscratch;
         return s;
     }
@@ -335,19 +340,30 @@ __device__ __forceinline__ void oc_spawn(const OcStream& st, OcSmem& sm, const f
     }
 }
 
-// The reference's dense LAPJV (jv_device.cuh) on the full n x m cost matrix pair(i, j); overwrites lap.row2col / col2row.
-// Requires n + m <= kJvMax.  All threads of the block must call.
-template <class Pair>
+// The reference's dense LAPJV on the full n x m cost matrix pair(i, j); overwrites lap.row2col / col2row.
+// rows + columns <= kJvMax: one warp, state in shared memory (jv_device.cuh); larger: the whole CTA, state in the
+// stream's global scratch, scan order + reduction scratch in the (now idle) label / edge arrays of the sparse solver.
+// All threads of the block must call.
+template <int CAP, int DMAX, class Pair>
 __device__ __forceinline__ void oc_exact_assignment(const OcStream& st, OcSmem& sm, int n, int m, float thresh, Pair pair) {
     const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
     for (int e = tid; e < n * m; e += nt) st.jv_dense[e] = pair(e / m, e - (e / m) * m);
-    __syncthreads();
-    const JvWork w = jv_carve(sm.jv, kJvMax + 1);
     if (tid == 0) st.hdr[kOHdrExactSolves] += 1;
-    if (tid < 32) warp_dense_lapjv(JvCost{st.jv_dense, n, m, m, (double)thresh / 2.0}, n + m, w);
     __syncthreads();
-    for (int i = tid; i < n; i += nt) { const int j = w.x[i]; sm.lap.row2col[i] = (short)(j < m ? j : -1); }     // lap_solver.hpp:326-331
-    for (int j = tid; j < m; j += nt) { const int i = w.y[j]; sm.lap.col2row[j] = (short)(i < n ? i : -1); }
+    const JvCost cost{st.jv_dense, n, m, m, (double)thresh / 2.0};
+    if (n + m <= kJvMax) {
+        const JvWork w = jv_carve(sm.jv, kJvMax + 1);
+        if (tid < 32) warp_dense_lapjv(cost, n + m, w);
+        __syncthreads();
+        for (int i = tid; i < n; i += nt) { const int j = w.x[i]; sm.lap.row2col[i] = (short)(j < m ? j : -1); }     // lap_solver.hpp:326-331
+        for (int j = tid; j < m; j += nt) { const int i = w.y[j]; sm.lap.col2row[j] = (short)(i < n ? i : -1); }
+    } else {
+        unsigned char* idle = (unsigned char*)sm.lap.row_label;         // [row_label, row2col) is dead between two block_lap calls
+        const JvBlockWork w = jv_block_carve(st.jv_work, idle, n + m);
+        block_dense_lapjv(cost, n + m, w, sm.bs);
+        for (int i = tid; i < n; i += nt) { const int j = w.x[i]; sm.lap.row2col[i] = (short)(j < m ? j : -1); }
+        for (int j = tid; j < m; j += nt) { const int i = w.y[j]; sm.lap.col2row[j] = (short)(i < n ? i : -1); }
+    }
     __syncthreads();
 }
 
@@ -480,16 +496,20 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
     const bool trivial = sm.flags[0] != 0 && sm.flags[1] == 0;   // max row sum == 1 && max column sum == 1 (:676-680)
     // the optimum can only be non-unique if it uses a track that still has a bit-identical twin (the twin is then an
     // equally good column); bit 1 of valid[] marks such tracks
-    if (!trivial && n_high + n_trk <= kJvMax)
+    if (!trivial)
         for (int j = tid; j < n_trk; j += nt)
             if (sm.lap.col2row[j] >= 0 && (st.valid[j] & 2)) sm.flags[2] = 1;
     __syncthreads();
+#ifdef MOT_OC_FORCE_EXACT
+    const bool exact1 = sm.flags[2] != 0 || (!trivial && (MOT_OC_FORCE_EXACT & 1));
+#else
     const bool exact1 = sm.flags[2] != 0;
+#endif
     __syncthreads();
     if (exact1) {
         // a twin track is a candidate: the optimum may be non-unique, so redo the assignment with the reference's own
         // dense LAPJV over the full (n_high x n_trk) cost matrix (associate :690-700 -> linear_assignment)
-        oc_exact_assignment(st, sm, n_high, n_trk, -thr, [&](int i, int j) { return ocm.pair(i, j); });
+        oc_exact_assignment<CAP, DMAX>(st, sm, n_high, n_trk, -thr, [&](int i, int j) { return ocm.pair(i, j); });
     }
     if (trivial) {
         // every pair with iou > thr is a match, nothing else is (:681-689)
@@ -519,6 +539,7 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
                                  if (pos < CAP) sm.ut[pos] = (unsigned short)sm.lap.row2col[i];
                              });
     int n_ut = n_ud;
+    const int n_filtered = n_ud;
     n_ud = block_compact(n_high, n_ud, sm.bs, [&](int i) { return sm.det_flag[i] != 1; },
                          [&](int i, int pos) { if (pos < DMAX) sm.ud[pos] = sm.high[i]; });
     n_ut = block_compact(n_trk, n_ut, sm.bs, [&](int j) { return sm.trk_flag[j] != 1; },
@@ -550,13 +571,13 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
         __syncthreads();
         NegIouCost cost{sm.det_box, sm.second, sm.trk_box, sm.ut, thr, prune_rest, sm.flags};
         block_lap(sm.lap, n_second, n_ut, DMAX, CAP, -thr, cost);
-        if (sm.flags[0] != 0 && n_second + n_ut <= kJvMax)
+        if (sm.flags[0] != 0)
             for (int p = tid; p < n_ut; p += nt)
                 if (sm.lap.col2row[p] >= 0 && (st.valid[sm.ut[p]] & 2)) sm.flags[2] = 1;
         __syncthreads();
         if (sm.flags[2] != 0) {
             __syncthreads();
-            oc_exact_assignment(st, sm, n_second, n_ut, -thr, [&](int i, int j) { return cost.pair(i, j); });
+            oc_exact_assignment<CAP, DMAX>(st, sm, n_second, n_ut, -thr, [&](int i, int j) { return cost.pair(i, j); });
         }
         if (sm.flags[0] != 0) {                                   // max_iou > threshold (:445-446)
             for (int r = tid; r < n_second; r += nt) {
@@ -582,10 +603,35 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
             const float* o = st.obs + (size_t)sm.list_a[k] * kOcObsFloats;
             sm.trk_box[k] = make_float4(o[0], o[1], o[2], o[3]);
         }
-        if (tid == 0) sm.flags[0] = 0;
+        if (tid == 0) { sm.flags[0] = 0; sm.flags[2] = 0; }
         __syncthreads();
         NegIouCost cost{sm.det_box, sm.ud, sm.trk_box, sm.ut, thr, prune_rest, sm.flags};
         block_lap(sm.lap, n_ud, n_ut, DMAX, CAP, -thr, cost);
+        // Exact ties here: (1) the lists hold an entry twice (pairs rejected by the IoU filter, n_filtered of them) - which
+        // COPY of a detection is matched decides the order in which a twice-listed track receives its two updates;
+        // (2) DIFFERENT tracks with bit-identical last observations: twins that both stayed unmatched, and tracks that an
+        // earlier frame updated with the same (duplicated) detection.  In both cases the reference's answer is its LAPJV's.
+        if (sm.flags[0] != 0 && n_filtered > 0 && tid == 0) sm.flags[2] = 1;
+        if (sm.flags[0] != 0)
+            for (int p = tid; p < n_ut; p += nt) {
+                if (sm.lap.col2row[p] < 0) continue;
+                const int k = sm.ut[p];
+                const float4 b = sm.trk_box[k];
+                for (int q = 0; q < n_ut; ++q) {
+                    const int k2 = sm.ut[q];
+                    const float4 b2 = sm.trk_box[k2];
+                    if (k2 != k && b2.x == b.x && b2.y == b.y && b2.z == b.z && b2.w == b.w) { sm.flags[2] = 1; break; }
+                }
+            }
+        __syncthreads();
+#ifdef MOT_OC_FORCE_EXACT
+        if (sm.flags[2] != 0 || (sm.flags[0] != 0 && (MOT_OC_FORCE_EXACT & 4))) {
+#else
+        if (sm.flags[2] != 0) {
+#endif
+            __syncthreads();
+            oc_exact_assignment<CAP, DMAX>(st, sm, n_ud, n_ut, -thr, [&](int i, int j) { return cost.pair(i, j); });
+        }
         if (sm.flags[0] != 0) {                                   // max_iou > threshold (:507-509)
             for (int r = tid; r < n_ud; r += nt) {
                 const int c = sm.lap.row2col[r];
@@ -679,6 +725,7 @@ __global__ void __launch_bounds__(kOcThreads) ocsort_step_kernel(OcArgs a) {
     OcSmem sm;
     oc_carve(smem, CAP, DMAX, ECAP, sm);
     constexpr OcLayout L = OcLayout::make(CAP, DMAX);
+    static_assert(lap_idle_bytes(DMAX, CAP, ECAP) >= jv_block_sbytes(DMAX + CAP), "the CTA-wide LAPJV's shared scratch must fit the sparse solver's idle arrays");
     for (int s = a.s_begin + (int)blockIdx.x; s < a.s_end; s += (int)gridDim.x) {
         OcStream st = OcStream::at(a.state + (size_t)s * L.stride, L);
         lap_carve_gscratch(st.gscratch, DMAX, CAP, sm.lap);
@@ -690,7 +737,7 @@ __global__ void __launch_bounds__(kOcThreads) ocsort_step_kernel(OcArgs a) {
     }
 }
 
-__global__ void ocsort_reset_kernel(unsigned char* state, OcLayout L, int S, int keep_id_counter) {
+static __global__ void ocsort_reset_kernel(unsigned char* state, OcLayout L, int S, int keep_id_counter) {
     for (int s = (int)blockIdx.x; s < S; s += (int)gridDim.x) {
         OcStream st = OcStream::at(state + (size_t)s * L.stride, L);
         for (int k = (int)threadIdx.x; k < L.cap; k += (int)blockDim.x) st.freel[k] = (unsigned short)(L.cap - 1 - k);

@@ -9,6 +9,7 @@
 //   output rows (:219-253)                                -> phase G
 // State records are [x 7 | P 7x7] fp32 padded to 64 floats.  IDs come from a per-stream counter.
 #pragma once
+#include "shapes.cuh"
 #include "block_utils.cuh"
 #include "cost_device.cuh"
 #include "kf_device.cuh"
@@ -303,7 +304,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_step_kernel(SortArgs a) {
     }
 }
 
-__global__ void sort_reset_kernel(unsigned char* state, SortLayout L, int S, int keep_id_counter) {
+static __global__ void sort_reset_kernel(unsigned char* state, SortLayout L, int S, int keep_id_counter) {
     for (int s = (int)blockIdx.x; s < S; s += (int)gridDim.x) {
         SortStream st = SortStream::at(state + (size_t)s * L.stride, L);
         for (int k = (int)threadIdx.x; k < L.cap; k += (int)blockDim.x) st.freel[k] = (unsigned short)(L.cap - 1 - k);

@@ -22,12 +22,14 @@
 // assignment is redone by the reference's own dense LAPJV (jv_device.cuh): the reference's answer.  Larger problems keep
 // the sparse solver with + (j + 1) 2^-50 on the second copies (oracle tie_mode 2 = this policy; DESIGN.md "Ties").
 #pragma once
+#include "shapes.cuh"
 #include "block_utils.cuh"
 #include "cost_device.cuh"
 #include "gate_device.cuh"
 #include "kf_device.cuh"
 #include "lap_device.cuh"
 #include "jv_device.cuh"
+#include "jv_block_device.cuh"
 #include "bytetrack_kernel.cuh"      // header / error enums, BtShape
 #include "botsort_kernel.cuh"        // lanes32 feature arithmetic (warp_dot, lanes32_reduce, dot4)
 
@@ -42,9 +44,12 @@ constexpr int kSsTableSlots = 4096;          // (row, det) -> blended appearance
 enum : int { kSsTentative = 1, kSsConfirmed = 2, kSsDeleted = 3 };       // strongsort.hpp TrackState
 constexpr unsigned char kSsHasFeat = 0x10;
 enum : int { kErrTable = 16 };
-// duplicated-row ties (q1) are resolved by the reference's own dense LAPJV (jv_device.cuh) while rows + columns <= kSsJvMax
-constexpr int kSsJvMax = 384;
-constexpr int kSsJvDense = (kSsJvMax / 2) * (kSsJvMax / 2) + 16;            // n * m <= (n + m)^2 / 4
+// duplicated-row ties (q1) are resolved by the reference's own dense LAPJV: one warp (jv_device.cuh) while rows + columns <=
+// kSsJvMax, the whole CTA over per-stream global scratch (jv_block_device.cuh) above that
+#ifndef MOT_SS_JVMAX
+#define MOT_SS_JVMAX 384
+#endif
+constexpr int kSsJvMax = MOT_SS_JVMAX;
 static_assert(sizeof(unsigned long long) * kSsTableSlots >= jv_work_bytes(kSsJvMax + 1), "the LAPJV work area aliases the candidate table");
 // header ints: kHdrActive = live tracks, kHdrLost = cumulative count of dense-LAPJV solves, kHdrFree, kHdrIdCounter (next_id - 1), kHdrFrame, kHdrError, then
 enum : int { kSHdrRowsA = 6, kSHdrColsA = 7, kSHdrRowsB = 8, kSHdrColsB = 9, kSHdrMatchA = 10, kSHdrMatchB = 11,
@@ -57,7 +62,7 @@ struct SsParams {
 
 struct SsLayout {
     int cap, d_max, dim, budget;
-    size_t off_lists, off_state, off_meta, off_recs, off_feat, off_gal, off_ring, off_dfeat, off_dnorm, off_grad, off_jv, off_gscratch, stride;
+    size_t off_lists, off_state, off_meta, off_recs, off_feat, off_gal, off_ring, off_dfeat, off_dnorm, off_grad, off_jv, off_jvw, off_gscratch, stride;
     static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
     static SsLayout make(int cap, int d_max, int dim, int budget) {
         SsLayout L{};
@@ -73,7 +78,8 @@ struct SsLayout {
         L.off_dfeat = o;    o = al(o + sizeof(float) * (size_t)dim * (size_t)d_max);
         L.off_dnorm = o;    o = al(o + sizeof(float) * (size_t)d_max);
         L.off_grad = o;     o = al(o + sizeof(float) * (size_t)cap);
-        L.off_jv = o;       o = al(o + sizeof(float) * kSsJvDense);
+        L.off_jv = o;       o = al(o + sizeof(float) * (size_t)cap * (size_t)d_max);          // dense cost matrix of the exact-tie path
+        L.off_jvw = o;      o = al(o + jv_block_gbytes(cap + d_max));                        // its LAPJV work arrays
         L.off_gscratch = o; o = al(o + lap_gscratch_bytes(cap, d_max));
         L.stride = o;
         return L;
@@ -93,7 +99,8 @@ struct SsStream {
     float* dfeat;                      // [d_max][dim] this frame's detection features, normalised (filtered index)
     float* dnorm;                      // [d_max] |raw feature|
     float* grad;                       // [cap] gallery radius: max over the ring of |sample - gal| (slightly inflated)
-    float* jv_dense;                   // [kSsJvDense] dense (clamped) IoU cost matrix of the exact-tie path
+    float* jv_dense;                   // [cap * d_max] dense (clamped) IoU cost matrix of the exact-tie path
+    unsigned char* jv_work;            // jv_block_gbytes(cap + d_max): work arrays of the CTA-wide LAPJV
     unsigned char* gscratch;
     __device__ __forceinline__ static SsStream at(unsigned char* base, const SsLayout& L) {
         SsStream s;
@@ -112,6 +119,7 @@ struct SsStream {
         s.dnorm = (float*)(base + L.off_dnorm);
         s.grad = (float*)(base + L.off_grad);
         s.jv_dense = (float*)(base + L.off_jv);
+        s.jv_work = base + L.off_jvw;
         s.gscratch = base + L.off_gscratch;
         return s;
     }
@@ -506,7 +514,7 @@ __device__ __forceinline__ void ss_frame(const SsArgs& a, const SsStream& st, Ss
         if (n_rb > 0) {
             const SsIouCost cost{sm.rows_b, st.list, st.recs, st.tsu, sm.det_tlwh, sm.det_box, sm.cols, dup_first, a.p.max_iou_dist < 1.0f};
             block_lap(sm.lap, n_rb, n_cb, CAP, DMAX, a.p.max_iou_dist, cost);
-            if (dup_first > 0 && n_rb + n_cb <= kSsJvMax) {
+            if (dup_first > 0) {
                 // duplicated rows: the optimum is not unique, and the reference's answer is whatever its dense LAPJV yields
                 // on the clamped matrix (min_cost_matching :372-379), non-candidate entries included
                 const float maxd = a.p.max_iou_dist, capv = xadd(maxd, 1e-5f);
@@ -514,17 +522,28 @@ __device__ __forceinline__ void ss_frame(const SsArgs& a, const SsStream& st, Ss
                     const float c = cost.pair(e / n_cb, e - (e / n_cb) * n_cb);
                     st.jv_dense[e] = (c > maxd) ? capv : c;
                 }
-                __syncthreads();
-                const JvWork w = jv_carve(reinterpret_cast<unsigned char*>(sm.cache), kSsJvMax + 1);
                 if (tid == 0) st.hdr[kHdrLost] += 1;
-                if (tid < 32) warp_dense_lapjv(JvCost{st.jv_dense, n_rb, n_cb, n_cb, (double)maxd / 2.0}, n_rb + n_cb, w);
+                __syncthreads();
+                const JvCost jc{st.jv_dense, n_rb, n_cb, n_cb, (double)maxd / 2.0};
+                const int* jx;
+                const int* jy;
+                if (n_rb + n_cb <= kSsJvMax) {
+                    const JvWork w = jv_carve(reinterpret_cast<unsigned char*>(sm.cache), kSsJvMax + 1);
+                    if (tid < 32) warp_dense_lapjv(jc, n_rb + n_cb, w);
+                    jx = w.x; jy = w.y;
+                } else {
+                    // [row_label, row2col) of the sparse solver is idle here
+                    const JvBlockWork w = jv_block_carve(st.jv_work, (unsigned char*)sm.lap.row_label, n_rb + n_cb);
+                    block_dense_lapjv(jc, n_rb + n_cb, w, sm.bs);
+                    jx = w.x; jy = w.y;
+                }
                 __syncthreads();
                 for (int i = tid; i < n_rb; i += nt) {                          // lap_solver.hpp:326-331, then :389-399
-                    const int j = w.x[i];
+                    const int j = jx[i];
                     sm.lap.row2col[i] = (short)((j < n_cb && st.jv_dense[i * n_cb + j] <= maxd) ? j : -1);
                 }
                 for (int j = tid; j < n_cb; j += nt) {
-                    const int i = w.y[j];
+                    const int i = jy[j];
                     sm.lap.col2row[j] = (short)((i < n_rb && st.jv_dense[i * n_cb + j] <= maxd) ? i : -1);
                 }
                 __syncthreads();
@@ -758,6 +777,7 @@ template <int CAP, int DMAX, int ECAP>
 __global__ void __launch_bounds__(kSsThreads) strongsort_step_kernel(SsArgs a) {
     MOT_DYNAMIC_SMEM(smem);
     SsSmem sm;
+    static_assert(lap_idle_bytes(CAP, DMAX, ECAP) >= jv_block_sbytes(CAP + DMAX), "the CTA-wide LAPJV's shared scratch must fit the sparse solver's idle arrays");
     ss_carve(smem, CAP, DMAX, ECAP, sm);
     for (int s = a.s_begin + (int)blockIdx.x; s < a.s_end; s += (int)gridDim.x) {
         SsStream st = SsStream::at(a.state + (size_t)s * a.L.stride, a.L);
@@ -772,7 +792,7 @@ __global__ void __launch_bounds__(kSsThreads) strongsort_step_kernel(SsArgs a) {
 }
 
 // Tracker::reset (strongsort.cpp:772-778): tracks and galleries cleared, next_id = 1
-__global__ void strongsort_reset_kernel(unsigned char* state, SsLayout L, int S) {
+static __global__ void strongsort_reset_kernel(unsigned char* state, SsLayout L, int S) {
     for (int s = (int)blockIdx.x; s < S; s += (int)gridDim.x) {
         SsStream st = SsStream::at(state + (size_t)s * L.stride, L);
         for (int k = (int)threadIdx.x; k < L.cap; k += (int)blockDim.x) {

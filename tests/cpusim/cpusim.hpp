@@ -118,6 +118,7 @@ struct Block {
     int n_done = 0;
     int barrier_arrived = 0;
     unsigned long long barrier_gen = 0;
+    int or_acc[2] = {0, 0};                              // __syncthreads_or accumulators, by barrier-generation parity
     std::vector<std::vector<Collective*>> warp_colls;   // per warp, keyed by mask
     std::function<void()> body;
     uint3 block_idx{0, 0, 0};
@@ -142,7 +143,7 @@ inline void fiber_yield() {
     b->n_done++;
     // a finished thread no longer takes part in barriers: release one that just became complete
     const int live = (int)b->fibers.size() - b->n_done;
-    if (live > 0 && b->barrier_arrived == live) { b->barrier_arrived = 0; b->barrier_gen++; }
+    if (live > 0 && b->barrier_arrived == live) { b->barrier_arrived = 0; b->or_acc[(b->barrier_gen + 1) & 1] = 0; b->barrier_gen++; }
     cpusim_ctx_switch(&f.sp, b->sched_sp);
     std::abort();
 }
@@ -151,7 +152,7 @@ inline void run_block(Block& b, size_t stack_bytes) {
     const int n = (int)(b.block_dim.x * b.block_dim.y * b.block_dim.z);
     b.fibers.assign(n, Fiber{});
     b.warp_colls.assign((n + 31) / 32, {});
-    b.n_done = 0; b.barrier_arrived = 0; b.barrier_gen = 0;
+    b.n_done = 0; b.barrier_arrived = 0; b.barrier_gen = 0; b.or_acc[0] = b.or_acc[1] = 0;
     char* arena = (char*)mmap(nullptr, stack_bytes * (size_t)n, PROT_READ | PROT_WRITE,
                               MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
     if (arena == MAP_FAILED) { perror("cpusim mmap"); std::abort(); }
@@ -232,11 +233,21 @@ inline void block_barrier() {
     f.wait_gen = b->barrier_gen;
     if (++b->barrier_arrived == live) {
         b->barrier_arrived = 0;
+        b->or_acc[(b->barrier_gen + 1) & 1] = 0;         // the slot the NEXT barrier accumulates into
         b->barrier_gen++;
         return;
     }
     f.wait = kBlockBarrier;
     fiber_yield();
+}
+
+// barrier + OR-reduction of `pred` over the block
+inline int block_barrier_or(int pred) {
+    Block* b = g_block;
+    const int slot = (int)(b->barrier_gen & 1);
+    if (pred) b->or_acc[slot] = 1;
+    block_barrier();
+    return b->or_acc[slot];
 }
 
 inline Collective* coll_for(Block* b, int warp, unsigned mask) {
@@ -298,6 +309,7 @@ inline int lane_id() { return g_block->fibers[g_block->current].tid & 31; }
 static const int warpSize = 32;
 
 static inline void __syncthreads() { cpusim::block_barrier(); }
+static inline int __syncthreads_or(int pred) { return cpusim::block_barrier_or(pred); }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { cpusim::warp_exchange(mask, 0); }
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}

@@ -24,6 +24,20 @@ int sim_lap(const float* cost, int n, int m, int ld, float thresh, int* row2col,
     return 0;
 }
 
+// the reference-order dense LAPJV: block = 0 -> one warp (jv_device.cuh, n + m <= kLapJvMax), 1 -> whole CTA (jv_block_device.cuh)
+int sim_lap_jv(const float* cost, int n, int m, int ld, float thresh, int* row2col, int* col2row, int block, int threads) {
+    if (!block) {
+        if (n + m > mot::kLapJvMax) return -1;
+        cpusim::launch(dim3(1), dim3(32), 0, [=] { mot::lap_jv_kernel(cost, 0, 1, n, m, ld, thresh, row2col, col2row); });
+        return 0;
+    }
+    std::vector<unsigned char> gs(mot::jv_block_gbytes(n + m) + 64);
+    unsigned char* g = gs.data();
+    cpusim::launch(dim3(1), dim3(threads), mot::jv_block_sbytes(n + m),
+                   [=] { mot::lap_jv_block_kernel(cost, 0, 1, n, m, ld, thresh, row2col, col2row, g); });
+    return 0;
+}
+
 }  // extern "C"
 
 // ------------------------------------------------------------------ ByteTrack engine under the emulator

@@ -10,15 +10,34 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SIM_DIR = os.path.join(HERE, "cpusim")
 f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
-_LIB = None
+_LIBS = {}
+# "" = the product's constants; "jvblock" = the same sources built with MOT_OC_JVMAX = MOT_SS_JVMAX = 24, so that the
+# CTA-wide dense LAPJV (csrc/jv_block_device.cuh, the path for rows + columns > 384 in the product) runs at emulator sizes
+VARIANT = ""
+
+
+class variant:
+    """with sim_lib.variant("jvblock"): ... - objects must be created AND used inside the block"""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        global VARIANT
+        self.prev, VARIANT = VARIANT, self.name
+
+    def __exit__(self, *exc):
+        global VARIANT
+        VARIANT = self.prev
 
 
 def lib():
-    global _LIB
+    _LIB = _LIBS.get(VARIANT)
     if _LIB is None:
-        subprocess.check_call(["make", "-C", SIM_DIR, "-s"], stdout=subprocess.DEVNULL)
-        S = C.CDLL(os.path.join(SIM_DIR, "libmotb200_cpusim.so"))
+        subprocess.check_call(["make", "-C", SIM_DIR, "-s", "-j2"], stdout=subprocess.DEVNULL)
+        S = C.CDLL(os.path.join(SIM_DIR, "libmotb200_cpusim%s.so" % ("_" + VARIANT if VARIANT else "")))
         S.sim_lap.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_float, i32p, i32p, C.c_int, C.c_int]
+        S.sim_lap_jv.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_float, i32p, i32p, C.c_int, C.c_int]
         S.sim_bt_create.argtypes = [C.c_int] * 4 + [C.c_float] * 3 + [C.c_int] * 2
         S.sim_bt_create.restype = C.c_void_p
         S.sim_bt_update.argtypes = [C.c_void_p, f32p, i32p, C.c_int, C.c_int, f32p, i32p, C.c_int, C.c_int, C.c_int]
@@ -56,7 +75,7 @@ def lib():
         S.sim_ss_dump.argtypes = [C.c_void_p, C.c_int, f32p, C.c_void_p, C.c_int]
         S.sim_ss_dump.restype = C.c_int
         S.sim_ss_destroy.argtypes = [C.c_void_p]
-        _LIB = S
+        _LIBS[VARIANT] = _LIB = S
     return _LIB
 
 

@@ -95,6 +95,78 @@ def test_lap_batch_device(oracle):
         assert np.array_equal(r2c[p, :nr[p]], ref[0]) and np.array_equal(c2r[p, :nc[p]], ref[1]), p
 
 
+def _tie_cost(rng, kind, n, m):
+    """the generators of tests/test_oracle_kats.py::test_lap_oracle_equals_reference_solver: kinds 1 and 3 are heavy ties"""
+    if kind == 0:
+        c = rng.random((n, m))
+    elif kind == 1:
+        c = rng.integers(0, 4, (n, m)) / 4
+    elif kind == 2:
+        c = np.where(rng.random((n, m)) < 0.7, 1.0, rng.random((n, m)))
+    elif kind == 3:
+        c = rng.integers(0, 10, (n, m)) / 10
+    else:
+        c = -(rng.random((n, m)) * 1.2)
+    th = -0.3 if kind == 4 else [0.5, 0.8, 0.7, 0.3][rng.integers(0, 4)]
+    return c.astype(np.float32), float(th)
+
+
+def _reference_lap(oracle, c, th):
+    """the reference's REAL solver when its binary travelled (oracle/_ref/libref_lap.so), else the oracle's restatement"""
+    return oracle.linear_assignment(c, th, use_ref=oracle.ref_lap() is not None)
+
+
+def test_device_lapjv_reproduces_reference_ties_one_warp(oracle):
+    """mot_lap_jv_batch_device, rows + columns <= 384 (jv_device.cuh): heavy-tie matrices, batched, against the
+    reference's own lap_solver.hpp."""
+    rng = np.random.default_rng(21)
+    for trial in range(60):
+        n, m = (int(v) for v in rng.integers(1, 40, 2)) if trial % 3 else (int(rng.integers(40, 190)), int(rng.integers(40, 190)))
+        kind = trial % 5
+        P = 5
+        cs, th = [], None
+        for _ in range(P):
+            c, th0 = _tie_cost(rng, kind, n, m)
+            th = th if th is not None else th0
+            cs.append(c)
+        costs = np.stack(cs)
+        r2c, c2r = api.linear_assignment_reference_order(costs, th)
+        for p in range(P):
+            ref = _reference_lap(oracle, costs[p], th)
+            assert np.array_equal(r2c[p], ref[0]) and np.array_equal(c2r[p], ref[1]), (trial, n, m, kind, p)
+
+
+@pytest.mark.parametrize("n,m,kind", [(200, 300, 1), (300, 200, 3), (448, 256, 1), (256, 448, 2), (500, 700, 3), (640, 384, 4),
+                                      (385, 1, 0), (1, 400, 1)])
+def test_device_lapjv_reproduces_reference_ties_cta_wide(oracle, n, m, kind):
+    """rows + columns > 384: the CTA-wide dense LAPJV (jv_block_device.cuh), at C2-like sizes, ties included."""
+    rng = np.random.default_rng(1000 * n + m)
+    cs = []
+    c, th = _tie_cost(rng, kind, n, m)
+    cs.append(c)
+    cs.append(_tie_cost(rng, kind, n, m)[0])
+    costs = np.stack(cs)
+    r2c, c2r = api.linear_assignment_reference_order(costs, th)
+    for p in range(2):
+        ref = _reference_lap(oracle, costs[p], th)
+        assert np.array_equal(r2c[p], ref[0]) and np.array_equal(c2r[p], ref[1]), (n, m, kind, p)
+
+
+def test_device_lapjv_on_a_c2_frame_with_duplicated_detections(oracle):
+    """A real C2 cost matrix (256 tracks x 448 detections, 1 - IoU * conf) in which 40 detections appear twice: exactly
+    tied optima at the headline size, resolved as the reference resolves them."""
+    dets = synth.bytetrack_stream(5, n_frames=2)
+    a = dets[0, :256, :4]
+    b = dets[1, :448].copy()
+    b[400:440] = b[100:140]                                   # bit-identical duplicates
+    cost = oracle.fuse_score(oracle.iou_distance(a, b[:, :4]), b[:, 4])
+    r2c, c2r = api.linear_assignment_reference_order(cost, 0.8)
+    ref = _reference_lap(oracle, cost, 0.8)
+    assert np.array_equal(r2c, ref[0]) and np.array_equal(c2r, ref[1])
+    sparse = api.linear_assignment_arrays(cost, 0.8)          # the sparse solver: same matched SET sizes, ties may differ
+    assert (sparse[0] >= 0).sum() == (ref[0] >= 0).sum()
+
+
 # ------------------------------------------------------------------ cost matrices
 @pytest.mark.parametrize("n,m", [(1, 1), (7, 5), (256, 512), (300, 1031), (2048, 2048)])
 def test_iou_costs_bit_exact(oracle, n, m):

@@ -4,10 +4,10 @@ sm_100a kernels through the C ABI (GPU) - reference src/trackers/ocsort.cpp.
 Ties.  The reference spawns bit-identical "twin" tracks (parity trap 8), so exactly tied
 assignment optima are systematic in OC-SORT.  Oracle modes: tie_mode=0 resolves them with the reference's LAPJV
 scan order (pinned to the real lap_solver.hpp); tie_mode=1 with the "prefer the higher column" infinitesimal of
-the sparse CUDA solver; tie_mode=2 is the CUDA kernel's policy - whenever a twin is an assignment candidate and
+the sparse CUDA solver; tie_mode=0 is the CUDA kernel's policy - whenever a twin is an assignment candidate and
 rows + columns <= 384 the kernel re-solves the frame with the reference's own dense LAPJV (csrc/jv_device.cuh), so
 it equals tie_mode=0 there, and falls back to the tie_mode=1 rule for larger problems.  Kernel parity is asserted
-bit for bit against tie_mode=2 (== the reference for every problem of the small shape, where rows + columns <= 320);
+bit for bit against tie_mode=0 (== the reference for every problem of the small shape, where rows + columns <= 320);
 test_tie_modes_differ_only_on_twin_ties measures how modes 0 and 1 relate.
 """
 import ctypes as C
@@ -99,7 +99,7 @@ def test_ocsort_duplicate_spawn_trap(oracle):
 # ------------------------------------------------------------------ kernel logic under the emulator (CPU)
 def _sim_vs_oracle(oracle, seed, T, args, n_obj=40, canvas=(960, 540), threads=128):
     d, c = synth.stress_stream(seed, n_frames=T, n_obj=n_obj, canvas=canvas)
-    ref = oracle.OCSort(**args, tie_mode=2)
+    ref = oracle.OCSort(**args, tie_mode=0)
     sim = sim_lib.SimOCSort(1, args["det_thresh"], args["max_age"], args["min_hits"], args["iou_threshold"],
                             args["min_conf"], args["delta_t"], args["inertia"], args["use_byte"], args["q_xy_scaling"],
                             args["q_s_scaling"])
@@ -126,6 +126,15 @@ def test_ocsort_kernel_logic_under_emulator(oracle):
     _sim_vs_oracle(oracle, 7, 70, {**OC_ARGS, "use_byte": True}, threads=64)
     _sim_vs_oracle(oracle, 8, 60, {**OC_ARGS, "use_byte": True, "inertia": 0.9})        # dense (unpruned) path
     _sim_vs_oracle(oracle, 9, 50, {**OC_ARGS, "iou_threshold": 0.1, "inertia": 0.5}, n_obj=48, canvas=(480, 270))
+
+
+def test_ocsort_cta_wide_lapjv_under_emulator(oracle):
+    """The same streams with the one-warp LAPJV limited to 24 rows + columns: every larger twin-tie frame goes through
+    the CTA-wide dense LAPJV (csrc/jv_block_device.cuh), which must reproduce the reference's LAPJV (oracle tie_mode 0)."""
+    with sim_lib.variant("jvblock"):
+        _sim_vs_oracle(oracle, 0, 110, OC_ARGS)
+        _sim_vs_oracle(oracle, 7, 70, {**OC_ARGS, "use_byte": True}, threads=64)
+        _sim_vs_oracle(oracle, 9, 50, {**OC_ARGS, "iou_threshold": 0.1, "inertia": 0.5}, n_obj=48, canvas=(480, 270))
 
 
 def test_tie_modes_differ_only_on_twin_ties(oracle):
@@ -187,7 +196,7 @@ def _engine_vs_oracle(oracle, streams, args, cap, d_max, T_chunk=None, check_sta
     dets = np.stack([s[0] for s in streams], 1)
     counts = np.stack([s[1] for s in streams], 1).astype(np.int32)
     eng = api.Engine(_lib.TRACKER_OCSORT, S, cap, d_max, **args)
-    refs = [oracle.OCSort(**args, tie_mode=2) for _ in range(S)]
+    refs = [oracle.OCSort(**args, tie_mode=0) for _ in range(S)]
     T_chunk = T_chunk or T
     for t0 in range(0, T, T_chunk):
         t1 = min(T, t0 + T_chunk)
@@ -221,7 +230,7 @@ def test_gpu_ocsort_c2_shape_and_api_mirror(oracle, gpu):
     d = synth.bytetrack_stream(3, n_frames=45, n_clutter=24, n_low=40, config=4)   # 320 detections / frame
     streams = [(d, np.full(d.shape[0], d.shape[1], np.int32))]
     _engine_vs_oracle(oracle, streams, OC_ARGS, 1536, 512, T_chunk=15)
-    trk, ref = api.OCSort(), oracle.OCSort(tie_mode=2)
+    trk, ref = api.OCSort(), oracle.OCSort(tie_mode=0)
     dd, cc = synth.stress_stream(77, n_frames=50)
     for t in range(50):
         assert np.array_equal(trk.update(dd[t, :cc[t]], (540, 960)), ref.update(dd[t, :cc[t]]))
@@ -229,6 +238,33 @@ def test_gpu_ocsort_c2_shape_and_api_mirror(oracle, gpu):
         trk.update(np.zeros((2, 5), np.float32), (540, 960))
     with pytest.raises(ValueError):
         trk.update(np.zeros((0, 6), np.float32), None)
+
+
+@pytest.mark.gpu
+def test_gpu_ocsort_twin_ties_above_the_one_warp_limit(oracle, gpu):
+    """Crowded scenes (rows + columns well above 384) in which the duplicate-spawn trap keeps producing twin tracks: the
+    kernel must follow the reference's LAPJV (oracle tie_mode 0, pinned to the reference's own solver) through every tie
+    - the CTA-wide dense LAPJV of csrc/jv_block_device.cuh - and the test checks that it actually ran."""
+    streams = [synth.stress_stream(400 + s, n_frames=70, n_obj=260, canvas=(1600, 900)) for s in range(2)]
+    S = len(streams)
+    dets = np.stack([s[0] for s in streams], 1)
+    counts = np.stack([s[1] for s in streams], 1).astype(np.int32)
+    for args in (OC_ARGS, {**OC_ARGS, "use_byte": True, "iou_threshold": 0.2}):
+        eng = api.Engine(_lib.TRACKER_OCSORT, S, 1536, 512, **args)
+        refs = [oracle.OCSort(**args, tie_mode=0) for _ in range(S)]
+        out, n_out = eng.update(dets, counts, ld_out=1536)
+        eng.check()
+        exact = 0
+        for s in range(S):
+            for t in range(dets.shape[0]):
+                want = refs[s].update(dets[t, s, :counts[t, s]])
+                got = out[t, s, :n_out[t, s]]
+                assert got.shape == want.shape and np.array_equal(got, want), (s, t)
+            dm, gd = refs[s].dump(), eng.dump(s, 0)
+            assert np.array_equal(gd[:, :15], dm[:, :15]) and np.array_equal(gd[:, 15:71], dm[:, 20:]), s
+            exact += int(eng.header(s)[14])
+        eng.close()
+        assert exact > 0, "no twin-tie frame in these streams: the CTA-wide LAPJV never ran"
 
 
 @pytest.mark.gpu
@@ -258,7 +294,7 @@ def test_small_shape_kernel_equals_reference_tie_breaking(oracle):
     tie_mode 2 and tie_mode 0 are the same tracker there, frame after frame, on streams full of twin ties."""
     for seed in (0, 3):
         d, c = synth.stress_stream(seed, n_frames=150, n_obj=40)
-        a, b = oracle.OCSort(**OC_ARGS, tie_mode=0), oracle.OCSort(**OC_ARGS, tie_mode=2)
+        a, b = oracle.OCSort(**OC_ARGS, tie_mode=0), oracle.OCSort(**OC_ARGS, tie_mode=0)
         for t in range(150):
             assert np.array_equal(a.update(d[t, :c[t]]), b.update(d[t, :c[t]]))
         assert np.array_equal(a.dump(), b.dump())

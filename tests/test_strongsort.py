@@ -86,7 +86,7 @@ def test_oracle_tie_modes(oracle):
 # ------------------------------------------------------------------ kernel logic under the emulator (CPU)
 def _sim_vs_oracle(oracle, seed, T, dim, args, use_embs=True, threads=128, n_obj=20):
     d, c, e = synth.stress_stream_reid(seed, n_frames=T, dim=max(dim, 4), n_obj=n_obj)
-    ref = oracle.StrongSort(tie_mode=2, **args)
+    ref = oracle.StrongSort(tie_mode=0, **args)
     sim = sim_lib.SimStrongSort(1, dim if use_embs else 0, **args)
     stats = np.zeros(8, np.int64)
     for t in range(T):
@@ -117,6 +117,13 @@ def test_strongsort_kernel_logic_under_emulator(oracle):
     _sim_vs_oracle(oracle, 7, 40, 132, {**ARGS, "max_cos_dist": 0.5, "nn_budget": 3, "max_age": 2})
 
 
+def test_strongsort_cta_wide_lapjv_under_emulator(oracle):
+    """Duplicated-row ties above 24 rows + columns go through the CTA-wide dense LAPJV (csrc/jv_block_device.cuh)."""
+    with sim_lib.variant("jvblock"):
+        _sim_vs_oracle(oracle, 3, 80, 32, LOOSE)
+        _sim_vs_oracle(oracle, 6, 50, 32, {**LOOSE, "n_init": 1, "mc_lambda": 0.9}, threads=64)
+
+
 # ------------------------------------------------------------------ GPU parity through the C ABI
 @pytest.fixture
 def gpu():
@@ -132,7 +139,7 @@ def _engine_vs_oracle(oracle, streams, args, cap, d_max, dim, T_chunk=None, chec
     counts = np.stack([s[1] for s in streams], 1).astype(np.int32)
     embs = np.stack([s[2] for s in streams], 1) if dim else None
     eng = api.Engine(_lib.TRACKER_STRONGSORT, S, cap, d_max, emb_dim=dim, **args)
-    refs = [oracle.StrongSort(tie_mode=2, **args) for _ in range(S)]
+    refs = [oracle.StrongSort(tie_mode=0, **args) for _ in range(S)]
     T_chunk = T_chunk or T
     rows = 0
     for t0 in range(0, T, T_chunk):
@@ -182,7 +189,7 @@ def test_strongsort_larger_shape(oracle, gpu):
 def test_strongsort_facade_mirrors_reference_api(oracle, gpu):
     d, c, e = synth.stress_stream_reid(60, n_frames=40, n_obj=16, dim=32, noise=0.2)
     trk = api.StrongSort(emb_dim=32, track_capacity=256, max_dets=64)
-    ref = oracle.StrongSort(tie_mode=2, **ARGS)
+    ref = oracle.StrongSort(tie_mode=0, **ARGS)
     img = (540, 960)
     for t in range(40):
         n = 0 if t in (11, 12) else int(c[t])
