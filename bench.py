@@ -7,8 +7,9 @@
 
 A "step" = `--frames` consecutive update()s for every one of the `--streams` streams of a rank.
   value      frames/s, inputs already resident in HBM (mot_engine_update_device, one launch/step)
-  e2e        frames/s through the host-buffer C-ABI call (mot_engine_update_host): pinned host
-             detections in, result rows out, copies inside the timed region
+  e2e        frames/s through the host-buffer C-ABI call (mot_engine_update_host_packed): pinned host
+             detections in, valid result rows out, copies inside the timed region; next to it the box's
+             measured copy ceiling for the same bytes (plain cudaMemcpyAsync at all ranks)
   roofline   bytetrack_step_kernel: SURVEY.md 8(d) algorithmic bytes per update() x frames per
              launch / measured launch time, against MEASURED_PEAKS.json HBM bandwidth
   cpu_baseline  the oracle (restated reference, oracle/liboracle.so) on the host cores, bounded sample
@@ -55,6 +56,9 @@ def parse():
     ap.add_argument("--streams", type=int, default=296, help="camera streams per GPU (default 2 per SM)")
     ap.add_argument("--frames", type=int, default=50, help="update() calls per stream per step")
     ap.add_argument("--base-streams", type=int, default=16, help="distinct seeded streams tiled to --streams")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
+                    help="c2 = BASELINE configs[1] batched to --streams streams per GPU (headline); c5 = configs[4] taken "
+                         "literally: 64 streams in total, sharded over the GPUs (64 / N per GPU)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -230,6 +234,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     lib = _lib.load()
+    if args.workload == "c5":
+        args.streams = max(1, 64 // world)
     S, F, W, K = args.streams, args.frames, args.warmup, args.steps
     T_total = (W + K) * F
 
@@ -283,7 +289,8 @@ def main():
     elapsed_ms = float(el.item())
     value = world * S * F * K / (elapsed_ms * 1e-3)
 
-    # ---- e2e: host-buffer C-ABI call, pinned host memory, copies inside the timed region
+    # ---- e2e: host-buffer C-ABI call, pinned host memory, copies inside the timed region.  The packed call returns
+    #      exactly the rows BaseTracker::update would have returned (no padding crosses the bus).
     e2e = None
     if not args.no_e2e:
         eng.reset()
@@ -291,29 +298,58 @@ def main():
         h_dets[...] = dets.cpu().numpy()
         h_nd = api.pinned_empty((T_total, S), np.int32)
         h_nd[...] = N_DETS
-        h_out = api.pinned_empty((F, S, LD_OUT, 8), np.float32)
+        h_rows = api.pinned_empty((F * S * LD_OUT, 8), np.float32)
+        h_off = api.pinned_empty((F * S + 1,), np.int64)
         h_no = api.pinned_empty((F, S), np.int32)
 
         def step_host(i):
-            api.check(lib.mot_engine_update_host(eng._h, F, h_dets[i * F].ctypes.data, h_nd[i * F].ctypes.data, N_DETS,
-                                                 h_out.ctypes.data, h_no.ctypes.data, LD_OUT))
+            api.check(lib.mot_engine_update_host_packed(eng._h, F, h_dets[i * F].ctypes.data, h_nd[i * F].ctypes.data, N_DETS,
+                                                        LD_OUT, h_rows.ctypes.data, h_rows.shape[0], h_off.ctypes.data,
+                                                        h_no.ctypes.data))
         for i in range(W):
             step_host(i)
         barrier()
+        rows_total = 0
         t0 = time.perf_counter()
         for i in range(K):
             step_host(W + i)
+            rows_total += int(h_off[F * S])                    # the step's result, read on the host
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         dtt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(dtt, op=dist.ReduceOp.MAX)
         eng.check()
-        e2e = {"value": world * S * F * K / float(dtt.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(S * F * (N_DETS * 6 * 4 + 4)),
-               "d2h_bytes_per_step": int(S * F * (LD_OUT * 8 * 4 + 4)),
-               "api": "mot_engine_update_host (pinned host buffers; copy-in / kernel / copy-out pipelined over %d frame chunks)" % min(32, F // 2),
-               "checksum_rows": int(h_no.sum())}
+        h2d_step = int(S * F * (N_DETS * 6 * 4 + 4))
+        d2h_step = int(rows_total // K * 32 + S * F * 4 + (S * F + 32) * 4)
+        e2e_value = world * S * F * K / float(dtt.item())
+        # the box's copy ceiling for exactly these byte counts: plain pinned cudaMemcpyAsync, H2D and D2H on two streams
+        # at once, all ranks together, nothing else running - NOT part of the metric, it says what limits e2e
+        s_a, s_b = torch.cuda.Stream(), torch.cuda.Stream()
+        d_sink, d_src = dets[:F].data_ptr(), out.data_ptr()
+
+        def step_copy():
+            api.check(lib.mot_copy_h2d(d_sink, h_dets.ctypes.data, h2d_step, s_a.cuda_stream))
+            api.check(lib.mot_copy_d2h(h_rows.ctypes.data, d_src, min(d2h_step, h_rows.nbytes), s_b.cuda_stream))
+        for _ in range(2):
+            step_copy()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            step_copy()
+        torch.cuda.synchronize()
+        dc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dc, op=dist.ReduceOp.MAX)
+        ceiling = world * S * F * K / float(dc.item())
+        e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
+               "api": "mot_engine_update_host_packed (pinned host buffers; copy-in / kernel + row compaction / copy-out of the "
+                      "valid rows, pipelined over %d frame chunks)" % min(32, F // 2),
+               "checksum_rows": int(h_no.sum()), "rows_per_frame": rows_total / float(K * S * F),
+               "copy_ceiling": {"value": ceiling, "unit": UNIT, "frac": e2e_value / ceiling,
+                                "gbs_all_ranks": world * (h2d_step + d2h_step) * K / float(dc.item()) / 1e9,
+                                "what": "same H2D + D2H bytes per step as plain pinned cudaMemcpyAsync on two streams, all "
+                                        "ranks at once, no kernel: the host-memory / PCIe limit of this box for the e2e path"}}
 
     if rank != 0:
         if world > 1:
@@ -348,7 +384,8 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ByteTrack, synthetic 256 tracks x 512 dets/frame, 1xB200 (BASELINE configs[1])",
+        "config": {"workload": ("ByteTrack, synthetic 256 tracks x 512 dets/frame, 1xB200 (BASELINE configs[1])" if args.workload == "c2"
+                                else "64 independent streams x ByteTrack 256x512, sharded across the GPUs (BASELINE configs[4]): %d per GPU" % S),
                    "streams_per_gpu": S, "frames_per_step": F, "dets_per_frame": N_DETS, "canvas": [3840, 2160],
                    "distinct_seeded_streams": B, "track_capacity": TRACK_CAPACITY, "tracker_args": BT_ARGS,
                    "l2": "inputs larger than L2: every step reads %.0f MB of fresh detections and %.0f MB of tracker state"

@@ -113,6 +113,16 @@ int mot_engine_reset(mot_engine* e);
  * chunks).  n_frames = 1 is the reference's tracker->update(dets, img) for S trackers at once. */
 int mot_engine_update_host(mot_engine* e, int n_frames, const float* dets, const int* n_dets, int ld_dets,
                            float* out, int* n_out, int ld_out);
+/* Host buffers in, PACKED rows out - what n_frames x S calls of BaseTracker::update would have returned, back to back
+ * (reference: the (M, 8) result matrix, e.g. src/trackers/bytetrack.cpp:596-620), without the padding of the call above:
+ *   out_rows [out_cap_rows][8]   rows of frame f = t * S + s at out_rows[offsets[f] .. offsets[f + 1])
+ *   offsets  [n_frames * S + 1]  exclusive row offsets (offsets[n_frames * S] = total rows)
+ *   n_out    [n_frames][S]
+ * max_rows bounds the rows of ONE frame (more are truncated and flagged, see mot_engine_check).  The rows are compacted
+ * on the device, so only valid rows cross the bus (C2 workload: 361 of 512).  MOT_ERR_INVALID_ARGUMENT when out_cap_rows
+ * is too small (state has advanced).  ByteTrack / SORT / OC-SORT engines, and BoT-SORT / StrongSORT without embeddings. */
+int mot_engine_update_host_packed(mot_engine* e, int n_frames, const float* dets, const int* n_dets, int ld_dets, int max_rows,
+                                  float* out_rows, long long out_cap_rows, long long* offsets, int* n_out);
 /* Same contract with DEVICE buffers, asynchronous on `stream`; no host synchronisation. */
 int mot_engine_update_device(mot_engine* e, int n_frames, const float* d_dets, const int* d_n_dets, int ld_dets,
                              float* d_out, int* d_n_out, int ld_out, void* stream);
@@ -123,9 +133,10 @@ int mot_engine_update_host_embs(mot_engine* e, int n_frames, const float* dets, 
                                 const float* embs, float* out, int* n_out, int ld_out);
 int mot_engine_update_device_embs(mot_engine* e, int n_frames, const float* d_dets, const int* d_n_dets, int ld_dets,
                                   const float* d_embs, float* d_out, int* d_n_out, int ld_out, void* stream);
-/* Per-stream sticky error bits since the last reset (0 = fine): 1 track capacity, 2 too many
- * detections, 4 output rows truncated, 8 Kalman fallback, 16 StrongSORT candidate table full.  Synchronises.  flags may be NULL; the
- * return value is MOT_OK or the most severe condition as a mot_status. */
+/* Per-stream error bits raised since the previous mot_engine_check / reset (0 = fine): 1 track capacity, 2 too many
+ * detections, 4 output rows truncated, 8 Kalman fallback, 16 StrongSORT candidate table full.  READ-AND-CLEAR: a
+ * transient condition is reported once, by the check that follows it.  Synchronises.  flags may be NULL; the return
+ * value is MOT_OK or the most severe condition as a mot_status. */
 int mot_engine_check(mot_engine* e, int* flags_per_stream);
 /* Introspection for tests: header ints of one stream [n_active,n_lost,n_free,id_counter,frame,err,
  * n1,m1,n2,m2,n3,m3,dupA,dupB,..] (16 ints), and a dump of one list (0 active, 1 lost) as rows of

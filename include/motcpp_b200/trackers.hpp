@@ -37,6 +37,12 @@ public:
         for (int i = 0; i < n; ++i)                       // Eigen is column-major, the ABI row-major
             for (int c = 0; c < 6; ++c) dets_rm_[static_cast<size_t>(i) * 6 + c] = dets(i, c);
         const float* embs_ptr = nullptr;
+        // The reference uses whatever `embs` it is handed; here the feature dimension is fixed at construction, so a
+        // mismatch is an error - never a silent fall-back to IoU-only association.
+        if (embs.rows() > 0 && embs.cols() > 0 && n > 0 && (embs.rows() != dets.rows() || embs.cols() != emb_dim_))
+            throw std::invalid_argument("embeddings are (" + std::to_string(embs.rows()) + ", " + std::to_string(embs.cols()) +
+                                        ") but the tracker was constructed for emb_dim = " + std::to_string(emb_dim_) +
+                                        " and this frame has " + std::to_string(n) + " detections");
         if (emb_dim_ > 0 && embs.rows() == dets.rows() && embs.cols() == emb_dim_ && n > 0) {
             for (int i = 0; i < n; ++i)
                 for (int c = 0; c < emb_dim_; ++c) embs_rm_[static_cast<size_t>(i) * emb_dim_ + c] = embs(i, c);

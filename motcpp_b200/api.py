@@ -494,6 +494,8 @@ class Engine:
         if S != self.n_streams:
             raise ValueError(f"expected {self.n_streams} streams, got {S}")
         n_dets = np.ascontiguousarray(n_dets, np.int32).reshape(T, S)
+        if n_dets.size and (int(n_dets.max()) > ld or int(n_dets.min()) < 0):
+            raise ValueError("n_dets must lie in [0, dets.shape[2]]")
         if ld_out <= 0:
             ld_out = self.cfg.track_capacity or 1536
         if out is None:
@@ -512,6 +514,31 @@ class Engine:
         except MotError as e:
             _raise(e)
         return (out[0], n_out[0]) if squeeze else (out, n_out)
+
+    def update_packed(self, dets: np.ndarray, n_dets: np.ndarray, max_rows: int = 0, out_rows: Optional[np.ndarray] = None):
+        """mot_engine_update_host_packed: dets (T,S,ld,6), n_dets (T,S) -> (rows (R,8), offsets (T*S+1,), n_out (T,S)); the rows
+        of frame t, stream s are rows[offsets[t*S+s] : offsets[t*S+s+1]] - exactly what update() would have returned."""
+        dets = np.ascontiguousarray(dets, np.float32)
+        T, S, ld, six = dets.shape
+        if six != 6:
+            raise ValueError("Detections must have 6 (AABB) or 7 (OBB) columns")
+        if S != self.n_streams:
+            raise ValueError(f"expected {self.n_streams} streams, got {S}")
+        n_dets = np.ascontiguousarray(n_dets, np.int32).reshape(T, S)
+        if n_dets.size and (int(n_dets.max()) > ld or int(n_dets.min()) < 0):
+            raise ValueError("n_dets must lie in [0, dets.shape[2]]")
+        max_rows = max_rows or (self.cfg.track_capacity or 1536)
+        if out_rows is None:
+            out_rows = np.empty((T * S * max_rows, 8), np.float32)
+        offsets = np.empty(T * S + 1, np.int64)
+        n_out = np.empty((T, S), np.int32)
+        try:
+            check(load().mot_engine_update_host_packed(self._h, T, dets.ctypes.data, n_dets.ctypes.data, ld, max_rows,
+                                                       out_rows.ctypes.data, out_rows.shape[0], offsets.ctypes.data,
+                                                       n_out.ctypes.data))
+        except MotError as e:
+            _raise(e)
+        return out_rows[:offsets[-1]], offsets, n_out
 
     def update_device(self, n_frames, d_dets, d_n_dets, ld_dets, d_out, d_n_out, ld_out, stream=None):
         """Raw device-pointer path (ints / c_void_p), asynchronous on `stream`."""
@@ -729,13 +756,18 @@ class BotSort:
             raise ValueError("ReID inference is outside the accelerated hot path: pass embeddings to update()")
         if asso_func != "iou" or per_class or is_obb:
             raise ValueError("only asso_func=\"iou\", per_class=False, is_obb=False are on the accelerated path")
-        self._engine = Engine(_lib.TRACKER_BOTSORT, 1, track_capacity, max_dets, device, det_thresh=det_thresh,
-                              max_age=max_age, max_obs=max_obs, min_hits=min_hits, iou_threshold=iou_threshold,
-                              track_high_thresh=track_high_thresh, track_low_thresh=track_low_thresh,
-                              new_track_thresh=new_track_thresh, track_buffer=track_buffer, match_thresh=match_thresh,
-                              proximity_thresh=proximity_thresh, appearance_thresh=appearance_thresh,
-                              frame_rate=frame_rate, fuse_first_associate=int(bool(fuse_first_associate)),
-                              with_reid=int(bool(with_reid)), emb_dim=emb_dim)
+        self._make = lambda dim: Engine(_lib.TRACKER_BOTSORT, 1, track_capacity, max_dets, device, det_thresh=det_thresh,
+                                        max_age=max_age, max_obs=max_obs, min_hits=min_hits, iou_threshold=iou_threshold,
+                                        track_high_thresh=track_high_thresh, track_low_thresh=track_low_thresh,
+                                        new_track_thresh=new_track_thresh, track_buffer=track_buffer, match_thresh=match_thresh,
+                                        proximity_thresh=proximity_thresh, appearance_thresh=appearance_thresh,
+                                        frame_rate=frame_rate, fuse_first_associate=int(bool(fuse_first_associate)),
+                                        with_reid=int(bool(with_reid)), emb_dim=dim)
+        self._frames = 0
+        self._build(emb_dim)
+
+    def _build(self, emb_dim):
+        self._engine = self._make(emb_dim)
         self._dim = emb_dim
         self._max_dets = self._engine.cfg.max_dets
         self._cap = self._engine.cfg.track_capacity
@@ -743,6 +775,21 @@ class BotSort:
         self._embs = np.zeros((1, 1, self._max_dets, emb_dim), np.float32) if emb_dim else None
         self._out = np.empty((1, 1, self._cap, 8), np.float32)
         self._n_out = np.empty((1, 1), np.int32)
+
+    def _adopt_embedding_dim(self, embs, n):
+        """The reference takes whatever `embs` it is handed with the same positional constructor.  A tracker built without
+        emb_dim therefore sizes itself from the first embeddings it sees; once frames have been processed the dimension
+        is fixed and a mismatch is an error - never a silent fall-back to IoU-only association."""
+        embs = np.asarray(embs, np.float32)
+        if embs.ndim != 2 or embs.shape[0] != n:
+            raise ValueError("Detections and embeddings must have same number of rows")
+        if embs.shape[1] != self._dim:
+            if self._dim == 0 and self._frames == 0:
+                self._engine.close()
+                self._build(int(embs.shape[1]))
+            else:
+                raise ValueError(f"embeddings have {embs.shape[1]} columns but the tracker was built for emb_dim={self._dim}")
+        return embs
 
     def reset(self):
         self._engine.reset()
@@ -765,14 +812,14 @@ class BotSort:
             raise ValueError(f"{n} detections exceed max_dets={self._max_dets}")
         self._dets[0, 0, :n] = dets[:, :6]
         e = None
-        if embs is not None and np.size(embs) and self._dim:
-            embs = np.asarray(embs, np.float32)
-            if embs.shape != (n, self._dim):
-                raise ValueError("Detections and embeddings must have same number of rows")
+        if embs is not None and np.size(embs):
+            embs = self._adopt_embedding_dim(embs, n)
+            self._dets[0, 0, :n] = dets[:, :6]
             self._embs[0, 0, :n] = embs
             e = self._embs
         self._engine.update(self._dets, np.array([[n]], np.int32), self._out, self._n_out, embs=e)
         self._engine.check()
+        self._frames += 1
         return self._out[0, 0, :int(self._n_out[0, 0])].copy()
 
 
@@ -791,10 +838,17 @@ class StrongSort:
             raise ValueError("ReID inference is outside the accelerated hot path: pass embeddings to update()")
         if per_class or is_obb:
             raise ValueError("only per_class=False, is_obb=False are on the accelerated path")
-        self._engine = Engine(_lib.TRACKER_STRONGSORT, 1, track_capacity, max_dets, device, det_thresh=det_thresh,
-                              max_age=max_age, max_obs=max_obs, min_hits=min_hits, iou_threshold=iou_threshold,
-                              min_conf=min_conf, max_cos_dist=max_cos_dist, max_iou_dist=max_iou_dist, n_init=n_init,
-                              nn_budget=nn_budget, mc_lambda=mc_lambda, ema_alpha=ema_alpha, emb_dim=emb_dim)
+        self._make = lambda dim: Engine(_lib.TRACKER_STRONGSORT, 1, track_capacity, max_dets, device, det_thresh=det_thresh,
+                                        max_age=max_age, max_obs=max_obs, min_hits=min_hits, iou_threshold=iou_threshold,
+                                        min_conf=min_conf, max_cos_dist=max_cos_dist, max_iou_dist=max_iou_dist, n_init=n_init,
+                                        nn_budget=nn_budget, mc_lambda=mc_lambda, ema_alpha=ema_alpha, emb_dim=dim)
+        self._frames = 0
+        self._build(emb_dim)
+
+    _adopt_embedding_dim = BotSort._adopt_embedding_dim
+
+    def _build(self, emb_dim):
+        self._engine = self._make(emb_dim)
         self._dim = emb_dim
         self._max_dets = self._engine.cfg.max_dets
         self._cap = self._engine.cfg.track_capacity
@@ -824,13 +878,13 @@ class StrongSort:
             raise ValueError(f"{n} detections exceed max_dets={self._max_dets}")
         self._dets[0, 0, :n] = dets[:, :6] if n else 0
         e = None
-        if n and embs is not None and np.size(embs) and self._dim:
-            embs = np.asarray(embs, np.float32)
-            if embs.shape != (n, self._dim):
-                raise ValueError(f"embeddings must be (n, {self._dim})")
+        if n and embs is not None and np.size(embs):
+            embs = self._adopt_embedding_dim(embs, n)
+            self._dets[0, 0, :n] = dets[:, :6]
             self._embs[0, 0, :n] = embs
             e = self._embs
         # an empty frame still advances the tracker: predict + every track missed (strongsort.cpp:833-837)
         self._engine.update(self._dets, np.array([[n]], np.int32), self._out, self._n_out, embs=e)
         self._engine.check()
+        self._frames += 1
         return self._out[0, 0, :int(self._n_out[0, 0])].copy()

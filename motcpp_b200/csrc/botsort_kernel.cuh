@@ -474,7 +474,7 @@ __device__ __forceinline__ void bot_frame(const BotArgs& a, const BotStream& st,
     int n_free = st.hdr[kHdrFree];
     const int id_base = st.hdr[kHdrIdCounter];
     int n_det = n_det_in;
-    if (n_det > DMAX) { n_det = DMAX; if (tid == 0) atomicOr(&st.hdr[kHdrError], (int)kErrTooManyDets); }
+    if (n_det > min(DMAX, a.ld_dets)) { n_det = min(DMAX, a.ld_dets); if (tid == 0) atomicOr(&st.hdr[kHdrError], (int)kErrTooManyDets); }
 
     // ---- A. detections: IoU boxes, confidence split, feature normalisation
     for (int j = tid; j < n_det; j += nt) {

@@ -221,7 +221,7 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
     int n_free = st.hdr[kHdrFree];
     const int id_base = st.hdr[kHdrIdCounter];
     int n_det = n_det_in;
-    if (n_det > d_max) { n_det = d_max; if (tid == 0) atomicOr(&st.hdr[kHdrError], (int)kErrTooManyDets); }
+    if (n_det > min(d_max, a.ld_dets)) { n_det = min(d_max, a.ld_dets); if (tid == 0) atomicOr(&st.hdr[kHdrError], (int)kErrTooManyDets); }
 
     // ---- A. detections: IoU boxes, confidence split
     for (int j = tid; j < n_det; j += nt) {

@@ -19,6 +19,7 @@
 #include "kernels_kf.cuh"
 #include "kernels_lap.cuh"
 #include "kernels_cosine.cuh"
+#include "kernels_pack.cuh"
 #include "sort_kernel.cuh"
 #include "ocsort_kernel.cuh"
 #include "botsort_kernel.cuh"
@@ -99,6 +100,11 @@ struct mot_engine {
     int* d_ndets = nullptr;   size_t ndets_cap = 0;
     float* d_out = nullptr;   size_t out_cap = 0;
     int* d_nout = nullptr;    size_t nout_cap = 0;
+    // packed host path: compacted rows, per-frame offsets, per-chunk totals (pinned)
+    float* d_packed = nullptr; size_t packed_cap = 0;
+    int* d_off = nullptr;      size_t off_cap = 0;
+    int* h_off = nullptr;      size_t h_off_cap = 0;   // pinned mirror of d_off
+    cudaEvent_t ev_tot[kMaxChunks] = {};
 };
 
 
@@ -265,9 +271,15 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     if (cfg->kind == MOT_TRACKER_OCSORT && (cfg->delta_t < 1 || cfg->delta_t > mot::kOcRing))
         return fail(MOT_ERR_UNSUPPORTED, "delta_t %d is outside 1..%d (observation ring size)", cfg->delta_t, mot::kOcRing);
     if (int rc = require_device()) return rc;
+    int prev_device = 0;
+    MOT_CUDA(cudaGetDevice(&prev_device));
     MOT_CUDA(cudaSetDevice(cfg->device));
     mot_engine* e = new mot_engine();
     e->cfg = *cfg;
+    struct Guard {                       // every early return below frees the half-built engine and restores the device
+        mot_engine** e; int dev;
+        ~Guard() { if (*e) mot_engine_destroy(*e); cudaSetDevice(dev); }
+    } guard{&e, prev_device};
     const bool is_sort = cfg->kind == MOT_TRACKER_SORT, is_oc = cfg->kind == MOT_TRACKER_OCSORT;
     const bool is_bot = cfg->kind == MOT_TRACKER_BOTSORT, is_ss = cfg->kind == MOT_TRACKER_STRONGSORT;
     if (e->cfg.track_capacity <= 0) e->cfg.track_capacity = 1536;
@@ -289,7 +301,6 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     }
     if (e->shape < 0) {
         const int tc = e->cfg.track_capacity, md = e->cfg.max_dets;
-        delete e;
         return fail(MOT_ERR_INVALID_ARGUMENT, "track_capacity %d / max_dets %d exceed the largest built shape (%s)", tc, md,
                     is_oc ? "3072 tracks / 2048 detections" : (is_bot ? "2048 tracks / 1024 detections" : (is_ss ? "1536 tracks / 512 detections" : "3072 tracks / 1024 detections")));
     }
@@ -349,7 +360,6 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     MOT_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
     if (e->smem_bytes > (size_t)max_optin) {
         const size_t need = e->smem_bytes;
-        delete e;
         return fail(MOT_ERR_INVALID_ARGUMENT, "track_capacity/max_dets need %zu B of shared memory per CTA (limit %d)",
                     need, max_optin);
     }
@@ -365,8 +375,9 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     }
     MOT_CUDA(cudaMalloc(&e->d_state, e->stride * (size_t)cfg->n_streams));
     MOT_CUDA(cudaMemsetAsync(e->d_state, 0, e->stride * (size_t)cfg->n_streams, e->streams[0]));
-    if (int rc = engine_reset_impl(e, 0)) { mot_engine_destroy(e); return rc; }
+    if (int rc = engine_reset_impl(e, 0)) return rc;
     *out = e;
+    e = nullptr;                         // ownership passes to the caller; the guard only restores the device
     return MOT_OK;
 }
 
@@ -377,7 +388,10 @@ int mot_engine_destroy(mot_engine* e) {
         if (e->streams[c]) cudaStreamDestroy(e->streams[c]);
         if (e->ev_in[c]) cudaEventDestroy(e->ev_in[c]);
         if (e->ev_run[c]) cudaEventDestroy(e->ev_run[c]);
+        if (e->ev_tot[c]) cudaEventDestroy(e->ev_tot[c]);
     }
+    cudaFree(e->d_packed); cudaFree(e->d_off);
+    if (e->h_off) cudaFreeHost(e->h_off);
     cudaFree(e->d_state); cudaFree(e->d_embs); cudaFree(e->d_dets); cudaFree(e->d_ndets); cudaFree(e->d_out); cudaFree(e->d_nout);
     delete e;
     return MOT_OK;
@@ -398,6 +412,7 @@ int mot_engine_update_device_embs(mot_engine* e, int T, const float* d_dets, con
     if (d_embs && ((e->cfg.kind != MOT_TRACKER_BOTSORT && e->cfg.kind != MOT_TRACKER_STRONGSORT) || e->cfg.emb_dim <= 0))
         return fail(MOT_ERR_INVALID_ARGUMENT, "embeddings need a BoT-SORT / StrongSORT engine created with emb_dim > 0");
     if (d_embs && (((size_t)d_embs) & 15)) return fail(MOT_ERR_INVALID_ARGUMENT, "embs must be 16-byte aligned");
+    MOT_CUDA(cudaSetDevice(e->cfg.device));          // a NULL stream must mean the ENGINE's device
     const int S = e->cfg.n_streams;
     engine_launch(e, T, d_dets, d_n_dets, ld_dets, d_embs, d_out, d_n_out, ld_out, 0, S, (cudaStream_t)stream);
     MOT_CUDA(cudaGetLastError());
@@ -474,6 +489,78 @@ int mot_engine_update_host_embs(mot_engine* e, int T, const float* dets, const i
                                    (s1 - s0) * sizeof(int), T, cudaMemcpyDeviceToHost, st));
     }
     for (int c = 0; c < C; ++c) MOT_CUDA(cudaStreamSynchronize(e->streams[c]));
+    return MOT_OK;
+}
+
+// Host buffers in, PACKED rows out: only the valid rows cross the bus (on the C2 workload 361 of the 512 padded rows).
+int mot_engine_update_host_packed(mot_engine* e, int T, const float* dets, const int* n_dets, int ld_dets, int max_rows,
+                                  float* out_rows, long long out_cap_rows, long long* offsets, int* n_out) {
+    if (!e || !dets || !n_dets || !out_rows || !offsets || !n_out) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
+    if (T <= 0 || ld_dets <= 0 || max_rows <= 0 || out_cap_rows < 0) return fail(MOT_ERR_INVALID_ARGUMENT, "non-positive size");
+    if (e->cfg.kind == MOT_TRACKER_BOTSORT || e->cfg.kind == MOT_TRACKER_STRONGSORT)
+        if (e->cfg.emb_dim > 0) return fail(MOT_ERR_UNSUPPORTED, "the packed host path carries no embeddings; use mot_engine_update_host_embs");
+    MOT_CUDA(cudaSetDevice(e->cfg.device));
+    const int S = e->cfg.n_streams, ld_out = max_rows;
+    const size_t TS = (size_t)T * S;
+    const int C = std::max(1, std::min(kMaxChunks, T / 2));
+    if (int rc = grow(&e->d_dets, &e->dets_cap, TS * ld_dets * 6)) return rc;
+    if (int rc = grow(&e->d_ndets, &e->ndets_cap, TS)) return rc;
+    if (int rc = grow(&e->d_out, &e->out_cap, TS * ld_out * 8)) return rc;
+    if (int rc = grow(&e->d_nout, &e->nout_cap, TS)) return rc;
+    if (int rc = grow(&e->d_packed, &e->packed_cap, TS * ld_out * 8)) return rc;
+    if (int rc = grow(&e->d_off, &e->off_cap, TS + (size_t)C)) return rc;
+    if (e->h_off_cap < TS + (size_t)C) {
+        if (e->h_off) cudaFreeHost(e->h_off);
+        e->h_off = nullptr; e->h_off_cap = 0;
+        MOT_CUDA(cudaHostAlloc((void**)&e->h_off, sizeof(int) * (TS + (size_t)C), cudaHostAllocDefault));
+        e->h_off_cap = TS + (size_t)C;
+    }
+    for (int c = 0; c < C; ++c)
+        if (!e->ev_tot[c]) MOT_CUDA(cudaEventCreateWithFlags(&e->ev_tot[c], cudaEventDisableTiming));
+    cudaStream_t s_run = e->streams[0], s_in = e->streams[1], s_out = e->streams[2];
+    const size_t det_fr = (size_t)S * ld_dets * 6, out_fr = (size_t)S * ld_out * 8;
+    long long base = 0;                                    // rows already handed to the caller
+    auto t_of = [&](int c) { return (int)((long long)T * c / C); };
+    auto enqueue = [&](int c) -> int {
+        const int t0 = t_of(c), nt = t_of(c + 1) - t0, nf = nt * S;
+        MOT_CUDA(cudaMemcpyAsync(e->d_dets + t0 * det_fr, dets + t0 * det_fr, nt * det_fr * sizeof(float), cudaMemcpyHostToDevice, s_in));
+        MOT_CUDA(cudaMemcpyAsync(e->d_ndets + (size_t)t0 * S, n_dets + (size_t)t0 * S, (size_t)nf * sizeof(int), cudaMemcpyHostToDevice, s_in));
+        MOT_CUDA(cudaEventRecord(e->ev_in[c], s_in));
+        MOT_CUDA(cudaStreamWaitEvent(s_run, e->ev_in[c], 0));
+        engine_launch(e, nt, e->d_dets + t0 * det_fr, e->d_ndets + (size_t)t0 * S, ld_dets, nullptr, e->d_out + t0 * out_fr,
+                      e->d_nout + (size_t)t0 * S, ld_out, 0, S, s_run);
+        int* off = e->d_off + (size_t)t0 * S + c;          // nf + 1 ints per chunk
+        mot::pack_scan_kernel<<<1, 1024, 0, s_run>>>(e->d_nout + (size_t)t0 * S, nf, ld_out, off);
+        mot::pack_rows_kernel<<<std::min(nf, sm_count() * 8), 256, 0, s_run>>>((const float4*)(e->d_out + t0 * out_fr), e->d_nout + (size_t)t0 * S,
+                                                                                 off, nf, ld_out, (float4*)(e->d_packed + t0 * out_fr));
+        MOT_CUDA(cudaGetLastError());
+        MOT_CUDA(cudaEventRecord(e->ev_run[c], s_run));
+        MOT_CUDA(cudaStreamWaitEvent(s_out, e->ev_run[c], 0));
+        MOT_CUDA(cudaMemcpyAsync(e->h_off + (size_t)t0 * S + c, off, (size_t)(nf + 1) * sizeof(int), cudaMemcpyDeviceToHost, s_out));
+        MOT_CUDA(cudaMemcpyAsync(n_out + (size_t)t0 * S, e->d_nout + (size_t)t0 * S, (size_t)nf * sizeof(int), cudaMemcpyDeviceToHost, s_out));
+        MOT_CUDA(cudaEventRecord(e->ev_tot[c], s_out));
+        return MOT_OK;
+    };
+    auto drain = [&](int c) -> int {                       // the chunk's row count is known: copy exactly that many rows
+        const int t0 = t_of(c), nf = (t_of(c + 1) - t0) * S;
+        MOT_CUDA(cudaEventSynchronize(e->ev_tot[c]));
+        const int* off = e->h_off + (size_t)t0 * S + c;
+        const long long rows = off[nf];
+        if (base + rows > out_cap_rows) return fail(MOT_ERR_INVALID_ARGUMENT, "out_rows holds %lld rows, %lld needed so far", out_cap_rows, base + rows);
+        if (rows > 0)
+            MOT_CUDA(cudaMemcpyAsync(out_rows + base * 8, e->d_packed + t0 * out_fr, (size_t)rows * 8 * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+        for (int f = 0; f < nf; ++f) offsets[(size_t)t0 * S + f] = base + off[f];
+        base += rows;
+        return MOT_OK;
+    };
+    // software pipeline: chunk c + 1 is queued before the host waits for the row count of chunk c
+    if (int rc = enqueue(0)) return rc;
+    for (int c = 0; c < C; ++c) {
+        if (c + 1 < C) if (int rc = enqueue(c + 1)) return rc;
+        if (int rc = drain(c)) { cudaStreamSynchronize(s_run); cudaStreamSynchronize(s_out); return rc; }
+    }
+    offsets[TS] = base;
+    MOT_CUDA(cudaStreamSynchronize(s_out));
     return MOT_OK;
 }
 
@@ -562,6 +649,9 @@ int mot_engine_check(mot_engine* e, int* flags) {
                           sizeof(int), S, cudaMemcpyDeviceToHost));
     int all = 0;
     for (int s = 0; s < S; ++s) { all |= err[s]; if (flags) flags[s] = err[s]; }
+    // read-and-clear: a transient condition (one crowded frame, one truncated output) is reported once, by the check
+    // that follows it, instead of failing every later update() until reset()
+    if (all) MOT_CUDA(cudaMemset2D(e->d_state + sizeof(int) * mot::kHdrError, e->stride, 0, sizeof(int), S));
     if (all & (mot::kErrCapacity | mot::kErrTooManyDets | mot::kErrOutput))
         return fail(MOT_ERR_CAPACITY, "engine capacity exceeded (flags 0x%x: 1 track slots, 2 detections, 4 output rows)", all);
     if (all & mot::kErrTable) return fail(MOT_ERR_CAPACITY, "StrongSORT appearance candidate table full (flag 16)");
@@ -711,6 +801,7 @@ int mot_cost_iou(const float* a, int n, const float* b, int m, const float* conf
     if (n < 0 || m < 0 || ld < m) return fail(MOT_ERR_INVALID_ARGUMENT, "bad sizes");
     if (n == 0 || m == 0) return MOT_OK;
     if (!a || !b || !out) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
+    if ((((size_t)a) | ((size_t)b)) & 15) return fail(MOT_ERR_INVALID_ARGUMENT, "box arrays must be 16-byte aligned (they are read as float4)");
     if (mode == mot::kCostIouDistanceFused && !conf) return fail(MOT_ERR_INVALID_ARGUMENT, "fuse_score needs det confidences");
     if (mode < 0 || mode > 2) return fail(MOT_ERR_INVALID_ARGUMENT, "unknown mode %d", mode);
     if (int rc = require_device()) return rc;
@@ -727,6 +818,7 @@ int mot_cost_iou_variant(const float* a, int n, const float* b, int m, int kind,
     if (n < 0 || m < 0 || ld < m) return fail(MOT_ERR_INVALID_ARGUMENT, "bad sizes");
     if (kind < mot::kVarHmIou || kind > mot::kVarCentroid)
         return fail(MOT_ERR_INVALID_ARGUMENT, "Invalid association mode: %d (3 hmiou, 4 giou, 5 diou, 6 centroid)", kind);   // iou.hpp:407
+    if ((((size_t)a) | ((size_t)b)) & 15) return fail(MOT_ERR_INVALID_ARGUMENT, "box arrays must be 16-byte aligned (they are read as float4)");
     if (n == 0 || m == 0) return MOT_OK;
     if (!a || !b || !out) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
     if (int rc = require_device()) return rc;
@@ -782,6 +874,7 @@ int mot_cost_gate(float* cost, int ld, const float* recs, int n_tracks, const fl
     if (n_tracks < 0 || n_meas < 0 || ld < n_meas) return fail(MOT_ERR_INVALID_ARGUMENT, "bad sizes");
     if (n_tracks == 0 || n_meas == 0) return MOT_OK;
     if (!cost || !recs || !meas4) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
+    if (((size_t)meas4) & 15) return fail(MOT_ERR_INVALID_ARGUMENT, "meas4 must be 16-byte aligned (read as float4)");
     if (int rc = require_device()) return rc;
     const int blocks = std::max(1, std::min((n_tracks + 7) / 8, sm_count() * 8));
     mot::gate_cost_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(cost, ld, recs, n_tracks, meas4, n_meas, mc_lambda,
@@ -795,6 +888,7 @@ int mot_cost_iou_tlwh(const float* trk_tlwh, const int* tsu, int n, const float*
     if (n < 0 || m < 0 || ld < m) return fail(MOT_ERR_INVALID_ARGUMENT, "bad sizes");
     if (n == 0 || m == 0) return MOT_OK;
     if (!trk_tlwh || !det_tlwh || !out) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
+    if ((((size_t)trk_tlwh) | ((size_t)det_tlwh)) & 15) return fail(MOT_ERR_INVALID_ARGUMENT, "box arrays must be 16-byte aligned (they are read as float4)");
     if (int rc = require_device()) return rc;
     const int col_tiles = (m + mot::kCostTileCols - 1) / mot::kCostTileCols;
     const int row_groups = (n + mot::kCostTileRows - 1) / mot::kCostTileRows;

@@ -20,6 +20,7 @@
 //   warps 0-3 epilogue: tcgen05.ld (32 lanes x 32 columns) -> norm division, 1 - x, max(0, .) -> float4 stores
 // SASS evidence to look for: UTCHMMA (tcgen05.mma), UTMALDG (TMA), LDTM (tcgen05.ld).
 #pragma once
+#include <atomic>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -378,20 +379,20 @@ inline int launch_cosine(const float* t, int n, const float* d, int m, int dim, 
         return 2;   // MOT_ERR_CUDA
     };
     cudaError_t e;
-    // grow-only per-device workspace for the split operands and the norms; calls on one device are stream-ordered
-    // by the caller (like every other entry point, mot_cost_cosine is not re-entrant on the same buffers)
-    struct Workspace { unsigned char* p = nullptr; size_t cap = 0; };
-    static Workspace ws[64];
+    // Workspace for the split operands and the norms: stream-ordered allocation (cudaMallocAsync / cudaFreeAsync on `st`),
+    // so concurrent calls on different streams or host threads never share buffers; after the first call the driver's
+    // pool serves it without touching the OS.
+    struct Workspace { unsigned char* p = nullptr; };
+    Workspace w;
     int dev = 0;
     cudaGetDevice(&dev);
-    Workspace& w = ws[dev & 63];
     const size_t a_bytes = (((size_t)n * kp * 2) + 1023) & ~(size_t)1023, b_bytes = (((size_t)m * kp * 2) + 1023) & ~(size_t)1023;
     const size_t need = a_bytes + b_bytes + sizeof(float) * ((size_t)n + m) + 1024;
-    if (w.cap < need) {
-        if (w.p) { cudaDeviceSynchronize(); cudaFree(w.p); w.p = nullptr; w.cap = 0; }
-        if ((e = cudaMalloc((void**)&w.p, need)) != cudaSuccess) return fail("workspace", e);
-        w.cap = need;
-    }
+    if ((e = cudaMallocAsync((void**)&w.p, need, st)) != cudaSuccess) return fail("workspace", e);
+    struct Release {                                   // freed in stream order once the GEMM has consumed it
+        unsigned char* p; cudaStream_t st;
+        ~Release() { cudaFreeAsync(p, st); }
+    } release{w.p, st};
     __nv_bfloat16* a = (__nv_bfloat16*)w.p;
     __nv_bfloat16* b = (__nv_bfloat16*)(w.p + a_bytes);
     float* tn = (float*)(w.p + a_bytes + b_bytes);
@@ -408,14 +409,14 @@ inline int launch_cosine(const float* t, int n, const float* d, int m, int dim, 
         err = "mot_cost_cosine: cuTensorMapEncodeTiled failed";
         return 2;
     }
-    static bool attr_done[64] = {};
-    bool& attr_set = attr_done[dev & 63];
-    if (!attr_set) {
+    static std::atomic<bool> attr_done[64];              // idempotent: a racing second caller just sets the same values
+    std::atomic<bool>& attr_set = attr_done[dev & 63];
+    if (!attr_set.load(std::memory_order_acquire)) {
         if ((e = cudaFuncSetAttribute(cosine_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(64))) != cudaSuccess ||
             (e = cudaFuncSetAttribute(cosine_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(128))) != cudaSuccess ||
             (e = cudaFuncSetAttribute(cosine_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(256))) != cudaSuccess)
             return fail("smem attribute", e);
-        attr_set = true;
+        attr_set.store(true, std::memory_order_release);
     }
     const int tiles_m = (n + kBlockM - 1) / kBlockM;
     if (block_n == 256) {

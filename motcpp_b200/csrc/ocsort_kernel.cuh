@@ -381,7 +381,7 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
     const float thr = a.p.iou_threshold;
     const int delta_t = a.p.delta_t;
     int n_det = n_det_in;
-    if (n_det > DMAX) { n_det = DMAX; if (tid == 0) atomicOr(&st.hdr[kOHdrError], 2); }
+    if (n_det > min(DMAX, a.ld_dets)) { n_det = min(DMAX, a.ld_dets); if (tid == 0) atomicOr(&st.hdr[kOHdrError], 2); }
 
     // ---- A. detections and the confidence split (:311-320)
     float max_abs_score = 0.0f;

@@ -135,7 +135,7 @@ __device__ __forceinline__ void sort_frame(const SortArgs& a, const SortStream& 
     int n_free = st.hdr[kSHdrFree];
     const int id_base = st.hdr[kSHdrIdCounter];
     int n_det = n_det_in;
-    if (n_det > DMAX) { n_det = DMAX; if (tid == 0) atomicOr(&st.hdr[kSHdrError], 2); }
+    if (n_det > min(DMAX, a.ld_dets)) { n_det = min(DMAX, a.ld_dets); if (tid == 0) atomicOr(&st.hdr[kSHdrError], 2); }
 
     // ---- A. detections
     for (int j = tid; j < n_det; j += nt) {

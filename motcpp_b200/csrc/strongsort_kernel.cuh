@@ -317,7 +317,7 @@ __device__ __forceinline__ void ss_frame(const SsArgs& a, const SsStream& st, Ss
     const int id_base = st.hdr[kHdrIdCounter];
     const int frame_no = st.hdr[kHdrFrame];
     int n_in = n_det_in < 0 ? 0 : n_det_in;
-    if (n_in > DMAX) { n_in = DMAX; if (tid == 0) atomicOr(&st.hdr[kHdrError], (int)kErrTooManyDets); }
+    if (n_in > min(DMAX, a.ld_dets)) { n_in = min(DMAX, a.ld_dets); if (tid == 0) atomicOr(&st.hdr[kHdrError], (int)kErrTooManyDets); }
 
     // ---- A. detections with conf >= min_conf (:849-854): tlwh (:923-932), corners, xyah (:33-40)
     const float min_conf = a.p.min_conf;

@@ -403,6 +403,70 @@ def test_bytetrack_chunked_host_path_equals_single_launch(oracle):
     e1.close(); e4.close()
 
 
+def test_packed_host_path_equals_padded_path(oracle):
+    """mot_engine_update_host_packed: the same rows as the padded call, back to back, plus exclusive offsets - for many
+    frames per call (frame-chunk pipeline), a single frame, and an engine of every box-only tracker kind."""
+    S, T = 7, 41
+    streams = [synth.stress_stream(60 + s, n_frames=T) for s in range(S)]
+    dets = np.stack([st[0] for st in streams], 1)
+    counts = np.stack([st[1] for st in streams], 1).astype(np.int32)
+    ld = dets.shape[2]
+    for kind, kw in ((_lib.TRACKER_BYTETRACK, BT_ARGS), (_lib.TRACKER_SORT, dict(det_thresh=0.3, max_age=3, min_hits=1, iou_threshold=0.3)),
+                     (_lib.TRACKER_OCSORT, dict(det_thresh=0.2, max_age=30, min_hits=3, iou_threshold=0.3, min_conf=0.1, delta_t=3,
+                                                inertia=0.2, use_byte=0, q_xy_scaling=0.01, q_s_scaling=0.0001))):
+        ea = api.Engine(kind, S, 256, ld, **kw)
+        eb = api.Engine(kind, S, 256, ld, **kw)
+        o, n = ea.update(dets, counts, ld_out=256)
+        rows, off, n2 = eb.update_packed(dets[:30], counts[:30], max_rows=256)
+        assert np.array_equal(n2, n[:30]) and off[0] == 0 and off[-1] == n[:30].sum() == len(rows)
+        assert np.array_equal(np.diff(off), n[:30].reshape(-1))
+        for t in range(30):
+            for s_ in range(S):
+                f = t * S + s_
+                assert np.array_equal(rows[off[f]:off[f + 1]], o[t, s_, :n[t, s_]]), (kind, t, s_)
+        for t in range(30, T):                                    # one frame per call
+            rows, off, n2 = eb.update_packed(dets[t:t + 1], counts[t:t + 1], max_rows=256)
+            for s_ in range(S):
+                assert np.array_equal(rows[off[s_]:off[s_ + 1]], o[t, s_, :n[t, s_]]), (kind, t, s_)
+        ea.check(); eb.check()
+        with pytest.raises(_lib.MotError, match="out_rows holds"):
+            eb.update_packed(dets[:4], counts[:4], max_rows=256, out_rows=np.empty((3, 8), np.float32))
+        ea.close(); eb.close()
+
+
+def test_engine_rejects_counts_beyond_the_leading_dimension_and_reports_flags_once():
+    """n_dets > ld_dets used to read the next stream's rows; the Python mirror refuses it, the kernels clamp and
+    flag it.  Error bits are read-and-clear: reported by the check that follows, not by every later one."""
+    dets, counts = synth.stress_stream(4, n_frames=4)
+    eng = api.Engine(_lib.TRACKER_BYTETRACK, 2, 256, 64, **BT_ARGS)
+    d2 = np.stack([dets[:, :32], dets[:, :32]], 1)                 # ld_dets = 32 < the 64 the shape allows
+    with pytest.raises(ValueError, match="n_dets"):
+        eng.update(d2, np.full((4, 2), 40, np.int32), ld_out=64)
+    dd, nn = api.DeviceArray.from_host(d2), api.DeviceArray.from_host(np.full((4, 2), 40, np.int32))
+    do, dn = api.DeviceArray((4, 2, 64, 8), np.float32), api.DeviceArray((4, 2), np.int32)
+    eng.update_device(4, dd.ptr, nn.ptr, 32, do.ptr, dn.ptr, 64)
+    with pytest.raises(RuntimeError, match="too many detections|detections"):
+        eng.check()
+    eng.check()                                                   # cleared by the failing check
+    eng.update(d2, np.full((4, 2), 32, np.int32), ld_out=64)
+    eng.check()
+    eng.close()
+
+
+def test_reid_wrappers_size_themselves_from_the_first_embeddings(oracle):
+    """a default-constructed BotSort / StrongSort must not drop `embs` silently - it adopts their dimension on
+    the first frame (the reference uses whatever it is handed) and matches the oracle that uses them."""
+    d, c, e = synth.stress_stream_reid(3, n_frames=25, dim=32)
+    trk, ref = api.BotSort(track_capacity=256, max_dets=64), oracle.BotSort()
+    for t in range(25):
+        assert np.array_equal(trk.update(d[t, :c[t]], (540, 960), e[t, :c[t]]), ref.update(d[t, :c[t]], e[t, :c[t]])), t
+    with pytest.raises(ValueError, match="emb_dim"):
+        trk.update(d[0, :c[0]], (540, 960), e[0, :c[0], :16])
+    trk, ref = api.StrongSort(track_capacity=256, max_dets=64), oracle.StrongSort(tie_mode=0)
+    for t in range(25):
+        assert np.array_equal(trk.update(d[t, :c[t]], (540, 960), e[t, :c[t]]), ref.update(d[t, :c[t]], e[t, :c[t]])), t
+
+
 def test_bytetrack_reset_keeps_id_counter(oracle):
     # reference: ByteTrack::reset clears lists but STrack::clear_count is empty (bytetrack.hpp:38-40)
     dets, counts = synth.stress_stream(4, n_frames=20)
