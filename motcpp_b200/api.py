@@ -515,7 +515,8 @@ class Engine:
             _raise(e)
         return (out[0], n_out[0]) if squeeze else (out, n_out)
 
-    def update_packed(self, dets: np.ndarray, n_dets: np.ndarray, max_rows: int = 0, out_rows: Optional[np.ndarray] = None):
+    def update_packed(self, dets: np.ndarray, n_dets: np.ndarray, max_rows: int = 0, out_rows: Optional[np.ndarray] = None,
+                      pinned: bool = False):
         """mot_engine_update_host_packed: dets (T,S,ld,6), n_dets (T,S) -> (rows (R,8), offsets (T*S+1,), n_out (T,S)); the rows
         of frame t, stream s are rows[offsets[t*S+s] : offsets[t*S+s+1]] - exactly what update() would have returned."""
         dets = np.ascontiguousarray(dets, np.float32)
@@ -528,9 +529,10 @@ class Engine:
         if n_dets.size and (int(n_dets.max()) > ld or int(n_dets.min()) < 0):
             raise ValueError("n_dets must lie in [0, dets.shape[2]]")
         max_rows = max_rows or (self.cfg.track_capacity or 1536)
+        # pinned result buffers take the zero-copy route (rows stored straight into them by the compaction kernel)
         if out_rows is None:
-            out_rows = np.empty((T * S * max_rows, 8), np.float32)
-        offsets = np.empty(T * S + 1, np.int64)
+            out_rows = (pinned_empty if pinned else np.empty)((T * S * max_rows, 8), np.float32)
+        offsets = (pinned_empty if pinned else np.empty)((T * S + 1,), np.int64)
         n_out = np.empty((T, S), np.int32)
         try:
             check(load().mot_engine_update_host_packed(self._h, T, dets.ctypes.data, n_dets.ctypes.data, ld, max_rows,

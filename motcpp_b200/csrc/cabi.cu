@@ -105,6 +105,8 @@ struct mot_engine {
     int* d_off = nullptr;      size_t off_cap = 0;
     int* h_off = nullptr;      size_t h_off_cap = 0;   // pinned mirror of d_off
     cudaEvent_t ev_tot[kMaxChunks] = {};
+    long long* d_off64 = nullptr; size_t off64_cap = 0;   // zero-copy packed path: global offsets + [base, overflow]
+    long long* d_base = nullptr;
 };
 
 
@@ -390,7 +392,7 @@ int mot_engine_destroy(mot_engine* e) {
         if (e->ev_run[c]) cudaEventDestroy(e->ev_run[c]);
         if (e->ev_tot[c]) cudaEventDestroy(e->ev_tot[c]);
     }
-    cudaFree(e->d_packed); cudaFree(e->d_off);
+    cudaFree(e->d_packed); cudaFree(e->d_off); cudaFree(e->d_off64); cudaFree(e->d_base);
     if (e->h_off) cudaFreeHost(e->h_off);
     cudaFree(e->d_state); cudaFree(e->d_embs); cudaFree(e->d_dets); cudaFree(e->d_ndets); cudaFree(e->d_out); cudaFree(e->d_nout);
     delete e;
@@ -507,6 +509,47 @@ int mot_engine_update_host_packed(mot_engine* e, int T, const float* dets, const
     if (int rc = grow(&e->d_ndets, &e->ndets_cap, TS)) return rc;
     if (int rc = grow(&e->d_out, &e->out_cap, TS * ld_out * 8)) return rc;
     if (int rc = grow(&e->d_nout, &e->nout_cap, TS)) return rc;
+    cudaStream_t s_run = e->streams[0], s_in = e->streams[1], s_out = e->streams[2];
+    const size_t det_fr = (size_t)S * ld_dets * 6, out_fr = (size_t)S * ld_out * 8;
+    auto t_of = [&](int c) { return (int)((long long)T * c / C); };
+    // ---- pinned (device-accessible) result buffers: the compaction kernel stores the valid rows and the offsets straight
+    //      into them over PCIe - no staging copy, no host synchronisation until the end of the call
+    cudaPointerAttributes pa_rows{}, pa_off{};
+    const bool zero_copy = cudaPointerGetAttributes(&pa_rows, out_rows) == cudaSuccess && pa_rows.type == cudaMemoryTypeHost &&
+                           cudaPointerGetAttributes(&pa_off, offsets) == cudaSuccess && pa_off.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (zero_copy) {
+        if (int rc = grow(&e->d_off64, &e->off64_cap, TS + 1)) return rc;
+        if (!e->d_base) MOT_CUDA(cudaMalloc((void**)&e->d_base, 2 * sizeof(long long)));
+        MOT_CUDA(cudaMemsetAsync(e->d_base, 0, 2 * sizeof(long long), s_run));
+        long long* h_off_dev = (long long*)pa_off.devicePointer;
+        float4* h_rows_dev = (float4*)pa_rows.devicePointer;
+        for (int c = 0; c < C; ++c) {
+            const int t0 = t_of(c), nt = t_of(c + 1) - t0, nf = nt * S;
+            MOT_CUDA(cudaMemcpyAsync(e->d_dets + t0 * det_fr, dets + t0 * det_fr, nt * det_fr * sizeof(float), cudaMemcpyHostToDevice, s_in));
+            MOT_CUDA(cudaMemcpyAsync(e->d_ndets + (size_t)t0 * S, n_dets + (size_t)t0 * S, (size_t)nf * sizeof(int), cudaMemcpyHostToDevice, s_in));
+            MOT_CUDA(cudaEventRecord(e->ev_in[c], s_in));
+            MOT_CUDA(cudaStreamWaitEvent(s_run, e->ev_in[c], 0));
+            engine_launch(e, nt, e->d_dets + t0 * det_fr, e->d_ndets + (size_t)t0 * S, ld_dets, nullptr, e->d_out + t0 * out_fr,
+                          e->d_nout + (size_t)t0 * S, ld_out, 0, S, s_run);
+            MOT_CUDA(cudaEventRecord(e->ev_run[c], s_run));
+            // compaction runs on the copy-out stream so that the next chunk's step kernel starts at once
+            MOT_CUDA(cudaStreamWaitEvent(s_out, e->ev_run[c], 0));
+            mot::pack_scan_global_kernel<<<1, 1024, 0, s_out>>>(e->d_nout + (size_t)t0 * S, nf, ld_out, e->d_base, e->d_off64 + (size_t)t0 * S,
+                                                                h_off_dev + (size_t)t0 * S, c == C - 1 ? 1 : 0);
+            mot::pack_rows_to_kernel<<<std::min(nf, sm_count() * 4), 256, 0, s_out>>>((const float4*)(e->d_out + t0 * out_fr), e->d_nout + (size_t)t0 * S,
+                                                                                      e->d_off64 + (size_t)t0 * S, nf, ld_out, h_rows_dev, out_cap_rows,
+                                                                                      (int*)(e->d_base + 1));
+            MOT_CUDA(cudaGetLastError());
+            MOT_CUDA(cudaMemcpyAsync(n_out + (size_t)t0 * S, e->d_nout + (size_t)t0 * S, (size_t)nf * sizeof(int), cudaMemcpyDeviceToHost, s_out));
+        }
+        long long tail[2] = {0, 0};
+        MOT_CUDA(cudaMemcpyAsync(tail, e->d_base, sizeof(tail), cudaMemcpyDeviceToHost, s_out));
+        MOT_CUDA(cudaStreamSynchronize(s_out));
+        if (tail[1] != 0) return fail(MOT_ERR_INVALID_ARGUMENT, "out_rows holds %lld rows, %lld needed", out_cap_rows, tail[0]);
+        return MOT_OK;
+    }
+    // ---- pageable result buffers: rows are compacted into a device staging buffer and copied out chunk by chunk
     if (int rc = grow(&e->d_packed, &e->packed_cap, TS * ld_out * 8)) return rc;
     if (int rc = grow(&e->d_off, &e->off_cap, TS + (size_t)C)) return rc;
     if (e->h_off_cap < TS + (size_t)C) {
@@ -517,10 +560,7 @@ int mot_engine_update_host_packed(mot_engine* e, int T, const float* dets, const
     }
     for (int c = 0; c < C; ++c)
         if (!e->ev_tot[c]) MOT_CUDA(cudaEventCreateWithFlags(&e->ev_tot[c], cudaEventDisableTiming));
-    cudaStream_t s_run = e->streams[0], s_in = e->streams[1], s_out = e->streams[2];
-    const size_t det_fr = (size_t)S * ld_dets * 6, out_fr = (size_t)S * ld_out * 8;
     long long base = 0;                                    // rows already handed to the caller
-    auto t_of = [&](int c) { return (int)((long long)T * c / C); };
     auto enqueue = [&](int c) -> int {
         const int t0 = t_of(c), nt = t_of(c + 1) - t0, nf = nt * S;
         MOT_CUDA(cudaMemcpyAsync(e->d_dets + t0 * det_fr, dets + t0 * det_fr, nt * det_fr * sizeof(float), cudaMemcpyHostToDevice, s_in));

@@ -417,7 +417,10 @@ def test_packed_host_path_equals_padded_path(oracle):
         ea = api.Engine(kind, S, 256, ld, **kw)
         eb = api.Engine(kind, S, 256, ld, **kw)
         o, n = ea.update(dets, counts, ld_out=256)
-        rows, off, n2 = eb.update_packed(dets[:30], counts[:30], max_rows=256)
+        ec = api.Engine(kind, S, 256, ld, **kw)
+        rows_p, off_p, n_p = ec.update_packed(dets[:30], counts[:30], max_rows=256, pinned=True)     # zero-copy route
+        rows, off, n2 = eb.update_packed(dets[:30], counts[:30], max_rows=256)                         # staged route
+        assert np.array_equal(rows_p, rows) and np.array_equal(off_p, off) and np.array_equal(n_p, n2)
         assert np.array_equal(n2, n[:30]) and off[0] == 0 and off[-1] == n[:30].sum() == len(rows)
         assert np.array_equal(np.diff(off), n[:30].reshape(-1))
         for t in range(30):
@@ -428,10 +431,12 @@ def test_packed_host_path_equals_padded_path(oracle):
             rows, off, n2 = eb.update_packed(dets[t:t + 1], counts[t:t + 1], max_rows=256)
             for s_ in range(S):
                 assert np.array_equal(rows[off[s_]:off[s_ + 1]], o[t, s_, :n[t, s_]]), (kind, t, s_)
-        ea.check(); eb.check()
-        with pytest.raises(_lib.MotError, match="out_rows holds"):
+        ea.check(); eb.check(); ec.check()
+        with pytest.raises(ValueError, match="out_rows holds"):
             eb.update_packed(dets[:4], counts[:4], max_rows=256, out_rows=np.empty((3, 8), np.float32))
-        ea.close(); eb.close()
+        with pytest.raises(ValueError, match="out_rows holds"):
+            ec.update_packed(dets[:4], counts[:4], max_rows=256, out_rows=api.pinned_empty((3, 8), np.float32), pinned=True)
+        ea.close(); eb.close(); ec.close()
 
 
 def test_engine_rejects_counts_beyond_the_leading_dimension_and_reports_flags_once():
