@@ -64,6 +64,7 @@ SYMBOLS = {
     "mot_engine_reset": (_I, [_VP]),
     "mot_engine_update_host": (_I, [_VP, _I, _VP, _VP, _I, _VP, _VP, _I]),
     "mot_engine_update_host_packed": (_I, [_VP, _I, _VP, _VP, _I, _I, _VP, C.c_longlong, _VP, _VP]),
+    "mot_engine_profile": (_I, [_VP, _I, _VP]),
     "mot_engine_update_device": (_I, [_VP, _I, _VP, _VP, _I, _VP, _VP, _I, _VP]),
     "mot_engine_update_host_embs": (_I, [_VP, _I, _VP, _VP, _I, _VP, _VP, _VP, _I]),
     "mot_engine_update_device_embs": (_I, [_VP, _I, _VP, _VP, _I, _VP, _VP, _VP, _I, _VP]),

@@ -529,7 +529,6 @@ class Engine:
         if n_dets.size and (int(n_dets.max()) > ld or int(n_dets.min()) < 0):
             raise ValueError("n_dets must lie in [0, dets.shape[2]]")
         max_rows = max_rows or (self.cfg.track_capacity or 1536)
-        # pinned result buffers take the zero-copy route (rows stored straight into them by the compaction kernel)
         if out_rows is None:
             out_rows = (pinned_empty if pinned else np.empty)((T * S * max_rows, 8), np.float32)
         offsets = (pinned_empty if pinned else np.empty)((T * S + 1,), np.int64)

@@ -99,6 +99,7 @@ struct BtArgs {
     int T, S, ld_dets, ld_out, e_cap;
     int s_begin, s_end;       // streams handled by this launch
     BtParams p;
+    unsigned long long* prof; // optional [16] per-phase cycle counters (mot_engine_profile), nullptr = off
 };
 
 // ---- shared-memory plan
@@ -216,6 +217,8 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
     constexpr int cap = CAP, d_max = DMAX;
     const int lap_m_max = d_max;
     __syncthreads();
+    PhaseClock clk;
+    clk.start(a.prof);
     const int frame = st.hdr[kHdrFrame] + 1;                  // frame_count_ == frame_id_ (:181-182)
     const int n_active = st.hdr[kHdrActive], n_lost = st.hdr[kHdrLost];
     int n_free = st.hdr[kHdrFree];
@@ -237,6 +240,7 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
                                    [&](int j) { const float c = sm.det_conf[j]; return c > t_lo && c < t_hi; },
                                    [&](int j, int pos) { sm.lo[pos] = (unsigned short)j; });
 
+    clk.tick(0);
     // ---- B. pool = tracked (activated) ++ lost ; unconfirmed kept aside
     const int n_trk = block_compact(n_active, 0, sm.bs,
                                     [&](int k) { return (st.sflag[st.active[k]] & kFlagActivated) != 0; },
@@ -248,6 +252,7 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
     const int n1 = n_trk + n_lost;
     __syncthreads();
 
+    clk.tick(1);
     // ---- C. predicted box of every pool row (the prediction itself is redone in registers for the
     //         rows that get matched: only the mean is needed to build costs)
     for (int r = tid; r < n1; r += nt) {
@@ -260,10 +265,14 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
     }
     __syncthreads();
 
+    clk.tick(2);
     // ---- D. first association
     {
         IouCost cost{sm.row_box, sm.det_box, sm.det_conf, sm.hi, true, a.p.match_thresh < 1.0f};
+        sm.lap.clk = a.prof ? &clk : nullptr;
+        sm.lap.clk_base = 3;
         block_lap(sm.lap, n1, n_hi, cap, lap_m_max, a.p.match_thresh, cost);
+        sm.lap.clk = nullptr;
     }
     // harvest what later phases need before the LAP workspace is reused
     const int n_m1 = block_compact(n1, 0, sm.bs, [&](int r) { return sm.lap.row2col[r] >= 0; },
@@ -277,11 +286,13 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
                                  [&](int r, int pos) { sm.list_a[pos] = sm.pool[r]; });
     __syncthreads();
 
+    clk.tick(7);
     // ---- E. Kalman predict + update for the matches of the first association
     bt_kalman_pairs(st, dets, n_m1, 0, frame, [&](int k) { return (int)sm.pool[sm.sel[k]]; },
                     [&](int k) { return (int)sm.list_c[k]; });
     __syncthreads();
 
+    clk.tick(8);
     // ---- F. second association: r_tracked (slots in list_a) x low-confidence detections
     int n_lost_new = 0;
     if (n2 > 0 && n_lo > 0) {
@@ -306,6 +317,7 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
     __syncthreads();
     // list_c[0 .. n_lost_new) now holds the slots that became Lost this frame; keep it until phase J.
 
+    clk.tick(9);
     // ---- G. unconfirmed tracks x leftover high detections
     int n_final = n_udet;
     const unsigned short* final_list = sm.udet;
@@ -329,6 +341,7 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
     }
     __syncthreads();
 
+    clk.tick(10);
     // ---- H. new tracks from the remaining high detections, IDs in list order (:546-554)
     const float det_thresh = a.p.det_thresh;
     const int n_new_want = block_compact(n_final, 0, sm.bs, [&](int k) { return sm.det_conf[final_list[k]] >= det_thresh; },
@@ -360,6 +373,7 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
     }
     __syncthreads();
 
+    clk.tick(11);
     // ---- I. expire lost tracks (:557-562); re-found ones are Tracked by now and skipped
     for (int k = tid; k < n_lost; k += nt) {
         const int slot = st.lost[k];
@@ -388,6 +402,7 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
     n_free = block_compact(n_lost, n_free, sm.bs, [&](int k) { return (st.sflag[st.lost[k]] & 0x0f) == kStRemoved; },
                            [&](int k, int pos) { st.freel[pos] = st.lost[k]; });
 
+    clk.tick(12);
     // ---- K. remove_duplicate_stracks(active', lost') (:659-706)
     for (int i = tid; i < na; i += nt) sm.dup_a[i] = 0;
     for (int j = tid; j < nl; j += nt) sm.dup_b[j] = 0;
@@ -460,6 +475,7 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
                            [&](int j, int pos) { st.freel[pos] = sm.list_b[j]; });
     __syncthreads();
 
+    clk.tick(13);
     // ---- L. output rows for activated tracks, in list order (:589-620)
     const int n_rows = block_compact(na2, 0, sm.bs, [&](int i) { return (st.sflag[st.active[i]] & kFlagActivated) != 0; },
                                      [&](int i, int pos) {
@@ -484,6 +500,7 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
         st.hdr[kHdrN3] = n_unc; st.hdr[kHdrM3] = n_udet; st.hdr[kHdrDupA] = na; st.hdr[kHdrDupB] = nl;
     }
     __syncthreads();
+    clk.tick(14);
 }
 
 // One CTA per stream; each CTA walks its streams' T frames in order (state stays hot in L1/L2).

@@ -49,57 +49,4 @@ static __global__ void __launch_bounds__(256) pack_rows_kernel(const float4* __r
     }
 }
 
-// Zero-copy variant for a PINNED (device-accessible) result buffer: offsets are global over the whole call (a running base
-// kept in device memory carries from chunk to chunk), written as int64 straight into the caller's array; the rows kernel
-// below then stores the valid rows over PCIe into the caller's buffer.  No host synchronisation anywhere.
-static __global__ void __launch_bounds__(1024) pack_scan_global_kernel(const int* __restrict__ n_out, int n, int ld_out,
-                                                                       long long* __restrict__ base_io, long long* __restrict__ off_dev,
-                                                                       long long* __restrict__ off_host, int write_total) {
-    __shared__ int warp_sum[32];
-    __shared__ int carry;
-    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long base = *base_io;
-    if (tid == 0) carry = 0;
-    __syncthreads();
-    for (int b0 = 0; b0 < n; b0 += 1024) {
-        const int f = b0 + tid;
-        const int v = f < n ? min(n_out[f], ld_out) : 0;
-        int incl = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(kFullMask, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) warp_sum[warp] = incl;
-        __syncthreads();
-        const int ws = warp_sum[lane];
-        const int before = __reduce_add_sync(kFullMask, lane < warp ? ws : 0);
-        const int total = __reduce_add_sync(kFullMask, ws);
-        const int c = carry;
-        if (f < n) { const long long o = base + c + before + incl - v; off_dev[f] = o; off_host[f] = o; }
-        __syncthreads();
-        if (tid == 0) carry = c + total;
-        __syncthreads();
-    }
-    if (tid == 0) {
-        *base_io = base + carry;
-        if (write_total) off_host[n] = base + carry;
-    }
-}
-
-// rows of frame block f -> dst_rows + off[f] * 8 (global offsets); dst may be mapped pinned host memory (full 16-byte stores,
-// consecutive threads write consecutive addresses).  cap_rows guards the caller's capacity; overflow is flagged.
-static __global__ void __launch_bounds__(256) pack_rows_to_kernel(const float4* __restrict__ padded, const int* __restrict__ n_out,
-                                                                  const long long* __restrict__ off, int n, int ld_out,
-                                                                  float4* __restrict__ dst, long long cap_rows, int* __restrict__ overflow) {
-    for (int f = (int)blockIdx.x; f < n; f += (int)gridDim.x) {
-        const int rows = min(n_out[f], ld_out);
-        const long long first = off[f];
-        if (first + rows > cap_rows) { if (threadIdx.x == 0) *overflow = 1; continue; }
-        const float4* src = padded + (size_t)f * ld_out * 2;
-        float4* d = dst + (size_t)first * 2;
-        for (int k = (int)threadIdx.x; k < 2 * rows; k += (int)blockDim.x) d[k] = src[k];
-    }
-}
-
 }  // namespace mot

@@ -45,6 +45,8 @@ struct LapWorkspace {
     int* g_way;                // [m_max + n_max]
     int* g_prow;               // [m_max + n_max]
     unsigned char* g_flags;    // [m_max + 2 * n_max] used[] then in_tree[]
+    PhaseClock* clk;           // optional cycle accounting (nullptr = off): slots clk_base .. clk_base + 3
+    int clk_base;
 };
 
 __device__ __forceinline__ double lap_inf() { return 1.0e300; }
@@ -305,6 +307,7 @@ __device__ void block_lap_solve(LapWorkspace& ws, int n, int m, int n_max, int m
         }
     }
 
+    if (ws.clk) ws.clk->tick(ws.clk_base + 1);
     // ---- 3. group rows / columns by component: counts (packed rows | cols << 16) -> offsets -> fill
     int* off = ws.scratch_a;       // [n + 1] packed exclusive offsets per label
     int* cur = ws.scratch_b;       // [n] packed fill cursors per label
@@ -325,6 +328,7 @@ __device__ void block_lap_solve(LapWorkspace& ws, int n, int m, int n_max, int m
     }
     __syncthreads();
 
+    if (ws.clk) ws.clk->tick(ws.clk_base + 2);
     // ---- 4. solve every component with the cheapest exact method that fits it
     //   trivial (one row or one column): a thread takes the best candidate directly
     //   r + c <= 8 : an 8-lane team (four components per warp at a time)
@@ -392,6 +396,7 @@ __device__ void block_lap_solve(LapWorkspace& ws, int n, int m, int n_max, int m
                                 rows, r, pr, cols, c, pc, thresh, cost, ws.row2col, ws.col2row);
     }
     __syncthreads();
+    if (ws.clk) ws.clk->tick(ws.clk_base + 3);
 }
 
 template <class Cost>
@@ -479,6 +484,7 @@ __device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, 
             for (int i = tid; i < n; i += nt) scan_row(i);
         }
     }
+    if (ws.clk) { __syncthreads(); ws.clk->tick(ws.clk_base); }
     block_lap_solve(ws, n, m, n_max, m_max, thresh, cost);
 }
 
@@ -530,6 +536,8 @@ __device__ __forceinline__ unsigned char* lap_carve(unsigned char* p, int n_max,
     ws.bs = (BlockScratch*)p;          p += lap_align16(sizeof(BlockScratch));
     grid_carve(p, n_max > m_max ? n_max : m_max, ws.grid);  p += lap_align16(grid_smem_bytes(n_max > m_max ? n_max : m_max));
     ws.e_cap = e_cap;
+    ws.clk = nullptr;
+    ws.clk_base = 0;
     ws.pairs = ws.scratch_b;
     ws.p_cap = (int)(((unsigned char*)ws.row2col - (unsigned char*)ws.scratch_b) / sizeof(int));
     return p;

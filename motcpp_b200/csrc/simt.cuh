@@ -31,6 +31,30 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 #endif
 }
 
+// Optional per-phase cycle accounting (diagnostics: mot_engine_profile).  p == nullptr -> every tick is one predictable
+// branch.  Thread 0's clock after a barrier is the block's clock.
+struct PhaseClock {
+    unsigned long long* p;
+    long long t;
+    __device__ __forceinline__ void start(unsigned long long* prof) {
+        p = prof;
+#if !defined(MOT_CPUSIM)
+        if (p && threadIdx.x == 0) t = clock64();
+#endif
+    }
+    __device__ __forceinline__ void tick(int k) {
+#if !defined(MOT_CPUSIM)
+        if (p && threadIdx.x == 0) {
+            const long long n = clock64();
+            atomicAdd(&p[k], (unsigned long long)(n - t));
+            t = n;
+        }
+#else
+        (void)k;
+#endif
+    }
+};
+
 __device__ __forceinline__ int lane_id() { return (int)(threadIdx.x & 31u); }
 __device__ __forceinline__ int warp_id() { return (int)(threadIdx.x >> 5); }
 

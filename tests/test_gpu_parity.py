@@ -418,8 +418,8 @@ def test_packed_host_path_equals_padded_path(oracle):
         eb = api.Engine(kind, S, 256, ld, **kw)
         o, n = ea.update(dets, counts, ld_out=256)
         ec = api.Engine(kind, S, 256, ld, **kw)
-        rows_p, off_p, n_p = ec.update_packed(dets[:30], counts[:30], max_rows=256, pinned=True)     # zero-copy route
-        rows, off, n2 = eb.update_packed(dets[:30], counts[:30], max_rows=256)                         # staged route
+        rows_p, off_p, n_p = ec.update_packed(dets[:30], counts[:30], max_rows=256, pinned=True)     # pinned result buffers
+        rows, off, n2 = eb.update_packed(dets[:30], counts[:30], max_rows=256)                         # pageable result buffers
         assert np.array_equal(rows_p, rows) and np.array_equal(off_p, off) and np.array_equal(n_p, n2)
         assert np.array_equal(n2, n[:30]) and off[0] == 0 and off[-1] == n[:30].sum() == len(rows)
         assert np.array_equal(np.diff(off), n[:30].reshape(-1))
