@@ -167,36 +167,44 @@ __device__ __forceinline__ void bt_det_xyah(const float* det_row, float (&z)[4])
     z[0] = q.x; z[1] = q.y; z[2] = q.z; z[3] = q.w;
 }
 
-// Kalman work for a list of (track slot, detection) pairs, one 8-lane group per pair.
+// Kalman work for a list of (track slot, detection) pairs: one thread per (pair, coordinate) - four consecutive lanes
+// advance the four independent (position, velocity) filters of a track (kf_device.cuh, "independent-coordinate form").
 //   mode 0: predict (zeroing vh unless Tracked) then update   - 1st association
 //   mode 1: predict then update                               - 2nd association (always Tracked)
 //   mode 2: update only                                       - unconfirmed association
-// slot_of(k) / det_of(k) give the k-th pair; the group's lane 0 also refreshes the track's metadata
+// slot_of(k) / det_of(k) give the k-th pair; the quad's lane 0 also refreshes the track's metadata
 // (STrack::update / re_activate, bytetrack.cpp:51-85).
 template <class SlotOf, class DetOf>
 __device__ __forceinline__ void bt_kalman_pairs(const BtStream& st, const float* dets, int n_pairs, int mode,
                                                 int frame, SlotOf slot_of, DetOf det_of) {
-    const int lane = lane_id(), g = lane & 7, base = lane & ~7;
-    const int groups = (int)(blockDim.x >> 3);
-    const int gid = (int)(threadIdx.x >> 3);
-    const int rounds = (n_pairs + groups - 1) / groups;
+    const int lane = lane_id(), c = lane & 3, qbase = lane & ~3;
+    const int quads = (int)(blockDim.x >> 2);
+    const int qid = (int)(threadIdx.x >> 2);
+    const int rounds = (n_pairs + quads - 1) / quads;
     for (int it = 0; it < rounds; ++it) {
-        const int k = it * groups + gid;
+        const int k = it * quads + qid;
         const bool live = k < n_pairs;
         const int slot = live ? slot_of(k) : 0;
         const int det = live ? det_of(k) : 0;
         float* rec = st.recs + (size_t)slot * kRecFloats;
-        KfRow s;
-        if (live) kf_load_row(rec, g, s);
-        else { s.m = 1.0f; for (int j = 0; j < 8; ++j) s.p[j] = (j == g) ? 1.0f : 0.0f; }
+        KfBlock s;
+        if (live) kfb_load(rec, c, s);
+        else { s.mc = 1.0f; s.mv = 0.0f; s.pcc = 1.0f; s.pcv = 0.0f; s.pvc = 0.0f; s.pvv = 1.0f; }
         const int state = live ? (int)(st.sflag[slot] & 0x0f) : kStTracked;
         float z[4] = {0.0f, 0.0f, 0.0f, 1.0f};
         if (live) bt_det_xyah(dets + (size_t)det * 6, z);
-        if (mode != 2) kf_xyah_predict(s, g, base, mode == 0 && state != kStTracked);
-        const bool ok = kf_xyah_update(s, g, base, z, 0.0f);
+        const float zc = (c == 0) ? z[0] : (c == 1) ? z[1] : (c == 2) ? z[2] : z[3];
+        if (mode != 2) {
+            const float h0 = __shfl_sync(kFullMask, s.mc, qbase + 3);            // mean(3) before the motion step
+            kfb_xyah_predict(s, c, h0, mode == 0 && state != kStTracked);
+        }
+        const float h1 = __shfl_sync(kFullMask, s.mc, qbase + 3);                // mean(3) of the predicted state
+        const bool okc = kfb_xyah_update(s, c, h1, zc, 0.0f);
+        const unsigned bad = __ballot_sync(kFullMask, !okc);
+        const bool ok = ((bad >> qbase) & 0xfu) == 0;                             // all four pivots positive
         if (live) {
-            if (ok) kf_store_row(rec, g, s);
-            if (g == 0) {
+            if (ok) kfb_store(rec, c, s);
+            if (c == 0) {
                 if (!ok) atomicOr(&st.hdr[kHdrError], (int)kErrKalman);
                 if (state == kStTracked) st.tracklet_len[slot] += 1;     // STrack::update
                 else st.tracklet_len[slot] = 0;                          // STrack::re_activate
@@ -429,8 +437,9 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
                 const int i = base + tid;
                 if (tid == 0) sm.lap.ctl[7] = 0;
                 __syncthreads();
+                // a duplicate needs 1 - IoU < 0.15: only boxes whose corner lies within 16 % of a box size can qualify
                 if (i < na)
-                    grid_query(sm.lap.grid, sm.row_box[i], [&](int j) { return sm.row_box[na + j]; }, [&](int j, float4) {
+                    grid_query_iou_above(sm.lap.grid, sm.row_box[i], 0.84f, [&](int j) { return sm.row_box[na + j]; }, [&](int j, float4) {
                         const int q = atomicAdd(&sm.lap.ctl[7], 1);
                         if (q < sm.lap.p_cap) sm.lap.pairs[q] = (i << 16) | j;
                     });

@@ -370,8 +370,13 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
                               : (is_bot ? mot::bot_prepare(e->shape, e->smem_bytes) : mot::bt_prepare(e->shape, e->smem_bytes))));
     e->n_chunks = cfg->n_chunks > 0 ? std::min(cfg->n_chunks, kMaxChunks) : (cfg->n_streams >= 128 ? 8 : (cfg->n_streams >= 32 ? 4 : 1));
     e->n_chunks = std::min(e->n_chunks, cfg->n_streams);
+    int prio_lo = 0, prio_hi = 0;
+    MOT_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     for (int c = 0; c < kMaxChunks; ++c) {
-        MOT_CUDA(cudaStreamCreateWithFlags(&e->streams[c], cudaStreamNonBlocking));
+        // streams[2] (copy-out + row compaction of the host paths) outranks the compute stream: its small kernels must not
+        // queue behind the next chunk's step kernel, which fills every SM
+        if (c == 2) MOT_CUDA(cudaStreamCreateWithPriority(&e->streams[c], cudaStreamNonBlocking, prio_hi));
+        else MOT_CUDA(cudaStreamCreateWithFlags(&e->streams[c], cudaStreamNonBlocking));
         MOT_CUDA(cudaEventCreateWithFlags(&e->ev_in[c], cudaEventDisableTiming));
         MOT_CUDA(cudaEventCreateWithFlags(&e->ev_run[c], cudaEventDisableTiming));
     }
@@ -509,7 +514,7 @@ int mot_engine_update_host_packed(mot_engine* e, int T, const float* dets, const
     if (int rc = grow(&e->d_ndets, &e->ndets_cap, TS)) return rc;
     if (int rc = grow(&e->d_out, &e->out_cap, TS * ld_out * 8)) return rc;
     if (int rc = grow(&e->d_nout, &e->nout_cap, TS)) return rc;
-    cudaStream_t s_run = e->streams[0], s_in = e->streams[1], s_out = e->streams[2];
+    cudaStream_t s_run = e->streams[0], s_in = e->streams[1], s_out = e->streams[2], s_rows = e->streams[3];
     const size_t det_fr = (size_t)S * ld_dets * 6, out_fr = (size_t)S * ld_out * 8;
     auto t_of = [&](int c) { return (int)((long long)T * c / C); };
     // Rows are compacted into a device staging buffer and leave through the copy engine, chunk by chunk.  (Storing them
@@ -554,8 +559,8 @@ int mot_engine_update_host_packed(mot_engine* e, int T, const float* dets, const
         const int* off = e->h_off + (size_t)t0 * S + c;
         const long long rows = off[nf];
         if (base + rows > out_cap_rows) return fail(MOT_ERR_INVALID_ARGUMENT, "out_rows holds %lld rows, %lld needed so far", out_cap_rows, base + rows);
-        if (rows > 0)
-            MOT_CUDA(cudaMemcpyAsync(out_rows + base * 8, e->d_packed + t0 * out_fr, (size_t)rows * 8 * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+        if (rows > 0)     // own stream: s_out already holds the compaction of the next two chunks (the event implies pack(c) is done)
+            MOT_CUDA(cudaMemcpyAsync(out_rows + base * 8, e->d_packed + t0 * out_fr, (size_t)rows * 8 * sizeof(float), cudaMemcpyDeviceToHost, s_rows));
         for (int f = 0; f < nf; ++f) offsets[(size_t)t0 * S + f] = base + off[f];
         base += rows;
         return MOT_OK;
@@ -565,10 +570,11 @@ int mot_engine_update_host_packed(mot_engine* e, int T, const float* dets, const
     if (C > 1) if (int rc = enqueue(1)) return rc;
     for (int c = 0; c < C; ++c) {
         if (c + 2 < C) if (int rc = enqueue(c + 2)) return rc;
-        if (int rc = drain(c)) { cudaStreamSynchronize(s_run); cudaStreamSynchronize(s_out); return rc; }
+        if (int rc = drain(c)) { cudaStreamSynchronize(s_run); cudaStreamSynchronize(s_out); cudaStreamSynchronize(s_rows); return rc; }
     }
     offsets[TS] = base;
     MOT_CUDA(cudaStreamSynchronize(s_out));
+    MOT_CUDA(cudaStreamSynchronize(s_rows));
     return MOT_OK;
 }
 

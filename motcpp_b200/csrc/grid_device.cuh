@@ -124,4 +124,28 @@ __device__ __forceinline__ void grid_query(const BoxGrid& g, float4 a, BoxOf box
     }
 }
 
+// Like grid_query, for callers that only care about pairs with IoU > t (0 < t < 1): such a column box b has its corner
+// within  a.x1 - (1 - t) max_w < b.x1 < a.x1 + (1 - t) w_a  (and likewise in y):
+//   IoU > t  =>  intersection > t * area_a and > t * area_b  =>  intersection width > t * w_a and > t * w_b;
+//   b.x1 >= a.x1: width <= a.x2 - b.x1, so b.x1 - a.x1 < (1 - t) w_a;   b.x1 < a.x1: width <= w_b - (a.x1 - b.x1), so
+//   a.x1 - b.x1 < (1 - t) w_b <= (1 - t) max_w.
+// The window is widened by a relative 1e-5; pairs outside it provably have IoU <= t, pairs inside are still judged
+// exactly by the caller, so results are identical to the dense evaluation.
+template <class BoxOf, class Visit>
+__device__ __forceinline__ void grid_query_iou_above(const BoxGrid& g, float4 a, float t, BoxOf box_of, Visit visit) {
+    const float u = 1.0f - t;
+    const float wa = a.z - a.x, ha = a.w - a.y;
+    const float lx = u * g.max_w + (fabsf(a.x) + g.max_w) * 1e-5f, ly = u * g.max_h + (fabsf(a.y) + g.max_h) * 1e-5f;
+    const float rx = u * wa + (fabsf(a.x) + fabsf(wa)) * 1e-5f, ry = u * ha + (fabsf(a.y) + fabsf(ha)) * 1e-5f;
+    const int cx0 = g.cx(a.x - lx), cx1 = g.cx(a.x + rx), cy0 = g.cy(a.y - ly), cy1 = g.cy(a.y + ry);
+    for (int yy = cy0; yy <= cy1; ++yy) {
+        const int e1 = g.cell[yy * kGridX + cx1 + 1];
+        for (int e = g.cell[yy * kGridX + cx0]; e < e1; ++e) {
+            const int j = g.items[e];
+            const float4 b = box_of(j);
+            if ((fminf(a.z, b.z) > fmaxf(a.x, b.x)) && (fminf(a.w, b.w) > fmaxf(a.y, b.y))) visit(j, b);
+        }
+    }
+}
+
 }  // namespace mot

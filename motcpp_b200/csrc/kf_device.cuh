@@ -221,6 +221,59 @@ __device__ __forceinline__ bool kf_xyah_update(KfRow& s, int g, int base, const 
     return true;
 }
 
+// ------------------------------------------------------------------ independent-coordinate form (fused trackers)
+// F and H never mix x, y, a, h, and initiate() starts from a diagonal covariance, so every state the fused trackers can
+// reach has P(i, j) = 0 unless i = j (mod 4): four independent (position, velocity) filters.  The dense expressions of
+// kf_xyah_predict / kf_xyah_update applied to such a state only ever add, subtract or multiply EXACT zeros outside
+// the four 2 x 2 blocks, so evaluating just the blocks - same operations, same order - gives the same values for the
+// in-block entries and leaves the other 48 entries of the record at zero.  One thread per (track, coordinate), no
+// shuffles in the arithmetic: the dependent chain is ~40 operations instead of ~60 shuffles + the dense update.
+//   s.mc = mean[c], s.mv = mean[c+4]; pcc = P[c][c], pcv = P[c][c+4], pvc = P[c+4][c], pvv = P[c+4][c+4]
+struct KfBlock {
+    float mc, mv, pcc, pcv, pvc, pvv;
+};
+__device__ __forceinline__ void kfb_load(const float* __restrict__ rec, int c, KfBlock& s) {
+    s.mc = rec[c]; s.mv = rec[c + 4];
+    s.pcc = rec[8 + 9 * c]; s.pcv = rec[8 + 9 * c + 4];
+    s.pvc = rec[8 + 8 * (c + 4) + c]; s.pvv = rec[8 + 9 * (c + 4)];
+}
+__device__ __forceinline__ void kfb_store(float* __restrict__ rec, int c, const KfBlock& s) {
+    rec[c] = s.mc; rec[c + 4] = s.mv;
+    rec[8 + 9 * c] = s.pcc; rec[8 + 9 * c + 4] = s.pcv;
+    rec[8 + 8 * (c + 4) + c] = s.pvc; rec[8 + 9 * (c + 4)] = s.pvv;
+}
+// kf_xyah_predict restricted to block c.  h = mean(3) BEFORE the motion step; zero_vh as in kf_xyah_predict.
+__device__ __forceinline__ void kfb_xyah_predict(KfBlock& s, int c, float h, bool zero_vh) {
+    if (zero_vh && c == 3) s.mv = 0.0f;
+    const float sp = xmul(kf_wpos(), h), sv = xmul(kf_wvel(), h);
+    const float qp = (c == 2) ? 1e-2f : sp, qv = (c == 2) ? 1e-5f : sv;
+    s.mc = xadd(s.mc, s.mv);
+    const float tcc = xadd(s.pcc, s.pvc), tcv = xadd(s.pcv, s.pvv);      // row c of F P
+    const float ncc = xadd(xadd(tcc, tcv), xmul(qp, qp));
+    const float nvc = xadd(s.pvc, s.pvv);
+    const float nvv = xadd(s.pvv, xmul(qv, qv));
+    s.pcc = ncc; s.pcv = tcv; s.pvc = nvc; s.pvv = nvv;
+}
+// kf_xyah_update restricted to block c.  h = mean(3) of the CURRENT (predicted) state, z = measurement of coordinate c.
+// Returns false when this coordinate's pivot is not positive (the caller combines the four).
+__device__ __forceinline__ bool kfb_xyah_update(KfBlock& s, int c, float h, float z, float conf) {
+    const float one_minus = xsub(1.0f, conf);
+    const float r = (c == 2) ? xmul(1e-1f, one_minus) : xmul(xmul(kf_wpos(), h), one_minus);
+    const float scc = xadd(s.pcc, xmul(r, r));
+    if (!(scc > 0.0f)) return false;
+    const float innov = xsub(z, s.mc);
+    const float l = xsqrt(scc);
+    const float kc = xdiv_pos(xdiv_pos(s.pcc, l), l), kv = xdiv_pos(xdiv_pos(s.pvc, l), l);
+    s.mc = xadd(s.mc, xmul(kc, innov));
+    s.mv = xadd(s.mv, xmul(kv, innov));
+    const float ksc = xmul(kc, scc), ksv = xmul(kv, scc);
+    s.pcc = xsub(s.pcc, xmul(ksc, kc));
+    s.pcv = xsub(s.pcv, xmul(ksc, kv));
+    s.pvc = xsub(s.pvc, xmul(ksv, kc));
+    s.pvv = xsub(s.pvv, xmul(ksv, kv));
+    return true;
+}
+
 // KalmanFilterXYAH::initiate for row g (kalman_filter.cpp:29-42, xyah_kf.cpp:14-29)
 __device__ __forceinline__ void kf_xyah_initiate(KfRow& s, int g, const float (&z)[4]) {
     const float h = z[3];

@@ -278,6 +278,10 @@ __device__ void block_lap_solve(LapWorkspace& ws, int n, int m, int n_max, int m
     __syncthreads();
     const int n_edges = min(ws.ctl[0], ws.e_cap);
     const bool overflow = ws.ctl[1] != 0;
+    if (n_edges == 0 && !overflow) {                 // no candidate at all: everything stays unmatched (results are already -1)
+        if (ws.clk) { ws.clk->tick(ws.clk_base + 1); ws.clk->tick(ws.clk_base + 2); ws.clk->tick(ws.clk_base + 3); }
+        return;
+    }
 
     // ---- 2. connected components by min-label propagation
     if (overflow) {
