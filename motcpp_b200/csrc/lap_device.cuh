@@ -322,13 +322,34 @@ __device__ void block_lap_solve(LapWorkspace& ws, int n, int m, int n_max, int m
     for (int j = tid; j < m; j += nt) { const int l = ws.col_label[j]; if (l != kLapNone) atomicAdd(&off[l], 1 << 16); }
     __syncthreads();
     block_exclusive_scan(off, n, ws.bs, true);
-    for (int i = tid; i < n; i += nt) {
-        const int l = ws.row_label[i];
-        if (l != kLapNone) { const int k = atomicAdd(&cur[l], 1) & 0xffff; ws.comp_rows[(off[l] & 0xffff) + k] = (unsigned short)i; }
-    }
-    for (int j = tid; j < m; j += nt) {
-        const int l = ws.col_label[j];
-        if (l != kLapNone) { const int k = atomicAdd(&cur[l], 1 << 16) >> 16; ws.comp_cols[(off[l] >> 16) + k] = (unsigned short)j; }
+    // ORDERED fill: warp 0 walks the rows, warp 1 the columns, 32 at a time in ascending order; lanes with the same label
+    // find each other with match.any, so every component's rows / columns come out sorted ascending (what the solvers'
+    // lowest-index tie-breaking needs) without a sort per component.  The two cursors of a label are separate halfwords.
+    {
+        unsigned short* cur16 = reinterpret_cast<unsigned short*>(cur);
+        const int warp = tid >> 5, nwarps = nt >> 5;
+        for (int pass = warp; pass < 2; pass += nwarps) {   // (a one-warp block does both passes)
+            const bool rows_pass = (pass == 0);
+            const int cnt = rows_pass ? n : m;
+            const int* label = rows_pass ? ws.row_label : ws.col_label;
+            unsigned short* dst = rows_pass ? ws.comp_rows : ws.comp_cols;
+            const int half = rows_pass ? 0 : 1;
+            for (int b0 = 0; b0 < cnt; b0 += 32) {
+                const int k = b0 + lane;
+                const int l = (k < cnt) ? label[k] : kLapNone;
+                const unsigned same = __match_any_sync(kFullMask, l);
+                if (l != kLapNone) {
+                    const int rank = __popc(same & ((1u << lane) - 1u));
+                    const int leader = __ffs((int)same) - 1;
+                    const int base0 = cur16[2 * l + half];                 // read by every lane of the group before the write
+                    const int first = rows_pass ? (off[l] & 0xffff) : (off[l] >> 16);
+                    dst[first + base0 + rank] = (unsigned short)k;
+                    __syncwarp(same);
+                    if (lane == leader) cur16[2 * l + half] = (unsigned short)(base0 + __popc(same));
+                }
+                __syncwarp();
+            }
+        }
     }
     __syncthreads();
 
@@ -377,8 +398,6 @@ __device__ void block_lap_solve(LapWorkspace& ws, int n, int m, int n_max, int m
             const int pc = o0 >> 16, c = (o1 >> 16) - pc;
             unsigned short* rows = ws.comp_rows + pr;
             unsigned short* cols = ws.comp_cols + pc;
-            if (tl == 0) { insertion_sort_u16(rows, r); insertion_sort_u16(cols, c); }
-            __syncwarp(tmask);
             team_hungarian<8>(tmask, tl, rows, r, cols, c, thresh, cost, ws.row2col, ws.col2row);
         }
     }
@@ -393,8 +412,6 @@ __device__ void block_lap_solve(LapWorkspace& ws, int n, int m, int n_max, int m
         const int pc = o0 >> 16, c = (o1 >> 16) - pc;
         unsigned short* rows = ws.comp_rows + pr;
         unsigned short* cols = ws.comp_cols + pc;
-        warp_sort_u16(rows, r);
-        warp_sort_u16(cols, c);
         if (r + c <= 32) team_hungarian<32>(kFullMask, lane, rows, r, cols, c, thresh, cost, ws.row2col, ws.col2row);
         else warp_hungarian_big(LapGlobalScratch{ws.g_u, ws.g_v, ws.g_minv, ws.g_way, ws.g_prow, ws.g_flags}, m_max, n_max,
                                 rows, r, pr, cols, c, pc, thresh, cost, ws.row2col, ws.col2row);
@@ -459,11 +476,15 @@ __device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, 
             if constexpr (Cost::kGrid) {
                 // one row per thread and chunk: (1) collect the overlapping pairs of the chunk through the
                 // grid, (2) evaluate their exact costs densely, one pair per thread (no divergence)
-                for (int base = 0; base < n; base += nt) {
+                // `step` rows per pass, halved (down to one warp's worth) whenever their overlapping pairs do not fit the
+                // pair buffer - the alternative, scanning every column of those rows, costs far more than a second pass
+                int step = nt;
+                for (int base = 0; base < n;) {
                     const int i = base + tid;
+                    const bool mine = tid < step && i < n;
                     if (tid == 0) ws.ctl[7] = 0;
                     __syncthreads();
-                    if (i < n) {
+                    if (mine) {
                         const typename Cost::Row rw = cost.row(i);
                         grid_query(ws.grid, rw.b, [&](int j) { return cost.col_box(j); }, [&](int j, float4) {
                             const int q = atomicAdd(&ws.ctl[7], 1);
@@ -472,20 +493,35 @@ __device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, 
                     }
                     __syncthreads();
                     const int n_pairs = ws.ctl[7];
+                    if (n_pairs > ws.p_cap && step > 32) {          // uniform decision: retry this base with fewer rows
+                        step >>= 1;
+                        __syncthreads();                            // everyone has read n_pairs before thread 0 clears it
+                        continue;
+                    }
                     if (n_pairs <= ws.p_cap) {
                         for (int q = tid; q < n_pairs; q += nt) {
                             const int pk = ws.pairs[q];
                             const int pi = pk >> 16, pj = pk & 0xffff;
                             if (cost.is_candidate(cost.row(pi), pi, pj, thresh)) push_edge(pi, pj);
                         }
-                    } else if (i < n) {
-                        scan_row(i);                           // pair buffer too small for this chunk
+                    } else if (mine) {
+                        scan_row(i);                           // 32 rows still overflow the buffer: every column of those rows
                     }
                     __syncthreads();
+                    base += step;
                 }
             }
         } else {
-            for (int i = tid; i < n; i += nt) scan_row(i);
+            if (n < nt) {
+                // fewer rows than threads (second association: a handful of tracks x 64 detections): one pair per thread
+                for (int pq = tid; pq < n * m; pq += nt) {
+                    const int i = pq / m, j = pq - i * m;
+                    const typename Cost::Row rw = cost.row(i);
+                    if (!cost.reject(rw, j) && cost.is_candidate(rw, i, j, thresh)) push_edge(i, j);
+                }
+            } else {
+                for (int i = tid; i < n; i += nt) scan_row(i);
+            }
         }
     }
     if (ws.clk) { __syncthreads(); ws.clk->tick(ws.clk_base); }

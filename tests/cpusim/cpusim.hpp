@@ -358,6 +358,15 @@ static inline int __reduce_add_sync(unsigned mask, int v) {          // full-war
     return v;
 }
 static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == mask; }
+template <class T>
+static inline unsigned __match_any_sync(unsigned mask, T v) {
+    const uint64_t mine = cpusim::to_bits(v);
+    const uint64_t* s = cpusim::warp_exchange(mask, mine);
+    unsigned r = 0;
+    for (int l = 0; l < 32; ++l)
+        if (((mask >> l) & 1u) && s[l] == mine) r |= (1u << l);
+    return r;
+}
 static inline unsigned __activemask() { return 0xffffffffu; }
 
 // atomics: fibers of a block share one OS thread, and blocks never share addresses in these kernels

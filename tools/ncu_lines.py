@@ -16,8 +16,14 @@ import tempfile
 def line_map(so, kernel):
     tmp = tempfile.mkdtemp()
     subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
-    cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-    txt = subprocess.run(["nvdisasm", "-gi", "-c", cubin], capture_output=True, text=True).stdout
+    txt = ""
+    for f in sorted(os.listdir(tmp)):          # the library is several translation units: find the cubin that holds the kernel
+        if not f.endswith(".cubin"):
+            continue
+        t = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
+        if re.search(r"\.text\.[^\n]*" + re.escape(kernel), t):
+            txt = t
+            break
     m = {}
     chain = []
     fresh = True
