@@ -438,11 +438,8 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
                 if (tid == 0) sm.lap.ctl[7] = 0;
                 __syncthreads();
                 // a duplicate needs 1 - IoU < 0.15: only boxes whose corner lies within 16 % of a box size can qualify
-                if (i < na)
-                    grid_query_iou_above(sm.lap.grid, sm.row_box[i], 0.84f, [&](int j) { return sm.row_box[na + j]; }, [&](int j, float4) {
-                        const int q = atomicAdd(&sm.lap.ctl[7], 1);
-                        if (q < sm.lap.p_cap) sm.lap.pairs[q] = (i << 16) | j;
-                    });
+                grid_collect_pairs(sm.lap.grid, i < na, i < na ? sm.row_box[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f), i, 0.84f,
+                                   [&](int j) { return sm.row_box[na + j]; }, &sm.lap.ctl[7], sm.lap.pairs, sm.lap.p_cap);
                 __syncthreads();
                 const int n_pairs = sm.lap.ctl[7];
                 if (n_pairs <= sm.lap.p_cap) {

@@ -361,13 +361,27 @@ __device__ void block_lap_solve(LapWorkspace& ws, int n, int m, int n_max, int m
     unsigned short* list_triv = ws.comp_list;
     unsigned short* list_team = (unsigned short*)ws.scratch_b;           // the fill cursors are dead now
     unsigned short* list_warp = list_team + n;
-    for (int i = tid; i < n; i += nt) {
-        const int o0 = off[i], o1 = off[i + 1];
-        const int r = (o1 & 0xffff) - (o0 & 0xffff), c = (o1 >> 16) - (o0 >> 16);
-        if (r == 0) continue;
-        if (r == 1 || c == 1) list_triv[atomicAdd(&ws.ctl[3], 1)] = (unsigned short)i;
-        else if (r + c <= 8) list_team[atomicAdd(&ws.ctl[5], 1)] = (unsigned short)i;
-        else list_warp[atomicAdd(&ws.ctl[6], 1)] = (unsigned short)i;
+    for (int i0 = 0; i0 < n; i0 += nt) {                       // lock-step, one aggregated counter update per class and warp
+        const int i = i0 + tid;
+        int cls = -1;
+        if (i < n) {
+            const int o0 = off[i], o1 = off[i + 1];
+            const int r = (o1 & 0xffff) - (o0 & 0xffff), c = (o1 >> 16) - (o0 >> 16);
+            if (r != 0) cls = (r == 1 || c == 1) ? 0 : ((r + c <= 8) ? 1 : 2);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const unsigned hit = __ballot_sync(kFullMask, cls == k);
+            if (!hit) continue;
+            int* ctr = &ws.ctl[k == 0 ? 3 : (k == 1 ? 5 : 6)];
+            int b0 = 0;
+            if (lane == __ffs((int)hit) - 1) b0 = atomicAdd(ctr, __popc(hit));
+            b0 = __shfl_sync(kFullMask, b0, __ffs((int)hit) - 1);
+            if (cls == k) {
+                unsigned short* dst = (k == 0) ? list_triv : ((k == 1) ? list_team : list_warp);
+                dst[b0 + __popc(hit & ((1u << lane) - 1u))] = (unsigned short)i;
+            }
+        }
     }
     __syncthreads();
     const int n_triv = ws.ctl[3], n_team = ws.ctl[5], n_warp = ws.ctl[6];
@@ -484,12 +498,11 @@ __device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, 
                     const bool mine = tid < step && i < n;
                     if (tid == 0) ws.ctl[7] = 0;
                     __syncthreads();
-                    if (mine) {
-                        const typename Cost::Row rw = cost.row(i);
-                        grid_query(ws.grid, rw.b, [&](int j) { return cost.col_box(j); }, [&](int j, float4) {
-                            const int q = atomicAdd(&ws.ctl[7], 1);
-                            if (q < ws.p_cap) ws.pairs[q] = (i << 16) | j;
-                        });
+                    {
+                        float4 rb = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        if (mine) rb = cost.row(i).b;
+                        grid_collect_pairs(ws.grid, mine, rb, i, 0.0f, [&](int j) { return cost.col_box(j); }, &ws.ctl[7], ws.pairs,
+                                           ws.p_cap);
                     }
                     __syncthreads();
                     const int n_pairs = ws.ctl[7];
@@ -499,10 +512,22 @@ __device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, 
                         continue;
                     }
                     if (n_pairs <= ws.p_cap) {
-                        for (int q = tid; q < n_pairs; q += nt) {
-                            const int pk = ws.pairs[q];
+                        for (int q0 = 0; q0 < n_pairs; q0 += nt) {       // lock-step: one aggregated edge push per warp and pass
+                            const int q = q0 + tid;
+                            const int pk = (q < n_pairs) ? ws.pairs[q] : 0;
                             const int pi = pk >> 16, pj = pk & 0xffff;
-                            if (cost.is_candidate(cost.row(pi), pi, pj, thresh)) push_edge(pi, pj);
+                            const bool cand = (q < n_pairs) && cost.is_candidate(cost.row(pi), pi, pj, thresh);
+                            const unsigned hit = __ballot_sync(kFullMask, cand);
+                            if (hit) {
+                                int e0 = 0;
+                                if (lane == __ffs((int)hit) - 1) e0 = atomicAdd(&ws.ctl[0], __popc(hit));
+                                e0 = __shfl_sync(kFullMask, e0, __ffs((int)hit) - 1);
+                                if (cand) {
+                                    const int e = e0 + __popc(hit & ((1u << lane) - 1u));
+                                    if (e < ws.e_cap) ws.scratch_a[e] = (pi << 16) | pj;
+                                    else ws.ctl[1] = 1;
+                                }
+                            }
                         }
                     } else if (mine) {
                         scan_row(i);                           // 32 rows still overflow the buffer: every column of those rows
