@@ -139,11 +139,11 @@ int mot_engine_update_device_embs(mot_engine* e, int n_frames, const float* d_de
  * value is MOT_OK or the most severe condition as a mot_status. */
 int mot_engine_check(mot_engine* e, int* flags_per_stream);
 /* Diagnostics (ByteTrack engines): per-phase SM cycle counters of the fused frame step, summed over streams and frames
- * since the previous call.  Returns the 16 counters accumulated so far (cycles16 may be NULL), then enables / disables
+ * since the previous call.  Returns the 32 counters accumulated so far (cycles32 may be NULL; slots 16.. are reserved for finer splits), then enables / disables
  * and clears the accounting.  Slots: 0 detections + confidence split, 1 pool lists, 2 predicted boxes, 3 first association
  * candidates, 4 components, 5 grouping, 6 exact solves, 7 harvest, 8 Kalman of the matches, 9 second association, 10
  * unconfirmed association, 11 new tracks, 12 list algebra, 13 duplicate removal, 14 output rows.  Synchronises. */
-int mot_engine_profile(mot_engine* e, int enable, unsigned long long* cycles16);
+int mot_engine_profile(mot_engine* e, int enable, unsigned long long* cycles32);
 /* Introspection for tests: header ints of one stream [n_active,n_lost,n_free,id_counter,frame,err,
  * n1,m1,n2,m2,n3,m3,dupA,dupB,..] (16 ints), and a dump of one list (0 active, 1 lost) as rows of
  * [id,state,is_activated,frame_id,start_frame,tracklet_len,mean 8,cov 64] (78 floats). */

@@ -50,6 +50,23 @@ __device__ __forceinline__ int block_compact(int n, int start, BlockScratch* bs,
     return start + total;
 }
 
+// Exclusive scan of one value per thread; *total receives the block-wide sum.  Two barriers; all threads must call.
+__device__ __forceinline__ int block_exclusive_scan_value(int v, BlockScratch* bs, int* total) {
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (int)blockDim.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFullMask, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();                       // bs may still be read by a previous call
+    if (lane == 31) bs->warp_sum[warp] = incl;
+    __syncthreads();
+    const int ws = (lane < nwarps) ? bs->warp_sum[lane] : 0;
+    *total = __reduce_add_sync(kFullMask, ws);
+    return __reduce_add_sync(kFullMask, (lane < warp) ? ws : 0) + incl - v;
+}
+
 // In-place exclusive scan of data[0..n) (shared or global memory); writes the grand total to
 // data[n] when write_total is set (the array must then hold n + 1 entries).  Returns the total.
 __device__ __forceinline__ int block_exclusive_scan(int* data, int n, BlockScratch* bs, bool write_total) {

@@ -32,6 +32,10 @@ namespace mot {
 #endif
 constexpr int kBtThreads = MOT_BT_THREADS;
 
+// per-track Kalman record: the compact independent-coordinate form (kf_device.cuh), 96 B instead of 288 B - the whole
+// state of 296 C2 streams (80 MB) then stays resident in the 126 MB L2 instead of cycling through HBM
+constexpr int kBtRecFloats = kRecFloatsCompact;
+
 enum : int { kStNew = 0, kStTracked = 1, kStLost = 2, kStRemoved = 3 };
 constexpr unsigned char kFlagActivated = 0x10;
 
@@ -59,7 +63,7 @@ struct BtLayout {
         L.off_lists = o;    o = al(o + sizeof(unsigned short) * 3 * (size_t)cap);
         L.off_sflag = o;    o = al(o + (size_t)cap);
         L.off_meta = o;     o = al(o + sizeof(int) * 7 * (size_t)cap);
-        L.off_recs = o;     o = al(o + sizeof(float) * kRecFloats * (size_t)cap);
+        L.off_recs = o;     o = al(o + sizeof(float) * kBtRecFloats * (size_t)cap);
         L.off_gscratch = o; o = al(o + lap_gscratch_bytes(cap, d_max));
         L.stride = o;
         return L;
@@ -186,7 +190,7 @@ __device__ __forceinline__ void bt_kalman_pairs(const BtStream& st, const float*
         const bool live = k < n_pairs;
         const int slot = live ? slot_of(k) : 0;
         const int det = live ? det_of(k) : 0;
-        float* rec = st.recs + (size_t)slot * kRecFloats;
+        float* rec = st.recs + (size_t)slot * kBtRecFloats;
         KfBlock s;
         if (live) kfb_load(rec, c, s);
         else { s.mc = 1.0f; s.mv = 0.0f; s.pcc = 1.0f; s.pcv = 0.0f; s.pvc = 0.0f; s.pvv = 1.0f; }
@@ -265,7 +269,7 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
     //         rows that get matched: only the mean is needed to build costs)
     for (int r = tid; r < n1; r += nt) {
         const int slot = sm.pool[r];
-        const float* rec = st.recs + (size_t)slot * kRecFloats;
+        const float* rec = st.recs + (size_t)slot * kBtRecFloats;
         const float4 m = *reinterpret_cast<const float4*>(rec);
         const float4 v = *reinterpret_cast<const float4*>(rec + 4);
         const float vh = ((st.sflag[slot] & 0x0f) != kStTracked) ? 0.0f : v.w;
@@ -304,7 +308,7 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
     // ---- F. second association: r_tracked (slots in list_a) x low-confidence detections
     int n_lost_new = 0;
     if (n2 > 0 && n_lo > 0) {
-        for (int i = tid; i < n2; i += nt) sm.row_box[i] = bt_track_box(st.recs + (size_t)sm.list_a[i] * kRecFloats);
+        for (int i = tid; i < n2; i += nt) sm.row_box[i] = bt_track_box(st.recs + (size_t)sm.list_a[i] * kBtRecFloats);
         __syncthreads();
         IouCost cost{sm.row_box, sm.det_box, sm.det_conf, sm.lo, false, true};
         block_lap(sm.lap, n2, n_lo, cap, lap_m_max, 0.5f, cost);
@@ -330,7 +334,7 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
     int n_final = n_udet;
     const unsigned short* final_list = sm.udet;
     if (n_unc > 0 && n_udet > 0) {
-        for (int i = tid; i < n_unc; i += nt) sm.row_box[i] = bt_track_box(st.recs + (size_t)sm.unconf[i] * kRecFloats);
+        for (int i = tid; i < n_unc; i += nt) sm.row_box[i] = bt_track_box(st.recs + (size_t)sm.unconf[i] * kBtRecFloats);
         __syncthreads();
         IouCost cost{sm.row_box, sm.det_box, sm.det_conf, sm.udet, true, true};
         block_lap(sm.lap, n_unc, n_udet, cap, lap_m_max, 0.7f, cost);
@@ -357,17 +361,18 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
     int n_new = n_new_want;
     if (n_new > n_free) { n_new = n_free; if (tid == 0) atomicOr(&st.hdr[kHdrError], (int)kErrCapacity); }
     {
-        const int lane = lane_id(), g = lane & 7;
-        const int groups = nt >> 3, gid = tid >> 3;
-        for (int k = gid; k < n_new; k += groups) {
+        const int c = tid & 3;
+        const int quads = nt >> 2, qid = tid >> 2;
+        for (int k = qid; k < n_new; k += quads) {
             const int det = sm.sel[k];
             const int slot = st.freel[n_free - 1 - k];
             float z[4];
             bt_det_xyah(dets + (size_t)det * 6, z);
-            KfRow s;
-            kf_xyah_initiate(s, g, z);
-            kf_store_row(st.recs + (size_t)slot * kRecFloats, g, s);
-            if (g == 0) {
+            const float zc = (c == 0) ? z[0] : (c == 1) ? z[1] : (c == 2) ? z[2] : z[3];
+            KfBlock s;
+            kfb_xyah_initiate(s, c, zc, z[3]);
+            kfb_store(st.recs + (size_t)slot * kBtRecFloats, c, s);
+            if (c == 0) {
                 st.id[slot] = id_base + 1 + k;
                 st.sflag[slot] = (unsigned char)(kStTracked | (frame == 1 ? kFlagActivated : 0));
                 st.tracklet_len[slot] = 0;
@@ -415,11 +420,11 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
     for (int i = tid; i < na; i += nt) sm.dup_a[i] = 0;
     for (int j = tid; j < nl; j += nt) sm.dup_b[j] = 0;
     if (na > 0 && nl > 0) {
-        for (int i = tid; i < na; i += nt) sm.row_box[i] = bt_track_box(st.recs + (size_t)sm.list_a[i] * kRecFloats);
+        for (int i = tid; i < na; i += nt) sm.row_box[i] = bt_track_box(st.recs + (size_t)sm.list_a[i] * kBtRecFloats);
         // the lost boxes share row_box's tail when they fit, else they are recomputed from global
         const bool fits = na + nl <= cap;
         if (fits)
-            for (int j = tid; j < nl; j += nt) sm.row_box[na + j] = bt_track_box(st.recs + (size_t)sm.list_b[j] * kRecFloats);
+            for (int j = tid; j < nl; j += nt) sm.row_box[na + j] = bt_track_box(st.recs + (size_t)sm.list_b[j] * kBtRecFloats);
         __syncthreads();
         auto mark = [&](int i, int j, float4 ba, float area, float4 bb) {
             const float pd = xsub(1.0f, iou_pair(ba, area, bb));
@@ -435,13 +440,17 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
             grid_build(sm.lap.grid, nl, sm.bs, [&](int j) { return sm.row_box[na + j]; });
             for (int base = 0; base < na; base += nt) {
                 const int i = base + tid;
-                if (tid == 0) sm.lap.ctl[7] = 0;
+                // a duplicate needs 1 - IoU < 0.15: only boxes whose corner lies within 16 % of a box size can qualify.
+                // count, scan, write: private slices of the pair buffer instead of a shared counter
+                int cnt = 0;
+                if (i < na)
+                    grid_query_iou_above(sm.lap.grid, sm.row_box[i], 0.84f, [&](int j) { return sm.row_box[na + j]; }, [&](int, float4) { ++cnt; });
+                int n_pairs = 0;
+                int q0 = block_exclusive_scan_value(cnt, sm.bs, &n_pairs);
+                if (i < na && n_pairs <= sm.lap.p_cap)
+                    grid_query_iou_above(sm.lap.grid, sm.row_box[i], 0.84f, [&](int j) { return sm.row_box[na + j]; },
+                                         [&](int j, float4) { sm.lap.pairs[q0++] = (i << 16) | j; });
                 __syncthreads();
-                // a duplicate needs 1 - IoU < 0.15: only boxes whose corner lies within 16 % of a box size can qualify
-                grid_collect_pairs(sm.lap.grid, i < na, i < na ? sm.row_box[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f), i, 0.84f,
-                                   [&](int j) { return sm.row_box[na + j]; }, &sm.lap.ctl[7], sm.lap.pairs, sm.lap.p_cap);
-                __syncthreads();
-                const int n_pairs = sm.lap.ctl[7];
                 if (n_pairs <= sm.lap.p_cap) {
                     for (int q = tid; q < n_pairs; q += nt) {
                         const int pk = sm.lap.pairs[q];
@@ -463,7 +472,7 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
                 const float4 ba = sm.row_box[i];
                 const float area = box_area(ba);
                 for (int j = 0; j < nl; ++j) {
-                    const float4 bb = fits ? sm.row_box[na + j] : bt_track_box(st.recs + (size_t)sm.list_b[j] * kRecFloats);
+                    const float4 bb = fits ? sm.row_box[na + j] : bt_track_box(st.recs + (size_t)sm.list_b[j] * kBtRecFloats);
                     if (boxes_disjoint(ba, bb)) continue;                  // distance exactly 1
                     mark(i, j, ba, area, bb);
                 }
@@ -487,7 +496,7 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
                                      [&](int i, int pos) {
                                          if (pos >= a.ld_out) return;
                                          const int slot = st.active[i];
-                                         const float4 b = bt_track_box(st.recs + (size_t)slot * kRecFloats);
+                                         const float4 b = bt_track_box(st.recs + (size_t)slot * kBtRecFloats);
                                          float* o = out + (size_t)pos * 8;
                                          *reinterpret_cast<float4*>(o) = b;
                                          *reinterpret_cast<float4*>(o + 4) =

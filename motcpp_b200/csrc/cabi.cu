@@ -673,15 +673,15 @@ int mot_engine_check(mot_engine* e, int* flags) {
     return MOT_OK;
 }
 
-int mot_engine_profile(mot_engine* e, int enable, unsigned long long* cycles16) {
+int mot_engine_profile(mot_engine* e, int enable, unsigned long long* cycles32) {
     if (!e) return fail(MOT_ERR_INVALID_ARGUMENT, "null engine");
     MOT_CUDA(cudaSetDevice(e->cfg.device));
     MOT_CUDA(cudaDeviceSynchronize());
-    if (e->d_prof && cycles16) MOT_CUDA(cudaMemcpy(cycles16, e->d_prof, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    else if (cycles16) memset(cycles16, 0, 16 * sizeof(unsigned long long));
+    if (e->d_prof && cycles32) MOT_CUDA(cudaMemcpy(cycles32, e->d_prof, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    else if (cycles32) memset(cycles32, 0, 32 * sizeof(unsigned long long));
     if (enable) {
-        if (!e->d_prof) MOT_CUDA(cudaMalloc((void**)&e->d_prof, 16 * sizeof(unsigned long long)));
-        MOT_CUDA(cudaMemset(e->d_prof, 0, 16 * sizeof(unsigned long long)));
+        if (!e->d_prof) MOT_CUDA(cudaMalloc((void**)&e->d_prof, 32 * sizeof(unsigned long long)));
+        MOT_CUDA(cudaMemset(e->d_prof, 0, 32 * sizeof(unsigned long long)));
     } else if (e->d_prof) {
         cudaFree(e->d_prof);
         e->d_prof = nullptr;
@@ -743,7 +743,7 @@ int mot_engine_dump_list(mot_engine* e, int s, int which, float* rows, int cap_r
         float* o = rows + 78 * (size_t)k;
         o[0] = (float)meta[slot]; o[1] = (float)(sflag[slot] & 0x0f); o[2] = (sflag[slot] & 0x10) ? 1.0f : 0.0f;
         o[3] = (float)meta[2 * L.cap + slot]; o[4] = (float)meta[3 * L.cap + slot]; o[5] = (float)meta[L.cap + slot];
-        std::memcpy(o + 6, recs + (size_t)slot * mot::kRecFloats, sizeof(float) * mot::kRecFloats);
+        mot::kfb_expand(recs + (size_t)slot * mot::kBtRecFloats, o + 6);     // compact record -> [mean 8 | cov 8x8]
     }
     *n_rows = k;
     return MOT_OK;

@@ -232,15 +232,35 @@ __device__ __forceinline__ bool kf_xyah_update(KfRow& s, int g, int base, const 
 struct KfBlock {
     float mc, mv, pcc, pcv, pvc, pvv;
 };
+// Compact record of the independent-coordinate form: 24 floats (96 B, three 32-byte sectors) instead of 72,
+//   [ mean 8 | P[c][c] x4 | P[c][c+4] x4 | P[c+4][c] x4 | P[c+4][c+4] x4 ]
+// - the 48 entries it leaves out are structural zeros.  A quad's loads are four consecutive floats per array.
+constexpr int kRecFloatsCompact = 24;
 __device__ __forceinline__ void kfb_load(const float* __restrict__ rec, int c, KfBlock& s) {
     s.mc = rec[c]; s.mv = rec[c + 4];
-    s.pcc = rec[8 + 9 * c]; s.pcv = rec[8 + 9 * c + 4];
-    s.pvc = rec[8 + 8 * (c + 4) + c]; s.pvv = rec[8 + 9 * (c + 4)];
+    s.pcc = rec[8 + c]; s.pcv = rec[12 + c]; s.pvc = rec[16 + c]; s.pvv = rec[20 + c];
 }
 __device__ __forceinline__ void kfb_store(float* __restrict__ rec, int c, const KfBlock& s) {
     rec[c] = s.mc; rec[c + 4] = s.mv;
-    rec[8 + 9 * c] = s.pcc; rec[8 + 9 * c + 4] = s.pcv;
-    rec[8 + 8 * (c + 4) + c] = s.pvc; rec[8 + 9 * (c + 4)] = s.pvv;
+    rec[8 + c] = s.pcc; rec[12 + c] = s.pcv; rec[16 + c] = s.pvc; rec[20 + c] = s.pvv;
+}
+// KalmanFilterXYAH::initiate (kalman_filter.cpp:29-42, xyah_kf.cpp:14-29) for coordinate c: a diagonal covariance
+__device__ __forceinline__ void kfb_xyah_initiate(KfBlock& s, int c, float zc, float h) {
+    const float sp = (c == 2) ? 1e-2f : xmul(xmul(2.0f, kf_wpos()), h);
+    const float sv = (c == 2) ? 1e-5f : xmul(xmul(10.0f, kf_wvel()), h);
+    s.mc = zc; s.mv = 0.0f;
+    s.pcc = xmul(sp, sp); s.pcv = 0.0f; s.pvc = 0.0f; s.pvv = xmul(sv, sv);
+}
+// dense 72-float record [mean 8 | cov 8x8 row-major] of a compact one (host side: state dumps)
+MOT_HD inline void kfb_expand(const float* compact, float* dense72) {
+    for (int k = 0; k < 72; ++k) dense72[k] = 0.0f;
+    for (int k = 0; k < 8; ++k) dense72[k] = compact[k];
+    for (int c = 0; c < 4; ++c) {
+        dense72[8 + 9 * c] = compact[8 + c];
+        dense72[8 + 9 * c + 4] = compact[12 + c];
+        dense72[8 + 8 * (c + 4) + c] = compact[16 + c];
+        dense72[8 + 9 * (c + 4)] = compact[20 + c];
+    }
 }
 // kf_xyah_predict restricted to block c.  h = mean(3) BEFORE the motion step; zero_vh as in kf_xyah_predict.
 __device__ __forceinline__ void kfb_xyah_predict(KfBlock& s, int c, float h, bool zero_vh) {

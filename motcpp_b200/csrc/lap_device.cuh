@@ -77,6 +77,22 @@ __device__ __forceinline__ void warp_sort_u16(unsigned short* seg, int n) {
     }
 }
 
+// Ascending sort of n <= W distinct ids by a team of W consecutive lanes: every lane ranks its element against the others.
+template <int W>
+__device__ __forceinline__ void team_sort_u16(unsigned mask, int tl, unsigned short* seg, int n) {
+    if (n <= 1) return;
+    const int v = tl < n ? (int)seg[tl] : 0x7fffffff;
+    int rank = 0;
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+        const int o = __shfl_sync(mask, v, k, W);
+        rank += (k < n && o < v) ? 1 : 0;
+    }
+    __syncwarp(mask);
+    if (tl < n) seg[rank] = (unsigned short)v;
+    __syncwarp(mask);
+}
+
 // (min value, lowest lane on ties) across a team of W consecutive lanes
 template <int W>
 __device__ __forceinline__ void team_argmin(unsigned mask, double& key, int& arg) {
@@ -322,34 +338,13 @@ __device__ void block_lap_solve(LapWorkspace& ws, int n, int m, int n_max, int m
     for (int j = tid; j < m; j += nt) { const int l = ws.col_label[j]; if (l != kLapNone) atomicAdd(&off[l], 1 << 16); }
     __syncthreads();
     block_exclusive_scan(off, n, ws.bs, true);
-    // ORDERED fill: warp 0 walks the rows, warp 1 the columns, 32 at a time in ascending order; lanes with the same label
-    // find each other with match.any, so every component's rows / columns come out sorted ascending (what the solvers'
-    // lowest-index tie-breaking needs) without a sort per component.  The two cursors of a label are separate halfwords.
-    {
-        unsigned short* cur16 = reinterpret_cast<unsigned short*>(cur);
-        const int warp = tid >> 5, nwarps = nt >> 5;
-        for (int pass = warp; pass < 2; pass += nwarps) {   // (a one-warp block does both passes)
-            const bool rows_pass = (pass == 0);
-            const int cnt = rows_pass ? n : m;
-            const int* label = rows_pass ? ws.row_label : ws.col_label;
-            unsigned short* dst = rows_pass ? ws.comp_rows : ws.comp_cols;
-            const int half = rows_pass ? 0 : 1;
-            for (int b0 = 0; b0 < cnt; b0 += 32) {
-                const int k = b0 + lane;
-                const int l = (k < cnt) ? label[k] : kLapNone;
-                const unsigned same = __match_any_sync(kFullMask, l);
-                if (l != kLapNone) {
-                    const int rank = __popc(same & ((1u << lane) - 1u));
-                    const int leader = __ffs((int)same) - 1;
-                    const int base0 = cur16[2 * l + half];                 // read by every lane of the group before the write
-                    const int first = rows_pass ? (off[l] & 0xffff) : (off[l] >> 16);
-                    dst[first + base0 + rank] = (unsigned short)k;
-                    __syncwarp(same);
-                    if (lane == leader) cur16[2 * l + half] = (unsigned short)(base0 + __popc(same));
-                }
-                __syncwarp();
-            }
-        }
+    for (int i = tid; i < n; i += nt) {
+        const int l = ws.row_label[i];
+        if (l != kLapNone) { const int k = atomicAdd(&cur[l], 1) & 0xffff; ws.comp_rows[(off[l] & 0xffff) + k] = (unsigned short)i; }
+    }
+    for (int j = tid; j < m; j += nt) {
+        const int l = ws.col_label[j];
+        if (l != kLapNone) { const int k = atomicAdd(&cur[l], 1 << 16) >> 16; ws.comp_cols[(off[l] >> 16) + k] = (unsigned short)j; }
     }
     __syncthreads();
 
@@ -412,6 +407,8 @@ __device__ void block_lap_solve(LapWorkspace& ws, int n, int m, int n_max, int m
             const int pc = o0 >> 16, c = (o1 >> 16) - pc;
             unsigned short* rows = ws.comp_rows + pr;
             unsigned short* cols = ws.comp_cols + pc;
+            team_sort_u16<8>(tmask, tl, rows, r);              // the fill order is arbitrary; ties go to the lowest index
+            team_sort_u16<8>(tmask, tl, cols, c);
             team_hungarian<8>(tmask, tl, rows, r, cols, c, thresh, cost, ws.row2col, ws.col2row);
         }
     }
@@ -426,6 +423,8 @@ __device__ void block_lap_solve(LapWorkspace& ws, int n, int m, int n_max, int m
         const int pc = o0 >> 16, c = (o1 >> 16) - pc;
         unsigned short* rows = ws.comp_rows + pr;
         unsigned short* cols = ws.comp_cols + pc;
+        warp_sort_u16(rows, r);
+        warp_sort_u16(cols, c);
         if (r + c <= 32) team_hungarian<32>(kFullMask, lane, rows, r, cols, c, thresh, cost, ws.row2col, ws.col2row);
         else warp_hungarian_big(LapGlobalScratch{ws.g_u, ws.g_v, ws.g_minv, ws.g_way, ws.g_prow, ws.g_flags}, m_max, n_max,
                                 rows, r, pr, cols, c, pc, thresh, cost, ws.row2col, ws.col2row);
@@ -470,7 +469,9 @@ __device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, 
         if constexpr (Cost::kGrid) {
             // box costs: index the columns so that only overlapping pairs are looked at
             if (cost.prune && (long long)n * m >= 8192 && m <= ws.grid.cap) {
+                if (ws.clk) ws.clk->tick(16 + 3);
                 grid_build(ws.grid, m, ws.bs, [&](int j) { return cost.col_box(j); });
+                if (ws.clk) ws.clk->tick(16 + 0);
                 use_grid = true;
             }
         }
@@ -488,23 +489,26 @@ __device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, 
         };
         if (use_grid) {
             if constexpr (Cost::kGrid) {
-                // one row per thread and chunk: (1) collect the overlapping pairs of the chunk through the
-                // grid, (2) evaluate their exact costs densely, one pair per thread (no divergence)
-                // `step` rows per pass, halved (down to one warp's worth) whenever their overlapping pairs do not fit the
-                // pair buffer - the alternative, scanning every column of those rows, costs far more than a second pass
+                // one row per thread and pass: (1) collect the overlapping pairs of the rows through the grid, (2) judge them
+                // densely, one pair per thread (no divergence).  Measured alternatives, all slower on the C2 workload: judging
+                // inside the walk (+16 %), count / scan / write instead of the shared counter (+20 %), a lock-step warp
+                // walk with one aggregated atomic per step (+70 %): the walk is a chain of dependent shared-memory loads.
+                // `step` rows per pass, halved (down to one warp's worth) whenever their pairs do not fit the pair buffer.
                 int step = nt;
                 for (int base = 0; base < n;) {
                     const int i = base + tid;
                     const bool mine = tid < step && i < n;
                     if (tid == 0) ws.ctl[7] = 0;
                     __syncthreads();
-                    {
-                        float4 rb = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                        if (mine) rb = cost.row(i).b;
-                        grid_collect_pairs(ws.grid, mine, rb, i, 0.0f, [&](int j) { return cost.col_box(j); }, &ws.ctl[7], ws.pairs,
-                                           ws.p_cap);
+                    if (mine) {
+                        const typename Cost::Row rw = cost.row(i);
+                        grid_query(ws.grid, rw.b, [&](int j) { return cost.col_box(j); }, [&](int j, float4) {
+                            const int q = atomicAdd(&ws.ctl[7], 1);
+                            if (q < ws.p_cap) ws.pairs[q] = (i << 16) | j;
+                        });
                     }
                     __syncthreads();
+                    if (ws.clk) ws.clk->tick(16 + 1);
                     const int n_pairs = ws.ctl[7];
                     if (n_pairs > ws.p_cap && step > 32) {          // uniform decision: retry this base with fewer rows
                         step >>= 1;
@@ -533,6 +537,7 @@ __device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, 
                         scan_row(i);                           // 32 rows still overflow the buffer: every column of those rows
                     }
                     __syncthreads();
+                    if (ws.clk) ws.clk->tick(16 + 2);
                     base += step;
                 }
             }

@@ -121,7 +121,7 @@ int sim_bt_dump(void* hv, int s, int which, float* outrows, int cap_rows) {
         float* o = outrows + 78 * k;
         o[0] = (float)meta[slot]; o[1] = (float)(sflag[slot] & 0x0f); o[2] = (sflag[slot] & 0x10) ? 1.0f : 0.0f;
         o[3] = (float)meta[2 * cap + slot]; o[4] = (float)meta[3 * cap + slot]; o[5] = (float)meta[cap + slot];
-        std::memcpy(o + 6, recs + (size_t)slot * mot::kRecFloats, sizeof(float) * mot::kRecFloats);
+        mot::kfb_expand(recs + (size_t)slot * mot::kBtRecFloats, o + 6);
     }
     return k;
 }

@@ -24,13 +24,16 @@ def main():
     lib = _lib.load()
     api.check(lib.mot_engine_profile(eng._h, 1, None))
     eng.update(dets[warm:], counts[warm:], ld_out=512)
-    cyc = np.zeros(16, np.uint64)
+    cyc = np.zeros(32, np.uint64)
     api.check(lib.mot_engine_profile(eng._h, 0, cyc.ctypes.data))
+    extra = cyc[16:].astype(np.float64) / (S * T)
+    cyc = cyc[:16]
     tot = float(cyc.sum())
     per_frame = cyc.astype(np.float64) / (S * T)
     print("streams %d, frames %d: %.0f cycles per frame per CTA (%.1f us at 1.965 GHz)" % (S, T, tot / (S * T), tot / (S * T) / 1965.0))
     for k, n in enumerate(NAMES):
         print("  %-16s %8.0f cycles  %5.1f %%" % (n, per_frame[k], 100.0 * cyc[k] / tot))
+    print("  D1 split: init %.0f, grid build %.0f, pair collection %.0f, pair evaluation %.0f cycles" % (extra[3], extra[0], extra[1], extra[2]))
     print(json.dumps({"streams": S, "frames": T, "cycles_per_frame": tot / (S * T), "share": {n: float(cyc[k] / tot) for k, n in enumerate(NAMES)}}))
 
 if __name__ == "__main__":
