@@ -246,20 +246,19 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
     }
     __syncthreads();
     const float t_hi = a.p.track_thresh, t_lo = a.p.min_conf;
-    const int n_hi = block_compact(n_det, 0, sm.bs, [&](int j) { return sm.det_conf[j] > t_hi; },
-                                   [&](int j, int pos) { sm.hi[pos] = (unsigned short)j; });
-    const int n_lo = block_compact(n_det, 0, sm.bs,
-                                   [&](int j) { const float c = sm.det_conf[j]; return c > t_lo && c < t_hi; },
-                                   [&](int j, int pos) { sm.lo[pos] = (unsigned short)j; });
+    int n_hi = 0, n_lo = 0;
+    block_compact2(n_det, 0, 0, sm.bs, [&](int j) { return sm.det_conf[j] > t_hi; },
+                   [&](int j) { const float c = sm.det_conf[j]; return c > t_lo && c < t_hi; },
+                   [&](int j, int pos) { sm.hi[pos] = (unsigned short)j; }, [&](int j, int pos) { sm.lo[pos] = (unsigned short)j; },
+                   n_hi, n_lo);
 
     clk.tick(0);
     // ---- B. pool = tracked (activated) ++ lost ; unconfirmed kept aside
-    const int n_trk = block_compact(n_active, 0, sm.bs,
-                                    [&](int k) { return (st.sflag[st.active[k]] & kFlagActivated) != 0; },
-                                    [&](int k, int pos) { sm.pool[pos] = st.active[k]; });
-    const int n_unc = block_compact(n_active, 0, sm.bs,
-                                    [&](int k) { return (st.sflag[st.active[k]] & kFlagActivated) == 0; },
-                                    [&](int k, int pos) { sm.unconf[pos] = st.active[k]; });
+    int n_trk = 0, n_unc = 0;
+    block_compact2(n_active, 0, 0, sm.bs, [&](int k) { return (st.sflag[st.active[k]] & kFlagActivated) != 0; },
+                   [&](int k) { return (st.sflag[st.active[k]] & kFlagActivated) == 0; },
+                   [&](int k, int pos) { sm.pool[pos] = st.active[k]; }, [&](int k, int pos) { sm.unconf[pos] = st.active[k]; },
+                   n_trk, n_unc);
     for (int k = tid; k < n_lost; k += nt) sm.pool[n_trk + k] = st.lost[k];
     const int n1 = n_trk + n_lost;
     __syncthreads();
@@ -287,15 +286,16 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
         sm.lap.clk = nullptr;
     }
     // harvest what later phases need before the LAP workspace is reused
-    const int n_m1 = block_compact(n1, 0, sm.bs, [&](int r) { return sm.lap.row2col[r] >= 0; },
-                                   [&](int r, int pos) { sm.sel[pos] = (unsigned short)r; });
+    // matched rows, and r_tracked = unmatched pool rows that came from the active list (state Tracked): one pass
+    int n_m1 = 0, n2 = 0;
+    block_compact2(n1, 0, 0, sm.bs, [&](int r) { return sm.lap.row2col[r] >= 0; },
+                   [&](int r) { return r < n_trk && sm.lap.row2col[r] < 0; },
+                   [&](int r, int pos) { sm.sel[pos] = (unsigned short)r; }, [&](int r, int pos) { sm.list_a[pos] = sm.pool[r]; },
+                   n_m1, n2);
     // matched rows: stash the detection index next to the row (list_c is free until phase F)
     for (int k = tid; k < n_m1; k += nt) sm.list_c[k] = sm.hi[sm.lap.row2col[sm.sel[k]]];
     const int n_udet = block_compact(n_hi, 0, sm.bs, [&](int j) { return sm.lap.col2row[j] < 0; },
                                      [&](int j, int pos) { sm.udet[pos] = sm.hi[j]; });
-    // r_tracked: unmatched pool rows that came from the active list (state Tracked)
-    const int n2 = block_compact(n_trk, 0, sm.bs, [&](int r) { return sm.lap.row2col[r] < 0; },
-                                 [&](int r, int pos) { sm.list_a[pos] = sm.pool[r]; });
     __syncthreads();
 
     clk.tick(7);
@@ -372,7 +372,9 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
             KfBlock s;
             kfb_xyah_initiate(s, c, zc, z[3]);
             kfb_store(st.recs + (size_t)slot * kBtRecFloats, c, s);
+            __syncwarp(0xfu << (lane_id() & ~3));                     // the quad has read sel[k]
             if (c == 0) {
+                sm.sel[k] = (unsigned short)slot;                    // phase J appends the new slots from here
                 st.id[slot] = id_base + 1 + k;
                 st.sflag[slot] = (unsigned char)(kStTracked | (frame == 1 ? kFlagActivated : 0));
                 st.tracklet_len[slot] = 0;
@@ -396,22 +398,22 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
     __syncthreads();
 
     // ---- J. next lists.  active' = kept active ++ new ++ re-found ; lost' = kept lost ++ lost-this-frame
-    int na = block_compact(n_active, 0, sm.bs, [&](int k) { return (st.sflag[st.active[k]] & 0x0f) == kStTracked; },
-                           [&](int k, int pos) { sm.list_a[pos] = st.active[k]; });
-    for (int k = tid; k < n_new; k += nt) sm.list_a[na + k] = st.freel[n_free - 1 - k];
+    // Slots that died this frame (removed unconfirmed tracks, expired lost tracks) go back on the free stack, on top of
+    // what is left after the new tracks took theirs (sel[] holds the new tracks' slots since phase H).
+    int na = 0, nl = 0;
+    n_free -= n_new;
+    block_compact2(n_active, 0, n_free, sm.bs, [&](int k) { return (st.sflag[st.active[k]] & 0x0f) == kStTracked; },
+                   [&](int k) { return (st.sflag[st.active[k]] & 0x0f) == kStRemoved; },
+                   [&](int k, int pos) { sm.list_a[pos] = st.active[k]; }, [&](int k, int pos) { st.freel[pos] = st.active[k]; },
+                   na, n_free);
+    for (int k = tid; k < n_new; k += nt) sm.list_a[na + k] = sm.sel[k];
     na += n_new;
-    na = block_compact(n_lost, na, sm.bs, [&](int k) { return (st.sflag[st.lost[k]] & 0x0f) == kStTracked; },
-                       [&](int k, int pos) { sm.list_a[pos] = st.lost[k]; });
-    int nl = block_compact(n_lost, 0, sm.bs, [&](int k) { return (st.sflag[st.lost[k]] & 0x0f) == kStLost; },
-                           [&](int k, int pos) { sm.list_b[pos] = st.lost[k]; });
+    block_compact2(n_lost, na, 0, sm.bs, [&](int k) { return (st.sflag[st.lost[k]] & 0x0f) == kStTracked; },
+                   [&](int k) { return (st.sflag[st.lost[k]] & 0x0f) == kStLost; },
+                   [&](int k, int pos) { sm.list_a[pos] = st.lost[k]; }, [&](int k, int pos) { sm.list_b[pos] = st.lost[k]; },
+                   na, nl);
     for (int k = tid; k < n_lost_new; k += nt) sm.list_b[nl + k] = sm.list_c[k];
     nl += n_lost_new;
-    __syncthreads();
-    // slots that died this frame (removed unconfirmed tracks, expired lost tracks) go back on the
-    // free stack, on top of what is left after the new tracks took theirs
-    n_free -= n_new;
-    n_free = block_compact(n_active, n_free, sm.bs, [&](int k) { return (st.sflag[st.active[k]] & 0x0f) == kStRemoved; },
-                           [&](int k, int pos) { st.freel[pos] = st.active[k]; });
     n_free = block_compact(n_lost, n_free, sm.bs, [&](int k) { return (st.sflag[st.lost[k]] & 0x0f) == kStRemoved; },
                            [&](int k, int pos) { st.freel[pos] = st.lost[k]; });
 
@@ -480,14 +482,13 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
         }
     }
     __syncthreads();
-    const int na2 = block_compact(na, 0, sm.bs, [&](int i) { return sm.dup_a[i] == 0; },
-                                  [&](int i, int pos) { st.active[pos] = sm.list_a[i]; });
-    const int nl2 = block_compact(nl, 0, sm.bs, [&](int j) { return sm.dup_b[j] == 0; },
-                                  [&](int j, int pos) { st.lost[pos] = sm.list_b[j]; });
-    n_free = block_compact(na, n_free, sm.bs, [&](int i) { return sm.dup_a[i] != 0; },
-                           [&](int i, int pos) { st.freel[pos] = sm.list_a[i]; });
-    n_free = block_compact(nl, n_free, sm.bs, [&](int j) { return sm.dup_b[j] != 0; },
-                           [&](int j, int pos) { st.freel[pos] = sm.list_b[j]; });
+    int na2 = 0, nl2 = 0;
+    block_compact2(na, 0, n_free, sm.bs, [&](int i) { return sm.dup_a[i] == 0; }, [&](int i) { return sm.dup_a[i] != 0; },
+                   [&](int i, int pos) { st.active[pos] = sm.list_a[i]; }, [&](int i, int pos) { st.freel[pos] = sm.list_a[i]; },
+                   na2, n_free);
+    block_compact2(nl, 0, n_free, sm.bs, [&](int j) { return sm.dup_b[j] == 0; }, [&](int j) { return sm.dup_b[j] != 0; },
+                   [&](int j, int pos) { st.lost[pos] = sm.list_b[j]; }, [&](int j, int pos) { st.freel[pos] = sm.list_b[j]; },
+                   nl2, n_free);
     __syncthreads();
 
     clk.tick(13);
