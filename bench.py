@@ -36,10 +36,10 @@ sys.path.insert(0, ROOT)
 METRIC = "tracker.update() frames/sec at 256 tracks x 512 dets (ByteTrack)"
 UNIT = "frames/s"
 ALGO_BYTES_PER_UPDATE = 167_936          # state in+out 147,456 + dets 12,288 + output 8,192
-# dram__bytes_read.sum + dram__bytes_write.sum of one bytetrack_step_kernel launch (ncu --set full, 148 streams x 20
-# frames, steady state) / 2960 frames: profiles/r1_bytetrack_step_ncu_full.txt.  Below the algorithmic figure because
-# most of a stream's 0.56 MB of state stays in the 126 MB L2 from one frame to the next.
-NCU_DRAM_BYTES_PER_UPDATE = 50_800          # (80.92 + 69.44) MB / 2960 frames
+# dram__bytes_read.sum + dram__bytes_write.sum of one bytetrack_step_kernel launch (ncu --set full, 296 streams x 20
+# frames, steady state) / 5920 frames: profiles/r2_bytetrack_step_ncu_full.txt.  Below the algorithmic figure because
+# the streams' state (0.27 MB each with the compact Kalman record) stays in the 126 MB L2 from one frame to the next.
+NCU_DRAM_BYTES_PER_UPDATE = 37_670          # (115.04 + 107.94) MB / 5920 frames
 BT_ARGS = dict(det_thresh=0.3, max_age=30, max_obs=50, min_hits=3, iou_threshold=0.3, min_conf=0.1,
                track_thresh=0.45, match_thresh=0.8, track_buffer=30, frame_rate=30)     # tools/motcpp_eval.cpp:133-148
 N_DETS = 512
@@ -365,7 +365,7 @@ def main():
     achieved = ALGO_BYTES_PER_UPDATE * S * F / avg_launch_s / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                 "traffic": NCU_DRAM_BYTES_PER_UPDATE * S * F, "kernel": "bytetrack_step_kernel",
-                "traffic_source": "ncu --set full dram__bytes_read+write per update() (profiles/r1_bytetrack_step_ncu_full.txt) "
+                "traffic_source": "ncu --set full dram__bytes_read+write per update() (profiles/r2_bytetrack_step_ncu_full.txt) "
                                   "x updates per launch",
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_UPDATE * S * F,
                 "avg_launch_ms": float(np.mean(launch_ms)),
