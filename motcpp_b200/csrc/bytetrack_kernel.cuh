@@ -522,8 +522,12 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
 // One CTA per stream; each CTA walks its streams' T frames in order (state stays hot in L1/L2).
 // CAP / DMAX / ECAP are compile-time so that every shared-memory and state pointer is "base +
 // constant" (no registers spent on the ~50 pointers of the carve-up).
-template <int CAP, int DMAX, int ECAP>
-__global__ void __launch_bounds__(kBtThreads, MOT_BT_MINBLOCKS) bytetrack_step_kernel(BtArgs a) {
+// THREADS = kBtThreads (two CTAs per SM) when there are streams to fill the machine; kBtThreadsWide (one 1024-thread CTA
+// per SM) when there are fewer streams than SMs (BASELINE configs[4]: 8 streams per GPU) - a frame's phases are then
+// latency-bound per stream and twice the threads shorten the parallel ones (one pass instead of two over the pool).
+constexpr int kBtThreadsWide = 1024;
+template <int CAP, int DMAX, int ECAP, int THREADS = kBtThreads>
+__global__ void __launch_bounds__(THREADS, (THREADS > 512) ? 1 : MOT_BT_MINBLOCKS) bytetrack_step_kernel(BtArgs a) {
     MOT_DYNAMIC_SMEM(smem);
     BtSmem sm;
     bt_carve(smem, CAP, DMAX, ECAP, sm);

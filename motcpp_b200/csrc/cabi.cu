@@ -170,7 +170,7 @@ static void engine_launch(mot_engine* e, int T, const float* dets, const int* nd
         mot::oc_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
     } else {
         mot::BtArgs a = make_args(e, T, dets, nd, ld_dets, out, nout, ld_out, s0, s1);
-        mot::bt_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
+        mot::bt_launch(e->shape, s1 - s0, e->smem_bytes, st, a, e->threads);
     }
 }
 
@@ -353,7 +353,7 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     e->ssp.mc_lambda = cfg->mc_lambda; e->ssp.ema_alpha = cfg->ema_alpha; e->ssp.max_age = cfg->max_age;
     e->ssp.n_init = cfg->n_init; e->ssp.budget = std::max(1, cfg->nn_budget); e->ssp.dim = cfg->emb_dim;
     e->stride = is_ss ? e->ss_layout.stride : is_sort ? e->sort_layout.stride : (is_oc ? e->oc_layout.stride : (is_bot ? e->bot_layout.stride : e->layout.stride));
-    e->threads = is_ss ? mot::kSsThreads : is_sort ? mot::kSortThreads : (is_oc ? mot::kOcThreads : (is_bot ? mot::kBotThreads : mot::kBtThreads));
+    e->threads = is_ss ? mot::kSsThreads : is_sort ? mot::kSortThreads : (is_oc ? mot::kOcThreads : (is_bot ? mot::kBotThreads : mot::bt_threads(e->shape, cfg->n_streams, sm_count())));
     e->smem_bytes = is_ss ? mot::ss_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap) : is_sort ? mot::sort_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap)
                   : is_oc   ? mot::oc_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap)
                   : is_bot  ? mot::bot_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap)
@@ -367,7 +367,7 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     }
     MOT_CUDA(is_ss ? mot::ss_prepare(e->shape, e->smem_bytes) : is_sort ? mot::sort_prepare(e->shape, e->smem_bytes)
                      : (is_oc ? mot::oc_prepare(e->shape, e->smem_bytes)
-                              : (is_bot ? mot::bot_prepare(e->shape, e->smem_bytes) : mot::bt_prepare(e->shape, e->smem_bytes))));
+                              : (is_bot ? mot::bot_prepare(e->shape, e->smem_bytes) : mot::bt_prepare(e->shape, e->smem_bytes, e->threads))));
     e->n_chunks = cfg->n_chunks > 0 ? std::min(cfg->n_chunks, kMaxChunks) : (cfg->n_streams >= 128 ? 8 : (cfg->n_streams >= 32 ? 4 : 1));
     e->n_chunks = std::min(e->n_chunks, cfg->n_streams);
     int prio_lo = 0, prio_hi = 0;

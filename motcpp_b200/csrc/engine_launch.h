@@ -7,8 +7,10 @@
 namespace mot {
 struct BtArgs; struct SortArgs; struct OcArgs; struct BotArgs; struct SsArgs;
 // *_prepare: opt the kernel of `shape` into `smem` bytes of dynamic shared memory; *_launch: one CTA per stream
-cudaError_t bt_prepare(int shape, size_t smem);
-void bt_launch(int shape, int grid, size_t smem, cudaStream_t st, const BtArgs& a);
+// ByteTrack picks its CTA width from the stream count: 512 threads x 2 CTAs per SM, or one 1024-thread CTA per SM
+int bt_threads(int shape, int n_streams, int n_sms);
+cudaError_t bt_prepare(int shape, size_t smem, int threads);
+void bt_launch(int shape, int grid, size_t smem, cudaStream_t st, const BtArgs& a, int threads);
 cudaError_t sort_prepare(int shape, size_t smem);
 void sort_launch(int shape, int grid, size_t smem, cudaStream_t st, const SortArgs& a);
 cudaError_t oc_prepare(int shape, size_t smem);

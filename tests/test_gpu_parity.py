@@ -563,6 +563,30 @@ def test_bytetrack_full_size_properties():
     a.close(); b.close()
 
 
+def test_bytetrack_both_cta_widths_agree_with_the_oracle(oracle):
+    """The C2 shape has two kernels: 512 threads x 2 CTAs per SM when the streams fill the machine (the bench), one
+    1024-thread CTA per SM when there are fewer streams than SMs (BASELINE configs[4]).  160 streams select the first,
+    8 the second; both must equal the oracle (4 distinct streams, the others are row permutations checked against each other
+    through their first copy)."""
+    T = 45
+    base = [synth.bytetrack_stream(20 + s, n_frames=T) for s in range(4)]
+    refs = []
+    for s in range(4):
+        r = _oracle_bt(oracle)
+        refs.append([r.update(base[s][t]) for t in range(T)])
+    for S in (160, 8):
+        dets = np.stack([base[s % 4] for s in range(S)], 1)
+        counts = np.full((T, S), 512, np.int32)
+        eng = api.Engine(_lib.TRACKER_BYTETRACK, S, 1536, 512, **BT_ARGS)
+        assert eng.info()["threads_per_cta"] == (512 if S > 148 else 1024)
+        out, n_out = eng.update(dets, counts, ld_out=640)
+        eng.check()
+        for s in range(S):
+            for t in range(T):
+                assert np.array_equal(out[t, s, :n_out[t, s]], refs[s % 4][t]), (S, s, t)
+        eng.close()
+
+
 # ------------------------------------------------------------------ cosine embedding cost (tcgen05)
 COSINE_ATOL = 2e-5     # 3-term bf16 split + fp32 tensor-core accumulation vs the oracle's sequential fp32 sum
 
