@@ -171,6 +171,22 @@ void orc_ocsort_last_sizes(const OrcOcSort*, int* sizes8);
  * k_previous_obs(delta_t) 5, x 7, P 49] = 76 floats */
 int orc_ocsort_dump(const OrcOcSort*, float* out, int cap_rows);
 
+/* ---------------- DeepOC-SORT (src/trackers/deepocsort.cpp; cmc_off = true, embeddings passed in) -------------- */
+typedef struct OrcDeepOcSort OrcDeepOcSort;
+/* arguments follow DeepOCSort's ctor (include/motcpp/trackers/deepocsort.hpp:95-114) without the ReID / BaseTracker knobs */
+OrcDeepOcSort* orc_deepocsort_create(float det_thresh, int max_age, int max_obs, int min_hits, float iou_threshold, int delta_t,
+                                     float inertia, float w_association_emb, float alpha_fixed_emb, float aw_param, int embedding_off,
+                                     int aw_off, float q_xy_scaling, float q_s_scaling);
+void orc_deepocsort_destroy(OrcDeepOcSort*);
+void orc_deepocsort_reset(OrcDeepOcSort*);
+/* dets (n x 6), embs (n x dim) or NULL (embedding_off); out rows [x1,y1,x2,y2,id,conf,cls,det_ind] */
+int orc_deepocsort_update(OrcDeepOcSort*, const float* dets, int n, const float* embs, int dim, float* out, int out_cap);
+int orc_deepocsort_count(const OrcDeepOcSort*);
+/* [n_dets, n_trks, used_lap, n_first_matches, n_left_dets, n_left_trks, n_rematched, n_spawned] of the last update() */
+void orc_deepocsort_last_sizes(const OrcDeepOcSort*, int* sizes8);
+/* rows of [id, age, hits, hit_streak, time_since_update, conf, cls, det_ind, last_obs 5, velocity 2, x 7, P 49] = 71 floats */
+int orc_deepocsort_dump(const OrcDeepOcSort*, float* out, float* embs, int dim, int cap_rows);
+
 /* ---------------- BoT-SORT (src/trackers/botsort.cpp; cmc_method = "none", embeddings passed in) ------ */
 typedef struct OrcBotSort OrcBotSort;
 /* BotSort-specific ctor arguments (include/motcpp/trackers/botsort.hpp:108-134); BaseTracker knobs are unused by

@@ -122,6 +122,15 @@ def lib() -> C.CDLL:
         L.orc_botsort_last_sizes.argtypes = [C.c_void_p, i32p]
         L.orc_botsort_dump.argtypes = [C.c_void_p, C.c_int, f32p, C.c_void_p, C.c_int, C.c_int]
         L.orc_botsort_dump.restype = C.c_int
+        L.orc_deepocsort_create.argtypes = [C.c_float, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float, C.c_float,
+                                            C.c_float, C.c_int, C.c_int, C.c_float, C.c_float]
+        L.orc_deepocsort_create.restype = C.c_void_p
+        L.orc_deepocsort_destroy.argtypes = [C.c_void_p]
+        L.orc_deepocsort_reset.argtypes = [C.c_void_p]
+        L.orc_deepocsort_update.argtypes = [C.c_void_p, f32p, C.c_int, C.c_void_p, C.c_int, f32p, C.c_int]
+        L.orc_deepocsort_count.argtypes = [C.c_void_p]
+        L.orc_deepocsort_last_sizes.argtypes = [C.c_void_p, i32p]
+        L.orc_deepocsort_dump.argtypes = [C.c_void_p, f32p, C.c_void_p, C.c_int, C.c_int]
         _LIB = L
     return _LIB
 
@@ -540,4 +549,51 @@ class StrongSort:
     def last_sizes(self):
         s = np.zeros(8, np.int32)
         lib().orc_strongsort_last_sizes(self._h, s)
+        return s
+
+
+class DeepOCSort:
+    """Oracle DeepOC-SORT: the constructor arguments that reach the association, reference names and defaults
+    (include/motcpp/trackers/deepocsort.hpp:95-114); cmc_off = True, embeddings passed to update()."""
+
+    def __init__(self, det_thresh=0.3, max_age=30, max_obs=50, min_hits=3, iou_threshold=0.3, delta_t=3, inertia=0.2,
+                 w_association_emb=0.5, alpha_fixed_emb=0.95, aw_param=0.5, embedding_off=False, aw_off=False,
+                 q_xy_scaling=0.01, q_s_scaling=0.0001):
+        self._h = lib().orc_deepocsort_create(det_thresh, max_age, max_obs, min_hits, iou_threshold, delta_t, inertia,
+                                              w_association_emb, alpha_fixed_emb, aw_param, int(embedding_off), int(aw_off),
+                                              q_xy_scaling, q_s_scaling)
+        self._out = np.zeros((8192, 8), np.float32)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_deepocsort_destroy(self._h)
+            self._h = None
+
+    def reset(self):
+        lib().orc_deepocsort_reset(self._h)
+
+    def update(self, dets, embs=None):
+        dets = _f32(dets).reshape(-1, 6)
+        if embs is not None and np.size(embs):
+            embs = _f32(embs).reshape(dets.shape[0], -1)
+            ep, dim = embs.ctypes.data_as(C.c_void_p), embs.shape[1]
+        else:
+            ep, dim = None, 0
+        n = lib().orc_deepocsort_update(self._h, dets, dets.shape[0], ep, dim, self._out, self._out.shape[0])
+        assert n >= 0
+        return self._out[:n].copy()
+
+    def count(self):
+        return lib().orc_deepocsort_count(self._h)
+
+    def dump(self, dim=0):
+        cap = max(1, self.count())
+        buf = np.zeros((cap, 71), np.float32)
+        embs = np.zeros((cap, max(dim, 1)), np.float32)
+        k = lib().orc_deepocsort_dump(self._h, buf, embs.ctypes.data_as(C.c_void_p) if dim else None, dim, cap)
+        return (buf[:k], embs[:k]) if dim else buf[:k]
+
+    def last_sizes(self):
+        s = np.zeros(8, np.int32)
+        lib().orc_deepocsort_last_sizes(self._h, s)
         return s

@@ -330,6 +330,24 @@ def test_strongsort_dense_workload_equals_reference(order):
     _run(order, O.StrongSort(**SS, tie_mode=0), ref, [(dets[t], embs[t]) for t in range(12)])
 
 
+DOC = dict(det_thresh=0.3, max_age=30, max_obs=50, min_hits=3, iou_threshold=0.3, delta_t=3, inertia=0.2, w_association_emb=0.5,
+           alpha_fixed_emb=0.95, aw_param=0.5, embedding_off=False, aw_off=False, q_xy_scaling=0.01, q_s_scaling=0.0001)
+
+
+@pytest.mark.parametrize("order", ["textbook", "eigen"])
+@pytest.mark.parametrize("sid,over,use_embs", [(0, {}, True), (1, {"aw_off": True}, True), (2, {"embedding_off": True}, False),
+                                               (3, {"inertia": 0.9, "min_hits": 1, "max_age": 5, "delta_t": 1}, True)])
+def test_deepocsort_stress_streams_equal_reference(order, sid, over, use_embs):
+    """SURVEY 8f-2.  The reference lists every detection its assignment leaves unmatched twice (deepocsort.cpp:476-478 and
+    :491-495), so two bit-identical tracks are spawned per new object whenever the assignment branch runs: exact ties in
+    nearly every frame, resolved by the reference's LAPJV - which the oracle must follow step for step."""
+    args = {**DOC, **over}
+    frames = _stress_reid(70 + sid, 150)
+    if not use_embs:
+        frames = [(d, None) for d, _ in frames]
+    _run(order, O.DeepOCSort(**args), R.Tracker("deepocsort", [float(v) for v in args.values()], order), frames)
+
+
 def test_reset_and_empty_frames_equal_reference():
     """reset() and empty inputs: BoT-SORT returns early WITHOUT advancing (botsort.cpp:267-269), ByteTrack advances."""
     for kind, orc, params in (("bytetrack", O.ByteTrack(*BT), BT), ("botsort", O.BotSort(**BOT), [float(v) for v in BOT.values()]),

@@ -128,6 +128,22 @@ def main():
         emit("lap_256x512_dense_adversarial", ms, us_per_solve=1e3 * ms[0],
              matches_oracle=bool(np.array_equal(r2c[0].cpu().numpy(), refd[0])), bound="latency")
 
+    # ---------------- the reference's dense LAPJV on the device (tie-exact): one warp (<= 384 rows + columns), one CTA above
+    if want("lapjv"):
+        import oracle_lib as O
+        dets = synth.bytetrack_stream(0, n_frames=2)
+        for (nr, nc, tag) in ((96, 160, "one_warp"), (256, 448, "cta_wide_c2_frame")):
+            cost = O.fuse_score(O.iou_distance(dets[0, :nr, :4], dets[1, :nc, :4]), dets[1, :nc, 4])
+            P = 148
+            costs = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(cost, (P,) + cost.shape))).to(dev).contiguous()
+            r2c = torch.empty((P, nr), dtype=torch.int32, device=dev)
+            c2r = torch.empty((P, nc), dtype=torch.int32, device=dev)
+            ms = timeit(lambda: api.check(lib.mot_lap_jv_batch_device(costs.data_ptr(), nr * nc, P, nr, nc, nc, 0.8, r2c.data_ptr(),
+                                                                      c2r.data_ptr(), st)), iters=3, warm=1)
+            ref = O.linear_assignment(cost, 0.8)
+            emit(f"lapjv_{nr}x{nc}_{tag}", ms, problems=P, us_per_solve_per_sm=1e3 * ms[0], matches_oracle=bool(np.array_equal(r2c[0].cpu().numpy(), ref[0])),
+                 bound="latency (serial shortest augmenting paths; no HBM/tensor roofline)")
+
     # ---------------- OC-SORT association cost (ocm): 4 B written per pair, one fp64 acos per pair
     for (N, M) in ((2048, 2048), (8192, 8192)):
         if not want("ocm") or (args.quick and N > 2048):
