@@ -61,7 +61,8 @@ typedef enum mot_tracker_kind {
     MOT_TRACKER_BYTETRACK = 1,
     MOT_TRACKER_OCSORT = 2,
     MOT_TRACKER_BOTSORT = 3,
-    MOT_TRACKER_STRONGSORT = 4
+    MOT_TRACKER_STRONGSORT = 4,
+    MOT_TRACKER_DEEPOCSORT = 5
 } mot_tracker_kind;
 
 typedef struct mot_engine_config {
@@ -92,6 +93,11 @@ typedef struct mot_engine_config {
     float max_cos_dist, max_iou_dist;
     int n_init, nn_budget;
     float mc_lambda, ema_alpha;
+    /* DeepOCSort ctor (include/motcpp/trackers/deepocsort.hpp:93-117); det_thresh, max_age, min_hits, iou_threshold,
+     * delta_t, inertia, q_*_scaling and emb_dim above are shared.  Camera-motion compensation is not part of the hot
+     * path (the engine behaves as cmc_off = true).  emb_dim may be any positive size; embedding_off = 1 needs none. */
+    float w_association_emb, alpha_fixed_emb, aw_param;
+    int embedding_off, aw_off;
 } mot_engine_config;
 
 typedef struct mot_engine mot_engine;
@@ -126,7 +132,7 @@ int mot_engine_update_host_packed(mot_engine* e, int n_frames, const float* dets
 /* Same contract with DEVICE buffers, asynchronous on `stream`; no host synchronisation. */
 int mot_engine_update_device(mot_engine* e, int n_frames, const float* d_dets, const int* d_n_dets, int ld_dets,
                              float* d_out, int* d_n_out, int ld_out, void* stream);
-/* BoT-SORT engines (created with emb_dim = D > 0): the same calls with the detections' ReID embeddings,
+/* BoT-SORT / StrongSORT / DeepOC-SORT engines (created with emb_dim = D > 0): the same calls with the detections' ReID embeddings,
  * embs [n_frames][S][ld_dets][D] fp32 (row j of a frame belongs to detection j; NULL = no embeddings).  Replaces the
  * `embs` argument of BaseTracker::update (include/motcpp/tracker.hpp:67-69, src/trackers/botsort.cpp:260-283). */
 int mot_engine_update_host_embs(mot_engine* e, int n_frames, const float* dets, const int* n_dets, int ld_dets,
@@ -153,6 +159,9 @@ int mot_engine_stream_header(mot_engine* e, int stream_index, int* hdr16);
  * smoothed features, emb_dim floats per row. */
 int mot_engine_dump_bot(mot_engine* e, int stream_index, int which, float* rows82, float* feats, int cap_rows, int* n_rows);
 int mot_engine_dump_list(mot_engine* e, int stream_index, int which, float* rows78, int cap_rows, int* n_rows);
+/* DeepOC-SORT engines (created with embeddings on): the tracks' unit-length embeddings in track-list order (the row
+ * order of mot_engine_dump_list), emb_dim floats per row. */
+int mot_engine_dump_deep_embs(mot_engine* e, int stream_index, float* embs, int cap_rows, int* n_rows);
 /* StrongSORT engines: the track list (reference order) as rows of [id,state,hits,0,time_since_update,conf,cls,det_ind,
  * has_feat,n_gallery_samples,mean 8,cov 64] (82 floats); feats (nullable) receives the smoothed features. */
 int mot_engine_dump_strong(mot_engine* e, int stream_index, float* rows82, float* feats, int cap_rows, int* n_rows);

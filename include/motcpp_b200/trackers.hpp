@@ -48,6 +48,12 @@ public:
                 for (int c = 0; c < emb_dim_; ++c) embs_rm_[static_cast<size_t>(i) * emb_dim_ + c] = embs(i, c);
             embs_ptr = embs_rm_.data();
         }
+        if (need_embs_) {
+            // DeepOC-SORT with embeddings on: the reference would run its ReID network on a frame without `embs`
+            if (n > 0 && !embs_ptr)
+                throw std::invalid_argument("ReID inference is outside the accelerated hot path: pass embeddings to update()");
+            embs_ptr = embs_rm_.data();
+        }
         int n_out = 0;
         throw_on(mot_engine_update_host_embs(engine_, 1, dets_rm_.data(), &n, max_dets_, embs_ptr, out_rm_.data(), &n_out,
                                              cap_));
@@ -78,6 +84,7 @@ protected:
         max_dets_ = cfg.max_dets > 0 ? cfg.max_dets : 512;
         cap_ = cfg.track_capacity > 0 ? cfg.track_capacity : 1536;
         emb_dim_ = (cfg.kind == MOT_TRACKER_BOTSORT || cfg.kind == MOT_TRACKER_STRONGSORT) ? cfg.emb_dim : 0;
+        if (cfg.kind == MOT_TRACKER_DEEPOCSORT && !cfg.embedding_off) { emb_dim_ = cfg.emb_dim; need_embs_ = true; }
         dets_rm_.resize(static_cast<size_t>(max_dets_) * 6);
         out_rm_.resize(static_cast<size_t>(cap_) * 8);
         embs_rm_.resize(static_cast<size_t>(max_dets_) * static_cast<size_t>(emb_dim_));
@@ -89,6 +96,7 @@ protected:
     mot_engine* engine_ = nullptr;
     int max_dets_ = 512, cap_ = 1536, emb_dim_ = 0;
     bool validate_ = true;
+    bool need_embs_ = false;
     std::vector<float> dets_rm_, out_rm_, embs_rm_;
 };
 
@@ -262,6 +270,45 @@ private:
         c.det_thresh = det_thresh; c.max_age = max_age; c.max_obs = max_obs; c.min_hits = min_hits;
         c.iou_threshold = iou_threshold; c.min_conf = min_conf; c.max_cos_dist = max_cos_dist; c.max_iou_dist = max_iou_dist;
         c.n_init = n_init; c.nn_budget = nn_budget; c.mc_lambda = mc_lambda; c.ema_alpha = ema_alpha; c.emb_dim = emb_dim;
+        return c;
+    }
+};
+
+// motcpp::trackers::DeepOCSort (include/motcpp/trackers/deepocsort.hpp:93-117).  ReID inference and camera-motion
+// compensation are image processing outside the association hot path: reid_weights must be empty (unless embedding_off),
+// cmc_off must be true, and the embeddings are passed to update() (the reference's own `embs` argument,
+// deepocsort.cpp:629-633); emb_dim fixes their width at construction.  The reference lists unmatched detections and
+// tracks twice (:476-481, :485-501): size track_capacity for 2 x the tracks that can be unmatched in one frame.
+class DeepOCSort : public BaseTracker {
+public:
+    DeepOCSort(const std::string& reid_weights = "", bool use_half = false, bool use_gpu = false, float det_thresh = 0.3f,
+               int max_age = 30, int max_obs = 50, int min_hits = 3, float iou_threshold = 0.3f, bool per_class = false,
+               int nr_classes = 80, const std::string& asso_func = "iou", bool is_obb = false, int delta_t = 3,
+               float inertia = 0.2f, float w_association_emb = 0.5f, float alpha_fixed_emb = 0.95f, float aw_param = 0.5f,
+               bool embedding_off = false, bool cmc_off = true, bool aw_off = false, float Q_xy_scaling = 0.01f,
+               float Q_s_scaling = 0.0001f, int emb_dim = 0, int track_capacity = 0, int max_dets = 0, int device = 0)
+        : BaseTracker(make(reid_weights, use_half, use_gpu, det_thresh, max_age, max_obs, min_hits, iou_threshold, per_class,
+                           nr_classes, asso_func, is_obb, delta_t, inertia, w_association_emb, alpha_fixed_emb, aw_param,
+                           embedding_off, cmc_off, aw_off, Q_xy_scaling, Q_s_scaling, emb_dim, track_capacity, max_dets,
+                           device)) {}
+
+private:
+    static mot_engine_config make(const std::string& reid_weights, bool, bool, float det_thresh, int max_age, int max_obs,
+                                  int min_hits, float iou_threshold, bool per_class, int, const std::string& asso_func,
+                                  bool is_obb, int delta_t, float inertia, float w_assoc, float alpha_fixed, float aw_param,
+                                  bool embedding_off, bool cmc_off, bool aw_off, float q_xy, float q_s, int emb_dim,
+                                  int track_capacity, int max_dets, int device) {
+        only_iou_aabb(asso_func, per_class, is_obb);
+        if (!cmc_off) throw std::invalid_argument("camera-motion compensation is outside the accelerated hot path (cmc_off must be true)");
+        if (!reid_weights.empty() && !embedding_off)
+            throw std::invalid_argument("ReID inference is outside the accelerated hot path: pass embeddings to update()");
+        mot_engine_config c;
+        throw_on(mot_engine_default_config(MOT_TRACKER_DEEPOCSORT, &c));
+        c.n_streams = 1; c.track_capacity = track_capacity; c.max_dets = max_dets; c.device = device;
+        c.det_thresh = det_thresh; c.max_age = max_age; c.max_obs = max_obs; c.min_hits = min_hits;
+        c.iou_threshold = iou_threshold; c.delta_t = delta_t; c.inertia = inertia; c.w_association_emb = w_assoc;
+        c.alpha_fixed_emb = alpha_fixed; c.aw_param = aw_param; c.embedding_off = embedding_off ? 1 : 0;
+        c.aw_off = aw_off ? 1 : 0; c.q_xy_scaling = q_xy; c.q_s_scaling = q_s; c.emb_dim = embedding_off ? 0 : emb_dim;
         return c;
     }
 };

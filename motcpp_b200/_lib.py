@@ -16,7 +16,7 @@ MOT_ERR_CAPACITY = 4
 MOT_ERR_NUMERIC = 5
 MOT_ERR_UNSUPPORTED = 6
 
-TRACKER_SORT, TRACKER_BYTETRACK, TRACKER_OCSORT, TRACKER_BOTSORT, TRACKER_STRONGSORT = 0, 1, 2, 3, 4
+TRACKER_SORT, TRACKER_BYTETRACK, TRACKER_OCSORT, TRACKER_BOTSORT, TRACKER_STRONGSORT, TRACKER_DEEPOCSORT = 0, 1, 2, 3, 4, 5
 KF_XYAH, KF_XYSR, KF_XYWH = 0, 1, 2
 
 
@@ -41,6 +41,8 @@ class EngineConfig(C.Structure):
         ("fuse_first_associate", C.c_int), ("with_reid", C.c_int), ("emb_dim", C.c_int),
         ("max_cos_dist", C.c_float), ("max_iou_dist", C.c_float), ("n_init", C.c_int), ("nn_budget", C.c_int),
         ("mc_lambda", C.c_float), ("ema_alpha", C.c_float),
+        ("w_association_emb", C.c_float), ("alpha_fixed_emb", C.c_float), ("aw_param", C.c_float),
+        ("embedding_off", C.c_int), ("aw_off", C.c_int),
     ]
 
 
@@ -73,6 +75,7 @@ SYMBOLS = {
     "mot_engine_check": (_I, [_VP, _VP]),
     "mot_engine_stream_header": (_I, [_VP, _I, _VP]),
     "mot_engine_dump_list": (_I, [_VP, _I, _I, _VP, _I, C.POINTER(_I)]),
+    "mot_engine_dump_deep_embs": (_I, [_VP, _I, _VP, _I, C.POINTER(_I)]),
     "mot_engine_info": (_I, [_VP, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "mot_kf_initiate": (_I, [_I, _VP, _VP, _LL, _VP]),
     "mot_kf_predict": (_I, [_I, _VP, _VP, _LL, _F, _F, _VP]),

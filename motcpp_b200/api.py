@@ -565,12 +565,21 @@ class Engine:
         [id, age, hits, hit_streak, time_since_update, conf, cls, det_ind, last_obs 5, velocity 2, x 7, P 49, pad]."""
         hdr = self.header(stream)
         n = int(hdr[0] if which == 0 else hdr[1])
-        if self.cfg.kind == _lib.TRACKER_OCSORT and which != 0:
+        if self.cfg.kind in (_lib.TRACKER_OCSORT, _lib.TRACKER_DEEPOCSORT) and which != 0:
             n = 0
         buf = np.zeros((max(n, 1), 78), np.float32)
         k = C.c_int()
         check(load().mot_engine_dump_list(self._h, stream, which, buf.ctypes.data, max(n, 1), C.byref(k)))
         return buf[:k.value]
+
+    def dump_deep_embs(self, stream: int) -> np.ndarray:
+        """DeepOC-SORT engines: the tracks' unit-length embeddings, in the row order of dump(stream)."""
+        n = max(int(self.header(stream)[0]), 1)
+        dim = int(self.cfg.emb_dim)
+        embs = np.zeros((n, max(dim, 1)), np.float32)
+        k = C.c_int()
+        check(load().mot_engine_dump_deep_embs(self._h, stream, embs.ctypes.data, n, C.byref(k)))
+        return embs[:k.value, :dim]
 
     def dump_bot(self, stream: int, which: int, with_feats: bool = False):
         """BoT-SORT engines: rows of [id, state, is_activated, frame_id, start_frame, tracklet_len, conf, cls, det_ind,
@@ -738,6 +747,99 @@ class OCSort:
         self._engine.update(self._dets, np.array([[n]], np.int32), self._out, self._n_out)
         self._engine.check()
         return self._out[0, 0, :int(self._n_out[0, 0])].copy()
+
+
+class DeepOCSort:
+    """motcpp::trackers::DeepOCSort with the reference's positional constructor
+    (include/motcpp/trackers/deepocsort.hpp:93-117).  The ReID network and camera-motion compensation are image
+    processing outside the accelerated path: embeddings are passed to update() (the reference's `embs` argument,
+    src/trackers/deepocsort.cpp:629-633) and cmc_off must be True.  With embedding_off=True no embeddings are needed
+    (the reference substitutes a column of ones, :624-626, which never reaches the cost).  One stream; for many streams
+    use Engine(TRACKER_DEEPOCSORT, ...).  The reference lists unmatched detections and tracks twice (:476-481, :485-501):
+    size track_capacity for 2 x the tracks that can be unmatched in one frame."""
+
+    def __init__(self, reid_weights="", use_half=False, use_gpu=False, det_thresh=0.3, max_age=30, max_obs=50,
+                 min_hits=3, iou_threshold=0.3, per_class=False, nr_classes=80, asso_func="iou", is_obb=False,
+                 delta_t=3, inertia=0.2, w_association_emb=0.5, alpha_fixed_emb=0.95, aw_param=0.5, embedding_off=False,
+                 cmc_off=True, aw_off=False, Q_xy_scaling=0.01, Q_s_scaling=0.0001, emb_dim=0, track_capacity=1536,
+                 max_dets=512, device=0):
+        if not cmc_off:
+            raise ValueError("camera-motion compensation is outside the accelerated hot path: pass cmc_off=True")
+        if reid_weights and not embedding_off:
+            raise ValueError("ReID inference is outside the accelerated hot path: pass embeddings to update()")
+        if asso_func != "iou" or per_class or is_obb:
+            raise ValueError("only asso_func=\"iou\", per_class=False, is_obb=False are on the accelerated path")
+        self._off = bool(embedding_off)
+        self._make = lambda dim: Engine(_lib.TRACKER_DEEPOCSORT, 1, track_capacity, max_dets, device, det_thresh=det_thresh,
+                                        max_age=max_age, max_obs=max_obs, min_hits=min_hits, iou_threshold=iou_threshold,
+                                        delta_t=delta_t, inertia=inertia, w_association_emb=w_association_emb,
+                                        alpha_fixed_emb=alpha_fixed_emb, aw_param=aw_param, embedding_off=int(self._off),
+                                        aw_off=int(bool(aw_off)), q_xy_scaling=Q_xy_scaling, q_s_scaling=Q_s_scaling,
+                                        emb_dim=dim)
+        self._engine = None
+        self._dim = 0
+        self._pending_empty = 0          # empty frames seen before the embedding dimension is known
+        if self._off or emb_dim > 0:
+            self._build(0 if self._off else emb_dim)
+
+    def _build(self, emb_dim):
+        self._engine = self._make(emb_dim)
+        self._dim = emb_dim
+        self._max_dets = self._engine.cfg.max_dets
+        self._cap = self._engine.cfg.track_capacity
+        self._dets = np.zeros((1, 1, self._max_dets, 6), np.float32)
+        self._embs = np.zeros((1, 1, self._max_dets, emb_dim), np.float32) if emb_dim else None
+        self._out = np.empty((1, 1, self._cap, 8), np.float32)
+        self._n_out = np.empty((1, 1), np.int32)
+
+    def reset(self):
+        self._pending_empty = 0
+        if self._engine is not None:
+            self._engine.reset()
+
+    def _step(self, n):
+        self._engine.update(self._dets, np.array([[n]], np.int32), self._out, self._n_out, embs=self._embs)
+        self._engine.check()
+        return self._out[0, 0, :int(self._n_out[0, 0])].copy()
+
+    def update(self, dets, img, embs=None) -> np.ndarray:
+        dets = np.asarray(dets, np.float32)
+        if dets.ndim != 2:
+            dets = dets.reshape(0, 6) if dets.size == 0 else dets
+        # BaseTracker::check_inputs(dets, img, embs) (src/tracker.cpp:108-125)
+        if dets.shape[0] > 0 and dets.shape[1] not in (6, 7):
+            raise ValueError("Detections must have 6 (AABB) or 7 (OBB) columns")
+        if _Image(img).empty():
+            raise ValueError("Image cannot be empty")
+        n = dets.shape[0]
+        have = embs is not None and np.size(embs) > 0
+        if have and np.shape(embs)[0] != n:
+            raise ValueError("Detections and embeddings must have same number of rows")
+        if n > 0 and dets.shape[1] == 7:
+            raise ValueError("OBB detections are outside the accelerated hot path")
+        if not self._off:
+            if n > 0 and not have:
+                raise ValueError("ReID inference is outside the accelerated hot path: pass embeddings to update()")
+            if have:
+                embs = np.asarray(embs, np.float32)
+                if embs.ndim != 2:
+                    raise ValueError("Detections and embeddings must have same number of rows")
+                if self._engine is None:
+                    self._build(int(embs.shape[1]))
+                    for _ in range(self._pending_empty):       # the empty frames that came first only advanced the clock
+                        self._step(0)
+                    self._pending_empty = 0
+                elif embs.shape[1] != self._dim:
+                    raise ValueError(f"embeddings have {embs.shape[1]} columns but the tracker was built for emb_dim={self._dim}")
+            elif self._engine is None:
+                self._pending_empty += 1                       # no tracks yet: frame_count_++ and an empty result (:655-668)
+                return np.zeros((0, 8), np.float32)
+        if n > self._max_dets:
+            raise ValueError(f"{n} detections exceed max_dets={self._max_dets}")
+        self._dets[0, 0, :n] = dets[:, :6] if n else 0
+        if not self._off and n:
+            self._embs[0, 0, :n] = embs
+        return self._step(n)
 
 
 class BotSort:

@@ -79,6 +79,7 @@ struct mot_engine {
     mot::SortLayout sort_layout;   // SORT slab layout (kind == SORT)
     mot::OcLayout oc_layout;       // OC-SORT slab layout (kind == OCSORT)
     mot::OcParams ocp;
+    mot::DeepLayout deep_layout;   // DeepOC-SORT appearance state behind every OC-SORT slab (kind == DEEPOCSORT)
     mot::BotLayout bot_layout;     // BoT-SORT slab layout (kind == BOTSORT; feature dimension is a run-time size)
     mot::BotParams botp;
     mot::SsLayout ss_layout;       // StrongSORT slab layout (kind == STRONGSORT; dim and gallery budget are run-time sizes)
@@ -114,8 +115,8 @@ static int engine_reset_impl(mot_engine* e, int keep_ids) {
     const int grid = std::min(e->cfg.n_streams, 4096);
     if (e->cfg.kind == MOT_TRACKER_SORT)
         mot::sort_reset_kernel<<<grid, 256, 0, e->streams[0]>>>(e->d_state, e->sort_layout, e->cfg.n_streams, keep_ids);
-    else if (e->cfg.kind == MOT_TRACKER_OCSORT)
-        mot::ocsort_reset_kernel<<<grid, 256, 0, e->streams[0]>>>(e->d_state, e->oc_layout, e->cfg.n_streams, keep_ids);
+    else if (e->cfg.kind == MOT_TRACKER_OCSORT || e->cfg.kind == MOT_TRACKER_DEEPOCSORT)
+        mot::ocsort_reset_kernel<<<grid, 256, 0, e->streams[0]>>>(e->d_state, e->oc_layout, e->stride, e->cfg.n_streams, keep_ids);
     else if (e->cfg.kind == MOT_TRACKER_BOTSORT)
         mot::botsort_reset_kernel<<<grid, 256, 0, e->streams[0]>>>(e->d_state, e->bot_layout, e->cfg.n_streams);
     else if (e->cfg.kind == MOT_TRACKER_STRONGSORT)
@@ -162,12 +163,14 @@ static void engine_launch(mot_engine* e, int T, const float* dets, const int* nd
         a.T = T; a.S = e->cfg.n_streams; a.ld_dets = ld_dets; a.ld_out = ld_out; a.s_begin = s0; a.s_end = s1;
         a.p = e->sortp;
         mot::sort_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
-    } else if (e->cfg.kind == MOT_TRACKER_OCSORT) {
+    } else if (e->cfg.kind == MOT_TRACKER_OCSORT || e->cfg.kind == MOT_TRACKER_DEEPOCSORT) {
         mot::OcArgs a{};
         a.state = e->d_state; a.dets = dets; a.n_dets = nd; a.out = out; a.n_out = nout;
         a.T = T; a.S = e->cfg.n_streams; a.ld_dets = ld_dets; a.ld_out = ld_out; a.s_begin = s0; a.s_end = s1;
         a.p = e->ocp;
-        mot::oc_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
+        a.embs = embs; a.dim = e->deep_layout.dim; a.stride = e->stride;
+        if (e->cfg.kind == MOT_TRACKER_DEEPOCSORT) mot::deepoc_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
+        else mot::oc_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
     } else {
         mot::BtArgs a = make_args(e, T, dets, nd, ld_dets, out, nout, ld_out, s0, s1);
         mot::bt_launch(e->shape, s1 - s0, e->smem_bytes, st, a, e->threads);
@@ -249,12 +252,15 @@ int mot_engine_default_config(int kind, mot_engine_config* c) {
     c->emb_dim = 0;
     // StrongSORT (strongsort.hpp:287-305)
     c->max_cos_dist = 0.2f; c->max_iou_dist = 0.7f; c->n_init = 3; c->nn_budget = 100; c->mc_lambda = 0.98f; c->ema_alpha = 0.9f;
+    // DeepOCSort (deepocsort.hpp:93-117)
+    c->w_association_emb = 0.5f; c->alpha_fixed_emb = 0.95f; c->aw_param = 0.5f; c->embedding_off = 0; c->aw_off = 0;
     switch (kind) {
         case MOT_TRACKER_SORT: c->max_age = 1; break;             // sort.hpp:70
         case MOT_TRACKER_BYTETRACK: break;
         case MOT_TRACKER_OCSORT: c->det_thresh = 0.2f; break;
         case MOT_TRACKER_BOTSORT: c->track_buffer = 30; break;
         case MOT_TRACKER_STRONGSORT: break;
+        case MOT_TRACKER_DEEPOCSORT: break;
         default: return fail(MOT_ERR_INVALID_ARGUMENT, "unknown tracker kind %d", kind);
     }
     return MOT_OK;
@@ -263,15 +269,17 @@ int mot_engine_default_config(int kind, mot_engine_config* c) {
 int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     if (!cfg || !out) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
     *out = nullptr;
-    if (cfg->kind < MOT_TRACKER_SORT || cfg->kind > MOT_TRACKER_STRONGSORT)
+    if (cfg->kind < MOT_TRACKER_SORT || cfg->kind > MOT_TRACKER_DEEPOCSORT)
         return fail(MOT_ERR_INVALID_ARGUMENT, "unknown tracker kind %d", cfg->kind);
     if (cfg->kind == MOT_TRACKER_STRONGSORT && (cfg->nn_budget < 1 || cfg->nn_budget > 4096))
         return fail(MOT_ERR_UNSUPPORTED, "nn_budget %d is outside 1..4096 (gallery ring size; the reference's unlimited budget is not supported)", cfg->nn_budget);
     if ((cfg->kind == MOT_TRACKER_BOTSORT || cfg->kind == MOT_TRACKER_STRONGSORT) && (cfg->emb_dim < 0 || (cfg->emb_dim & 3)))
         return fail(MOT_ERR_INVALID_ARGUMENT, "emb_dim %d must be a non-negative multiple of 4", cfg->emb_dim);
     if (cfg->n_streams <= 0) return fail(MOT_ERR_INVALID_ARGUMENT, "n_streams must be positive");
-    if (cfg->kind == MOT_TRACKER_OCSORT && (cfg->delta_t < 1 || cfg->delta_t > mot::kOcRing))
-        return fail(MOT_ERR_UNSUPPORTED, "delta_t %d is outside 1..%d (observation ring size)", cfg->delta_t, mot::kOcRing);
+    if (cfg->kind == MOT_TRACKER_DEEPOCSORT && !cfg->embedding_off && cfg->emb_dim < 1)
+        return fail(MOT_ERR_INVALID_ARGUMENT, "a DeepOC-SORT engine needs emb_dim >= 1 (or embedding_off = 1)");
+    if ((cfg->kind == MOT_TRACKER_OCSORT || cfg->kind == MOT_TRACKER_DEEPOCSORT) && (cfg->delta_t < 1 || cfg->delta_t > mot::kOcRing - 1))
+        return fail(MOT_ERR_UNSUPPORTED, "delta_t %d is outside 1..%d (the observation ring keeps the current age and the %d before it)", cfg->delta_t, mot::kOcRing - 1, mot::kOcRing - 1);
     if (int rc = require_device()) return rc;
     int prev_device = 0;
     MOT_CUDA(cudaGetDevice(&prev_device));
@@ -282,7 +290,8 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
         mot_engine** e; int dev;
         ~Guard() { if (*e) mot_engine_destroy(*e); cudaSetDevice(dev); }
     } guard{&e, prev_device};
-    const bool is_sort = cfg->kind == MOT_TRACKER_SORT, is_oc = cfg->kind == MOT_TRACKER_OCSORT;
+    const bool is_deep = cfg->kind == MOT_TRACKER_DEEPOCSORT;
+    const bool is_sort = cfg->kind == MOT_TRACKER_SORT, is_oc = cfg->kind == MOT_TRACKER_OCSORT || is_deep;   // same kernel text and shapes
     const bool is_bot = cfg->kind == MOT_TRACKER_BOTSORT, is_ss = cfg->kind == MOT_TRACKER_STRONGSORT;
     if (e->cfg.track_capacity <= 0) e->cfg.track_capacity = 1536;
     if (e->cfg.max_dets <= 0) e->cfg.max_dets = 512;
@@ -336,7 +345,13 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     e->ocp.max_age = cfg->max_age;
     e->ocp.min_hits = cfg->min_hits;
     e->ocp.delta_t = cfg->delta_t;
-    e->ocp.use_byte = cfg->use_byte;
+    e->ocp.use_byte = is_deep ? 0 : cfg->use_byte;                               // DeepOC-SORT has no BYTE pass
+    e->ocp.w_assoc_emb = cfg->w_association_emb;
+    e->ocp.alpha_fixed_emb = cfg->alpha_fixed_emb;
+    e->ocp.aw_param = cfg->aw_param;
+    e->ocp.aw_off = cfg->aw_off;
+    e->ocp.embedding_off = cfg->embedding_off;
+    e->deep_layout = mot::DeepLayout::make(e->cfg.track_capacity, e->cfg.max_dets, cfg->embedding_off ? 0 : cfg->emb_dim);
     e->bot_layout = mot::BotLayout::make(e->cfg.track_capacity, e->cfg.max_dets, cfg->emb_dim);
     e->botp.track_high_thresh = cfg->track_high_thresh;
     e->botp.track_low_thresh = cfg->track_low_thresh;
@@ -352,7 +367,7 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     e->ssp.min_conf = cfg->min_conf; e->ssp.max_cos_dist = cfg->max_cos_dist; e->ssp.max_iou_dist = cfg->max_iou_dist;
     e->ssp.mc_lambda = cfg->mc_lambda; e->ssp.ema_alpha = cfg->ema_alpha; e->ssp.max_age = cfg->max_age;
     e->ssp.n_init = cfg->n_init; e->ssp.budget = std::max(1, cfg->nn_budget); e->ssp.dim = cfg->emb_dim;
-    e->stride = is_ss ? e->ss_layout.stride : is_sort ? e->sort_layout.stride : (is_oc ? e->oc_layout.stride : (is_bot ? e->bot_layout.stride : e->layout.stride));
+    e->stride = is_ss ? e->ss_layout.stride : is_sort ? e->sort_layout.stride : (is_oc ? e->oc_layout.stride + (is_deep ? e->deep_layout.bytes : 0) : (is_bot ? e->bot_layout.stride : e->layout.stride));
     e->threads = is_ss ? mot::kSsThreads : is_sort ? mot::kSortThreads : (is_oc ? mot::kOcThreads : (is_bot ? mot::kBotThreads : mot::bt_threads(e->shape, cfg->n_streams, sm_count())));
     e->smem_bytes = is_ss ? mot::ss_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap) : is_sort ? mot::sort_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap)
                   : is_oc   ? mot::oc_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap)
@@ -366,7 +381,7 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
                     need, max_optin);
     }
     MOT_CUDA(is_ss ? mot::ss_prepare(e->shape, e->smem_bytes) : is_sort ? mot::sort_prepare(e->shape, e->smem_bytes)
-                     : (is_oc ? mot::oc_prepare(e->shape, e->smem_bytes)
+                     : (is_oc ? (is_deep ? mot::deepoc_prepare(e->shape, e->smem_bytes) : mot::oc_prepare(e->shape, e->smem_bytes))
                               : (is_bot ? mot::bot_prepare(e->shape, e->smem_bytes) : mot::bt_prepare(e->shape, e->smem_bytes, e->threads))));
     e->n_chunks = cfg->n_chunks > 0 ? std::min(cfg->n_chunks, kMaxChunks) : (cfg->n_streams >= 128 ? 8 : (cfg->n_streams >= 32 ? 4 : 1));
     e->n_chunks = std::min(e->n_chunks, cfg->n_streams);
@@ -416,8 +431,10 @@ int mot_engine_update_device_embs(mot_engine* e, int T, const float* d_dets, con
     if (!e || !d_dets || !d_n_dets || !d_out || !d_n_out) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
     if (T <= 0 || ld_dets <= 0 || ld_out <= 0) return fail(MOT_ERR_INVALID_ARGUMENT, "non-positive size");
     if ((ld_out * 8 * sizeof(float)) % 16 != 0 || (((size_t)d_out) & 15)) return fail(MOT_ERR_INVALID_ARGUMENT, "out must be 16-byte aligned");
-    if (d_embs && ((e->cfg.kind != MOT_TRACKER_BOTSORT && e->cfg.kind != MOT_TRACKER_STRONGSORT) || e->cfg.emb_dim <= 0))
-        return fail(MOT_ERR_INVALID_ARGUMENT, "embeddings need a BoT-SORT / StrongSORT engine created with emb_dim > 0");
+    if (d_embs && ((e->cfg.kind != MOT_TRACKER_BOTSORT && e->cfg.kind != MOT_TRACKER_STRONGSORT && e->cfg.kind != MOT_TRACKER_DEEPOCSORT) || e->cfg.emb_dim <= 0))
+        return fail(MOT_ERR_INVALID_ARGUMENT, "embeddings need a BoT-SORT / StrongSORT / DeepOC-SORT engine created with emb_dim > 0");
+    if (!d_embs && e->cfg.kind == MOT_TRACKER_DEEPOCSORT && !e->cfg.embedding_off)
+        return fail(MOT_ERR_INVALID_ARGUMENT, "a DeepOC-SORT engine with embedding_off = 0 needs the detections' embeddings (the reference would run its ReID network here)");
     if (d_embs && (((size_t)d_embs) & 15)) return fail(MOT_ERR_INVALID_ARGUMENT, "embs must be 16-byte aligned");
     MOT_CUDA(cudaSetDevice(e->cfg.device));          // a NULL stream must mean the ENGINE's device
     const int S = e->cfg.n_streams;
@@ -435,8 +452,10 @@ int mot_engine_update_host_embs(mot_engine* e, int T, const float* dets, const i
                                 float* out, int* n_out, int ld_out) {
     if (!e || !dets || !n_dets || !out || !n_out) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
     if (T <= 0 || ld_dets <= 0 || ld_out <= 0) return fail(MOT_ERR_INVALID_ARGUMENT, "non-positive size");
-    if (embs && ((e->cfg.kind != MOT_TRACKER_BOTSORT && e->cfg.kind != MOT_TRACKER_STRONGSORT) || e->cfg.emb_dim <= 0))
-        return fail(MOT_ERR_INVALID_ARGUMENT, "embeddings need a BoT-SORT / StrongSORT engine created with emb_dim > 0");
+    if (embs && ((e->cfg.kind != MOT_TRACKER_BOTSORT && e->cfg.kind != MOT_TRACKER_STRONGSORT && e->cfg.kind != MOT_TRACKER_DEEPOCSORT) || e->cfg.emb_dim <= 0))
+        return fail(MOT_ERR_INVALID_ARGUMENT, "embeddings need a BoT-SORT / StrongSORT / DeepOC-SORT engine created with emb_dim > 0");
+    if (!embs && e->cfg.kind == MOT_TRACKER_DEEPOCSORT && !e->cfg.embedding_off)
+        return fail(MOT_ERR_INVALID_ARGUMENT, "a DeepOC-SORT engine with embedding_off = 0 needs the detections' embeddings (the reference would run its ReID network here)");
     MOT_CUDA(cudaSetDevice(e->cfg.device));
     const int S = e->cfg.n_streams;
     const size_t TS = (size_t)T * S;
@@ -506,6 +525,8 @@ int mot_engine_update_host_packed(mot_engine* e, int T, const float* dets, const
     if (T <= 0 || ld_dets <= 0 || max_rows <= 0 || out_cap_rows < 0) return fail(MOT_ERR_INVALID_ARGUMENT, "non-positive size");
     if (e->cfg.kind == MOT_TRACKER_BOTSORT || e->cfg.kind == MOT_TRACKER_STRONGSORT)
         if (e->cfg.emb_dim > 0) return fail(MOT_ERR_UNSUPPORTED, "the packed host path carries no embeddings; use mot_engine_update_host_embs");
+    if (e->cfg.kind == MOT_TRACKER_DEEPOCSORT && !e->cfg.embedding_off)
+        return fail(MOT_ERR_UNSUPPORTED, "the packed host path carries no embeddings; use mot_engine_update_host_embs");
     MOT_CUDA(cudaSetDevice(e->cfg.device));
     const int S = e->cfg.n_streams, ld_out = max_rows;
     const size_t TS = (size_t)T * S;
@@ -699,15 +720,15 @@ int mot_engine_stream_header(mot_engine* e, int s, int* hdr16) {
 
 int mot_engine_dump_list(mot_engine* e, int s, int which, float* rows, int cap_rows, int* n_rows) {
     if (!e || !rows || !n_rows || s < 0 || s >= e->cfg.n_streams) return fail(MOT_ERR_INVALID_ARGUMENT, "bad argument");
-    if (e->cfg.kind != MOT_TRACKER_BYTETRACK && e->cfg.kind != MOT_TRACKER_OCSORT)
-        return fail(MOT_ERR_UNSUPPORTED, "list dumps exist for ByteTrack and OC-SORT engines only");
+    if (e->cfg.kind != MOT_TRACKER_BYTETRACK && e->cfg.kind != MOT_TRACKER_OCSORT && e->cfg.kind != MOT_TRACKER_DEEPOCSORT)
+        return fail(MOT_ERR_UNSUPPORTED, "list dumps exist for ByteTrack, OC-SORT and DeepOC-SORT engines only");
     MOT_CUDA(cudaSetDevice(e->cfg.device));
     MOT_CUDA(cudaDeviceSynchronize());
-    if (e->cfg.kind == MOT_TRACKER_OCSORT) {
+    if (e->cfg.kind == MOT_TRACKER_OCSORT || e->cfg.kind == MOT_TRACKER_DEEPOCSORT) {
         // rows of [id, age, hits, hit_streak, time_since_update, conf, cls, det_ind, last_obs 5, velocity 2, x 7, P 49, pad 7]
         const mot::OcLayout& L = e->oc_layout;
         std::vector<unsigned char> slab(L.off_ocm);
-        MOT_CUDA(cudaMemcpy(slab.data(), e->d_state + (size_t)s * L.stride, slab.size(), cudaMemcpyDeviceToHost));
+        MOT_CUDA(cudaMemcpy(slab.data(), e->d_state + (size_t)s * e->stride, slab.size(), cudaMemcpyDeviceToHost));
         const int* hdr = (const int*)slab.data();
         const unsigned short* list = (const unsigned short*)(slab.data() + L.off_lists);
         const int* m = (const int*)(slab.data() + L.off_meta);
@@ -745,6 +766,27 @@ int mot_engine_dump_list(mot_engine* e, int s, int which, float* rows, int cap_r
         o[3] = (float)meta[2 * L.cap + slot]; o[4] = (float)meta[3 * L.cap + slot]; o[5] = (float)meta[L.cap + slot];
         mot::kfb_expand(recs + (size_t)slot * mot::kBtRecFloats, o + 6);     // compact record -> [mean 8 | cov 8x8]
     }
+    *n_rows = k;
+    return MOT_OK;
+}
+
+int mot_engine_dump_deep_embs(mot_engine* e, int s, float* embs, int cap_rows, int* n_rows) {
+    if (!e || !embs || !n_rows || s < 0 || s >= e->cfg.n_streams) return fail(MOT_ERR_INVALID_ARGUMENT, "bad argument");
+    if (e->cfg.kind != MOT_TRACKER_DEEPOCSORT || e->deep_layout.dim <= 0)
+        return fail(MOT_ERR_UNSUPPORTED, "not a DeepOC-SORT engine with embeddings");
+    MOT_CUDA(cudaSetDevice(e->cfg.device));
+    MOT_CUDA(cudaDeviceSynchronize());
+    const mot::OcLayout& L = e->oc_layout;
+    const int dim = e->deep_layout.dim;
+    const unsigned char* base = e->d_state + (size_t)s * e->stride;
+    std::vector<unsigned char> head(L.off_meta);
+    MOT_CUDA(cudaMemcpy(head.data(), base, head.size(), cudaMemcpyDeviceToHost));
+    const int n = ((const int*)head.data())[mot::kOHdrTracks];
+    const unsigned short* list = (const unsigned short*)(head.data() + L.off_lists);
+    const float* d_emb = (const float*)(base + L.stride + e->deep_layout.off_emb);
+    int k = 0;
+    for (; k < n && k < cap_rows; ++k)
+        MOT_CUDA(cudaMemcpy(embs + (size_t)k * dim, d_emb + (size_t)list[k] * dim, sizeof(float) * dim, cudaMemcpyDeviceToHost));
     *n_rows = k;
     return MOT_OK;
 }

@@ -1,4 +1,4 @@
-// engine_launch.h - host-side launchers of the five fused frame-step kernels.  Each family is instantiated in its own
+// engine_launch.h - host-side launchers of the six fused frame-step kernels.  Each family is instantiated in its own
 // translation unit (engine_<name>.cu) so that the library builds in parallel; cabi.cu only sees these declarations.
 #pragma once
 #include <cuda_runtime.h>
@@ -15,6 +15,8 @@ cudaError_t sort_prepare(int shape, size_t smem);
 void sort_launch(int shape, int grid, size_t smem, cudaStream_t st, const SortArgs& a);
 cudaError_t oc_prepare(int shape, size_t smem);
 void oc_launch(int shape, int grid, size_t smem, cudaStream_t st, const OcArgs& a);
+cudaError_t deepoc_prepare(int shape, size_t smem);
+void deepoc_launch(int shape, int grid, size_t smem, cudaStream_t st, const OcArgs& a);
 cudaError_t bot_prepare(int shape, size_t smem);
 void bot_launch(int shape, int grid, size_t smem, cudaStream_t st, const BotArgs& a);
 cudaError_t ss_prepare(int shape, size_t smem);

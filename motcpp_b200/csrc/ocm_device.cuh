@@ -131,8 +131,8 @@ struct OcmCost {
     // infinitesimal that prefers the HIGHER column (what LAPJV's right-to-left column reduction yields in most
     // cases) - DESIGN.md "Ties".
     __device__ __forceinline__ double pair_bias(int i, int j) const { return twin_bias(i, j); }
-    __device__ __forceinline__ bool is_candidate(const Row& r, int i, int j, float thresh) const {
-        const float v = iou(r, j);
+    // the "trivial one-to-one" tallies for a pair with IoU v
+    __device__ __forceinline__ void tally(int i, int j, float v) const {
         if (v > iou_thr) {
             const unsigned rb = 1u << (i & 31), cb = 1u << (j & 31);
             const unsigned ro = atomicOr(&row_bits[i >> 5], rb), co = atomicOr(&col_bits[j >> 5], cb);
@@ -140,6 +140,59 @@ struct OcmCost {
             flags[0] = 1;
             if ((ro & rb) || (co & cb)) flags[1] = 1;
         }
+    }
+    __device__ __forceinline__ bool is_candidate(const Row& r, int i, int j, float thresh) const {
+        const float v = iou(r, j);
+        tally(i, j, v);
+        return cost_from_iou(r, j, v) <= thresh;
+    }
+};
+
+// DeepOC-SORT's first association (deepocsort.cpp:348-504): OcmCost plus the appearance term,
+//   cost = -((iou + angle cost * score) + w(i, j) * emb(i, j)),  emb = detection . track embedding where iou > 0, else 0 (:421-423),
+//   w = w_assoc_emb x adaptive row weight x adaptive column weight (compute_aw_max_metric :294-345) or plain w_assoc_emb (aw_off).
+// The products and weights are prepared per frame by deep_embedding_terms() (ocsort_kernel.cuh).
+struct DeepOcmCost {
+    static constexpr bool kWarpPerRow = false;
+    static constexpr bool kGrid = true;
+    OcmCost base;
+    const float* dense;               // [n][m] products, valid only where iou > 0
+    const float* row_w;               // [n] w_assoc_emb x row weight, 0 for an all-zero row (mode 1)
+    const float* col_w;               // [m] column weight (mode 1, n >= 2)
+    const unsigned char* col_z;       // [m] column maximum is 0 (mode 1, n >= 2)
+    int m;
+    int mode;                         // 0: no appearance term (embedding_off), 1: adaptive weights, 2: w_assoc_emb only (aw_off)
+    float w_assoc;
+    bool cols_weighted;               // n >= 2 (:324)
+    bool prune;
+    struct Row : OcmCost::Row { int i; float rw; };
+    __device__ __forceinline__ Row row(int i) const {
+        Row r;
+        static_cast<OcmCost::Row&>(r) = base.row(i);
+        r.i = i;
+        r.rw = (mode == 1) ? row_w[i] : w_assoc;
+        return r;
+    }
+    __device__ __forceinline__ float4 col_box(int j) const { return base.col_box(j); }
+    __device__ __forceinline__ bool reject(const Row& r, int j) const { return base.reject(r, j); }
+    __device__ __forceinline__ float iou(const Row& r, int j) const { return base.iou(r, j); }
+    __device__ __forceinline__ float emb_term(const Row& r, int j, float v) const {
+        if (mode == 0 || v <= 0.0f) return 0.0f;
+        float w = r.rw;
+        if (mode == 1 && cols_weighted) w = col_z[j] ? 0.0f : xmul(w, col_w[j]);
+        return xmul(w, dense[(size_t)r.i * m + j]);
+    }
+    __device__ __forceinline__ float cost_from_iou(const Row& r, int j, float v) const {
+        float t = v;                                   // + (0 * angle * inertia * score) adds exactly +-0
+        if (base.valid[j] & 1) t = xadd(v, xmul(ocm_angle_cost(r.cx, r.cy, base.ocm[j], 1.0f, base.inertia), r.score));
+        return -xadd(t, emb_term(r, j, v));
+    }
+    __device__ __forceinline__ float cost(const Row& r, int j) const { return cost_from_iou(r, j, iou(r, j)); }
+    __device__ __forceinline__ float pair(int i, int j) const { return cost(row(i), j); }
+    __device__ __forceinline__ double pair_bias(int i, int j) const { return twin_bias(i, j); }
+    __device__ __forceinline__ bool is_candidate(const Row& r, int i, int j, float thresh) const {
+        const float v = iou(r, j);
+        base.tally(i, j, v);
         return cost_from_iou(r, j, v) <= thresh;
     }
 };

@@ -28,6 +28,7 @@
 #include "ocm_device.cuh"
 #include "jv_device.cuh"
 #include "jv_block_device.cuh"
+#include <type_traits>
 
 namespace mot {
 
@@ -36,7 +37,8 @@ namespace mot {
 #endif
 constexpr int kOcThreads = MOT_OC_THREADS;
 constexpr int kOcRecFloats = 64;       // 56 used
-constexpr int kOcRing = 8;             // observation ring entries per track: delta_t <= kOcRing
+constexpr int kOcRing = 8;             // observation ring entries per track: delta_t <= kOcRing - 1 (a track updated twice in one
+                                       // frame still needs age - delta_t after its first update has stored age)
 constexpr int kOcObsFloats = 8;        // last_observation[5], velocity (dy, dx), pad
 // Exact reference tie-breaking: when a "twin" track (see the file header) is an assignment candidate, the frame's
 // assignment is redone by the reference's own dense LAPJV on the full cost matrix - by one warp out of shared memory
@@ -58,6 +60,9 @@ struct OcParams {
     float det_thresh, iou_threshold, min_conf, inertia;
     float q44, q66;                    // fl(0.01f * Q_xy_scaling), fl(0.0001f * Q_s_scaling)
     int max_age, min_hits, delta_t, use_byte;
+    // DeepOC-SORT only (deepocsort.hpp:96-121)
+    float w_assoc_emb, alpha_fixed_emb, aw_param;
+    int aw_off, embedding_off;
 };
 
 struct OcLayout {
@@ -135,6 +140,62 @@ struct OcArgs {
     int T, S, ld_dets, ld_out;
     int s_begin, s_end;
     OcParams p;
+    // DeepOC-SORT only: detection embeddings [T][S][ld_dets][dim] and the per-stream slab stride (OcLayout::stride +
+    // DeepLayout::bytes; the embedding dimension is a run-time size)
+    const float* embs;
+    int dim;
+    size_t stride;
+};
+
+// DeepOC-SORT's appearance state, appended to every stream's OC-SORT slab (at OcLayout::stride):
+//   trk_emb  [cap][dim]      the tracks' unit-length embeddings, by slot (deepocsort.cpp:75-80, :143-161)
+//   dense    [d_max][cap]    this frame's detection x track embedding products, written and read ONLY at the pairs whose
+//                            boxes overlap - everywhere else the reference's masked matrix is exactly 0 (:421-423)
+//   row_w    [d_max]         w_assoc_emb x adaptive row weight (0 when the row maximum is 0)        (:294-345)
+//   col_top  [cap]           packed (largest, second largest) entry of every column, order-preserving encoding
+//   col_nnz  [cap]           number of stored entries per column
+//   col_w    [cap], col_z [cap]   adaptive column weight / "column maximum is 0" flag
+struct DeepLayout {
+    int dim;
+    size_t off_emb, off_dense, off_roww, off_coltop, off_colnnz, off_colw, off_colz, bytes;
+    MOT_HD static DeepLayout make(int cap, int d_max, int dim) {
+        DeepLayout D{};
+        D.dim = dim;
+        size_t o = 0;
+        D.off_emb = o;     o = OcLayout::al(o + sizeof(float) * (size_t)cap * (size_t)(dim > 0 ? dim : 1));
+        D.off_dense = o;   o = OcLayout::al(o + sizeof(float) * (size_t)d_max * (size_t)cap);
+        D.off_roww = o;    o = OcLayout::al(o + sizeof(float) * (size_t)d_max);
+        D.off_coltop = o;  o = OcLayout::al(o + sizeof(unsigned long long) * (size_t)cap);
+        D.off_colnnz = o;  o = OcLayout::al(o + sizeof(int) * (size_t)cap);
+        D.off_colw = o;    o = OcLayout::al(o + sizeof(float) * (size_t)cap);
+        D.off_colz = o;    o = OcLayout::al(o + (size_t)cap);
+        D.bytes = o;
+        return D;
+    }
+};
+
+struct DeepStream {
+    float* trk_emb;
+    float* dense;
+    float* row_w;
+    unsigned long long* col_top;
+    int* col_nnz;
+    float* col_w;
+    unsigned char* col_z;
+    int dim;
+    __device__ __forceinline__ static DeepStream at(unsigned char* base, int cap, int d_max, int dim) {
+        const DeepLayout D = DeepLayout::make(cap, d_max, dim);
+        DeepStream s;
+        s.trk_emb = (float*)(base + D.off_emb);
+        s.dense = (float*)(base + D.off_dense);
+        s.row_w = (float*)(base + D.off_roww);
+        s.col_top = (unsigned long long*)(base + D.off_coltop);
+        s.col_nnz = (int*)(base + D.off_colnnz);
+        s.col_w = (float*)(base + D.off_colw);
+        s.col_z = base + D.off_colz;
+        s.dim = dim;
+        return s;
+    }
 };
 
 struct OcSmem {
@@ -276,9 +337,11 @@ __device__ __forceinline__ void oc_update_pairs(const OcStream& st, const OcSmem
 // Updates for the matches of a BYTE / re-match assignment, whose column list may name a track twice: the
 // reference applies them in ascending row order, so a track's second update must see its first.
 //   row r matched iff lap.row2col[r] >= 0; det_of_row(r), trk_of_col(c) translate list positions.
+// dp != nullptr (DeepOC-SORT with embeddings): every box update is followed by the track's update_emb (:869-870).
 template <class DetOfRow, class TrkOfCol>
 __device__ __forceinline__ int oc_apply_matches(const OcStream& st, OcSmem& sm, const float* dets, int n_rows, int delta_t,
-                                                DetOfRow det_of_row, TrkOfCol trk_of_col) {
+                                                DetOfRow det_of_row, TrkOfCol trk_of_col, const DeepStream* dp = nullptr,
+                                                const float* embs = nullptr, const OcParams* prm = nullptr) {
     const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
     int* first_row = sm.lap.col_label;                 // dead between block_lap calls; one int per track position
     for (int r = tid; r < n_rows; r += nt) {
@@ -307,6 +370,8 @@ __device__ __forceinline__ int oc_apply_matches(const OcStream& st, OcSmem& sm, 
         total += n_pairs;
         oc_update_pairs(st, sm, dets, n_pairs, delta_t, [&](int q) { return (int)sm.pair_trk[q]; },
                         [&](int q) { return (int)sm.pair_det[q]; });
+        if (dp) deep_update_embs(*dp, sm, embs, *prm, n_pairs, [&](int q) { return (int)sm.pair_trk[q]; },
+                                 [&](int q) { return (int)sm.pair_det[q]; });
         __syncthreads();
     }
     return total;
@@ -367,9 +432,163 @@ __device__ __forceinline__ void oc_exact_assignment(const OcStream& st, OcSmem& 
     __syncthreads();
 }
 
-template <int CAP, int DMAX>
+// ------------------------------------------------------------------------------------------------ DeepOC-SORT helpers
+// order-preserving float <-> unsigned (so that an integer atomic can keep a maximum); -0 sorts below +0, which the
+// callers do not distinguish
+__device__ __forceinline__ unsigned deep_f2ord(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float deep_ord2f(unsigned u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+// the reference's running (largest, second largest) scan (deepocsort.cpp:303-313): a multiset top-2, NaNs never enter
+struct DeepTop2 {
+    float mx, se;
+    __device__ __forceinline__ void push(float v) {
+        if (v > mx) { se = mx; mx = v; }
+        else if (v > se) se = v;
+    }
+};
+
+// 1 - max(second / max - bottom, 0) / (1 - bottom) with std::max's operand order (a NaN first operand survives) (:318-320)
+__device__ __forceinline__ float deep_aw_weight(float mx, float se, float bottom) {
+    const float t = xsub(xdiv(se, mx), bottom);
+    const float c = (t < 0.0f) ? 0.0f : t;
+    return xsub(1.0f, xdiv(c, xsub(1.0f, bottom)));
+}
+
+// ascending-index dot product, one rounding per operation: the order oracle/deepocsort.cpp pins against the reference
+__device__ __forceinline__ float deep_dot_seq(const float* __restrict__ a, const float* __restrict__ b, int dim) {
+    if ((dim & 3) == 0 && ((((size_t)a) | ((size_t)b)) & 15) == 0) {
+        const float4* a4 = reinterpret_cast<const float4*>(a);
+        const float4* b4 = reinterpret_cast<const float4*>(b);
+        float4 x = a4[0], y = b4[0];
+        float acc = xmul(x.x, y.x);
+        acc = xadd(acc, xmul(x.y, y.y)); acc = xadd(acc, xmul(x.z, y.z)); acc = xadd(acc, xmul(x.w, y.w));
+        for (int k = 1; k < (dim >> 2); ++k) {
+            x = a4[k]; y = b4[k];
+            acc = xadd(acc, xmul(x.x, y.x)); acc = xadd(acc, xmul(x.y, y.y));
+            acc = xadd(acc, xmul(x.z, y.z)); acc = xadd(acc, xmul(x.w, y.w));
+        }
+        return acc;
+    }
+    float acc = xmul(a[0], b[0]);
+    for (int k = 1; k < dim; ++k) acc = xadd(acc, xmul(a[k], b[k]));
+    return acc;
+}
+
+// v <- v / ||v|| when the norm exceeds 1e-6 (deepocsort.cpp:75-80, :154-158); ascending-index sum of squares
+__device__ __forceinline__ void deep_normalise(float* v, int dim) {
+    float acc = xmul(v[0], v[0]);
+    for (int k = 1; k < dim; ++k) acc = xadd(acc, xmul(v[k], v[k]));
+    const float n = xsqrt(acc);
+    if (n > 1e-6f)
+        for (int k = 0; k < dim; ++k) v[k] = xdiv(v[k], n);
+}
+
+// DeepOCSortKalmanBoxTracker ctor's embedding copy (:73-80) for the n_new tracks just appended to list_a at n_trk
+template <class DetOf>
+__device__ __forceinline__ void deep_spawn_embs(const DeepStream& dp, const OcSmem& sm, const float* embs, int n_new, int n_trk,
+                                                DetOf det_of) {
+    for (int k = (int)threadIdx.x; k < n_new; k += (int)blockDim.x) {
+        float* e = dp.trk_emb + (size_t)sm.list_a[n_trk + k] * dp.dim;
+        const float* src = embs + (size_t)det_of(k) * dp.dim;
+        for (int q = 0; q < dp.dim; ++q) e[q] = src[q];
+        deep_normalise(e, dp.dim);
+    }
+}
+
+// update_emb (:143-161) after the box updates of n_pairs (track position, detection) pairs over DISTINCT tracks:
+//   alpha = alpha_fixed + (1 - alpha_fixed) * (1 - trust),  trust = (conf - det_thresh) / (1 - det_thresh)   (:650-652)
+//   emb <- normalise(alpha * emb + (1 - alpha) * det_emb)
+template <class TrkOf, class DetOf>
+__device__ __forceinline__ void deep_update_embs(const DeepStream& dp, const OcSmem& sm, const float* embs, const OcParams& p,
+                                                 int n_pairs, TrkOf trk_of, DetOf det_of) {
+    for (int q = (int)threadIdx.x; q < n_pairs; q += (int)blockDim.x) {
+        const int det = det_of(q);
+        float* e = dp.trk_emb + (size_t)sm.list_a[trk_of(q)] * dp.dim;
+        const float* src = embs + (size_t)det * dp.dim;
+        const float trust = xdiv(xsub(sm.det_conf[det], p.det_thresh), xsub(1.0f, p.det_thresh));
+        const float alpha = xadd(p.alpha_fixed_emb, xmul(xsub(1.0f, p.alpha_fixed_emb), xsub(1.0f, trust)));
+        const float beta = xsub(1.0f, alpha);
+        for (int k = 0; k < dp.dim; ++k) e[k] = xadd(xmul(alpha, e[k]), xmul(beta, src[k]));
+        deep_normalise(e, dp.dim);
+    }
+}
+
+// The appearance terms of the first association (deepocsort.cpp:756-766 GEMM, :420-440 mask + weights), sparse: only
+// the (detection, track) pairs whose boxes overlap (iou > 0) have a non-zero entry in the reference's masked matrix, so
+// only they are multiplied out; the adaptive weights' row / column top-2 scans count the remaining entries as zeros.
+// Rows = high detections, one thread per row walking the column grid.  All threads of the block must call.
+// Returns the DeepOcmCost mode (1 adaptive weights, 2 plain w_assoc_emb).
+__device__ __forceinline__ int deep_embedding_terms(const DeepStream& dp, const OcStream& st, OcSmem& sm, const float* embs,
+                                                    const OcParams& p, int n_high, int n_trk) {
+    const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
+    const int mode = p.aw_off ? 2 : 1;
+    const float ninf = __int_as_float(0xff800000);
+    const unsigned long long empty = ((unsigned long long)deep_f2ord(ninf) << 32) | deep_f2ord(ninf);
+    for (int j = tid; j < n_trk; j += nt) { dp.col_top[j] = empty; dp.col_nnz[j] = 0; }
+    grid_build(sm.lap.grid, n_trk, sm.bs, [&](int j) { return sm.trk_box[j]; });
+    for (int i = tid; i < n_high; i += nt) {
+        const int det = sm.high[i];
+        const float4 box = sm.det_box[det];
+        const float area = box_area(box);
+        const float* de = embs + (size_t)det * dp.dim;
+        DeepTop2 t{ninf, ninf};
+        int nnz = 0;
+        grid_query(sm.lap.grid, box, [&](int j) { return sm.trk_box[j]; }, [&](int j, float4 b) {
+            if (iou_pair(box, area, b) <= 0.0f) return;
+            const float val = deep_dot_seq(de, dp.trk_emb + (size_t)sm.list_a[j] * dp.dim, dp.dim);
+            dp.dense[(size_t)i * n_trk + j] = val;
+            t.push(val);
+            ++nnz;
+            if (mode == 1 && val == val) {
+                const unsigned ov = deep_f2ord(val);
+                unsigned long long old = dp.col_top[j];
+                for (;;) {
+                    const unsigned mx = (unsigned)(old >> 32), se = (unsigned)old;
+                    unsigned long long upd;
+                    if (ov > mx) upd = ((unsigned long long)ov << 32) | mx;
+                    else if (ov > se) upd = ((unsigned long long)mx << 32) | ov;
+                    else break;
+                    const unsigned long long seen = atomicCAS(&dp.col_top[j], old, upd);
+                    if (seen == old) break;
+                    old = seen;
+                }
+            }
+            if (mode == 1) atomicAdd(&dp.col_nnz[j], 1);
+        });
+        if (mode == 1) {
+            float w = p.w_assoc_emb;
+            if (n_trk >= 2) {                                                    // (:302)
+                const int zeros = n_trk - nnz;
+                if (zeros >= 1) t.push(0.0f);
+                if (zeros >= 2) t.push(0.0f);
+                w = (t.mx == 0.0f) ? 0.0f : xmul(w, deep_aw_weight(t.mx, t.se, p.aw_param));
+            }
+            dp.row_w[i] = w;
+        }
+    }
+    __syncthreads();
+    if (mode == 1 && n_high >= 2) {                                              // (:324)
+        for (int j = tid; j < n_trk; j += nt) {
+            const unsigned long long top = dp.col_top[j];
+            DeepTop2 t{deep_ord2f((unsigned)(top >> 32)), deep_ord2f((unsigned)top)};
+            const int zeros = n_high - dp.col_nnz[j];
+            if (zeros >= 1) t.push(0.0f);
+            if (zeros >= 2) t.push(0.0f);
+            const bool z = (t.mx == 0.0f);
+            dp.col_z[j] = z ? 1 : 0;
+            dp.col_w[j] = z ? 0.0f : deep_aw_weight(t.mx, t.se, p.aw_param);
+        }
+    }
+    __syncthreads();
+    return mode;
+}
+
+template <int CAP, int DMAX, bool DEEP>
 __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, OcSmem& sm, const float* dets, int n_det_in,
-                                         float* out, int* n_out) {
+                                         float* out, int* n_out, const DeepStream& dp, const float* embs) {
     const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
     const int lane = tid & 31, g = lane & 7, base = lane & ~7;
     const int groups = nt >> 3, gid = tid >> 3;
@@ -411,6 +630,7 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
     const float score_bound = __int_as_float(sm.flags[3]);
     const bool prune_first = thr >= 0.0f && (0.5f * fabsf(a.p.inertia) * score_bound * 1.0001f + 1e-7f) < thr;
     const bool prune_rest = thr > 0.0f;
+    const bool use_emb = DEEP && !a.p.embedding_off;
     __syncthreads();
     if (tid == 0) sm.flags[3] = 0;
 
@@ -458,6 +678,9 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
         if (n_new > n_free) { n_new = n_free; if (tid == 0) atomicOr(&st.hdr[kOHdrError], 1); }
         oc_spawn(st, sm, dets, n_new, 0, n_free, id_base, [&](int k) { return (int)sm.high[k]; });
         __syncthreads();
+        if constexpr (DEEP) {
+            if (use_emb) deep_spawn_embs(dp, sm, embs, n_new, 0, [&](int k) { return (int)sm.high[k]; });
+        }
         for (int k = tid; k < n_new; k += nt) { st.list[k] = sm.list_a[k]; st.twin[sm.list_a[k]] = kNoTwin; }
         if (tid == 0) {
             *n_out = 0;
@@ -490,8 +713,16 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
     __syncthreads();
 
     // ---- D. first association (:413-420, associate :610-737); rows = high detections, columns = tracks
-    OcmCost ocm{sm.det_box, sm.det_conf, sm.high, sm.trk_box, st.ocm, st.valid, a.p.inertia, thr, prune_first,
-                sm.row_bits, sm.col_bits, sm.pair_det /* row_hit */, sm.flags};
+    const OcmCost ocm_base{sm.det_box, sm.det_conf, sm.high, sm.trk_box, st.ocm, st.valid, a.p.inertia, thr, prune_first,
+                           sm.row_bits, sm.col_bits, sm.pair_det /* row_hit */, sm.flags};
+    std::conditional_t<DEEP, DeepOcmCost, OcmCost> ocm;
+    if constexpr (DEEP) {
+        // appearance term (deepocsort.cpp:420-440): needs detections (the reference leaves the matrix empty without, :756)
+        const int emb_mode = (use_emb && n_high > 0) ? deep_embedding_terms(dp, st, sm, embs, a.p, n_high, n_trk) : 0;
+        ocm = DeepOcmCost{ocm_base, dp.dense, dp.row_w, dp.col_w, dp.col_z, n_trk, emb_mode, a.p.w_assoc_emb, n_high >= 2, prune_first};
+    } else {
+        ocm = ocm_base;
+    }
     block_lap(sm.lap, n_high, n_trk, DMAX, CAP, -thr, ocm);
     const bool trivial = sm.flags[0] != 0 && sm.flags[1] == 0;   // max row sum == 1 && max column sum == 1 (:676-680)
     // the optimum can only be non-unique if it uses a track that still has a bit-identical twin (the twin is then an
@@ -526,7 +757,7 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
         for (int i = tid; i < n_high; i += nt) {
             const int j = sm.lap.row2col[i];
             if (j < 0) continue;
-            const OcmCost::Row rw = ocm.row(i);
+            const auto rw = ocm.row(i);
             const unsigned char f = (ocm.iou(rw, j) >= thr) ? 1 : 2;
             sm.det_flag[i] = f; sm.trk_flag[j] = f;
         }
@@ -539,7 +770,18 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
                                  if (pos < CAP) sm.ut[pos] = (unsigned short)sm.lap.row2col[i];
                              });
     int n_ut = n_ud;
-    const int n_filtered = n_ud;
+    int n_dup = n_ud;                       // list entries that the final sweep below adds a second time
+    if constexpr (DEEP) {
+        // DeepOC-SORT's associate also lists what the assignment left unmatched BEFORE the sweep (:476-481), so after
+        // an assignment every unmatched detection and track sits in its list twice
+        if (!trivial && n_high > 0) {
+            n_ud = block_compact(n_high, n_ud, sm.bs, [&](int i) { return sm.det_flag[i] == 0; },
+                                 [&](int i, int pos) { if (pos < DMAX) sm.ud[pos] = sm.high[i]; });
+            n_ut = block_compact(n_trk, n_ut, sm.bs, [&](int j) { return sm.trk_flag[j] == 0; },
+                                 [&](int j, int pos) { if (pos < CAP) sm.ut[pos] = (unsigned short)j; });
+            n_dup = max(n_ud, n_ut);
+        }
+    }
     n_ud = block_compact(n_high, n_ud, sm.bs, [&](int i) { return sm.det_flag[i] != 1; },
                          [&](int i, int pos) { if (pos < DMAX) sm.ud[pos] = sm.high[i]; });
     n_ut = block_compact(n_trk, n_ut, sm.bs, [&](int j) { return sm.trk_flag[j] != 1; },
@@ -557,6 +799,10 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
     // ---- E. update the matched tracks (:423-430)
     oc_update_pairs(st, sm, dets, n_match, delta_t, [&](int q) { return (int)sm.pair_trk[q]; },
                     [&](int q) { return (int)sm.pair_det[q]; });
+    if constexpr (DEEP) {
+        if (use_emb) deep_update_embs(dp, sm, embs, a.p, n_match, [&](int q) { return (int)sm.pair_trk[q]; },
+                                      [&](int q) { return (int)sm.pair_det[q]; });
+    }
     __syncthreads();
     // detection / track flags now mean "taken out of the unmatched lists"
     for (int j = tid; j < n_det; j += nt) sm.det_flag[j] = 0;
@@ -607,11 +853,11 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
         __syncthreads();
         NegIouCost cost{sm.det_box, sm.ud, sm.trk_box, sm.ut, thr, prune_rest, sm.flags};
         block_lap(sm.lap, n_ud, n_ut, DMAX, CAP, -thr, cost);
-        // Exact ties here: (1) the lists hold an entry twice (pairs rejected by the IoU filter, n_filtered of them) - which
+        // Exact ties here: (1) the lists hold an entry twice (pairs rejected by the IoU filter; in DeepOC-SORT also everything the assignment left unmatched) - which
         // COPY of a detection is matched decides the order in which a twice-listed track receives its two updates;
         // (2) DIFFERENT tracks with bit-identical last observations: twins that both stayed unmatched, and tracks that an
         // earlier frame updated with the same (duplicated) detection.  In both cases the reference's answer is its LAPJV's.
-        if (sm.flags[0] != 0 && n_filtered > 0 && tid == 0) sm.flags[2] = 1;
+        if (sm.flags[0] != 0 && n_dup > 0 && tid == 0) sm.flags[2] = 1;
         if (sm.flags[0] != 0)
             for (int p = tid; p < n_ut; p += nt) {
                 if (sm.lap.col2row[p] < 0) continue;
@@ -638,7 +884,7 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
                 if (c >= 0) { sm.trk_flag[sm.ut[c]] = 1; sm.det_flag[sm.ud[r]] = 1; }
             }
             n_rematch = oc_apply_matches(st, sm, dets, n_ud, delta_t, [&](int r) { return (int)sm.ud[r]; },
-                                         [&](int c) { return (int)sm.ut[c]; });
+                                         [&](int c) { return (int)sm.ut[c]; }, use_emb ? &dp : nullptr, embs, &a.p);
             const int kt = block_compact(n_ut, 0, sm.bs, [&](int p) { return sm.trk_flag[sm.ut[p]] == 0; },
                                          [&](int p, int pos) { sm.ut2[pos] = sm.ut[p]; });
             const int kd = block_compact(n_ud, 0, sm.bs, [&](int p) { return sm.det_flag[sm.ud[p]] == 0; },
@@ -661,6 +907,9 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
     }
     oc_spawn(st, sm, dets, n_new, n_trk, n_free, id_base, [&](int k) { return (int)sm.ud[k]; });
     __syncthreads();
+    if constexpr (DEEP) {
+        if (use_emb) deep_spawn_embs(dp, sm, embs, n_new, n_trk, [&](int k) { return (int)sm.ud[k]; });
+    }
     {
         // a detection that sits twice in the list has just spawned two bit-identical tracks: link them as twins
         int* first_pos = sm.lap.row_label;          // [DMAX] ints, idle outside block_lap
@@ -693,7 +942,7 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
                                          if (box_sum4(b) < 0.0f) b = oc_track_box(st.recs + (size_t)slot * kOcRecFloats);
                                          float* w = out + (size_t)pos * 8;
                                          *reinterpret_cast<float4*>(w) = b;
-                                         *reinterpret_cast<float4*>(w + 4) = make_float4((float)(st.id[slot] + 1), st.conf[slot],
+                                         *reinterpret_cast<float4*>(w + 4) = make_float4((float)(st.id[slot] + (DEEP ? 0 : 1)), st.conf[slot],
                                                                                          (float)st.cls[slot], (float)st.det_ind[slot]);
                                      });
     const int n_keep = block_compact(n_all, 0, sm.bs, [&](int k) { return st.tsu[sm.list_a[k]] <= max_age; },
@@ -719,27 +968,41 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
     __syncthreads();
 }
 
-template <int CAP, int DMAX, int ECAP>
-__global__ void __launch_bounds__(kOcThreads) ocsort_step_kernel(OcArgs a) {
+template <int CAP, int DMAX, int ECAP, bool DEEP>
+__device__ __forceinline__ void oc_step_body(const OcArgs& a) {
     MOT_DYNAMIC_SMEM(smem);
     OcSmem sm;
     oc_carve(smem, CAP, DMAX, ECAP, sm);
     constexpr OcLayout L = OcLayout::make(CAP, DMAX);
     static_assert(lap_idle_bytes(DMAX, CAP, ECAP) >= jv_block_sbytes(DMAX + CAP), "the CTA-wide LAPJV's shared scratch must fit the sparse solver's idle arrays");
+    const size_t stride = DEEP ? a.stride : L.stride;
     for (int s = a.s_begin + (int)blockIdx.x; s < a.s_end; s += (int)gridDim.x) {
-        OcStream st = OcStream::at(a.state + (size_t)s * L.stride, L);
+        unsigned char* base = a.state + (size_t)s * stride;
+        OcStream st = OcStream::at(base, L);
+        DeepStream dp{};
+        if constexpr (DEEP) dp = DeepStream::at(base + L.stride, CAP, DMAX, a.dim);
         lap_carve_gscratch(st.gscratch, DMAX, CAP, sm.lap);
         for (int t = 0; t < a.T; ++t) {
             const size_t fs = (size_t)t * a.S + s;
-            oc_frame<CAP, DMAX>(a, st, sm, a.dets + fs * (size_t)a.ld_dets * 6, a.n_dets[fs],
-                                a.out + fs * (size_t)a.ld_out * 8, a.n_out + fs);
+            const float* embs = (DEEP && a.embs) ? a.embs + fs * (size_t)a.ld_dets * (size_t)a.dim : nullptr;
+            oc_frame<CAP, DMAX, DEEP>(a, st, sm, a.dets + fs * (size_t)a.ld_dets * 6, a.n_dets[fs],
+                                      a.out + fs * (size_t)a.ld_out * 8, a.n_out + fs, dp, embs);
         }
     }
 }
 
-static __global__ void ocsort_reset_kernel(unsigned char* state, OcLayout L, int S, int keep_id_counter) {
+template <int CAP, int DMAX, int ECAP>
+__global__ void __launch_bounds__(kOcThreads) ocsort_step_kernel(OcArgs a) { oc_step_body<CAP, DMAX, ECAP, false>(a); }
+
+// DeepOC-SORT (reference src/trackers/deepocsort.cpp:589-944, associate :348-504): the OC-SORT frame step without the
+// BYTE pass, plus the appearance term of the first association, the embedding EMA of every updated track and the
+// reference's twice-listed leftovers (see oc_frame).  Camera-motion compensation is outside the hot path (cmc_off).
+template <int CAP, int DMAX, int ECAP>
+__global__ void __launch_bounds__(kOcThreads) deepocsort_step_kernel(OcArgs a) { oc_step_body<CAP, DMAX, ECAP, true>(a); }
+
+static __global__ void ocsort_reset_kernel(unsigned char* state, OcLayout L, size_t stride, int S, int keep_id_counter) {
     for (int s = (int)blockIdx.x; s < S; s += (int)gridDim.x) {
-        OcStream st = OcStream::at(state + (size_t)s * L.stride, L);
+        OcStream st = OcStream::at(state + (size_t)s * stride, L);
         for (int k = (int)threadIdx.x; k < L.cap; k += (int)blockDim.x) st.freel[k] = (unsigned short)(L.cap - 1 - k);
         if (threadIdx.x == 0) {
             const int idc = keep_id_counter ? st.hdr[kOHdrIdCounter] : 0;

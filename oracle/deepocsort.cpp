@@ -251,6 +251,7 @@ int orc_deepocsort_update(OrcDeepOcSort* s, const float* dets, int n, const floa
     for (int i = 0; i < n; ++i)
         if (dets[6 * i + 4] > s->det_thresh) remain.push_back(i);                   // :611-615
     const int nd = (int)remain.size();
+    s->last_sizes[0] = nd;
     std::vector<float> ones(1, 1.0f);
     const int edim = use_emb ? dim : 1;                                              // dets_embs = Ones(n, 1) when off (:624-626)
     auto det_emb = [&](int k) -> const float* { return use_emb ? embs + (size_t)remain[k] * dim : ones.data(); };

@@ -199,7 +199,7 @@ void* sim_oc_create(int S, float det_thresh, int max_age, int min_hits, float io
     h->state.assign(h->L.stride * (size_t)S + 256, 0);
     unsigned char* st = h->state.data();
     const mot::OcLayout L = h->L;
-    cpusim::launch(dim3(S), dim3(64), 0, [=] { mot::ocsort_reset_kernel(st, L, S, 0); });
+    cpusim::launch(dim3(S), dim3(64), 0, [=] { mot::ocsort_reset_kernel(st, L, L.stride, S, 0); });
     return h;
 }
 void sim_oc_destroy(void* hv) { delete (SimOc*)hv; }
@@ -239,6 +239,87 @@ int sim_oc_dump(void* hv, int s, float* rows, int cap_rows) {
         o[7] = (float)m[6 * cap + slot];
         std::memcpy(o + 8, obs + (size_t)slot * mot::kOcObsFloats, 7 * sizeof(float));
         std::memcpy(o + 15, recs + (size_t)slot * mot::kOcRecFloats, 56 * sizeof(float));
+    }
+    return k;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ DeepOC-SORT engine under the emulator
+namespace {
+struct SimDeepOc {
+    mot::OcLayout L;
+    mot::DeepLayout D;
+    size_t stride;
+    int S;
+    mot::OcParams p;
+    std::vector<unsigned char> state;
+};
+}  // namespace
+
+extern "C" {
+
+void* sim_deepoc_create(int S, int dim, float det_thresh, int max_age, int min_hits, float iou_threshold, int delta_t,
+                        float inertia, float w_assoc_emb, float alpha_fixed_emb, float aw_param, int embedding_off, int aw_off,
+                        float q_xy, float q_s) {
+    auto* h = new SimDeepOc();
+    h->L = mot::OcLayout::make(256, 64);
+    h->D = mot::DeepLayout::make(256, 64, embedding_off ? 0 : dim);
+    h->stride = h->L.stride + h->D.bytes;
+    h->S = S;
+    h->p = mot::OcParams{};
+    h->p.det_thresh = det_thresh; h->p.max_age = max_age; h->p.min_hits = min_hits; h->p.iou_threshold = iou_threshold;
+    h->p.min_conf = 0.1f; h->p.delta_t = delta_t; h->p.inertia = inertia; h->p.use_byte = 0;
+    h->p.q44 = 0.01f * q_xy; h->p.q66 = 0.0001f * q_s;
+    h->p.w_assoc_emb = w_assoc_emb; h->p.alpha_fixed_emb = alpha_fixed_emb; h->p.aw_param = aw_param;
+    h->p.embedding_off = embedding_off; h->p.aw_off = aw_off;
+    h->state.assign(h->stride * (size_t)S + 256, 0);
+    unsigned char* st = h->state.data();
+    const mot::OcLayout L = h->L;
+    const size_t stride = h->stride;
+    cpusim::launch(dim3(S), dim3(64), 0, [=] { mot::ocsort_reset_kernel(st, L, stride, S, 0); });
+    return h;
+}
+void sim_deepoc_destroy(void* hv) { delete (SimDeepOc*)hv; }
+
+int sim_deepoc_update(void* hv, const float* dets, const int* n_dets, const float* embs, int T, int ld_dets, float* out,
+                      int* n_out, int ld_out, int threads) {
+    auto* h = (SimDeepOc*)hv;
+    mot::OcArgs a{};
+    a.state = h->state.data(); a.dets = dets; a.n_dets = n_dets; a.out = out; a.n_out = n_out;
+    a.T = T; a.S = h->S; a.ld_dets = ld_dets; a.ld_out = ld_out; a.s_begin = 0; a.s_end = h->S; a.p = h->p;
+    a.embs = embs; a.dim = h->D.dim; a.stride = h->stride;
+    const size_t smem = mot::oc_smem_bytes(256, 64, 1024);
+    cpusim::launch(dim3(h->S), dim3(threads), smem, [=] { mot::deepocsort_step_kernel<256, 64, 1024>(a); });
+    return 0;
+}
+void sim_deepoc_header(void* hv, int s, int* hdr16) {
+    auto* h = (SimDeepOc*)hv;
+    std::memcpy(hdr16, h->state.data() + (size_t)s * h->stride, sizeof(int) * 16);
+}
+
+// rows as sim_oc_dump (71 floats); embs (nullable): dim floats per row
+int sim_deepoc_dump(void* hv, int s, float* rows, float* embs, int cap_rows) {
+    auto* h = (SimDeepOc*)hv;
+    unsigned char* base = h->state.data() + (size_t)s * h->stride;
+    const mot::OcLayout& L = h->L;
+    const int* hdr = (const int*)base;
+    const unsigned short* list = (const unsigned short*)(base + L.off_lists);
+    const int* m = (const int*)(base + L.off_meta);
+    const float* obs = (const float*)(base + L.off_obs);
+    const float* recs = (const float*)(base + L.off_recs);
+    const float* temb = (const float*)(base + L.stride + h->D.off_emb);
+    const int n = hdr[mot::kOHdrTracks], cap = L.cap;
+    int k = 0;
+    for (; k < n && k < cap_rows; ++k) {
+        const int slot = list[k];
+        float* o = rows + 71 * k;
+        o[0] = (float)m[slot]; o[1] = (float)m[cap + slot]; o[2] = (float)m[2 * cap + slot]; o[3] = (float)m[3 * cap + slot];
+        o[4] = (float)m[4 * cap + slot]; o[5] = ((const float*)m)[7 * cap + slot]; o[6] = (float)m[5 * cap + slot];
+        o[7] = (float)m[6 * cap + slot];
+        std::memcpy(o + 8, obs + (size_t)slot * mot::kOcObsFloats, 7 * sizeof(float));
+        std::memcpy(o + 15, recs + (size_t)slot * mot::kOcRecFloats, 56 * sizeof(float));
+        if (embs && h->D.dim > 0) std::memcpy(embs + (size_t)k * h->D.dim, temb + (size_t)slot * h->D.dim, sizeof(float) * h->D.dim);
     }
     return k;
 }

@@ -60,6 +60,14 @@ def lib():
         S.sim_oc_dump.argtypes = [C.c_void_p, C.c_int, f32p, C.c_int]
         S.sim_oc_dump.restype = C.c_int
         S.sim_oc_destroy.argtypes = [C.c_void_p]
+        S.sim_deepoc_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float,
+                                        C.c_float, C.c_float, C.c_int, C.c_int, C.c_float, C.c_float]
+        S.sim_deepoc_create.restype = C.c_void_p
+        S.sim_deepoc_update.argtypes = [C.c_void_p, f32p, i32p, C.c_void_p, C.c_int, C.c_int, f32p, i32p, C.c_int, C.c_int]
+        S.sim_deepoc_header.argtypes = [C.c_void_p, C.c_int, i32p]
+        S.sim_deepoc_dump.argtypes = [C.c_void_p, C.c_int, f32p, C.c_void_p, C.c_int]
+        S.sim_deepoc_dump.restype = C.c_int
+        S.sim_deepoc_destroy.argtypes = [C.c_void_p]
         S.sim_bot_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float,
                                      C.c_float, C.c_int, C.c_int, C.c_int]
         S.sim_bot_create.restype = C.c_void_p
@@ -176,6 +184,46 @@ class SimOCSort:
         buf = np.zeros((self.cap, 71), np.float32)
         k = lib().sim_oc_dump(self.h, s, buf, self.cap)
         return buf[:k]
+
+
+class SimDeepOCSort:
+    def __init__(self, n_streams=1, emb_dim=0, det_thresh=0.3, max_age=30, min_hits=3, iou_threshold=0.3, delta_t=3,
+                 inertia=0.2, w_association_emb=0.5, alpha_fixed_emb=0.95, aw_param=0.5, embedding_off=False, aw_off=False,
+                 q_xy_scaling=0.01, q_s_scaling=0.0001):
+        self.S, self.cap, self.dim = n_streams, 256, 0 if embedding_off else emb_dim
+        self.h = lib().sim_deepoc_create(n_streams, emb_dim, det_thresh, max_age, min_hits, iou_threshold, delta_t, inertia,
+                                         w_association_emb, alpha_fixed_emb, aw_param, int(embedding_off), int(aw_off),
+                                         q_xy_scaling, q_s_scaling)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().sim_deepoc_destroy(self.h)
+            self.h = None
+
+    def update(self, dets, n_dets, embs=None, threads=128):
+        dets = np.ascontiguousarray(dets, np.float32)
+        T, S, ld, _ = dets.shape
+        n_dets = np.ascontiguousarray(n_dets, np.int32).reshape(T, S)
+        out = np.zeros((T, S, self.cap, 8), np.float32)
+        n_out = np.zeros((T, S), np.int32)
+        ep = None
+        if embs is not None:
+            embs = np.ascontiguousarray(embs, np.float32)
+            assert embs.shape == (T, S, ld, self.dim)
+            ep = embs.ctypes.data_as(C.c_void_p)
+        lib().sim_deepoc_update(self.h, dets, n_dets, ep, T, ld, out, n_out, self.cap, threads)
+        return out, n_out
+
+    def header(self, s=0):
+        h = np.zeros(16, np.int32)
+        lib().sim_deepoc_header(self.h, s, h)
+        return h
+
+    def dump(self, s=0):
+        buf = np.zeros((self.cap, 71), np.float32)
+        emb = np.zeros((self.cap, max(self.dim, 1)), np.float32)
+        k = lib().sim_deepoc_dump(self.h, s, buf, emb.ctypes.data_as(C.c_void_p), self.cap)
+        return buf[:k], emb[:k, :self.dim]
 
 
 class SimBotSort:

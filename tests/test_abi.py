@@ -113,3 +113,4 @@ def test_cpp_binding_runs_on_gpu(lib, tmp_path):
     p = subprocess.run([_build_cpp_example(tmp_path)], capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
     assert "frame 2 rows: sort 2 ocsort 2 botsort 2" in p.stdout and "frame 2 id 1" in p.stdout
+    assert "frame 2 deepocsort rows 2" in p.stdout

@@ -284,7 +284,7 @@ def test_gpu_ocsort_capacity_and_argument_errors(oracle, gpu):
         eng.check()
     eng.close()
     with pytest.raises(_lib.MotError):
-        api.Engine(_lib.TRACKER_OCSORT, 1, 256, 64, **{**OC_ARGS, "delta_t": 9})     # observation ring holds 8 ages
+        api.Engine(_lib.TRACKER_OCSORT, 1, 256, 64, **{**OC_ARGS, "delta_t": 8})     # observation ring holds 8 ages: the current one and the 7 before it
     with pytest.raises(ValueError):
         api.Engine(_lib.TRACKER_OCSORT, 1, 4096, 4096, **OC_ARGS)                    # beyond the largest built shape
 
