@@ -76,6 +76,13 @@ def test_deepocsort_cta_wide_lapjv_under_emulator(oracle):
 
 
 # ------------------------------------------------------------------ the sm_100a kernel through the C ABI (GPU)
+@pytest.fixture
+def gpu():
+    from motcpp_b200 import build
+    build.build()
+    _lib.require_gpu()
+
+
 def _engine_vs_oracle(oracle, streams, over, cap, d_max, dim, T_chunk=None):
     """streams: [(dets (T, ld, 6), counts (T,), embs (T, ld, dim))]; returns the number of exact LAPJV re-solves."""
     args = {**DOC, **over}
