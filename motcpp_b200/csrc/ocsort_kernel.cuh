@@ -152,12 +152,12 @@ struct OcArgs {
 //   dense    [d_max][cap]    this frame's detection x track embedding products, written and read ONLY at the pairs whose
 //                            boxes overlap - everywhere else the reference's masked matrix is exactly 0 (:421-423)
 //   row_w    [d_max]         w_assoc_emb x adaptive row weight (0 when the row maximum is 0)        (:294-345)
-//   col_top  [cap]           packed (largest, second largest) entry of every column, order-preserving encoding
-//   col_nnz  [cap]           number of stored entries per column
+//   col_top  [cap], row_top [d_max]   packed (largest, second largest) stored entry, order-preserving encoding
+//   col_nnz  [cap], row_nnz [d_max]   number of stored entries per column / row
 //   col_w    [cap], col_z [cap]   adaptive column weight / "column maximum is 0" flag
 struct DeepLayout {
     int dim;
-    size_t off_emb, off_dense, off_roww, off_coltop, off_colnnz, off_colw, off_colz, bytes;
+    size_t off_emb, off_dense, off_roww, off_coltop, off_colnnz, off_colw, off_colz, off_rowtop, off_rownnz, bytes;
     MOT_HD static DeepLayout make(int cap, int d_max, int dim) {
         DeepLayout D{};
         D.dim = dim;
@@ -169,6 +169,8 @@ struct DeepLayout {
         D.off_colnnz = o;  o = OcLayout::al(o + sizeof(int) * (size_t)cap);
         D.off_colw = o;    o = OcLayout::al(o + sizeof(float) * (size_t)cap);
         D.off_colz = o;    o = OcLayout::al(o + (size_t)cap);
+        D.off_rowtop = o;  o = OcLayout::al(o + sizeof(unsigned long long) * (size_t)d_max);
+        D.off_rownnz = o;  o = OcLayout::al(o + sizeof(int) * (size_t)d_max);
         D.bytes = o;
         return D;
     }
@@ -182,6 +184,8 @@ struct DeepStream {
     int* col_nnz;
     float* col_w;
     unsigned char* col_z;
+    unsigned long long* row_top;
+    int* row_nnz;
     int dim;
     __device__ __forceinline__ static DeepStream at(unsigned char* base, int cap, int d_max, int dim) {
         const DeepLayout D = DeepLayout::make(cap, d_max, dim);
@@ -193,6 +197,8 @@ struct DeepStream {
         s.col_nnz = (int*)(base + D.off_colnnz);
         s.col_w = (float*)(base + D.off_colw);
         s.col_z = base + D.off_colz;
+        s.row_top = (unsigned long long*)(base + D.off_rowtop);
+        s.row_nnz = (int*)(base + D.off_rownnz);
         s.dim = dim;
         return s;
     }
@@ -457,130 +463,216 @@ __device__ __forceinline__ float deep_aw_weight(float mx, float se, float bottom
     return xsub(1.0f, xdiv(c, xsub(1.0f, bottom)));
 }
 
-// ascending-index dot product, one rounding per operation: the order oracle/deepocsort.cpp pins against the reference
-__device__ __forceinline__ float deep_dot_seq(const float* __restrict__ a, const float* __restrict__ b, int dim) {
-    if ((dim & 3) == 0 && ((((size_t)a) | ((size_t)b)) & 15) == 0) {
-        const float4* a4 = reinterpret_cast<const float4*>(a);
-        const float4* b4 = reinterpret_cast<const float4*>(b);
-        float4 x = a4[0], y = b4[0];
-        float acc = xmul(x.x, y.x);
-        acc = xadd(acc, xmul(x.y, y.y)); acc = xadd(acc, xmul(x.z, y.z)); acc = xadd(acc, xmul(x.w, y.w));
-        for (int k = 1; k < (dim >> 2); ++k) {
-            x = a4[k]; y = b4[k];
-            acc = xadd(acc, xmul(x.x, y.x)); acc = xadd(acc, xmul(x.y, y.y));
-            acc = xadd(acc, xmul(x.z, y.z)); acc = xadd(acc, xmul(x.w, y.w));
+// Ordered sums, warp-cooperative.  The contract (oracle/deepocsort.cpp, pinned against the reference) is the ascending-index
+// sum with one rounding per operation - a serial chain per sum.  A warp therefore takes up to 32 sums at once: for 32
+// consecutive indices at a time all lanes produce term(p, k) for item p (coalesced loads across the lanes), the 32 x 32
+// block goes through a padded shared tile, and lane p adds ITS item's 32 terms in ascending order.  Loads are coalesced,
+// the chains of 32 items run side by side, and the order of every sum is exactly the scalar loop's.
+constexpr int kDeepK = 16;                                   // indices per tile pass (two items per pass of the warp)
+constexpr int kDeepTileFloats = 32 * (kDeepK + 1);
+
+// [scratch_a, row2col) of the sparse solver's workspace is dead outside block_lap (and outside oc_apply_matches'
+// col_label use): the tiles live there, one per participating warp
+__device__ __forceinline__ int deep_tiles(const OcSmem& sm, float*& tiles) {
+    tiles = (float*)sm.lap.scratch_a;
+    const size_t bytes = (size_t)((const unsigned char*)sm.lap.row2col - (const unsigned char*)sm.lap.scratch_a);
+    const int n = (int)(bytes / (sizeof(float) * kDeepTileFloats));
+    const int nwarps = (int)(blockDim.x >> 5);
+    return n < nwarps ? n : nwarps;
+}
+
+// returns, in lane p < n_items (<= 32), sum_{k < dim} term(p, k) in ascending k.  term must be free of side effects
+// (it is also evaluated, and discarded, at clamped indices).  All 32 lanes of the warp must call.
+template <class Term>
+__device__ __forceinline__ float deep_warp_ordered_sums(float* tile, int n_items, int dim, Term term) {
+    const int lane = lane_id(), sub = lane & (kDeepK - 1), half = lane >> 4;
+    float acc = 0.0f;
+    for (int k0 = 0; k0 < dim; k0 += kDeepK) {
+        const int kk = k0 + sub;
+        const int kc = kk < dim ? kk : dim - 1;
+        for (int p0 = 0; p0 < n_items; p0 += 16) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {                    // all the loads of 16 items first, then the stores
+                const int q = p0 + 2 * u + half;
+                const float t = term(q < n_items ? q : n_items - 1, kc);
+                v[u] = (q < n_items && kk < dim) ? t : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) tile[(p0 + 2 * u + half) * (kDeepK + 1) + sub] = v[u];
         }
-        return acc;
+        __syncwarp();
+        if (lane < n_items) {
+            const int cnt = min(kDeepK, dim - k0);
+            const float* row = tile + lane * (kDeepK + 1);
+            int q = 0;
+            if (k0 == 0) { acc = row[0]; q = 1; }
+            for (; q < cnt; ++q) acc = xadd(acc, row[q]);
+        }
+        __syncwarp();
     }
-    float acc = xmul(a[0], b[0]);
-    for (int k = 1; k < dim; ++k) acc = xadd(acc, xmul(a[k], b[k]));
     return acc;
 }
 
-// v <- v / ||v|| when the norm exceeds 1e-6 (deepocsort.cpp:75-80, :154-158); ascending-index sum of squares
-__device__ __forceinline__ void deep_normalise(float* v, int dim) {
-    float acc = xmul(v[0], v[0]);
-    for (int k = 1; k < dim; ++k) acc = xadd(acc, xmul(v[k], v[k]));
-    const float n = xsqrt(acc);
-    if (n > 1e-6f)
-        for (int k = 0; k < dim; ++k) v[k] = xdiv(v[k], n);
-}
-
-// DeepOCSortKalmanBoxTracker ctor's embedding copy (:73-80) for the n_new tracks just appended to list_a at n_trk
-template <class DetOf>
-__device__ __forceinline__ void deep_spawn_embs(const DeepStream& dp, const OcSmem& sm, const float* embs, int n_new, int n_trk,
-                                                DetOf det_of) {
-    for (int k = (int)threadIdx.x; k < n_new; k += (int)blockDim.x) {
-        float* e = dp.trk_emb + (size_t)sm.list_a[n_trk + k] * dp.dim;
-        const float* src = embs + (size_t)det_of(k) * dp.dim;
-        for (int q = 0; q < dp.dim; ++q) e[q] = src[q];
-        deep_normalise(e, dp.dim);
+// emb <- normalise(blend ? alpha * emb + (1 - alpha) * det_emb : det_emb) for n_items (track slot, detection) pairs over
+// DISTINCT slots: DeepOCSortKalmanBoxTracker's ctor copy (:73-80) and update_emb (:143-161) with
+//   alpha = alpha_fixed + (1 - alpha_fixed) * (1 - trust),  trust = (conf - det_thresh) / (1 - det_thresh)   (:650-652)
+// v <- v / ||v|| when the norm exceeds 1e-6 (:75-80, :154-158); ascending-index sum of squares.
+template <class SlotOf, class DetOf>
+__device__ __forceinline__ void deep_write_embs(const DeepStream& dp, const OcSmem& sm, const float* embs, const OcParams& p,
+                                                int n_items, bool blend, SlotOf slot_of, DetOf det_of) {
+    float* tiles;
+    const int nw = deep_tiles(sm, tiles);
+    const int warp = (int)(threadIdx.x >> 5), lane = lane_id();
+    if (warp >= nw) return;
+    float* tile = tiles + (size_t)warp * kDeepTileFloats;
+    const int dim = dp.dim;
+    for (int b0 = warp * 32; b0 < n_items; b0 += nw * 32) {
+        const int cnt = min(32, n_items - b0);
+        float alpha = 0.0f, beta = 1.0f;
+        if (blend && lane < cnt) {
+            const float trust = xdiv(xsub(sm.det_conf[det_of(b0 + lane)], p.det_thresh), xsub(1.0f, p.det_thresh));
+            alpha = xadd(p.alpha_fixed_emb, xmul(xsub(1.0f, p.alpha_fixed_emb), xsub(1.0f, trust)));
+            beta = xsub(1.0f, alpha);
+        }
+        const float sq = deep_warp_ordered_sums(tile, cnt, dim, [&](int q, int k) {
+            float v = __ldg(embs + (size_t)det_of(b0 + q) * dim + k);
+            if (blend) {
+                const float al = __shfl_sync(kFullMask, alpha, q), be = __shfl_sync(kFullMask, beta, q);
+                v = xadd(xmul(al, dp.trk_emb[(size_t)slot_of(b0 + q) * dim + k]), xmul(be, v));
+            }
+            return xmul(v, v);
+        });
+        const float norm = xsqrt(sq);
+        for (int q = 0; q < cnt; ++q) {
+            const float n = __shfl_sync(kFullMask, norm, q);
+            const float al = __shfl_sync(kFullMask, alpha, q), be = __shfl_sync(kFullMask, beta, q);
+            float* e = dp.trk_emb + (size_t)slot_of(b0 + q) * dim;
+            const float* src = embs + (size_t)det_of(b0 + q) * dim;
+            const bool scale = n > 1e-6f;
+#pragma unroll 4
+            for (int k = lane; k < dim; k += 32) {
+                float v = __ldg(src + k);
+                if (blend) v = xadd(xmul(al, e[k]), xmul(be, v));
+                e[k] = scale ? xdiv(v, n) : v;
+            }
+        }
     }
 }
 
-// update_emb (:143-161) after the box updates of n_pairs (track position, detection) pairs over DISTINCT tracks:
-//   alpha = alpha_fixed + (1 - alpha_fixed) * (1 - trust),  trust = (conf - det_thresh) / (1 - det_thresh)   (:650-652)
-//   emb <- normalise(alpha * emb + (1 - alpha) * det_emb)
+template <class DetOf>
+__device__ __forceinline__ void deep_spawn_embs(const DeepStream& dp, const OcSmem& sm, const float* embs, const OcParams& p,
+                                                int n_new, int n_trk, DetOf det_of) {
+    deep_write_embs(dp, sm, embs, p, n_new, false, [&](int k) { return (int)sm.list_a[n_trk + k]; }, det_of);
+}
 template <class TrkOf, class DetOf>
 __device__ __forceinline__ void deep_update_embs(const DeepStream& dp, const OcSmem& sm, const float* embs, const OcParams& p,
                                                  int n_pairs, TrkOf trk_of, DetOf det_of) {
-    for (int q = (int)threadIdx.x; q < n_pairs; q += (int)blockDim.x) {
-        const int det = det_of(q);
-        float* e = dp.trk_emb + (size_t)sm.list_a[trk_of(q)] * dp.dim;
-        const float* src = embs + (size_t)det * dp.dim;
-        const float trust = xdiv(xsub(sm.det_conf[det], p.det_thresh), xsub(1.0f, p.det_thresh));
-        const float alpha = xadd(p.alpha_fixed_emb, xmul(xsub(1.0f, p.alpha_fixed_emb), xsub(1.0f, trust)));
-        const float beta = xsub(1.0f, alpha);
-        for (int k = 0; k < dp.dim; ++k) e[k] = xadd(xmul(alpha, e[k]), xmul(beta, src[k]));
-        deep_normalise(e, dp.dim);
+    deep_write_embs(dp, sm, embs, p, n_pairs, true, [&](int q) { return (int)sm.list_a[trk_of(q)]; }, det_of);
+}
+
+// insert v into the packed (largest, second largest) pair at *top (order-preserving encodings); NaNs never enter
+__device__ __forceinline__ void deep_top2_insert(unsigned long long* top, float v) {
+    if (!(v == v)) return;
+    const unsigned ov = deep_f2ord(v);
+    unsigned long long old = *top;
+    for (;;) {
+        const unsigned mx = (unsigned)(old >> 32), se = (unsigned)old;
+        unsigned long long upd;
+        if (ov > mx) upd = ((unsigned long long)ov << 32) | mx;
+        else if (ov > se) upd = ((unsigned long long)mx << 32) | ov;
+        else break;
+        const unsigned long long seen = atomicCAS(top, old, upd);
+        if (seen == old) break;
+        old = seen;
     }
+}
+
+// (largest, second largest) of `stored` entries + `total - stored` zeros -> weight and "maximum is 0" flag (:303-321)
+__device__ __forceinline__ float deep_top2_weight(unsigned long long top, int zeros, float bottom, bool& is_zero) {
+    DeepTop2 t{deep_ord2f((unsigned)(top >> 32)), deep_ord2f((unsigned)top)};
+    if (zeros >= 1) t.push(0.0f);
+    if (zeros >= 2) t.push(0.0f);
+    is_zero = (t.mx == 0.0f);
+    return is_zero ? 0.0f : deep_aw_weight(t.mx, t.se, bottom);
 }
 
 // The appearance terms of the first association (deepocsort.cpp:756-766 GEMM, :420-440 mask + weights), sparse: only
 // the (detection, track) pairs whose boxes overlap (iou > 0) have a non-zero entry in the reference's masked matrix, so
 // only they are multiplied out; the adaptive weights' row / column top-2 scans count the remaining entries as zeros.
-// Rows = high detections, one thread per row walking the column grid.  All threads of the block must call.
-// Returns the DeepOcmCost mode (1 adaptive weights, 2 plain w_assoc_emb).
+//   1. one thread per row walks the column grid and appends its overlapping pairs to a list (the idle dense-LAPJV
+//      matrix of the stream's slab holds it: n_high x n_trk entries at most);
+//   2. warps take 32 pairs at a time through deep_warp_ordered_sums, store the products in `dense` and fold them into
+//      the packed row / column top-2 (one atomic per pair and side);
+//   3. one thread per row / column turns its top-2 into the weight.
+// All threads of the block must call.  Returns the DeepOcmCost mode (1 adaptive weights, 2 plain w_assoc_emb).
 __device__ __forceinline__ int deep_embedding_terms(const DeepStream& dp, const OcStream& st, OcSmem& sm, const float* embs,
                                                     const OcParams& p, int n_high, int n_trk) {
     const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
     const int mode = p.aw_off ? 2 : 1;
+    const int dim = dp.dim;
     const float ninf = __int_as_float(0xff800000);
     const unsigned long long empty = ((unsigned long long)deep_f2ord(ninf) << 32) | deep_f2ord(ninf);
-    for (int j = tid; j < n_trk; j += nt) { dp.col_top[j] = empty; dp.col_nnz[j] = 0; }
+    unsigned* pairs = (unsigned*)st.jv_dense;
+    if (mode == 1) {
+        for (int j = tid; j < n_trk; j += nt) { dp.col_top[j] = empty; dp.col_nnz[j] = 0; }
+        for (int i = tid; i < n_high; i += nt) { dp.row_top[i] = empty; dp.row_nnz[i] = 0; }
+    }
     grid_build(sm.lap.grid, n_trk, sm.bs, [&](int j) { return sm.trk_box[j]; });
     for (int i = tid; i < n_high; i += nt) {
-        const int det = sm.high[i];
-        const float4 box = sm.det_box[det];
+        const float4 box = sm.det_box[sm.high[i]];
         const float area = box_area(box);
-        const float* de = embs + (size_t)det * dp.dim;
-        DeepTop2 t{ninf, ninf};
-        int nnz = 0;
         grid_query(sm.lap.grid, box, [&](int j) { return sm.trk_box[j]; }, [&](int j, float4 b) {
             if (iou_pair(box, area, b) <= 0.0f) return;
-            const float val = deep_dot_seq(de, dp.trk_emb + (size_t)sm.list_a[j] * dp.dim, dp.dim);
-            dp.dense[(size_t)i * n_trk + j] = val;
-            t.push(val);
-            ++nnz;
-            if (mode == 1 && val == val) {
-                const unsigned ov = deep_f2ord(val);
-                unsigned long long old = dp.col_top[j];
-                for (;;) {
-                    const unsigned mx = (unsigned)(old >> 32), se = (unsigned)old;
-                    unsigned long long upd;
-                    if (ov > mx) upd = ((unsigned long long)ov << 32) | mx;
-                    else if (ov > se) upd = ((unsigned long long)mx << 32) | ov;
-                    else break;
-                    const unsigned long long seen = atomicCAS(&dp.col_top[j], old, upd);
-                    if (seen == old) break;
-                    old = seen;
+            pairs[atomicAdd(&sm.flags[3], 1)] = ((unsigned)i << 16) | (unsigned)j;
+        });
+    }
+    __syncthreads();
+    const int n_pairs = sm.flags[3];
+    {
+        float* tiles;
+        const int nw = deep_tiles(sm, tiles);
+        const int warp = tid >> 5, lane = tid & 31;
+        if (warp < nw) {
+            float* tile = tiles + (size_t)warp * kDeepTileFloats;
+            for (int b0 = warp * 32; b0 < n_pairs; b0 += nw * 32) {
+                const int cnt = min(32, n_pairs - b0);
+                const float val = deep_warp_ordered_sums(tile, cnt, dim, [&](int q, int k) {
+                    const unsigned pr = pairs[b0 + q];
+                    const float* de = embs + (size_t)sm.high[pr >> 16] * dim;
+                    const float* te = dp.trk_emb + (size_t)sm.list_a[pr & 0xffffu] * dim;
+                    return xmul(__ldg(de + k), te[k]);
+                });
+                if (lane < cnt) {
+                    const unsigned pr = pairs[b0 + lane];
+                    const int i = (int)(pr >> 16), j = (int)(pr & 0xffffu);
+                    dp.dense[(size_t)i * n_trk + j] = val;
+                    if (mode == 1) {
+                        deep_top2_insert(&dp.row_top[i], val); atomicAdd(&dp.row_nnz[i], 1);
+                        deep_top2_insert(&dp.col_top[j], val); atomicAdd(&dp.col_nnz[j], 1);
+                    }
                 }
             }
-            if (mode == 1) atomicAdd(&dp.col_nnz[j], 1);
-        });
-        if (mode == 1) {
-            float w = p.w_assoc_emb;
-            if (n_trk >= 2) {                                                    // (:302)
-                const int zeros = n_trk - nnz;
-                if (zeros >= 1) t.push(0.0f);
-                if (zeros >= 2) t.push(0.0f);
-                w = (t.mx == 0.0f) ? 0.0f : xmul(w, deep_aw_weight(t.mx, t.se, p.aw_param));
-            }
-            dp.row_w[i] = w;
         }
     }
     __syncthreads();
-    if (mode == 1 && n_high >= 2) {                                              // (:324)
-        for (int j = tid; j < n_trk; j += nt) {
-            const unsigned long long top = dp.col_top[j];
-            DeepTop2 t{deep_ord2f((unsigned)(top >> 32)), deep_ord2f((unsigned)top)};
-            const int zeros = n_high - dp.col_nnz[j];
-            if (zeros >= 1) t.push(0.0f);
-            if (zeros >= 2) t.push(0.0f);
-            const bool z = (t.mx == 0.0f);
-            dp.col_z[j] = z ? 1 : 0;
-            dp.col_w[j] = z ? 0.0f : deep_aw_weight(t.mx, t.se, p.aw_param);
+    if (tid == 0) sm.flags[3] = 0;
+    if (mode == 1) {
+        for (int i = tid; i < n_high; i += nt) {
+            float w = p.w_assoc_emb;
+            if (n_trk >= 2) {                                                    // (:302)
+                bool z;
+                const float rw = deep_top2_weight(dp.row_top[i], n_trk - dp.row_nnz[i], p.aw_param, z);
+                w = z ? 0.0f : xmul(w, rw);
+            }
+            dp.row_w[i] = w;
         }
+        if (n_high >= 2)                                                         // (:324)
+            for (int j = tid; j < n_trk; j += nt) {
+                bool z;
+                dp.col_w[j] = deep_top2_weight(dp.col_top[j], n_high - dp.col_nnz[j], p.aw_param, z);
+                dp.col_z[j] = z ? 1 : 0;
+            }
     }
     __syncthreads();
     return mode;
@@ -679,7 +771,7 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
         oc_spawn(st, sm, dets, n_new, 0, n_free, id_base, [&](int k) { return (int)sm.high[k]; });
         __syncthreads();
         if constexpr (DEEP) {
-            if (use_emb) deep_spawn_embs(dp, sm, embs, n_new, 0, [&](int k) { return (int)sm.high[k]; });
+            if (use_emb) deep_spawn_embs(dp, sm, embs, a.p, n_new, 0, [&](int k) { return (int)sm.high[k]; });
         }
         for (int k = tid; k < n_new; k += nt) { st.list[k] = sm.list_a[k]; st.twin[sm.list_a[k]] = kNoTwin; }
         if (tid == 0) {
@@ -908,7 +1000,8 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
     oc_spawn(st, sm, dets, n_new, n_trk, n_free, id_base, [&](int k) { return (int)sm.ud[k]; });
     __syncthreads();
     if constexpr (DEEP) {
-        if (use_emb) deep_spawn_embs(dp, sm, embs, n_new, n_trk, [&](int k) { return (int)sm.ud[k]; });
+        if (use_emb) deep_spawn_embs(dp, sm, embs, a.p, n_new, n_trk, [&](int k) { return (int)sm.ud[k]; });
+        __syncthreads();
     }
     {
         // a detection that sits twice in the list has just spawned two bit-identical tracks: link them as twins

@@ -206,7 +206,7 @@ def main():
         hdr = eng.header(0)
         ms = float(np.median(times))
         rows = float(n_out.float().mean().item())
-        n_trk = int(hdr[0]) + (int(hdr[1]) if kind != _lib.TRACKER_OCSORT else 0)
+        n_trk = int(hdr[0]) + (int(hdr[1]) if kind not in (_lib.TRACKER_OCSORT, _lib.TRACKER_DEEPOCSORT) else 0)
         by_frame = 2 * n_trk * state_bytes_per_track + D * 24 + rows * 32 + D * dim * 4
         emit(name, (ms, float(np.min(times))), streams=S, frames_per_launch=T, frames_per_s=S * T / ms * 1e3,
              us_per_frame_per_cta=ms * 1e3 / T / max(1, (S + 147) // 148), mean_output_rows=rows, tracks=n_trk, header=hdr[:16].tolist(),
@@ -230,6 +230,35 @@ def main():
         e = np.stack([p[1] for p in pairs], 1)
         engine_bench("engine_botsort_c3_1024x1024x512", _lib.TRACKER_BOTSORT, 148, 2048, 1024, d, e, warm, T, iters, BOT,
                      state_bytes_per_track=288 + 2048, dim=512)
+    if want("engine_deepocsort"):
+        DOC = dict(det_thresh=0.3, max_age=30, max_obs=50, min_hits=3, iou_threshold=0.3, delta_t=3, inertia=0.2,
+                   w_association_emb=0.5, alpha_fixed_emb=0.95, aw_param=0.5, embedding_off=0, aw_off=0, q_xy_scaling=0.01,
+                   q_s_scaling=0.0001)
+        T, iters, warm = (4, 3, 4) if args.quick else (6, 4, 6)
+        pairs = [synth.embeddings_stream(s, n_frames=warm + T * iters) for s in range(2)]
+        d = np.stack([p[0] for p in pairs], 1)
+        e = np.stack([p[1] for p in pairs], 1)
+        # stable scene (C3's generator): every detection matches, no new objects -> no twin tracks, no exact re-solves
+        engine_bench("engine_deepocsort_c3_1024x1024x512", _lib.TRACKER_DEEPOCSORT, 148, 3072, 2048, d, e, warm, T, iters, DOC,
+                     state_bytes_per_track=224 + 32 + 32 + 2 * 2048, dim=512)
+        # 256 objects + 16 clutter boxes per frame: every clutter box spawns TWO tracks (the reference's twice-listed
+        # leftovers), the re-match sees every row and column twice -> the reference's dense LAPJV runs in every frame
+        T, iters, warm = (5, 3, 15) if args.quick else (10, 4, 20)
+        rng = np.random.default_rng(11)
+        pairs = [synth.embeddings_stream(10 + s, n_frames=warm + T * iters, n_obj=256, dim=128, canvas=(3840, 2160)) for s in range(2)]
+        def with_clutter(dd, ee, k=16):
+            F = dd.shape[0]
+            cw = rng.uniform(40, 120, (F, k))
+            cx, cy = rng.uniform(0, 3840, (F, k)), rng.uniform(0, 2160, (F, k))
+            cl = np.stack([cx - cw / 2, cy - 1.1 * cw, cx + cw / 2, cy + 1.1 * cw, rng.uniform(0.35, 0.9, (F, k)), np.zeros((F, k))], -1)
+            ce = rng.normal(0, 1, (F, k, ee.shape[-1]))
+            ce /= np.linalg.norm(ce, axis=-1, keepdims=True)
+            return np.concatenate([dd, cl.astype(np.float32)], 1), np.concatenate([ee, ce.astype(np.float32)], 1)
+        pairs = [with_clutter(*p) for p in pairs]
+        d = np.stack([p[0] for p in pairs], 1)
+        e = np.stack([p[1] for p in pairs], 1)
+        engine_bench("engine_deepocsort_256obj_16clutter_128d_maxage10", _lib.TRACKER_DEEPOCSORT, 148, 1536, 512, d, e, warm, T, iters,
+                     {**DOC, "max_age": 10}, state_bytes_per_track=224 + 32 + 32 + 2 * 512, dim=128)
     if want("engine_strongsort"):
         SS = dict(max_age=30, min_conf=0.1, max_cos_dist=0.2, max_iou_dist=0.7, n_init=3, nn_budget=100, mc_lambda=0.98, ema_alpha=0.9)
         T, iters, warm = (4, 3, 110) if args.quick else (10, 4, 120)
