@@ -195,10 +195,10 @@ int mot_kf_gating(int kind, const float* recs, int n_tracks, const float* meas4,
  *   2 iou_distance then fuse_score with conf[m] (matching.cpp:130-143) */
 int mot_cost_iou(const float* a, int n, const float* b, int m, const float* conf, float* out, int ld, int mode,
                  void* stream);
-/* hmiou_batch / giou_batch / diou_batch / centroid_batch (include/motcpp/utils/iou.hpp:119-146, :151-187, :258-293, :298-330;
- * SURVEY 8f-4) evaluated pair-wise, kind 3 / 4 / 5 / 6 (frame_w, frame_h: centroid normalisation).  The reference's own
- * expressions only line up when b has one row (SURVEY 8 trap 11); on that domain the results are identical.  ciou (atan)
- * is not provided. */
+/* hmiou_batch / giou_batch / diou_batch / centroid_batch / ciou_batch (include/motcpp/utils/iou.hpp:119-146, :151-187,
+ * :258-293, :298-330, :197-253) evaluated pair-wise, kind 3 / 4 / 5 / 6 / 7 (frame_w, frame_h: centroid
+ * normalisation).  The reference's own expressions only line up when b has one row (SURVEY 8 trap 11); on that domain the
+ * results are identical.  ciou's arc tangent is the correctly rounded fp32 atan (Eigen's array atan is version dependent). */
 int mot_cost_iou_variant(const float* a, int n, const float* b, int m, int kind, int frame_w, int frame_h, float* out, int ld,
                          void* stream);
 /* OC-SORT association cost (ocsort_assoc::associate, src/trackers/ocsort.cpp:617-700): rows = detections

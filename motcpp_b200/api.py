@@ -113,11 +113,11 @@ def iou_distance_fused(atracks, btracks, det_confs) -> np.ndarray:
     return iou_batch(atracks, btracks, _mode=2, _conf=det_confs)
 
 
-_ASSO_KINDS = {"hmiou": 3, "giou": 4, "diou": 5, "centroid": 6}
+_ASSO_KINDS = {"hmiou": 3, "giou": 4, "diou": 5, "centroid": 6, "ciou": 7}
 
 
 def asso_batch(asso_func: str, bboxes1, bboxes2, frame_width: int = 0, frame_height: int = 0) -> np.ndarray:
-    """AssociationFunction (iou.hpp:371-411) for "iou", "hmiou", "giou", "diou", "centroid": (N,4),(M,4) xyxy -> (N,M),
+    """AssociationFunction (iou.hpp:371-411) for "iou", "hmiou", "giou", "diou", "ciou", "centroid": (N,4),(M,4) xyxy -> (N,M),
     evaluated pair-wise (the reference's hmiou / giou / diou expressions only line up for M == 1)."""
     if asso_func == "iou":
         return iou_batch(bboxes1, bboxes2)

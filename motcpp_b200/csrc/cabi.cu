@@ -888,8 +888,8 @@ int mot_cost_iou(const float* a, int n, const float* b, int m, const float* conf
 int mot_cost_iou_variant(const float* a, int n, const float* b, int m, int kind, int frame_w, int frame_h, float* out, int ld,
                          void* stream) {
     if (n < 0 || m < 0 || ld < m) return fail(MOT_ERR_INVALID_ARGUMENT, "bad sizes");
-    if (kind < mot::kVarHmIou || kind > mot::kVarCentroid)
-        return fail(MOT_ERR_INVALID_ARGUMENT, "Invalid association mode: %d (3 hmiou, 4 giou, 5 diou, 6 centroid)", kind);   // iou.hpp:407
+    if (kind < mot::kVarHmIou || kind > mot::kVarCIoU)
+        return fail(MOT_ERR_INVALID_ARGUMENT, "Invalid association mode: %d (3 hmiou, 4 giou, 5 diou, 6 centroid, 7 ciou)", kind);   // iou.hpp:407
     if ((((size_t)a) | ((size_t)b)) & 15) return fail(MOT_ERR_INVALID_ARGUMENT, "box arrays must be 16-byte aligned (they are read as float4)");
     if (n == 0 || m == 0) return MOT_OK;
     if (!a || !b || !out) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");

@@ -108,7 +108,57 @@ struct IouCost {
 };
 
 // hmiou / giou / diou / centroid for ONE pair (include/motcpp/utils/iou.hpp:119-330, pair-wise: see kernels_cost.cuh)
-enum : int { kVarHmIou = 3, kVarGIoU = 4, kVarDIoU = 5, kVarCentroid = 6 };
+enum : int { kVarHmIou = 3, kVarGIoU = 4, kVarDIoU = 5, kVarCentroid = 6, kVarCIoU = 7 };
+
+// correctly rounded fp32 arc tangent: fdlibm's atan in fp64, a fixed sequence of IEEE operations (no FMA), rounded once.
+// oracle/cost.cpp: orc_atanf repeats it operation for operation (ciou, iou.hpp:238-239; see the note there).
+__device__ __forceinline__ float atanf_cr(float xf) {
+    const double hi0 = 4.63647609000806093515e-01, hi1 = 7.85398163397448278999e-01, hi2 = 9.82793723247329054082e-01,
+                 hi3 = 1.57079632679489655800e+00;
+    const double lo0 = 2.26987774529616870924e-17, lo1 = 3.06161699786838301793e-17, lo2 = 1.39033110312309984516e-17,
+                 lo3 = 6.12323399573676603587e-17;
+    const double aT0 = 3.33333333333329318027e-01, aT1 = -1.99999999998764832476e-01, aT2 = 1.42857142725034663711e-01,
+                 aT3 = -1.11111104054623557880e-01, aT4 = 9.09088713343650656196e-02, aT5 = -7.69187620504482999495e-02,
+                 aT6 = 6.66107313738753120669e-02, aT7 = -5.83357013379057348645e-02, aT8 = 4.97687799461593236017e-02,
+                 aT9 = -3.65315727442169155270e-02, aT10 = 1.62858201153657823623e-02;
+    double x = (double)xf;
+    if (!(x == x)) return xf;
+    const bool neg = (__float_as_uint(xf) >> 31) != 0;
+    const double ax = fabs(x);
+    if (ax >= 7.378697629483821e+19) {
+        const double r = __dadd_rn(hi3, lo3);
+        return __double2float_rn(neg ? -r : r);
+    }
+    int id;
+    double hi = 0.0, lo = 0.0;
+    if (ax < 0.4375) {
+        if (ax < 1.862645149230957e-09) return xf;
+        id = -1;
+    } else {
+        x = ax;
+        if (ax < 1.1875) {
+            if (ax < 0.6875) { id = 0; hi = hi0; lo = lo0; x = __ddiv_rn(__dsub_rn(__dmul_rn(2.0, x), 1.0), __dadd_rn(2.0, x)); }
+            else { id = 1; hi = hi1; lo = lo1; x = __ddiv_rn(__dsub_rn(x, 1.0), __dadd_rn(x, 1.0)); }
+        } else {
+            if (ax < 2.4375) { id = 2; hi = hi2; lo = lo2; x = __ddiv_rn(__dsub_rn(x, 1.5), __dadd_rn(1.0, __dmul_rn(1.5, x))); }
+            else { id = 3; hi = hi3; lo = lo3; x = __ddiv_rn(-1.0, x); }
+        }
+    }
+    const double z = __dmul_rn(x, x), w = __dmul_rn(z, z);
+    double s1 = __dadd_rn(aT8, __dmul_rn(w, aT10));
+    s1 = __dadd_rn(aT6, __dmul_rn(w, s1));
+    s1 = __dadd_rn(aT4, __dmul_rn(w, s1));
+    s1 = __dadd_rn(aT2, __dmul_rn(w, s1));
+    s1 = __dmul_rn(z, __dadd_rn(aT0, __dmul_rn(w, s1)));
+    double s2 = __dadd_rn(aT7, __dmul_rn(w, aT9));
+    s2 = __dadd_rn(aT5, __dmul_rn(w, s2));
+    s2 = __dadd_rn(aT3, __dmul_rn(w, s2));
+    s2 = __dmul_rn(w, __dadd_rn(aT1, __dmul_rn(w, s2)));
+    const double t = __dmul_rn(x, __dadd_rn(s1, s2));
+    if (id < 0) return __double2float_rn(__dsub_rn(x, t));
+    const double r = __dsub_rn(hi, __dsub_rn(__dsub_rn(t, lo), x));
+    return __double2float_rn(neg ? -r : r);
+}
 __device__ __forceinline__ float iou_variant_pair(int kind, float4 p, float area_p, float4 q, float norm) {
     if (kind == kVarCentroid) {
         const float dx = xsub(xdiv(xadd(p.x, p.z), 2.0f), xdiv(xadd(q.x, q.z), 2.0f));
@@ -134,6 +184,16 @@ __device__ __forceinline__ float iou_variant_pair(int kind, float4 p, float area
     const float dy = xsub(xdiv(xadd(p.y, p.w), 2.0f), xdiv(xadd(q.y, q.w), 2.0f));
     const float inner = xadd(xmul(dx, dx), xmul(dy, dy));
     const float outer = xadd(xmul(ox, ox), xmul(oy, oy));
+    if (kind == kVarCIoU) {                                                  // iou.hpp:197-253
+        const float eps = 1e-7f;
+        const float w1 = xsub(p.z, p.x), h1 = xsub(p.w, p.y), w2 = xsub(q.z, q.x), h2 = xsub(q.w, q.y);
+        const float ad = xsub(atanf_cr(xdiv(w2, xadd(h2, eps))), atanf_cr(xdiv(w1, xadd(h1, eps))));
+        const float v = xmul(0.40528473f /* 4.0f / float(pi * pi) */, xmul(ad, ad));
+        const float S = xsub(1.0f, iou);
+        const float alpha = xdiv(v, xadd(xadd(S, v), eps));
+        const float c = xadd(xsub(iou, xdiv(inner, xadd(outer, eps))), xmul(alpha, v));
+        return xdiv(xadd(c, 1.0f), 2.0f);
+    }
     return xdiv(xadd(xsub(iou, xdiv(inner, xadd(outer, 1e-10f))), 1.0f), 2.0f);
 }
 

@@ -65,6 +65,7 @@ void orc_iou_batch(const float* a, int n, const float* b, int m, float* out);   
 void orc_iou_distance(const float* a, int n, const float* b, int m, float* out);   /* 1 - iou */
 void orc_fuse_score(float* cost, int n, int m, const float* det_conf);             /* in place */
 /* pair-wise hmiou (kind 3) / giou (4) / diou (5) / centroid (6): include/motcpp/utils/iou.hpp:119-330 */
+float orc_atanf(float x);   /* correctly rounded fp32 arc tangent (ciou contract, cost.cpp) */
 void orc_iou_variant(const float* a, int n, const float* b, int m, int kind, int frame_w, int frame_h, float* out);
 /* metric 0 = cosine, 1 = euclidean (matching.cpp:67-107) */
 void orc_embedding_distance(const float* t, int n, const float* d, int m, int dim, int metric, float* out);

@@ -90,6 +90,7 @@ def lib() -> C.CDLL:
         L.orc_iou_cost_tlwh.argtypes = [f32p, C.c_void_p, C.c_int, f32p, C.c_int, f32p]
         L.orc_clamp_cost.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_float]
         L.orc_kf_xysr_affine.argtypes = [f32p, f32p, f32p, f32p]
+        L.orc_atanf.argtypes, L.orc_atanf.restype = [C.c_float], C.c_float
         L.orc_iou_variant.argtypes = [f32p, C.c_int, f32p, C.c_int, C.c_int, C.c_int, C.c_int, f32p]
         L.orc_aw_max_metric.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, f32p, C.c_int]
         L.orc_ocsort_create.argtypes = [C.c_float, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,

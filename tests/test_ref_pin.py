@@ -202,6 +202,11 @@ def test_cost_builders_and_assignment_equal_reference(order):
             OL.orc_iou_variant(A[:1], 1, B[:1], 1, kind, 1920, 1080, v1)
             assert L.ref_asso_func(name, A[:1], 1, B[:1], 1, 1920, 1080, v2) == 0, L.ref_last_error()
             assert np.array_equal(v1, v2), name
+        # ciou: the stand-in Eigen's .atan() is the box's libm atanf, within 1 ulp of the oracle's correctly rounded atan
+        v1, v2 = np.zeros((1, 1), np.float32), np.zeros((1, 1), np.float32)
+        OL.orc_iou_variant(A[:1], 1, B[:1], 1, 7, 1920, 1080, v1)
+        assert L.ref_asso_func(b"ciou", A[:1], 1, B[:1], 1, 1920, 1080, v2) == 0, L.ref_last_error()
+        assert abs(float(v1[0, 0]) - float(v2[0, 0])) <= 2e-7, (v1, v2)
     assert not cmp.bad, sorted(set(cmp.bad))
 
 

@@ -118,6 +118,37 @@ def test_oracle_iou_variant_kats(oracle):
     assert oracle.iou_variant(5, b1, b1)[0, 0] == 1.0 and oracle.iou_variant(4, b1, b1)[0, 0] == 0.5
 
 
+def test_atanf_is_correctly_rounded_and_ciou_follows_the_formula(oracle):
+    """ciou (iou.hpp:197-253) needs an arc tangent; the contract is the correctly rounded fp32 value (see oracle/cost.cpp)."""
+    import ctypes as C
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([rng.uniform(-4, 4, 20000), 10.0 ** rng.uniform(-12, 25, 4000), -10.0 ** rng.uniform(-12, 25, 1000),
+                         [0, 1, -1, 0.4375, 0.6875, 1.1875, 2.4375, 1e30, -1e30, np.inf, -np.inf]]).astype(np.float32)
+    mine = np.array([oracle.lib().orc_atanf(float(x)) for x in xs], np.float32)
+    assert np.array_equal(mine, np.arctan(xs.astype(np.float64)).astype(np.float32))
+    libm = C.CDLL("libm.so.6")
+    libm.atanf.argtypes, libm.atanf.restype = [C.c_float], C.c_float
+    lm = np.array([libm.atanf(float(x)) for x in xs[:5000]], np.float32)
+    assert np.abs(mine[:5000].view(np.int32) - lm.view(np.int32)).max() <= 1     # the box's libm: within 1 ulp of it
+    # ciou against a float64 re-derivation, and its fixed points
+    def boxes(k):
+        xy = rng.uniform(0, 600, (k, 2)); wh = rng.uniform(5, 200, (k, 2))
+        return np.concatenate([xy, xy + wh], 1).astype(np.float32)
+    a, b = boxes(40), boxes(30)
+    got = oracle.iou_variant(7, a, b)
+    A, B = a.astype(np.float64)[:, None], b.astype(np.float64)[None]
+    iou = oracle.iou_batch(a, b).astype(np.float64)
+    inner = ((A[..., 0] + A[..., 2]) / 2 - (B[..., 0] + B[..., 2]) / 2) ** 2 + ((A[..., 1] + A[..., 3]) / 2 - (B[..., 1] + B[..., 3]) / 2) ** 2
+    outer = (np.maximum(A[..., 2], B[..., 2]) - np.minimum(A[..., 0], B[..., 0])) ** 2 + \
+            (np.maximum(A[..., 3], B[..., 3]) - np.minimum(A[..., 1], B[..., 1])) ** 2 + 1e-7
+    ad = np.arctan((B[..., 2] - B[..., 0]) / (B[..., 3] - B[..., 1] + 1e-7)) - np.arctan((A[..., 2] - A[..., 0]) / (A[..., 3] - A[..., 1] + 1e-7))
+    v = 4 / np.pi ** 2 * ad ** 2
+    want = (iou - inner / outer + v / (1 - iou + v + 1e-7) * v + 1) / 2
+    assert np.allclose(got, want, rtol=0, atol=3e-6)
+    assert oracle.iou_variant(7, [[0, 0, 100, 100]], [[0, 0, 100, 100]])[0, 0] == 1.0          # identical boxes: v = 0, ciou = iou = 1
+    assert oracle.iou_variant(7, [[0, 0, 100, 100]], [[50, 50, 150, 150]])[0, 0] == oracle.iou_variant(5, [[0, 0, 100, 100]], [[50, 50, 150, 150]])[0, 0]
+
+
 # ------------------------------------------------------------------ GPU parity (through the C ABI)
 @pytest.fixture()
 def _gpu():
@@ -233,9 +264,9 @@ def test_iou_variants_bit_exact(oracle, _gpu, n, m):
         return np.concatenate([xy, xy + wh], 1).astype(np.float32)
     a, b = boxes(n), boxes(m)
     b[0] = a[0]
-    for name, kind in (("hmiou", 3), ("giou", 4), ("diou", 5), ("centroid", 6)):
+    for name, kind in (("hmiou", 3), ("giou", 4), ("diou", 5), ("centroid", 6), ("ciou", 7)):
         got = api.asso_batch(name, a, b, 1920, 1080)
         assert np.array_equal(got, oracle.iou_variant(kind, a, b, 1920, 1080)), (name, n, m)
     assert np.array_equal(api.asso_batch("iou", a, b), oracle.iou_batch(a, b))
     with pytest.raises(ValueError):
-        api.asso_batch("ciou", a, b)
+        api.asso_batch("ct_dist", a, b)
