@@ -11,12 +11,11 @@
  * operation order documented in DESIGN.md "Arithmetic contract", compiled with
  * -ffp-contract=off so no FMA is ever formed.
  *
- * Pinning status (see oracle/README.md):
- *   - LAP: pinned against the reference's REAL lap_solver.hpp (oracle/_ref/libref_lap.so)
- *     and against the KATs of reference tests/test_matching.cpp.
- *   - IoU: pinned against tests/test_iou.cpp KATs.  XYSR KF: tests/test_kalman_filter.cpp KATs.
- *   - XYAH / XYWH KF covariances, fuse_score, cosine, gating, tracker state machines:
- *     the reference holds no golden values => "parity unpinned" beyond hand-derived KATs.
+ * Pinning status (see oracle/README.md): every function and all six tracker state
+ * machines are compared with the reference's OWN sources compiled in place (oracle/_ref/libref_lap.so,
+ * libref_core_tb.so, libref_core.so; tests/test_ref_pin.py): bit-exact when the reference's Eigen sums run in
+ * textbook order, ids exact and <= 2e-5 on floats in Eigen 3.4's packet order.  The reference's own KATs
+ * (tests/test_matching.cpp, test_iou.cpp, test_kalman_filter.cpp, test_sort.cpp, test_trackers.cpp) are a second check.
  *
  * All matrices are ROW-MAJOR float unless stated otherwise.
  */

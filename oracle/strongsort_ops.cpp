@@ -6,8 +6,9 @@
 //   linear_assignment::min_cost_matching (threshold clamp)                         src/trackers/strongsort.cpp:372-377
 //   KalmanFilterXYSR::apply_affine_correction                                      src/motion/kalman_filters/xysr_kf.cpp:114-141
 //   deepocsort_assoc::compute_aw_max_metric (DeepOC-SORT adaptive embedding weights) src/trackers/deepocsort.cpp:294-345
-// Pinning: the reference holds no golden values for any of these ("parity unpinned" beyond hand-derived KATs in
-// tests/test_oracle_kats.py).  Eigen's GEMM / .norm() summation order is unspecified; sums here are sequential.
+// Pinning: compute_aw_max_metric and the affine correction are compared with the reference's compiled code
+// (tests/test_ref_pin.py), the StrongSORT builders through the whole compiled strongsort.cpp; hand-derived KATs in
+// tests/test_strongsort_ops.py.  Eigen's GEMM / .norm() summation order is unspecified; sums here are sequential.
 #include "oracle.h"
 
 #include <algorithm>

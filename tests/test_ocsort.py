@@ -3,12 +3,11 @@ sm_100a kernels through the C ABI (GPU) - reference src/trackers/ocsort.cpp.
 
 Ties.  The reference spawns bit-identical "twin" tracks (parity trap 8), so exactly tied
 assignment optima are systematic in OC-SORT.  Oracle modes: tie_mode=0 resolves them with the reference's LAPJV
-scan order (pinned to the real lap_solver.hpp); tie_mode=1 with the "prefer the higher column" infinitesimal of
-the sparse CUDA solver; tie_mode=0 is the CUDA kernel's policy - whenever a twin is an assignment candidate and
-rows + columns <= 384 the kernel re-solves the frame with the reference's own dense LAPJV (csrc/jv_device.cuh), so
-it equals tie_mode=0 there, and falls back to the tie_mode=1 rule for larger problems.  Kernel parity is asserted
-bit for bit against tie_mode=0 (== the reference for every problem of the small shape, where rows + columns <= 320);
-test_tie_modes_differ_only_on_twin_ties measures how modes 0 and 1 relate.
+scan order (pinned to the real lap_solver.hpp and to the reference's compiled ocsort.cpp); tie_mode=1 with the "prefer
+the higher column" infinitesimal of the sparse CUDA solver.  The CUDA kernel's policy is tie_mode=0 at ANY size: every
+frame that can tie is re-solved with the reference's own dense LAPJV on the device (one warp, csrc/jv_device.cuh, while
+rows + columns <= 384; the whole CTA, csrc/jv_block_device.cuh, above).  Kernel parity is asserted bit for bit against
+tie_mode=0; test_tie_modes_differ_only_on_twin_ties measures how modes 0 and 1 relate.
 """
 import ctypes as C
 
@@ -291,7 +290,7 @@ def test_gpu_ocsort_capacity_and_argument_errors(oracle, gpu):
 
 def test_small_shape_kernel_equals_reference_tie_breaking(oracle):
     """rows + columns <= 320 for the 256-track / 64-detection shape, so the kernel's policy IS the reference's LAPJV:
-    tie_mode 2 and tie_mode 0 are the same tracker there, frame after frame, on streams full of twin ties."""
+    two independent oracle instances in tie_mode 0 stay identical frame after frame on streams full of twin ties."""
     for seed in (0, 3):
         d, c = synth.stress_stream(seed, n_frames=150, n_obj=40)
         a, b = oracle.OCSort(**OC_ARGS, tie_mode=0), oracle.OCSort(**OC_ARGS, tie_mode=0)

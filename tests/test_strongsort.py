@@ -68,8 +68,9 @@ def test_oracle_confirmed_track_follows_by_appearance(oracle):
 
 def test_oracle_tie_modes(oracle):
     """Exact ties only come from q1's duplicated rows, and there they matter: the reference's LAPJV order (tie_mode 0)
-    and the large-problem fallback rule (tie_mode 1) part ways on most stress streams.  tie_mode 2 - the CUDA kernel's
-    policy, LAPJV itself while rows + columns <= 384 - is the reference's behaviour on all of them."""
+    and the sparse solver's own rule (tie_mode 1) part ways on most stress streams - which is why the CUDA kernel re-solves
+    every duplicated-row frame with LAPJV itself, at any size.  (tie_mode 2, round 1's size-limited policy, is kept in the
+    oracle only to show that it coincides with tie_mode 0 at these sizes.)"""
     differing = 0
     for sid in range(6):
         d, c, e = synth.stress_stream_reid(sid, n_frames=60, n_obj=20, dim=16)
