@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -1051,27 +1052,33 @@ int mot_lap_jv_batch_device(const float* cost, long long stride_cost, int n_prob
     if (n_problems == 0) return MOT_OK;
     if (!cost || !row2col || !col2row) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
-    if (n + m <= mot::kLapJvMax) {          // one warp per problem, all state in shared memory
-        mot::lap_jv_kernel<<<std::min(n_problems, sm_count() * 16), 32, 0, st>>>(cost, stride_cost, n_problems, n, m, ld, thresh,
-                                                                                 row2col, col2row);
+    int warp_max = mot::kLapJvMax;
+    if (const char* ev = std::getenv("MOT_LAPJV_WARP_MAX")) warp_max = std::atoi(ev);      // measurement aid
+    if (n + m <= warp_max) {                // one warp per problem, all state in shared memory
+        const size_t wsm = mot::jv_work_bytes(n + m + 1);
+        if (wsm > 48 * 1024) MOT_CUDA(cudaFuncSetAttribute(mot::lap_jv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm));
+        mot::lap_jv_kernel<<<std::min(n_problems, sm_count() * 16), 32, wsm, st>>>(cost, stride_cost, n_problems, n, m, ld, thresh,
+                                                                                   row2col, col2row);
         MOT_CUDA(cudaGetLastError());
         return MOT_OK;
     }
-    // any size: one CTA per problem, work arrays in stream-ordered global scratch
-    const size_t smem = mot::jv_block_sbytes(n + m);
+    // any size: one CTA per problem; work arrays in shared memory when they fit, else in stream-ordered global scratch
+    size_t smem = mot::jv_block_sbytes(n + m);
     int dev = 0, max_optin = 0;
     MOT_CUDA(cudaGetDevice(&dev));
     MOT_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const bool all_shared = mot::jv_block_sbytes_full(n + m) + 1024 <= (size_t)max_optin && !std::getenv("MOT_LAPJV_GLOBAL_WORK");
+    if (all_shared) smem = mot::jv_block_sbytes_full(n + m);
     if (smem > (size_t)max_optin)
         return fail(MOT_ERR_INVALID_ARGUMENT, "problem %d x %d needs %zu B of shared memory (limit %d)", n, m, smem, max_optin);
     MOT_CUDA(cudaFuncSetAttribute(mot::lap_jv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = std::min(n_problems, sm_count() * 2);
     unsigned char* gs = nullptr;
-    MOT_CUDA(cudaMallocAsync((void**)&gs, mot::jv_block_gbytes(n + m) * (size_t)grid, st));
+    if (!all_shared) MOT_CUDA(cudaMallocAsync((void**)&gs, mot::jv_block_gbytes(n + m) * (size_t)grid, st));
     mot::lap_jv_block_kernel<<<grid, mot::kLapJvBlockThreads, smem, st>>>(cost, stride_cost, n_problems, n, m, ld, thresh, row2col,
-                                                                          col2row, gs);
+                                                                          col2row, gs, all_shared ? 1 : 0);
     MOT_CUDA(cudaGetLastError());
-    MOT_CUDA(cudaFreeAsync(gs, st));
+    if (gs) MOT_CUDA(cudaFreeAsync(gs, st));
     return MOT_OK;
 }
 

@@ -18,8 +18,9 @@
 //                           prefix-min marks them in a bitmap, thread 0 replays just those swaps; a relax step updates
 //                           all TODO columns in parallel and only the (rare) columns that land exactly on the level are
 //                           replayed in position order - one barrier (__syncthreads_or) per relax step otherwise.
-// fp64 throughout, like the reference.  Work arrays live in global memory (per-stream scratch, L2 resident), the
-// scan order permutation and small reduction scratch in shared memory.
+// fp64 throughout, like the reference.  Work arrays live in shared memory when the caller has room for them
+// (jv_block_sbytes_full), else in global memory (per-stream scratch, L2 resident) with only the scan order permutation
+// and the small reduction scratch in shared memory.
 #pragma once
 #include "jv_device.cuh"
 
@@ -48,9 +49,15 @@ MOT_HD constexpr size_t jv_block_sbytes(int n_max) {          // shared bytes (o
     return (sizeof(int) * (size_t)n_max + sizeof(unsigned) * 2 * (size_t)((n_max + 31) / 32) + 2 * 32 * sizeof(double) +
             2 * 32 * sizeof(int) + 8 * sizeof(int) + 32 + 15) & ~(size_t)15;
 }
-// g: global scratch of jv_block_gbytes(n_max); s: shared scratch of jv_block_sbytes(n_max), 8-byte aligned
-__device__ __forceinline__ JvBlockWork jv_block_carve(unsigned char* g, unsigned char* s, int n_max) {
+// Everything in shared memory: the solver is a chain of a few thousand short steps (one per augmenting-row-reduction
+// row, level and relax step), each a handful of DEPENDENT reads of these arrays - out of L2 that is ~4 us per step
+// (42 ms for a 30 x 622 re-match of duplicated lists), out of shared memory a fraction of it.
+MOT_HD constexpr size_t jv_block_sbytes_full(int n_max) { return jv_block_sbytes(n_max) + jv_block_gbytes(n_max); }
+// g: global scratch of jv_block_gbytes(n_max); s: shared scratch of jv_block_sbytes(n_max), 16-byte aligned -
+// or, all_shared, of jv_block_sbytes_full(n_max) (g is then not touched)
+__device__ __forceinline__ JvBlockWork jv_block_carve(unsigned char* g, unsigned char* s, int n_max, bool all_shared = false) {
     JvBlockWork w;
+    if (all_shared) g = s + jv_block_sbytes(n_max);
     w.v = (double*)g;       g += sizeof(double) * (size_t)n_max;
     w.dist = (double*)g;    g += sizeof(double) * (size_t)n_max;
     w.x = (int*)g;          g += sizeof(int) * (size_t)n_max;

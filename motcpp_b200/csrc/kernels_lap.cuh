@@ -45,8 +45,8 @@ constexpr int kLapJvMax = 384;
 
 __global__ void __launch_bounds__(32) lap_jv_kernel(const float* __restrict__ cost, long long stride_cost, int n_problems, int n, int m,
                                                     int ld, float thresh, int* __restrict__ row2col, int* __restrict__ col2row) {
-    __shared__ __align__(16) unsigned char work[jv_work_bytes(kLapJvMax + 1)];
-    const JvWork w = jv_carve(work, kLapJvMax + 1);
+    MOT_DYNAMIC_SMEM(work);                                   // jv_work_bytes(n + m + 1)
+    const JvWork w = jv_carve(work, n + m + 1);
     for (int p = (int)blockIdx.x; p < n_problems; p += (int)gridDim.x) {
         warp_dense_lapjv(JvCost{cost + (size_t)p * stride_cost, n, m, ld, (double)thresh / 2.0}, n + m, w);
         for (int i = (int)threadIdx.x; i < n; i += 32) { const int j = w.x[i]; row2col[(size_t)p * n + i] = j < m ? j : -1; }
@@ -62,11 +62,11 @@ constexpr int kLapJvBlockThreads = 512;
 __global__ void __launch_bounds__(kLapJvBlockThreads) lap_jv_block_kernel(const float* __restrict__ cost, long long stride_cost,
                                                                           int n_problems, int n, int m, int ld, float thresh,
                                                                           int* __restrict__ row2col, int* __restrict__ col2row,
-                                                                          unsigned char* __restrict__ gscratch) {
+                                                                          unsigned char* __restrict__ gscratch, int all_shared) {
     MOT_DYNAMIC_SMEM(smem);
     __shared__ BlockScratch bs;
     const int N = n + m;
-    const JvBlockWork w = jv_block_carve(gscratch + (size_t)blockIdx.x * jv_block_gbytes(N), smem, N);
+    const JvBlockWork w = jv_block_carve(all_shared ? nullptr : gscratch + (size_t)blockIdx.x * jv_block_gbytes(N), smem, N, all_shared != 0);
     for (int p = (int)blockIdx.x; p < n_problems; p += (int)gridDim.x) {
         block_dense_lapjv(JvCost{cost + (size_t)p * stride_cost, n, m, ld, (double)thresh / 2.0}, N, w, &bs);
         for (int i = (int)threadIdx.x; i < n; i += (int)blockDim.x) { const int j = w.x[i]; row2col[(size_t)p * n + i] = j < m ? j : -1; }

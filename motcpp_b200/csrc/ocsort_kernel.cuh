@@ -430,7 +430,7 @@ __device__ __forceinline__ void oc_exact_assignment(const OcStream& st, OcSmem& 
         for (int j = tid; j < m; j += nt) { const int i = w.y[j]; sm.lap.col2row[j] = (short)(i < n ? i : -1); }
     } else {
         unsigned char* idle = (unsigned char*)sm.lap.row_label;         // [row_label, row2col) is dead between two block_lap calls
-        const JvBlockWork w = jv_block_carve(st.jv_work, idle, n + m);
+        const JvBlockWork w = jv_block_carve(st.jv_work, idle, n + m, jv_block_sbytes_full(n + m) <= (size_t)((unsigned char*)sm.lap.row2col - idle));
         block_dense_lapjv(cost, n + m, w, sm.bs);
         for (int i = tid; i < n; i += nt) { const int j = w.x[i]; sm.lap.row2col[i] = (short)(j < m ? j : -1); }
         for (int j = tid; j < m; j += nt) { const int i = w.y[j]; sm.lap.col2row[j] = (short)(i < n ? i : -1); }

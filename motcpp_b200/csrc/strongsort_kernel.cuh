@@ -533,7 +533,9 @@ __device__ __forceinline__ void ss_frame(const SsArgs& a, const SsStream& st, Ss
                     jx = w.x; jy = w.y;
                 } else {
                     // [row_label, row2col) of the sparse solver is idle here
-                    const JvBlockWork w = jv_block_carve(st.jv_work, (unsigned char*)sm.lap.row_label, n_rb + n_cb);
+                    const size_t idle_bytes = (size_t)((unsigned char*)sm.lap.row2col - (unsigned char*)sm.lap.row_label);
+                    const JvBlockWork w = jv_block_carve(st.jv_work, (unsigned char*)sm.lap.row_label, n_rb + n_cb,
+                                                         jv_block_sbytes_full(n_rb + n_cb) <= idle_bytes);
                     block_dense_lapjv(jc, n_rb + n_cb, w, sm.bs);
                     jx = w.x; jy = w.y;
                 }

@@ -28,13 +28,15 @@ int sim_lap(const float* cost, int n, int m, int ld, float thresh, int* row2col,
 int sim_lap_jv(const float* cost, int n, int m, int ld, float thresh, int* row2col, int* col2row, int block, int threads) {
     if (!block) {
         if (n + m > mot::kLapJvMax) return -1;
-        cpusim::launch(dim3(1), dim3(32), 0, [=] { mot::lap_jv_kernel(cost, 0, 1, n, m, ld, thresh, row2col, col2row); });
+        cpusim::launch(dim3(1), dim3(32), mot::jv_work_bytes(n + m + 1), [=] { mot::lap_jv_kernel(cost, 0, 1, n, m, ld, thresh, row2col, col2row); });
         return 0;
     }
     std::vector<unsigned char> gs(mot::jv_block_gbytes(n + m) + 64);
     unsigned char* g = gs.data();
-    cpusim::launch(dim3(1), dim3(threads), mot::jv_block_sbytes(n + m),
-                   [=] { mot::lap_jv_block_kernel(cost, 0, 1, n, m, ld, thresh, row2col, col2row, g); });
+    // block = 1: work arrays in global scratch; block = 2: everything in shared memory
+    const int all_shared = block == 2;
+    cpusim::launch(dim3(1), dim3(threads), all_shared ? mot::jv_block_sbytes_full(n + m) : mot::jv_block_sbytes(n + m),
+                   [=] { mot::lap_jv_block_kernel(cost, 0, 1, n, m, ld, thresh, row2col, col2row, g, all_shared); });
     return 0;
 }
 

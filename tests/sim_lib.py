@@ -87,6 +87,17 @@ def lib():
     return _LIB
 
 
+def sim_lap_jv(cost, thresh, block=0, threads=128):
+    """the reference-order dense LAPJV kernels under the emulator: block 0 = one warp, 1 = whole CTA with the work arrays in
+    global scratch, 2 = whole CTA with everything in shared memory"""
+    cost = np.ascontiguousarray(cost, np.float32)
+    n, m = cost.shape
+    r = np.full(max(n, 1), -7, np.int32)
+    q = np.full(max(m, 1), -7, np.int32)
+    assert lib().sim_lap_jv(cost, n, m, max(m, 1), float(thresh), r, q, block, threads) == 0
+    return r[:n], q[:m]
+
+
 def sim_lap(cost, thresh, e_cap=4096, threads=128):
     cost = np.ascontiguousarray(cost, np.float32)
     n, m = cost.shape

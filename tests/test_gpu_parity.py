@@ -152,6 +152,18 @@ def test_device_lapjv_reproduces_reference_ties_cta_wide(oracle, n, m, kind):
         assert np.array_equal(r2c[p], ref[0]) and np.array_equal(c2r[p], ref[1]), (n, m, kind, p)
 
 
+def test_device_lapjv_with_work_arrays_in_global_scratch(oracle, monkeypatch):
+    """The CTA-wide LAPJV keeps its work arrays in shared memory when they fit (always, at these sizes, for the stand-alone
+    entry point); the engines fall back to per-stream global scratch for big problems - force that path here."""
+    monkeypatch.setenv("MOT_LAPJV_GLOBAL_WORK", "1")
+    rng = np.random.default_rng(77)
+    for n, m, kind in ((300, 200, 3), (256, 448, 1)):
+        c, th = _tie_cost(rng, kind, n, m)
+        r2c, c2r = api.linear_assignment_reference_order(c, th)
+        ref = _reference_lap(oracle, c, th)
+        assert np.array_equal(r2c, ref[0]) and np.array_equal(c2r, ref[1]), (n, m, kind)
+
+
 def test_device_lapjv_on_a_c2_frame_with_duplicated_detections(oracle):
     """A real C2 cost matrix (256 tracks x 448 detections, 1 - IoU * conf) in which 40 detections appear twice: exactly
     tied optima at the headline size, resolved as the reference resolves them."""

@@ -132,15 +132,28 @@ def main():
     if want("lapjv"):
         import oracle_lib as O
         dets = synth.bytetrack_stream(0, n_frames=2)
-        for (nr, nc, tag) in ((96, 160, "one_warp"), (256, 448, "cta_wide_c2_frame")):
-            cost = O.fuse_score(O.iou_distance(dets[0, :nr, :4], dets[1, :nc, :4]), dets[1, :nc, 4])
+        rng = np.random.default_rng(3)
+        dd = np.concatenate([dets[0, :15, :4]] * 2)                      # a DeepOC-SORT style re-match: every row and column twice
+        tt = np.concatenate([np.concatenate([dets[1, :10, :4], dets[1, 100:401, :4]])] * 2)
+        rematch = -O.iou_batch(dd, tt)
+        for (nr, nc, tag) in ((96, 160, "one_warp"), (256, 448, "cta_wide_c2_frame"), (256, 448, "one_warp_c2_frame"),
+                              (30, 622, "cta_wide_rematch"), (30, 622, "one_warp_rematch")):
+            os.environ.pop("MOT_LAPJV_WARP_MAX", None)
+            if tag.startswith("one_warp_"):
+                os.environ["MOT_LAPJV_WARP_MAX"] = "4000"
+            thr = 0.8
+            if "rematch" in tag:
+                cost, thr = rematch, -0.3
+            else:
+                cost = O.fuse_score(O.iou_distance(dets[0, :nr, :4], dets[1, :nc, :4]), dets[1, :nc, 4])
             P = 148
             costs = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(cost, (P,) + cost.shape))).to(dev).contiguous()
             r2c = torch.empty((P, nr), dtype=torch.int32, device=dev)
             c2r = torch.empty((P, nc), dtype=torch.int32, device=dev)
-            ms = timeit(lambda: api.check(lib.mot_lap_jv_batch_device(costs.data_ptr(), nr * nc, P, nr, nc, nc, 0.8, r2c.data_ptr(),
+            ms = timeit(lambda: api.check(lib.mot_lap_jv_batch_device(costs.data_ptr(), nr * nc, P, nr, nc, nc, thr, r2c.data_ptr(),
                                                                       c2r.data_ptr(), st)), iters=3, warm=1)
-            ref = O.linear_assignment(cost, 0.8)
+            ref = O.linear_assignment(cost, thr)
+            os.environ.pop("MOT_LAPJV_WARP_MAX", None)
             emit(f"lapjv_{nr}x{nc}_{tag}", ms, problems=P, us_per_solve_per_sm=1e3 * ms[0], matches_oracle=bool(np.array_equal(r2c[0].cpu().numpy(), ref[0])),
                  bound="latency (serial shortest augmenting paths; no HBM/tensor roofline)")
 
