@@ -15,7 +15,10 @@
 //   augmenting row reduct.  per free row a lexicographic (value, index) top-2 block reduction, bookkeeping on
 //                           thread 0 (two barriers per row)
 //   shortest augm. paths    the level-opening scan only acts at weak prefix minima of dist[order[k]]: a block-wide
-//                           prefix-min marks them in a bitmap, thread 0 replays just those swaps; a relax step updates
+//                           prefix-min marks them in a bitmap.  On the extended matrix these "records" come by the
+//                           hundred (its dummy rows / columns tie exactly), so their swaps are not replayed one by one
+//                           (measured: 130 k cycles per level, 80 % of the solve) but applied as the permutation they
+//                           compose to, in parallel (jv_block_apply_records); a relax step updates
 //                           all TODO columns in parallel and only the (rare) columns that land exactly on the level are
 //                           replayed in position order - one barrier (__syncthreads_or) per relax step otherwise.
 // fp64 throughout, like the reference.  Work arrays live in shared memory when the caller has room for them
@@ -23,6 +26,10 @@
 // and the small reduction scratch in shared memory.
 #pragma once
 #include "jv_device.cuh"
+
+#ifndef MOT_JV_SERIAL_RECORDS
+#define MOT_JV_SERIAL_RECORDS 40     // level openings with at most this many records are replayed by thread 0
+#endif
 
 namespace mot {
 
@@ -33,7 +40,8 @@ struct JvBlockWork {            // N_max entries each
     int* y;                     // global
     int* fr;                    // global: free rows
     int* pred;                  // global
-    int* cnt;                   // global: columns whose minimum sits in this row (column reduction)
+    int* cnt;                   // global: columns whose minimum sits in this row (column reduction); later the event ranks
+    int* tmp;                   // global: staging of the level-opening permutation
     int* order;                 // shared (or global): scan-order permutation of find_path_dense
     unsigned* bits;             // shared: 2 x ceil(N_max / 32) words (event bitmap, strict-record bitmap)
     // reduction scratch, shared
@@ -43,7 +51,7 @@ struct JvBlockWork {            // N_max entries each
 };
 
 MOT_HD constexpr size_t jv_block_gbytes(int n_max) {          // global bytes
-    return ((size_t)n_max * (2 * sizeof(double) + 5 * sizeof(int)) + 64 + 15) & ~(size_t)15;
+    return ((size_t)n_max * (2 * sizeof(double) + 6 * sizeof(int)) + 64 + 15) & ~(size_t)15;
 }
 MOT_HD constexpr size_t jv_block_sbytes(int n_max) {          // shared bytes (order included)
     return (sizeof(int) * (size_t)n_max + sizeof(unsigned) * 2 * (size_t)((n_max + 31) / 32) + 2 * 32 * sizeof(double) +
@@ -64,7 +72,8 @@ __device__ __forceinline__ JvBlockWork jv_block_carve(unsigned char* g, unsigned
     w.y = (int*)g;          g += sizeof(int) * (size_t)n_max;
     w.fr = (int*)g;         g += sizeof(int) * (size_t)n_max;
     w.pred = (int*)g;       g += sizeof(int) * (size_t)n_max;
-    w.cnt = (int*)g;
+    w.cnt = (int*)g;        g += sizeof(int) * (size_t)n_max;
+    w.tmp = (int*)g;
     w.pv1 = (double*)s;     s += 32 * sizeof(double);
     w.pv2 = (double*)s;     s += 32 * sizeof(double);
     w.pi1 = (int*)s;        s += 32 * sizeof(int);
@@ -104,6 +113,67 @@ __device__ __forceinline__ JvTop2 jv_block_top2(JvTop2 t, const JvBlockWork& w) 
     if (tid == 0)
         for (int k = 1; k < nw; ++k) t = jv_merge(t, JvTop2{w.pv1[k], w.pi1[k], w.pv2[k], w.pi2[k]});
     return t;
+}
+
+// The swaps of one run of level-opening records, as ONE permutation.  Sequentially (lap_solver.hpp:127-137) the records
+// at positions k_0 < k_1 < ... < k_{T-1} do   swap(order[k_t], order[h0 + t]),  t = 0 .. T-1   (k_t >= h0 + t).
+//   * order[k_t] is untouched before step t and position h0 + t is untouched after it, so the front ends up as
+//     order'[h0 + t] = order[k_t];
+//   * what step t displaces from position h0 + t goes to k_t; if k_t lies inside the front [h0, h0 + T) it is displaced
+//     again at step k_t - h0, and so on: the element that STARTS at a front position which is not itself a record hops
+//     along  p -> k_{p - h0}  until it leaves the front.  The hops only go up, so in-place pointer jumping on the k
+//     array finds every chain's landing position in log T rounds.
+// ev: record bitmap by position; records taken from [pb, pe).  K = w.cnt (ranks -> positions), staging in w.tmp, the
+// per-word rank offsets in wb.  All threads of the block must call; returns T.
+__device__ __forceinline__ int jv_block_apply_records(const JvBlockWork& w, const unsigned* ev, unsigned* wb, int pb, int pe, int h0) {
+    const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
+    int* K = w.cnt;
+    const int q0 = pb >> 5, q1 = (pe - 1) >> 5;
+    auto word = [&](int q) {                              // the records of word q that lie in [pb, pe)
+        unsigned b = ev[q];
+        if (q == q0) b &= 0xffffffffu << (pb & 31);
+        if (q == q1 && (pe & 31)) b &= 0xffffffffu >> (32 - (pe & 31));
+        return b;
+    };
+    if (tid == 0) {
+        int acc = 0;
+        for (int q = q0; q <= q1; ++q) { wb[q] = (unsigned)acc; acc += __popc(word(q)); }
+        w.ctl[4] = acc;
+    }
+    __syncthreads();
+    const int T = w.ctl[4];
+    __syncthreads();                                      // ctl[4] is rewritten by the next run
+    if (T == 0) return 0;
+    for (int p = pb + tid; p < pe; p += nt) {
+        const unsigned b = word(p >> 5);
+        if ((b >> (p & 31)) & 1u) K[wb[p >> 5] + __popc(b & ((1u << (p & 31)) - 1u))] = p;
+    }
+    __syncthreads();
+    auto is_record = [&](int p) { return p >= pb && p < pe && ((ev[p >> 5] >> (p & 31)) & 1u); };
+    for (int t = tid; t < T; t += nt) w.tmp[h0 + t] = w.order[K[t]];
+    __syncthreads();
+    const int front_end = h0 + T;
+    for (;;) {                                            // K[t] <- landing position of the chain through node t
+        bool more = false;
+        for (int t = tid; t < T; t += nt) {
+            const int q = K[t];
+            if (q < front_end && q != h0 + t) {
+                const int nq = K[q - h0];
+                K[t] = nq;
+                more |= nq < front_end;
+            }
+        }
+        if (!__syncthreads_or(more ? 1 : 0)) break;
+    }
+    for (int t = tid; t < T; t += nt)
+        if (!is_record(h0 + t)) w.tmp[K[t]] = w.order[h0 + t];
+    __syncthreads();
+    for (int t = tid; t < T; t += nt) {
+        w.order[h0 + t] = w.tmp[h0 + t];
+        if (!is_record(h0 + t)) w.order[K[t]] = w.tmp[K[t]];
+    }
+    __syncthreads();
+    return T;
 }
 
 // lap_solver.hpp:115-211 (find_path_dense + the augmentation), whole block.
@@ -148,26 +218,58 @@ static __device__ __noinline__ void jv_block_augment_from(const JvCost& c, int N
                 if (a < run) run = a;
             }
             __syncthreads();
+            // few records: thread 0 replays their swaps; many (the extended matrix ties by the hundred): the runs between
+            // strict records are applied as permutations by the whole block
+            constexpr int kSerialRecords = MOT_JV_SERIAL_RECORDS, kMaxRuns = 30;
             if (tid == 0) {
-                int h = lo + 1;
+                int n_rec = 0, n_strict = 0;
                 for (int q = (lo + 1) >> 5; q < words; ++q) {
-                    unsigned bitsq = ev[q];
-                    const unsigned sq = strict[q];
-                    ev[q] = 0; strict[q] = 0;
-                    while (bitsq) {
-                        const int b = __ffs((int)bitsq) - 1;
-                        bitsq &= bitsq - 1;
-                        const int k = (q << 5) + b;
-                        const int j = w.order[k];
-                        if ((sq >> b) & 1u) h = lo;          // strictly smaller: the level restarts at lo (:131)
-                        w.order[k] = w.order[h];
-                        w.order[h++] = j;
+                    n_rec += __popc(ev[q]);
+                    unsigned sq = strict[q];
+                    while (sq) {
+                        const int b = __ffs((int)sq) - 1;
+                        sq &= sq - 1;
+                        if (n_strict < kMaxRuns) w.pi1[n_strict] = (q << 5) + b;
+                        ++n_strict;
                     }
                 }
-                w.ctl[0] = h;
+                const bool serial = n_rec <= kSerialRecords || n_strict > kMaxRuns;
+                if (serial) {
+                    int h = lo + 1;
+                    for (int q = (lo + 1) >> 5; q < words; ++q) {
+                        unsigned bitsq = ev[q];
+                        const unsigned sq = strict[q];
+                        ev[q] = 0; strict[q] = 0;
+                        while (bitsq) {
+                            const int b = __ffs((int)bitsq) - 1;
+                            bitsq &= bitsq - 1;
+                            const int k = (q << 5) + b;
+                            const int j = w.order[k];
+                            if ((sq >> b) & 1u) h = lo;          // strictly smaller: the level restarts at lo (:131)
+                            w.order[k] = w.order[h];
+                            w.order[h++] = j;
+                        }
+                    }
+                    w.ctl[0] = h;
+                }
                 w.ctl[1] = -1;
+                w.ctl[2] = serial ? -1 : n_strict;
             }
             __syncthreads();
+            const int n_runs = w.ctl[2];                         // strict records = run boundaries; -1: already replayed
+            if (n_runs >= 0) {
+                int h = lo + 1;
+                for (int g = 0; g <= n_runs; ++g) {
+                    const int pb = g == 0 ? lo + 1 : w.pi1[g - 1];
+                    const int pe = g == n_runs ? N : w.pi1[g];
+                    const int h0 = g == 0 ? lo + 1 : lo;         // a strict record restarts the level at lo (:131)
+                    if (pe > pb) h = h0 + jv_block_apply_records(w, ev, strict, pb, pe, h0);
+                    else h = h0;
+                }
+                for (int q = ((lo + 1) >> 5) + tid; q < words; q += nt) { ev[q] = 0; strict[q] = 0; }
+                if (tid == 0) w.ctl[0] = h;
+                __syncthreads();
+            }
             hi = w.ctl[0];
             // the LAST free column of the level is the sink (:139-141)
             for (int k = lo + tid; k < hi; k += nt)

@@ -599,7 +599,8 @@ MOT_HD constexpr size_t lap_idle_bytes(int n_max, int m_max, int e_cap) {
     const int a = e_cap > n_max + 1 ? e_cap : n_max + 1;
     return lap_align16(sizeof(int) * (size_t)n_max) + lap_align16(sizeof(int) * (size_t)m_max) + lap_align16(sizeof(int) * (size_t)a) +
            lap_align16(sizeof(int) * (size_t)n_max) + lap_align16(sizeof(unsigned short) * (size_t)n_max) +
-           lap_align16(sizeof(unsigned short) * (size_t)m_max) + lap_align16(sizeof(unsigned short) * (size_t)n_max);
+           lap_align16(sizeof(unsigned short) * (size_t)m_max) + lap_align16(sizeof(unsigned short) * (size_t)n_max) +
+           lap_align16(grid_smem_bytes(n_max > m_max ? n_max : m_max));
 }
 
 __device__ __forceinline__ unsigned char* lap_carve(unsigned char* p, int n_max, int m_max, int e_cap, LapWorkspace& ws) {
@@ -611,16 +612,19 @@ __device__ __forceinline__ unsigned char* lap_carve(unsigned char* p, int n_max,
     ws.comp_rows = (unsigned short*)p; p += lap_align16(sizeof(unsigned short) * (size_t)n_max);
     ws.comp_cols = (unsigned short*)p; p += lap_align16(sizeof(unsigned short) * (size_t)m_max);
     ws.comp_list = (unsigned short*)p; p += lap_align16(sizeof(unsigned short) * (size_t)n_max);
+    // the grid sits inside the idle span [row_label, row2col): it is rebuilt by every block_lap call, so between calls its
+    // bytes serve the dense LAPJV's work arrays / the DeepOC-SORT summation tiles like the arrays above
+    unsigned char* const grid_at = p;
+    grid_carve(p, n_max > m_max ? n_max : m_max, ws.grid);  p += lap_align16(grid_smem_bytes(n_max > m_max ? n_max : m_max));
     ws.row2col = (short*)p;            p += lap_align16(sizeof(short) * (size_t)n_max);
     ws.col2row = (short*)p;            p += lap_align16(sizeof(short) * (size_t)m_max);
     ws.ctl = (int*)p;                  p += lap_align16(sizeof(int) * 8);
     ws.bs = (BlockScratch*)p;          p += lap_align16(sizeof(BlockScratch));
-    grid_carve(p, n_max > m_max ? n_max : m_max, ws.grid);  p += lap_align16(grid_smem_bytes(n_max > m_max ? n_max : m_max));
     ws.e_cap = e_cap;
     ws.clk = nullptr;
     ws.clk_base = 0;
-    ws.pairs = ws.scratch_b;
-    ws.p_cap = (int)(((unsigned char*)ws.row2col - (unsigned char*)ws.scratch_b) / sizeof(int));
+    ws.pairs = ws.scratch_b;           // overlapping-pair buffer of the candidate search: up to the grid it is collected through
+    ws.p_cap = (int)((grid_at - (unsigned char*)ws.scratch_b) / sizeof(int));
     return p;
 }
 

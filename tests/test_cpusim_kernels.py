@@ -166,3 +166,21 @@ def test_reference_order_lapjv_kernels_under_emulator(oracle):
         for block, threads in ((0, 32), (1, 64), (2, 64), (2, 128)):
             got = sim_lib.sim_lap_jv(c, th, block, threads)
             assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), (trial, n, m, kind, block)
+        with sim_lib.variant("jvblock"):            # level-opening records applied as parallel permutations (serial limit 2)
+            for block, threads in ((1, 64), (2, 96)):
+                got = sim_lib.sim_lap_jv(c, th, block, threads)
+                assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), (trial, n, m, kind, block, "parallel records")
+    # larger problems: more than 40 records per level with the product's own limit
+    for trial, (n, m, kind) in enumerate(((60, 90, 1), (20, 140, 3), (100, 70, 2), (12, 150, 3))):
+        if kind == 1:
+            c = rng.integers(0, 4, (n, m)) / 4
+        elif kind == 2:
+            c = np.where(rng.random((n, m)) < 0.7, 1.0, rng.random((n, m)))
+        else:
+            c = -(rng.integers(0, 6, (n, m)) / 5.0)
+        th = -0.3 if kind == 3 else 0.8
+        c = c.astype(np.float32)
+        want = oracle.linear_assignment(c, th)
+        for block, threads in ((1, 128), (2, 128)):
+            got = sim_lib.sim_lap_jv(c, th, block, threads)
+            assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), ("large", trial, block)
