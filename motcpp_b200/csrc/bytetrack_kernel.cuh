@@ -311,7 +311,10 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
         for (int i = tid; i < n2; i += nt) sm.row_box[i] = bt_track_box(st.recs + (size_t)sm.list_a[i] * kBtRecFloats);
         __syncthreads();
         IouCost cost{sm.row_box, sm.det_box, sm.det_conf, sm.lo, false, true};
+        sm.lap.clk = a.prof ? &clk : nullptr;
+        sm.lap.clk_base = 20;
         block_lap(sm.lap, n2, n_lo, cap, lap_m_max, 0.5f, cost);
+        sm.lap.clk = nullptr;
         const int n_m2 = block_compact(n2, 0, sm.bs, [&](int i) { return sm.lap.row2col[i] >= 0; },
                                        [&](int i, int pos) { sm.sel[pos] = (unsigned short)i; });
         for (int k = tid; k < n_m2; k += nt) sm.list_c[k] = sm.lo[sm.lap.row2col[sm.sel[k]]];
@@ -337,7 +340,10 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
         for (int i = tid; i < n_unc; i += nt) sm.row_box[i] = bt_track_box(st.recs + (size_t)sm.unconf[i] * kBtRecFloats);
         __syncthreads();
         IouCost cost{sm.row_box, sm.det_box, sm.det_conf, sm.udet, true, true};
+        sm.lap.clk = a.prof ? &clk : nullptr;
+        sm.lap.clk_base = 24;
         block_lap(sm.lap, n_unc, n_udet, cap, lap_m_max, 0.7f, cost);
+        sm.lap.clk = nullptr;
         const int n_m3 = block_compact(n_unc, 0, sm.bs, [&](int i) { return sm.lap.row2col[i] >= 0; },
                                        [&](int i, int pos) { sm.sel[pos] = (unsigned short)i; });
         for (int k = tid; k < n_m3; k += nt) sm.list_a[k] = sm.udet[sm.lap.row2col[sm.sel[k]]];

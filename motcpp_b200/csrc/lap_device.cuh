@@ -378,40 +378,13 @@ __device__ void block_lap_solve(LapWorkspace& ws, int n, int m, int n_max, int m
             }
         }
     }
+    if (tid == 0) ws.ctl[2] = 0;                               // (the label-propagation flag is dead) cursor of the team queue
     __syncthreads();
     const int n_triv = ws.ctl[3], n_team = ws.ctl[5], n_warp = ws.ctl[6];
-    for (int k = tid; k < n_triv; k += nt) {
-        const int root = (int)list_triv[k];
-        const int o0 = off[root], o1 = off[root + 1];
-        const int pr = o0 & 0xffff, r = (o1 & 0xffff) - pr;
-        const int pc = o0 >> 16, c = (o1 >> 16) - pc;
-        double best = 0.0;
-        int bi = -1, bj = -1;
-        for (int a = 0; a < r; ++a)
-            for (int b = 0; b < c; ++b) {
-                const int i = (int)ws.comp_rows[pr + a], j = (int)ws.comp_cols[pc + b];
-                const float cf0 = cost.pair(i, j);
-                if (!(cf0 <= thresh)) continue;
-                const double cf = (double)cf0 + cost.pair_bias(i, j);
-                if (bi < 0 || cf < best || (cf == best && (i < bi || (i == bi && j < bj)))) { best = cf; bi = i; bj = j; }
-            }
-        if (bi >= 0) { ws.row2col[bi] = (short)bj; ws.col2row[bj] = (short)bi; }
-    }
-    {
-        const int tl = lane & 7, team = tid >> 3, n_teams = nt >> 3;
-        const unsigned tmask = 0xffu << (lane & 24);
-        for (int k = team; k < n_team; k += n_teams) {
-            const int root = (int)list_team[k];
-            const int o0 = off[root], o1 = off[root + 1];
-            const int pr = o0 & 0xffff, r = (o1 & 0xffff) - pr;
-            const int pc = o0 >> 16, c = (o1 >> 16) - pc;
-            unsigned short* rows = ws.comp_rows + pr;
-            unsigned short* cols = ws.comp_cols + pc;
-            team_sort_u16<8>(tmask, tl, rows, r);              // the fill order is arbitrary; ties go to the lowest index
-            team_sort_u16<8>(tmask, tl, cols, c);
-            team_hungarian<8>(tmask, tl, rows, r, cols, c, thresh, cost, ws.row2col, ws.col2row);
-        }
-    }
+    // Longest work first: the warp-class components are the long poles of this phase (measured on the C2 workload: 33 k of
+    // its 59 k cycles, against 18 k for the teams and 5 k for the trivial ones), so every warp pulls from their queue
+    // before anything else and the short components fill in behind them; all three classes are handed out dynamically or
+    // per thread, so no warp waits for another until the final barrier.  Components are disjoint: any order is the same result.
     for (;;) {
         int k = 0;
         if (lane == 0) k = atomicAdd(&ws.ctl[4], 1);
@@ -428,6 +401,46 @@ __device__ void block_lap_solve(LapWorkspace& ws, int n, int m, int n_max, int m
         if (r + c <= 32) team_hungarian<32>(kFullMask, lane, rows, r, cols, c, thresh, cost, ws.row2col, ws.col2row);
         else warp_hungarian_big(LapGlobalScratch{ws.g_u, ws.g_v, ws.g_minv, ws.g_way, ws.g_prow, ws.g_flags}, m_max, n_max,
                                 rows, r, pr, cols, c, pc, thresh, cost, ws.row2col, ws.col2row);
+    }
+    {
+        const int tl = lane & 7;
+        const unsigned tmask = 0xffu << (lane & 24);
+        for (;;) {                                             // four team components per warp and pull
+            int k4 = 0;
+            if (lane == 0) k4 = atomicAdd(&ws.ctl[2], 4);
+            k4 = __shfl_sync(kFullMask, k4, 0);
+            if (k4 >= n_team) break;
+            const int k = k4 + (lane >> 3);
+            if (k < n_team) {
+                const int root = (int)list_team[k];
+                const int o0 = off[root], o1 = off[root + 1];
+                const int pr = o0 & 0xffff, r = (o1 & 0xffff) - pr;
+                const int pc = o0 >> 16, c = (o1 >> 16) - pc;
+                unsigned short* rows = ws.comp_rows + pr;
+                unsigned short* cols = ws.comp_cols + pc;
+                team_sort_u16<8>(tmask, tl, rows, r);          // the fill order is arbitrary; ties go to the lowest index
+                team_sort_u16<8>(tmask, tl, cols, c);
+                team_hungarian<8>(tmask, tl, rows, r, cols, c, thresh, cost, ws.row2col, ws.col2row);
+            }
+            __syncwarp();
+        }
+    }
+    for (int k = tid; k < n_triv; k += nt) {
+        const int root = (int)list_triv[k];
+        const int o0 = off[root], o1 = off[root + 1];
+        const int pr = o0 & 0xffff, r = (o1 & 0xffff) - pr;
+        const int pc = o0 >> 16, c = (o1 >> 16) - pc;
+        double best = 0.0;
+        int bi = -1, bj = -1;
+        for (int a = 0; a < r; ++a)
+            for (int b = 0; b < c; ++b) {
+                const int i = (int)ws.comp_rows[pr + a], j = (int)ws.comp_cols[pc + b];
+                const float cf0 = cost.pair(i, j);
+                if (!(cf0 <= thresh)) continue;
+                const double cf = (double)cf0 + cost.pair_bias(i, j);
+                if (bi < 0 || cf < best || (cf == best && (i < bi || (i == bi && j < bj)))) { best = cf; bi = i; bj = j; }
+            }
+        if (bi >= 0) { ws.row2col[bi] = (short)bj; ws.col2row[bj] = (short)bi; }
     }
     __syncthreads();
     if (ws.clk) ws.clk->tick(ws.clk_base + 3);
@@ -469,9 +482,9 @@ __device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, 
         if constexpr (Cost::kGrid) {
             // box costs: index the columns so that only overlapping pairs are looked at
             if (cost.prune && (long long)n * m >= 65536 && m <= ws.grid.cap) {
-                if (ws.clk) ws.clk->tick(16 + 3);
+                if (ws.clk && ws.clk_base == 3) ws.clk->tick(16 + 3);
                 grid_build(ws.grid, m, ws.bs, [&](int j) { return cost.col_box(j); });
-                if (ws.clk) ws.clk->tick(16 + 0);
+                if (ws.clk && ws.clk_base == 3) ws.clk->tick(16 + 0);
                 use_grid = true;
             }
         }
@@ -508,7 +521,7 @@ __device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, 
                         });
                     }
                     __syncthreads();
-                    if (ws.clk) ws.clk->tick(16 + 1);
+                    if (ws.clk && ws.clk_base == 3) ws.clk->tick(16 + 1);
                     const int n_pairs = ws.ctl[7];
                     if (n_pairs > ws.p_cap && step > 32) {          // uniform decision: retry this base with fewer rows
                         step >>= 1;
@@ -537,7 +550,7 @@ __device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, 
                         scan_row(i);                           // 32 rows still overflow the buffer: every column of those rows
                     }
                     __syncthreads();
-                    if (ws.clk) ws.clk->tick(16 + 2);
+                    if (ws.clk && ws.clk_base == 3) ws.clk->tick(16 + 2);
                     base += step;
                 }
             }

@@ -26,13 +26,20 @@ def main():
     eng.update(dets[warm:], counts[warm:], ld_out=512)
     cyc = np.zeros(32, np.uint64)
     api.check(lib.mot_engine_profile(eng._h, 0, cyc.ctypes.data))
-    extra = cyc[16:].astype(np.float64) / (S * T)
-    cyc = cyc[:16]
+    raw = cyc.copy()
+    extra = raw[16:].astype(np.float64) / (S * T)
+    sub = raw[20:28].astype(np.float64) / (S * T)      # F: 20 solves, 21 candidates, 22 components, 23 grouping; G: 24..27 likewise
+    cyc = raw[:16].copy()
+    cyc[9] += raw[20:24].sum()                         # the association's own sub-phases belong to F / G
+    cyc[10] += raw[24:28].sum()
     tot = float(cyc.sum())
     per_frame = cyc.astype(np.float64) / (S * T)
     print("streams %d, frames %d: %.0f cycles per frame per CTA (%.1f us at 1.965 GHz)" % (S, T, tot / (S * T), tot / (S * T) / 1965.0))
     for k, n in enumerate(NAMES):
         print("  %-16s %8.0f cycles  %5.1f %%" % (n, per_frame[k], 100.0 * cyc[k] / tot))
+    print("  F inside block_lap: candidates %.0f, components %.0f, grouping %.0f, solves %.0f cycles" % (sub[1], sub[2], sub[3], sub[0]))
+    print("  G inside block_lap: candidates %.0f, components %.0f, grouping %.0f, solves %.0f cycles" % (sub[5], sub[6], sub[7], sub[4]))
+    print("  D4 split (with extra barriers): class lists %.0f, trivial %.0f, teams %.0f, warps = D4 solves above" % tuple(raw[28:31].astype(np.float64) / (S * T)))
     print("  D1 split: init %.0f, grid build %.0f, pair collection %.0f, pair evaluation %.0f cycles" % (extra[3], extra[0], extra[1], extra[2]))
     print(json.dumps({"streams": S, "frames": T, "cycles_per_frame": tot / (S * T), "share": {n: float(cyc[k] / tot) for k, n in enumerate(NAMES)}}))
 
