@@ -98,6 +98,12 @@ typedef struct mot_engine_config {
      * path (the engine behaves as cmc_off = true).  emb_dim may be any positive size; embedding_off = 1 needs none. */
     float w_association_emb, alpha_fixed_emb, aw_param;
     int embedding_off, aw_off;
+    /* asso_func constructor argument (include/motcpp/tracker.hpp:47-55, AssociationFunction include/motcpp/utils/iou.hpp:371-411),
+     * OC-SORT engines: 0 = "iou" (default), 6 = "centroid" (iou.hpp:298-330) with frame_width / frame_height = the size of
+     * the frames the reference would read from `img` (src/trackers/ocsort.cpp:413).  The other variants ("hmiou", "giou",
+     * "diou", "ciou") are only defined by the reference when the second box set has one row and are refused; every other
+     * front-end uses plain IoU internally whatever asso_func says, as in the reference. */
+    int asso_func, frame_width, frame_height;
 } mot_engine_config;
 
 typedef struct mot_engine mot_engine;

@@ -152,29 +152,44 @@ private:
 };
 
 // motcpp::trackers::OCSort (include/motcpp/trackers/ocsort.hpp:88-102)
+// asso_func: "iou" or "centroid" (AssociationFunction, iou.hpp:371-411; the reference's other variants are only defined
+// for one-row box sets).  "centroid" normalises by the frame diagonal, which the reference reads from every img
+// (ocsort.cpp:413): pass the frame size as frame_width / frame_height; update() checks img against it.
 class OCSort : public BaseTracker {
 public:
     OCSort(float det_thresh = 0.2f, int max_age = 30, int max_obs = 50, int min_hits = 3, float iou_threshold = 0.3f,
            bool per_class = false, int nr_classes = 80, const std::string& asso_func = "iou", bool is_obb = false,
            float min_conf = 0.1f, int delta_t = 3, float inertia = 0.2f, bool use_byte = false,
            float Q_xy_scaling = 0.01f, float Q_s_scaling = 0.0001f, int track_capacity = 0, int max_dets = 0,
-           int device = 0)
+           int device = 0, int frame_width = 0, int frame_height = 0)
         : BaseTracker(make(det_thresh, max_age, max_obs, min_hits, iou_threshold, per_class, nr_classes, asso_func, is_obb,
                            min_conf, delta_t, inertia, use_byte, Q_xy_scaling, Q_s_scaling, track_capacity, max_dets,
-                           device)) {}
+                           device, frame_width, frame_height)),
+          centroid_(asso_func == "centroid"), frame_w_(frame_width), frame_h_(frame_height) {}
+
+    Eigen::MatrixXf update(const Eigen::MatrixXf& dets, const cv::Mat& img,
+                           const Eigen::MatrixXf& embs = Eigen::MatrixXf()) override {
+        if (centroid_ && !img.empty() && (img.cols != frame_w_ || img.rows != frame_h_))
+            throw std::invalid_argument("asso_func \"centroid\": the frame size differs from the frame_width / frame_height the tracker was built for");
+        return BaseTracker::update(dets, img, embs);
+    }
 
 private:
+    bool centroid_;
+    int frame_w_, frame_h_;
     static mot_engine_config make(float det_thresh, int max_age, int max_obs, int min_hits, float iou_threshold,
                                   bool per_class, int /*nr_classes*/, const std::string& asso_func, bool is_obb,
                                   float min_conf, int delta_t, float inertia, bool use_byte, float q_xy, float q_s,
-                                  int track_capacity, int max_dets, int device) {
-        only_iou_aabb(asso_func, per_class, is_obb);
+                                  int track_capacity, int max_dets, int device, int frame_width, int frame_height) {
+        if (asso_func != "iou" && asso_func != "centroid") throw std::invalid_argument("Invalid association mode: " + asso_func);   // iou.hpp:407
+        if (per_class || is_obb) throw std::invalid_argument("per_class / OBB are outside the accelerated hot path");
         mot_engine_config c;
         throw_on(mot_engine_default_config(MOT_TRACKER_OCSORT, &c));
         c.n_streams = 1; c.track_capacity = track_capacity; c.max_dets = max_dets; c.device = device;
         c.det_thresh = det_thresh; c.max_age = max_age; c.max_obs = max_obs; c.min_hits = min_hits;
         c.iou_threshold = iou_threshold; c.min_conf = min_conf; c.delta_t = delta_t; c.inertia = inertia;
         c.use_byte = use_byte ? 1 : 0; c.q_xy_scaling = q_xy; c.q_s_scaling = q_s;
+        if (asso_func == "centroid") { c.asso_func = 6; c.frame_width = frame_width; c.frame_height = frame_height; }
         return c;
     }
 };

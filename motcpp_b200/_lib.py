@@ -43,6 +43,7 @@ class EngineConfig(C.Structure):
         ("mc_lambda", C.c_float), ("ema_alpha", C.c_float),
         ("w_association_emb", C.c_float), ("alpha_fixed_emb", C.c_float), ("aw_param", C.c_float),
         ("embedding_off", C.c_int), ("aw_off", C.c_int),
+        ("asso_func", C.c_int), ("frame_width", C.c_int), ("frame_height", C.c_int),
     ]
 
 

@@ -710,14 +710,25 @@ class OCSort:
     def __init__(self, det_thresh=0.2, max_age=30, max_obs=50, min_hits=3, iou_threshold=0.3, per_class=False,
                  nr_classes=80, asso_func="iou", is_obb=False, min_conf=0.1, delta_t=3, inertia=0.2, use_byte=False,
                  Q_xy_scaling=0.01, Q_s_scaling=0.0001, track_capacity=1536, max_dets=512, device=0):
-        if asso_func != "iou":
-            raise ValueError("Invalid association mode: " + str(asso_func) + " (only \"iou\" is accelerated)")
+        # AssociationFunction (iou.hpp:371-411): "iou" and "centroid" are wired in; the reference's hmiou / giou / diou / ciou
+        # expressions are only defined when the second box set has one row (trap 11) and are refused
+        if asso_func not in ("iou", "centroid"):
+            raise ValueError("Invalid association mode: " + str(asso_func) + " (\"iou\" and \"centroid\" are accelerated)")
         if per_class or is_obb:
             raise ValueError("per_class / OBB tracking are outside the accelerated hot path")
-        self._engine = Engine(_lib.TRACKER_OCSORT, 1, track_capacity, max_dets, device, det_thresh=det_thresh,
-                              max_age=max_age, max_obs=max_obs, min_hits=min_hits, iou_threshold=iou_threshold,
-                              min_conf=min_conf, delta_t=delta_t, inertia=inertia, use_byte=int(bool(use_byte)),
-                              q_xy_scaling=Q_xy_scaling, q_s_scaling=Q_s_scaling)
+        self._make = lambda w, h: Engine(_lib.TRACKER_OCSORT, 1, track_capacity, max_dets, device, det_thresh=det_thresh,
+                                         max_age=max_age, max_obs=max_obs, min_hits=min_hits, iou_threshold=iou_threshold,
+                                         min_conf=min_conf, delta_t=delta_t, inertia=inertia, use_byte=int(bool(use_byte)),
+                                         q_xy_scaling=Q_xy_scaling, q_s_scaling=Q_s_scaling,
+                                         asso_func=0 if asso_func == "iou" else 6, frame_width=w, frame_height=h)
+        self._centroid = asso_func == "centroid"
+        self._frame = None
+        self._engine = None
+        if not self._centroid:
+            self._build(0, 0)
+
+    def _build(self, w, h):
+        self._engine = self._make(w, h)
         self._max_dets = self._engine.cfg.max_dets
         self._cap = self._engine.cfg.track_capacity
         self._dets = np.zeros((1, 1, self._max_dets, 6), np.float32)
@@ -725,7 +736,8 @@ class OCSort:
         self._n_out = np.empty((1, 1), np.int32)
 
     def reset(self):
-        self._engine.reset()
+        if self._engine is not None:
+            self._engine.reset()
 
     def update(self, dets, img, embs=None) -> np.ndarray:
         dets = np.asarray(dets, np.float32)
@@ -734,12 +746,21 @@ class OCSort:
         # BaseTracker::check_inputs (src/tracker.cpp:108-125)
         if dets.shape[0] > 0 and dets.shape[1] not in (6, 7):
             raise ValueError("Detections must have 6 (AABB) or 7 (OBB) columns")
-        if _Image(img).empty():
+        im = _Image(img)
+        if im.empty():
             raise ValueError("Image cannot be empty")
         if embs is not None and np.shape(embs)[0] > 0 and np.shape(embs)[0] != dets.shape[0]:
             raise ValueError("Detections and embeddings must have same number of rows")
         if dets.shape[0] > 0 and dets.shape[1] == 7:
             raise ValueError("OBB detections are outside the accelerated hot path")
+        if self._centroid:
+            # the reference normalises centre distances by the diagonal of the frame it is handed (ocsort.cpp:413); the engine
+            # fixes it with the first frame
+            if self._engine is None:
+                self._frame = (im.cols, im.rows)
+                self._build(im.cols, im.rows)
+            elif (im.cols, im.rows) != self._frame:
+                raise ValueError(f"frame size changed from {self._frame} to {(im.cols, im.rows)}: asso_func=\"centroid\" fixes it at the first update")
         n = dets.shape[0]
         if n > self._max_dets:
             raise ValueError(f"{n} detections exceed max_dets={self._max_dets}")

@@ -255,6 +255,7 @@ int mot_engine_default_config(int kind, mot_engine_config* c) {
     c->max_cos_dist = 0.2f; c->max_iou_dist = 0.7f; c->n_init = 3; c->nn_budget = 100; c->mc_lambda = 0.98f; c->ema_alpha = 0.9f;
     // DeepOCSort (deepocsort.hpp:93-117)
     c->w_association_emb = 0.5f; c->alpha_fixed_emb = 0.95f; c->aw_param = 0.5f; c->embedding_off = 0; c->aw_off = 0;
+    c->asso_func = 0; c->frame_width = 0; c->frame_height = 0;
     switch (kind) {
         case MOT_TRACKER_SORT: c->max_age = 1; break;             // sort.hpp:70
         case MOT_TRACKER_BYTETRACK: break;
@@ -277,6 +278,14 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     if ((cfg->kind == MOT_TRACKER_BOTSORT || cfg->kind == MOT_TRACKER_STRONGSORT) && (cfg->emb_dim < 0 || (cfg->emb_dim & 3)))
         return fail(MOT_ERR_INVALID_ARGUMENT, "emb_dim %d must be a non-negative multiple of 4", cfg->emb_dim);
     if (cfg->n_streams <= 0) return fail(MOT_ERR_INVALID_ARGUMENT, "n_streams must be positive");
+    if (cfg->asso_func != 0) {
+        if (cfg->asso_func != mot::kVarCentroid)
+            return fail(MOT_ERR_UNSUPPORTED, "Invalid association mode: %d (engines take 0 \"iou\" or 6 \"centroid\"; the reference's hmiou / giou / diou / ciou are only defined for one-row box sets)", cfg->asso_func);
+        if (cfg->kind != MOT_TRACKER_OCSORT)
+            return fail(MOT_ERR_UNSUPPORTED, "asso_func \"centroid\" is wired into the OC-SORT engine only");
+        if (cfg->frame_width <= 0 || cfg->frame_height <= 0)
+            return fail(MOT_ERR_INVALID_ARGUMENT, "asso_func \"centroid\" needs frame_width / frame_height (the reference reads them from img)");
+    }
     if (cfg->kind == MOT_TRACKER_DEEPOCSORT && !cfg->embedding_off && cfg->emb_dim < 1)
         return fail(MOT_ERR_INVALID_ARGUMENT, "a DeepOC-SORT engine needs emb_dim >= 1 (or embedding_off = 1)");
     if ((cfg->kind == MOT_TRACKER_OCSORT || cfg->kind == MOT_TRACKER_DEEPOCSORT) && (cfg->delta_t < 1 || cfg->delta_t > mot::kOcRing - 1))
@@ -352,6 +361,8 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     e->ocp.aw_param = cfg->aw_param;
     e->ocp.aw_off = cfg->aw_off;
     e->ocp.embedding_off = cfg->embedding_off;
+    e->ocp.asso = cfg->asso_func;
+    e->ocp.asso_norm = cfg->asso_func ? static_cast<float>(std::sqrt((double)(cfg->frame_width * cfg->frame_width + cfg->frame_height * cfg->frame_height))) : 1.0f;   // iou.hpp:325
     e->deep_layout = mot::DeepLayout::make(e->cfg.track_capacity, e->cfg.max_dets, cfg->embedding_off ? 0 : cfg->emb_dim);
     e->bot_layout = mot::BotLayout::make(e->cfg.track_capacity, e->cfg.max_dets, cfg->emb_dim);
     e->botp.track_high_thresh = cfg->track_high_thresh;

@@ -85,6 +85,14 @@ __device__ __forceinline__ float ocm_angle_cost(float det_cx, float det_cy, floa
     return xmul(xmul(valid, ang), inertia);
 }
 
+// The tracker's AssociationFunction (iou.hpp:371-411) for one pair.  kind 0 = iou_batch; kind 6 = centroid_batch
+// (1 - centre distance / frame diagonal, :298-330), the one variant whose expression is defined for every N x M.
+// Centroid similarities are non-zero for every pair, so the callers switch the disjoint-box pruning off with it.
+__device__ __forceinline__ float asso_pair(int kind, float norm, float4 a, float area_a, float4 b) {
+    if (kind == kVarCentroid) return iou_variant_pair(kVarCentroid, a, area_a, b, norm);
+    return iou_pair(a, area_a, b);
+}
+
 // Cost functor for block_lap(): rows = high-confidence detections (row_map -> detection index), columns =
 // tracks in list order.  cost = -(iou + angle cost * score).  is_candidate() additionally tallies the
 // reference's "trivial one-to-one" test (ocsort.cpp:676-689): which rows / columns see more than one
@@ -104,6 +112,8 @@ struct OcmCost {
     unsigned* col_bits;               // [ceil(m/32)]
     unsigned short* row_hit;          // [n] column of (the last) such pair
     int* flags;                       // [0] any pair with iou > thr, [1] a row or column saw two
+    int asso;                         // AssociationFunction: 0 iou, 6 centroid ("iou" below means its value)
+    float asso_norm;                  // frame diagonal (centroid)
     struct Row { float4 b; float area, cx, cy, score; };
     __device__ __forceinline__ Row row(int i) const {
         Row r;
@@ -117,7 +127,7 @@ struct OcmCost {
     }
     __device__ __forceinline__ float4 col_box(int j) const { return trk_box[j]; }
     __device__ __forceinline__ bool reject(const Row& r, int j) const { return prune && boxes_disjoint(r.b, trk_box[j]); }
-    __device__ __forceinline__ float iou(const Row& r, int j) const { return iou_pair(r.b, r.area, trk_box[j]); }
+    __device__ __forceinline__ float iou(const Row& r, int j) const { return asso_pair(asso, asso_norm, r.b, r.area, trk_box[j]); }
     __device__ __forceinline__ float cost_from_iou(const Row& r, int j, float v) const {
         const float va = (valid[j] & 1) ? 1.0f : 0.0f;
         if (va == 0.0f) return -v;                     // 0 * angle * inertia * score adds exactly +-0
@@ -209,6 +219,8 @@ struct NegIouCost {
     float iou_thr;
     bool prune;
     int* flags;                       // [0] any pair with iou > thr  (the reference's max_iou > threshold gate)
+    int asso;                         // AssociationFunction: 0 iou, 6 centroid
+    float asso_norm;
     struct Row { float4 b; float area; };
     __device__ __forceinline__ Row row(int i) const {
         Row r;
@@ -218,11 +230,11 @@ struct NegIouCost {
     }
     __device__ __forceinline__ float4 col_box(int j) const { return trk_box[col_map[j]]; }
     __device__ __forceinline__ bool reject(const Row& r, int j) const { return prune && boxes_disjoint(r.b, col_box(j)); }
-    __device__ __forceinline__ float cost(const Row& r, int j) const { return -iou_pair(r.b, r.area, col_box(j)); }
+    __device__ __forceinline__ float cost(const Row& r, int j) const { return -asso_pair(asso, asso_norm, r.b, r.area, col_box(j)); }
     __device__ __forceinline__ float pair(int i, int j) const { return cost(row(i), j); }
     __device__ __forceinline__ double pair_bias(int i, int j) const { return twin_bias(i, j); }   // twins, as OcmCost
     __device__ __forceinline__ bool is_candidate(const Row& r, int, int j, float thresh) const {
-        const float v = iou_pair(r.b, r.area, col_box(j));
+        const float v = asso_pair(asso, asso_norm, r.b, r.area, col_box(j));
         if (v > iou_thr) flags[0] = 1;
         return -v <= thresh;
     }

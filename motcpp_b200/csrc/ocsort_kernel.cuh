@@ -63,6 +63,9 @@ struct OcParams {
     // DeepOC-SORT only (deepocsort.hpp:96-121)
     float w_assoc_emb, alpha_fixed_emb, aw_param;
     int aw_off, embedding_off;
+    // asso_func (ocsort.hpp:93; OC-SORT only): 0 iou, 6 centroid with the frame diagonal the reference derives from img
+    int asso;
+    float asso_norm;
 };
 
 struct OcLayout {
@@ -720,8 +723,9 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
     }
     __syncthreads();
     const float score_bound = __int_as_float(sm.flags[3]);
-    const bool prune_first = thr >= 0.0f && (0.5f * fabsf(a.p.inertia) * score_bound * 1.0001f + 1e-7f) < thr;
-    const bool prune_rest = thr > 0.0f;
+    // (a centroid similarity is non-zero for disjoint boxes too: no pruning with it)
+    const bool prune_first = a.p.asso == 0 && thr >= 0.0f && (0.5f * fabsf(a.p.inertia) * score_bound * 1.0001f + 1e-7f) < thr;
+    const bool prune_rest = a.p.asso == 0 && thr > 0.0f;
     const bool use_emb = DEEP && !a.p.embedding_off;
     __syncthreads();
     if (tid == 0) sm.flags[3] = 0;
@@ -806,7 +810,7 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
 
     // ---- D. first association (:413-420, associate :610-737); rows = high detections, columns = tracks
     const OcmCost ocm_base{sm.det_box, sm.det_conf, sm.high, sm.trk_box, st.ocm, st.valid, a.p.inertia, thr, prune_first,
-                           sm.row_bits, sm.col_bits, sm.pair_det /* row_hit */, sm.flags};
+                           sm.row_bits, sm.col_bits, sm.pair_det /* row_hit */, sm.flags, a.p.asso, a.p.asso_norm};
     std::conditional_t<DEEP, DeepOcmCost, OcmCost> ocm;
     if constexpr (DEEP) {
         // appearance term (deepocsort.cpp:420-440): needs detections (the reference leaves the matrix empty without, :756)
@@ -907,7 +911,7 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
         __syncthreads();
         if (tid == 0) sm.flags[2] = 0;
         __syncthreads();
-        NegIouCost cost{sm.det_box, sm.second, sm.trk_box, sm.ut, thr, prune_rest, sm.flags};
+        NegIouCost cost{sm.det_box, sm.second, sm.trk_box, sm.ut, thr, prune_rest, sm.flags, a.p.asso, a.p.asso_norm};
         block_lap(sm.lap, n_second, n_ut, DMAX, CAP, -thr, cost);
         if (sm.flags[0] != 0)
             for (int p = tid; p < n_ut; p += nt)
@@ -943,7 +947,7 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
         }
         if (tid == 0) { sm.flags[0] = 0; sm.flags[2] = 0; }
         __syncthreads();
-        NegIouCost cost{sm.det_box, sm.ud, sm.trk_box, sm.ut, thr, prune_rest, sm.flags};
+        NegIouCost cost{sm.det_box, sm.ud, sm.trk_box, sm.ut, thr, prune_rest, sm.flags, a.p.asso, a.p.asso_norm};
         block_lap(sm.lap, n_ud, n_ut, DMAX, CAP, -thr, cost);
         // Exact ties here: (1) the lists hold an entry twice (pairs rejected by the IoU filter; in DeepOC-SORT also everything the assignment left unmatched) - which
         // COPY of a detection is matched decides the order in which a twice-listed track receives its two updates;

@@ -63,12 +63,49 @@ float orc_acosf(float xf) {
 
 // ocsort.cpp:610-700.  dets5 (n_dets x 5) [xyxy, score], trks4 (n_trks x 4) predicted boxes, vel2 (n_trks x 2)
 // (dy, dx), prev5 (n_trks x 5) k_previous_obs rows.  out_cost / out_iou are (n_dets x n_trks) row-major.
+}  // extern "C"
+
+namespace {
+// the AssociationFunction of the tracker (iou.hpp:371-411) for one pair: 0 = iou_batch, 6 = centroid_batch (the variant
+// whose expression is defined for every N x M; hmiou / giou / diou / ciou only line up when the second set has one row)
+inline float asso_pair(int asso, float norm, const float* d, const float* t) {
+    if (asso == 6) {                                                         // iou.hpp:298-330
+        const float dx = (d[0] + d[2]) / 2.0f - (t[0] + t[2]) / 2.0f;
+        const float dy = (d[1] + d[3]) / 2.0f - (t[1] + t[3]) / 2.0f;
+        const float dist = std::sqrt(dx * dx + dy * dy);
+        return 1.0f - dist / norm;
+    }
+    const float area_d = (d[2] - d[0]) * (d[3] - d[1]), area_t = (t[2] - t[0]) * (t[3] - t[1]);
+    const float w = std::max(0.0f, std::min(d[2], t[2]) - std::max(d[0], t[0]));
+    const float h = std::max(0.0f, std::min(d[3], t[3]) - std::max(d[1], t[1]));
+    const float inter = w * h;
+    const float uni = area_d + area_t - inter;
+    return (uni > 0.0f) ? (inter / uni) : 0.0f;
+}
+inline float asso_norm(int w, int h) { return static_cast<float>(std::sqrt(w * w + h * h)); }   // iou.hpp:325
+void asso_matrix(int asso, float norm, const float* a, int n, const float* b, int m, float* out) {
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < m; ++j) out[(size_t)i * m + j] = asso_pair(asso, norm, a + 4 * i, b + 4 * j);
+}
+void ocm_cost_impl(const float* dets5, int n_dets, const float* trks4, const float* vel2, const float* prev5,
+                   int n_trks, float inertia, int asso, float asso_nrm, float* out_cost, float* out_iou);
+}  // namespace
+
+extern "C" {
+
 void orc_ocm_cost(const float* dets5, int n_dets, const float* trks4, const float* vel2, const float* prev5,
                   int n_trks, float inertia, float* out_cost, float* out_iou) {
+    ocm_cost_impl(dets5, n_dets, trks4, vel2, prev5, n_trks, inertia, 0, 1.0f, out_cost, out_iou);
+}
+
+}  // extern "C"
+
+namespace {
+void ocm_cost_impl(const float* dets5, int n_dets, const float* trks4, const float* vel2, const float* prev5,
+                   int n_trks, float inertia, int asso, float asso_nrm, float* out_cost, float* out_iou) {
     const float PI = 3.14159265358979323846f;
     for (int j = 0; j < n_dets; ++j) {
         const float* d = dets5 + 5 * j;
-        const float area_d = (d[2] - d[0]) * (d[3] - d[1]);
         const float cx1 = (d[0] + d[2]) / 2.0f, cy1 = (d[1] + d[3]) / 2.0f;
         for (int i = 0; i < n_trks; ++i) {
             const float* p = prev5 + 5 * i;
@@ -82,21 +119,14 @@ void orc_ocm_cost(const float* dets5, int n_dets, const float* trks4, const floa
             const float valid = (p[4] >= 0.0f) ? 1.0f : 0.0f;                // :653
             float ac = (valid * ang) * inertia;                              // :667
             ac = ac * d[4];                                                  // :669
-            // iou_batch(detections, trackers) iou.hpp:63-100
-            const float* t = trks4 + 4 * i;
-            const float area_t = (t[2] - t[0]) * (t[3] - t[1]);
-            const float w = std::max(0.0f, std::min(d[2], t[2]) - std::max(d[0], t[0]));
-            const float h = std::max(0.0f, std::min(d[3], t[3]) - std::max(d[1], t[1]));
-            const float inter = w * h;
-            const float uni = area_d + area_t - inter;
-            const float iou = (uni > 0.0f) ? (inter / uni) : 0.0f;
+            // asso_func(detections, trackers): iou_batch iou.hpp:63-100 by default
+            const float iou = asso_pair(asso, asso_nrm, d, trks4 + 4 * i);
             if (out_iou) out_iou[(size_t)j * n_trks + i] = iou;
             out_cost[(size_t)j * n_trks + i] = -(iou + ac);                  // :700
         }
     }
 }
-
-}  // extern "C"
+}  // namespace
 
 namespace {
 
@@ -189,7 +219,7 @@ struct Assoc {
 // ocsort.cpp:610-737
 Assoc associate(const std::vector<float>& dets5, int n_dets, const std::vector<float>& trks4, int n_trks,
                 float iou_threshold, const std::vector<float>& vel2, const std::vector<float>& prev5, float vdc_weight,
-                int* used_lap, std::vector<float>* keep_cost, int tie_mode) {
+                int* used_lap, std::vector<float>* keep_cost, int tie_mode, int asso, float norm) {
     Assoc r;
     *used_lap = 0;
     if (n_trks == 0) {
@@ -198,8 +228,8 @@ Assoc associate(const std::vector<float>& dets5, int n_dets, const std::vector<f
     }
     if (n_dets > 0) {
         std::vector<float> cost((size_t)n_dets * n_trks), iou((size_t)n_dets * n_trks);
-        orc_ocm_cost(dets5.data(), n_dets, trks4.data(), vel2.data(), prev5.data(), n_trks, vdc_weight, cost.data(),
-                     iou.data());
+        ocm_cost_impl(dets5.data(), n_dets, trks4.data(), vel2.data(), prev5.data(), n_trks, vdc_weight, asso, norm, cost.data(),
+                      iou.data());
         if (keep_cost) *keep_cost = cost;
         int max_row = 0, max_col = 0;                                          // :676-678
         std::vector<int> col_sum(n_trks, 0);
@@ -249,6 +279,8 @@ struct OrcOcSort {
     int frame_count = 0;
     int id_counter = 0;
     int last_sizes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int asso = 0;                               // AssociationFunction: 0 iou, 6 centroid (orc_ocsort_set_asso)
+    float asso_norm = 1.0f;                     // sqrt(w^2 + h^2) of the frames (centroid)
     int tie_mode = 0;                           // 0 = the reference's LAPJV scan order, 1 = prefer the higher column,
                                                 // 2 = the CUDA kernel's policy: 0 while rows + columns <= 384, else 1
     bool capture = false;                       // tests: keep the first-association cost matrix of the last update()
@@ -267,6 +299,14 @@ OrcOcSort* orc_ocsort_create(float det_thresh, int max_age, int max_obs, int min
     s->min_conf = min_conf; s->delta_t = delta_t; s->inertia = inertia; s->use_byte = use_byte;
     s->q_xy = q_xy_scaling; s->q_s = q_s_scaling;
     return s;
+}
+// asso_func constructor argument (ocsort.hpp:93) + the size of the frames update() is given (the reference builds its
+// AssociationFunction from img.cols / img.rows in every call, ocsort.cpp:413, :438, :494): 0 "iou", 6 "centroid"
+int orc_ocsort_set_asso(OrcOcSort* s, int asso, int frame_w, int frame_h) {
+    if (asso != 0 && asso != 6) return -1;
+    s->asso = asso;
+    s->asso_norm = asso_norm(frame_w, frame_h);
+    return 0;
 }
 void orc_ocsort_destroy(OrcOcSort* s) { delete s; }
 void orc_ocsort_reset(OrcOcSort* s) { s->frame_count = 0; s->tracks.clear(); }      // ocsort.cpp:222-227
@@ -317,7 +357,7 @@ int orc_ocsort_update(OrcOcSort* s, const float* dets, int n, float* out, int ou
     for (int j = 0; j < n_high; ++j) std::memcpy(&dets5[5 * j], dets + 6 * remain[j], 5 * sizeof(float));
     int used_lap = 0;
     Assoc a = associate(dets5, n_high, trks4, n_trk, s->iou_threshold, vel2, prev5, s->inertia, &used_lap,
-                        s->capture ? &s->last_cost : nullptr, s->tie_mode);   // :413-420
+                        s->capture ? &s->last_cost : nullptr, s->tie_mode, s->asso, s->asso_norm);   // :413-420
     s->last_sizes[2] = used_lap;
     s->last_sizes[3] = (int)a.matches.size();
     for (const auto& m : a.matches) {                                              // :423-430
@@ -333,7 +373,7 @@ int orc_ocsort_update(OrcOcSort* s, const float* dets, int n, float* out, int ou
         for (int k = 0; k < nu; ++k) std::memcpy(&ub[4 * k], &trks4[4 * a.unmatched_trks[k]], 4 * sizeof(float));
         for (int j = 0; j < n_second; ++j) std::memcpy(&sb[4 * j], dets + 6 * second[j], 4 * sizeof(float));
         std::vector<float> iou((size_t)n_second * nu);
-        orc_iou_batch(sb.data(), n_second, ub.data(), nu, iou.data());
+        asso_matrix(s->asso, s->asso_norm, sb.data(), n_second, ub.data(), nu, iou.data());            // :438-439
         float mx = iou[0];
         for (float v : iou) mx = std::max(mx, v);
         if (mx > s->iou_threshold) {
@@ -367,7 +407,7 @@ int orc_ocsort_update(OrcOcSort* s, const float* dets, int n, float* out, int ou
         for (int k = 0; k < nu; ++k)
             std::memcpy(&tb[4 * k], s->tracks[a.unmatched_trks[k]].last_observation, 4 * sizeof(float));
         std::vector<float> iou((size_t)nd * nu);
-        orc_iou_batch(db.data(), nd, tb.data(), nu, iou.data());
+        asso_matrix(s->asso, s->asso_norm, db.data(), nd, tb.data(), nu, iou.data());                  // :494-495
         float mx = iou[0];
         for (float v : iou) mx = std::max(mx, v);
         if (mx > s->iou_threshold) {

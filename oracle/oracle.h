@@ -155,6 +155,8 @@ typedef struct OrcOcSort OrcOcSort;
 OrcOcSort* orc_ocsort_create(float det_thresh, int max_age, int max_obs, int min_hits, float iou_threshold,
                              float min_conf, int delta_t, float inertia, int use_byte, float q_xy_scaling,
                              float q_s_scaling);
+/* asso_func (ocsort.hpp:93): 0 "iou", 6 "centroid" + the frame size the reference reads from img (returns -1 otherwise) */
+int orc_ocsort_set_asso(OrcOcSort* s, int asso, int frame_w, int frame_h);
 void orc_ocsort_destroy(OrcOcSort*);
 void orc_ocsort_reset(OrcOcSort*);
 int orc_ocsort_update(OrcOcSort*, const float* dets, int n, float* out, int out_cap);

@@ -277,6 +277,10 @@ int ref_aw_max_metric(const float* emb, int n, int m, int ld, float w_assoc, flo
 // ---------------- tracker front-ends ------------------------------------------------------------------
 // kind: "sort" | "bytetrack" | "ocsort" | "botsort" | "strongsort" | "deepocsort"; p = the numeric ctor
 // arguments in the order documented per kind below (same order as the oracle's orc_*_create).
+// the asso_func constructor argument of the trackers created next ("iou" unless set; OC-SORT and DeepOC-SORT use it)
+static std::string g_asso_func = "iou";
+void ref_set_asso_func(const char* name) { g_asso_func = name ? name : "iou"; }
+
 void* ref_tracker_create(const char* kind, const float* p, int np) {
     g_err.clear();
     try {
@@ -292,7 +296,7 @@ void* ref_tracker_create(const char* kind, const float* p, int np) {
                                                 p[5], p[6], p[7], (int)p[8], (int)p[9]);
         } else if (k == "ocsort") {    // det_thresh, max_age, max_obs, min_hits, iou_threshold, min_conf, delta_t, inertia, use_byte, Q_xy_scaling, Q_s_scaling
             need(11);
-            t = new motcpp::trackers::OCSort(p[0], (int)p[1], (int)p[2], (int)p[3], p[4], false, 80, "iou", false,
+            t = new motcpp::trackers::OCSort(p[0], (int)p[1], (int)p[2], (int)p[3], p[4], false, 80, g_asso_func, false,
                                              p[5], (int)p[6], p[7], p[8] != 0.0f, p[9], p[10]);
         } else if (k == "botsort") {   // track_high, track_low, new_track, track_buffer, match_thresh, proximity, appearance, frame_rate, fuse_first_associate, with_reid
             need(10);

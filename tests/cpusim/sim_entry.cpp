@@ -204,6 +204,11 @@ void* sim_oc_create(int S, float det_thresh, int max_age, int min_hits, float io
     cpusim::launch(dim3(S), dim3(64), 0, [=] { mot::ocsort_reset_kernel(st, L, L.stride, S, 0); });
     return h;
 }
+void sim_oc_set_asso(void* hv, int asso, int frame_w, int frame_h) {
+    auto* h = (SimOc*)hv;
+    h->p.asso = asso;
+    h->p.asso_norm = static_cast<float>(std::sqrt((double)(frame_w * frame_w + frame_h * frame_h)));
+}
 void sim_oc_destroy(void* hv) { delete (SimOc*)hv; }
 
 int sim_oc_update(void* hv, const float* dets, const int* n_dets, int T, int ld_dets, float* out, int* n_out, int ld_out,

@@ -96,6 +96,7 @@ def lib() -> C.CDLL:
         L.orc_ocsort_create.argtypes = [C.c_float, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
                                         C.c_float, C.c_int, C.c_float, C.c_float]
         L.orc_ocsort_create.restype = C.c_void_p
+        L.orc_ocsort_set_asso.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.orc_ocsort_destroy.argtypes = [C.c_void_p]
         L.orc_ocsort_reset.argtypes = [C.c_void_p]
         L.orc_ocsort_update.argtypes = [C.c_void_p, f32p, C.c_int, f32p, C.c_int]
@@ -415,10 +416,13 @@ class OCSort:
     """Oracle OC-SORT with the reference's constructor argument order (ocsort.hpp:88-102)."""
 
     def __init__(self, det_thresh=0.2, max_age=30, max_obs=50, min_hits=3, iou_threshold=0.3, min_conf=0.1,
-                 delta_t=3, inertia=0.2, use_byte=False, q_xy_scaling=0.01, q_s_scaling=0.0001, tie_mode=0):
+                 delta_t=3, inertia=0.2, use_byte=False, q_xy_scaling=0.01, q_s_scaling=0.0001, tie_mode=0,
+                 asso_func="iou", frame=(1920, 1080)):
         self._h = lib().orc_ocsort_create(det_thresh, max_age, max_obs, min_hits, iou_threshold, min_conf, delta_t,
                                           inertia, int(use_byte), q_xy_scaling, q_s_scaling)
         lib().orc_ocsort_set_tie_mode(self._h, int(tie_mode))
+        # asso_func: "iou" | "centroid" (the reference's other variants are undefined beyond one row); frame = (width, height)
+        assert lib().orc_ocsort_set_asso(self._h, {"iou": 0, "centroid": 6}[asso_func], int(frame[0]), int(frame[1])) == 0
         self._out = np.zeros((8192, 8), np.float32)
 
     def __del__(self):

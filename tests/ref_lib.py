@@ -57,6 +57,7 @@ def _bind(L):
     L.ref_asso_func.argtypes = [C.c_char_p, f32p, C.c_int, f32p, C.c_int, C.c_int, C.c_int, f32p]
     L.ref_linear_assignment.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_float, i32p, i32p]
     L.ref_aw_max_metric.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, f32p, C.c_int]
+    L.ref_set_asso_func.argtypes = [C.c_char_p]
     L.ref_tracker_create.argtypes = [C.c_char_p, f32p, C.c_int]
     L.ref_tracker_create.restype = C.c_void_p
     L.ref_tracker_destroy.argtypes = [C.c_void_p]
@@ -99,10 +100,12 @@ class Tracker:
     """One reference tracker (kind = sort | bytetrack | ocsort | botsort | strongsort | deepocsort) in a private
     image of the library.  `params` = the numeric constructor arguments in the order of ref_tracker_create."""
 
-    def __init__(self, kind: str, params, order: str = "eigen"):
+    def __init__(self, kind: str, params, order: str = "eigen", asso_func: str = "iou"):
         self.L = private_lib(order)
         p = _f32(params)
+        self.L.ref_set_asso_func(asso_func.encode())          # OC-SORT's asso_func ctor argument; frames are 1920 x 1080
         self.h = self.L.ref_tracker_create(kind.encode(), p, p.size)
+        self.L.ref_set_asso_func(b"iou")
         if not self.h:
             raise RuntimeError(self.L.ref_last_error().decode())
         self._out = np.zeros((8192, 8), np.float32)

@@ -55,6 +55,7 @@ def lib():
         S.sim_oc_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float,
                                     C.c_int, C.c_float, C.c_float]
         S.sim_oc_create.restype = C.c_void_p
+        S.sim_oc_set_asso.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         S.sim_oc_update.argtypes = [C.c_void_p, f32p, i32p, C.c_int, C.c_int, f32p, i32p, C.c_int, C.c_int]
         S.sim_oc_header.argtypes = [C.c_void_p, C.c_int, i32p]
         S.sim_oc_dump.argtypes = [C.c_void_p, C.c_int, f32p, C.c_int]
@@ -167,10 +168,12 @@ class SimSort:
 
 class SimOCSort:
     def __init__(self, n_streams=1, det_thresh=0.2, max_age=30, min_hits=3, iou_threshold=0.3, min_conf=0.1, delta_t=3,
-                 inertia=0.2, use_byte=False, q_xy_scaling=0.01, q_s_scaling=0.0001):
+                 inertia=0.2, use_byte=False, q_xy_scaling=0.01, q_s_scaling=0.0001, asso_func="iou", frame=(1920, 1080)):
         self.S, self.cap = n_streams, 256
         self.h = lib().sim_oc_create(n_streams, det_thresh, max_age, min_hits, iou_threshold, min_conf, delta_t, inertia,
                                      int(use_byte), q_xy_scaling, q_s_scaling)
+        if asso_func != "iou":
+            lib().sim_oc_set_asso(self.h, {"centroid": 6}[asso_func], int(frame[0]), int(frame[1]))
 
     def __del__(self):
         if getattr(self, "h", None):

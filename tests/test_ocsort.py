@@ -96,12 +96,12 @@ def test_ocsort_duplicate_spawn_trap(oracle):
 
 
 # ------------------------------------------------------------------ kernel logic under the emulator (CPU)
-def _sim_vs_oracle(oracle, seed, T, args, n_obj=40, canvas=(960, 540), threads=128):
+def _sim_vs_oracle(oracle, seed, T, args, n_obj=40, canvas=(960, 540), threads=128, asso_func="iou"):
     d, c = synth.stress_stream(seed, n_frames=T, n_obj=n_obj, canvas=canvas)
-    ref = oracle.OCSort(**args, tie_mode=0)
+    ref = oracle.OCSort(**args, tie_mode=0, asso_func=asso_func, frame=canvas)
     sim = sim_lib.SimOCSort(1, args["det_thresh"], args["max_age"], args["min_hits"], args["iou_threshold"],
                             args["min_conf"], args["delta_t"], args["inertia"], args["use_byte"], args["q_xy_scaling"],
-                            args["q_s_scaling"])
+                            args["q_s_scaling"], asso_func=asso_func, frame=canvas)
     stats = np.zeros(8, np.int64)
     for t in range(T):
         n = int(c[t])
@@ -125,6 +125,17 @@ def test_ocsort_kernel_logic_under_emulator(oracle):
     _sim_vs_oracle(oracle, 7, 70, {**OC_ARGS, "use_byte": True}, threads=64)
     _sim_vs_oracle(oracle, 8, 60, {**OC_ARGS, "use_byte": True, "inertia": 0.9})        # dense (unpruned) path
     _sim_vs_oracle(oracle, 9, 50, {**OC_ARGS, "iou_threshold": 0.1, "inertia": 0.5}, n_obj=48, canvas=(480, 270))
+
+
+def test_ocsort_centroid_association_under_emulator(oracle):
+    """asso_func = "centroid" (iou.hpp:298-330): similarity 1 - centre distance / frame diagonal for EVERY pair - no
+    pruning, dense candidate sets, thresholds near 1."""
+    st = _sim_vs_oracle(oracle, 11, 80, {**OC_ARGS, "iou_threshold": 0.95}, asso_func="centroid")
+    assert st[2] > 30 and st[3] > 500                       # assignments ran and matched
+    _sim_vs_oracle(oracle, 12, 60, {**OC_ARGS, "iou_threshold": 0.9, "use_byte": True, "inertia": 0.5}, asso_func="centroid", threads=64)
+    _sim_vs_oracle(oracle, 13, 40, {**OC_ARGS, "iou_threshold": 0.3}, asso_func="centroid", n_obj=20)   # nearly everything is a candidate
+    with sim_lib.variant("jvblock"):
+        _sim_vs_oracle(oracle, 11, 80, {**OC_ARGS, "iou_threshold": 0.95}, asso_func="centroid")
 
 
 def test_ocsort_cta_wide_lapjv_under_emulator(oracle):
@@ -189,13 +200,17 @@ def test_gpu_acos_and_ocm_cost_match_oracle(oracle, gpu):
         assert np.array_equal(got_i, want_i) and np.array_equal(got_c.view(np.int32), want_c.view(np.int32)), (n, m)
 
 
-def _engine_vs_oracle(oracle, streams, args, cap, d_max, T_chunk=None, check_state_every=10):
+def _engine_vs_oracle(oracle, streams, args, cap, d_max, T_chunk=None, check_state_every=10, centroid_frame=None):
     S = len(streams)
     T = streams[0][0].shape[0]
     dets = np.stack([s[0] for s in streams], 1)
     counts = np.stack([s[1] for s in streams], 1).astype(np.int32)
-    eng = api.Engine(_lib.TRACKER_OCSORT, S, cap, d_max, **args)
-    refs = [oracle.OCSort(**args, tie_mode=0) for _ in range(S)]
+    if centroid_frame:                                   # asso_func = "centroid", frames of this (width, height)
+        eng = api.Engine(_lib.TRACKER_OCSORT, S, cap, d_max, **args, asso_func=6, frame_width=centroid_frame[0], frame_height=centroid_frame[1])
+        refs = [oracle.OCSort(**args, tie_mode=0, asso_func="centroid", frame=centroid_frame) for _ in range(S)]
+    else:
+        eng = api.Engine(_lib.TRACKER_OCSORT, S, cap, d_max, **args)
+        refs = [oracle.OCSort(**args, tie_mode=0) for _ in range(S)]
     T_chunk = T_chunk or T
     for t0 in range(0, T, T_chunk):
         t1 = min(T, t0 + T_chunk)
@@ -237,6 +252,31 @@ def test_gpu_ocsort_c2_shape_and_api_mirror(oracle, gpu):
         trk.update(np.zeros((2, 5), np.float32), (540, 960))
     with pytest.raises(ValueError):
         trk.update(np.zeros((0, 6), np.float32), None)
+
+
+@pytest.mark.gpu
+def test_gpu_ocsort_centroid_association(oracle, gpu):
+    """asso_func = "centroid" wired into the engine (reference iou.hpp:298-330 through ocsort.cpp:413, :438, :494): every pair
+    is a candidate above the threshold, nothing is pruned; engine = oracle = the reference's compiled ocsort.cpp (test_ref_pin)."""
+    streams = [synth.stress_stream(700 + s, n_frames=100) for s in range(3)]
+    _engine_vs_oracle(oracle, streams, {**OC_ARGS, "iou_threshold": 0.95}, 256, 64, T_chunk=25, centroid_frame=(960, 540))
+    _engine_vs_oracle(oracle, streams, {**OC_ARGS, "iou_threshold": 0.9, "use_byte": True, "inertia": 0.5}, 256, 64, centroid_frame=(960, 540))
+    d = synth.bytetrack_stream(4, n_frames=12, n_clutter=24, n_low=40, config=4)       # 320 detections per frame, C2 canvas
+    _engine_vs_oracle(oracle, [(d, np.full(d.shape[0], d.shape[1], np.int32))], {**OC_ARGS, "iou_threshold": 0.97}, 1536, 512,
+                      centroid_frame=(3840, 2160))
+    trk, ref = api.OCSort(iou_threshold=0.95, asso_func="centroid", track_capacity=256, max_dets=64), \
+        oracle.OCSort(**{**OC_ARGS, "iou_threshold": 0.95}, tie_mode=0, asso_func="centroid", frame=(960, 540))
+    dd, cc = synth.stress_stream(78, n_frames=40)
+    for t in range(40):
+        assert np.array_equal(trk.update(dd[t, :cc[t]], (540, 960)), ref.update(dd[t, :cc[t]])), t
+    with pytest.raises(ValueError):
+        trk.update(dd[0, :cc[0]], (720, 1280))                                        # the frame size is fixed by the first update
+    with pytest.raises(ValueError):
+        api.OCSort(asso_func="giou")                                                  # undefined in the reference beyond one row
+    with pytest.raises(ValueError):
+        api.Engine(_lib.TRACKER_OCSORT, 1, 256, 64, **OC_ARGS, asso_func=6)           # centroid without a frame size
+    with pytest.raises(_lib.MotError):
+        api.Engine(_lib.TRACKER_BYTETRACK, 1, 256, 64, asso_func=6, frame_width=640, frame_height=480)
 
 
 @pytest.mark.gpu

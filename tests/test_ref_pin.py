@@ -377,3 +377,13 @@ def test_reset_and_empty_frames_equal_reference():
         # the id sequences must be equal up to that constant offset
         io, ir = np.concatenate(ids_o), np.concatenate(ids_r)
         assert io.size and np.all(ir - io == ir[0] - io[0]), kind
+
+
+@pytest.mark.parametrize("order", ["textbook", "eigen"])
+@pytest.mark.parametrize("sid,over", [(0, {}), (1, {"use_byte": True, "iou_threshold": 0.9}), (2, {"iou_threshold": 0.95, "inertia": 0.5})])
+def test_ocsort_centroid_association_equals_reference(order, sid, over):
+    """asso_func = "centroid" (iou.hpp:298-330, the one variant whose expression is defined for every N x M): the similarity is
+    1 - centre distance / frame diagonal for EVERY pair, so thresholds near 1 are the meaningful ones and nothing is sparse."""
+    args = {**OC, **over}
+    ref = R.Tracker("ocsort", [float(v) for v in args.values()], order, asso_func="centroid")
+    _run(order, O.OCSort(**args, tie_mode=0, asso_func="centroid", frame=(1920, 1080)), ref, _stress(90 + sid, 120))
