@@ -425,6 +425,7 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
 
     clk.tick(12);
     // ---- K. remove_duplicate_stracks(active', lost') (:659-706)
+    __syncthreads();                       // list_a / list_b tails were written without a barrier when the lost list was empty
     for (int i = tid; i < na; i += nt) sm.dup_a[i] = 0;
     for (int j = tid; j < nl; j += nt) sm.dup_b[j] = 0;
     if (na > 0 && nl > 0) {

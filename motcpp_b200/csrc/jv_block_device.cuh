@@ -154,14 +154,23 @@ __device__ __forceinline__ int jv_block_apply_records(const JvBlockWork& w, cons
     __syncthreads();
     const int front_end = h0 + T;
     for (;;) {                                            // K[t] <- landing position of the chain through node t
+        // pointer jumping in synchronous rounds: read, barrier, write (jumping in place without the barrier converges as
+        // well - every pointer only ever moves further along its own chain - but it is a data race by the letter)
         bool more = false;
-        for (int t = tid; t < T; t += nt) {
+        const int t0 = tid;                               // T <= N <= a few thousand: a handful of nodes per thread
+        int nxt[8];
+        int cnt = 0;
+        for (int t = t0; t < T && cnt < 8; t += nt, ++cnt) {
             const int q = K[t];
-            if (q < front_end && q != h0 + t) {
-                const int nq = K[q - h0];
-                K[t] = nq;
-                more |= nq < front_end;
-            }
+            nxt[cnt] = (q < front_end && q != h0 + t) ? K[q - h0] : -1;
+        }
+        __syncthreads();
+        cnt = 0;
+        for (int t = t0; t < T && cnt < 8; t += nt, ++cnt)
+            if (nxt[cnt] >= 0) { K[t] = nxt[cnt]; more |= nxt[cnt] < front_end; }
+        for (int t = t0 + 8 * nt; t < T; t += nt) {       // beyond 8 nodes per thread (never at the built shapes): in place
+            const int q = K[t];
+            if (q < front_end && q != h0 + t) { const int nq = K[q - h0]; K[t] = nq; more |= nq < front_end; }
         }
         if (!__syncthreads_or(more ? 1 : 0)) break;
     }

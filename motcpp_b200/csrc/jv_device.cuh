@@ -185,6 +185,7 @@ static __device__ __noinline__ void warp_dense_lapjv(const JvCost c, int N, cons
             int j2 = (i1 == j1) ? i2 : i1;
             warp_lexmin(u2, j2);
             if (!(u2 < kJvBig)) { u2 = kJvBig; j2 = -1; }          // the scan only accepts a runner-up below LARGE
+            __syncwarp();                                          // every lane has read fr[cur] before lane 0 rewrites it
             if (lane == 0) {
                 int owner = w.y[j1];
                 const double lowered = w.v[j1] - (u2 - u1);

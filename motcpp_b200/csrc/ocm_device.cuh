@@ -146,9 +146,11 @@ struct OcmCost {
         if (v > iou_thr) {
             const unsigned rb = 1u << (i & 31), cb = 1u << (j & 31);
             const unsigned ro = atomicOr(&row_bits[i >> 5], rb), co = atomicOr(&col_bits[j >> 5], cb);
-            row_hit[i] = (unsigned short)j;
-            flags[0] = 1;
-            if ((ro & rb) || (co & cb)) flags[1] = 1;
+            if (!(ro & rb)) {                          // the row's first such pair (its only one whenever row_hit is read)
+                row_hit[i] = (unsigned short)j;
+                atomicOr(&flags[0], 1);
+            }
+            if ((ro & rb) || (co & cb)) atomicOr(&flags[1], 1);
         }
     }
     __device__ __forceinline__ bool is_candidate(const Row& r, int i, int j, float thresh) const {
@@ -235,7 +237,7 @@ struct NegIouCost {
     __device__ __forceinline__ double pair_bias(int i, int j) const { return twin_bias(i, j); }   // twins, as OcmCost
     __device__ __forceinline__ bool is_candidate(const Row& r, int, int j, float thresh) const {
         const float v = asso_pair(asso, asso_norm, r.b, r.area, col_box(j));
-        if (v > iou_thr) flags[0] = 1;
+        if (v > iou_thr && *(volatile int*)&flags[0] == 0) atomicOr(&flags[0], 1);
         return -v <= thresh;
     }
 };

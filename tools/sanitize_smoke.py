@@ -46,6 +46,30 @@ api.iou_cost_tlwh(A[:9], A, np.ones(9, np.int32))
 api.aw_max_metric(rng.random((33, 70)).astype(np.float32))
 api.KalmanFilterXYSR().apply_affine_correction(rng.normal(size=(5, 7)).astype(np.float32), np.tile(np.eye(7, dtype=np.float32), (5, 1, 1)),
                                                np.eye(2, dtype=np.float32), np.zeros(2, np.float32))
-for _name in ("hmiou", "giou", "diou", "centroid"):
+for _name in ("hmiou", "giou", "diou", "centroid", "ciou"):
     api.asso_batch(_name, A, A[:17], 640, 480)
+# round 2: DeepOC-SORT (appearance terms, ordered-sum tiles, embedding EMA, twice-listed leftovers -> LAPJV every frame),
+# OC-SORT with the centroid association, the reference-order LAPJV kernels (one warp; CTA-wide with the parallel record
+# permutations, work arrays in shared memory and - forced - in global scratch), the packed host path
+trk = api.DeepOCSort(max_age=6, track_capacity=256, max_dets=64)
+for t in range(T):
+    trk.update(d[t, :c[t]], (540, 960), e[t, :c[t]])
+trk = api.OCSort(iou_threshold=0.95, asso_func="centroid", track_capacity=256, max_dets=64)
+for t in range(T):
+    trk.update(d[t, :c[t]], (540, 960))
+tie = (rng.integers(0, 4, (2, 90, 120)) / 4).astype(np.float32)
+api.linear_assignment_reference_order(tie, 0.8)                       # one warp (rows + columns <= 384)
+tie = (rng.integers(0, 4, (2, 200, 260)) / 4).astype(np.float32)
+api.linear_assignment_reference_order(tie, 0.8)                       # CTA-wide, shared work arrays
+os.environ["MOT_LAPJV_GLOBAL_WORK"] = "1"
+api.linear_assignment_reference_order(tie, 0.8)                       # CTA-wide, global work arrays
+del os.environ["MOT_LAPJV_GLOBAL_WORK"]
+streams = [synth.stress_stream(400 + s, n_frames=4, n_obj=260, canvas=(1600, 900)) for s in range(2)]   # crowded: exact solves above 384
+eng = api.Engine(_lib.TRACKER_DEEPOCSORT, 2, 1536, 512, emb_dim=8, max_age=3)
+dets2 = np.stack([s_[0] for s_ in streams], 1); cnt2 = np.stack([s_[1] for s_ in streams], 1).astype(np.int32)
+eng.update(dets2, cnt2, ld_out=1536, embs=rng.normal(size=dets2.shape[:3] + (8,)).astype(np.float32))
+eng.check()
+eng = api.Engine(_lib.TRACKER_BYTETRACK, 2, 1536, 512)
+eng.update_packed(np.stack([dd, dd], 1), np.full((3, 2), 512, np.int32), max_rows=512)
+eng.check()
 print("sanitize_smoke done")
