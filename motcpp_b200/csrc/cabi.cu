@@ -171,6 +171,7 @@ static void engine_launch(mot_engine* e, int T, const float* dets, const int* nd
         a.p = e->ocp;
         a.embs = embs; a.dim = e->deep_layout.dim; a.stride = e->stride;
         if (e->cfg.kind == MOT_TRACKER_DEEPOCSORT) mot::deepoc_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
+        else if (e->ocp.asso == mot::kVarCentroid) mot::oc_centroid_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
         else mot::oc_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
     } else {
         mot::BtArgs a = make_args(e, T, dets, nd, ld_dets, out, nout, ld_out, s0, s1);
@@ -393,7 +394,8 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
                     need, max_optin);
     }
     MOT_CUDA(is_ss ? mot::ss_prepare(e->shape, e->smem_bytes) : is_sort ? mot::sort_prepare(e->shape, e->smem_bytes)
-                     : (is_oc ? (is_deep ? mot::deepoc_prepare(e->shape, e->smem_bytes) : mot::oc_prepare(e->shape, e->smem_bytes))
+                     : (is_oc ? (is_deep ? mot::deepoc_prepare(e->shape, e->smem_bytes)
+                                        : (cfg->asso_func == mot::kVarCentroid ? mot::oc_centroid_prepare(e->shape, e->smem_bytes) : mot::oc_prepare(e->shape, e->smem_bytes)))
                               : (is_bot ? mot::bot_prepare(e->shape, e->smem_bytes) : mot::bt_prepare(e->shape, e->smem_bytes, e->threads))));
     e->n_chunks = cfg->n_chunks > 0 ? std::min(cfg->n_chunks, kMaxChunks) : (cfg->n_streams >= 128 ? 8 : (cfg->n_streams >= 32 ? 4 : 1));
     e->n_chunks = std::min(e->n_chunks, cfg->n_streams);

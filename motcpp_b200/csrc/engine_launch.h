@@ -15,6 +15,8 @@ cudaError_t sort_prepare(int shape, size_t smem);
 void sort_launch(int shape, int grid, size_t smem, cudaStream_t st, const SortArgs& a);
 cudaError_t oc_prepare(int shape, size_t smem);
 void oc_launch(int shape, int grid, size_t smem, cudaStream_t st, const OcArgs& a);
+cudaError_t oc_centroid_prepare(int shape, size_t smem);
+void oc_centroid_launch(int shape, int grid, size_t smem, cudaStream_t st, const OcArgs& a);
 cudaError_t deepoc_prepare(int shape, size_t smem);
 void deepoc_launch(int shape, int grid, size_t smem, cudaStream_t st, const OcArgs& a);
 cudaError_t bot_prepare(int shape, size_t smem);

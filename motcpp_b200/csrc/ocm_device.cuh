@@ -88,16 +88,19 @@ __device__ __forceinline__ float ocm_angle_cost(float det_cx, float det_cy, floa
 // The tracker's AssociationFunction (iou.hpp:371-411) for one pair.  kind 0 = iou_batch; kind 6 = centroid_batch
 // (1 - centre distance / frame diagonal, :298-330), the one variant whose expression is defined for every N x M.
 // Centroid similarities are non-zero for every pair, so the callers switch the disjoint-box pruning off with it.
-__device__ __forceinline__ float asso_pair(int kind, float norm, float4 a, float area_a, float4 b) {
-    if (kind == kVarCentroid) return iou_variant_pair(kVarCentroid, a, area_a, b, norm);
-    return iou_pair(a, area_a, b);
+// A compile-time choice: as a run-time field it cost the default "iou" path 10 % (registers spilled in the solvers' inner loops).
+template <int ASSO>
+__device__ __forceinline__ float asso_pair(float norm, float4 a, float area_a, float4 b) {
+    if constexpr (ASSO == kVarCentroid) return iou_variant_pair(kVarCentroid, a, area_a, b, norm);
+    else return iou_pair(a, area_a, b);
 }
 
 // Cost functor for block_lap(): rows = high-confidence detections (row_map -> detection index), columns =
 // tracks in list order.  cost = -(iou + angle cost * score).  is_candidate() additionally tallies the
 // reference's "trivial one-to-one" test (ocsort.cpp:676-689): which rows / columns see more than one
 // pair with iou > iou_threshold.
-struct OcmCost {
+template <int ASSO>
+struct OcmCostT {
     static constexpr bool kWarpPerRow = false;
     static constexpr bool kGrid = true;
     const float4* det_box;
@@ -112,8 +115,7 @@ struct OcmCost {
     unsigned* col_bits;               // [ceil(m/32)]
     unsigned short* row_hit;          // [n] column of (the last) such pair
     int* flags;                       // [0] any pair with iou > thr, [1] a row or column saw two
-    int asso;                         // AssociationFunction: 0 iou, 6 centroid ("iou" below means its value)
-    float asso_norm;                  // frame diagonal (centroid)
+    float asso_norm;                  // frame diagonal (ASSO = centroid; "iou" below means the AssociationFunction's value)
     struct Row { float4 b; float area, cx, cy, score; };
     __device__ __forceinline__ Row row(int i) const {
         Row r;
@@ -127,7 +129,7 @@ struct OcmCost {
     }
     __device__ __forceinline__ float4 col_box(int j) const { return trk_box[j]; }
     __device__ __forceinline__ bool reject(const Row& r, int j) const { return prune && boxes_disjoint(r.b, trk_box[j]); }
-    __device__ __forceinline__ float iou(const Row& r, int j) const { return asso_pair(asso, asso_norm, r.b, r.area, trk_box[j]); }
+    __device__ __forceinline__ float iou(const Row& r, int j) const { return asso_pair<ASSO>(asso_norm, r.b, r.area, trk_box[j]); }
     __device__ __forceinline__ float cost_from_iou(const Row& r, int j, float v) const {
         const float va = (valid[j] & 1) ? 1.0f : 0.0f;
         if (va == 0.0f) return -v;                     // 0 * angle * inertia * score adds exactly +-0
@@ -148,9 +150,10 @@ struct OcmCost {
             const unsigned ro = atomicOr(&row_bits[i >> 5], rb), co = atomicOr(&col_bits[j >> 5], cb);
             if (!(ro & rb)) {                          // the row's first such pair (its only one whenever row_hit is read)
                 row_hit[i] = (unsigned short)j;
-                atomicOr(&flags[0], 1);
+                if (*(volatile int*)&flags[0] == 0) atomicOr(&flags[0], 1);
             }
-            if ((ro & rb) || (co & cb)) atomicOr(&flags[1], 1);
+            // (same-address atomics serialise: only the first such pair of a frame pays one)
+            if (((ro & rb) || (co & cb)) && *(volatile int*)&flags[1] == 0) atomicOr(&flags[1], 1);
         }
     }
     __device__ __forceinline__ bool is_candidate(const Row& r, int i, int j, float thresh) const {
@@ -159,6 +162,8 @@ struct OcmCost {
         return cost_from_iou(r, j, v) <= thresh;
     }
 };
+
+using OcmCost = OcmCostT<0>;
 
 // DeepOC-SORT's first association (deepocsort.cpp:348-504): OcmCost plus the appearance term,
 //   cost = -((iou + angle cost * score) + w(i, j) * emb(i, j)),  emb = detection . track embedding where iou > 0, else 0 (:421-423),
@@ -211,7 +216,8 @@ struct DeepOcmCost {
 
 // Cost functor of the BYTE pass and the last-observation re-match: cost = -iou(detection, box of a track);
 // rows / columns are LIST positions (the lists may hold an index twice, see ocsort_kernel.cuh).
-struct NegIouCost {
+template <int ASSO>
+struct NegIouCostT {
     static constexpr bool kWarpPerRow = false;
     static constexpr bool kGrid = true;
     const float4* det_box;
@@ -221,7 +227,6 @@ struct NegIouCost {
     float iou_thr;
     bool prune;
     int* flags;                       // [0] any pair with iou > thr  (the reference's max_iou > threshold gate)
-    int asso;                         // AssociationFunction: 0 iou, 6 centroid
     float asso_norm;
     struct Row { float4 b; float area; };
     __device__ __forceinline__ Row row(int i) const {
@@ -232,11 +237,11 @@ struct NegIouCost {
     }
     __device__ __forceinline__ float4 col_box(int j) const { return trk_box[col_map[j]]; }
     __device__ __forceinline__ bool reject(const Row& r, int j) const { return prune && boxes_disjoint(r.b, col_box(j)); }
-    __device__ __forceinline__ float cost(const Row& r, int j) const { return -asso_pair(asso, asso_norm, r.b, r.area, col_box(j)); }
+    __device__ __forceinline__ float cost(const Row& r, int j) const { return -asso_pair<ASSO>(asso_norm, r.b, r.area, col_box(j)); }
     __device__ __forceinline__ float pair(int i, int j) const { return cost(row(i), j); }
     __device__ __forceinline__ double pair_bias(int i, int j) const { return twin_bias(i, j); }   // twins, as OcmCost
     __device__ __forceinline__ bool is_candidate(const Row& r, int, int j, float thresh) const {
-        const float v = asso_pair(asso, asso_norm, r.b, r.area, col_box(j));
+        const float v = asso_pair<ASSO>(asso_norm, r.b, r.area, col_box(j));
         if (v > iou_thr && *(volatile int*)&flags[0] == 0) atomicOr(&flags[0], 1);
         return -v <= thresh;
     }

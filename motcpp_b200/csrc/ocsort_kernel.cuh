@@ -468,14 +468,38 @@ __device__ __forceinline__ float deep_aw_weight(float mx, float se, float bottom
 
 // Ordered sums, warp-cooperative.  The contract (oracle/deepocsort.cpp, pinned against the reference) is the ascending-index
 // sum with one rounding per operation - a serial chain per sum.  A warp therefore takes up to 32 sums at once: for 32
-// consecutive indices at a time all lanes produce term(p, k) for item p (coalesced loads across the lanes), the 32 x 32
-// block goes through a padded shared tile, and lane p adds ITS item's 32 terms in ascending order.  Loads are coalesced,
-// the chains of 32 items run side by side, and the order of every sum is exactly the scalar loop's.
-constexpr int kDeepK = 16;                                   // indices per tile pass (two items per pass of the warp)
-constexpr int kDeepTileFloats = 32 * (kDeepK + 1);
+// consecutive indices at a time the operand slices of all 32 items are staged into padded shared tiles with cp.async
+// (one coalesced 128-byte row per instruction, up to 64 of them in flight per warp and no registers held - the loop is
+// bound by memory latency, so bytes in flight are what counts), and lane p then forms ITS item's 32 terms and adds them in
+// ascending order.  The chains of 32 items run side by side and the order of every sum is exactly the scalar loop's.
+constexpr int kDeepK = 32;                                   // indices per staged slice
+constexpr int kDeepRow = kDeepK + 4;                         // padded tile row, 16-byte aligned for the 16-byte copies
+constexpr int kDeepTileFloats = 2 * 32 * kDeepRow;           // operand tiles A and B of one warp
+
+__device__ __forceinline__ void deep_cp4(float* dst_shared, const float* src_global) {
+#if defined(MOT_CPUSIM)
+    *dst_shared = *src_global;
+#else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_shared)), "l"(src_global)
+                 : "memory");
+#endif
+}
+__device__ __forceinline__ void deep_cp16(float* dst_shared, const float* src_global) {
+#if defined(MOT_CPUSIM)
+    for (int k = 0; k < 4; ++k) dst_shared[k] = src_global[k];
+#else
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_shared)), "l"(src_global)
+                 : "memory");
+#endif
+}
+__device__ __forceinline__ void deep_cp_wait() {
+#if !defined(MOT_CPUSIM)
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
 
 // [scratch_a, row2col) of the sparse solver's workspace is dead outside block_lap (and outside oc_apply_matches'
-// col_label use): the tiles live there, one per participating warp
+// col_label use): the tiles live there, one pair per participating warp
 __device__ __forceinline__ int deep_tiles(const OcSmem& sm, float*& tiles) {
     tiles = (float*)sm.lap.scratch_a;
     const size_t bytes = (size_t)((const unsigned char*)sm.lap.row2col - (const unsigned char*)sm.lap.scratch_a);
@@ -484,33 +508,49 @@ __device__ __forceinline__ int deep_tiles(const OcSmem& sm, float*& tiles) {
     return n < nwarps ? n : nwarps;
 }
 
-// returns, in lane p < n_items (<= 32), sum_{k < dim} term(p, k) in ascending k.  term must be free of side effects
-// (it is also evaluated, and discarded, at clamped indices).  All 32 lanes of the warp must call.
-template <class Term>
-__device__ __forceinline__ float deep_warp_ordered_sums(float* tile, int n_items, int dim, Term term) {
-    const int lane = lane_id(), sub = lane & (kDeepK - 1), half = lane >> 4;
+// stage columns k0 .. k0 + 31 of row_a(p) (and row_b(p)) for the items p < n_items into tile rows p; warp-wide
+template <class RowA, class RowB>
+__device__ __forceinline__ void deep_stage(float* tile, int n_items, int k0, int dim, bool has_b, RowA row_a, RowB row_b) {
+    const int lane = lane_id(), kk = k0 + lane;
+    float* ta = tile + lane;
+    float* tb = tile + 32 * kDeepRow + lane;
+    // 16-byte copies when every row is 16-byte aligned and the slice is whole: a lane moves 4 floats, 8 lanes one row slice,
+    // a warp instruction four items' slices
+    const bool wide = (dim & 3) == 0 && k0 + kDeepK <= dim && ((((size_t)row_a(0)) | (has_b ? (size_t)row_b(0) : 0)) & 15) == 0;
+    if (wide) {
+        const int sub = (lane & 7) * 4, pi = lane >> 3;
+        for (int p0 = 0; p0 < n_items; p0 += 4) {
+            const int q = p0 + pi;
+            if (q < n_items) {
+                deep_cp16(tile + q * kDeepRow + sub, row_a(q) + k0 + sub);
+                if (has_b) deep_cp16(tile + 32 * kDeepRow + q * kDeepRow + sub, row_b(q) + k0 + sub);
+            }
+        }
+    } else if (kk < dim) {
+#pragma unroll 4
+        for (int p = 0; p < n_items; ++p) {
+            deep_cp4(ta + p * kDeepRow, row_a(p) + kk);
+            if (has_b) deep_cp4(tb + p * kDeepRow, row_b(p) + kk);
+        }
+    }
+    deep_cp_wait();
+    __syncwarp();
+}
+
+// returns, in lane p < n_items (<= 32), sum_{k < dim} f(p, row_a(p)[k], row_b(p)[k]) in ascending k.  All 32 lanes must call.
+template <class RowA, class RowB, class F>
+__device__ __forceinline__ float deep_warp_ordered_sums(float* tile, int n_items, int dim, bool has_b, RowA row_a, RowB row_b, F f) {
+    const int lane = lane_id();
     float acc = 0.0f;
     for (int k0 = 0; k0 < dim; k0 += kDeepK) {
-        const int kk = k0 + sub;
-        const int kc = kk < dim ? kk : dim - 1;
-        for (int p0 = 0; p0 < n_items; p0 += 16) {
-            float v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {                    // all the loads of 16 items first, then the stores
-                const int q = p0 + 2 * u + half;
-                const float t = term(q < n_items ? q : n_items - 1, kc);
-                v[u] = (q < n_items && kk < dim) ? t : 0.0f;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) tile[(p0 + 2 * u + half) * (kDeepK + 1) + sub] = v[u];
-        }
-        __syncwarp();
+        deep_stage(tile, n_items, k0, dim, has_b, row_a, row_b);
         if (lane < n_items) {
             const int cnt = min(kDeepK, dim - k0);
-            const float* row = tile + lane * (kDeepK + 1);
+            const float* ra = tile + lane * kDeepRow;
+            const float* rb = ra + 32 * kDeepRow;
             int q = 0;
-            if (k0 == 0) { acc = row[0]; q = 1; }
-            for (; q < cnt; ++q) acc = xadd(acc, row[q]);
+            if (k0 == 0) { acc = f(lane, ra[0], has_b ? rb[0] : 0.0f); q = 1; }
+            for (; q < cnt; ++q) acc = xadd(acc, f(lane, ra[q], has_b ? rb[q] : 0.0f));
         }
         __syncwarp();
     }
@@ -538,27 +578,28 @@ __device__ __forceinline__ void deep_write_embs(const DeepStream& dp, const OcSm
             alpha = xadd(p.alpha_fixed_emb, xmul(xsub(1.0f, p.alpha_fixed_emb), xsub(1.0f, trust)));
             beta = xsub(1.0f, alpha);
         }
-        const float sq = deep_warp_ordered_sums(tile, cnt, dim, [&](int q, int k) {
-            float v = __ldg(embs + (size_t)det_of(b0 + q) * dim + k);
-            if (blend) {
-                const float al = __shfl_sync(kFullMask, alpha, q), be = __shfl_sync(kFullMask, beta, q);
-                v = xadd(xmul(al, dp.trk_emb[(size_t)slot_of(b0 + q) * dim + k]), xmul(be, v));
-            }
+        // operand A: the detection's embedding; operand B (blend only): the track's current embedding
+        auto row_a = [&](int q) { return embs + (size_t)det_of(b0 + q) * dim; };
+        auto row_b = [&](int q) { return (const float*)(dp.trk_emb + (size_t)slot_of(b0 + q) * dim); };
+        const float sq = deep_warp_ordered_sums(tile, cnt, dim, blend, row_a, row_b, [&](int, float s, float e) {
+            const float v = blend ? xadd(xmul(alpha, e), xmul(beta, s)) : s;       // lane q owns item q: its own alpha / beta
             return xmul(v, v);
         });
         const float norm = xsqrt(sq);
-        for (int q = 0; q < cnt; ++q) {
-            const float n = __shfl_sync(kFullMask, norm, q);
-            const float al = __shfl_sync(kFullMask, alpha, q), be = __shfl_sync(kFullMask, beta, q);
-            float* e = dp.trk_emb + (size_t)slot_of(b0 + q) * dim;
-            const float* src = embs + (size_t)det_of(b0 + q) * dim;
-            const bool scale = n > 1e-6f;
-#pragma unroll 4
-            for (int k = lane; k < dim; k += 32) {
-                float v = __ldg(src + k);
-                if (blend) v = xadd(xmul(al, e[k]), xmul(be, v));
-                e[k] = scale ? xdiv(v, n) : v;
+        // second pass: the same slices again, every lane now writes column `lane` of all items (coalesced rows)
+        for (int k0 = 0; k0 < dim; k0 += kDeepK) {
+            deep_stage(tile, cnt, k0, dim, blend, row_a, row_b);
+            const int kk = k0 + lane;
+            for (int q = 0; q < cnt; ++q) {
+                const float n = __shfl_sync(kFullMask, norm, q);
+                const float al = __shfl_sync(kFullMask, alpha, q), be = __shfl_sync(kFullMask, beta, q);
+                if (kk < dim) {
+                    const float sv = tile[q * kDeepRow + lane];
+                    const float v = blend ? xadd(xmul(al, tile[32 * kDeepRow + q * kDeepRow + lane]), xmul(be, sv)) : sv;
+                    dp.trk_emb[(size_t)slot_of(b0 + q) * dim + kk] = (n > 1e-6f) ? xdiv(v, n) : v;
+                }
             }
+            __syncwarp();
         }
     }
 }
@@ -640,12 +681,10 @@ __device__ __forceinline__ int deep_embedding_terms(const DeepStream& dp, const 
             float* tile = tiles + (size_t)warp * kDeepTileFloats;
             for (int b0 = warp * 32; b0 < n_pairs; b0 += nw * 32) {
                 const int cnt = min(32, n_pairs - b0);
-                const float val = deep_warp_ordered_sums(tile, cnt, dim, [&](int q, int k) {
-                    const unsigned pr = pairs[b0 + q];
-                    const float* de = embs + (size_t)sm.high[pr >> 16] * dim;
-                    const float* te = dp.trk_emb + (size_t)sm.list_a[pr & 0xffffu] * dim;
-                    return xmul(__ldg(de + k), te[k]);
-                });
+                const float val = deep_warp_ordered_sums(
+                    tile, cnt, dim, true, [&](int q) { return embs + (size_t)sm.high[pairs[b0 + q] >> 16] * dim; },
+                    [&](int q) { return (const float*)(dp.trk_emb + (size_t)sm.list_a[pairs[b0 + q] & 0xffffu] * dim); },
+                    [&](int, float de, float te) { return xmul(de, te); });
                 if (lane < cnt) {
                     const unsigned pr = pairs[b0 + lane];
                     const int i = (int)(pr >> 16), j = (int)(pr & 0xffffu);
@@ -681,7 +720,7 @@ __device__ __forceinline__ int deep_embedding_terms(const DeepStream& dp, const 
     return mode;
 }
 
-template <int CAP, int DMAX, bool DEEP>
+template <int CAP, int DMAX, bool DEEP, int ASSO>
 __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, OcSmem& sm, const float* dets, int n_det_in,
                                          float* out, int* n_out, const DeepStream& dp, const float* embs) {
     const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
@@ -724,8 +763,8 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
     __syncthreads();
     const float score_bound = __int_as_float(sm.flags[3]);
     // (a centroid similarity is non-zero for disjoint boxes too: no pruning with it)
-    const bool prune_first = a.p.asso == 0 && thr >= 0.0f && (0.5f * fabsf(a.p.inertia) * score_bound * 1.0001f + 1e-7f) < thr;
-    const bool prune_rest = a.p.asso == 0 && thr > 0.0f;
+    const bool prune_first = ASSO == 0 && thr >= 0.0f && (0.5f * fabsf(a.p.inertia) * score_bound * 1.0001f + 1e-7f) < thr;
+    const bool prune_rest = ASSO == 0 && thr > 0.0f;
     const bool use_emb = DEEP && !a.p.embedding_off;
     __syncthreads();
     if (tid == 0) sm.flags[3] = 0;
@@ -809,9 +848,10 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
     __syncthreads();
 
     // ---- D. first association (:413-420, associate :610-737); rows = high detections, columns = tracks
-    const OcmCost ocm_base{sm.det_box, sm.det_conf, sm.high, sm.trk_box, st.ocm, st.valid, a.p.inertia, thr, prune_first,
-                           sm.row_bits, sm.col_bits, sm.pair_det /* row_hit */, sm.flags, a.p.asso, a.p.asso_norm};
-    std::conditional_t<DEEP, DeepOcmCost, OcmCost> ocm;
+    static_assert(!DEEP || ASSO == 0, "DeepOC-SORT's sparse appearance terms rely on IoU (iou <= 0 masks the product)");
+    const OcmCostT<ASSO> ocm_base{sm.det_box, sm.det_conf, sm.high, sm.trk_box, st.ocm, st.valid, a.p.inertia, thr, prune_first,
+                                  sm.row_bits, sm.col_bits, sm.pair_det /* row_hit */, sm.flags, a.p.asso_norm};
+    std::conditional_t<DEEP, DeepOcmCost, OcmCostT<ASSO>> ocm;
     if constexpr (DEEP) {
         // appearance term (deepocsort.cpp:420-440): needs detections (the reference leaves the matrix empty without, :756)
         const int emb_mode = (use_emb && n_high > 0) ? deep_embedding_terms(dp, st, sm, embs, a.p, n_high, n_trk) : 0;
@@ -911,7 +951,7 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
         __syncthreads();
         if (tid == 0) sm.flags[2] = 0;
         __syncthreads();
-        NegIouCost cost{sm.det_box, sm.second, sm.trk_box, sm.ut, thr, prune_rest, sm.flags, a.p.asso, a.p.asso_norm};
+        NegIouCostT<ASSO> cost{sm.det_box, sm.second, sm.trk_box, sm.ut, thr, prune_rest, sm.flags, a.p.asso_norm};
         block_lap(sm.lap, n_second, n_ut, DMAX, CAP, -thr, cost);
         if (sm.flags[0] != 0)
             for (int p = tid; p < n_ut; p += nt)
@@ -947,7 +987,7 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
         }
         if (tid == 0) { sm.flags[0] = 0; sm.flags[2] = 0; }
         __syncthreads();
-        NegIouCost cost{sm.det_box, sm.ud, sm.trk_box, sm.ut, thr, prune_rest, sm.flags, a.p.asso, a.p.asso_norm};
+        NegIouCostT<ASSO> cost{sm.det_box, sm.ud, sm.trk_box, sm.ut, thr, prune_rest, sm.flags, a.p.asso_norm};
         block_lap(sm.lap, n_ud, n_ut, DMAX, CAP, -thr, cost);
         // Exact ties here: (1) the lists hold an entry twice (pairs rejected by the IoU filter; in DeepOC-SORT also everything the assignment left unmatched) - which
         // COPY of a detection is matched decides the order in which a twice-listed track receives its two updates;
@@ -1065,13 +1105,15 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
     __syncthreads();
 }
 
-template <int CAP, int DMAX, int ECAP, bool DEEP>
+template <int CAP, int DMAX, int ECAP, bool DEEP, int ASSO = 0>
 __device__ __forceinline__ void oc_step_body(const OcArgs& a) {
     MOT_DYNAMIC_SMEM(smem);
     OcSmem sm;
     oc_carve(smem, CAP, DMAX, ECAP, sm);
     constexpr OcLayout L = OcLayout::make(CAP, DMAX);
     static_assert(lap_idle_bytes(DMAX, CAP, ECAP) >= jv_block_sbytes(DMAX + CAP), "the CTA-wide LAPJV's shared scratch must fit the sparse solver's idle arrays");
+    static_assert(!DEEP || lap_idle_bytes(DMAX, CAP, ECAP) - lap_align16(sizeof(int) * (size_t)DMAX) - lap_align16(sizeof(int) * (size_t)CAP) >=
+                               sizeof(float) * kDeepTileFloats, "DeepOC-SORT needs room for at least one pair of summation tiles");
     const size_t stride = DEEP ? a.stride : L.stride;
     for (int s = a.s_begin + (int)blockIdx.x; s < a.s_end; s += (int)gridDim.x) {
         unsigned char* base = a.state + (size_t)s * stride;
@@ -1082,7 +1124,7 @@ __device__ __forceinline__ void oc_step_body(const OcArgs& a) {
         for (int t = 0; t < a.T; ++t) {
             const size_t fs = (size_t)t * a.S + s;
             const float* embs = (DEEP && a.embs) ? a.embs + fs * (size_t)a.ld_dets * (size_t)a.dim : nullptr;
-            oc_frame<CAP, DMAX, DEEP>(a, st, sm, a.dets + fs * (size_t)a.ld_dets * 6, a.n_dets[fs],
+            oc_frame<CAP, DMAX, DEEP, ASSO>(a, st, sm, a.dets + fs * (size_t)a.ld_dets * 6, a.n_dets[fs],
                                       a.out + fs * (size_t)a.ld_out * 8, a.n_out + fs, dp, embs);
         }
     }
@@ -1090,6 +1132,10 @@ __device__ __forceinline__ void oc_step_body(const OcArgs& a) {
 
 template <int CAP, int DMAX, int ECAP>
 __global__ void __launch_bounds__(kOcThreads) ocsort_step_kernel(OcArgs a) { oc_step_body<CAP, DMAX, ECAP, false>(a); }
+
+// OC-SORT with asso_func = "centroid" (iou.hpp:298-330): the same frame step over 1 - centre distance / frame diagonal
+template <int CAP, int DMAX, int ECAP>
+__global__ void __launch_bounds__(kOcThreads) ocsort_centroid_step_kernel(OcArgs a) { oc_step_body<CAP, DMAX, ECAP, false, kVarCentroid>(a); }
 
 // DeepOC-SORT (reference src/trackers/deepocsort.cpp:589-944, associate :348-504): the OC-SORT frame step without the
 // BYTE pass, plus the appearance term of the first association, the embedding EMA of every updated track and the

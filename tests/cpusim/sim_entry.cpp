@@ -218,7 +218,8 @@ int sim_oc_update(void* hv, const float* dets, const int* n_dets, int T, int ld_
     a.state = h->state.data(); a.dets = dets; a.n_dets = n_dets; a.out = out; a.n_out = n_out;
     a.T = T; a.S = h->S; a.ld_dets = ld_dets; a.ld_out = ld_out; a.s_begin = 0; a.s_end = h->S; a.p = h->p;
     const size_t smem = mot::oc_smem_bytes(256, 64, 1024);
-    cpusim::launch(dim3(h->S), dim3(threads), smem, [=] { mot::ocsort_step_kernel<256, 64, 1024>(a); });
+    if (h->p.asso == mot::kVarCentroid) cpusim::launch(dim3(h->S), dim3(threads), smem, [=] { mot::ocsort_centroid_step_kernel<256, 64, 1024>(a); });
+    else cpusim::launch(dim3(h->S), dim3(threads), smem, [=] { mot::ocsort_step_kernel<256, 64, 1024>(a); });
     return 0;
 }
 void sim_oc_header(void* hv, int s, int* hdr16) {
