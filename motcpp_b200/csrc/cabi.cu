@@ -544,7 +544,13 @@ int mot_engine_update_host_packed(mot_engine* e, int T, const float* dets, const
     MOT_CUDA(cudaSetDevice(e->cfg.device));
     const int S = e->cfg.n_streams, ld_out = max_rows;
     const size_t TS = (size_t)T * S;
-    const int C = std::max(1, std::min(kMaxChunks, T / 2));
+    // frames per pipeline chunk: 1-2 is the plateau on the C2 workload (1.79 M frames/s; 3 -> 1.75, 5 -> 1.72, 8 -> 1.65 M);
+    // what is left between this path and the device-resident rate (12 %) is the compaction kernels, which cannot co-reside
+    // with the frame-step kernel (its two CTAs per SM take the whole register file) and so run between its launches.
+    // (Also measured: an L2 persisting window over the tracker state - no effect.)
+    int chunk_frames = 2;
+    if (const char* ev = std::getenv("MOT_PACKED_CHUNK_FRAMES")) chunk_frames = std::max(1, std::atoi(ev));   // measurement aid
+    const int C = std::max(1, std::min(kMaxChunks, T / chunk_frames));
     if (int rc = grow(&e->d_dets, &e->dets_cap, TS * ld_dets * 6)) return rc;
     if (int rc = grow(&e->d_ndets, &e->ndets_cap, TS)) return rc;
     if (int rc = grow(&e->d_out, &e->out_cap, TS * ld_out * 8)) return rc;
