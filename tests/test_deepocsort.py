@@ -162,3 +162,39 @@ def test_gpu_deepocsort_api_mirror(oracle, gpu):
     trk.reset(); ref = oracle.DeepOCSort(**{**DOC, "max_age": 10})
     with pytest.raises((_lib.MotError, ValueError)):
         api.Engine(_lib.TRACKER_DEEPOCSORT, 1, 256, 64)                                # embeddings on but no width
+
+
+@pytest.mark.gpu
+def test_gpu_deepocsort_reset_capacity_flag_and_packed_path(oracle, gpu):
+    """reset() clears the tracks and keeps the id counter (deepocsort.cpp:575-579); the reference's twice-listed leftovers
+    overflow a too-small engine loudly (flag bit 1), never silently; the packed host path carries no embeddings."""
+    d, c, e = _stream(91, 50, 8)
+    args = {**DOC, "max_age": 8}
+    eng = api.Engine(_lib.TRACKER_DEEPOCSORT, 1, 256, 64, emb_dim=8, **{k: v for k, v in args.items()})
+    ref = oracle.DeepOCSort(**args)
+    def run(t0, t1):
+        out, n_out = eng.update(d[t0:t1, None], c[t0:t1, None].astype(np.int32), ld_out=256, embs=e[t0:t1, None])
+        eng.check()
+        for t in range(t0, t1):
+            want = ref.update(d[t, :c[t]], e[t, :c[t]])
+            assert np.array_equal(out[t - t0, 0, :n_out[t - t0, 0]], want), t
+    run(0, 20)
+    eng.reset(); ref.reset()
+    run(20, 50)                                            # fresh tracks, ids continue where they stopped
+    assert eng.dump(0, 0)[:, 0].min() > 20
+    eng.close()
+    # capacity: 40 objects + clutter with max_age 30 need far more than 2 x unmatched <= 256 after a while
+    eng = api.Engine(_lib.TRACKER_DEEPOCSORT, 1, 256, 64, emb_dim=16, **{**DOC, "aw_off": True})
+    d2, c2, e2 = _stream(71, 60, 16)
+    eng.update(d2[:, None], c2[:, None].astype(np.int32), ld_out=256, embs=e2[:, None])
+    with pytest.raises(RuntimeError, match="capacity"):
+        eng.check()
+    with pytest.raises(_lib.MotError):
+        eng.update_packed(d2[:4, None], c2[:4, None].astype(np.int32), max_rows=64)
+    eng.close()
+    off = api.Engine(_lib.TRACKER_DEEPOCSORT, 1, 256, 64, embedding_off=1, max_age=6)
+    rows, offsets, n_out = off.update_packed(d[:10, None], c[:10, None].astype(np.int32), max_rows=256)
+    ref = oracle.DeepOCSort(**{**DOC, "embedding_off": True, "max_age": 6})
+    for t in range(10):
+        assert np.array_equal(rows[offsets[t]:offsets[t + 1]], ref.update(d[t, :c[t]])), t
+    off.close()
