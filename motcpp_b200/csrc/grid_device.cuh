@@ -148,57 +148,4 @@ __device__ __forceinline__ void grid_query_iou_above(const BoxGrid& g, float4 a,
     }
 }
 
-// Warp-synchronous pair collection: every lane walks the cells of ITS row box `a` (lanes without a row pass
-// active = false) and the warp appends the overlapping (row << 16 | column) pairs to pairs[0 .. cap) with ONE shared-memory
-// atomic per step (ballot + leader) instead of one per pair - the single counter was the hot spot of the candidate
-// search (thousands of same-address atomics per frame).  *counter keeps counting past cap (the caller checks).
-// t = 0: every overlapping column (grid_query's window); 0 < t < 1: only the window an IoU > t partner can sit in
-// (grid_query_iou_above).  ALL 32 lanes of the warp must call.
-template <class BoxOf>
-__device__ __forceinline__ void grid_collect_pairs(const BoxGrid& g, bool active, float4 a, int row, float t, BoxOf box_of,
-                                                   int* counter, int* pairs, int cap) {
-    const int lane = lane_id();
-    int cx0 = 0, cx1 = -1, cy0 = 1, cy1 = 0;
-    if (active) {
-        if (t > 0.0f) {
-            const float u = 1.0f - t;
-            const float wa = a.z - a.x, ha = a.w - a.y;
-            const float lx = u * g.max_w + (fabsf(a.x) + g.max_w) * 1e-5f, ly = u * g.max_h + (fabsf(a.y) + g.max_h) * 1e-5f;
-            const float rx = u * wa + (fabsf(a.x) + fabsf(wa)) * 1e-5f, ry = u * ha + (fabsf(a.y) + fabsf(ha)) * 1e-5f;
-            cx0 = g.cx(a.x - lx); cx1 = g.cx(a.x + rx); cy0 = g.cy(a.y - ly); cy1 = g.cy(a.y + ry);
-        } else {
-            const float mx = g.max_w + (fabsf(a.x) + g.max_w) * 1e-6f, my = g.max_h + (fabsf(a.y) + g.max_h) * 1e-6f;
-            cx0 = g.cx(a.x - mx); cx1 = g.cx(a.z); cy0 = g.cy(a.y - my); cy1 = g.cy(a.w);
-        }
-    }
-    int yy = cy0, e = 0, e1 = 0;
-    bool more = active;
-    while (__any_sync(kFullMask, more)) {
-        int found = -1;
-        while (more && found < 0) {                       // this lane's next overlapping column, if any
-            if (e < e1) {
-                const int j = g.items[e++];
-                const float4 b = box_of(j);
-                if ((fminf(a.z, b.z) > fmaxf(a.x, b.x)) && (fminf(a.w, b.w) > fmaxf(a.y, b.y))) found = j;
-            } else if (yy <= cy1) {
-                e = g.cell[yy * kGridX + cx0];
-                e1 = g.cell[yy * kGridX + cx1 + 1];
-                ++yy;
-            } else {
-                more = false;
-            }
-        }
-        const unsigned hit = __ballot_sync(kFullMask, found >= 0);
-        if (hit) {
-            int base = 0;
-            if (lane == __ffs((int)hit) - 1) base = atomicAdd(counter, __popc(hit));
-            base = __shfl_sync(kFullMask, base, __ffs((int)hit) - 1);
-            if (found >= 0) {
-                const int q = base + __popc(hit & ((1u << lane) - 1u));
-                if (q < cap) pairs[q] = (row << 16) | found;
-            }
-        }
-    }
-}
-
 }  // namespace mot

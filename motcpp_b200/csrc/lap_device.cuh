@@ -169,16 +169,6 @@ __device__ __forceinline__ void team_hungarian(unsigned mask, int tl, const unsi
     }
 }
 
-// ascending insertion sort of a short segment by ONE thread
-__device__ __forceinline__ void insertion_sort_u16(unsigned short* seg, int n) {
-    for (int a = 1; a < n; ++a) {
-        const unsigned short key = seg[a];
-        int b = a - 1;
-        while (b >= 0 && seg[b] > key) { seg[b + 1] = seg[b]; --b; }
-        seg[b + 1] = key;
-    }
-}
-
 struct LapGlobalScratch {      // by-value view of the global-memory scratch (keeps LapWorkspace out of local memory)
     double* g_u; double* g_v; double* g_minv; int* g_way; int* g_prow; unsigned char* g_flags;
 };

@@ -867,11 +867,7 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
         for (int j = tid; j < n_trk; j += nt)
             if (sm.lap.col2row[j] >= 0 && (st.valid[j] & 2)) sm.flags[2] = 1;
     __syncthreads();
-#ifdef MOT_OC_FORCE_EXACT
-    const bool exact1 = sm.flags[2] != 0 || (!trivial && (MOT_OC_FORCE_EXACT & 1));
-#else
     const bool exact1 = sm.flags[2] != 0;
-#endif
     __syncthreads();
     if (exact1) {
         // a twin track is a candidate: the optimum may be non-unique, so redo the assignment with the reference's own
@@ -1006,11 +1002,7 @@ __device__ __forceinline__ void oc_frame(const OcArgs& a, const OcStream& st, Oc
                 }
             }
         __syncthreads();
-#ifdef MOT_OC_FORCE_EXACT
-        if (sm.flags[2] != 0 || (sm.flags[0] != 0 && (MOT_OC_FORCE_EXACT & 4))) {
-#else
         if (sm.flags[2] != 0) {
-#endif
             __syncthreads();
             oc_exact_assignment<CAP, DMAX>(st, sm, n_ud, n_ut, -thr, [&](int i, int j) { return cost.pair(i, j); });
         }
