@@ -254,9 +254,10 @@ int mot_lap_device(const float* cost, int n, int m, int ld, float thresh, int* r
 int mot_lap_batch_device(const float* cost, long long stride_cost, int n_problems, const int* n_rows,
                          const int* n_cols, int n, int m, int ld, float thresh, int* row2col, int* col2row,
                          void* stream);
-/* The reference's dense LAPJV itself, step for step (lap_solver.hpp:36-231 on the (n+m)^2 extended matrix), one warp
- * per problem, n + m <= 384: same matches as mot_lap_* whenever the optimum is unique, and the REFERENCE's choice when
- * it is not (exact cost ties).  The OC-SORT engine uses it for frames with bit-identical twin tracks. */
+/* The reference's dense LAPJV itself, step for step (lap_solver.hpp:36-231 on the (n+m)^2 extended matrix): one warp per
+ * problem while n + m <= 384, one CTA per problem above that (any size up to n + m = 32000).  Same matches as mot_lap_*
+ * whenever the optimum is unique, and the REFERENCE's choice when it is not (exact cost ties).  The OC-SORT, DeepOC-SORT and
+ * StrongSORT engines run it on every frame that can tie (twin tracks, duplicated lists / rows). */
 int mot_lap_jv_batch_device(const float* cost, long long stride_cost, int n_problems, int n, int m, int ld, float thresh,
                             int* row2col, int* col2row, void* stream);
 /* convenience: host pointers, synchronous */
