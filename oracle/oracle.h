@@ -207,6 +207,22 @@ void orc_botsort_last_sizes(const OrcBotSort*, int* sizes8);
  * det_ind, has_feat, mean 8, cov 64] = 82 floats; feats (nullable): smooth_feat rows of dim floats */
 int orc_botsort_dump(const OrcBotSort*, int which, float* out, float* feats, int dim, int cap_rows);
 
+/* ---------------- BoostTrack (src/trackers/boosttrack.cpp; default options, ECC / ReID off) ---------- */
+typedef struct OrcBoostTrack OrcBoostTrack;
+void orc_boost_iou_dist(const float* dets4, int n, const float* trk4, int m, float* out);                  /* :297-329 */
+void orc_boost_mh_dist(const float* dets4, int n, const float* mean4, const float* var4, int m, float* out); /* :331-358 */
+void orc_boost_cost(const float* iou_dist, const float* mh_dist, const float* emb, int n, int m, float lambda_iou, float lambda_mhd,
+                    float lambda_shape, float* out);                                                        /* :571-626 */
+OrcBoostTrack* orc_boosttrack_create(float det_thresh, int max_age, int max_obs, int min_hits, float iou_threshold, int min_box_area,
+                                     float aspect_ratio_thresh, float lambda_iou, float lambda_mhd, float lambda_shape,
+                                     int use_dlo_boost, float dlo_boost_coef, int use_vt);
+void orc_boosttrack_destroy(OrcBoostTrack* s);
+void orc_boosttrack_reset(OrcBoostTrack* s);
+int orc_boosttrack_update(OrcBoostTrack* s, const float* dets, int n, float* out, int out_cap);
+int orc_boosttrack_count(const OrcBoostTrack* s);
+void orc_boosttrack_last_sizes(const OrcBoostTrack* s, int* out4);
+int orc_boosttrack_dump(const OrcBoostTrack* s, float* out80, int cap_rows);
+
 #ifdef __cplusplus
 }
 #endif

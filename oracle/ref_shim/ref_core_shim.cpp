@@ -27,6 +27,7 @@
 #include <motcpp/tracker.hpp>
 #include <motcpp/trackers/botsort.hpp>
 #include <motcpp/trackers/bytetrack.hpp>
+#include <motcpp/trackers/boosttrack.hpp>
 #include <motcpp/trackers/deepocsort.hpp>
 #include <motcpp/trackers/ocsort.hpp>
 #include <motcpp/trackers/sort.hpp>
@@ -312,6 +313,12 @@ void* ref_tracker_create(const char* kind, const float* p, int np) {
             t = new motcpp::trackers::DeepOCSort("", false, false, p[0], (int)p[1], (int)p[2], (int)p[3], p[4], false, 80,
                                                  "iou", false, (int)p[5], p[6], p[7], p[8], p[9], p[10] != 0.0f, true,
                                                  p[11] != 0.0f, p[12], p[13]);
+        } else if (k == "boosttrack") { // det_thresh, max_age, max_obs, min_hits, iou_threshold, min_box_area, aspect_ratio_thresh, lambda_iou, lambda_mhd, lambda_shape, use_dlo_boost, dlo_boost_coef, use_vt   (use_ecc = false, with_reid = false, use_sb = false)
+            need(13);
+            t = new motcpp::trackers::BoostTrackTracker("", false, false, p[0], (int)p[1], (int)p[2], (int)p[3], p[4], false, 80,
+                                                        "iou", false, /*use_ecc=*/false, (int)p[5], p[6], "none", p[7], p[8], p[9],
+                                                        p[10] != 0.0f, true, p[11], false, false, /*use_sb=*/false, p[12] != 0.0f,
+                                                        /*with_reid=*/false);
         } else {
             throw std::invalid_argument("ref_tracker_create: unknown kind " + k);
         }

@@ -91,6 +91,18 @@ def lib() -> C.CDLL:
         L.orc_clamp_cost.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_float]
         L.orc_kf_xysr_affine.argtypes = [f32p, f32p, f32p, f32p]
         L.orc_atanf.argtypes, L.orc_atanf.restype = [C.c_float], C.c_float
+        L.orc_boost_iou_dist.argtypes = [f32p, C.c_int, f32p, C.c_int, f32p]
+        L.orc_boost_mh_dist.argtypes = [f32p, C.c_int, f32p, f32p, C.c_int, f32p]
+        L.orc_boost_cost.argtypes = [f32p, f32p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, f32p]
+        L.orc_boosttrack_create.argtypes = [C.c_float, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float, C.c_float,
+                                            C.c_float, C.c_int, C.c_float, C.c_int]
+        L.orc_boosttrack_create.restype = C.c_void_p
+        L.orc_boosttrack_destroy.argtypes = [C.c_void_p]
+        L.orc_boosttrack_reset.argtypes = [C.c_void_p]
+        L.orc_boosttrack_update.argtypes = [C.c_void_p, f32p, C.c_int, f32p, C.c_int]
+        L.orc_boosttrack_count.argtypes = [C.c_void_p]
+        L.orc_boosttrack_last_sizes.argtypes = [C.c_void_p, i32p]
+        L.orc_boosttrack_dump.argtypes = [C.c_void_p, f32p, C.c_int]
         L.orc_iou_variant.argtypes = [f32p, C.c_int, f32p, C.c_int, C.c_int, C.c_int, C.c_int, f32p]
         L.orc_aw_max_metric.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, f32p, C.c_int]
         L.orc_ocsort_create.argtypes = [C.c_float, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
@@ -602,3 +614,56 @@ class DeepOCSort:
         s = np.zeros(8, np.int32)
         lib().orc_deepocsort_last_sizes(self._h, s)
         return s
+
+
+class BoostTrack:
+    """Oracle BoostTrack: the constructor arguments that reach the association, reference names and defaults
+    (include/motcpp/trackers/boosttrack.hpp:95-124); ECC and ReID off, use_sb = False."""
+
+    def __init__(self, det_thresh=0.6, max_age=60, max_obs=50, min_hits=3, iou_threshold=0.3, min_box_area=10,
+                 aspect_ratio_thresh=1.6, lambda_iou=0.5, lambda_mhd=0.25, lambda_shape=0.25, use_dlo_boost=True,
+                 dlo_boost_coef=0.65, use_vt=False):
+        self._h = lib().orc_boosttrack_create(det_thresh, max_age, max_obs, min_hits, iou_threshold, int(min_box_area),
+                                              aspect_ratio_thresh, lambda_iou, lambda_mhd, lambda_shape, int(use_dlo_boost),
+                                              dlo_boost_coef, int(use_vt))
+        self._out = np.zeros((8192, 8), np.float32)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_boosttrack_destroy(self._h)
+            self._h = None
+
+    def reset(self):
+        lib().orc_boosttrack_reset(self._h)
+
+    def update(self, dets, embs=None):
+        dets = _f32(dets).reshape(-1, 6)
+        n = lib().orc_boosttrack_update(self._h, dets, dets.shape[0], self._out, self._out.shape[0])
+        assert n >= 0
+        return self._out[:n].copy()
+
+    def dump(self):
+        cap = max(1, lib().orc_boosttrack_count(self._h))
+        buf = np.zeros((cap, 80), np.float32)
+        return buf[:lib().orc_boosttrack_dump(self._h, buf, cap)]
+
+    def last_sizes(self):
+        s = np.zeros(4, np.int32)
+        lib().orc_boosttrack_last_sizes(self._h, s)
+        return s
+
+
+def boost_cost(dets4, trk_boxes, mean4, var4, lambda_iou=0.5, lambda_mhd=0.25, lambda_shape=0.25, emb=None):
+    """BoostTrack's association cost (boosttrack.cpp:297-358, :571-626): (cost, iou_dist, mh_dist), each (n, m)"""
+    d, t, mu, va = _f32(dets4).reshape(-1, 4), _f32(trk_boxes).reshape(-1, 4), _f32(mean4).reshape(-1, 4), _f32(var4).reshape(-1, 4)
+    n, m = d.shape[0], t.shape[0]
+    iou, mh, cost = (np.zeros((n, m), np.float32) for _ in range(3))
+    if n and m:
+        lib().orc_boost_iou_dist(d, n, t, m, iou)
+        lib().orc_boost_mh_dist(d, n, mu, va, m, mh)
+        ep = None
+        if emb is not None:
+            emb = _f32(emb).reshape(n, m)
+            ep = emb.ctypes.data_as(C.c_void_p)
+        lib().orc_boost_cost(iou, mh, ep, n, m, lambda_iou, lambda_mhd, lambda_shape, cost)
+    return cost, iou, mh

@@ -387,3 +387,19 @@ def test_ocsort_centroid_association_equals_reference(order, sid, over):
     args = {**OC, **over}
     ref = R.Tracker("ocsort", [float(v) for v in args.values()], order, asso_func="centroid")
     _run(order, O.OCSort(**args, tie_mode=0, asso_func="centroid", frame=(1920, 1080)), ref, _stress(90 + sid, 120))
+
+
+BOOST = dict(det_thresh=0.6, max_age=60, max_obs=50, min_hits=3, iou_threshold=0.3, min_box_area=10, aspect_ratio_thresh=1.6,
+             lambda_iou=0.5, lambda_mhd=0.25, lambda_shape=0.25, use_dlo_boost=True, dlo_boost_coef=0.65, use_vt=False)
+
+
+@pytest.mark.parametrize("order", ["textbook", "eigen"])
+@pytest.mark.parametrize("sid,over", [(0, {}), (1, {"det_thresh": 0.4, "max_age": 8, "min_hits": 1, "use_vt": True}),
+                                      (2, {"use_dlo_boost": False, "lambda_mhd": 0.6, "iou_threshold": 0.5, "aspect_ratio_thresh": 0.5}),
+                                      (3, {"det_thresh": 0.3, "dlo_boost_coef": 0.9, "max_age": 3, "min_box_area": 4000})])
+def test_boosttrack_stress_streams_equal_reference(order, sid, over):
+    """SURVEY 8f-1, second half: BoostTrack (ECC / ReID off) - Kalman filter through Eigen's dynamic 4 x 4 inverse, IoU +
+    diagonal-Mahalanobis cost blend, detection-confidence boost, output filter."""
+    args = {**BOOST, **over}
+    ref = R.Tracker("boosttrack", [float(v) for v in args.values()], order)
+    _run(order, O.BoostTrack(**args), ref, _stress(110 + sid, 200))
