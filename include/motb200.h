@@ -62,7 +62,8 @@ typedef enum mot_tracker_kind {
     MOT_TRACKER_OCSORT = 2,
     MOT_TRACKER_BOTSORT = 3,
     MOT_TRACKER_STRONGSORT = 4,
-    MOT_TRACKER_DEEPOCSORT = 5
+    MOT_TRACKER_DEEPOCSORT = 5,
+    MOT_TRACKER_BOOSTTRACK = 6
 } mot_tracker_kind;
 
 typedef struct mot_engine_config {
@@ -104,6 +105,14 @@ typedef struct mot_engine_config {
      * "diou", "ciou") are only defined by the reference when the second box set has one row and are refused; every other
      * front-end uses plain IoU internally whatever asso_func says, as in the reference. */
     int asso_func, frame_width, frame_height;
+    /* BoostTrackTracker ctor (include/motcpp/trackers/boosttrack.hpp:95-124); det_thresh, max_age, min_hits, iou_threshold
+     * above are shared.  Camera-motion compensation and ReID are outside the hot path (the engine behaves as use_ecc =
+     * false, with_reid = false); use_sb (a powf in the confidence boost) is refused. */
+    int min_box_area;
+    float aspect_ratio_thresh, lambda_iou, lambda_mhd, lambda_shape;
+    int use_dlo_boost;
+    float dlo_boost_coef;
+    int use_sb, use_vt;
 } mot_engine_config;
 
 typedef struct mot_engine mot_engine;
@@ -171,6 +180,9 @@ int mot_engine_dump_deep_embs(mot_engine* e, int stream_index, float* embs, int 
 /* StrongSORT engines: the track list (reference order) as rows of [id,state,hits,0,time_since_update,conf,cls,det_ind,
  * has_feat,n_gallery_samples,mean 8,cov 64] (82 floats); feats (nullable) receives the smoothed features. */
 int mot_engine_dump_strong(mot_engine* e, int stream_index, float* rows82, float* feats, int cap_rows, int* n_rows);
+/* BoostTrack engines: the track list as rows of [id, age, hit_streak, time_since_update, conf, cls, det_ind, 0, x 8, P 8x8]
+ * (80 floats; the covariance expanded from its four 2 x 2 blocks). */
+int mot_engine_dump_boost(mot_engine* e, int stream_index, float* rows80, int cap_rows, int* n_rows);
 /* launch geometry actually used (for the bench's gpu_launches / roofline bookkeeping) */
 int mot_engine_info(mot_engine* e, int* threads_per_cta, int* smem_bytes, int* ctas, int* state_bytes_per_stream);
 

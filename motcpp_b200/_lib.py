@@ -17,6 +17,7 @@ MOT_ERR_NUMERIC = 5
 MOT_ERR_UNSUPPORTED = 6
 
 TRACKER_SORT, TRACKER_BYTETRACK, TRACKER_OCSORT, TRACKER_BOTSORT, TRACKER_STRONGSORT, TRACKER_DEEPOCSORT = 0, 1, 2, 3, 4, 5
+TRACKER_BOOSTTRACK = 6
 KF_XYAH, KF_XYSR, KF_XYWH = 0, 1, 2
 
 
@@ -44,6 +45,8 @@ class EngineConfig(C.Structure):
         ("w_association_emb", C.c_float), ("alpha_fixed_emb", C.c_float), ("aw_param", C.c_float),
         ("embedding_off", C.c_int), ("aw_off", C.c_int),
         ("asso_func", C.c_int), ("frame_width", C.c_int), ("frame_height", C.c_int),
+        ("min_box_area", C.c_int), ("aspect_ratio_thresh", C.c_float), ("lambda_iou", C.c_float), ("lambda_mhd", C.c_float),
+        ("lambda_shape", C.c_float), ("use_dlo_boost", C.c_int), ("dlo_boost_coef", C.c_float), ("use_sb", C.c_int), ("use_vt", C.c_int),
     ]
 
 
@@ -77,6 +80,7 @@ SYMBOLS = {
     "mot_engine_stream_header": (_I, [_VP, _I, _VP]),
     "mot_engine_dump_list": (_I, [_VP, _I, _I, _VP, _I, C.POINTER(_I)]),
     "mot_engine_dump_deep_embs": (_I, [_VP, _I, _VP, _I, C.POINTER(_I)]),
+    "mot_engine_dump_boost": (_I, [_VP, _I, _VP, _I, C.POINTER(_I)]),
     "mot_engine_info": (_I, [_VP, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "mot_kf_initiate": (_I, [_I, _VP, _VP, _LL, _VP]),
     "mot_kf_predict": (_I, [_I, _VP, _VP, _LL, _F, _F, _VP]),

@@ -572,6 +572,14 @@ class Engine:
         check(load().mot_engine_dump_list(self._h, stream, which, buf.ctypes.data, max(n, 1), C.byref(k)))
         return buf[:k.value]
 
+    def dump_boost(self, stream: int) -> np.ndarray:
+        """BoostTrack engines: rows of [id, age, hit_streak, time_since_update, conf, cls, det_ind, 0, x 8, P 8x8]"""
+        n = max(int(self.header(stream)[0]), 1)
+        buf = np.zeros((n, 80), np.float32)
+        k = C.c_int()
+        check(load().mot_engine_dump_boost(self._h, stream, buf.ctypes.data, n, C.byref(k)))
+        return buf[:k.value]
+
     def dump_deep_embs(self, stream: int) -> np.ndarray:
         """DeepOC-SORT engines: the tracks' unit-length embeddings, in the row order of dump(stream)."""
         n = max(int(self.header(stream)[0]), 1)
@@ -861,6 +869,59 @@ class DeepOCSort:
         if not self._off and n:
             self._embs[0, 0, :n] = embs
         return self._step(n)
+
+
+class BoostTrack:
+    """motcpp::trackers::BoostTrackTracker with the reference's positional constructor
+    (include/motcpp/trackers/boosttrack.hpp:95-124).  Camera-motion compensation and ReID are image processing outside
+    the accelerated path: use_ecc must be False (or cmc_method not "ecc"), with_reid False; use_sb (a powf) is not built.
+    One stream; for many streams use Engine(TRACKER_BOOSTTRACK, ...)."""
+
+    def __init__(self, reid_weights="", use_half=False, use_gpu=False, det_thresh=0.6, max_age=60, max_obs=50, min_hits=3,
+                 iou_threshold=0.3, per_class=False, nr_classes=80, asso_func="iou", is_obb=False, use_ecc=False,
+                 min_box_area=10, aspect_ratio_thresh=1.6, cmc_method="ecc", lambda_iou=0.5, lambda_mhd=0.25, lambda_shape=0.25,
+                 use_dlo_boost=True, use_duo_boost=True, dlo_boost_coef=0.65, s_sim_corr=False, use_rich_s=False, use_sb=False,
+                 use_vt=False, with_reid=False, track_capacity=1536, max_dets=512, device=0):
+        if use_ecc and cmc_method == "ecc":
+            raise ValueError("camera-motion compensation is outside the accelerated hot path: pass use_ecc=False")
+        if with_reid:
+            raise ValueError("BoostTrack with ReID multiplies out every detection x track pair; only with_reid=False is built")
+        if use_sb:
+            raise ValueError("use_sb (std::pow in the confidence boost) is not built")
+        if per_class or is_obb:
+            raise ValueError("per_class / OBB tracking are outside the accelerated hot path")
+        self._engine = Engine(_lib.TRACKER_BOOSTTRACK, 1, track_capacity, max_dets, device, det_thresh=det_thresh, max_age=max_age,
+                              max_obs=max_obs, min_hits=min_hits, iou_threshold=iou_threshold, min_box_area=int(min_box_area),
+                              aspect_ratio_thresh=aspect_ratio_thresh, lambda_iou=lambda_iou, lambda_mhd=lambda_mhd,
+                              lambda_shape=lambda_shape, use_dlo_boost=int(bool(use_dlo_boost)), dlo_boost_coef=dlo_boost_coef,
+                              use_vt=int(bool(use_vt)))
+        self._max_dets = self._engine.cfg.max_dets
+        self._cap = self._engine.cfg.track_capacity
+        self._dets = np.zeros((1, 1, self._max_dets, 6), np.float32)
+        self._out = np.empty((1, 1, self._cap, 8), np.float32)
+        self._n_out = np.empty((1, 1), np.int32)
+
+    def reset(self):
+        self._engine.reset()
+
+    def update(self, dets, img, embs=None) -> np.ndarray:
+        dets = np.asarray(dets, np.float32)
+        if dets.ndim != 2:
+            dets = dets.reshape(0, 6) if dets.size == 0 else dets
+        # BaseTracker::check_inputs(dets, img) (src/tracker.cpp:108-125)
+        if dets.shape[0] > 0 and dets.shape[1] not in (6, 7):
+            raise ValueError("Detections must have 6 (AABB) or 7 (OBB) columns")
+        if _Image(img).empty():
+            raise ValueError("Image cannot be empty")
+        if dets.shape[0] > 0 and dets.shape[1] == 7:
+            raise ValueError("OBB detections are outside the accelerated hot path")
+        n = dets.shape[0]
+        if n > self._max_dets:
+            raise ValueError(f"{n} detections exceed max_dets={self._max_dets}")
+        self._dets[0, 0, :n] = dets[:, :6] if n else 0
+        self._engine.update(self._dets, np.array([[n]], np.int32), self._out, self._n_out)
+        self._engine.check()
+        return self._out[0, 0, :int(self._n_out[0, 0])].copy()
 
 
 class BotSort:

@@ -23,6 +23,7 @@
 #include "kernels_pack.cuh"
 #include "sort_kernel.cuh"
 #include "ocsort_kernel.cuh"
+#include "boosttrack_kernel.cuh"
 #include "botsort_kernel.cuh"
 #include "strongsort_kernel.cuh"
 
@@ -80,6 +81,7 @@ struct mot_engine {
     mot::SortLayout sort_layout;   // SORT slab layout (kind == SORT)
     mot::OcLayout oc_layout;       // OC-SORT slab layout (kind == OCSORT)
     mot::OcParams ocp;
+    mot::BoostParams boostp;       // BoostTrack (kind == BOOSTTRACK) lives in a SORT slab
     mot::DeepLayout deep_layout;   // DeepOC-SORT appearance state behind every OC-SORT slab (kind == DEEPOCSORT)
     mot::BotLayout bot_layout;     // BoT-SORT slab layout (kind == BOTSORT; feature dimension is a run-time size)
     mot::BotParams botp;
@@ -116,6 +118,8 @@ static int engine_reset_impl(mot_engine* e, int keep_ids) {
     const int grid = std::min(e->cfg.n_streams, 4096);
     if (e->cfg.kind == MOT_TRACKER_SORT)
         mot::sort_reset_kernel<<<grid, 256, 0, e->streams[0]>>>(e->d_state, e->sort_layout, e->cfg.n_streams, keep_ids);
+    else if (e->cfg.kind == MOT_TRACKER_BOOSTTRACK)      // BoostTrack::next_id_ restarts (boosttrack.cpp:272-277)
+        mot::sort_reset_kernel<<<grid, 256, 0, e->streams[0]>>>(e->d_state, e->sort_layout, e->cfg.n_streams, 0);
     else if (e->cfg.kind == MOT_TRACKER_OCSORT || e->cfg.kind == MOT_TRACKER_DEEPOCSORT)
         mot::ocsort_reset_kernel<<<grid, 256, 0, e->streams[0]>>>(e->d_state, e->oc_layout, e->stride, e->cfg.n_streams, keep_ids);
     else if (e->cfg.kind == MOT_TRACKER_BOTSORT)
@@ -158,6 +162,12 @@ static void engine_launch(mot_engine* e, int T, const float* dets, const int* nd
         a.T = T; a.S = e->cfg.n_streams; a.ld_dets = ld_dets; a.ld_out = ld_out; a.s_begin = s0; a.s_end = s1;
         a.p = e->botp;
         mot::bot_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
+    } else if (e->cfg.kind == MOT_TRACKER_BOOSTTRACK) {
+        mot::BoostArgs a{};
+        a.state = e->d_state; a.dets = dets; a.n_dets = nd; a.out = out; a.n_out = nout;
+        a.T = T; a.S = e->cfg.n_streams; a.ld_dets = ld_dets; a.ld_out = ld_out; a.s_begin = s0; a.s_end = s1;
+        a.p = e->boostp;
+        mot::boost_launch(e->shape, s1 - s0, e->smem_bytes, st, a);
     } else if (e->cfg.kind == MOT_TRACKER_SORT) {
         mot::SortArgs a{};
         a.state = e->d_state; a.dets = dets; a.n_dets = nd; a.out = out; a.n_out = nout;
@@ -257,6 +267,9 @@ int mot_engine_default_config(int kind, mot_engine_config* c) {
     // DeepOCSort (deepocsort.hpp:93-117)
     c->w_association_emb = 0.5f; c->alpha_fixed_emb = 0.95f; c->aw_param = 0.5f; c->embedding_off = 0; c->aw_off = 0;
     c->asso_func = 0; c->frame_width = 0; c->frame_height = 0;
+    // BoostTrackTracker (boosttrack.hpp:95-124)
+    c->min_box_area = 10; c->aspect_ratio_thresh = 1.6f; c->lambda_iou = 0.5f; c->lambda_mhd = 0.25f; c->lambda_shape = 0.25f;
+    c->use_dlo_boost = 1; c->dlo_boost_coef = 0.65f; c->use_sb = 0; c->use_vt = 0;
     switch (kind) {
         case MOT_TRACKER_SORT: c->max_age = 1; break;             // sort.hpp:70
         case MOT_TRACKER_BYTETRACK: break;
@@ -264,6 +277,7 @@ int mot_engine_default_config(int kind, mot_engine_config* c) {
         case MOT_TRACKER_BOTSORT: c->track_buffer = 30; break;
         case MOT_TRACKER_STRONGSORT: break;
         case MOT_TRACKER_DEEPOCSORT: break;
+        case MOT_TRACKER_BOOSTTRACK: c->det_thresh = 0.6f; c->max_age = 60; break;
         default: return fail(MOT_ERR_INVALID_ARGUMENT, "unknown tracker kind %d", kind);
     }
     return MOT_OK;
@@ -272,13 +286,15 @@ int mot_engine_default_config(int kind, mot_engine_config* c) {
 int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     if (!cfg || !out) return fail(MOT_ERR_INVALID_ARGUMENT, "null argument");
     *out = nullptr;
-    if (cfg->kind < MOT_TRACKER_SORT || cfg->kind > MOT_TRACKER_DEEPOCSORT)
+    if (cfg->kind < MOT_TRACKER_SORT || cfg->kind > MOT_TRACKER_BOOSTTRACK)
         return fail(MOT_ERR_INVALID_ARGUMENT, "unknown tracker kind %d", cfg->kind);
     if (cfg->kind == MOT_TRACKER_STRONGSORT && (cfg->nn_budget < 1 || cfg->nn_budget > 4096))
         return fail(MOT_ERR_UNSUPPORTED, "nn_budget %d is outside 1..4096 (gallery ring size; the reference's unlimited budget is not supported)", cfg->nn_budget);
     if ((cfg->kind == MOT_TRACKER_BOTSORT || cfg->kind == MOT_TRACKER_STRONGSORT) && (cfg->emb_dim < 0 || (cfg->emb_dim & 3)))
         return fail(MOT_ERR_INVALID_ARGUMENT, "emb_dim %d must be a non-negative multiple of 4", cfg->emb_dim);
     if (cfg->n_streams <= 0) return fail(MOT_ERR_INVALID_ARGUMENT, "n_streams must be positive");
+    if (cfg->kind == MOT_TRACKER_BOOSTTRACK && cfg->use_sb)
+        return fail(MOT_ERR_UNSUPPORTED, "BoostTrack's use_sb confidence boost (std::pow(iou, 1.5f)) is not built; use_dlo_boost / use_vt are");
     if (cfg->asso_func != 0) {
         if (cfg->asso_func != mot::kVarCentroid)
             return fail(MOT_ERR_UNSUPPORTED, "Invalid association mode: %d (engines take 0 \"iou\" or 6 \"centroid\"; the reference's hmiou / giou / diou / ciou are only defined for one-row box sets)", cfg->asso_func);
@@ -302,7 +318,8 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
         ~Guard() { if (*e) mot_engine_destroy(*e); cudaSetDevice(dev); }
     } guard{&e, prev_device};
     const bool is_deep = cfg->kind == MOT_TRACKER_DEEPOCSORT;
-    const bool is_sort = cfg->kind == MOT_TRACKER_SORT, is_oc = cfg->kind == MOT_TRACKER_OCSORT || is_deep;   // same kernel text and shapes
+    const bool is_boost = cfg->kind == MOT_TRACKER_BOOSTTRACK;
+    const bool is_sort = cfg->kind == MOT_TRACKER_SORT || is_boost /* same slab layout and shapes */, is_oc = cfg->kind == MOT_TRACKER_OCSORT || is_deep;   // same kernel text and shapes
     const bool is_bot = cfg->kind == MOT_TRACKER_BOTSORT, is_ss = cfg->kind == MOT_TRACKER_STRONGSORT;
     if (e->cfg.track_capacity <= 0) e->cfg.track_capacity = 1536;
     if (e->cfg.max_dets <= 0) e->cfg.max_dets = 512;
@@ -347,6 +364,11 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     e->sortp.iou_threshold = cfg->iou_threshold;
     e->sortp.max_age = cfg->max_age;
     e->sortp.min_hits = cfg->min_hits;
+    e->boostp.det_thresh = cfg->det_thresh; e->boostp.iou_threshold = cfg->iou_threshold;
+    e->boostp.aspect_ratio_thresh = cfg->aspect_ratio_thresh; e->boostp.lambda_mhd = cfg->lambda_mhd;
+    e->boostp.dlo_boost_coef = cfg->dlo_boost_coef; e->boostp.min_box_area = (float)cfg->min_box_area;
+    e->boostp.max_age = cfg->max_age; e->boostp.min_hits = cfg->min_hits; e->boostp.use_dlo_boost = cfg->use_dlo_boost;
+    e->boostp.use_vt = cfg->use_vt;
     e->ocp.det_thresh = cfg->det_thresh;
     e->ocp.iou_threshold = cfg->iou_threshold;                                   // asso_threshold_ (ocsort.cpp:195)
     e->ocp.min_conf = cfg->min_conf;
@@ -382,7 +404,7 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     e->ssp.n_init = cfg->n_init; e->ssp.budget = std::max(1, cfg->nn_budget); e->ssp.dim = cfg->emb_dim;
     e->stride = is_ss ? e->ss_layout.stride : is_sort ? e->sort_layout.stride : (is_oc ? e->oc_layout.stride + (is_deep ? e->deep_layout.bytes : 0) : (is_bot ? e->bot_layout.stride : e->layout.stride));
     e->threads = is_ss ? mot::kSsThreads : is_sort ? mot::kSortThreads : (is_oc ? mot::kOcThreads : (is_bot ? mot::kBotThreads : mot::bt_threads(e->shape, cfg->n_streams, sm_count())));
-    e->smem_bytes = is_ss ? mot::ss_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap) : is_sort ? mot::sort_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap)
+    e->smem_bytes = is_ss ? mot::ss_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap) : is_boost ? mot::boost_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap) : is_sort ? mot::sort_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap)
                   : is_oc   ? mot::oc_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap)
                   : is_bot  ? mot::bot_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap)
                             : mot::bt_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap);
@@ -393,7 +415,7 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
         return fail(MOT_ERR_INVALID_ARGUMENT, "track_capacity/max_dets need %zu B of shared memory per CTA (limit %d)",
                     need, max_optin);
     }
-    MOT_CUDA(is_ss ? mot::ss_prepare(e->shape, e->smem_bytes) : is_sort ? mot::sort_prepare(e->shape, e->smem_bytes)
+    MOT_CUDA(is_ss ? mot::ss_prepare(e->shape, e->smem_bytes) : is_boost ? mot::boost_prepare(e->shape, e->smem_bytes) : is_sort ? mot::sort_prepare(e->shape, e->smem_bytes)
                      : (is_oc ? (is_deep ? mot::deepoc_prepare(e->shape, e->smem_bytes)
                                         : (cfg->asso_func == mot::kVarCentroid ? mot::oc_centroid_prepare(e->shape, e->smem_bytes) : mot::oc_prepare(e->shape, e->smem_bytes)))
                               : (is_bot ? mot::bot_prepare(e->shape, e->smem_bytes) : mot::bt_prepare(e->shape, e->smem_bytes, e->threads))));
@@ -785,6 +807,38 @@ int mot_engine_dump_list(mot_engine* e, int s, int which, float* rows, int cap_r
         o[0] = (float)meta[slot]; o[1] = (float)(sflag[slot] & 0x0f); o[2] = (sflag[slot] & 0x10) ? 1.0f : 0.0f;
         o[3] = (float)meta[2 * L.cap + slot]; o[4] = (float)meta[3 * L.cap + slot]; o[5] = (float)meta[L.cap + slot];
         mot::kfb_expand(recs + (size_t)slot * mot::kBtRecFloats, o + 6);     // compact record -> [mean 8 | cov 8x8]
+    }
+    *n_rows = k;
+    return MOT_OK;
+}
+
+int mot_engine_dump_boost(mot_engine* e, int s, float* rows, int cap_rows, int* n_rows) {
+    if (!e || !rows || !n_rows || s < 0 || s >= e->cfg.n_streams) return fail(MOT_ERR_INVALID_ARGUMENT, "bad argument");
+    if (e->cfg.kind != MOT_TRACKER_BOOSTTRACK) return fail(MOT_ERR_UNSUPPORTED, "not a BoostTrack engine");
+    MOT_CUDA(cudaSetDevice(e->cfg.device));
+    MOT_CUDA(cudaDeviceSynchronize());
+    const mot::SortLayout& L = e->sort_layout;
+    std::vector<unsigned char> slab(L.off_gscratch);
+    MOT_CUDA(cudaMemcpy(slab.data(), e->d_state + (size_t)s * L.stride, slab.size(), cudaMemcpyDeviceToHost));
+    const int* hdr = (const int*)slab.data();
+    const unsigned short* list = (const unsigned short*)(slab.data() + L.off_lists);
+    const int* m = (const int*)(slab.data() + L.off_meta);
+    const float* recs = (const float*)(slab.data() + L.off_recs);
+    const int n = hdr[mot::kSHdrTracks], cap = L.cap;
+    int k = 0;
+    for (; k < n && k < cap_rows; ++k) {
+        const int slot = list[k];
+        float* o = rows + 80 * (size_t)k;
+        std::memset(o, 0, 80 * sizeof(float));
+        // meta arrays of the SORT slab: id, hits (= hit_streak here), tsu, age, cls, det_ind, conf
+        o[0] = (float)m[slot]; o[1] = (float)m[3 * cap + slot]; o[2] = (float)m[cap + slot]; o[3] = (float)m[2 * cap + slot];
+        o[4] = ((const float*)m)[6 * cap + slot]; o[5] = (float)m[4 * cap + slot]; o[6] = (float)m[5 * cap + slot];
+        const float* rec = recs + (size_t)slot * mot::kBoostRecFloats;
+        std::memcpy(o + 8, rec, 8 * sizeof(float));
+        for (int c = 0; c < 4; ++c) {
+            const float* P = rec + 8 + 4 * c;
+            o[16 + c * 8 + c] = P[0]; o[16 + c * 8 + c + 4] = P[1]; o[16 + (c + 4) * 8 + c] = P[2]; o[16 + (c + 4) * 8 + c + 4] = P[3];
+        }
     }
     *n_rows = k;
     return MOT_OK;

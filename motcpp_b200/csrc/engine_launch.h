@@ -5,7 +5,7 @@
 #include <cstddef>
 
 namespace mot {
-struct BtArgs; struct SortArgs; struct OcArgs; struct BotArgs; struct SsArgs;
+struct BtArgs; struct SortArgs; struct OcArgs; struct BotArgs; struct SsArgs; struct BoostArgs;
 // *_prepare: opt the kernel of `shape` into `smem` bytes of dynamic shared memory; *_launch: one CTA per stream
 // ByteTrack picks its CTA width from the stream count: 512 threads x 2 CTAs per SM, or one 1024-thread CTA per SM
 int bt_threads(int shape, int n_streams, int n_sms);
@@ -19,6 +19,8 @@ cudaError_t oc_centroid_prepare(int shape, size_t smem);
 void oc_centroid_launch(int shape, int grid, size_t smem, cudaStream_t st, const OcArgs& a);
 cudaError_t deepoc_prepare(int shape, size_t smem);
 void deepoc_launch(int shape, int grid, size_t smem, cudaStream_t st, const OcArgs& a);
+cudaError_t boost_prepare(int shape, size_t smem);
+void boost_launch(int shape, int grid, size_t smem, cudaStream_t st, const BoostArgs& a);
 cudaError_t bot_prepare(int shape, size_t smem);
 void bot_launch(int shape, int grid, size_t smem, cudaStream_t st, const BotArgs& a);
 cudaError_t ss_prepare(int shape, size_t smem);

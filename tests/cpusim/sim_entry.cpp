@@ -334,6 +334,74 @@ int sim_deepoc_dump(void* hv, int s, float* rows, float* embs, int cap_rows) {
 
 }  // extern "C"
 
+// ------------------------------------------------------------------ BoostTrack engine under the emulator
+#include "../../motcpp_b200/csrc/boosttrack_kernel.cuh"
+namespace {
+struct SimBoost {
+    mot::SortLayout L;
+    int S;
+    mot::BoostParams p;
+    std::vector<unsigned char> state;
+};
+}  // namespace
+
+extern "C" {
+
+void* sim_boost_create(int S, float det_thresh, int max_age, int min_hits, float iou_threshold, int min_box_area,
+                       float aspect_ratio_thresh, float lambda_mhd, int use_dlo_boost, float dlo_boost_coef, int use_vt) {
+    auto* h = new SimBoost();
+    h->L = mot::SortLayout::make(256, 64);
+    h->S = S;
+    h->p = mot::BoostParams{det_thresh, iou_threshold, aspect_ratio_thresh, lambda_mhd, dlo_boost_coef, (float)min_box_area,
+                            max_age, min_hits, use_dlo_boost, use_vt};
+    h->state.assign(h->L.stride * (size_t)S + 256, 0);
+    unsigned char* st = h->state.data();
+    const mot::SortLayout L = h->L;
+    cpusim::launch(dim3(S), dim3(64), 0, [=] { mot::sort_reset_kernel(st, L, S, 0); });
+    return h;
+}
+void sim_boost_destroy(void* hv) { delete (SimBoost*)hv; }
+int sim_boost_update(void* hv, const float* dets, const int* n_dets, int T, int ld_dets, float* out, int* n_out, int ld_out, int threads) {
+    auto* h = (SimBoost*)hv;
+    mot::BoostArgs a{};
+    a.state = h->state.data(); a.dets = dets; a.n_dets = n_dets; a.out = out; a.n_out = n_out;
+    a.T = T; a.S = h->S; a.ld_dets = ld_dets; a.ld_out = ld_out; a.s_begin = 0; a.s_end = h->S; a.p = h->p;
+    cpusim::launch(dim3(h->S), dim3(threads), mot::boost_smem_bytes(256, 64, 1024), [=] { mot::boosttrack_step_kernel<256, 64, 1024>(a); });
+    return 0;
+}
+void sim_boost_header(void* hv, int s, int* hdr16) {
+    auto* h = (SimBoost*)hv;
+    std::memcpy(hdr16, h->state.data() + (size_t)s * h->L.stride, sizeof(int) * 16);
+}
+// rows of [id, age, streak, tsu, conf, cls, det_ind, 0, x 8, P 64]
+int sim_boost_dump(void* hv, int s, float* rows, int cap_rows) {
+    auto* h = (SimBoost*)hv;
+    unsigned char* base = h->state.data() + (size_t)s * h->L.stride;
+    const mot::SortLayout& L = h->L;
+    const int* hdr = (const int*)base;
+    const unsigned short* list = (const unsigned short*)(base + L.off_lists);
+    const int* m = (const int*)(base + L.off_meta);
+    const float* recs = (const float*)(base + L.off_recs);
+    const int n = hdr[mot::kSHdrTracks], cap = L.cap;
+    int k = 0;
+    for (; k < n && k < cap_rows; ++k) {
+        const int slot = list[k];
+        float* o = rows + 80 * (size_t)k;
+        std::memset(o, 0, 80 * sizeof(float));
+        o[0] = (float)m[slot]; o[1] = (float)m[3 * cap + slot]; o[2] = (float)m[cap + slot]; o[3] = (float)m[2 * cap + slot];
+        o[4] = ((const float*)m)[6 * cap + slot]; o[5] = (float)m[4 * cap + slot]; o[6] = (float)m[5 * cap + slot];
+        const float* rec = recs + (size_t)slot * mot::kBoostRecFloats;
+        std::memcpy(o + 8, rec, 8 * sizeof(float));
+        for (int c = 0; c < 4; ++c) {
+            const float* P = rec + 8 + 4 * c;
+            o[16 + c * 8 + c] = P[0]; o[16 + c * 8 + c + 4] = P[1]; o[16 + (c + 4) * 8 + c] = P[2]; o[16 + (c + 4) * 8 + c + 4] = P[3];
+        }
+    }
+    return k;
+}
+
+}  // extern "C"
+
 // ------------------------------------------------------------------ BoT-SORT engine under the emulator
 #include "../../motcpp_b200/csrc/botsort_kernel.cuh"
 #include "../../motcpp_b200/csrc/strongsort_kernel.cuh"

@@ -69,6 +69,14 @@ def lib():
         S.sim_deepoc_dump.argtypes = [C.c_void_p, C.c_int, f32p, C.c_void_p, C.c_int]
         S.sim_deepoc_dump.restype = C.c_int
         S.sim_deepoc_destroy.argtypes = [C.c_void_p]
+        S.sim_boost_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float, C.c_int,
+                                       C.c_float, C.c_int]
+        S.sim_boost_create.restype = C.c_void_p
+        S.sim_boost_update.argtypes = [C.c_void_p, f32p, i32p, C.c_int, C.c_int, f32p, i32p, C.c_int, C.c_int]
+        S.sim_boost_header.argtypes = [C.c_void_p, C.c_int, i32p]
+        S.sim_boost_dump.argtypes = [C.c_void_p, C.c_int, f32p, C.c_int]
+        S.sim_boost_dump.restype = C.c_int
+        S.sim_boost_destroy.argtypes = [C.c_void_p]
         S.sim_bot_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float,
                                      C.c_float, C.c_int, C.c_int, C.c_int]
         S.sim_bot_create.restype = C.c_void_p
@@ -238,6 +246,37 @@ class SimDeepOCSort:
         emb = np.zeros((self.cap, max(self.dim, 1)), np.float32)
         k = lib().sim_deepoc_dump(self.h, s, buf, emb.ctypes.data_as(C.c_void_p), self.cap)
         return buf[:k], emb[:k, :self.dim]
+
+
+class SimBoostTrack:
+    def __init__(self, n_streams=1, det_thresh=0.6, max_age=60, min_hits=3, iou_threshold=0.3, min_box_area=10,
+                 aspect_ratio_thresh=1.6, lambda_mhd=0.25, use_dlo_boost=True, dlo_boost_coef=0.65, use_vt=False, **_ignored):
+        self.S, self.cap = n_streams, 256
+        self.h = lib().sim_boost_create(n_streams, det_thresh, max_age, min_hits, iou_threshold, int(min_box_area),
+                                        aspect_ratio_thresh, lambda_mhd, int(use_dlo_boost), dlo_boost_coef, int(use_vt))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().sim_boost_destroy(self.h)
+            self.h = None
+
+    def update(self, dets, n_dets, threads=128):
+        dets = np.ascontiguousarray(dets, np.float32)
+        T, S, ld, _ = dets.shape
+        n_dets = np.ascontiguousarray(n_dets, np.int32).reshape(T, S)
+        out = np.zeros((T, S, self.cap, 8), np.float32)
+        n_out = np.zeros((T, S), np.int32)
+        lib().sim_boost_update(self.h, dets, n_dets, T, ld, out, n_out, self.cap, threads)
+        return out, n_out
+
+    def header(self, s=0):
+        h = np.zeros(16, np.int32)
+        lib().sim_boost_header(self.h, s, h)
+        return h
+
+    def dump(self, s=0):
+        buf = np.zeros((self.cap, 80), np.float32)
+        return buf[:lib().sim_boost_dump(self.h, s, buf, self.cap)]
 
 
 class SimBotSort:
