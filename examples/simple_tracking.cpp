@@ -17,6 +17,9 @@ int main() {
         motcpp_b200::DeepOCSort deepocsort("", false, false, 0.3f, 30, 50, 3, 0.3f, false, 80, "iou", false, 3, 0.2f, 0.5f, 0.95f,
                                            0.5f, false, /*cmc_off=*/true, false, 0.01f, 0.0001f, /*emb_dim=*/4,
                                            /*track_capacity=*/256, /*max_dets=*/64);
+        motcpp_b200::BoostTrackTracker boosttrack("", false, false, 0.6f, 60, 50, 3, 0.3f, false, 80, "iou", false, /*use_ecc=*/false,
+                                                  10, 1.6f, "ecc", 0.5f, 0.25f, 0.25f, true, true, 0.65f, false, false, false, false,
+                                                  /*with_reid=*/false, /*track_capacity=*/256, /*max_dets=*/64);
         cv::Mat img(480, 640);
         Eigen::MatrixXf dets(2, 6);
         const float rows[2][6] = {{100, 100, 200, 200, 0.9f, 0}, {300, 300, 400, 420, 0.8f, 0}};
@@ -30,6 +33,7 @@ int main() {
                         (long)ocsort.update(dets, img).rows(), (long)botsort.update(dets, img, embs).rows());
             std::printf("frame %d strongsort rows %ld\n", frame, (long)strongsort.update(dets, img, embs).rows());
             std::printf("frame %d deepocsort rows %ld\n", frame, (long)deepocsort.update(dets, img, embs).rows());
+            std::printf("frame %d boosttrack rows %ld\n", frame, (long)boosttrack.update(dets, img).rows());
             const Eigen::MatrixXf tracks = tracker.update(dets, img);
             for (long i = 0; i < tracks.rows(); ++i)
                 std::printf("frame %d id %d box %.1f %.1f %.1f %.1f conf %.2f\n", frame, (int)tracks(i, 4), tracks(i, 0),

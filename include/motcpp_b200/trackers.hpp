@@ -1,5 +1,6 @@
 // trackers.hpp - C++17 binding of the C ABI (include/motb200.h) with motcpp's own class surface:
-//   motcpp_b200::{Sort, ByteTrack, OCSort, BotSort}(<the reference's positional ctor arguments>)
+//   motcpp_b200::{Sort, ByteTrack, OCSort, BotSort, StrongSORT, DeepOCSort, BoostTrackTracker}(<the reference's positional
+//   ctor arguments>)
 //       .update(dets, img[, embs]) / .reset()
 // Constructor arguments, defaults, return layout and exceptions follow include/motcpp/trackers/sort.hpp:69-77,
 // bytetrack.hpp:97-110, ocsort.hpp:88-102, botsort.hpp:108-134, include/motcpp/tracker.hpp:47-74 and
@@ -324,6 +325,49 @@ private:
         c.iou_threshold = iou_threshold; c.delta_t = delta_t; c.inertia = inertia; c.w_association_emb = w_assoc;
         c.alpha_fixed_emb = alpha_fixed; c.aw_param = aw_param; c.embedding_off = embedding_off ? 1 : 0;
         c.aw_off = aw_off ? 1 : 0; c.q_xy_scaling = q_xy; c.q_s_scaling = q_s; c.emb_dim = embedding_off ? 0 : emb_dim;
+        return c;
+    }
+};
+
+// motcpp::trackers::BoostTrackTracker (include/motcpp/trackers/boosttrack.hpp:95-124).  ECC camera-motion compensation and
+// ReID are image processing outside the association hot path: use_ecc must be false (the reference's default is true; its
+// ECC yields the identity warp on a static image) and with_reid false; use_sb (a std::pow in the confidence boost,
+// boosttrack.cpp:395-412) is not built.  use_duo_boost, s_sim_corr and use_rich_s are accepted and have no effect, as in
+// the reference (duo_confidence_boost returns its input, boosttrack.cpp:428-432; the other two are never read).
+class BoostTrackTracker : public BaseTracker {
+public:
+    BoostTrackTracker(const std::string& reid_weights = "", bool use_half = false, bool use_gpu = false, float det_thresh = 0.6f,
+                      int max_age = 60, int max_obs = 50, int min_hits = 3, float iou_threshold = 0.3f, bool per_class = false,
+                      int nr_classes = 80, const std::string& asso_func = "iou", bool is_obb = false, bool use_ecc = false,
+                      int min_box_area = 10, float aspect_ratio_thresh = 1.6f, const std::string& cmc_method = "ecc",
+                      float lambda_iou = 0.5f, float lambda_mhd = 0.25f, float lambda_shape = 0.25f, bool use_dlo_boost = true,
+                      bool use_duo_boost = true, float dlo_boost_coef = 0.65f, bool s_sim_corr = false, bool use_rich_s = false,
+                      bool use_sb = false, bool use_vt = false, bool with_reid = false, int track_capacity = 0,
+                      int max_dets = 0, int device = 0)
+        : BaseTracker(make(reid_weights, use_half, use_gpu, det_thresh, max_age, max_obs, min_hits, iou_threshold, per_class,
+                           nr_classes, asso_func, is_obb, use_ecc, min_box_area, aspect_ratio_thresh, cmc_method, lambda_iou,
+                           lambda_mhd, lambda_shape, use_dlo_boost, use_duo_boost, dlo_boost_coef, s_sim_corr, use_rich_s, use_sb,
+                           use_vt, with_reid, track_capacity, max_dets, device)) {}
+
+private:
+    static mot_engine_config make(const std::string&, bool, bool, float det_thresh, int max_age, int max_obs, int min_hits,
+                                  float iou_threshold, bool per_class, int, const std::string& asso_func, bool is_obb,
+                                  bool use_ecc, int min_box_area, float aspect_ratio_thresh, const std::string& cmc_method,
+                                  float lambda_iou, float lambda_mhd, float lambda_shape, bool use_dlo_boost, bool,
+                                  float dlo_boost_coef, bool, bool, bool use_sb, bool use_vt, bool with_reid,
+                                  int track_capacity, int max_dets, int device) {
+        only_iou_aabb(asso_func, per_class, is_obb);
+        if (use_ecc && cmc_method == "ecc")
+            throw std::invalid_argument("camera-motion compensation is outside the accelerated hot path (use_ecc must be false)");
+        if (with_reid) throw std::invalid_argument("BoostTrack with ReID is outside the accelerated hot path (with_reid must be false)");
+        if (use_sb) throw std::invalid_argument("use_sb (std::pow in the confidence boost) is not built");
+        mot_engine_config c;
+        throw_on(mot_engine_default_config(MOT_TRACKER_BOOSTTRACK, &c));
+        c.n_streams = 1; c.track_capacity = track_capacity; c.max_dets = max_dets; c.device = device;
+        c.det_thresh = det_thresh; c.max_age = max_age; c.max_obs = max_obs; c.min_hits = min_hits;
+        c.iou_threshold = iou_threshold; c.min_box_area = min_box_area; c.aspect_ratio_thresh = aspect_ratio_thresh;
+        c.lambda_iou = lambda_iou; c.lambda_mhd = lambda_mhd; c.lambda_shape = lambda_shape;
+        c.use_dlo_boost = use_dlo_boost ? 1 : 0; c.dlo_boost_coef = dlo_boost_coef; c.use_sb = 0; c.use_vt = use_vt ? 1 : 0;
         return c;
     }
 };

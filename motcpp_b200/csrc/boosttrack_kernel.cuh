@@ -22,7 +22,10 @@
 
 namespace mot {
 
-constexpr int kBoostThreads = kSortThreads;
+#ifndef MOT_BOOST_THREADS
+#define MOT_BOOST_THREADS 512
+#endif
+constexpr int kBoostThreads = MOT_BOOST_THREADS;
 constexpr int kBoostRecFloats = kSortRecFloats;      // 24 used: x 8 | (pcc, pcv, pvc, pvv) x 4
 
 struct BoostParams {
@@ -97,6 +100,7 @@ __device__ __forceinline__ float4 boost_bbox_to_z(float4 b) {
 struct BoostCost {
     static constexpr bool kWarpPerRow = false;
     static constexpr bool kGrid = true;
+    static constexpr bool kBigList = true;
     const float4* det_box;
     const unsigned short* row_map;    // row -> detection index
     const float4* trk_box;
@@ -104,6 +108,9 @@ struct BoostCost {
     const float4* trk_inv;
     float lambda_mhd;
     bool prune;                       // a disjoint pair costs 1 - lambda_mhd * mh_sim >= 1 - lambda_mhd > thresh
+    float big_w, big_h;               // track boxes beyond twice the largest detection: listed apart from the grid
+    float4 roi;                       // hull of the frame's detections: tracks that miss it cannot be looked at by any row
+    float iou_floor;                  // cost <= thresh needs IoU >= 1 - thresh - lambda_mhd (mh_sim <= 1); 0: unknown
     struct Row { float4 b; float4 z; float area; };
     __device__ __forceinline__ Row row(int i) const {
         Row r;
@@ -159,45 +166,92 @@ __device__ __forceinline__ void boost_frame(const BoostArgs& a, const SortStream
     for (int k = tid; k < n_trk; k += nt) {
         const int slot = st.list[k];
         float* rec = st.recs + (size_t)slot * kBoostRecFloats;
-        float x[8];
+        // the record is 256-byte aligned: six 16-byte loads, five 16-byte stores (the velocities do not change)
+        float4* rec4 = reinterpret_cast<float4*>(rec);
+        const float4 xp = rec4[0], xv = rec4[1];
+        float x[8] = {xp.x, xp.y, xp.z, xp.w, xv.x, xv.y, xv.z, xv.w};
+        float p00[4];                                                                // predicted position variances
+        float4 blk[4];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) x[c] = rec[c];
+        for (int c = 0; c < 4; ++c) blk[c] = rec4[2 + c];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             x[c] = xadd(x[c], x[c + 4]);                                             // x = F x
-            float* P = rec + 8 + 4 * c;
-            const float pcc = P[0], pcv = P[1], pvc = P[2], pvv = P[3];
+            const float pcc = blk[c].x, pcv = blk[c].y, pvc = blk[c].z, pvv = blk[c].w;
             const float fcc = xadd(pcc, pvc), fcv = xadd(pcv, pvv);                   // F P
-            P[0] = xadd(xadd(fcc, fcv), 10.0f);                                      // (F P) F^T + Q
-            P[1] = xadd(fcv, 0.0f);
-            P[2] = xadd(pvc, pvv);
-            P[3] = xadd(pvv, 0.01f);
-            rec[c] = x[c];
+            p00[c] = xadd(xadd(fcc, fcv), 10.0f);                                    // (F P) F^T + Q
+            rec4[2 + c] = make_float4(p00[c], xadd(fcv, 0.0f), xadd(pvc, pvv), xadd(pvv, 0.01f));
         }
+        rec4[0] = make_float4(x[0], x[1], x[2], x[3]);
         st.age[slot] += 1;
         if (st.tsu[slot] > 0) st.hits[slot] = 0;                                     // hit_streak (:160-162)
         st.tsu[slot] += 1;
         sm.trk_box[k] = boost_state_box(x[0], x[1], x[2], x[3]);
         sm.trk_mean[k] = make_float4(x[0], x[1], x[2], x[3]);
-        sm.trk_inv[k] = make_float4(xdiv(1.0f, rec[8]), xdiv(1.0f, rec[12]), xdiv(1.0f, rec[16]), xdiv(1.0f, rec[20]));
+        sm.trk_inv[k] = make_float4(xdiv(1.0f, p00[0]), xdiv(1.0f, p00[1]), xdiv(1.0f, p00[2]), xdiv(1.0f, p00[3]));
         sm.tsu1[k] = (unsigned char)min(st.tsu[slot] - 1, 255);
     }
     __syncthreads();
 
+    // A coasting track's height / ratio velocities can inflate its box without bound (nothing clamps them in the reference);
+    // the grid keeps such boxes - wider or taller than twice the largest detection of the frame - in its overflow list.
+    float big_w = 0.0f, big_h = 0.0f;
+    float4 roi = make_float4(3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f);                  // hull of the detections
+    {
+        for (int j = tid; j < n_det; j += nt) {
+            const float4 b = sm.det_box[j];
+            if (!box_finite(b)) continue;
+            big_w = fmaxf(big_w, b.z - b.x); big_h = fmaxf(big_h, b.w - b.y);
+            roi.x = fminf(roi.x, b.x); roi.y = fminf(roi.y, b.y); roi.z = fmaxf(roi.z, b.z); roi.w = fmaxf(roi.w, b.w);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            big_w = fmaxf(big_w, __shfl_xor_sync(kFullMask, big_w, o));
+            big_h = fmaxf(big_h, __shfl_xor_sync(kFullMask, big_h, o));
+            roi.x = fminf(roi.x, __shfl_xor_sync(kFullMask, roi.x, o));
+            roi.y = fminf(roi.y, __shfl_xor_sync(kFullMask, roi.y, o));
+            roi.z = fmaxf(roi.z, __shfl_xor_sync(kFullMask, roi.z, o));
+            roi.w = fmaxf(roi.w, __shfl_xor_sync(kFullMask, roi.w, o));
+        }
+        float* red = sm.lap.grid.red;
+        if ((tid & 31) == 0) {
+            const int w = tid >> 5;
+            red[w] = big_w; red[32 + w] = big_h; red[64 + w] = roi.x; red[96 + w] = roi.y; red[128 + w] = roi.z; red[160 + w] = roi.w;
+        }
+        __syncthreads();
+        for (int w = 0; w < (nt >> 5); ++w) {
+            big_w = fmaxf(big_w, red[w]); big_h = fmaxf(big_h, red[32 + w]);
+            roi.x = fminf(roi.x, red[64 + w]); roi.y = fminf(roi.y, red[96 + w]);
+            roi.z = fmaxf(roi.z, red[128 + w]); roi.w = fmaxf(roi.w, red[160 + w]);
+        }
+        big_w *= 2.0f; big_h *= 2.0f;
+        __syncthreads();                                                             // red is reused by grid_build
+    }
+
     // ---- C. detection-confidence boost against the predicted tracks (:361-426), then the det_thresh filter (:532-538)
     if (a.p.use_dlo_boost && n_det > 0 && n_trk > 0) {
-        grid_build(sm.lap.grid, n_trk, sm.bs, [&](int j) { return sm.trk_box[j]; });
+        grid_build<true>(sm.lap.grid, n_trk, sm.bs, [&](int j) { return sm.trk_box[j]; }, big_w, big_h, roi);
         const float dth_eps = xadd(a.p.det_thresh, 1e-5f);
         for (int i = tid; i < n_det; i += nt) {
             const float4 b = sm.det_box[i];
             const float area = box_area(b);
+            // Only an IoU that can change the outcome has to be found: the basic rule raises conf to mx * coef, i.e. needs
+            // mx > conf / coef; the use_vt rule needs one IoU > max(0.95 - (tsu - 1), 0.8) >= 0.8 and only acts below
+            // det_thresh.  t sits a relative 1e-4 under that bound; pairs the tighter window skips have IoU <= t.
+            const float c0 = sm.det_conf[i];
+            float t = 0.0f;
+            if (!a.p.use_vt) { if (c0 > 0.0f && a.p.dlo_boost_coef > 0.0f) t = c0 / a.p.dlo_boost_coef * (1.0f - 1e-4f) - 1e-6f; }
+            else t = (c0 < dth_eps) ? 0.79f : 2.0f;
             float mx = 0.0f;                       // S >= 0 and at least one track exists: the row maximum over ALL tracks
             bool boost = false;
-            grid_query(sm.lap.grid, b, [&](int j) { return sm.trk_box[j]; }, [&](int j, float4 t) {
-                const float v = iou_pair(b, area, t);
+            auto see = [&](int j, float4 tb) {
+                const float v = iou_pair(b, area, tb);
                 if (mx < v) mx = v;
                 if (v > fmaxf(xsub(0.95f, (float)sm.tsu1[j]), 0.8f)) boost = true;
-            });
+            };
+            if (t >= 1.0f) {}                      // no IoU can matter
+            else if (t > 0.01f) grid_query_iou_above<true>(sm.lap.grid, b, t, [&](int j) { return sm.trk_box[j]; }, see);
+            else grid_query<true>(sm.lap.grid, b, [&](int j) { return sm.trk_box[j]; }, see);
             const float c = sm.det_conf[i];
             if (!a.p.use_vt) {
                 const float bc = xmul(mx, a.p.dlo_boost_coef);
@@ -216,7 +270,8 @@ __device__ __forceinline__ void boost_frame(const BoostArgs& a, const SortStream
     {
         const float thresh = a.p.iou_threshold;
         const bool prune = a.p.lambda_mhd >= 0.0f && xsub(1.0f, a.p.lambda_mhd) > thresh * 1.0001f + 1e-6f;
-        BoostCost cost{sm.det_box, sm.valid, sm.trk_box, sm.trk_mean, sm.trk_inv, a.p.lambda_mhd, prune};
+        BoostCost cost{sm.det_box, sm.valid, sm.trk_box, sm.trk_mean, sm.trk_inv, a.p.lambda_mhd, prune, big_w, big_h, roi,
+                       prune ? 1.0f - (thresh + a.p.lambda_mhd) * 1.001f - 1e-5f : 0.0f};
         block_lap(sm.lap, m, n_trk, DMAX, CAP, thresh, cost);
     }
     const int n_match = block_compact(m, 0, sm.bs, [&](int r) { return sm.lap.row2col[r] >= 0; },
@@ -228,26 +283,30 @@ __device__ __forceinline__ void boost_frame(const BoostArgs& a, const SortStream
         const int r = sm.sel2[q];
         const int det = sm.valid[r];
         const int slot = st.list[sm.lap.row2col[r]];
-        float* rec = st.recs + (size_t)slot * kBoostRecFloats;
+        float4* rec4 = reinterpret_cast<float4*>(st.recs + (size_t)slot * kBoostRecFloats);
         const float4 zz = boost_bbox_to_z(sm.det_box[det]);
         const float z[4] = {zz.x, zz.y, zz.z, zz.w};
         const float R[4] = {1.0f, 1.0f, 10.0f, 0.01f};
+        const float4 xp = rec4[0], xv = rec4[1];
+        float x[8] = {xp.x, xp.y, xp.z, xp.w, xv.x, xv.y, xv.z, xv.w};
+        float4 blk[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) blk[c] = rec4[2 + c];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            float* P = rec + 8 + 4 * c;
-            const float pcc = P[0], pcv = P[1], pvc = P[2], pvv = P[3];
+            const float pcc = blk[c].x, pcv = blk[c].y, pvc = blk[c].z, pvv = blk[c].w;
             const float S = xadd(pcc, R[c]);
             const float Sinv = xdiv(1.0f, S);                                        // LU inverse of the diagonal S
             const float kc = xmul(pcc, Sinv), kv = xmul(pvc, Sinv);                   // K = P H^T S^-1
-            const float innov = xsub(z[c], rec[c]);
-            rec[c] = xadd(rec[c], xmul(kc, innov));
-            rec[c + 4] = xadd(rec[c + 4], xmul(kv, innov));
+            const float innov = xsub(z[c], x[c]);
+            x[c] = xadd(x[c], xmul(kc, innov));
+            x[c + 4] = xadd(x[c + 4], xmul(kv, innov));
             const float kcs = xmul(kc, S), kvs = xmul(kv, S);                         // P - (K S) K^T
-            P[0] = xsub(pcc, xmul(kcs, kc));
-            P[1] = xsub(pcv, xmul(kcs, kv));
-            P[2] = xsub(pvc, xmul(kvs, kc));
-            P[3] = xsub(pvv, xmul(kvs, kv));
+            rec4[2 + c] = make_float4(xsub(pcc, xmul(kcs, kc)), xsub(pcv, xmul(kcs, kv)), xsub(pvc, xmul(kvs, kc)),
+                                      xsub(pvv, xmul(kvs, kv)));
         }
+        rec4[0] = make_float4(x[0], x[1], x[2], x[3]);
+        rec4[1] = make_float4(x[4], x[5], x[6], x[7]);
         st.tsu[slot] = 0;
         st.hits[slot] += 1;
         st.conf[slot] = sm.det_conf[det];

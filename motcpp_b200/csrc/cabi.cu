@@ -403,7 +403,7 @@ int mot_engine_create(const mot_engine_config* cfg, mot_engine** out) {
     e->ssp.mc_lambda = cfg->mc_lambda; e->ssp.ema_alpha = cfg->ema_alpha; e->ssp.max_age = cfg->max_age;
     e->ssp.n_init = cfg->n_init; e->ssp.budget = std::max(1, cfg->nn_budget); e->ssp.dim = cfg->emb_dim;
     e->stride = is_ss ? e->ss_layout.stride : is_sort ? e->sort_layout.stride : (is_oc ? e->oc_layout.stride + (is_deep ? e->deep_layout.bytes : 0) : (is_bot ? e->bot_layout.stride : e->layout.stride));
-    e->threads = is_ss ? mot::kSsThreads : is_sort ? mot::kSortThreads : (is_oc ? mot::kOcThreads : (is_bot ? mot::kBotThreads : mot::bt_threads(e->shape, cfg->n_streams, sm_count())));
+    e->threads = is_ss ? mot::kSsThreads : is_boost ? mot::kBoostThreads : is_sort ? mot::kSortThreads : (is_oc ? mot::kOcThreads : (is_bot ? mot::kBotThreads : mot::bt_threads(e->shape, cfg->n_streams, sm_count())));
     e->smem_bytes = is_ss ? mot::ss_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap) : is_boost ? mot::boost_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap) : is_sort ? mot::sort_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap)
                   : is_oc   ? mot::oc_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap)
                   : is_bot  ? mot::bot_smem_bytes(e->layout.cap, e->layout.d_max, e->e_cap)

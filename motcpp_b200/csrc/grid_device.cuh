@@ -7,6 +7,11 @@
 // box scans the cells that can hold the corner of a box overlapping it (its own extent dilated by
 // the largest column box), so every overlapping pair is visited exactly once and the results are
 // identical to the dense evaluation.
+// Outliers: one runaway column box (a coasting Kalman track whose height grew for 30 frames) would dilate EVERY row's
+// window.  Callers that know what a sane box is (the detections' own extent) build and query with kBig = true and pass big_w / big_h: column boxes beyond
+// them are kept out of the cells and of max_w / max_h, in a short list every query walks in full (stored from the end of
+// items[]); column boxes that miss `roi`, the hull of all row boxes, are dropped (a track that coasted off the canvas
+// would otherwise stretch the cells).  Which pairs are visited is unchanged - only where they are found.
 #pragma once
 #include "block_utils.cuh"
 
@@ -20,8 +25,9 @@ struct BoxGrid {
     int* cell;                 // [kGridCells + 1] start offset of every cell in items[] (exclusive scan)
     int* cursor;               // [kGridCells] build-time fill cursors
     unsigned short* items;     // [cap] column indices grouped by cell (one entry per finite box)
-    float* red;                // [6 * 32] block-reduction scratch
+    float* red;                // [6 * 32] block-reduction scratch, then one int: number of listed big boxes
     int cap;
+    int n_big;                 // big boxes: items[cap - 1], items[cap - 2], ...
     float x0, y0, sx, sy;      // cell = clamp((corner - origin) * scale)
     float max_w, max_h;        // largest column box
 
@@ -35,14 +41,14 @@ struct BoxGrid {
 
 MOT_HD constexpr size_t grid_smem_bytes(int cap) {
     return ((sizeof(int) * (kGridCells + 1) + 15) & ~(size_t)15) + sizeof(int) * kGridCells +
-           ((sizeof(unsigned short) * (size_t)cap + 15) & ~(size_t)15) + sizeof(float) * 6 * 32;
+           ((sizeof(unsigned short) * (size_t)cap + 15) & ~(size_t)15) + sizeof(float) * (6 * 32 + 4);
 }
 
 __device__ __forceinline__ unsigned char* grid_carve(unsigned char* p, int cap, BoxGrid& g) {
     g.cell = (int*)p;               p += (sizeof(int) * (kGridCells + 1) + 15) & ~(size_t)15;
     g.cursor = (int*)p;             p += sizeof(int) * kGridCells;
     g.items = (unsigned short*)p;   p += (sizeof(unsigned short) * (size_t)cap + 15) & ~(size_t)15;
-    g.red = (float*)p;              p += sizeof(float) * 6 * 32;
+    g.red = (float*)p;              p += sizeof(float) * (6 * 32 + 4);
     g.cap = cap;
     return p;
 }
@@ -54,13 +60,18 @@ __device__ __forceinline__ bool box_finite(float4 b) {
 
 // Build the grid over boxes box_of(0..n), n <= g.cap.  All threads of the block must call.
 // Non-finite boxes are left out (their IoU is NaN: never a candidate).
-template <class BoxOf>
-__device__ __forceinline__ void grid_build(BoxGrid& g, int n, BlockScratch* bs, BoxOf box_of) {
+__device__ __forceinline__ bool box_big(float4 b, float big_w, float big_h) { return (b.z - b.x > big_w) || (b.w - b.y > big_h); }
+// no row box inside `roi` can have an interior intersection with b (the same comparisons grid_query makes, on the hull)
+__device__ __forceinline__ bool box_outside(float4 b, float4 roi) { return !(fminf(roi.z, b.z) > fmaxf(roi.x, b.x)) || !(fminf(roi.w, b.w) > fmaxf(roi.y, b.y)); }
+
+template <bool kBig = false, class BoxOf>
+__device__ __forceinline__ void grid_build(BoxGrid& g, int n, BlockScratch* bs, BoxOf box_of, float big_w = 3.0e38f,
+                                           float big_h = 3.0e38f, float4 roi = make_float4(-3.0e38f, -3.0e38f, 3.0e38f, 3.0e38f)) {
     const int tid = (int)threadIdx.x, nt = (int)blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     float lo_x = 3.0e38f, lo_y = 3.0e38f, hi_x = -3.0e38f, hi_y = -3.0e38f, mw = 0.0f, mh = 0.0f;
     for (int j = tid; j < n; j += nt) {
         const float4 b = box_of(j);
-        if (!box_finite(b)) continue;
+        if (!box_finite(b) || (kBig && (box_big(b, big_w, big_h) || box_outside(b, roi)))) continue;
         lo_x = fminf(lo_x, b.x); lo_y = fminf(lo_y, b.y);
         hi_x = fmaxf(hi_x, b.x); hi_y = fmaxf(hi_y, b.y);
         mw = fmaxf(mw, b.z - b.x); mh = fmaxf(mh, b.w - b.y);
@@ -81,6 +92,8 @@ __device__ __forceinline__ void grid_build(BoxGrid& g, int n, BlockScratch* bs, 
     }
     for (int c = tid; c <= kGridCells; c += nt) g.cell[c] = 0;
     for (int c = tid; c < kGridCells; c += nt) g.cursor[c] = 0;
+    int* big_count = reinterpret_cast<int*>(g.red + 6 * 32);
+    if (tid == 0) *big_count = 0;
     __syncthreads();
     for (int w = 0; w < nwarps; ++w) {
         lo_x = fminf(lo_x, g.red[w]); lo_y = fminf(lo_y, g.red[32 + w]);
@@ -95,22 +108,25 @@ __device__ __forceinline__ void grid_build(BoxGrid& g, int n, BlockScratch* bs, 
     g.max_w = mw; g.max_h = mh;
     for (int j = tid; j < n; j += nt) {
         const float4 b = box_of(j);
-        if (box_finite(b)) atomicAdd(&g.cell[g.cy(b.y) * kGridX + g.cx(b.x)], 1);
+        if (!box_finite(b) || (kBig && box_outside(b, roi))) continue;
+        if (kBig && box_big(b, big_w, big_h)) g.items[g.cap - 1 - atomicAdd(big_count, 1)] = (unsigned short)j;   // n <= cap: never meets the cell items
+        else atomicAdd(&g.cell[g.cy(b.y) * kGridX + g.cx(b.x)], 1);
     }
     block_exclusive_scan(g.cell, kGridCells, bs, true);
     for (int j = tid; j < n; j += nt) {
         const float4 b = box_of(j);
-        if (!box_finite(b)) continue;
+        if (!box_finite(b) || (kBig && (box_big(b, big_w, big_h) || box_outside(b, roi)))) continue;
         const int c = g.cy(b.y) * kGridX + g.cx(b.x);
         g.items[g.cell[c] + atomicAdd(&g.cursor[c], 1)] = (unsigned short)j;
     }
     __syncthreads();
+    g.n_big = kBig ? *big_count : 0;
 }
 
 // Visit every column j whose box has a non-empty interior intersection with row box `a`, once.
 // A column box b can only overlap a if  a.x1 - max_w < b.x1 < a.x2  (and likewise in y); the scan
 // range is widened by a relative 1e-6 so fp32 rounding in the widths can never drop a pair.
-template <class BoxOf, class Visit>
+template <bool kBig = false, class BoxOf, class Visit>
 __device__ __forceinline__ void grid_query(const BoxGrid& g, float4 a, BoxOf box_of, Visit visit) {
     const float mx = g.max_w + (fabsf(a.x) + g.max_w) * 1e-6f, my = g.max_h + (fabsf(a.y) + g.max_h) * 1e-6f;
     const int cx0 = g.cx(a.x - mx), cx1 = g.cx(a.z), cy0 = g.cy(a.y - my), cy1 = g.cy(a.w);
@@ -121,6 +137,10 @@ __device__ __forceinline__ void grid_query(const BoxGrid& g, float4 a, BoxOf box
             const float4 b = box_of(j);
             if ((fminf(a.z, b.z) > fmaxf(a.x, b.x)) && (fminf(a.w, b.w) > fmaxf(a.y, b.y))) visit(j, b);
         }
+    }    for (int e = 0; kBig && e < g.n_big; ++e) {
+        const int j = g.items[g.cap - 1 - e];
+        const float4 b = box_of(j);
+        if ((fminf(a.z, b.z) > fmaxf(a.x, b.x)) && (fminf(a.w, b.w) > fmaxf(a.y, b.y))) visit(j, b);
     }
 }
 
@@ -131,7 +151,7 @@ __device__ __forceinline__ void grid_query(const BoxGrid& g, float4 a, BoxOf box
 //   a.x1 - b.x1 < (1 - t) w_b <= (1 - t) max_w.
 // The window is widened by a relative 1e-5; pairs outside it provably have IoU <= t, pairs inside are still judged
 // exactly by the caller, so results are identical to the dense evaluation.
-template <class BoxOf, class Visit>
+template <bool kBig = false, class BoxOf, class Visit>
 __device__ __forceinline__ void grid_query_iou_above(const BoxGrid& g, float4 a, float t, BoxOf box_of, Visit visit) {
     const float u = 1.0f - t;
     const float wa = a.z - a.x, ha = a.w - a.y;
@@ -145,6 +165,13 @@ __device__ __forceinline__ void grid_query_iou_above(const BoxGrid& g, float4 a,
             const float4 b = box_of(j);
             if ((fminf(a.z, b.z) > fmaxf(a.x, b.x)) && (fminf(a.w, b.w) > fmaxf(a.y, b.y))) visit(j, b);
         }
+    }    // big boxes: IoU > t also needs area_b < area_a / t (the intersection is at most area_a, the union at least area_b)
+    const float area_cap = wa * ha * (1.0f + 1e-4f);
+    for (int e = 0; kBig && e < g.n_big; ++e) {
+        const int j = g.items[g.cap - 1 - e];
+        const float4 b = box_of(j);
+        if ((b.z - b.x) * (b.w - b.y) * t > area_cap) continue;
+        if ((fminf(a.z, b.z) > fmaxf(a.x, b.x)) && (fminf(a.w, b.w) > fmaxf(a.y, b.y))) visit(j, b);
     }
 }
 

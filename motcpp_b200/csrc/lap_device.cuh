@@ -51,6 +51,10 @@ struct LapWorkspace {
 
 __device__ __forceinline__ double lap_inf() { return 1.0e300; }
 
+// cost functors that carry big_w / big_h (and say so with kBigList) have outlier column boxes listed apart from the grid
+template <class C, class = void> struct lap_has_big_list { static constexpr bool value = false; };
+template <class C> struct lap_has_big_list<C, decltype((void)C::kBigList)> { static constexpr bool value = true; };
+
 // Ascending sort of a short segment held in shared memory, by one warp.
 __device__ __forceinline__ void warp_sort_u16(unsigned short* seg, int n) {
     const int lane = lane_id();
@@ -473,7 +477,10 @@ __device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, 
             // box costs: index the columns so that only overlapping pairs are looked at
             if (cost.prune && (long long)n * m >= 65536 && m <= ws.grid.cap) {
                 if (ws.clk && ws.clk_base == 3) ws.clk->tick(16 + 3);
-                grid_build(ws.grid, m, ws.bs, [&](int j) { return cost.col_box(j); });
+                if constexpr (lap_has_big_list<Cost>::value)       // outlier column boxes kept out of the cells (grid_device.cuh)
+                    grid_build<true>(ws.grid, m, ws.bs, [&](int j) { return cost.col_box(j); }, cost.big_w, cost.big_h, cost.roi);
+                else
+                    grid_build(ws.grid, m, ws.bs, [&](int j) { return cost.col_box(j); });
                 if (ws.clk && ws.clk_base == 3) ws.clk->tick(16 + 0);
                 use_grid = true;
             }
@@ -505,10 +512,17 @@ __device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, 
                     __syncthreads();
                     if (mine) {
                         const typename Cost::Row rw = cost.row(i);
-                        grid_query(ws.grid, rw.b, [&](int j) { return cost.col_box(j); }, [&](int j, float4) {
+                        auto note = [&](int j, float4) {
                             const int q = atomicAdd(&ws.ctl[7], 1);
                             if (q < ws.p_cap) ws.pairs[q] = (i << 16) | j;
-                        });
+                        };
+                        if constexpr (lap_has_big_list<Cost>::value) {
+                            // such functors also know an IoU below which no pair is a candidate: a tighter corner window
+                            if (cost.iou_floor > 0.01f) grid_query_iou_above<true>(ws.grid, rw.b, cost.iou_floor, [&](int j) { return cost.col_box(j); }, note);
+                            else grid_query<true>(ws.grid, rw.b, [&](int j) { return cost.col_box(j); }, note);
+                        } else {
+                            grid_query(ws.grid, rw.b, [&](int j) { return cost.col_box(j); }, note);
+                        }
                     }
                     __syncthreads();
                     if (ws.clk && ws.clk_base == 3) ws.clk->tick(16 + 1);

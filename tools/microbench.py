@@ -289,6 +289,16 @@ def main():
         engine_bench("engine_sort_256x320", _lib.TRACKER_SORT, 296, 1536, 512, d, None, warm, T, iters, SORT,
                      state_bytes_per_track=224)
 
+    if want("engine_boosttrack"):
+        # BoostTrack with its default options on the SORT bench scene (256 objects + 32 clutter + 32 low boxes per frame); max_age 30 as the
+        # other engines (the reference default 60 only lengthens the tail of clutter tracks)
+        BOOST = dict(det_thresh=0.6, max_age=30, max_obs=50, min_hits=3, iou_threshold=0.3, min_box_area=10, aspect_ratio_thresh=1.6,
+                     lambda_iou=0.5, lambda_mhd=0.25, lambda_shape=0.25, use_dlo_boost=1, dlo_boost_coef=0.65, use_vt=0)
+        T, iters, warm = (10, 3, 40) if args.quick else (25, 5, 50)
+        d = np.stack([synth.bytetrack_stream(s, n_frames=warm + T * iters, n_clutter=32, n_low=32, config=1) for s in range(4)], 1)
+        engine_bench("engine_boosttrack_256obj_320dets", _lib.TRACKER_BOOSTTRACK, 296, 1536, 512, d, None, warm, T, iters, BOOST,
+                     state_bytes_per_track=96 + 28)
+
     # ---------------- drop-in latency: ONE stream, ONE frame per call through the host-buffer C ABI (the reference's
     #                  tracker.update(dets, img) usage pattern), pinned buffers, synchronous
     if want("latency"):

@@ -11,6 +11,17 @@ from motcpp_b200 import _lib, api, synth  # noqa: E402
 
 T = int(os.environ.get("SAN_FRAMES", "12"))
 d, c = synth.stress_stream(7, n_frames=T)
+if os.environ.get("SAN_ONLY") == "boosttrack":                       # the BoostTrack engine alone: small shape, use_vt, and the 1536 x 512 shape
+    for kw in (dict(max_age=6), dict(max_age=4, use_vt=True, det_thresh=0.4, min_hits=1)):
+        trk = api.BoostTrack(track_capacity=256, max_dets=64, **kw)
+        for t in range(T):
+            trk.update(d[t, :c[t]], (540, 960))
+    dd = synth.bytetrack_stream(0, n_frames=6)
+    eng = api.Engine(_lib.TRACKER_BOOSTTRACK, 2, 1536, 512, max_age=3)
+    eng.update(np.stack([dd, dd], 1), np.full((6, 2), 512, np.int32), ld_out=1536)
+    eng.check()
+    print("sanitize_smoke (boosttrack) done")
+    sys.exit(0)
 trk = api.OCSort(track_capacity=256, max_dets=64, use_byte=True)
 for t in range(T):
     trk.update(d[t, :c[t]], (540, 960))
@@ -55,6 +66,9 @@ trk = api.DeepOCSort(max_age=6, track_capacity=256, max_dets=64)
 for t in range(T):
     trk.update(d[t, :c[t]], (540, 960), e[t, :c[t]])
 trk = api.OCSort(iou_threshold=0.95, asso_func="centroid", track_capacity=256, max_dets=64)
+for t in range(T):
+    trk.update(d[t, :c[t]], (540, 960))
+trk = api.BoostTrack(max_age=6, track_capacity=256, max_dets=64)
 for t in range(T):
     trk.update(d[t, :c[t]], (540, 960))
 tie = (rng.integers(0, 4, (2, 90, 120)) / 4).astype(np.float32)
