@@ -239,12 +239,14 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
     if (n_det > min(d_max, a.ld_dets)) { n_det = min(d_max, a.ld_dets); if (tid == 0) atomicOr(&st.hdr[kHdrError], (int)kErrTooManyDets); }
 
     // ---- A. detections: IoU boxes, confidence split
+    int conf_above_one = 0;
     for (int j = tid; j < n_det; j += nt) {
         const float* r = dets + (size_t)j * 6;
         sm.det_box[j] = xywh2xyxy(xyxy2xywh(make_float4(r[0], r[1], r[2], r[3])));
         sm.det_conf[j] = r[4];
+        conf_above_one |= !(r[4] <= 1.0f);
     }
-    __syncthreads();
+    conf_above_one = __syncthreads_or(conf_above_one);      // fuse_score with a confidence > 1 voids the IoU floor below
     const float t_hi = a.p.track_thresh, t_lo = a.p.min_conf;
     int n_hi = 0, n_lo = 0;
     block_compact2(n_det, 0, 0, sm.bs, [&](int j) { return sm.det_conf[j] > t_hi; },
@@ -279,7 +281,9 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
     clk.tick(2);
     // ---- D. first association
     {
-        IouCost cost{sm.row_box, sm.det_box, sm.det_conf, sm.hi, true, a.p.match_thresh < 1.0f};
+        // 1 - iou * conf <= match_thresh needs iou >= 1 - match_thresh (conf <= 1); the floor sits a relative 1e-3 under it
+        const float floor1 = conf_above_one ? 0.0f : 1.0f - a.p.match_thresh * 1.001f - 1e-5f;
+        IouCost cost{sm.row_box, sm.det_box, sm.det_conf, sm.hi, true, a.p.match_thresh < 1.0f, floor1};
         sm.lap.clk = a.prof ? &clk : nullptr;
         sm.lap.clk_base = 3;
         block_lap(sm.lap, n1, n_hi, cap, lap_m_max, a.p.match_thresh, cost);
@@ -544,6 +548,12 @@ __global__ void __launch_bounds__(THREADS, (THREADS > 512) ? 1 : MOT_BT_MINBLOCK
         lap_carve_gscratch(st.gscratch, CAP, DMAX, sm.lap);
         for (int t = 0; t < a.T; ++t) {
             const size_t fs = (size_t)t * a.S + s;
+            if (t + 1 < a.T) {                       // the next frame's detections are fresh HBM lines: start them towards L2 now
+                const char* nx = reinterpret_cast<const char*>(a.dets + (fs + a.S) * (size_t)a.ld_dets * 6);
+                const int lines = (min(a.ld_dets, DMAX) * 24 + 127) >> 7;
+                if ((int)threadIdx.x < lines) prefetch_l2(nx + ((size_t)threadIdx.x << 7));
+                if ((int)threadIdx.x == lines) prefetch_l2(a.n_dets + fs + a.S);
+            }
             bt_frame<CAP, DMAX>(a, st, sm, a.dets + fs * (size_t)a.ld_dets * 6, a.n_dets[fs],
                                 a.out + fs * (size_t)a.ld_out * 8, a.n_out + fs);
         }

@@ -82,6 +82,10 @@ struct IouCost {
     const unsigned short* col_map;
     bool fuse;
     bool prune;
+    // an IoU no candidate can be below (cost <= thresh needs iou >= 1 - thresh; with fuse, as long as every confidence is
+    // <= 1): block_lap's grid walk then only looks at the corner window such a pair can sit in.  0: unknown.
+    static constexpr bool kIouFloor = true;
+    float iou_floor = 0.0f;
     struct Row { float4 b; float area; };
     __device__ __forceinline__ Row row(int i) const {
         Row r;

@@ -54,6 +54,8 @@ __device__ __forceinline__ double lap_inf() { return 1.0e300; }
 // cost functors that carry big_w / big_h (and say so with kBigList) have outlier column boxes listed apart from the grid
 template <class C, class = void> struct lap_has_big_list { static constexpr bool value = false; };
 template <class C> struct lap_has_big_list<C, decltype((void)C::kBigList)> { static constexpr bool value = true; };
+template <class C, class = void> struct lap_has_iou_floor { static constexpr bool value = false; };
+template <class C> struct lap_has_iou_floor<C, decltype((void)C::kIouFloor)> { static constexpr bool value = true; };
 
 // Ascending sort of a short segment held in shared memory, by one warp.
 __device__ __forceinline__ void warp_sort_u16(unsigned short* seg, int n) {
@@ -520,6 +522,9 @@ __device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, 
                             // such functors also know an IoU below which no pair is a candidate: a tighter corner window
                             if (cost.iou_floor > 0.01f) grid_query_iou_above<true>(ws.grid, rw.b, cost.iou_floor, [&](int j) { return cost.col_box(j); }, note);
                             else grid_query<true>(ws.grid, rw.b, [&](int j) { return cost.col_box(j); }, note);
+                        } else if constexpr (lap_has_iou_floor<Cost>::value) {
+                            if (cost.iou_floor > 0.01f) grid_query_iou_above(ws.grid, rw.b, cost.iou_floor, [&](int j) { return cost.col_box(j); }, note);
+                            else grid_query(ws.grid, rw.b, [&](int j) { return cost.col_box(j); }, note);
                         } else {
                             grid_query(ws.grid, rw.b, [&](int j) { return cost.col_box(j); }, note);
                         }
