@@ -123,56 +123,63 @@ __device__ __forceinline__ void grid_build(BoxGrid& g, int n, BlockScratch* bs, 
     g.n_big = kBig ? *big_count : 0;
 }
 
-// Visit every column j whose box has a non-empty interior intersection with row box `a`, once.
-// A column box b can only overlap a if  a.x1 - max_w < b.x1 < a.x2  (and likewise in y); the scan
+// The cells a query walks: columns cx0..cx1 of rows cy0..cy1; t > 0 marks an IoU-floor window (the big list is then
+// pruned by area as well).
+struct GridWindow { int cx0, cx1, cy0, cy1; float t; };
+
+// Every column box with a non-empty interior intersection with row box `a` has its corner in this window:
+// a column box b can only overlap a if  a.x1 - max_w < b.x1 < a.x2  (and likewise in y); the scan
 // range is widened by a relative 1e-6 so fp32 rounding in the widths can never drop a pair.
-template <bool kBig = false, class BoxOf, class Visit>
-__device__ __forceinline__ void grid_query(const BoxGrid& g, float4 a, BoxOf box_of, Visit visit) {
+__device__ __forceinline__ GridWindow grid_window(const BoxGrid& g, float4 a) {
     const float mx = g.max_w + (fabsf(a.x) + g.max_w) * 1e-6f, my = g.max_h + (fabsf(a.y) + g.max_h) * 1e-6f;
-    const int cx0 = g.cx(a.x - mx), cx1 = g.cx(a.z), cy0 = g.cy(a.y - my), cy1 = g.cy(a.w);
-    for (int yy = cy0; yy <= cy1; ++yy) {
-        const int e1 = g.cell[yy * kGridX + cx1 + 1];
-        for (int e = g.cell[yy * kGridX + cx0]; e < e1; ++e) {
-            const int j = g.items[e];
-            const float4 b = box_of(j);
-            if ((fminf(a.z, b.z) > fmaxf(a.x, b.x)) && (fminf(a.w, b.w) > fmaxf(a.y, b.y))) visit(j, b);
-        }
-    }    for (int e = 0; kBig && e < g.n_big; ++e) {
-        const int j = g.items[g.cap - 1 - e];
-        const float4 b = box_of(j);
-        if ((fminf(a.z, b.z) > fmaxf(a.x, b.x)) && (fminf(a.w, b.w) > fmaxf(a.y, b.y))) visit(j, b);
-    }
+    return GridWindow{g.cx(a.x - mx), g.cx(a.z), g.cy(a.y - my), g.cy(a.w), 0.0f};
 }
 
-// Like grid_query, for callers that only care about pairs with IoU > t (0 < t < 1): such a column box b has its corner
+// For callers that only care about pairs with IoU > t (0 < t < 1): such a column box b has its corner
 // within  a.x1 - (1 - t) max_w < b.x1 < a.x1 + (1 - t) w_a  (and likewise in y):
 //   IoU > t  =>  intersection > t * area_a and > t * area_b  =>  intersection width > t * w_a and > t * w_b;
 //   b.x1 >= a.x1: width <= a.x2 - b.x1, so b.x1 - a.x1 < (1 - t) w_a;   b.x1 < a.x1: width <= w_b - (a.x1 - b.x1), so
 //   a.x1 - b.x1 < (1 - t) w_b <= (1 - t) max_w.
 // The window is widened by a relative 1e-5; pairs outside it provably have IoU <= t, pairs inside are still judged
 // exactly by the caller, so results are identical to the dense evaluation.
-template <bool kBig = false, class BoxOf, class Visit>
-__device__ __forceinline__ void grid_query_iou_above(const BoxGrid& g, float4 a, float t, BoxOf box_of, Visit visit) {
+__device__ __forceinline__ GridWindow grid_window_iou_above(const BoxGrid& g, float4 a, float t) {
     const float u = 1.0f - t;
     const float wa = a.z - a.x, ha = a.w - a.y;
     const float lx = u * g.max_w + (fabsf(a.x) + g.max_w) * 1e-5f, ly = u * g.max_h + (fabsf(a.y) + g.max_h) * 1e-5f;
     const float rx = u * wa + (fabsf(a.x) + fabsf(wa)) * 1e-5f, ry = u * ha + (fabsf(a.y) + fabsf(ha)) * 1e-5f;
-    const int cx0 = g.cx(a.x - lx), cx1 = g.cx(a.x + rx), cy0 = g.cy(a.y - ly), cy1 = g.cy(a.y + ry);
-    for (int yy = cy0; yy <= cy1; ++yy) {
-        const int e1 = g.cell[yy * kGridX + cx1 + 1];
-        for (int e = g.cell[yy * kGridX + cx0]; e < e1; ++e) {
+    return GridWindow{g.cx(a.x - lx), g.cx(a.x + rx), g.cy(a.y - ly), g.cy(a.y + ry), t};
+}
+
+// Visit every column of the window (and of the big list) that overlaps `a`, once.
+template <bool kBig = false, class BoxOf, class Visit>
+__device__ __forceinline__ void grid_walk(const BoxGrid& g, const GridWindow& w, float4 a, BoxOf box_of, Visit visit) {
+    for (int yy = w.cy0; yy <= w.cy1; ++yy) {
+        const int e1 = g.cell[yy * kGridX + w.cx1 + 1];
+        for (int e = g.cell[yy * kGridX + w.cx0]; e < e1; ++e) {
             const int j = g.items[e];
             const float4 b = box_of(j);
             if ((fminf(a.z, b.z) > fmaxf(a.x, b.x)) && (fminf(a.w, b.w) > fmaxf(a.y, b.y))) visit(j, b);
         }
-    }    // big boxes: IoU > t also needs area_b < area_a / t (the intersection is at most area_a, the union at least area_b)
-    const float area_cap = wa * ha * (1.0f + 1e-4f);
-    for (int e = 0; kBig && e < g.n_big; ++e) {
-        const int j = g.items[g.cap - 1 - e];
-        const float4 b = box_of(j);
-        if ((b.z - b.x) * (b.w - b.y) * t > area_cap) continue;
-        if ((fminf(a.z, b.z) > fmaxf(a.x, b.x)) && (fminf(a.w, b.w) > fmaxf(a.y, b.y))) visit(j, b);
     }
+    if (kBig) {
+        // big boxes: IoU > t also needs area_b < area_a / t (the intersection is at most area_a, the union at least area_b)
+        const float area_cap = (a.z - a.x) * (a.w - a.y) * (1.0f + 1e-4f);
+        for (int e = 0; e < g.n_big; ++e) {
+            const int j = g.items[g.cap - 1 - e];
+            const float4 b = box_of(j);
+            if (w.t > 0.0f && (b.z - b.x) * (b.w - b.y) * w.t > area_cap) continue;
+            if ((fminf(a.z, b.z) > fmaxf(a.x, b.x)) && (fminf(a.w, b.w) > fmaxf(a.y, b.y))) visit(j, b);
+        }
+    }
+}
+
+template <bool kBig = false, class BoxOf, class Visit>
+__device__ __forceinline__ void grid_query(const BoxGrid& g, float4 a, BoxOf box_of, Visit visit) {
+    grid_walk<kBig>(g, grid_window(g, a), a, box_of, visit);
+}
+template <bool kBig = false, class BoxOf, class Visit>
+__device__ __forceinline__ void grid_query_iou_above(const BoxGrid& g, float4 a, float t, BoxOf box_of, Visit visit) {
+    grid_walk<kBig>(g, grid_window_iou_above(g, a, t), a, box_of, visit);
 }
 
 }  // namespace mot

@@ -512,22 +512,21 @@ __device__ void block_lap(LapWorkspace& ws, int n, int m, int n_max, int m_max, 
                     const bool mine = tid < step && i < n;
                     if (tid == 0) ws.ctl[7] = 0;
                     __syncthreads();
+                    constexpr bool kBigList = lap_has_big_list<Cost>::value;
+                    auto window_of = [&](const float4 b) {
+                        if constexpr (kBigList || lap_has_iou_floor<Cost>::value) {
+                            // such functors know an IoU below which no pair is a candidate: a tighter corner window
+                            if (cost.iou_floor > 0.01f) return grid_window_iou_above(ws.grid, b, cost.iou_floor);
+                        }
+                        return grid_window(ws.grid, b);
+                    };
                     if (mine) {
+                        // (handing rows with crowded windows to whole warps was measured: no gain on C2, the walk is issue-bound)
                         const typename Cost::Row rw = cost.row(i);
-                        auto note = [&](int j, float4) {
+                        grid_walk<kBigList>(ws.grid, window_of(rw.b), rw.b, [&](int j) { return cost.col_box(j); }, [&](int j, float4) {
                             const int q = atomicAdd(&ws.ctl[7], 1);
                             if (q < ws.p_cap) ws.pairs[q] = (i << 16) | j;
-                        };
-                        if constexpr (lap_has_big_list<Cost>::value) {
-                            // such functors also know an IoU below which no pair is a candidate: a tighter corner window
-                            if (cost.iou_floor > 0.01f) grid_query_iou_above<true>(ws.grid, rw.b, cost.iou_floor, [&](int j) { return cost.col_box(j); }, note);
-                            else grid_query<true>(ws.grid, rw.b, [&](int j) { return cost.col_box(j); }, note);
-                        } else if constexpr (lap_has_iou_floor<Cost>::value) {
-                            if (cost.iou_floor > 0.01f) grid_query_iou_above(ws.grid, rw.b, cost.iou_floor, [&](int j) { return cost.col_box(j); }, note);
-                            else grid_query(ws.grid, rw.b, [&](int j) { return cost.col_box(j); }, note);
-                        } else {
-                            grid_query(ws.grid, rw.b, [&](int j) { return cost.col_box(j); }, note);
-                        }
+                        });
                     }
                     __syncthreads();
                     if (ws.clk && ws.clk_base == 3) ws.clk->tick(16 + 1);
