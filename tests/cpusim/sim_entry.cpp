@@ -40,6 +40,37 @@ int sim_lap_jv(const float* cost, int n, int m, int ld, float thresh, int* row2c
     return 0;
 }
 
+// the corner grid with its overflow list (grid_device.cuh): visits[i * m + j] counts how often row i's query saw column j.
+// t = 0: every overlapping pair; t > 0: the IoU-floor window.  big_w / big_h / use_roi as the BoostTrack kernel passes them.
+int sim_grid_pairs(const float* rows, int n, const float* cols, int m, float big_w, float big_h, int use_roi, float t,
+                   int* visits, int* n_big, int threads) {
+    const int cap = m > 0 ? m : 1;
+    const size_t smem = mot::grid_smem_bytes(cap) + sizeof(mot::BlockScratch) + 64;
+    const float4* rb = reinterpret_cast<const float4*>(rows);
+    const float4* cb = reinterpret_cast<const float4*>(cols);
+    cpusim::launch(dim3(1), dim3(threads), smem, [=] {
+        MOT_DYNAMIC_SMEM(sm);
+        mot::BoxGrid g;
+        unsigned char* p = mot::grid_carve(sm, cap, g);
+        mot::BlockScratch* bs = reinterpret_cast<mot::BlockScratch*>(p + ((16 - ((size_t)p & 15)) & 15));
+        float4 roi = make_float4(-3.0e38f, -3.0e38f, 3.0e38f, 3.0e38f);
+        if (use_roi) {
+            roi = make_float4(3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f);
+            for (int i = 0; i < n; ++i) {
+                roi.x = fminf(roi.x, rb[i].x); roi.y = fminf(roi.y, rb[i].y); roi.z = fmaxf(roi.z, rb[i].z); roi.w = fmaxf(roi.w, rb[i].w);
+            }
+        }
+        mot::grid_build<true>(g, m, bs, [&](int j) { return cb[j]; }, big_w, big_h, roi);
+        if (threadIdx.x == 0) *n_big = g.n_big;
+        for (int i = (int)threadIdx.x; i < n; i += (int)blockDim.x) {
+            auto see = [&](int j, float4) { visits[(size_t)i * m + j] += 1; };
+            if (t > 0.0f) mot::grid_query_iou_above<true>(g, rb[i], t, [&](int j) { return cb[j]; }, see);
+            else mot::grid_query<true>(g, rb[i], [&](int j) { return cb[j]; }, see);
+        }
+    });
+    return 0;
+}
+
 }  // extern "C"
 
 // ------------------------------------------------------------------ ByteTrack engine under the emulator

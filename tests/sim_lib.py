@@ -38,6 +38,7 @@ def lib():
         S = C.CDLL(os.path.join(SIM_DIR, "libmotb200_cpusim%s.so" % ("_" + VARIANT if VARIANT else "")))
         S.sim_lap.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_float, i32p, i32p, C.c_int, C.c_int]
         S.sim_lap_jv.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_float, i32p, i32p, C.c_int, C.c_int]
+        S.sim_grid_pairs.argtypes = [f32p, C.c_int, f32p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, i32p, i32p, C.c_int]
         S.sim_bt_create.argtypes = [C.c_int] * 4 + [C.c_float] * 3 + [C.c_int] * 2
         S.sim_bt_create.restype = C.c_void_p
         S.sim_bt_update.argtypes = [C.c_void_p, f32p, i32p, C.c_int, C.c_int, f32p, i32p, C.c_int, C.c_int, C.c_int]
@@ -114,6 +115,16 @@ def sim_lap(cost, thresh, e_cap=4096, threads=128):
     q = np.full(max(m, 1), -7, np.int32)
     lib().sim_lap(cost, n, m, max(m, 1), float(thresh), r, q, e_cap, threads)
     return r[:n], q[:m]
+
+
+def sim_grid_pairs(rows, cols, big_w=3.0e38, big_h=3.0e38, use_roi=False, t=0.0, threads=64):
+    """visits[i, j] = how often row i's grid query saw column j; also the length of the grid's overflow list"""
+    rows, cols = np.ascontiguousarray(rows, np.float32), np.ascontiguousarray(cols, np.float32)
+    n, m = rows.shape[0], cols.shape[0]
+    visits = np.zeros((n, max(m, 1)), np.int32)
+    n_big = np.zeros(1, np.int32)
+    lib().sim_grid_pairs(rows, n, cols, m, float(big_w), float(big_h), int(use_roi), float(t), visits, n_big, threads)
+    return visits[:, :m], int(n_big[0])
 
 
 class SimByteTrack:

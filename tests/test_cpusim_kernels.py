@@ -184,3 +184,44 @@ def test_reference_order_lapjv_kernels_under_emulator(oracle):
         for block, threads in ((1, 128), (2, 128)):
             got = sim_lib.sim_lap_jv(c, th, block, threads)
             assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), ("large", trial, block)
+
+
+def _iou(a, b):
+    x1, y1 = np.maximum(a[:, None, 0], b[None, :, 0]), np.maximum(a[:, None, 1], b[None, :, 1])
+    x2, y2 = np.minimum(a[:, None, 2], b[None, :, 2]), np.minimum(a[:, None, 3], b[None, :, 3])
+    inter = np.clip(x2 - x1, 0, None) * np.clip(y2 - y1, 0, None)
+    ar = lambda q: (q[:, 2] - q[:, 0]) * (q[:, 3] - q[:, 1])
+    return inter / (ar(a)[:, None] + ar(b)[None] - inter)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_corner_grid_with_overflow_list_visits_exactly_the_pairs_that_matter(seed):
+    """grid_device.cuh: runaway column boxes (inflated, or far off the canvas) go to the overflow list / are dropped; the
+    overlap query still sees every overlapping pair exactly once, the IoU-floor query every pair above the floor at most once."""
+    rng = np.random.default_rng(seed)
+    def boxes(k, lo, hi):
+        c = rng.uniform(0, [1920, 1080], (k, 2)); w = rng.uniform(lo, hi, (k, 1)); wh = np.concatenate([w, 2.2 * w], 1)
+        return np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    rows = boxes(120, 40, 120)
+    cols = boxes(300, 40, 120)
+    cols[:90] = rows[:90] + rng.normal(0, 6, (90, 4)).astype(np.float32)          # near-duplicates of rows: high IoU pairs
+    cols[100:108, 3] += rng.uniform(2000, 9000, 8).astype(np.float32)             # inflated heights
+    cols[108:112] = np.array([-500, -400, 2500, 1600], np.float32)                # covers the whole canvas
+    cols[112:120] += np.float32(30000)                                            # coasted far off the canvas
+    cols[120] = [np.nan, 0, 10, 10]                                               # non-finite: never visited
+    cols[121] = [500, 500, 400, 400]                                              # inverted: empty interior
+    big_w, big_h = 2 * (rows[:, 2] - rows[:, 0]).max(), 2 * (rows[:, 3] - rows[:, 1]).max()
+    overlap = (np.minimum(rows[:, None, 2], cols[None, :, 2]) > np.maximum(rows[:, None, 0], cols[None, :, 0])) & \
+              (np.minimum(rows[:, None, 3], cols[None, :, 3]) > np.maximum(rows[:, None, 1], cols[None, :, 1]))
+    for use_roi in (False, True):
+        v, n_big = sim_lib.sim_grid_pairs(rows, cols, big_w, big_h, use_roi)
+        assert n_big == 12 and np.array_equal(v, overlap.astype(np.int32))
+    v, n_big = sim_lib.sim_grid_pairs(rows, cols)                                 # thresholds off: everything in the cells, same visits
+    assert n_big == 0 and np.array_equal(v, overlap.astype(np.int32))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        iou = np.nan_to_num(_iou(rows.astype(np.float64), cols.astype(np.float64)), nan=0.0)
+    for t in (0.2, 0.45, 0.79):
+        v, _ = sim_lib.sim_grid_pairs(rows, cols, big_w, big_h, True, t)
+        assert v.max() <= 1 and not (v.astype(bool) & ~overlap).any()
+        assert v[iou > t].all(), t                                                # nothing above the floor is missed
+        assert v.sum() < overlap.sum()                                            # and the window is tighter
