@@ -8,21 +8,19 @@
 // fp32-level accuracy from bf16 tensor cores: every fp32 value is split into three bf16 terms
 // x = h + m + l (8 + 8 + 8 mantissa bits) and the dot product keeps the six significant partial
 // products  h.h' + h.m' + m.h' + h.l' + l.h' + m.m'  (what is dropped is below 2^-24 relative).
-// The split kernel lays them out side by side along K:
-//     A' = [ h | h | m | h | l | m ]   (n x 6 Dp, bf16)        B' = [ h'| m'| h'| l'| h'| m' ]
-// so the whole thing is ONE bf16 GEMM  C = A' B'^T  with K' = 6 Dp, accumulated in fp32 in TMEM.
+// Side by side along K -  A' = [ h | h | m | h | l | m ],  B' = [ h'| m'| h'| l'| h'| m' ]  - that would be ONE bf16 GEMM with
+// K' = 6 Dp, accumulated in fp32 in TMEM.  But a CTA is bound by operand ingress from L2 (~64 B/cycle per SM), not by the
+// MMA, and the concatenated layout loads h three times and m twice.  So the split pre-pass writes [ h | m | l ] once per
+// operand, a pipeline stage holds the three A tiles and the three B tiles of one 64-deep k-block (72 KB at N = 64, 96 KB
+// at N = 128), and the MMA warp issues the six products from them: half the bytes per MAC (measured against the
+// concatenated layout with N = 256 tiles, which this replaced: 4096 x 4096 x 512 108 -> 93 us, the nearest-neighbour mode
+// at 102400 x 1024 x 512 1.54 -> 0.82 ms, C3 GEMM 19.3 -> 15.0 us).
 //
-// GEMM kernel (persistent CTAs over 128 x 128 (or 128 x 64) output tiles, two TMEM accumulator stages, 192 threads; with N = 64 the MMA was starved by shared-memory
-// operand reads - 6 KB per K16 step for 131 k MACs - N = 128 balances the two):
-//   warp 4  TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B) into a 6-stage smem ring
-//   warp 5  TMEM allocation + MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M128 N128 K16,
+// GEMM kernel (persistent CTAs over 128 x 128 or 128 x 64 output tiles, two TMEM accumulator stages, 192 threads):
+//   warp 4  TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B), six tiles per stage, 2- or 3-stage smem ring
+//   warp 5  TMEM allocation + MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M128 N128/64 K16, 24 per stage,
 //           tcgen05.commit onto the ring's "empty" barriers and onto the accumulator barrier
 //   warps 0-3 epilogue: tcgen05.ld (32 lanes x 32 columns) -> norm division, 1 - x, max(0, .) -> float4 stores
-// Operand sharing (tiles narrower than 256): a CTA is bound by operand ingress from L2, and the concatenated layout loads
-// h three times, m twice.  With kShared the split writes [h | m | l] once per operand, a pipeline stage holds the three
-// A tiles and the three B tiles of one 64-deep k-block (72 / 96 KB), and the MMA warp issues the six products from them:
-// half the bytes per MAC.  N = 256 keeps the concatenated layout (three A + three B tiles of a stage would not leave room
-// for a second stage).
 // SASS evidence to look for: UTCHMMA (tcgen05.mma), UTMALDG (TMA), LDTM (tcgen05.ld).
 #pragma once
 #include <atomic>
@@ -43,25 +41,22 @@ constexpr int kBlockK = 64;                   // bf16 elements = 128 bytes = one
 constexpr int kUmmaK = 16;
 constexpr int kThreads = 192;
 constexpr int kABytes = kBlockM * kBlockK * 2;     // 16 KB
-// BLOCK_N = 64, 128 or 256 (template parameter): one SM ingests its operands from L2 at ~64 B/cycle, so a CTA is bound by
-// (128 + N) x 128 B per 64-deep k-block rather than by the MMA (N x 2 cycles per k-block): the wider the tile, the
-// closer to the tensor peak (N = 128: 50 %, N = 256: 67 %); narrower tiles put more SMs to work on small problems.
-__host__ __device__ constexpr bool shared_operands(int block_n) { return block_n < 256; }
-__host__ __device__ constexpr int n_stages(int block_n) { return block_n >= 256 ? 4 : (block_n >= 128 ? 2 : 3); }   // 4 x 48, 2 x 96 or 3 x 72 KB
+// BLOCK_N = 64 or 128 (template parameter): the wider tile moves fewer operand bytes per MAC, the narrower one puts more
+// SMs to work on small problems.  A stage = three A tiles + three B tiles (h, m, l of each operand).
+__host__ __device__ constexpr int n_stages(int block_n) { return block_n >= 128 ? 2 : 3; }     // 2 x 96 or 3 x 72 KB
 __host__ __device__ constexpr int b_bytes(int block_n) { return block_n * kBlockK * 2; }
-__host__ __device__ constexpr int stage_bytes(int block_n) { return (shared_operands(block_n) ? 3 : 1) * (kABytes + b_bytes(block_n)); }
+__host__ __device__ constexpr int stage_bytes(int block_n) { return 3 * (kABytes + b_bytes(block_n)); }
 constexpr size_t smem_bytes(int block_n) {
     return 1024 /*align slack*/ + (size_t)n_stages(block_n) * stage_bytes(block_n) + 256 /*barriers*/ + sizeof(float) * 2 * block_n;
 }
 
 // ---------------------------------------------------------------- split + norm pre-pass
 // One launch for both operands, one warp per row, four consecutive floats per lane (float4 in, 8-byte bf16x4 out).
-// out row = `segs` segments of Dp bf16 (Dp = dim rounded up to 64, zero padded).
-// segs = 6: A' rows [h h m h l m], B' rows [h m h l h m];  segs = 3 (operand sharing): both [h m l]
+// out row = 3 segments of Dp bf16 (Dp = dim rounded up to 64, zero padded): [h m l]
 struct __align__(8) bf16x4 { __nv_bfloat16 a, b, c, d; };
 
 __global__ void __launch_bounds__(256) cosine_split_kernel(const float* __restrict__ xa, int rows_a,
-                                                           const float* __restrict__ xb, int rows_b, int dim, int dp, int segs,
+                                                           const float* __restrict__ xb, int rows_b, int dim, int dp,
                                                            __nv_bfloat16* __restrict__ out_a, __nv_bfloat16* __restrict__ out_b,
                                                            float* __restrict__ norm_a, float* __restrict__ norm_b) {
     const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -72,7 +67,7 @@ __global__ void __launch_bounds__(256) cosine_split_kernel(const float* __restri
         const bool is_b = r >= rows_a;
         const int rr = is_b ? r - rows_a : r;
         const float* src = (is_b ? xb : xa) + (size_t)rr * dim;
-        __nv_bfloat16* dst = (is_b ? out_b : out_a) + (size_t)rr * segs * dp;
+        __nv_bfloat16* dst = (is_b ? out_b : out_a) + (size_t)rr * 3 * dp;
         float acc = 0.0f;
         for (int k = lane * 4; k < dp; k += 128) {
             float v[4];
@@ -96,9 +91,7 @@ __global__ void __launch_bounds__(256) cosine_split_kernel(const float* __restri
             const bf16x4 H{h[0], h[1], h[2], h[3]}, M{m[0], m[1], m[2], m[3]}, L{l[0], l[1], l[2], l[3]};
             bf16x4* o = reinterpret_cast<bf16x4*>(dst + k);
             const int seg = dp / 4;                     // bf16x4 units per segment
-            if (segs == 3)  { o[0] = H; o[seg] = M; o[2 * seg] = L; }
-            else if (!is_b) { o[0] = H; o[seg] = H; o[2 * seg] = M; o[3 * seg] = H; o[4 * seg] = L; o[5 * seg] = M; }
-            else            { o[0] = H; o[seg] = M; o[2 * seg] = H; o[3 * seg] = L; o[4 * seg] = H; o[5 * seg] = M; }
+            o[0] = H; o[seg] = M; o[2 * seg] = L;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
@@ -200,8 +193,7 @@ cosine_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     float* s_dn = (float*)(smem + (size_t)kStages * kStageBytes + 256);      // [2][kBlockN] |d_j| of a tile's columns
 
     const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
-    constexpr bool kShared = shared_operands(kBlockN);
-    const int dp = kShared ? kp / 3 : kp;                        // operand sharing: kp = 3 Dp, a k-block covers all three segments
+    const int dp = kp / 3;                                       // kp = 3 Dp: a k-block covers the same 64 columns of all three segments
     const int k_blocks = dp / kBlockK;
 
     if (threadIdx.x == 4 * 32) {
@@ -231,15 +223,10 @@ cosine_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     mbar_wait(&empty[s], ph ^ 1u);
                     mbar_expect_tx(&full[s], kStageBytes);
                     unsigned char* a_dst = tiles + (size_t)s * kStageBytes;
-                    if constexpr (kShared) {                        // [A_h A_m A_l | B_h B_m B_l]
 #pragma unroll
-                        for (int g = 0; g < 3; ++g) {
-                            tma_load_2d(a_dst + g * kABytes, &map_a, g * dp + kb * kBlockK, m0, &full[s]);
-                            tma_load_2d(a_dst + 3 * kABytes + g * kBBytes, &map_b, g * dp + kb * kBlockK, n0, &full[s]);
-                        }
-                    } else {
-                        tma_load_2d(a_dst, &map_a, kb * kBlockK, m0, &full[s]);
-                        tma_load_2d(a_dst + kABytes, &map_b, kb * kBlockK, n0, &full[s]);
+                    for (int g = 0; g < 3; ++g) {                   // [A_h A_m A_l | B_h B_m B_l]
+                        tma_load_2d(a_dst + g * kABytes, &map_a, g * dp + kb * kBlockK, m0, &full[s]);
+                        tma_load_2d(a_dst + 3 * kABytes + g * kBBytes, &map_b, g * dp + kb * kBlockK, n0, &full[s]);
                     }
                 }
             }
@@ -259,22 +246,15 @@ cosine_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     mbar_wait(&full[s], ph);
                     tcgen05_fence_after();
                     const uint32_t a_addr = smem_u32(tiles + (size_t)s * kStageBytes);
-                    if constexpr (kShared) {
-                        // the six significant products of (h + m + l)(h' + m' + l'), smallest first: l h', h l', m m', m h', h m', h h'
-                        constexpr int kPa[6] = {2, 0, 1, 1, 0, 0}, kPb[6] = {0, 2, 1, 0, 1, 0};
+                    // the six significant products of (h + m + l)(h' + m' + l'), smallest first: l h', h l', m m', m h', h m', h h'
+                    constexpr int kPa[6] = {2, 0, 1, 1, 0, 0}, kPb[6] = {0, 2, 1, 0, 1, 0};
 #pragma unroll
-                        for (int q = 0; q < 6; ++q) {
-                            const uint64_t adesc = umma_smem_desc(a_addr + kPa[q] * kABytes);
-                            const uint64_t bdesc = umma_smem_desc(a_addr + 3 * kABytes + kPb[q] * kBBytes);
+                    for (int q = 0; q < 6; ++q) {
+                        const uint64_t adesc = umma_smem_desc(a_addr + kPa[q] * kABytes);
+                        const uint64_t bdesc = umma_smem_desc(a_addr + 3 * kABytes + kPb[q] * kBBytes);
 #pragma unroll
-                            for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                                umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | q | k) != 0);
-                        }
-                    } else {
-                        const uint64_t adesc = umma_smem_desc(a_addr), bdesc = umma_smem_desc(a_addr + kABytes);
-#pragma unroll
-                        for (int k = 0; k < kBlockK / kUmmaK; ++k)      // advance 16 elements = 32 bytes inside the swizzle atom
-                            umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                        for (int k = 0; k < kBlockK / kUmmaK; ++k)  // advance 16 elements = 32 bytes inside the swizzle atom
+                            umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | q | k) != 0);
                     }
                     umma_commit(&empty[s]);                         // smem slot reusable when these MMAs retire
                 }
@@ -406,11 +386,9 @@ inline int launch_cosine(const float* t, int n, const float* d, int m, int dim, 
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    // widest tile that still gives every SM at least two tiles
-    const long long tm = (n + 127) / 128;
-    const int block_n = (tm * ((m + 255) / 256) >= 2LL * n_sm) ? 256 : ((tm * ((m + 127) / 128) >= n_sm) ? 128 : 64);
-    const int segs = shared_operands(block_n) ? 3 : 6;
-    const int kp = segs * dp;
+    // the wide tile whenever it still fills the machine
+    const int block_n = (((n + 127) / 128) * (long long)((m + 127) / 128) >= n_sm) ? 128 : 64;
+    const int kp = 3 * dp;
     auto fail = [&](const char* what, cudaError_t e) {
         err = std::string("mot_cost_cosine: ") + what + ": " + cudaGetErrorString(e);
         return 2;   // MOT_ERR_CUDA
@@ -432,7 +410,7 @@ inline int launch_cosine(const float* t, int n, const float* d, int m, int dim, 
     __nv_bfloat16* b = (__nv_bfloat16*)(w.p + a_bytes);
     float* tn = (float*)(w.p + a_bytes + b_bytes);
     float* dn = tn + n;
-    cosine_split_kernel<<<(n + m + 7) / 8, 256, 0, st>>>(t, n, d, m, dim, dp, segs, a, b, tn, dn);
+    cosine_split_kernel<<<(n + m + 7) / 8, 256, 0, st>>>(t, n, d, m, dim, dp, a, b, tn, dn);
     if ((e = cudaGetLastError()) != cudaSuccess) return fail("split launch", e);
     CUtensorMap map_a, map_b;
     if (!make_map(&map_a, a, n, kp, kBlockM) || !make_map(&map_b, b, m, kp, block_n)) {
@@ -443,17 +421,12 @@ inline int launch_cosine(const float* t, int n, const float* d, int m, int dim, 
     std::atomic<bool>& attr_set = attr_done[dev & 63];
     if (!attr_set.load(std::memory_order_acquire)) {
         if ((e = cudaFuncSetAttribute(cosine_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(64))) != cudaSuccess ||
-            (e = cudaFuncSetAttribute(cosine_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(128))) != cudaSuccess ||
-            (e = cudaFuncSetAttribute(cosine_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(256))) != cudaSuccess)
+            (e = cudaFuncSetAttribute(cosine_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(128))) != cudaSuccess)
             return fail("smem attribute", e);
         attr_set.store(true, std::memory_order_release);
     }
     const int tiles_m = (n + kBlockM - 1) / kBlockM;
-    if (block_n == 256) {
-        const int total = tiles_m * ((m + 255) / 256);
-        cosine_gemm_kernel<256><<<std::min(total, n_sm), kThreads, smem_bytes(256), st>>>(map_a, map_b, n, m, kp, tn, dn, out, ld,
-                                                                                        tiles_m, total, row_seg);
-    } else if (block_n == 128) {
+    if (block_n == 128) {
         const int total = tiles_m * ((m + 127) / 128);
         cosine_gemm_kernel<128><<<std::min(total, n_sm), kThreads, smem_bytes(128), st>>>(map_a, map_b, n, m, kp, tn, dn, out, ld,
                                                                                         tiles_m, total, row_seg);
