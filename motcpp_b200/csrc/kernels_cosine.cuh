@@ -59,6 +59,9 @@ __global__ void __launch_bounds__(256) cosine_split_kernel(const float* __restri
                                                            const float* __restrict__ xb, int rows_b, int dim, int dp,
                                                            __nv_bfloat16* __restrict__ out_a, __nv_bfloat16* __restrict__ out_b,
                                                            float* __restrict__ norm_a, float* __restrict__ norm_b) {
+    // programmatic dependent launch: the GEMM's CTAs may come up (barrier init, TMEM allocation, tensor-map prefetch) while
+    // this grid is still running; they wait for its completion (griddepcontrol.wait) before touching its output
+    asm volatile("griddepcontrol.launch_dependents;");
     const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = (int)(threadIdx.x & 31);
     const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
@@ -211,6 +214,7 @@ cosine_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    asm volatile("griddepcontrol.wait;" ::: "memory");          // the split pre-pass (operands, norms) has completed and is visible
 
     if (warp == 4) {
         if (lane == 0) {                                            // ---- TMA producer
@@ -426,15 +430,28 @@ inline int launch_cosine(const float* t, int n, const float* d, int m, int dim, 
         attr_set.store(true, std::memory_order_release);
     }
     const int tiles_m = (n + kBlockM - 1) / kBlockM;
+    cudaLaunchAttribute pdl[1];
+    pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = st;
+    cfg.attrs = pdl;
+    cfg.numAttrs = 1;
+    const float* tn_c = tn;
+    const float* dn_c = dn;
     if (block_n == 128) {
         const int total = tiles_m * ((m + 127) / 128);
-        cosine_gemm_kernel<128><<<std::min(total, n_sm), kThreads, smem_bytes(128), st>>>(map_a, map_b, n, m, kp, tn, dn, out, ld,
-                                                                                        tiles_m, total, row_seg);
+        cfg.gridDim = dim3(std::min(total, n_sm));
+        cfg.dynamicSmemBytes = smem_bytes(128);
+        e = cudaLaunchKernelEx(&cfg, cosine_gemm_kernel<128>, map_a, map_b, n, m, kp, tn_c, dn_c, out, ld, tiles_m, total, row_seg);
     } else {
         const int total = tiles_m * ((m + 63) / 64);
-        cosine_gemm_kernel<64><<<std::min(total, n_sm), kThreads, smem_bytes(64), st>>>(map_a, map_b, n, m, kp, tn, dn, out, ld,
-                                                                                      tiles_m, total, row_seg);
+        cfg.gridDim = dim3(std::min(total, n_sm));
+        cfg.dynamicSmemBytes = smem_bytes(64);
+        e = cudaLaunchKernelEx(&cfg, cosine_gemm_kernel<64>, map_a, map_b, n, m, kp, tn_c, dn_c, out, ld, tiles_m, total, row_seg);
     }
+    if (e != cudaSuccess) return fail("gemm launch", e);
     if ((e = cudaGetLastError()) != cudaSuccess) return fail("gemm launch", e);
     return 0;
 }
