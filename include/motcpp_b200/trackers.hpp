@@ -351,12 +351,12 @@ public:
 
 private:
     static mot_engine_config make(const std::string&, bool, bool, float det_thresh, int max_age, int max_obs, int min_hits,
-                                  float iou_threshold, bool per_class, int, const std::string& asso_func, bool is_obb,
+                                  float iou_threshold, bool per_class, int, const std::string& /*asso_func: stored, never read (src/tracker.cpp:27)*/, bool is_obb,
                                   bool use_ecc, int min_box_area, float aspect_ratio_thresh, const std::string& cmc_method,
                                   float lambda_iou, float lambda_mhd, float lambda_shape, bool use_dlo_boost, bool,
                                   float dlo_boost_coef, bool, bool, bool use_sb, bool use_vt, bool with_reid,
                                   int track_capacity, int max_dets, int device) {
-        only_iou_aabb(asso_func, per_class, is_obb);
+        if (per_class || is_obb) throw std::invalid_argument("per_class / OBB are outside the accelerated hot path");
         if (use_ecc && cmc_method == "ecc")
             throw std::invalid_argument("camera-motion compensation is outside the accelerated hot path (use_ecc must be false)");
         if (with_reid) throw std::invalid_argument("BoostTrack with ReID is outside the accelerated hot path (with_reid must be false)");

@@ -105,6 +105,13 @@ def test_gpu_boosttrack_engine_matches_oracle(oracle, gpu):
     _engine_vs_oracle(oracle, streams, {"use_dlo_boost": False, "lambda_mhd": 0.9, "iou_threshold": 0.5, "max_age": 10}, 256, 64)
     d = synth.bytetrack_stream(6, n_frames=30)                               # the C2 scene: 512 detections per frame
     _engine_vs_oracle(oracle, [(d, np.full(d.shape[0], d.shape[1], np.int32))], {"max_age": 4}, 1536, 512, T_chunk=10)
+    # the microbenchmark's scene: clutter tracks coast for 30 frames, some with runaway height / ratio velocities - the
+    # track boxes the grid keeps in its overflow list or drops as outside the detections' hull (grid_device.cuh)
+    streams = []
+    for s in range(2):
+        d = synth.bytetrack_stream(s, n_frames=70, n_clutter=32, n_low=32, config=1)
+        streams.append((d, np.full(d.shape[0], d.shape[1], np.int32)))
+    _engine_vs_oracle(oracle, streams, {"max_age": 30}, 1536, 512, T_chunk=35)
 
 
 @pytest.mark.gpu
