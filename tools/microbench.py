@@ -338,6 +338,24 @@ def main():
              useful_tflops=useful / ms[0] / 1e9, executed_tflops=6 * useful / ms[0] / 1e9, peak_tflops=TENSOR,
              frac_executed=6 * useful / ms[0] / 1e9 / TENSOR, bound="tensor",
              note="time includes the fp32->3xbf16 split pre-pass and stream-ordered allocation")
+        if N <= 1024:
+            # the same call captured once into a CUDA graph and replayed (allocation, split, programmatic-dependent GEMM and
+            # free become graph nodes; the tensor maps are encoded at capture time): what remains when the host-side issue
+            # cost of the call (two cuTensorMapEncodeTiled, cudaMallocAsync / cudaFreeAsync, two launches) is off the timeline
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    api.check(lib.mot_cost_cosine(t.data_ptr(), N, d.data_ptr(), M, D, out.data_ptr(), M,
+                                                  torch.cuda.current_stream().cuda_stream))
+                ref = out.clone()
+                out.zero_()
+                ms = timeit(g.replay)
+                assert torch.equal(out, ref)
+                emit(f"cosine_{N}x{M}x{D}_graph_replay", ms, useful_flop=useful, executed_bf16_flop=6 * useful,
+                     executed_tflops=6 * useful / ms[0] / 1e9, peak_tflops=TENSOR, frac_executed=6 * useful / ms[0] / 1e9 / TENSOR,
+                     bound="tensor", note="mot_cost_cosine captured into a CUDA graph, replayed")
+            except Exception as exc:                                   # capture support differs between driver versions
+                print(json.dumps({"kernel": f"cosine_{N}x{M}x{D}_graph_replay", "error": str(exc)[:200]}), flush=True)
 
     # ---------------- StrongSORT cost builders
     for (NT, BUD, M, D) in ((256, 100, 512, 512), (1024, 100, 1024, 512)):
