@@ -72,7 +72,8 @@ __global__ void __launch_bounds__(256) cosine_split_kernel(const float* __restri
         const float* src = (is_b ? xb : xa) + (size_t)rr * dim;
         __nv_bfloat16* dst = (is_b ? out_b : out_a) + (size_t)rr * 3 * dp;
         float acc = 0.0f;
-        for (int k = lane * 4; k < dp; k += 128) {
+#pragma unroll 4
+        for (int k = lane * 4; k < dp; k += 128) {       // unrolled: the four 16-byte loads of a 512-d row are in flight together
             float v[4];
             if (vec && k + 3 < dim) {
                 const float4 q = *reinterpret_cast<const float4*>(src + k);
