@@ -449,36 +449,15 @@ __device__ __forceinline__ void bt_frame(const BtArgs& a, const BtStream& st, Bt
             }
         };
         if (fits && (long long)na * nl >= 8192) {
-            // lost boxes in the grid; per chunk of rows: collect overlapping pairs, then judge them densely
+            // lost boxes in the grid.  A duplicate needs 1 - IoU < 0.15: only boxes whose corner lies within 16 % of a box
+            // size can qualify, so a row meets 0-2 of them and they are judged on the spot (collecting the pairs first -
+            // count, scan, write, judge densely - walked the grid twice for pair lists this short).
             grid_build(sm.lap.grid, nl, sm.bs, [&](int j) { return sm.row_box[na + j]; });
-            for (int base = 0; base < na; base += nt) {
-                const int i = base + tid;
-                // a duplicate needs 1 - IoU < 0.15: only boxes whose corner lies within 16 % of a box size can qualify.
-                // count, scan, write: private slices of the pair buffer instead of a shared counter
-                int cnt = 0;
-                if (i < na)
-                    grid_query_iou_above(sm.lap.grid, sm.row_box[i], 0.84f, [&](int j) { return sm.row_box[na + j]; }, [&](int, float4) { ++cnt; });
-                int n_pairs = 0;
-                int q0 = block_exclusive_scan_value(cnt, sm.bs, &n_pairs);
-                if (i < na && n_pairs <= sm.lap.p_cap)
-                    grid_query_iou_above(sm.lap.grid, sm.row_box[i], 0.84f, [&](int j) { return sm.row_box[na + j]; },
-                                         [&](int j, float4) { sm.lap.pairs[q0++] = (i << 16) | j; });
-                __syncthreads();
-                if (n_pairs <= sm.lap.p_cap) {
-                    for (int q = tid; q < n_pairs; q += nt) {
-                        const int pk = sm.lap.pairs[q];
-                        const float4 ba = sm.row_box[pk >> 16];
-                        mark(pk >> 16, pk & 0xffff, ba, box_area(ba), sm.row_box[na + (pk & 0xffff)]);
-                    }
-                } else if (i < na) {
-                    const float4 ba = sm.row_box[i];
-                    const float area = box_area(ba);
-                    for (int j = 0; j < nl; ++j) {
-                        const float4 bb = sm.row_box[na + j];
-                        if (!boxes_disjoint(ba, bb)) mark(i, j, ba, area, bb);
-                    }
-                }
-                __syncthreads();
+            for (int i = tid; i < na; i += nt) {
+                const float4 ba = sm.row_box[i];
+                const float area = box_area(ba);
+                grid_query_iou_above(sm.lap.grid, ba, 0.84f, [&](int j) { return sm.row_box[na + j]; },
+                                     [&](int j, float4 bb) { mark(i, j, ba, area, bb); });
             }
         } else {
             for (int i = tid; i < na; i += nt) {
