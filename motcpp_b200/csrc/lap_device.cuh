@@ -295,6 +295,56 @@ __device__ void block_lap_solve(LapWorkspace& ws, int n, int m, int n_max, int m
         return;
     }
 
+    // ---- fast path: a handful of candidates whose components are all trivial (one row or one column) - what the second and
+    //      the unconfirmed association of a ByteTrack frame look like (1-9 edges on the C2 workload, where the general
+    //      machinery below cost ~20 k cycles per call in barriers, scans and queue hand-outs).  Warp 0 holds one edge per
+    //      lane, finds the components as lane masks (neighbours = same row or same column, closed by OR-ing the members'
+    //      masks until nothing changes) and, if every component is trivial, picks each component's best candidate by the
+    //      same order as the general path (cost, then row, then column).  Anything else falls through, untouched.
+    if (!overflow && n_edges <= 32) {
+        if (tid < 32) {
+            const bool have = lane < n_edges;
+            const int pk = have ? ws.scratch_a[lane] : 0;
+            const int ei = have ? (pk >> 16) : -1 - lane, ej = have ? (pk & 0xffff) : -1 - lane;   // idle lanes: unique keys
+            const unsigned rm = __match_any_sync(kFullMask, ei), cm = __match_any_sync(kFullMask, ej);
+            unsigned comp = rm | cm;
+            for (;;) {
+                unsigned acc = comp;
+                for (int l = 0; l < 32; ++l) {
+                    const unsigned other = __shfl_sync(kFullMask, comp, l);
+                    if ((comp >> l) & 1u) acc |= other;
+                }
+                const bool grew = acc != comp;
+                comp = acc;
+                if (!__any_sync(kFullMask, grew)) break;
+            }
+            const bool trivial = ((comp & ~rm) == 0u) || ((comp & ~cm) == 0u);
+            const bool all_trivial = __all_sync(kFullMask, !have || trivial);
+            if (all_trivial) {
+                float cf0 = 0.0f;
+                double cf = 0.0;
+                if (have) { cf0 = cost.pair(ei, ej); cf = (double)cf0 + cost.pair_bias(ei, ej); }
+                const bool valid = have && (cf0 <= thresh);
+                bool beaten = false;
+                for (int l = 0; l < 32; ++l) {
+                    const double ocf = __shfl_sync(kFullMask, cf, l);
+                    const int oi = __shfl_sync(kFullMask, ei, l), oj = __shfl_sync(kFullMask, ej, l);
+                    const bool ovalid = __shfl_sync(kFullMask, valid ? 1 : 0, l) != 0;
+                    if (l != lane && ((comp >> l) & 1u) && ovalid &&
+                        (ocf < cf || (ocf == cf && (oi < ei || (oi == ei && oj < ej))))) beaten = true;
+                }
+                if (valid && !beaten) { ws.row2col[ei] = (short)ej; ws.col2row[ej] = (short)ei; }
+            }
+            if (lane == 0) ws.ctl[2] = all_trivial ? 1 : 0;
+        }
+        __syncthreads();
+        if (ws.ctl[2] != 0) {
+            if (ws.clk) { ws.clk->tick(ws.clk_base + 1); ws.clk->tick(ws.clk_base + 2); ws.clk->tick(ws.clk_base + 3); }
+            return;
+        }
+        __syncthreads();                              // everyone has read the flag before the general path reuses ctl[2]
+    }
+
     // ---- 2. connected components by min-label propagation
     if (overflow) {
         // too many candidates for the edge buffer: treat everything as one component (still exact)
