@@ -39,7 +39,7 @@ ALGO_BYTES_PER_UPDATE = 167_936          # state in+out 147,456 
 # dram__bytes_read.sum + dram__bytes_write.sum of one bytetrack_step_kernel launch (ncu --set full, 296 streams x 20
 # frames, steady state) / 5920 frames: profiles/r2_bytetrack_step_ncu_full.txt.  Below the algorithmic figure because
 # the streams' state (0.27 MB each with the compact Kalman record) stays in the 126 MB L2 from one frame to the next.
-NCU_DRAM_BYTES_PER_UPDATE = 47_546          # (121.83 + 159.64) MB / 5920 frames (earlier captures of this round: 48.4, 46.9 and 37.7 KB - write-back timing)
+NCU_DRAM_BYTES_PER_UPDATE = 45_290          # (120.12 + 148.00) MB / 5920 frames (earlier captures of this round: 47.5, 48.4, 46.9 and 37.7 KB - write-back timing)
 BT_ARGS = dict(det_thresh=0.3, max_age=30, max_obs=50, min_hits=3, iou_threshold=0.3, min_conf=0.1,
                track_thresh=0.45, match_thresh=0.8, track_buffer=30, frame_rate=30)     # tools/motcpp_eval.cpp:133-148
 N_DETS = 512

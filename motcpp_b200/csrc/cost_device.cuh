@@ -85,6 +85,7 @@ struct IouCost {
     // an IoU no candidate can be below (cost <= thresh needs iou >= 1 - thresh; with fuse, as long as every confidence is
     // <= 1): block_lap's grid walk then only looks at the corner window such a pair can sit in.  0: unknown.
     static constexpr bool kIouFloor = true;
+    static constexpr bool kSmallFast = true;   // block_lap_solve's one-warp path for a handful of trivial components
     float iou_floor = 0.0f;
     struct Row { float4 b; float area; };
     __device__ __forceinline__ Row row(int i) const {

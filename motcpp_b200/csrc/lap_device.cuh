@@ -54,6 +54,8 @@ __device__ __forceinline__ double lap_inf() { return 1.0e300; }
 // cost functors that carry big_w / big_h (and say so with kBigList) have outlier column boxes listed apart from the grid
 template <class C, class = void> struct lap_has_big_list { static constexpr bool value = false; };
 template <class C> struct lap_has_big_list<C, decltype((void)C::kBigList)> { static constexpr bool value = true; };
+template <class C, class = void> struct lap_has_small_path { static constexpr bool value = false; };
+template <class C> struct lap_has_small_path<C, decltype((void)C::kSmallFast)> { static constexpr bool value = true; };
 template <class C, class = void> struct lap_has_iou_floor { static constexpr bool value = false; };
 template <class C> struct lap_has_iou_floor<C, decltype((void)C::kIouFloor)> { static constexpr bool value = true; };
 
@@ -301,7 +303,8 @@ __device__ void block_lap_solve(LapWorkspace& ws, int n, int m, int n_max, int m
     //      lane, finds the components as lane masks (neighbours = same row or same column, closed by OR-ing the members'
     //      masks until nothing changes) and, if every component is trivial, picks each component's best candidate by the
     //      same order as the general path (cost, then row, then column).  Anything else falls through, untouched.
-    if (!overflow && n_edges <= 32) {
+    // Opt-in per cost functor (kSmallFast): in the OC-SORT kernels, already at their register limit, the extra code cost 8 %.
+    if (lap_has_small_path<Cost>::value && !overflow && n_edges <= 32) {
         if (tid < 32) {
             const bool have = lane < n_edges;
             const int pk = have ? ws.scratch_a[lane] : 0;
