@@ -185,7 +185,8 @@ __device__ __forceinline__ void sort_frame(const SortArgs& a, const SortStream& 
     // ---- C. association on IoU distance
     {
         const float thresh = xsub(1.0f, a.p.iou_threshold);
-        IouCost cost{sm.row_box, sm.det_box, sm.det_conf, sm.valid, false, thresh < 1.0f};
+        // 1 - iou <= thresh needs iou >= iou_threshold: the grid walk (taken above 64 k pairs) only looks at that corner window
+        IouCost cost{sm.row_box, sm.det_box, sm.det_conf, sm.valid, false, thresh < 1.0f, 1.0f - thresh * 1.001f - 1e-5f};
         block_lap(sm.lap, n_trk, m, CAP, DMAX, thresh, cost);
     }
     const int n_match = block_compact(n_trk, 0, sm.bs, [&](int r) { return sm.lap.row2col[r] >= 0; },
